@@ -1,0 +1,226 @@
+/*
+ * bkx.h -- C ABI of the B200-native `biokanga align` hot path.
+ *
+ * The reference has no plugin/FFI layer: CAligner (biokanga/Aligner.cpp) calls the C++ class
+ * CSfxArrayV3 (libbiokanga/SfxArrayV2.h:298-990) one read at a time from <=128 pthreads.  A per-read
+ * synchronous call is unusable for a GPU, so the boundary sits one level up: the host aligner hands
+ * BATCHES of reads to this library and gets back one fixed 32-byte record per read that carries
+ * exactly the fields CAligner::ProcCoredApprox stores into tsReadHit (Aligner.cpp:9311-9479).
+ * Everything here is plain C: pointers, sizes, PODs; no C++/torch types.  All functions return
+ * >= 0 on success and a negative teBSFrsltCodes-style code on failure (libbiokanga/ErrorCodes.h:15-96);
+ * bkx_last_error() returns the text of the last failure on the calling thread.
+ *
+ * Each entry point names the reference interface it replaces (file:line under /root/reference).
+ */
+#ifndef BKX_H
+#define BKX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BKX_ABI_VERSION 1
+
+/* ---- result codes (sign convention of libbiokanga/ErrorCodes.h) ------------------------------ */
+enum {
+  BKX_OK = 0,
+  BKX_ERR_PARAM = -1,     /* eBSFerrParams   */
+  BKX_ERR_FILE = -2,      /* eBSFerrOpnFile / eBSFerrFileAccess */
+  BKX_ERR_FORMAT = -3,    /* eBSFerrNotBioseq / eBSFerrFileVer  */
+  BKX_ERR_MEM = -4,       /* eBSFerrMem      */
+  BKX_ERR_CUDA = -5,      /* any CUDA runtime failure (no CPU fallback exists) */
+  BKX_ERR_UNSUPPORTED = -6,
+  BKX_ERR_ENTRY = -7      /* eBSFerrEntry    */
+};
+
+/* ---- base codes: libbiokanga/commdefs.h:108-123 (etSeqBase) ---------------------------------- */
+enum { BKX_BASE_A = 0, BKX_BASE_C = 1, BKX_BASE_G = 2, BKX_BASE_T = 3, BKX_BASE_N = 4,
+       BKX_BASE_UNDEF = 5, BKX_BASE_INDEL = 6, BKX_BASE_EOS = 7 };
+
+/* ---- tHRslt: libbiokanga/SfxArrayV2.h:68-74 -------------------------------------------------- */
+enum { BKX_HR_NONE = 0, BKX_HR_HITS = 1, BKX_HR_MMDELTA = 2, BKX_HR_HITINSTS = 3, BKX_HR_RMMDELTA = 4 };
+
+/* ---- teNAR: biokanga/Aligner.h:106-128 -------------------------------------------------------- */
+enum {
+  BKX_NAR_UNALIGNED = 0, BKX_NAR_ACCEPTED, BKX_NAR_NS, BKX_NAR_NOHIT, BKX_NAR_MMDELTA, BKX_NAR_MULTIALIGN,
+  BKX_NAR_TRIM, BKX_NAR_SPLICEJCTN, BKX_NAR_MICROINDEL, BKX_NAR_PCRDUP, BKX_NAR_NONUNIQUE, BKX_NAR_CHROMFILT,
+  BKX_NAR_REGIONFILT, BKX_NAR_PEINSERTMIN, BKX_NAR_PEINSERTMAX, BKX_NAR_PENOHIT, BKX_NAR_PESTRAND,
+  BKX_NAR_PECHROM, BKX_NAR_PEUNALIGN, BKX_NAR_LOCICONSTRAINED, BKX_NAR_COUNT
+};
+
+/* ---- eALStrand: libbiokanga/SfxArrayV2.h:61-66 ------------------------------------------------ */
+enum { BKX_STRAND_BOTH = 0, BKX_STRAND_WATSON = 1, BKX_STRAND_CRICK = 2 };
+
+/* ---- etPMode: biokanga/Aligner.h:214-220 ------------------------------------------------------ */
+enum { BKX_PMODE_DEFAULT = 0, BKX_PMODE_MORESENS = 1, BKX_PMODE_ULTRASENS = 2, BKX_PMODE_LESSSENS = 3 };
+
+/* ---- etPEproc: biokanga/Aligner.h:252-259 ----------------------------------------------------- */
+enum { BKX_PE_NONE = 0, BKX_PE_ORPHAN = 1, BKX_PE_UNIQUE = 2, BKX_PE_ORPHAN_SE = 3, BKX_PE_UNIQUE_SE = 4 };
+
+/* One chromosome / contig of the index: tsSfxEntry, libbiokanga/SfxArrayV2.h:79-88. */
+typedef struct bkx_entry {
+  uint32_t entry_id;     /* 1..n */
+  uint32_t seq_len;      /* excludes the EOS terminator */
+  uint64_t start_ofs;    /* offset of first base in the concatenated sequence */
+  uint64_t end_ofs;      /* offset of last base (inclusive) */
+  char name[88];         /* szSeqName[81], NUL terminated; sizeof(bkx_entry) == 112 */
+} bkx_entry;
+
+/* tsSfxHeaderV3 + tsSfxBlock summary: libbiokanga/SfxArrayV2.h:98-104,174-187. */
+typedef struct bkx_index_info {
+  uint64_t concat_len;     /* tsSfxBlock::ConcatSeqLen (bases + one EOS per entry) */
+  uint64_t tot_seq_len;    /* CSfxArrayV3::GetTotSeqsLen(), SfxArrayV2.cpp:2070 */
+  uint32_t num_entries;
+  uint32_t sfx_el_size;    /* 4 or 5 */
+  uint32_t version;        /* 3..5 */
+  uint32_t attributes;     /* bit0 bisulfite, bit1 colorspace (both rejected) */
+  uint32_t prefix_k;       /* k of the device k-mer prefix table */
+  uint32_t device;         /* CUDA ordinal the index lives on */
+  uint64_t device_bytes;   /* HBM bytes held by this index */
+  char dataset_name[84];
+} bkx_index_info;
+
+/* Everything CAligner feeds into CSfxArrayV3::AlignReads per run (tsThreadMatchPars, Aligner.h, and
+ * the per-read derivations at Aligner.cpp:9041-9095).  bkx_default_params() fills it the way
+ * kanga.cpp:322-1082 + CAligner::LocateCoredApprox (Aligner.cpp:8727-8761) do. */
+typedef struct bkx_align_params {
+  int32_t pmode;            /* -m  BKX_PMODE_*                                   */
+  int32_t max_subs;         /* -s  substitutions per 100 bp (default 10, max 15) */
+  int32_t min_edit_dist;    /* -e  MMDelta 1..2                                  */
+  int32_t max_ns;           /* -n  max N per read / per 100 bp (default 1)       */
+  int32_t align_strand;     /* -Q  BKX_STRAND_*                                  */
+  int32_t max_ml_matches;   /* MaxHits handed to AlignReads (1 unless -r/-R)     */
+  int32_t min_core_len;     /* m_MinCoreLen after the genome-size + mode rule    */
+  int32_t max_num_slides;   /* per 100 bp: 8 default, 9 ultra, 6 less sensitive  */
+  int32_t max_iter;         /* CSfxArrayV3::m_MaxIter: 5000/10000/20000/2500     */
+  int32_t max_ident_nodes;  /* cMaxNumIdentNodes = 1 024 000 (SfxArrayV2.h:15)   */
+  int32_t reserved[6];
+} bkx_align_params;
+
+/* Fixed 32-byte per-read record: the tsReadHit fields written by ProcCoredApprox
+ * (Aligner.cpp:9311-9479) plus two work counters that define the algorithmic-bytes numerator
+ * (SURVEY.md section 8(d)): seeds = LocateFirstExact calls the reference issues for this read,
+ * cands = candidate loci that reach its Hamming loop. */
+typedef struct bkx_read_result {
+  uint8_t nar;                /* BKX_NAR_*                                   */
+  uint8_t hit_rslt;           /* BKX_HR_* returned by AlignReads              */
+  uint8_t strand;             /* '+', '-', '?' or 0                           */
+  uint8_t num_hits;           /* tsReadHit::NumHits                           */
+  int8_t low_mm;              /* tsReadHit::LowMMCnt                          */
+  int8_t nxt_low_mm;          /* tsReadHit::NxtLowMMCnt                       */
+  int16_t low_hit_instances;  /* tsReadHit::LowHitInstances (clamped MaxML+1) */
+  uint32_t chrom_id;          /* Seg[0].ChromID = EntryID, 0 if no hit        */
+  uint32_t match_loci;        /* Seg[0].MatchLoci (0-based in chromosome)     */
+  uint16_t match_len;         /* Seg[0].MatchLen                              */
+  uint8_t mismatches;         /* Seg[0].Mismatches                            */
+  uint8_t flags;              /* BKX_FLG_*                                    */
+  uint32_t seeds;
+  uint32_t cands;
+  uint32_t reserved;
+} bkx_read_result;
+
+enum { BKX_FLG_PE_ALIGNED = 1, BKX_FLG_PE_RECOVERED = 2 };
+
+/* Paired-end parameters: CAligner::ProcessPairedEnds arguments, Aligner.cpp:2876-2881. */
+typedef struct bkx_pe_params {
+  int32_t pe_proc;          /* -U BKX_PE_*                         */
+  int32_t pair_min_len;     /* -d (default 100)                    */
+  int32_t pair_max_len;     /* -D (default 1000)                   */
+  int32_t pair_strand;      /* -E: 1 = both ends on same strand    */
+  int32_t circularised;     /* -c PE circularised fragments        */
+  int32_t reserved[3];
+} bkx_pe_params;
+
+/* The eight PE counters of tsPEThreadPars (Aligner.cpp:3479-3486).  partner_unpaired is the plain
+ * per-pair count; the reference's log line adds it twice (Aligner.cpp:2990,2997) -- the host
+ * reporter reproduces that, the library does not. */
+typedef struct bkx_pe_stats {
+  uint64_t unaligned_pairs, accepted_num_paired, accepted_num_se, partner_paired, partner_unpaired,
+      num_filtered_by_chrom, under_len_pairs, over_len_pairs;
+} bkx_pe_stats;
+
+/* Per-batch counters merged by the reference under m_hMtxIterReads (Aligner.cpp:9507-9525). */
+typedef struct bkx_align_stats {
+  uint64_t nar[BKX_NAR_COUNT];
+  uint64_t plus_hits, minus_hits;
+  uint64_t num_sloughed_ns, tot_non_aligned, tot_accepted_unique, tot_accepted_multi, tot_accepted_aligned,
+      tot_loci_aligned, tot_not_accepted_delta;
+  uint64_t seeds, cands;        /* sum of the per-read work counters */
+  uint64_t reads;
+} bkx_align_stats;
+
+typedef struct bkx_index bkx_index; /* opaque: device-resident index + streams + staging */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int bkx_abi_version(void);
+const char* bkx_last_error(void);
+int bkx_device_count(void);
+
+/* ---- index: replaces CSfxArrayV3::Open + SetTargBlock (SfxArrayV2.cpp:891-1100, 1836-1925) ----
+ * Reads a .sfx written by the reference's `biokanga index` (header tsSfxHeaderV3 / tsSfxHeaderVv,
+ * entries tsSfxEntry, one tsSfxBlock), uploads it to `device`, 2-bit packs the genome, builds the
+ * exception masks and the k-mer prefix table there.  prefix_k = 0 chooses k from the genome size. */
+int bkx_open_index(const char* sfx_path, int device, int prefix_k, bkx_index** out);
+/* Same, from host memory laid out like tsSfxBlock::SeqSuffix (1 byte/base then SA elements). */
+int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t sfx_el_size,
+                       const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
+                       int prefix_k, bkx_index** out);
+/* Same, from buffers already resident on `device` (bench / GPU-built suffix arrays). */
+int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, const void* d_sa, uint32_t sfx_el_size,
+                       const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
+                       int prefix_k, bkx_index** out);
+/* Replicate an open index onto another GPU by peer copies (multi-GPU read sharding). */
+int bkx_clone_index(const bkx_index* src, int device, bkx_index** out);
+void bkx_close_index(bkx_index* idx); /* CSfxArrayV3::Reset / Close */
+
+int bkx_index_info_get(const bkx_index* idx, bkx_index_info* out); /* GetSfxHeader/GetTotSeqsLen/GetNumEntries */
+int bkx_get_entry(const bkx_index* idx, uint32_t entry_id, bkx_entry* out); /* GetIdentName/GetSeqLen (SfxArrayV2.h) */
+int bkx_get_ident(const bkx_index* idx, const char* name);                  /* GetIdent(name) -> entry id or <0 */
+/* GetSeq(EntryID, Loci, buf, Len): 1 byte/base codes, returns number of bases copied. */
+int64_t bkx_get_seq(const bkx_index* idx, uint32_t entry_id, uint64_t loci, uint64_t len, uint8_t* buf);
+
+/* ---- parameters ------------------------------------------------------------------------------- */
+/* Defaults of kanga.cpp:322-1082 and the genome-size rule of Aligner.cpp:8727-8761 for this index. */
+int bkx_default_params(const bkx_index* idx, int pmode, bkx_align_params* out);
+
+/* ---- the hot path: replaces the ProcCoredApprox -> CSfxArrayV3::AlignReads loop ---------------
+ * (Aligner.cpp:9024-9505 -> SfxArrayV2.cpp:7666-7760, 5693-6262, 7765-8027)
+ * bases: concatenated reads, 1 byte/base, low 3 bits = etSeqBase code (as CAligner::AddEntry packs
+ * them, Aligner.cpp:10572-10677; bits 3..7 are ignored).  offsets[n_reads+1]: start of each read.
+ * Host variant: plain (pageable or pinned) host pointers; H2D, kernels and D2H run on the index's
+ * own streams, double buffered; returns when `out[0..n_reads)` is complete. */
+int bkx_align_reads(bkx_index* idx, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
+                    uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats /* may be NULL; accumulated */);
+/* Device variant: all pointers are device pointers on idx's GPU; asynchronous on `cuda_stream`
+ * (a cudaStream_t, NULL = the index's compute stream).  d_stats (device, may be NULL) is accumulated. */
+int bkx_align_reads_device(bkx_index* idx, const bkx_align_params* p, const uint8_t* d_bases,
+                           const uint64_t* d_offsets, uint32_t n_reads, uint32_t max_read_len,
+                           bkx_read_result* d_out, bkx_align_stats* d_stats, void* cuda_stream);
+/* Per-read shim with the exact CSfxArrayV3::AlignReads contract (SfxArrayV2.h:585-606) for unit
+ * parity tests: one read in, tHRslt out, In/Out (LowHitInstances, LowMMCnt, NxtLowMMCnt). */
+int bkx_align_one(bkx_index* idx, const bkx_align_params* p, const uint8_t* probe, int probe_len,
+                  int* low_hit_instances, int* low_mm, int* nxt_low_mm, bkx_read_result* hit);
+
+/* ---- paired ends: replaces CAligner::ProcessPairedEnds (Aligner.cpp:2726-2850, 3055-3489) -------
+ * results[2*i], results[2*i+1] are PE1 / PE2 of pair i (as after SortReadHits(eRSMPairReadID),
+ * Aligner.cpp:2899).  Updated in place; len_dist (may be NULL) is the insert-size histogram
+ * m_pLenDist[0..100000] (Aligner.cpp:2908-2915), accumulated.  bases/offsets are needed only for
+ * orphan recovery (pe_proc ORPHAN / ORPHAN_SE) and may be NULL otherwise. */
+int bkx_pair_reads(bkx_index* idx, const bkx_align_params* p, const bkx_pe_params* pe, bkx_read_result* results,
+                   uint32_t n_pairs, const uint8_t* bases, const uint64_t* offsets, bkx_pe_stats* stats,
+                   uint32_t* len_dist);
+
+/* ---- instrumentation -------------------------------------------------------------------------- */
+/* Device time (ms) of the kernels of the last bkx_align_reads* call on this index, measured with
+ * CUDA events on the launching stream; <0 if none. */
+float bkx_last_kernel_ms(const bkx_index* idx);
+/* Number of kernel launches issued by this library on this index since it was opened. */
+uint64_t bkx_kernel_launches(const bkx_index* idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BKX_H */
