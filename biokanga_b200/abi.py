@@ -1,7 +1,7 @@
 """ctypes / numpy mirrors of the PODs declared in include/bkx.h (the C ABI of the hot path).
 
 Plain data layouts only -- no compute.  Shared by the product binding (biokanga_b200.lib) and by the
-test-only oracle binding (oracle/pyoracle.py) so both sides speak the same records.
+test-only checker binding under oracle/ so both sides speak the same records.
 """
 from __future__ import annotations
 

@@ -1,0 +1,705 @@
+// Host side of libbkx.so: the extern "C" entry points declared in include/bkx.h.
+// Owns device memory, streams and staging; launches the kernels of bkx_kernels.cu.
+// There is deliberately no CPU fallback: every compute entry point fails with BKX_ERR_CUDA when
+// no CUDA device is usable.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "bkx_align.cuh"
+#include "bkx_kernels.h"
+
+using namespace bkx;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) return fail(BKX_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                        __FILE__, __LINE__);                                          \
+  } while (0)
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  uint8_t* d_bases = nullptr;
+  size_t bases_cap = 0;
+  uint64_t* d_offs = nullptr;
+  bkx_read_result* d_out = nullptr;
+  size_t reads_cap = 0;
+  cudaEvent_t k0 = nullptr, k1 = nullptr;
+  bool timed = false;
+};
+
+struct bkx_index {
+  int device = 0;
+  DevIndex d{};
+  std::vector<void*> owned;
+  std::vector<bkx_entry> entries;
+  bkx_index_info info{};
+  // runtime workspace
+  std::mutex mtx;
+  Slot slot[2];
+  unsigned int* d_cursor[2] = {nullptr, nullptr};
+  uint64_t* hash_pool = nullptr;
+  uint32_t hash_slots = 0;
+  uint32_t* epochs = nullptr;
+  int grid = 0;
+  int grid_W = 0;
+  bkx_align_stats* d_stats = nullptr;
+  bkx_pe_stats* d_pe_stats = nullptr;
+  uint32_t* d_len_dist = nullptr;
+  float last_ms = -1.f;
+  uint64_t launches = 0;
+};
+
+extern "C" int bkx_abi_version(void) { return BKX_ABI_VERSION; }
+extern "C" const char* bkx_last_error(void) { return g_err.c_str(); }
+extern "C" int bkx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+template <typename T>
+static int dev_alloc(bkx_index* x, T** p, size_t count, bool zero) {
+  void* q = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  CU(cudaMalloc(&q, bytes));
+  if (zero) CU(cudaMemset(q, 0, bytes));
+  x->owned.push_back(q);
+  x->info.device_bytes += bytes;
+  *p = (T*)q;
+  return BKX_OK;
+}
+
+static int choose_k(uint64_t n, int requested, size_t free_bytes, bool wide) {
+  if (requested > 0) return std::min(std::max(requested, 4), 16);
+  int k = 8;
+  while (k < 16 && (1ull << (2 * k)) < n) ++k;  // ceil(log4 n), clamped to [8,16]
+  size_t el = wide ? 8 : 4;
+  while (k > 8 && ((1ull << (2 * k)) + 1) * el > free_bytes / 3) --k;
+  return k;
+}
+
+// Build every derived structure from a device-resident 1-byte/base sequence and raw SA elements.
+static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const void* d_sa_raw, uint32_t el,
+                        bool sa_owned_u32, const bkx_entry* entries, uint32_t n_ent, const char* name, int prefix_k) {
+  if (el != 4 && el != 5) return fail(BKX_ERR_FORMAT, "unsupported suffix element size %u", el);
+  if (n < 2 || n_ent == 0) return fail(BKX_ERR_FORMAT, "empty index");
+  x->info.concat_len = n;
+  x->info.sfx_el_size = el;
+  x->info.num_entries = n_ent;
+  x->info.device = (uint32_t)x->device;
+  if (name) snprintf(x->info.dataset_name, sizeof(x->info.dataset_name), "%s", name);
+  x->entries.assign(entries, entries + n_ent);
+  std::sort(x->entries.begin(), x->entries.end(),
+            [](const bkx_entry& a, const bkx_entry& b) { return a.start_ofs < b.start_ofs; });
+  uint64_t tot = 0;
+  for (auto& e : x->entries) tot += e.seq_len;
+  x->info.tot_seq_len = tot;
+
+  cudaStream_t st = x->slot[0].st;
+  uint64_t* g2; uint64_t* gx; uint32_t* gxc;
+  size_t g2w = ((n + 63) >> 6) * 2 + 4, gxw = ((n + 63) >> 6) + 2, gcw = (((n + 63) >> 6) + 31) / 32 + 2;
+  int rc;
+  if ((rc = dev_alloc(x, &g2, g2w, true)) < 0) return rc;
+  if ((rc = dev_alloc(x, &gx, gxw, true)) < 0) return rc;
+  if ((rc = dev_alloc(x, &gxc, gcw, true)) < 0) return rc;
+  unsigned long long* d_bad;
+  CU(cudaMalloc((void**)&d_bad, 8));
+  CU(cudaMemsetAsync(d_bad, 0, 8, st));
+  CU(launch_pack_genome(d_seq, n, g2, gx, gxc, d_bad, st));
+  unsigned long long bad = 0;
+  CU(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  cudaFree(d_bad);
+  x->launches += 1;
+  if (bad) return fail(BKX_ERR_UNSUPPORTED, "%llu symbols other than A,C,G,T,N,EOS in the index sequence", bad);
+  x->d.g2 = g2; x->d.gx = gx; x->d.gxc = gxc; x->d.n = n;
+
+  if (el == 4) {
+    if (sa_owned_u32) {
+      x->d.sa_lo = (const uint32_t*)d_sa_raw;
+    } else {
+      uint32_t* lo;
+      if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
+      CU(cudaMemcpyAsync(lo, d_sa_raw, n * 4, cudaMemcpyDeviceToDevice, st));
+      x->d.sa_lo = lo;
+    }
+    x->d.sa_hi = nullptr;
+  } else {
+    uint32_t* lo; uint8_t* hi;
+    if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
+    if ((rc = dev_alloc(x, &hi, n, false)) < 0) return rc;
+    CU(launch_split_sa5((const uint8_t*)d_sa_raw, n, lo, hi, st));
+    x->launches += 1;
+    x->d.sa_lo = lo; x->d.sa_hi = hi;
+  }
+  // chromosome table
+  std::vector<uint64_t> es(n_ent), ee(n_ent);
+  std::vector<uint32_t> ei(n_ent);
+  for (uint32_t i = 0; i < n_ent; ++i) { es[i] = x->entries[i].start_ofs; ee[i] = x->entries[i].end_ofs; ei[i] = x->entries[i].entry_id; }
+  uint64_t *d_es, *d_ee; uint32_t* d_ei;
+  if ((rc = dev_alloc(x, &d_es, n_ent, false)) < 0) return rc;
+  if ((rc = dev_alloc(x, &d_ee, n_ent, false)) < 0) return rc;
+  if ((rc = dev_alloc(x, &d_ei, n_ent, false)) < 0) return rc;
+  CU(cudaMemcpy(d_es, es.data(), n_ent * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_ee, ee.data(), n_ent * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_ei, ei.data(), n_ent * 4, cudaMemcpyHostToDevice));
+  x->d.ent_start = d_es; x->d.ent_end = d_ee; x->d.ent_id = d_ei; x->d.n_ent = n_ent;
+  // prefix table
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  bool wide = n >= (1ull << 32);
+  int k = choose_k(n, prefix_k, free_b, wide);
+  uint64_t pt_entries = (1ull << (2 * k)) + 1;
+  void* pt = nullptr;
+  if (wide) { uint64_t* t; if ((rc = dev_alloc(x, &t, pt_entries, false)) < 0) return rc; pt = t; x->d.pt64 = t; x->d.pt32 = nullptr; }
+  else { uint32_t* t; if ((rc = dev_alloc(x, &t, pt_entries, false)) < 0) return rc; pt = t; x->d.pt32 = t; x->d.pt64 = nullptr; }
+  x->d.k = k;
+  x->info.prefix_k = (uint32_t)k;
+  CU(build_prefix_table(x->d, k, pt, wide, st));
+  x->launches += 2;
+  CU(cudaStreamSynchronize(st));
+  return BKX_OK;
+}
+
+static int new_index(int device, bkx_index** out) {
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd <= 0)
+    return fail(BKX_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= nd) return fail(BKX_ERR_PARAM, "device %d out of range (%d devices)", device, nd);
+  CU(cudaSetDevice(device));
+  bkx_index* x = new bkx_index();
+  x->device = device;
+  for (int s = 0; s < 2; ++s) {
+    CU(cudaStreamCreateWithFlags(&x->slot[s].st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&x->slot[s].k0));
+    CU(cudaEventCreate(&x->slot[s].k1));
+    CU(cudaMalloc((void**)&x->d_cursor[s], sizeof(unsigned int)));
+  }
+  CU(cudaMalloc((void**)&x->d_stats, sizeof(bkx_align_stats)));
+  CU(cudaMalloc((void**)&x->d_pe_stats, sizeof(bkx_pe_stats)));
+  *out = x;
+  return BKX_OK;
+}
+
+extern "C" void bkx_close_index(bkx_index* x) {
+  if (!x) return;
+  cudaSetDevice(x->device);
+  cudaDeviceSynchronize();
+  for (void* p : x->owned) cudaFree(p);
+  for (int s = 0; s < 2; ++s) {
+    if (x->slot[s].d_bases) cudaFree(x->slot[s].d_bases);
+    if (x->slot[s].d_offs) cudaFree(x->slot[s].d_offs);
+    if (x->slot[s].d_out) cudaFree(x->slot[s].d_out);
+    if (x->slot[s].k0) cudaEventDestroy(x->slot[s].k0);
+    if (x->slot[s].k1) cudaEventDestroy(x->slot[s].k1);
+    if (x->slot[s].st) cudaStreamDestroy(x->slot[s].st);
+    if (x->d_cursor[s]) cudaFree(x->d_cursor[s]);
+  }
+  if (x->hash_pool) cudaFree(x->hash_pool);
+  if (x->epochs) cudaFree(x->epochs);
+  if (x->d_stats) cudaFree(x->d_stats);
+  if (x->d_pe_stats) cudaFree(x->d_pe_stats);
+  if (x->d_len_dist) cudaFree(x->d_len_dist);
+  delete x;
+}
+
+extern "C" int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, const void* d_sa, uint32_t el,
+                                  const bkx_entry* entries, uint32_t n_ent, const char* name, int device, int prefix_k,
+                                  bkx_index** out) {
+  if (!d_seq || !d_sa || !entries || !out) return fail(BKX_ERR_PARAM, "null argument");
+  bkx_index* x = nullptr;
+  int rc = new_index(device, &x);
+  if (rc < 0) return rc;
+  x->info.version = 5;
+  rc = finish_index(x, d_seq, concat_len, d_sa, el, false, entries, n_ent, name, prefix_k);
+  if (rc < 0) { bkx_close_index(x); return rc; }
+  *out = x;
+  return BKX_OK;
+}
+
+extern "C" int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t el,
+                                  const bkx_entry* entries, uint32_t n_ent, const char* name, int device, int prefix_k,
+                                  bkx_index** out) {
+  if (!seq || !sa || !entries || !out) return fail(BKX_ERR_PARAM, "null argument");
+  bkx_index* x = nullptr;
+  int rc = new_index(device, &x);
+  if (rc < 0) return rc;
+  x->info.version = 5;
+  uint8_t* d_seq = nullptr;
+  void* d_sa = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_seq, concat_len);
+  if (e == cudaSuccess) e = cudaMemcpy(d_seq, seq, concat_len, cudaMemcpyHostToDevice);
+  bool keep_sa = (el == 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_sa, concat_len * el);
+  if (e == cudaSuccess) e = cudaMemcpy(d_sa, sa, concat_len * el, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(d_seq); cudaFree(d_sa); bkx_close_index(x);
+    return fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e));
+  }
+  if (keep_sa) { x->owned.push_back(d_sa); x->info.device_bytes += concat_len * 4; }
+  rc = finish_index(x, d_seq, concat_len, d_sa, el, keep_sa, entries, n_ent, name, prefix_k);
+  cudaFree(d_seq);
+  if (!keep_sa) cudaFree(d_sa);
+  if (rc < 0) { bkx_close_index(x); return rc; }
+  *out = x;
+  return BKX_OK;
+}
+
+// ---- .sfx file: header tsSfxHeaderV3/Vv (SfxArrayV2.h:174-203), entries tsSfxEntry (:79-88),
+//      block tsSfxBlock (:98-104); see Disk2Hdr / Disk2Entries (SfxArrayV2.cpp:551-747) ----------------
+static bool pread_all(int fd, void* buf, size_t len, off_t ofs) {
+  uint8_t* p = (uint8_t*)buf;
+  while (len) {
+    ssize_t n = pread(fd, p, std::min(len, (size_t)1 << 30), ofs);
+    if (n <= 0) return false;
+    p += n; len -= (size_t)n; ofs += n;
+  }
+  return true;
+}
+static uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_index** out) {
+  if (!path || !out) return fail(BKX_ERR_PARAM, "null argument");
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(BKX_ERR_FILE, "unable to open '%s'", path);
+  struct stat sb;
+  fstat(fd, &sb);
+  uint8_t hdr[1224];
+  memset(hdr, 0, sizeof(hdr));
+  size_t hlen = std::min((size_t)sb.st_size, sizeof(hdr));
+  if (hlen < 52 || !pread_all(fd, hdr, hlen, 0) || memcmp(hdr, "sfx", 3) != 0) {
+    close(fd);
+    return fail(BKX_ERR_FORMAT, "'%s' is not a biokanga suffix array file", path);
+  }
+  uint32_t version = rd32(hdr + 4), attributes = rd32(hdr + 8);
+  if (version < 3 || version > 5 || hdr[3] != (uint8_t)('0' + version)) {
+    close(fd);
+    return fail(BKX_ERR_FORMAT, "'%s': unsupported sfx version %u", path, version);
+  }
+  if (attributes & 0x03) {
+    close(fd);
+    return fail(BKX_ERR_UNSUPPORTED, "'%s': bisulfite / colorspace indexes are not supported", path);
+  }
+  uint64_t entries_ofs = rd64(hdr + 20), blk_ofs = rd64(hdr + 44);
+  uint32_t n_blocks = rd32(hdr + 32);
+  int name_len = (version <= 3) ? 36 : 81;
+  char dataset[88] = {0};
+  memcpy(dataset, hdr + 52, (size_t)std::min(name_len, 83));
+  if (n_blocks != 1 || entries_ofs == 0 || blk_ofs == 0 || entries_ofs + 8 > (uint64_t)sb.st_size) {
+    close(fd);
+    return fail(BKX_ERR_FORMAT, "'%s': no suffix block / entries", path);
+  }
+  uint8_t eh[8];
+  if (!pread_all(fd, eh, 8, (off_t)entries_ofs)) { close(fd); return fail(BKX_ERR_FILE, "'%s': short read", path); }
+  uint32_t n_ent = rd32(eh);
+  size_t esz = (size_t)(8 + name_len + 2 + 4 + 8 + 8);
+  std::vector<uint8_t> eb((size_t)n_ent * esz);
+  if (n_ent == 0 || !pread_all(fd, eb.data(), eb.size(), (off_t)entries_ofs + 8)) {
+    close(fd);
+    return fail(BKX_ERR_FORMAT, "'%s': bad entries block", path);
+  }
+  std::vector<bkx_entry> ents(n_ent);
+  for (uint32_t i = 0; i < n_ent; ++i) {
+    const uint8_t* e = eb.data() + esz * i;
+    bkx_entry& o = ents[i];
+    memset(&o, 0, sizeof(o));
+    o.entry_id = rd32(e);
+    memcpy(o.name, e + 8, (size_t)name_len);
+    o.seq_len = rd32(e + 8 + name_len + 2);
+    o.start_ofs = rd64(e + 8 + name_len + 6);
+    o.end_ofs = rd64(e + 8 + name_len + 14);
+  }
+  uint8_t bh[20];
+  if (!pread_all(fd, bh, 20, (off_t)blk_ofs)) { close(fd); return fail(BKX_ERR_FILE, "'%s': short read", path); }
+  uint64_t n = rd64(bh + 8);
+  uint32_t el = rd32(bh + 16);
+  if ((el != 4 && el != 5) || blk_ofs + 20 + n + n * el > (uint64_t)sb.st_size) {
+    close(fd);
+    return fail(BKX_ERR_FORMAT, "'%s': bad suffix block", path);
+  }
+  bkx_index* x = nullptr;
+  int rc = new_index(device, &x);
+  if (rc < 0) { close(fd); return rc; }
+  x->info.version = version;
+  x->info.attributes = attributes;
+  // stream the block to the GPU through two pinned staging buffers
+  uint8_t* d_seq = nullptr;
+  uint8_t* d_sa = nullptr;
+  const size_t chunk = (size_t)64 << 20;
+  uint8_t* pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2];
+  cudaError_t e = cudaMalloc((void**)&d_seq, n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_sa, n * el);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMallocHost((void**)&pin[i], chunk);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev[i]);
+  }
+  bool io_ok = true;
+  if (e == cudaSuccess) {
+    cudaStream_t st = x->slot[0].st;
+    uint64_t total = n + n * el, done = 0;
+    int b = 0;
+    bool used[2] = {false, false};
+    while (done < total && e == cudaSuccess) {
+      size_t len = (size_t)std::min<uint64_t>(chunk, total - done);
+      // never let one chunk straddle the sequence / suffix-array boundary
+      if (done < n && done + len > n) len = (size_t)(n - done);
+      if (used[b]) e = cudaEventSynchronize(ev[b]);
+      if (!pread_all(fd, pin[b], len, (off_t)(blk_ofs + 20 + done))) { io_ok = false; break; }
+      uint8_t* dst = done < n ? d_seq + done : d_sa + (done - n);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dst, pin[b], len, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+      used[b] = true;
+      done += len;
+      b ^= 1;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  close(fd);
+  for (int i = 0; i < 2; ++i) if (pin[i]) { cudaFreeHost(pin[i]); cudaEventDestroy(ev[i]); }
+  if (e != cudaSuccess || !io_ok) {
+    cudaFree(d_seq); cudaFree(d_sa); bkx_close_index(x);
+    return e != cudaSuccess ? fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e))
+                            : fail(BKX_ERR_FILE, "'%s': short read", path);
+  }
+  bool keep_sa = (el == 4);
+  if (keep_sa) { x->owned.push_back(d_sa); x->info.device_bytes += n * 4; }
+  rc = finish_index(x, d_seq, n, d_sa, el, keep_sa, ents.data(), n_ent, dataset, prefix_k);
+  cudaFree(d_seq);
+  if (!keep_sa) cudaFree(d_sa);
+  if (rc < 0) { bkx_close_index(x); return rc; }
+  *out = x;
+  return BKX_OK;
+}
+
+extern "C" int bkx_clone_index(const bkx_index* src, int device, bkx_index** out) {
+  (void)src; (void)device; (void)out;
+  return fail(BKX_ERR_UNSUPPORTED, "bkx_clone_index: peer replication not built yet (one process per GPU opens its own copy)");
+}
+
+extern "C" int bkx_index_info_get(const bkx_index* x, bkx_index_info* out) {
+  if (!x || !out) return fail(BKX_ERR_PARAM, "null argument");
+  *out = x->info;
+  return BKX_OK;
+}
+
+extern "C" int bkx_get_entry(const bkx_index* x, uint32_t entry_id, bkx_entry* out) {
+  if (!x || !out) return fail(BKX_ERR_PARAM, "null argument");
+  for (const auto& e : x->entries)
+    if (e.entry_id == entry_id) { *out = e; return BKX_OK; }
+  return fail(BKX_ERR_ENTRY, "no entry %u", entry_id);
+}
+
+extern "C" int bkx_get_ident(const bkx_index* x, const char* name) {
+  if (!x || !name) return fail(BKX_ERR_PARAM, "null argument");
+  for (const auto& e : x->entries)
+    if (strcasecmp(e.name, name) == 0) return (int)e.entry_id;
+  return fail(BKX_ERR_ENTRY, "no entry named '%s'", name);
+}
+
+__global__ void unpack_seq_kernel(DevIndex I, uint64_t start, uint64_t len, uint8_t* out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = (uint8_t)gsym(I, start + i);
+}
+
+extern "C" int64_t bkx_get_seq(const bkx_index* x, uint32_t entry_id, uint64_t loci, uint64_t len, uint8_t* buf) {
+  if (!x || !buf) return fail(BKX_ERR_PARAM, "null argument");
+  const bkx_entry* e = nullptr;
+  for (const auto& t : x->entries) if (t.entry_id == entry_id) e = &t;
+  if (!e) return fail(BKX_ERR_ENTRY, "no entry %u", entry_id);
+  if (loci >= e->seq_len) return 0;
+  len = std::min<uint64_t>(len, e->seq_len - loci);
+  if (len == 0) return 0;
+  CU(cudaSetDevice(x->device));
+  uint8_t* d = nullptr;
+  CU(cudaMalloc((void**)&d, len));
+  unpack_seq_kernel<<<(unsigned)std::min<uint64_t>((len + 255) / 256, 148 * 8), 256>>>(x->d, e->start_ofs + loci, len, d);
+  cudaError_t err = cudaMemcpy(buf, d, len, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (err != cudaSuccess) return fail(BKX_ERR_CUDA, "bkx_get_seq: %s", cudaGetErrorString(err));
+  return (int64_t)len;
+}
+
+extern "C" int bkx_default_params(const bkx_index* x, int pmode, bkx_align_params* p) {
+  if (!x || !p) return fail(BKX_ERR_PARAM, "null argument");
+  memset(p, 0, sizeof(*p));
+  uint64_t t = x->info.tot_seq_len;
+  int mcl;  // Aligner.cpp:8727-8739
+  if (t <= 500000) mcl = 4;
+  else if (t <= 20000000) mcl = 7;
+  else if (t <= 250000000) mcl = 11;
+  else if (t <= 3500000000ull) mcl = 12;
+  else mcl = 15;
+  int slides, iters;  // Aligner.cpp:8744-8760 and :341-356
+  switch (pmode) {
+    case BKX_PMODE_ULTRASENS: slides = 9; iters = 20000; break;
+    case BKX_PMODE_MORESENS: mcl += 1; slides = 8; iters = 10000; break;
+    case BKX_PMODE_DEFAULT: mcl += 2; slides = 8; iters = 5000; break;
+    case BKX_PMODE_LESSSENS: mcl += 4; slides = 6; iters = 2500; break;
+    default: return fail(BKX_ERR_PARAM, "bad processing mode %d", pmode);
+  }
+  p->pmode = pmode;
+  p->max_subs = 10;
+  p->min_edit_dist = 1;
+  p->max_ns = 1;
+  p->align_strand = BKX_STRAND_BOTH;
+  p->max_ml_matches = 1;
+  p->min_core_len = mcl;
+  p->max_num_slides = slides;
+  p->max_iter = iters;
+  p->max_ident_nodes = 1024000;
+  return BKX_OK;
+}
+
+static int check_params(const bkx_align_params* p, KParams* k) {
+  if (!p) return fail(BKX_ERR_PARAM, "null parameters");
+  if (p->max_subs < 0 || p->max_subs > 15) return fail(BKX_ERR_PARAM, "max_subs %d out of range 0..15", p->max_subs);
+  if (p->min_edit_dist < 1 || p->min_edit_dist > 2) return fail(BKX_ERR_PARAM, "min_edit_dist %d out of range 1..2", p->min_edit_dist);
+  if (p->max_ns < 0 || p->max_ns > 5) return fail(BKX_ERR_PARAM, "max_ns %d out of range 0..5", p->max_ns);
+  if (p->align_strand < 0 || p->align_strand > 2) return fail(BKX_ERR_PARAM, "bad align_strand %d", p->align_strand);
+  if (p->max_ml_matches != 1)
+    return fail(BKX_ERR_UNSUPPORTED, "max_ml_matches %d: multi-loci modes (-r/-R) are not built yet", p->max_ml_matches);
+  if (p->min_core_len < 4 || p->min_core_len > 100) return fail(BKX_ERR_PARAM, "bad min_core_len %d", p->min_core_len);
+  if (p->max_num_slides < 1 || p->max_num_slides > 16) return fail(BKX_ERR_PARAM, "bad max_num_slides %d", p->max_num_slides);
+  if (p->max_iter <= 100) return fail(BKX_ERR_PARAM, "max_iter %d must exceed 100", p->max_iter);
+  if (p->max_ident_nodes < 1) return fail(BKX_ERR_PARAM, "bad max_ident_nodes %d", p->max_ident_nodes);
+  k->max_subs = p->max_subs; k->mmd = p->min_edit_dist; k->max_ns = p->max_ns; k->strand_mode = p->align_strand;
+  k->max_hits = p->max_ml_matches; k->min_core_len = p->min_core_len; k->slides_per100 = p->max_num_slides;
+  k->max_iter = p->max_iter; k->max_nodes = p->max_ident_nodes;
+  return BKX_OK;
+}
+
+// Size the persistent grid and the per-warp overflow hash sets for reads up to max_len bases.
+static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int* W_out) {
+  if (max_len > 2000) return fail(BKX_ERR_PARAM, "read length %u exceeds cMaxSeqLen 2000", max_len);
+  int W = (int)((max_len + 31) / 32) + 1;
+  if (W < 3) W = 3;
+  if (W > x->grid_W || x->grid == 0) {
+    int nb = align_blocks_per_sm(W);
+    if (nb < 1) return fail(BKX_ERR_CUDA, "align kernel does not fit on an SM (W=%d)", W);
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, x->device));
+    x->grid = nb * sms;
+    x->grid_W = W;
+  }
+  int slides = std::max(1, (int)((k.slides_per100 * (uint64_t)std::max<uint32_t>(max_len, 100) + 99) / 100));
+  uint64_t cap = std::min<uint64_t>((uint64_t)k.max_nodes, (uint64_t)slides * (uint64_t)k.max_iter);
+  uint32_t slots = 1024;
+  while (slots < 2 * cap) slots <<= 1;
+  uint32_t warps = (uint32_t)x->grid * kWarpsPerBlock;
+  // the pool is sized for the widest grid ever used (grid only shrinks as W grows)
+  static const uint32_t kMaxWarps = 148 * 64 * 2;
+  if (slots > x->hash_slots || !x->hash_pool) {
+    if (x->hash_pool) { cudaFree(x->hash_pool); x->hash_pool = nullptr; }
+    if (x->epochs) { cudaFree(x->epochs); x->epochs = nullptr; }
+    uint32_t pool_warps = std::max(warps, (uint32_t)0);
+    (void)kMaxWarps;
+    CU(cudaMalloc((void**)&x->hash_pool, (size_t)pool_warps * slots * 8));
+    CU(cudaMemset(x->hash_pool, 0, (size_t)pool_warps * slots * 8));
+    CU(cudaMalloc((void**)&x->epochs, (size_t)pool_warps * 4));
+    CU(cudaMemset(x->epochs, 0, (size_t)pool_warps * 4));
+    x->hash_slots = slots;
+  }
+  *W_out = x->grid_W;
+  return BKX_OK;
+}
+
+extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, const uint8_t* d_bases,
+                                      const uint64_t* d_offsets, uint32_t n_reads, uint32_t max_read_len,
+                                      bkx_read_result* d_out, bkx_align_stats* d_stats, void* cuda_stream) {
+  if (!x || !d_bases || !d_offsets || !d_out) return fail(BKX_ERR_PARAM, "null argument");
+  KParams k;
+  int rc = check_params(p, &k);
+  if (rc < 0) return rc;
+  if (n_reads == 0) return BKX_OK;
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  int W = 0;
+  if ((rc = prepare_launch(x, k, max_read_len, &W)) < 0) return rc;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : x->slot[0].st;
+  Slot& s = x->slot[0];
+  CU(cudaEventRecord(s.k0, st));
+  CU(launch_align(x->d, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, x->d_cursor[0], x->hash_pool, x->hash_slots,
+                  x->epochs, x->grid, st));
+  CU(cudaEventRecord(s.k1, st));
+  s.timed = true;
+  x->slot[1].timed = false;
+  x->last_ms = -2.f;  // resolved lazily by bkx_last_kernel_ms
+  x->launches += 1;
+  return BKX_OK;
+}
+
+extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
+                               uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
+  if (!x || !bases || !offsets || !out) return fail(BKX_ERR_PARAM, "null argument");
+  KParams k;
+  int rc = check_params(p, &k);
+  if (rc < 0) return rc;
+  if (n_reads == 0) return BKX_OK;
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  uint32_t max_len = 0;
+  for (uint32_t i = 0; i < n_reads; ++i) {
+    if (offsets[i + 1] < offsets[i]) return fail(BKX_ERR_PARAM, "offsets not monotonic at read %u", i);
+    max_len = std::max<uint64_t>(max_len, offsets[i + 1] - offsets[i]);
+  }
+  int W = 0;
+  if ((rc = prepare_launch(x, k, max_len, &W)) < 0) return rc;
+  CU(cudaMemsetAsync(x->d_stats, 0, sizeof(bkx_align_stats), x->slot[0].st));
+  CU(cudaStreamSynchronize(x->slot[0].st));
+  const uint32_t kBatchReads = 1u << 20;
+  const uint64_t kBatchBases = 256ull << 20;
+  float ms_total = 0.f;
+  uint32_t start = 0;
+  int b = 0;
+  bool inflight[2] = {false, false};
+  auto drain = [&](int si) -> int {
+    Slot& s = x->slot[si];
+    CU(cudaStreamSynchronize(s.st));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s.k0, s.k1));
+    ms_total += ms;
+    inflight[si] = false;
+    return BKX_OK;
+  };
+  while (start < n_reads) {
+    uint32_t cnt = std::min(kBatchReads, n_reads - start);
+    while (cnt > 1 && offsets[start + cnt] - offsets[start] > kBatchBases) cnt = (cnt + 1) / 2;
+    uint64_t nb = offsets[start + cnt] - offsets[start];
+    Slot& s = x->slot[b];
+    if (inflight[b] && (rc = drain(b)) < 0) return rc;
+    if (nb + 64 > s.bases_cap) {
+      if (s.d_bases) cudaFree(s.d_bases);
+      s.bases_cap = (size_t)(nb + 64) * 5 / 4;
+      CU(cudaMalloc((void**)&s.d_bases, s.bases_cap));
+    }
+    if (cnt > s.reads_cap) {
+      if (s.d_offs) cudaFree(s.d_offs);
+      if (s.d_out) cudaFree(s.d_out);
+      s.reads_cap = (size_t)cnt * 5 / 4;
+      CU(cudaMalloc((void**)&s.d_offs, (s.reads_cap + 1) * 8));
+      CU(cudaMalloc((void**)&s.d_out, s.reads_cap * sizeof(bkx_read_result)));
+    }
+    CU(cudaMemcpyAsync(s.d_bases, bases + offsets[start], nb, cudaMemcpyHostToDevice, s.st));
+    CU(cudaMemcpyAsync(s.d_offs, offsets + start, ((size_t)cnt + 1) * 8, cudaMemcpyHostToDevice, s.st));
+    CU(cudaEventRecord(s.k0, s.st));
+    // offsets stay absolute: hand the kernel a base pointer shifted by the slice start
+    CU(launch_align(x->d, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, x->d_cursor[b],
+                    x->hash_pool, x->hash_slots, x->epochs, x->grid, s.st));
+    CU(cudaEventRecord(s.k1, s.st));
+    CU(cudaMemcpyAsync(out + start, s.d_out, (size_t)cnt * sizeof(bkx_read_result), cudaMemcpyDeviceToHost, s.st));
+    inflight[b] = true;
+    x->launches += 1;
+    start += cnt;
+    b ^= 1;
+  }
+  for (int si = 0; si < 2; ++si)
+    if (inflight[si] && (rc = drain(si)) < 0) return rc;
+  x->last_ms = ms_total;
+  x->slot[0].timed = x->slot[1].timed = false;
+  if (stats) {
+    bkx_align_stats h;
+    CU(cudaMemcpy(&h, x->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    uint64_t* d = (uint64_t*)stats;
+    const uint64_t* s = (const uint64_t*)&h;
+    for (size_t i = 0; i < sizeof(h) / 8; ++i) d[i] += s[i];
+  }
+  return BKX_OK;
+}
+
+extern "C" int bkx_align_one(bkx_index* x, const bkx_align_params* p, const uint8_t* probe, int probe_len,
+                             int* low_hit_instances, int* low_mm, int* nxt_low_mm, bkx_read_result* hit) {
+  if (!probe || probe_len < 1 || !hit) return fail(BKX_ERR_PARAM, "null argument");
+  uint64_t offs[2] = {0, (uint64_t)probe_len};
+  bkx_read_result r;
+  int rc = bkx_align_reads(x, p, probe, offs, 1, &r, nullptr);
+  if (rc < 0) return rc;
+  *hit = r;
+  if (low_hit_instances) *low_hit_instances = r.low_hit_instances;
+  if (low_mm) *low_mm = r.low_mm;
+  if (nxt_low_mm) *nxt_low_mm = r.nxt_low_mm;
+  return r.hit_rslt;
+}
+
+extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, bkx_read_result* results,
+                              uint32_t n_pairs, const uint8_t* bases, const uint64_t* offsets, bkx_pe_stats* stats,
+                              uint32_t* len_dist) {
+  (void)p; (void)bases; (void)offsets;
+  if (!x || !pe || !results) return fail(BKX_ERR_PARAM, "null argument");
+  if (pe->pe_proc < BKX_PE_ORPHAN || pe->pe_proc > BKX_PE_UNIQUE_SE) return fail(BKX_ERR_PARAM, "bad pe_proc %d", pe->pe_proc);
+  if (pe->pe_proc == BKX_PE_ORPHAN || pe->pe_proc == BKX_PE_ORPHAN_SE)
+    return fail(BKX_ERR_UNSUPPORTED, "orphan recovery (-U1/-U3) is not built yet");
+  if (pe->pair_min_len < 25 || pe->pair_max_len > 100000 || pe->pair_min_len > pe->pair_max_len)
+    return fail(BKX_ERR_PARAM, "bad insert size range %d..%d", pe->pair_min_len, pe->pair_max_len);
+  if (n_pairs == 0) return BKX_OK;
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  cudaStream_t st = x->slot[0].st;
+  if (!x->d_len_dist) CU(cudaMalloc((void**)&x->d_len_dist, 100001 * 4));
+  CU(cudaMemsetAsync(x->d_len_dist, 0, 100001 * 4, st));
+  CU(cudaMemsetAsync(x->d_pe_stats, 0, sizeof(bkx_pe_stats), st));
+  bkx_read_result* d_res = nullptr;
+  size_t bytes = (size_t)n_pairs * 2 * sizeof(bkx_read_result);
+  CU(cudaMalloc((void**)&d_res, bytes));
+  cudaError_t e = cudaMemcpyAsync(d_res, results, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_pair(*pe, d_res, n_pairs, x->d_pe_stats, x->d_len_dist, nullptr, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(results, d_res, bytes, cudaMemcpyDeviceToHost, st);
+  bkx_pe_stats hs;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, x->d_pe_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
+  std::vector<uint32_t> ld;
+  if (len_dist && e == cudaSuccess) {
+    ld.resize(100001);
+    e = cudaMemcpyAsync(ld.data(), x->d_len_dist, 100001 * 4, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_res);
+  if (e != cudaSuccess) return fail(BKX_ERR_CUDA, "bkx_pair_reads: %s", cudaGetErrorString(e));
+  x->launches += 1;
+  if (stats) {
+    uint64_t* d = (uint64_t*)stats;
+    const uint64_t* s = (const uint64_t*)&hs;
+    for (size_t i = 0; i < sizeof(hs) / 8; ++i) d[i] += s[i];
+  }
+  if (len_dist) for (size_t i = 0; i < ld.size(); ++i) len_dist[i] += ld[i];
+  return BKX_OK;
+}
+
+extern "C" float bkx_last_kernel_ms(const bkx_index* cx) {
+  bkx_index* x = const_cast<bkx_index*>(cx);
+  if (!x) return -1.f;
+  if (x->last_ms == -2.f) {
+    Slot& s = x->slot[0];
+    if (cudaEventSynchronize(s.k1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, s.k0, s.k1) != cudaSuccess) return -1.f;
+    x->last_ms = ms;
+  }
+  return x->last_ms;
+}
+
+extern "C" uint64_t bkx_kernel_launches(const bkx_index* x) { return x ? x->launches : 0; }

@@ -1,0 +1,107 @@
+// Device-resident index layout and the small inline accessors every kernel shares.
+//
+// HBM layout (one copy per GPU; replaces the mmap'd tsSfxBlock, libbiokanga/SfxArrayV2.h:98-104):
+//   g2   2 bits/base, 32 bases per u64, base i of the concatenation at bits [2*(i%32), +2) of word i/32
+//        (A0 C1 G2 T3; N is stored as 0 and EOS as 3, both flagged in gx)          n/4 bytes
+//   gx   1 bit/base "not ACGT" (N or EOS)                                             n/8 bytes
+//   gxc  1 bit per 64-base block: block holds any flagged base (L2 resident)          n/512 bytes
+//   sa   the reference's suffix array as written by `biokanga index`: u32 per element; for 5-byte
+//        elements (n >= 4e9) split into a u32 low plane and a u8 high plane           4n (+n) bytes
+//   pt   k-mer prefix table: pt[x] = number of suffixes whose first-k symbols sort below the ACGT
+//        k-mer x (first base most significant); 4^k+1 entries of u32 (u64 when n >= 2^32)
+//   ent  chromosome table sorted by start offset
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bkx {
+
+struct DevIndex {
+  const uint64_t* g2;
+  const uint64_t* gx;
+  const uint32_t* gxc;
+  const uint32_t* sa_lo;
+  const uint8_t* sa_hi;  // nullptr for 4-byte elements
+  const uint32_t* pt32;  // one of pt32 / pt64 is set
+  const uint64_t* pt64;
+  const uint64_t* ent_start;
+  const uint64_t* ent_end;
+  const uint32_t* ent_id;
+  uint64_t n;  // ConcatSeqLen
+  uint32_t n_ent;
+  int k;
+};
+
+__device__ __forceinline__ uint64_t sa_get(const DevIndex& I, uint64_t i) {
+  uint64_t v = __ldg(I.sa_lo + i);
+  if (I.sa_hi) v |= (uint64_t)__ldg(I.sa_hi + i) << 32;
+  return v;
+}
+
+__device__ __forceinline__ uint64_t pt_get(const DevIndex& I, uint64_t x) {
+  return I.pt32 ? (uint64_t)__ldg(I.pt32 + x) : __ldg(I.pt64 + x);
+}
+
+// 32 bases of the concatenation starting at base g (little-endian base order).
+__device__ __forceinline__ uint64_t gword(const DevIndex& I, uint64_t g) {
+  uint64_t w = g >> 5;
+  unsigned sh = (unsigned)(g & 31) * 2;
+  uint64_t a = __ldg(I.g2 + w);
+  if (sh == 0) return a;
+  uint64_t b = __ldg(I.g2 + w + 1);
+  return (a >> sh) | (b << (64 - sh));
+}
+
+// 4-bit symbol of the reference at concatenation offset i: 0..3, 4 = N, 7 = EOS (also past the end).
+__device__ __forceinline__ int gsym(const DevIndex& I, uint64_t i) {
+  if (i >= I.n) return 7;
+  int code = (int)((__ldg(I.g2 + (i >> 5)) >> ((i & 31) * 2)) & 3);
+  int ex = (int)((__ldg(I.gx + (i >> 6)) >> (i & 63)) & 1);
+  return ex ? (code == 3 ? 7 : 4) : code;
+}
+
+// true if any base in [g, g+len) is N/EOS or lies past the end of the concatenation.
+__device__ __forceinline__ bool span_has_exc(const DevIndex& I, uint64_t g, uint32_t len) {
+  if (g + len > I.n) return true;
+  uint64_t b0 = g >> 6, b1 = (g + len - 1) >> 6;
+  for (uint64_t w = b0 >> 5; w <= (b1 >> 5); ++w) {
+    uint32_t v = __ldg(I.gxc + w);
+    uint32_t lo = (w == (b0 >> 5)) ? (0xffffffffu << (b0 & 31)) : 0xffffffffu;
+    uint32_t hi = (w == (b1 >> 5)) ? (0xffffffffu >> (31 - (b1 & 31))) : 0xffffffffu;
+    if (v & lo & hi) return true;
+  }
+  return false;
+}
+
+// reverse the order of the 32 two-bit groups of a word (first base becomes most significant).
+__device__ __forceinline__ uint64_t rev2(uint64_t w) {
+  uint64_t r = __brevll(w);
+  return ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);
+}
+
+// spread the 32 bits of x to the even bit positions of a 64-bit word.
+__device__ __forceinline__ uint64_t spread32(uint32_t x) {
+  uint64_t v = x;
+  v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+  v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+  v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+  v = (v | (v << 2)) & 0x3333333333333333ull;
+  v = (v | (v << 1)) & 0x5555555555555555ull;
+  return v;
+}
+
+// chromosome (entry) index containing concatenation offset ofs, or -1 (MapChunkHit2Entry,
+// libbiokanga/SfxArrayV2.cpp:2530-2575).
+__device__ __forceinline__ int find_entry(const DevIndex& I, uint64_t ofs) {
+  int lo = 0, hi = (int)I.n_ent - 1;
+  while (hi >= lo) {
+    int mid = (hi + lo) >> 1;
+    uint64_t s = __ldg(I.ent_start + mid);
+    if (s > ofs) { hi = mid - 1; continue; }
+    if (__ldg(I.ent_end + mid) >= ofs) return mid;
+    lo = mid + 1;
+  }
+  return -1;
+}
+
+}  // namespace bkx

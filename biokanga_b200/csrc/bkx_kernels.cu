@@ -1,0 +1,490 @@
+// CUDA kernels of the bkx library (sm_100a): index preparation, read alignment, paired-end pairing.
+#include "bkx_align.cuh"
+#include "bkx_kernels.h"
+
+#include <cub/device/device_scan.cuh>
+
+namespace bkx {
+
+// ------------------------------------------------------------------------------------------------
+// Index preparation
+// ------------------------------------------------------------------------------------------------
+// One thread per 64-base block of the reference's 1-byte/base concatenation: writes two g2 words, one
+// gx word, and raises the block's coarse bit.  bad_count receives the number of symbols that are not
+// one of A C G T N EOS (soft-mask bit set, InDel/Undefined codes): such files are rejected.
+__global__ void pack_genome_kernel(const uint8_t* __restrict__ seq, uint64_t n, uint64_t* __restrict__ g2,
+                                   uint64_t* __restrict__ gx, uint32_t* __restrict__ gxc,
+                                   unsigned long long* __restrict__ bad_count) {
+  uint64_t nblk = (n + 63) >> 6;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t base = b << 6;
+    uint64_t w0 = 0, w1 = 0, x = 0;
+    unsigned bad = 0;
+    if (base + 64 <= n && ((uintptr_t)(seq + base) & 15) == 0) {
+      const uint4* v = reinterpret_cast<const uint4*>(seq + base);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u = __ldg(v + q);
+        uint32_t ws[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            unsigned sym = (ws[j] >> (8 * t)) & 0xff;
+            int i = q * 16 + j * 4 + t;
+            unsigned code = sym & 3, ex = 0;
+            if (sym > 3) { ex = 1; code = (sym == 7) ? 3 : 0; bad += (sym != 4 && sym != 7); }
+            if (i < 32) w0 |= (uint64_t)code << (2 * i); else w1 |= (uint64_t)code << (2 * (i - 32));
+            x |= (uint64_t)ex << i;
+          }
+        }
+      }
+    } else {
+      for (int i = 0; i < 64 && base + i < n; ++i) {
+        unsigned sym = seq[base + i];
+        unsigned code = sym & 3, ex = 0;
+        if (sym > 3) { ex = 1; code = (sym == 7) ? 3 : 0; bad += (sym != 4 && sym != 7); }
+        if (i < 32) w0 |= (uint64_t)code << (2 * i); else w1 |= (uint64_t)code << (2 * (i - 32));
+        x |= (uint64_t)ex << i;
+      }
+    }
+    g2[2 * b] = w0;
+    g2[2 * b + 1] = w1;
+    gx[b] = x;
+    if (x) atomicOr(gxc + (b >> 5), 1u << (b & 31));
+    if (bad) atomicAdd(bad_count, (unsigned long long)bad);
+  }
+}
+
+// 5-byte suffix elements -> u32 low plane + u8 high plane.
+__global__ void split_sa5_kernel(const uint8_t* __restrict__ sa5, uint64_t n, uint32_t* __restrict__ lo,
+                                 uint8_t* __restrict__ hi) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t* p = sa5 + i * 5;
+    lo[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    hi[i] = p[4];
+  }
+}
+
+// Table key of the suffix at position i: its first k symbols as a base-4 number (first base most
+// significant); a suffix whose j-th symbol (j<k) is N/EOS/past-the-end takes the key
+// (prefix_j << 2(k-j)) | 11..1, i.e. it is filed at the very end of its j-symbol prefix -- exactly
+// where the reference's symbol order (A<C<G<T<N<EOS) sorts it.
+__device__ __forceinline__ uint64_t suffix_key(const DevIndex& I, uint64_t i, int k) {
+  uint64_t w = i >> 5;
+  unsigned sh = (unsigned)(i & 31) * 2;
+  uint64_t a = I.g2[w];
+  uint64_t gw = sh ? ((a >> sh) | (I.g2[w + 1] << (64 - sh))) : a;
+  // exception bits of [i, i+k)
+  uint64_t xw = i >> 6;
+  unsigned xs = (unsigned)(i & 63);
+  uint64_t xa = I.gx[xw] >> xs;
+  if (xs) xa |= I.gx[xw + 1] << (64 - xs);
+  uint64_t kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1);
+  xa &= kmask;
+  // positions past the end behave as EOS
+  if (i + (uint64_t)k > I.n) xa |= (~0ull << (I.n - i)) & kmask;
+  uint64_t key = rev2(gw) >> (64 - 2 * k);
+  if (xa) {
+    int j = __ffsll((long long)xa) - 1;
+    key |= (1ull << (2 * (k - j))) - 1;
+  }
+  return key;
+}
+
+template <typename CntT>
+__global__ void kmer_hist_kernel(DevIndex I, int k, CntT* __restrict__ cnt) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < I.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t key = suffix_key(I, i, k);
+    atomicAdd(cnt + key + 1, (CntT)1);
+  }
+}
+
+cudaError_t launch_pack_genome(const uint8_t* seq, uint64_t n, uint64_t* g2, uint64_t* gx, uint32_t* gxc,
+                               unsigned long long* bad, cudaStream_t st) {
+  uint64_t nblk = (n + 63) >> 6;
+  int grid = (int)((nblk + 255) / 256 < 148 * 16 ? (nblk + 255) / 256 : 148 * 16);
+  if (grid < 1) grid = 1;
+  pack_genome_kernel<<<grid, 256, 0, st>>>(seq, n, g2, gx, gxc, bad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_sa5(const uint8_t* sa5, uint64_t n, uint32_t* lo, uint8_t* hi, cudaStream_t st) {
+  split_sa5_kernel<<<148 * 8, 256, 0, st>>>(sa5, n, lo, hi);
+  return cudaGetLastError();
+}
+
+cudaError_t build_prefix_table(const DevIndex& I, int k, void* table, bool wide, cudaStream_t st) {
+  uint64_t entries = (1ull << (2 * k)) + 1;
+  cudaError_t e;
+  if (wide) {
+    e = cudaMemsetAsync(table, 0, entries * 8, st);
+    if (e != cudaSuccess) return e;
+    kmer_hist_kernel<unsigned long long><<<148 * 16, 256, 0, st>>>(I, k, (unsigned long long*)table);
+  } else {
+    e = cudaMemsetAsync(table, 0, entries * 4, st);
+    if (e != cudaSuccess) return e;
+    kmer_hist_kernel<uint32_t><<<148 * 16, 256, 0, st>>>(I, k, (uint32_t*)table);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  if (wide) {
+    unsigned long long* t = (unsigned long long*)table;
+    e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, t, t, (long long)entries, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&tmp, tmp_bytes);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, t, t, (long long)entries, st);
+  } else {
+    uint32_t* t = (uint32_t*)table;
+    e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, t, t, (long long)entries, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&tmp, tmp_bytes);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, t, t, (long long)entries, st);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  return e != cudaSuccess ? e : e2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Read alignment
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t warp_smem_bytes(int W) {
+  return (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + 36 * 4;
+}
+size_t align_smem_bytes(int W) {
+  size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + 36 * 4;
+  per = (per + 15) & ~(size_t)15;
+  return per * kWarpsPerBlock;
+}
+
+struct BlockStats {
+  unsigned int nar[BKX_NAR_COUNT];
+  unsigned int plus, minus;
+  unsigned long long seeds, cands;
+};
+
+// Per-read driver: ProcCoredApprox body (Aligner.cpp:9027-9504) + AlignReads phase loop
+// (SfxArrayV2.cpp:7666-7760).  One warp per read; reads are claimed from a global cursor.
+__global__ void __launch_bounds__(kBlockThreads) align_reads_kernel(
+    DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
+    int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
+    uint64_t* __restrict__ hash_pool, uint32_t hash_slots, uint32_t* __restrict__ epochs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockStats bs;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
+  __syncthreads();
+
+  size_t per = ((size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + 36 * 4 + 15) & ~(size_t)15;
+  unsigned char* my = smem_raw + per * wib;
+  WarpCtx c;
+  c.s2[0] = (uint64_t*)my;
+  c.s2[1] = c.s2[0] + W;
+  c.sx[0] = (uint32_t*)(c.s2[1] + W);
+  c.sx[1] = c.sx[0] + W;
+  c.seen = c.sx[1] + W;
+  c.pre = (int*)(c.seen + kSeenCap);
+  c.lane = lane;
+  const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + wib;
+  c.hash = hash_pool + (size_t)gwarp * hash_slots;
+  c.hmask = hash_slots - 1;
+  c.epoch = epochs[gwarp];
+
+  for (;;) {
+    unsigned int r = 0;
+    if (lane == 0) r = atomicAdd(cursor, 1u);
+    r = __shfl_sync(kFull, r, 0);
+    if (r >= n_reads) break;
+    const uint64_t o0 = __ldg(offs + r);
+    const int L = (int)(__ldg(offs + r + 1) - o0);
+    const uint8_t* rd = bases + o0;
+    c.L = L;
+    // ---- unpack, N filter (Aligner.cpp:9041-9063), 2-bit pack both strands
+    int nN = 0;
+    bool bad = false;
+    const int words = (L + 31) >> 5;
+    for (int w = 0; w <= words && w < W; ++w) {
+      int i = w * 32 + lane;
+      unsigned code = 0, isn = 0;
+      if (i < L) {
+        unsigned b = rd[i] & 0x07;
+        if (b > 4) bad = true;
+        isn = (b == 4);
+        code = isn ? 0 : (b & 3);
+      }
+      unsigned b0 = __ballot_sync(kFull, code & 1), b1 = __ballot_sync(kFull, code & 2), bn = __ballot_sync(kFull, isn);
+      // reverse complement: position q of the '-' strand is the complement of base L-1-q
+      int q = w * 32 + lane;
+      unsigned rcode = 0, risn = 0;
+      if (q < L) {
+        unsigned b = rd[L - 1 - q] & 0x07;
+        risn = (b == 4);
+        rcode = (b < 4) ? (3 - b) : 0;
+      }
+      unsigned r0 = __ballot_sync(kFull, rcode & 1), r1 = __ballot_sync(kFull, rcode & 2), rn = __ballot_sync(kFull, risn);
+      if (lane == 0) {
+        c.s2[0][w] = spread32(b0) | (spread32(b1) << 1);
+        c.sx[0][w] = bn;
+        c.s2[1][w] = spread32(r0) | (spread32(r1) << 1);
+        c.sx[1][w] = rn;
+      }
+      nN += __popc(bn);
+    }
+    bad = __any_sync(kFull, bad);
+    __syncwarp();
+    c.hasN = nN > 0;
+    int max_ns_seq = 0;
+    if (P.max_ns) max_ns_seq = max((L * P.max_ns) / 100, P.max_ns);
+
+    bkx_read_result res;
+    res.nar = BKX_NAR_NOHIT; res.hit_rslt = 0; res.strand = 0; res.num_hits = 0; res.low_mm = 0; res.nxt_low_mm = 0;
+    res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0; res.mismatches = 0;
+    res.flags = 0; res.seeds = 0; res.cands = 0; res.reserved = 0;
+    c.seeds = c.cands = 0;
+
+    if (bad || nN > max_ns_seq || L < 1) {
+      // the reference stops at the first offending base; a code > N or too many Ns both give eNARNs
+      res.nar = BKX_NAR_NS;
+    } else {
+      // per-read search parameters, Aligner.cpp:9085-9095
+      int max_tot_mm = P.max_subs == 0 ? 0 : max(1, (L * P.max_subs + 50) / 100);
+      if (max_tot_mm > 63) max_tot_mm = 63;
+      int core_len = max(P.min_core_len, L / (P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
+      int slides = max(1, (P.slides_per100 * L + 99) / 100);
+      int core_delta = max(L / slides - 1, core_len);
+      c.inst = 0; c.low = 0; c.nxt = 0;
+      c.hit_strand = 0; c.hit_ent = -1; c.hit_mm = 0; c.hit_p = 0;
+      int hr = 0, allow = 0;
+      if (max_tot_mm > 0) {
+        for (allow = 0; allow <= max_tot_mm; ++allow) {
+          int cl = L / (allow + P.mmd);
+          if (cl <= core_len) break;
+          hr = run_phase(I, P, c, allow, cl, cl, slides);
+          if (hr != 0) break;
+        }
+      }
+      if (hr == 0 && allow <= max_tot_mm) hr = run_phase(I, P, c, max_tot_mm, core_len, core_delta, slides);
+      int inst = c.inst;
+      if (inst > P.max_hits) inst = P.max_hits + 1;  // Aligner.cpp:9241
+      res.hit_rslt = (uint8_t)hr;
+      res.seeds = c.seeds;
+      res.cands = c.cands;
+      switch (hr) {
+        case BKX_HR_HITS:
+          res.nar = BKX_NAR_ACCEPTED;
+          res.num_hits = 1;
+          res.strand = c.hit_strand ? '-' : '+';
+          res.chrom_id = __ldg(I.ent_id + c.hit_ent);
+          res.match_loci = (uint32_t)(c.hit_p - __ldg(I.ent_start + c.hit_ent));
+          res.match_len = (uint16_t)L;
+          res.mismatches = (uint8_t)c.hit_mm;
+          res.low_hit_instances = 1;
+          res.low_mm = (int8_t)c.low;
+          res.nxt_low_mm = (int8_t)c.nxt;
+          break;
+        case BKX_HR_MMDELTA:
+        case BKX_HR_HITINSTS:
+          res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
+          res.strand = '?';
+          res.match_len = (uint16_t)L;
+          res.low_hit_instances = (int16_t)inst;
+          res.low_mm = (int8_t)c.low;
+          res.nxt_low_mm = (int8_t)c.nxt;
+          break;
+        case BKX_HR_RMMDELTA:
+          res.nxt_low_mm = (int8_t)c.nxt;
+          break;
+        default:
+          break;
+      }
+    }
+    if (lane == 0) {
+      out[r] = res;
+      atomicAdd(&bs.nar[res.nar], 1u);
+      if (res.nar == BKX_NAR_ACCEPTED) atomicAdd(res.strand == '+' ? &bs.plus : &bs.minus, 1u);
+      atomicAdd(&bs.seeds, (unsigned long long)res.seeds);
+      atomicAdd(&bs.cands, (unsigned long long)res.cands);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) epochs[gwarp] = c.epoch;
+  __syncthreads();
+  if (stats) {
+    for (int i = threadIdx.x; i < BKX_NAR_COUNT; i += blockDim.x)
+      if (bs.nar[i]) atomicAdd((unsigned long long*)&stats->nar[i], (unsigned long long)bs.nar[i]);
+    if (threadIdx.x == 0) {
+      unsigned long long reads = 0;
+      for (int i = 0; i < BKX_NAR_COUNT; ++i) reads += bs.nar[i];
+      atomicAdd((unsigned long long*)&stats->plus_hits, (unsigned long long)bs.plus);
+      atomicAdd((unsigned long long*)&stats->minus_hits, (unsigned long long)bs.minus);
+      atomicAdd((unsigned long long*)&stats->num_sloughed_ns, (unsigned long long)bs.nar[BKX_NAR_NS]);
+      atomicAdd((unsigned long long*)&stats->tot_non_aligned,
+                (unsigned long long)bs.nar[BKX_NAR_NOHIT] + bs.nar[BKX_NAR_MULTIALIGN]);
+      atomicAdd((unsigned long long*)&stats->tot_accepted_unique, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
+      atomicAdd((unsigned long long*)&stats->tot_accepted_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
+      atomicAdd((unsigned long long*)&stats->tot_loci_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
+      atomicAdd((unsigned long long*)&stats->tot_not_accepted_delta, (unsigned long long)bs.nar[BKX_NAR_MMDELTA]);
+      atomicAdd((unsigned long long*)&stats->seeds, bs.seeds);
+      atomicAdd((unsigned long long*)&stats->cands, bs.cands);
+      atomicAdd((unsigned long long*)&stats->reads, reads);
+    }
+  }
+}
+
+cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
+                         uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats, unsigned int* cursor,
+                         uint64_t* hash_pool, uint32_t hash_slots, uint32_t* epochs, int grid, cudaStream_t st) {
+  size_t smem = align_smem_bytes(W);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(align_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  align_reads_kernel<<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hash_pool,
+                                                        hash_slots, epochs);
+  return cudaGetLastError();
+}
+
+int align_blocks_per_sm(int W) {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_reads_kernel, kBlockThreads, align_smem_bytes(W));
+  return nb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Paired ends: AcceptProvPE / PEInsertSize and the per-pair state machine without orphan recovery
+// (Aligner.cpp:2726-2850, 3107-3216, 3421-3477).  One thread per pair.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pe_insert_size(const bkx_pe_params& pe, uint8_t s1, uint32_t st1, uint32_t en1,
+                                              uint8_t s2, uint32_t st2, uint32_t en2) {
+  if ((pe.pair_strand && s1 != s2) || (!pe.pair_strand && s1 == s2)) return -1;
+  int frag;
+  if (pe.circularised) frag = (s1 == '+') ? 1 + (int)en1 - (int)st2 : 1 + (int)st2 - (int)en1;
+  else frag = (s1 == '+') ? 1 + (int)en2 - (int)st1 : 1 + (int)en1 - (int)st2;
+  if (frag < 0) return -1;
+  if (frag < pe.pair_min_len) return -6;
+  if (frag > pe.pair_max_len) return -7;
+  return frag;
+}
+
+struct PEBlock { unsigned int v[8]; };
+
+__global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict__ res, uint32_t n_pairs,
+                                  bkx_pe_stats* __restrict__ stats, uint32_t* __restrict__ len_dist,
+                                  uint8_t* __restrict__ orphan_flag) {
+  __shared__ PEBlock pb;
+  if (threadIdx.x < 8) pb.v[threadIdx.x] = 0;
+  __syncthreads();
+  enum { UNAL = 0, ACCP = 1, ACCSE = 2, PPAIRED = 3, PUNP = 4, FILT = 5, UNDER = 6, OVER = 7 };
+  const int mode = pe.pe_proc;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+    bkx_read_result f = res[2 * i], r = res[2 * i + 1];
+    if (orphan_flag) orphan_flag[i] = 0;
+    f.flags &= (uint8_t)~(BKX_FLG_PE_ALIGNED | BKX_FLG_PE_RECOVERED);
+    r.flags &= (uint8_t)~(BKX_FLG_PE_ALIGNED | BKX_FLG_PE_RECOVERED);
+    bool f_un = f.nar == BKX_NAR_NS || f.nar == BKX_NAR_NOHIT || f.nar == BKX_NAR_UNALIGNED;
+    bool r_un = r.nar == BKX_NAR_NS || r.nar == BKX_NAR_NOHIT || r.nar == BKX_NAR_UNALIGNED;
+    bool done = false;
+    if (!(f.nar == BKX_NAR_ACCEPTED || r.nar == BKX_NAR_ACCEPTED)) {
+      atomicAdd(&pb.v[UNAL], 1u);
+      done = true;
+    } else if (mode == BKX_PE_UNIQUE && (f_un || r_un)) {
+      f.num_hits = r.num_hits = 0;
+      f.low_hit_instances = r.low_hit_instances = 0;
+      if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
+      if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
+      atomicAdd(&pb.v[PUNP], 1u);
+      done = true;
+    } else if (f.nar == BKX_NAR_ACCEPTED && r.nar == BKX_NAR_ACCEPTED) {
+      int frag;
+      if (!(f.num_hits == 1 && r.num_hits == 1)) frag = 0;
+      else if (f.chrom_id != r.chrom_id) frag = -2;
+      else frag = pe_insert_size(pe, f.strand, f.match_loci, f.match_loci + f.match_len - 1, r.strand, r.match_loci,
+                                 r.match_loci + r.match_len - 1);
+      if (frag > 0) {
+        f.flags |= BKX_FLG_PE_ALIGNED;
+        r.flags |= BKX_FLG_PE_ALIGNED;
+        if (len_dist) atomicAdd(len_dist + frag, 1u);
+        atomicAdd(&pb.v[ACCP], 1u);
+        done = true;
+      } else {
+        switch (frag) {
+          case -1: f.nar = r.nar = BKX_NAR_PESTRAND; break;
+          case -2: f.nar = r.nar = BKX_NAR_PECHROM; break;
+          case -6: f.nar = r.nar = BKX_NAR_PEINSERTMIN; break;
+          case -7: f.nar = r.nar = BKX_NAR_PEINSERTMAX; break;
+          default: break;
+        }
+        if (mode == BKX_PE_UNIQUE) {
+          f.num_hits = r.num_hits = 0;
+          f.low_hit_instances = r.low_hit_instances = 0;
+          if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
+          if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
+          atomicAdd(&pb.v[PUNP], 1u);
+          done = true;
+        }
+      }
+    }
+    if (!done) {
+      atomicAdd(&pb.v[PUNP], 1u);
+      if ((mode == BKX_PE_ORPHAN || mode == BKX_PE_ORPHAN_SE) && orphan_flag &&
+          ((f.num_hits == 1 && !r_un) || (r.num_hits == 1 && !f_un))) {
+        // orphan recovery is a separate (warp per orphan) kernel; it finishes this pair
+        orphan_flag[i] = 1;
+        res[2 * i] = f;
+        res[2 * i + 1] = r;
+        continue;
+      }
+      if (f.nar == BKX_NAR_CHROMFILT || r.nar == BKX_NAR_CHROMFILT) atomicAdd(&pb.v[FILT], 1u);
+      if (f.nar == BKX_NAR_PEINSERTMIN || r.nar == BKX_NAR_PEINSERTMIN) atomicAdd(&pb.v[UNDER], 1u);
+      if (f.nar == BKX_NAR_PEINSERTMAX || r.nar == BKX_NAR_PEINSERTMAX) atomicAdd(&pb.v[OVER], 1u);
+      if (!(mode == BKX_PE_ORPHAN_SE || mode == BKX_PE_UNIQUE_SE)) {
+        f.num_hits = r.num_hits = 0;
+        f.low_hit_instances = r.low_hit_instances = 0;
+        if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
+        if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
+      } else {
+        if (f.num_hits != 1) {
+          f.num_hits = 0; f.low_hit_instances = 0;
+          if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PEUNALIGN;
+        } else { f.nar = BKX_NAR_ACCEPTED; atomicAdd(&pb.v[ACCSE], 1u); }
+        if (r.num_hits != 1) {
+          r.num_hits = 0; r.low_hit_instances = 0;
+          if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PEUNALIGN;
+        } else { r.nar = BKX_NAR_ACCEPTED; atomicAdd(&pb.v[ACCSE], 1u); }
+      }
+    }
+    res[2 * i] = f;
+    res[2 * i + 1] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && stats) {
+    atomicAdd((unsigned long long*)&stats->unaligned_pairs, (unsigned long long)pb.v[UNAL]);
+    atomicAdd((unsigned long long*)&stats->accepted_num_paired, (unsigned long long)pb.v[ACCP]);
+    atomicAdd((unsigned long long*)&stats->accepted_num_se, (unsigned long long)pb.v[ACCSE]);
+    atomicAdd((unsigned long long*)&stats->partner_paired, (unsigned long long)pb.v[PPAIRED]);
+    atomicAdd((unsigned long long*)&stats->partner_unpaired, (unsigned long long)pb.v[PUNP]);
+    atomicAdd((unsigned long long*)&stats->num_filtered_by_chrom, (unsigned long long)pb.v[FILT]);
+    atomicAdd((unsigned long long*)&stats->under_len_pairs, (unsigned long long)pb.v[UNDER]);
+    atomicAdd((unsigned long long*)&stats->over_len_pairs, (unsigned long long)pb.v[OVER]);
+  }
+}
+
+cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,
+                        uint32_t* len_dist, uint8_t* orphan_flag, cudaStream_t st) {
+  int grid = (int)((n_pairs + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  pair_reads_kernel<<<grid, 256, 0, st>>>(pe, res, n_pairs, stats, len_dist, orphan_flag);
+  return cudaGetLastError();
+}
+
+}  // namespace bkx

@@ -1,0 +1,201 @@
+"""ctypes binding of libbkx.so -- the C-ABI library that holds the CUDA hot path (include/bkx.h).
+
+This is the only way Python reaches the kernels; it fails loudly when the library or a CUDA device is
+missing.  There is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbkx.so")
+_LIB = None
+
+EXPORTS = [
+    "bkx_abi_version", "bkx_last_error", "bkx_device_count", "bkx_open_index", "bkx_open_index_mem",
+    "bkx_open_index_dev", "bkx_clone_index", "bkx_close_index", "bkx_index_info_get", "bkx_get_entry",
+    "bkx_get_ident", "bkx_get_seq", "bkx_default_params", "bkx_align_reads", "bkx_align_reads_device",
+    "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
+]
+
+
+class BkxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bkx error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile libbkx.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("building libbkx.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise BkxError(-5, "libbkx.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "-- there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.bkx_abi_version.restype = i32
+    L.bkx_last_error.restype = C.c_char_p
+    L.bkx_device_count.restype = i32
+    L.bkx_open_index.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.bkx_open_index_mem.argtypes = [vp, u64, vp, u32, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.bkx_open_index_dev.argtypes = [vp, u64, vp, u32, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.bkx_clone_index.argtypes = [vp, i32, C.POINTER(vp)]
+    L.bkx_close_index.argtypes = [vp]
+    L.bkx_close_index.restype = None
+    L.bkx_index_info_get.argtypes = [vp, C.POINTER(abi.IndexInfo)]
+    L.bkx_get_entry.argtypes = [vp, u32, C.POINTER(abi.Entry)]
+    L.bkx_get_ident.argtypes = [vp, C.c_char_p]
+    L.bkx_get_seq.argtypes = [vp, u32, u64, u64, vp]
+    L.bkx_get_seq.restype = C.c_int64
+    L.bkx_default_params.argtypes = [vp, i32, C.POINTER(abi.AlignParams)]
+    L.bkx_align_reads.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
+    L.bkx_align_reads_device.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, u32, vp, vp, vp]
+    L.bkx_align_one.argtypes = [vp, C.POINTER(abi.AlignParams), vp, i32, C.POINTER(i32), C.POINTER(i32),
+                                C.POINTER(i32), vp]
+    L.bkx_pair_reads.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, u32, vp, vp,
+                                 C.POINTER(abi.PEStats), vp]
+    L.bkx_last_kernel_ms.argtypes = [vp]
+    L.bkx_last_kernel_ms.restype = C.c_float
+    L.bkx_kernel_launches.argtypes = [vp]
+    L.bkx_kernel_launches.restype = u64
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc < 0:
+        raise BkxError(rc, lib().bkx_last_error().decode(errors="replace"))
+    return rc
+
+
+class Index:
+    """Device-resident index: the CSfxArrayV3 stand-in (Open/SetTargBlock/getters), SfxArrayV2.h:488-990."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.info = abi.IndexInfo()
+        check(lib().bkx_index_info_get(self._h, C.byref(self.info)))
+
+    @classmethod
+    def open(cls, sfx_path, device=0, prefix_k=0):
+        h = C.c_void_p()
+        check(lib().bkx_open_index(os.fsencode(sfx_path), device, prefix_k, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_host(cls, seq, sa, el_size, entries, name="mem", device=0, prefix_k=0):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        sa = np.ascontiguousarray(sa)
+        entries = np.ascontiguousarray(entries, dtype=abi.ENTRY_DTYPE)
+        h = C.c_void_p()
+        check(lib().bkx_open_index_mem(seq.ctypes.data, seq.size, sa.ctypes.data, el_size, entries.ctypes.data,
+                                       len(entries), name.encode(), device, prefix_k, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_device(cls, d_seq_ptr, concat_len, d_sa_ptr, el_size, entries, name="dev", device=0, prefix_k=0):
+        entries = np.ascontiguousarray(entries, dtype=abi.ENTRY_DTYPE)
+        h = C.c_void_p()
+        check(lib().bkx_open_index_dev(d_seq_ptr, concat_len, d_sa_ptr, el_size, entries.ctypes.data, len(entries),
+                                       name.encode(), device, prefix_k, C.byref(h)))
+        return cls(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().bkx_close_index(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- getters (GetIdentName / GetSeqLen / GetIdent / GetSeq) ---
+    def entry(self, entry_id):
+        e = abi.Entry()
+        check(lib().bkx_get_entry(self._h, entry_id, C.byref(e)))
+        return e
+
+    def entries(self):
+        return [self.entry(i) for i in range(1, self.info.num_entries + 1)]
+
+    def ident(self, name):
+        return check(lib().bkx_get_ident(self._h, name.encode()))
+
+    def get_seq(self, entry_id, loci, length):
+        buf = np.empty(length, dtype=np.uint8)
+        n = check(lib().bkx_get_seq(self._h, entry_id, loci, length, buf.ctypes.data))
+        return buf[:n]
+
+    def default_params(self, pmode=0, **kw):
+        p = abi.AlignParams()
+        check(lib().bkx_default_params(self._h, pmode, C.byref(p)))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    # --- the hot path ---
+    def align(self, params, bases, offsets, out=None, stats=None):
+        """Host buffers in, host records out (H2D + kernels + D2H inside)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        if out is None:
+            out = np.zeros(n, dtype=abi.RESULT_DTYPE)
+        st = stats if stats is not None else abi.AlignStats()
+        check(lib().bkx_align_reads(self._h, C.byref(params), bases.ctypes.data, offsets.ctypes.data, n,
+                                    out.ctypes.data, C.byref(st)))
+        return out, st
+
+    def align_ptr(self, params, bases_ptr, offsets_ptr, n_reads, out_ptr, stats=None):
+        """Same, raw host pointers (pinned buffers owned by the caller)."""
+        st = C.byref(stats) if stats is not None else None
+        check(lib().bkx_align_reads(self._h, C.byref(params), bases_ptr, offsets_ptr, n_reads, out_ptr, st))
+
+    def align_device(self, params, d_bases, d_offsets, n_reads, max_read_len, d_out, d_stats=None, stream=None):
+        """Device pointers, asynchronous on `stream` (a raw cudaStream_t value or None)."""
+        check(lib().bkx_align_reads_device(self._h, C.byref(params), d_bases, d_offsets, n_reads, max_read_len,
+                                           d_out, d_stats, stream))
+
+    def align_one(self, params, probe):
+        probe = np.ascontiguousarray(probe, dtype=np.uint8)
+        hit = np.zeros(1, dtype=abi.RESULT_DTYPE)
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        hr = check(lib().bkx_align_one(self._h, C.byref(params), probe.ctypes.data, len(probe), C.byref(a),
+                                       C.byref(b), C.byref(c), hit.ctypes.data))
+        return hr, (a.value, b.value, c.value), hit[0]
+
+    def pair(self, params, pe, results, bases=None, offsets=None, len_dist=None):
+        n_pairs = len(results) // 2
+        st = abi.PEStats()
+        b = np.ascontiguousarray(bases, dtype=np.uint8).ctypes.data if bases is not None else None
+        o = np.ascontiguousarray(offsets, dtype=np.uint64).ctypes.data if offsets is not None else None
+        ld = len_dist.ctypes.data if len_dist is not None else None
+        check(lib().bkx_pair_reads(self._h, C.byref(params), C.byref(pe), results.ctypes.data, n_pairs, b, o,
+                                   C.byref(st), ld))
+        return st
+
+    def last_kernel_ms(self):
+        return float(lib().bkx_last_kernel_ms(self._h))
+
+    def kernel_launches(self):
+        return int(lib().bkx_kernel_launches(self._h))

@@ -1,0 +1,200 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE: generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference binary (oracle/_ref/biokanga, built by oracle/build_ref.sh) on seeded synthetic inputs.
+
+The reference ships no tests or fixtures, so these outputs are the pin for the
+CPU oracle and, through it, for the CUDA path.  Run in the build container (needs /root/reference
+only to build oracle/_ref once):
+
+    python oracle/make_fixtures.py            # regenerates every case
+
+Each case directory holds: genome.fa.gz, the .sfx written by `biokanga index` (gzip), read files,
+and per run <tag>.sam.gz (-M6: every read with its YU:Z: class), <tag>.csv.gz (-M0: mismatch counts)
+and <tag>.log (alignment summary).  Sizes are kept to a few hundred kB per case.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import synth  # noqa: E402
+
+REF = os.path.join(HERE, "_ref", "biokanga")
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def run(args, cwd):
+    r = subprocess.run([REF] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout.decode(errors="replace")[-3000:])
+        raise SystemExit("reference failed: %s" % " ".join(args))
+
+
+def gz(src, dst):
+    with open(src, "rb") as f, gzip.GzipFile(dst, "wb", mtime=0) as g:
+        shutil.copyfileobj(f, g)
+
+
+def strip_log(src, dst):
+    """Keep the alignment-summary block of the log without timestamps (they differ per run)."""
+    keep = []
+    on = False
+    for ln in open(src, errors="replace"):
+        body = ln.split("](biokanga) ", 1)[1] if "](biokanga) " in ln else ln
+        if "Alignment of" in body and "completed" in body:
+            on = True
+        if on and ("Reporting of aligned result set" in body or "Exit code" in body or "Total processing" in body):
+            continue
+        if on:
+            keep.append(body.rstrip("\n"))
+    open(dst, "w").write("\n".join(keep) + "\n")
+
+
+def align_runs(case_dir, tmp, sfx, runs):
+    meta = {}
+    for tag, r in runs.items():
+        common = ["align", "-I", sfx, "-i", r["reads"][0], "-T4"] + r["args"]
+        if len(r["reads"]) > 1:
+            common += ["-u", r["reads"][1]]
+        run(common + ["-M6", "-o", tag + ".sam", "-F", tag + ".sam.log"], tmp)
+        run(common + ["-M0", "-o", tag + ".csv", "-F", tag + ".log"], tmp)
+        gz(os.path.join(tmp, tag + ".sam"), os.path.join(case_dir, tag + ".sam.gz"))
+        gz(os.path.join(tmp, tag + ".csv"), os.path.join(case_dir, tag + ".csv.gz"))
+        strip_log(os.path.join(tmp, tag + ".log"), os.path.join(case_dir, tag + ".log"))
+        meta[tag] = {"reads": [os.path.basename(x) + ".gz" for x in r["reads"]], "args": r["args"]}
+    json.dump(meta, open(os.path.join(case_dir, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
+def case_tiny():
+    """40 kbp, 4 chromosomes (one 300 bp contig), diverged repeats, one 60-N run."""
+    d = os.path.join(GOLD, "tiny")
+    os.makedirs(d, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        g = synth.make_genome([20000, 15000, 5000, 300], seed=11, repeat_frac=0.15, repeat_len=(100, 800), n_runs=1)
+        synth.write_fasta(os.path.join(tmp, "genome.fa"), g)
+        run(["index", "-i", "genome.fa", "-o", "tiny.sfx", "-r", "tiny", "-F", "idx.log"], tmp)
+        sets = {
+            "r100": dict(n=3000, length=100, seed=12, subs=(0, 1, 2, 3, 4, 5), boundary_frac=0.01),
+            "r50": dict(n=1500, length=50, seed=13, subs=(0, 1, 2, 3, 4), boundary_frac=0.01),
+            "r150": dict(n=1500, length=150, seed=14, subs=(0, 1, 2, 3, 4, 5, 6, 8), boundary_frac=0.01),
+            "r251": dict(n=600, length=251, seed=15, subs=(0, 2, 5, 9, 14), boundary_frac=0.01),
+        }
+        for nm, kw in sets.items():
+            n, r = synth.sim_reads(g, **kw)
+            synth.write_reads_fasta(os.path.join(tmp, nm + ".fa"), n, r)
+            gz(os.path.join(tmp, nm + ".fa"), os.path.join(d, nm + ".fa.gz"))
+        # mixed-length FASTQ set (exercises ragged batches + FASTQ parsing)
+        rng = np.random.default_rng(16)
+        names, reads = [], []
+        for i in range(800):
+            L = int(rng.integers(50, 301))
+            n1, r1 = synth.sim_reads(g, 1, L, seed=1000 + i, subs=(0, 1, 2, 3), junk_frac=0.05, n_frac=0.05)
+            names.append("m%d|%s" % (i + 1, n1[0]))
+            reads.append(r1[0])
+        synth.write_reads_fastq(os.path.join(tmp, "mixed.fq"), names, reads)
+        gz(os.path.join(tmp, "mixed.fq"), os.path.join(d, "mixed.fq.gz"))
+        # PE set
+        n1, r1, n2, r2 = synth.sim_reads(g, 2000, 100, seed=17, subs=(0, 1, 2, 3), pe=True, insert=(150, 450),
+                                         junk_frac=0.05)
+        synth.write_reads_fasta(os.path.join(tmp, "pe1.fa"), n1, r1)
+        synth.write_reads_fasta(os.path.join(tmp, "pe2.fa"), n2, r2)
+        gz(os.path.join(tmp, "pe1.fa"), os.path.join(d, "pe1.fa.gz"))
+        gz(os.path.join(tmp, "pe2.fa"), os.path.join(d, "pe2.fa.gz"))
+        gz(os.path.join(tmp, "genome.fa"), os.path.join(d, "genome.fa.gz"))
+        gz(os.path.join(tmp, "tiny.sfx"), os.path.join(d, "tiny.sfx.gz"))
+        runs = {
+            "r100_s3": {"reads": ["r100.fa"], "args": ["-s3"]},
+            "r100_s5_e2": {"reads": ["r100.fa"], "args": ["-s5", "-e2"]},
+            "r100_s0": {"reads": ["r100.fa"], "args": ["-s0"]},
+            "r100_s3_n5": {"reads": ["r100.fa"], "args": ["-s3", "-n5"]},
+            "r100_s4_m1": {"reads": ["r100.fa"], "args": ["-s4", "-m1"]},
+            "r100_s4_m2": {"reads": ["r100.fa"], "args": ["-s4", "-m2"]},
+            "r100_s4_m3": {"reads": ["r100.fa"], "args": ["-s4", "-m3"]},
+            "r100_s3_Q1": {"reads": ["r100.fa"], "args": ["-s3", "-Q1"]},
+            "r100_s3_Q2": {"reads": ["r100.fa"], "args": ["-s3", "-Q2"]},
+            "r50_s8": {"reads": ["r50.fa"], "args": ["-s8"]},
+            "r50_s8_e2": {"reads": ["r50.fa"], "args": ["-s8", "-e2"]},
+            "r150_s3": {"reads": ["r150.fa"], "args": ["-s3"]},
+            "r150_s5_e2": {"reads": ["r150.fa"], "args": ["-s5", "-e2"]},
+            "r251_s6": {"reads": ["r251.fa"], "args": ["-s6"]},
+            "mixed_s3": {"reads": ["mixed.fq"], "args": ["-s3", "-n2"]},
+            "pe_U2": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U2", "-d100", "-D1000"]},
+            "pe_U4": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U4", "-d100", "-D400"]},
+            "pe_U1": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U1", "-d100", "-D600"]},
+            "pe_U3": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U3", "-d120", "-D500"]},
+            "pe_U1_far": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U1", "-d100", "-D1500"]},
+        }
+        align_runs(d, tmp, "tiny.sfx", runs)
+
+
+def case_repeats():
+    """~300 kbp with interspersed high-copy short repeats: exercises the 100-candidate probe,
+    the MaxIter cap (2500 with -m3, 5000 default) and multi-loci classes."""
+    d = os.path.join(GOLD, "repeats")
+    os.makedirs(d, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.default_rng(21)
+        unit_a = rng.integers(0, 4, 64, dtype=np.uint8)     # ~3000 copies, ~2850 exact per 25-mer (> 2500, < 5000)
+        unit_b = rng.integers(0, 4, 90, dtype=np.uint8)     # ~400 copies   (> 100)
+        unit_c = rng.integers(0, 4, 120, dtype=np.uint8)    # ~60 copies    (< 100)
+        parts = []
+
+        def emit(unit, copies, div):
+            for _ in range(copies):
+                u = unit.copy()
+                if div > 0:
+                    m = rng.random(len(u)) < div
+                    u[m] = (u[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+                parts.append(u)
+                parts.append(rng.integers(0, 4, int(rng.integers(20, 50)), dtype=np.uint8))
+
+        emit(unit_a, 3000, 0.002)
+        emit(unit_b, 400, 0.02)
+        emit(unit_c, 60, 0.0)
+        order = rng.permutation(len(parts) // 2)
+        shuffled = []
+        for k in order:
+            shuffled.append(parts[2 * k])
+            shuffled.append(parts[2 * k + 1])
+        body = np.concatenate(shuffled)
+        uniq = rng.integers(0, 4, 40000, dtype=np.uint8)
+        half = len(body) // 2
+        g = [("rep1", np.concatenate([uniq[:20000], body[:half]])), ("rep2", np.concatenate([body[half:], uniq[20000:]]))]
+        synth.write_fasta(os.path.join(tmp, "genome.fa"), g)
+        run(["index", "-i", "genome.fa", "-o", "repeats.sfx", "-r", "repeats", "-F", "idx.log"], tmp)
+        n, r = synth.sim_reads(g, 4000, 100, seed=22, subs=(0, 1, 2, 3), junk_frac=0.01, n_frac=0.01)
+        synth.write_reads_fasta(os.path.join(tmp, "r100.fa"), n, r)
+        n, r = synth.sim_reads(g, 2000, 60, seed=23, subs=(0, 1, 2), junk_frac=0.01, n_frac=0.01)
+        synth.write_reads_fasta(os.path.join(tmp, "r60.fa"), n, r)
+        for f in ("r100.fa", "r60.fa", "genome.fa"):
+            gz(os.path.join(tmp, f), os.path.join(d, f + ".gz"))
+        gz(os.path.join(tmp, "repeats.sfx"), os.path.join(d, "repeats.sfx.gz"))
+        runs = {
+            "r100_s3": {"reads": ["r100.fa"], "args": ["-s3"]},
+            "r100_s5_e2": {"reads": ["r100.fa"], "args": ["-s5", "-e2"]},
+            "r100_s3_m3": {"reads": ["r100.fa"], "args": ["-s3", "-m3"]},
+            "r100_s3_m2": {"reads": ["r100.fa"], "args": ["-s3", "-m2"]},
+            "r60_s5": {"reads": ["r60.fa"], "args": ["-s5"]},
+            "r60_s5_e2_m3": {"reads": ["r60.fa"], "args": ["-s5", "-e2", "-m3"]},
+        }
+        align_runs(d, tmp, "repeats.sfx", runs)
+
+
+if __name__ == "__main__":
+    if not os.path.exists(REF):
+        raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
+    which = sys.argv[1:] or ["tiny", "repeats"]
+    if "tiny" in which:
+        case_tiny()
+    if "repeats" in which:
+        case_repeats()
+    print("fixtures written under", GOLD)
