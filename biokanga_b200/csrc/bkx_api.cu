@@ -22,7 +22,7 @@ using namespace bkx;
 
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...) {
+int bkx_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -31,6 +31,8 @@ static int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+
+#define fail bkx_fail
 
 #define CU(call)                                                                                      \
   do {                                                                                                \

@@ -22,6 +22,7 @@ EXPORTS = [
     "bkx_open_index_dev", "bkx_clone_index", "bkx_close_index", "bkx_index_info_get", "bkx_get_entry",
     "bkx_get_ident", "bkx_get_seq", "bkx_default_params", "bkx_align_reads", "bkx_align_reads_device",
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
+    "bkx_build_suffix_array_device", "bkx_write_sfx",
 ]
 
 
@@ -72,6 +73,8 @@ def lib():
                                 C.POINTER(i32), vp]
     L.bkx_pair_reads.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, u32, vp, vp,
                                  C.POINTER(abi.PEStats), vp]
+    L.bkx_build_suffix_array_device.argtypes = [vp, u64, vp, i32]
+    L.bkx_write_sfx.argtypes = [C.c_char_p, vp, u64, vp, u32, vp, u32, C.c_char_p]
     L.bkx_last_kernel_ms.argtypes = [vp]
     L.bkx_last_kernel_ms.restype = C.c_float
     L.bkx_kernel_launches.argtypes = [vp]
@@ -84,6 +87,20 @@ def check(rc):
     if rc < 0:
         raise BkxError(rc, lib().bkx_last_error().decode(errors="replace"))
     return rc
+
+
+def build_suffix_array_device(d_seq_ptr, concat_len, d_sa_ptr, device=0):
+    """GPU suffix-array construction (device pointers; u32 elements out)."""
+    check(lib().bkx_build_suffix_array_device(d_seq_ptr, concat_len, d_sa_ptr, device))
+
+
+def write_sfx(path, seq, sa, el_size, entries, name="bkx"):
+    """Write a version-5 .sfx file (the container `biokanga index` produces)."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    sa = np.ascontiguousarray(sa)
+    entries = np.ascontiguousarray(entries, dtype=abi.ENTRY_DTYPE)
+    check(lib().bkx_write_sfx(os.fsencode(path), seq.ctypes.data, seq.size, sa.ctypes.data, el_size,
+                              entries.ctypes.data, len(entries), name.encode()))
 
 
 class Index:

@@ -213,6 +213,15 @@ int bkx_pair_reads(bkx_index* idx, const bkx_align_params* p, const bkx_pe_param
                    uint32_t n_pairs, const uint8_t* bases, const uint64_t* offsets, bkx_pe_stats* stats,
                    uint32_t* len_dist);
 
+/* ---- index construction for synthetic / bench genomes: the two halves of `biokanga index` ---------
+ * (kangax.cpp:774-926 -> CSfxArrayV3::QSortSeq, SfxArrayV2.cpp:9451-9542; file layout SfxArrayV2.h:79-104,
+ * 174-187).  d_seq: device, 1 byte/base incl. one EOS(7) after every entry; d_sa: device, concat_len
+ * u32 elements out, sorted like the reference sorts (4-bit symbol order, through the terminators). */
+int bkx_build_suffix_array_device(const uint8_t* d_seq, uint64_t concat_len, uint32_t* d_sa, int device);
+/* Write host-resident sequence + suffix array as a version-5 .sfx the reference's `biokanga align` loads. */
+int bkx_write_sfx(const char* path, const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t sfx_el_size,
+                  const bkx_entry* entries, uint32_t num_entries, const char* dataset_name);
+
 /* ---- instrumentation -------------------------------------------------------------------------- */
 /* Device time (ms) of the kernels of the last bkx_align_reads* call on this index, measured with
  * CUDA events on the launching stream; <0 if none. */
