@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- aligned reads/s of the `biokanga align` hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl bkx|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- a 3.1 Gbp human-sized synthetic genome with
+injected diverged repeats, 20 M simulated 150 bp SE reads carrying 0..4 substitutions, aligned with
+`-s3` (MaxTotMM 5 at 150 bp).  Genome, suffix array (GPU prefix doubling)
+and reads are generated on the device with fixed seeds; there are no datasets to download.
+
+A "step" is one pass of the align hot path over the rank's 20 M reads.
+  value     reads/s with reads already resident in HBM (device-pointer C-ABI entry, CUDA events)
+  e2e       the same metric through bkx_align_reads() with pinned HOST buffers: H2D of the reads and
+            D2H of the 32-byte records are inside the timed region
+  roofline  algorithmic bytes of one launch / measured kernel time / measured HBM peak
+  cpu_baseline  the CPU restatement (oracle/, "port") on a bounded sample with all host cores
+N > 1 (torchrun): rank 0 builds the index and broadcasts it over NCCL/NVLink; every rank aligns its
+own 20 M reads (weak scaling); the stats vector is all-reduced each step; time = max over ranks.
+
+--impl reference: the UNMODIFIED reference binary (oracle/_ref/biokanga, built from /root/reference
+by oracle/build_ref.sh) run with all host threads on a bounded sample of the same workload; align-phase
+time from its own log timestamps.  Falls back to the oracle port when the binary is absent.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_workload(args, rank, world, dev, torch, dist):
+    """Genome + SA on the device (rank 0 builds, others receive over NCCL), then this rank's reads."""
+    from biokanga_b200 import lib as bkx
+    from biokanga_b200 import workload as wl
+    lens = wl.chrom_layout(int(args.genome_mbp * 1e6))
+    ents, n = wl.entries_for(lens)
+    t0 = time.time()
+    if rank == 0:
+        d_seq, ents = wl.make_genome(lens, seed=args.seed, device=dev)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        d_sa = torch.empty(n, dtype=torch.int32, device=dev)
+        bkx.build_suffix_array_device(d_seq.data_ptr(), n, d_sa.data_ptr(), torch.cuda.current_device())
+        torch.cuda.synchronize()
+        log("[bench] genome %.2f Gsym in %.1fs, suffix array in %.1fs" % (n / 1e9, t1 - t0, time.time() - t1))
+    else:
+        d_seq = torch.empty(n, dtype=torch.uint8, device=dev)
+        d_sa = torch.empty(n, dtype=torch.int32, device=dev)
+    if world > 1:  # index replication GPU0 -> all over NVLink (NCCL broadcast)
+        tb = time.time()
+        dist.broadcast(d_seq, 0)
+        dist.broadcast(d_sa, 0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            log("[bench] index broadcast to %d GPUs in %.2fs" % (world, time.time() - tb))
+    d_bases, d_offs = wl.sim_reads(d_seq, ents, args.reads, args.read_len, seed=args.seed + 100 + rank,
+                                   subs=tuple(range(0, args.read_subs + 1)), device=dev)
+    torch.cuda.synchronize()
+    return d_seq, d_sa, ents, n, d_bases, d_offs
+
+
+def run_bkx(args):
+    import torch
+    import torch.distributed as dist
+    from biokanga_b200 import abi
+    from biokanga_b200 import lib as bkx
+    from biokanga_b200 import workload as wl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the bkx path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    d_seq, d_sa, ents, n, d_bases, d_offs = build_workload(args, rank, world, dev, torch, dist)
+    t0 = time.time()
+    idx = bkx.Index.from_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 4, ents, name="synth%dM" % args.genome_mbp,
+                                device=local, prefix_k=args.prefix_k)
+    torch.cuda.synchronize()
+    log("[bench] rank %d index resident: %.1f GB HBM, prefix k=%d, %.1fs" % (rank, idx.info.device_bytes / 1e9,
+                                                                          idx.info.prefix_k, time.time() - t0))
+    host_seq = host_sa = None
+    if rank == 0 and not args.no_cpu_baseline:
+        host_seq = d_seq.cpu().numpy()
+        host_sa = d_sa.cpu().numpy().view(np.uint32)
+    del d_seq, d_sa
+    torch.cuda.empty_cache()
+
+    p = idx.default_params(0, max_subs=args.max_subs)
+    nreads = args.reads
+    d_out = torch.empty(nreads * 32, dtype=torch.uint8, device=dev)
+    d_stats = torch.zeros(C.sizeof(abi.AlignStats) // 8, dtype=torch.int64, device=dev)
+    # a dedicated (non-default) stream: launches, events and NCCL all ride on it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+
+    def step():
+        d_stats.zero_()
+        idx.align_device(p, d_bases.data_ptr(), d_offs.data_ptr(), nreads, args.read_len, d_out.data_ptr(),
+                         d_stats.data_ptr(), stream)
+        if world > 1:
+            dist.all_reduce(d_stats)  # the only collective of the path: global stats counters
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kern_ms = []
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+        if args.kernel_times:
+            kern_ms.append(idx.last_kernel_ms())  # syncs on the kernel's own events
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    if not kern_ms:
+        # one extra, untimed launch gives the kernel's own event-measured duration
+        step()
+        torch.cuda.synchronize()
+        kern_ms = [idx.last_kernel_ms()]
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    ms_per_step = total_ms / args.steps
+    value = world * nreads / (ms_per_step / 1e3)
+
+    res = d_out.cpu().numpy().view(abi.RESULT_DTYPE)
+    stats = d_stats.cpu().numpy()
+    alg_bytes = wl.algorithmic_bytes(res, n, 4, args.read_len)
+    kms = float(np.mean(kern_ms))
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kms / 1e3) / 1e9
+    nar = np.bincount(res["nar"], minlength=abi.NAR_COUNT)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    h_bases = torch.empty(nreads * args.read_len, dtype=torch.uint8).pin_memory()
+    h_bases.copy_(d_bases)
+    h_offs = torch.arange(nreads + 1, dtype=torch.int64) * args.read_len
+    h_out = torch.empty(nreads * 32, dtype=torch.uint8).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+    hst = abi.AlignStats()
+    idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * nreads / float(te.item())
+    same = bool(np.array_equal(h_out.numpy().view(abi.RESULT_DTYPE)["match_loci"], res["match_loci"]))
+
+    line = {
+        "metric": "aligned reads/sec (150bp, <=4 subs)", "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[1]: %.1f Gbp synthetic genome + injected repeats, %d x %d bp SE reads per GPU, "
+                               "0..%d subs, -s%d" % (args.genome_mbp / 1e3, nreads, args.read_len, args.read_subs,
+                                                      args.max_subs),
+                   "genome_symbols": int(n), "reads_per_gpu": nreads, "read_len": args.read_len,
+                   "max_subs_per_100bp": args.max_subs, "prefix_k": int(idx.info.prefix_k),
+                   "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (
+                       idx.info.device_bytes / 1e9, nreads * args.read_len / 1e9),
+                   "parallelism": "reads sharded over %d GPU(s), index replicated" % world},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(nreads * args.read_len + (nreads + 1) * 8),
+                "d2h_bytes_per_step": int(nreads * 32), "matches_device_run": same},
+        "gpu_launches": int(args.steps),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "align_reads_kernel", "kernel_ms": kms,
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "bytes_per_read": alg_bytes / nreads,
+                     "peak_source": peak_src},
+        "clocks": clocks,
+        "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]},
+        "stats_reads_all_ranks": int(stats[-1]),
+    }
+
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_port(args, host_seq, host_sa, ents, h_bases.numpy(), res)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_port(args, host_seq, host_sa, ents, h_bases, gpu_res):
+    """The CPU restatement on a bounded sample of the same reads, all host cores; also re-checks parity."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    cores = os.cpu_count() or 1
+    oidx = po.OracleIndex(seq=host_seq, sa=host_sa, el_size=4, entries=ents)
+    p = oidx.default_params(0, max_subs=args.max_subs)
+    m = min(args.cpu_sample, args.reads)
+    L = args.read_len
+    bases = h_bases[:m * L]
+    offs = (np.arange(m + 1, dtype=np.uint64) * L)
+    t0 = time.perf_counter()
+    res, st = oidx.align(p, bases, offs, nthreads=cores)
+    dt = time.perf_counter() - t0
+    ok = all(np.array_equal(res[f], gpu_res[f][:m]) for f in ("nar", "strand", "chrom_id", "match_loci", "mismatches",
+                                                              "low_hit_instances", "seeds", "cands"))
+    return {"value": m / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+            "sample": "first %d of the %d reads, %.1fs" % (m, args.reads, dt), "parity_with_gpu": bool(ok)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation on the box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import torch
+    from biokanga_b200 import abi
+    from biokanga_b200 import lib as bkx
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    import synth
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "needs the GPU box to generate the 3.1 Gbp workload"}))
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    cores = os.cpu_count() or 1
+    total_steps = args.steps + args.warmup
+    sample = args.ref_sample
+    if total_steps > 6:
+        sample = max(150000, int(sample * 6 / total_steps))
+    saved_reads = args.reads
+    args.reads = sample * total_steps
+    d_seq, d_sa, ents, n, d_bases, d_offs = build_workload(args, 0, 1, dev, torch, None)
+    host_seq = d_seq.cpu().numpy()
+    host_sa = d_sa.cpu().numpy().view(np.uint32)
+    h_bases = d_bases.cpu().numpy()
+    del d_seq, d_sa, d_bases
+    torch.cuda.empty_cache()
+    L = args.read_len
+    use_bin = os.path.exists(po.REF_BIN) and not args.ref_port
+    times = []
+    if use_bin:
+        tmp = tempfile.mkdtemp(prefix="bkxref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            t0 = time.time()
+            bkx.write_sfx(os.path.join(tmp, "g.sfx"), host_seq, host_sa, 4, ents, name="synth")
+            log("[bench] wrote %.1f GB .sfx in %.1fs" % (os.path.getsize(os.path.join(tmp, "g.sfx")) / 1e9, time.time() - t0))
+            del host_seq, host_sa
+            for s in range(total_steps):
+                rd = h_bases[s * sample * L:(s + 1) * sample * L].reshape(sample, L)
+                with open(os.path.join(tmp, "r.fa"), "wb") as f:
+                    asc = synth.BASES[rd]
+                    for i in range(sample):
+                        f.write(b">r%d\n" % (i + 1) + asc[i].tobytes() + b"\n")
+                subprocess.run([po.REF_BIN, "align", "-I", "g.sfx", "-i", "r.fa", "-s%d" % args.max_subs, "-M0", "-o",
+                                "out.csv", "-F", "run.log", "-T%d" % min(cores, 128)], cwd=tmp, check=True,
+                               stdout=subprocess.DEVNULL)
+                ts = {}
+                for ln in open(os.path.join(tmp, "run.log"), errors="replace"):
+                    m = re.match(r"\[\w+ \w+ +\d+ (\d+):(\d+):(\d+)\.(\d+) \d+\]", ln)
+                    if not m:
+                        continue
+                    t = int(m.group(1)) * 3600 + int(m.group(2)) * 60 + int(m.group(3)) + int(m.group(4)) / 1000.0
+                    if "Now aligning with minimum core size" in ln:
+                        ts["a"] = t
+                    if "Alignment of" in ln and "completed" in ln:
+                        ts["b"] = t
+                dt = (ts["b"] - ts["a"]) % 86400
+                log("[bench] reference step %d: %d reads, align phase %.2fs" % (s, sample, dt))
+                if s >= args.warmup:
+                    times.append(dt)
+        finally:
+            subprocess.run(["rm", "-rf", tmp])
+        kind = "reference"
+    else:
+        oidx = po.OracleIndex(seq=host_seq, sa=host_sa, el_size=4, entries=ents)
+        p = oidx.default_params(0, max_subs=args.max_subs)
+        for s in range(total_steps):
+            bases = h_bases[s * sample * L:(s + 1) * sample * L]
+            offs = np.arange(sample + 1, dtype=np.uint64) * L
+            t0 = time.perf_counter()
+            oidx.align(p, bases, offs, nthreads=cores)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+        kind = "port"
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "aligned reads/sec (150bp, <=4 subs)", "value": value, "unit": "reads/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "configs[1]: %.1f Gbp synthetic genome + injected repeats, %d bp SE reads, 0..%d subs, "
+                               "-s%d; each step a bounded sample of %d reads" % (args.genome_mbp / 1e3, L,
+                                                                                 args.read_subs, args.max_subs, sample),
+                   "genome_symbols": int(n), "read_len": L, "max_subs_per_100bp": args.max_subs},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind,
+                         "sample": "%d reads per step; align phase from the reference's log timestamps" % sample
+                         if kind == "reference" else "%d reads per step, %d threads" % (sample, cores)},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    args.reads = saved_reads
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bkx", choices=["bkx", "reference"])
+    ap.add_argument("--genome-mbp", type=float, default=3100.0)
+    ap.add_argument("--reads", type=int, default=20_000_000)
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--read-subs", type=int, default=4, help="reads carry 0..this many substitutions")
+    ap.add_argument("--max-subs", type=int, default=3, help="-s: allowed substitutions per 100 bp")
+    ap.add_argument("--prefix-k", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--cpu-sample", type=int, default=300000)
+    ap.add_argument("--ref-sample", type=int, default=400000)
+    ap.add_argument("--ref-port", action="store_true", help="reference arm: use the oracle port even if the binary exists")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-times", action="store_true", help="read the kernel's own events after every step")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "bkx":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_bkx(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""Synthetic workloads generated on the GPU with torch (plumbing for bench.py and the scale tests):
+human-sized random genomes with injected diverged repeats and reads
+drawn from them with a controlled number of substitutions.  Deterministic for a given seed.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import abi
+
+
+def chrom_layout(total_bp, n_chrom=24, short_contigs=(50000, 20000, 5000, 2000, 700)):
+    """Human-like: n_chrom large chromosomes of decreasing size plus a few short contigs."""
+    w = np.linspace(2.0, 0.6, n_chrom)
+    big = total_bp - sum(short_contigs)
+    lens = [int(big * x / w.sum()) for x in w]
+    lens[0] += big - sum(lens)
+    lens += [int(x) for x in short_contigs if x < total_bp // 50]
+    return lens
+
+
+def entries_for(lens):
+    ents = np.zeros(len(lens), dtype=abi.ENTRY_DTYPE)
+    ofs = 0
+    for i, ln in enumerate(lens):
+        ents[i] = (i + 1, ln, ofs, ofs + ln - 1, ("chr%d" % (i + 1)).encode())
+        ofs += ln + 1
+    return ents, ofs
+
+
+def make_genome(lens, seed=1, device="cuda", repeat_frac=0.05, repeat_len=(300, 5000),
+                divergences=(0.0, 0.005, 0.01, 0.03), n_runs=20, n_run_len=60):
+    """Returns (d_seq uint8[concat_len] with one EOS(7) after every chromosome, entries)."""
+    ents, n = entries_for(lens)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    seq = torch.randint(0, 4, (n,), dtype=torch.uint8, device=device, generator=g)
+    if repeat_frac > 0 and n > 40 * repeat_len[1]:
+        avg = (repeat_len[0] + repeat_len[1]) // 2
+        S = max(1, int(n * repeat_frac / avg))
+        stride = n // S
+        lens_t = torch.randint(repeat_len[0], repeat_len[1] + 1, (S,), device=device, generator=g)
+        jitter = (torch.rand(S, device=device, generator=g) * (stride - repeat_len[1] - 1)).long()
+        dst0 = torch.arange(S, device=device) * stride + jitter
+        src0 = (torch.rand(S, device=device, generator=g) * (n - repeat_len[1] - 1)).long()
+        rc = torch.rand(S, device=device, generator=g) < 0.5
+        div = torch.tensor(divergences, device=device)[torch.randint(0, len(divergences), (S,), device=device, generator=g)]
+        orig = seq.clone()  # sources are read from the pristine random sequence (deterministic, EOS-free)
+        CH = 4096  # segments per chunk keeps the flat index tensors small
+        for s0 in range(0, S, CH):
+            sl = slice(s0, min(S, s0 + CH))
+            ln = lens_t[sl]
+            seg = torch.repeat_interleave(torch.arange(ln.numel(), device=device), ln)
+            start = torch.cumsum(ln, 0) - ln
+            within = torch.arange(int(ln.sum()), device=device) - start[seg]
+            r = rc[sl][seg]
+            sidx = torch.where(r, src0[sl][seg] + ln[seg] - 1 - within, src0[sl][seg] + within)
+            v = orig[sidx]
+            v = torch.where(r, 3 - v, v)
+            mut = torch.rand(v.numel(), device=device, generator=g) < div[sl][seg]
+            add = torch.randint(1, 4, (v.numel(),), dtype=torch.uint8, device=device, generator=g)
+            v = torch.where(mut, (v + add) & 3, v)
+            seq[dst0[sl][seg] + within] = v
+        del orig
+    for i in range(n_runs):
+        p = int(torch.randint(0, n - n_run_len, (1,), generator=g, device=device).item())
+        seq[p:p + n_run_len] = 4
+    eos = torch.from_numpy((ents["end_ofs"] + 1).astype(np.int64)).to(device)
+    seq[eos] = 7
+    return seq, ents
+
+
+def sim_reads(d_seq, ents, n_reads, length, seed=2, subs=(0, 1, 2, 3, 4), device="cuda", chunk=1 << 21):
+    """Returns (d_bases uint8[n_reads*length], d_offsets int64[n_reads+1]).  Each read is a genome
+    substring (either strand) carrying k substitutions, k drawn uniformly from `subs`."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lens = torch.from_numpy(ents["seq_len"].astype(np.int64)).to(device)
+    starts = torch.from_numpy(ents["start_ofs"].astype(np.int64)).to(device)
+    ok = lens >= length
+    w = torch.where(ok, lens.double(), torch.zeros_like(lens, dtype=torch.double))
+    out = torch.empty(n_reads * length, dtype=torch.uint8, device=device)
+    subs_t = torch.tensor(subs, device=device)
+    kmax = int(max(subs))
+    ar = torch.arange(length, device=device)
+    for s0 in range(0, n_reads, chunk):
+        m = min(chunk, n_reads - s0)
+        c = torch.multinomial(w, m, replacement=True, generator=g)
+        p = starts[c] + (torch.rand(m, device=device, generator=g, dtype=torch.double) * (lens[c] - length + 1).double()).long()
+        b = d_seq[p[:, None] + ar[None, :]]
+        if kmax > 0:
+            k = subs_t[torch.randint(0, len(subs), (m,), device=device, generator=g)]
+            pos = torch.rand(m, length, device=device, generator=g).topk(kmax, dim=1).indices
+            add = torch.randint(1, 4, (m, kmax), dtype=torch.uint8, device=device, generator=g)
+            cur = torch.gather(b, 1, pos)
+            new = torch.where((torch.arange(kmax, device=device)[None, :] < k[:, None]) & (cur < 4), (cur + add) & 3, cur)
+            b = b.scatter(1, pos, new)
+        rcm = torch.rand(m, device=device, generator=g) < 0.5
+        br = torch.flip(b, dims=[1])
+        br = torch.where(br < 4, 3 - br, br)
+        b = torch.where(rcm[:, None], br, b)
+        out[s0 * length:(s0 + m) * length] = b.reshape(-1)
+    offs = torch.arange(n_reads + 1, device=device, dtype=torch.int64) * length
+    return out, offs
+
+
+def algorithmic_bytes(results, concat_len, el_size, read_len):
+    """W(read) = seeds*S*(E+8) + cands*(E+ceil(L/4)) + ceil(L/4) + 32, summed."""
+    S = int(np.ceil(np.log2(concat_len)))
+    q = (read_len + 3) // 4
+    seeds = int(results["seeds"].astype(np.int64).sum())
+    cands = int(results["cands"].astype(np.int64).sum())
+    return seeds * S * (el_size + 8) + cands * (el_size + q) + len(results) * (q + 32)

@@ -146,8 +146,11 @@ def test_device_resident_variant(golden_dir):
     d_o = torch.from_numpy(offs.astype(np.int64)).cuda()
     d_out = torch.zeros(len(exp) * 32, dtype=torch.uint8, device="cuda")
     d_st = torch.zeros(C.sizeof(abi.AlignStats), dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
-    gidx.align_device(p, d_b.data_ptr(), d_o.data_ptr(), len(exp), 150, d_out.data_ptr(), d_st.data_ptr(), st)
+    ts = torch.cuda.Stream()
+    ts.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(ts):
+        gidx.align_device(p, d_b.data_ptr(), d_o.data_ptr(), len(exp), 150, d_out.data_ptr(), d_st.data_ptr(),
+                          ts.cuda_stream)
     torch.cuda.synchronize()
     got = d_out.cpu().numpy().view(abi.RESULT_DTYPE)
     assert_same(names, got, exp)
