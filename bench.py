@@ -347,7 +347,7 @@ def run_reference(args):
                                stdout=subprocess.DEVNULL)
                 ts = {}
                 for ln in open(os.path.join(tmp, "run.log"), errors="replace"):
-                    m = re.match(r"\[\w+ \w+ +\d+ (\d+):(\d+):(\d+)\.(\d+) \d+\]", ln)
+                    m = re.match(r"\[\w+ +\d+ (\d+):(\d+):(\d+)\.(\d+) \d+\]", ln)
                     if not m:
                         continue
                     t = int(m.group(1)) * 3600 + int(m.group(2)) * 60 + int(m.group(3)) + int(m.group(4)) / 1000.0
