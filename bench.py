@@ -296,6 +296,22 @@ def cpu_baseline_port(args, host_seq, host_sa, ents, h_bases, gpu_res):
             "sample": "first %d of the %d reads, %.1fs" % (m, args.reads, dt), "parity_with_gpu": bool(ok)}
 
 
+def write_fasta_fast(path, reads2d, alphabet):
+    """Vectorised FASTA writer: fixed-width names '>r000000001'."""
+    n, L = reads2d.shape
+    rec = np.empty((n, 12 + L + 1), dtype=np.uint8)
+    rec[:, 0] = ord(">")
+    rec[:, 1] = ord("r")
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    for d in range(9):
+        rec[:, 10 - d] = ord("0") + (ids // (10 ** d)) % 10
+    rec[:, 11] = ord("\n")
+    rec[:, 12:12 + L] = alphabet[reads2d]
+    rec[:, 12 + L] = ord("\n")
+    with open(path, "wb") as f:
+        f.write(rec.tobytes())
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -315,9 +331,11 @@ def run_reference(args):
     dev = torch.device("cuda", 0)
     cores = os.cpu_count() or 1
     total_steps = args.steps + args.warmup
+    # the reference sleeps 5 s while its workers run (Aligner.cpp:8799): a step must take well over 5 s of
+    # alignment for its log timestamps to measure work, hence millions of reads per step
     sample = args.ref_sample
-    if total_steps > 6:
-        sample = max(150000, int(sample * 6 / total_steps))
+    if total_steps > 4:
+        sample = max(2500000, int(sample * 4 / total_steps))
     saved_reads = args.reads
     args.reads = sample * total_steps
     d_seq, d_sa, ents, n, d_bases, d_offs = build_workload(args, 0, 1, dev, torch, None)
@@ -338,10 +356,7 @@ def run_reference(args):
             del host_seq, host_sa
             for s in range(total_steps):
                 rd = h_bases[s * sample * L:(s + 1) * sample * L].reshape(sample, L)
-                with open(os.path.join(tmp, "r.fa"), "wb") as f:
-                    asc = synth.BASES[rd]
-                    for i in range(sample):
-                        f.write(b">r%d\n" % (i + 1) + asc[i].tobytes() + b"\n")
+                write_fasta_fast(os.path.join(tmp, "r.fa"), rd, synth.BASES)
                 subprocess.run([po.REF_BIN, "align", "-I", "g.sfx", "-i", "r.fa", "-s%d" % args.max_subs, "-M0", "-o",
                                 "out.csv", "-F", "run.log", "-T%d" % min(cores, 128)], cwd=tmp, check=True,
                                stdout=subprocess.DEVNULL)
@@ -408,7 +423,7 @@ def main():
     ap.add_argument("--prefix-k", type=int, default=0)
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--cpu-sample", type=int, default=300000)
-    ap.add_argument("--ref-sample", type=int, default=400000)
+    ap.add_argument("--ref-sample", type=int, default=4000000)
     ap.add_argument("--ref-port", action="store_true", help="reference arm: use the oracle port even if the binary exists")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-times", action="store_true", help="read the kernel's own events after every step")

@@ -1,4 +1,4 @@
-// The read-alignment kernel: one warp per read, persistent grid.
+// The read-alignment kernel body: one G-lane group per read (G = 8: four reads per warp), persistent grid.
 //
 // Reference loops replaced (file:line under /root/reference):
 //   CAligner::ProcCoredApprox        biokanga/Aligner.cpp:9027-9504   per-read driver + classification
@@ -6,31 +6,53 @@
 //   CSfxArrayV3::LocateCoreMultiples libbiokanga/SfxArrayV2.cpp:5693-6262  one phase (cores, walk, Hamming)
 //   LocateFirstExact/LocateLastExact libbiokanga/SfxArrayV2.cpp:7765-8027  SA interval of a core
 //
-// Mapping to the warp:
-//   * the read is 2-bit packed (both strands) into the warp's shared-memory slot once;
-//   * SEEDS: lane c owns core c of the current strand/phase: k-mer prefix-table bucket, then a
-//     lower/upper-bound refinement over the reference's suffix array -> interval [first, first+cnt);
-//   * WALK: the SA entries of all cores are flattened in the reference's processing order
-//     (core, then SA index) and handed out 32 per step, lane = one candidate locus: entry check,
-//     "already seen" test, XOR+popc Hamming over packed 64-bit words, then warp reductions keep
-//     (LowMMCnt, NxtLowMMCnt, LowHitInstances, first hit) exactly as the sequential loop would,
-//     including the ordered early exit, the 100th-candidate copy probe and the MaxIter cap.
+// Mapping to the lane group:
+//   * the read is 2-bit packed (both strands) into the group's shared-memory slot once;
+//   * SEEDS: the cores of BOTH strands of the current phase form one list; lane j owns seed j of the
+//     current chunk of G: k-mer prefix-table bucket, then a lower/upper-bound refinement over the
+//     reference's suffix array -> interval [first, first+cnt);
+//   * WALK: per strand, the SA entries of the chunk's cores are flattened in the reference's
+//     processing order (core, then SA index) and handed out G per step, lane = one candidate locus:
+//     entry check, "already seen" test, XOR+popc Hamming over packed 64-bit words, then group
+//     reductions keep (LowMMCnt, NxtLowMMCnt, LowHitInstances, first hit) exactly as the sequential
+//     loop would, including the ordered early exit, the 100th-candidate copy probe and the MaxIter cap.
+//
+// Why the parallel walk is exact.  For one phase the reference's final (LowMMCnt, LowHitInstances,
+// NxtLowMMCnt) are functions of the MULTISET of accepted mismatch counts of the candidates it
+// processes: low = min, instances = multiplicity of min, next = second distinct value (else the initial
+// MaxTotMM+MMDelta+1); its ">= NxtLowMMCnt" abort (SfxArrayV2.cpp:6150) only skips candidates that
+// cannot change any of the three.  WHICH candidates are processed depends on order only through
+// (a) the "already processed" set, (b) the 100th-candidate probe / MaxIter / node caps and (c) the
+// early exit at the (MaxHits+1)-th exact match -- all three are evaluated here in lane order, which is
+// the reference's processing order.  With MaxHits == 1 the stored hit is the first candidate at the
+// final minimum, again in that order.
 #pragma once
 #include "../../include/bkx.h"
 #include "bkx_index.cuh"
 
 namespace bkx {
 
-constexpr int kSeenCap = 128;        // "already processed" keys kept in shared memory per warp
+constexpr int kSeenCap = 96;         // "already processed" keys kept in shared memory per group
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
-constexpr unsigned kFull = 0xffffffffu;
+constexpr int kGroup = 8;            // lanes per read
 
 struct KParams {
   int max_subs, mmd, max_ns, strand_mode, max_hits, min_core_len, slides_per100, max_iter, max_nodes;
 };
 
-struct WarpCtx {
+// overflow hash sets for groups whose strand/phase sees more than kSeenCap keys (high-copy repeats)
+struct HashPool {
+  uint64_t* tables;      // n_tables x slots u64: (epoch << 32) | key
+  uint32_t* locks;       // 0 = free
+  uint32_t* epochs;      // per table, monotonically increasing
+  uint32_t n_tables;
+  uint32_t slots;        // power of two
+};
+
+template <int G>
+struct Grp {
+  static constexpr unsigned kLaneMask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
   // read, both strands, in shared memory
   uint64_t* s2[2];
   uint32_t* sx[2];
@@ -38,22 +60,45 @@ struct WarpCtx {
   int* pre;
   int L;
   bool hasN;
-  int lane;
+  int gl;             // lane within the group
+  unsigned gmask;     // this group's lanes within the warp
+  int gshift;
   // "already processed" set of the current strand
   int seen_n;
   bool overflow;
   uint64_t* hash;
-  uint32_t hmask;
-  uint32_t epoch;
+  uint32_t hmask, epoch;
+  int table_id;
   int nodes;
   // phase state (LowHitInstances, LowMMCnt, NxtLowMMCnt) and first hit
   int inst, low, nxt;
   int hit_strand, hit_ent, hit_mm;
   uint64_t hit_p;
   uint32_t seeds, cands;
+
+  __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & kLaneMask; }
+  template <typename T>
+  __device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(gmask, v, src, G); }
+  __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+  __device__ __forceinline__ int gmin(int v) const {
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) v = min(v, __shfl_xor_sync(gmask, v, o, G));
+    return v;
+  }
+  __device__ __forceinline__ uint64_t gmax64(uint64_t v) const {
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) { uint64_t t = __shfl_xor_sync(gmask, v, o, G); v = t > v ? t : v; }
+    return v;
+  }
+  __device__ __forceinline__ int gsum(int v) const {
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(gmask, v, o, G);
+    return v;
+  }
 };
 
-__device__ __forceinline__ uint64_t read_word(const WarpCtx& c, int s, int pos) {
+template <int G>
+__device__ __forceinline__ uint64_t read_word(const Grp<G>& c, int s, int pos) {
   int w = pos >> 5;
   unsigned sh = (unsigned)(pos & 31) * 2;
   uint64_t a = c.s2[s][w];
@@ -61,13 +106,15 @@ __device__ __forceinline__ uint64_t read_word(const WarpCtx& c, int s, int pos) 
   return (a >> sh) | (c.s2[s][w + 1] << (64 - sh));
 }
 
-__device__ __forceinline__ int rsym(const WarpCtx& c, int s, int i) {
+template <int G>
+__device__ __forceinline__ int rsym(const Grp<G>& c, int s, int i) {
   if ((c.sx[s][i >> 5] >> (i & 31)) & 1) return 4;
   return (int)((c.s2[s][i >> 5] >> ((i & 31) * 2)) & 3);
 }
 
 // probe-vs-suffix comparison of SfxArrayV2.cpp:7792-7811: -1 / 0 / +1, target EOS => -1.
-static __device__ __noinline__ int cmp_core_slow(const DevIndex& I, const WarpCtx& c, int s, int ofs, int len, uint64_t g) {
+template <int G>
+__device__ __noinline__ int cmp_core_slow(const DevIndex& I, const Grp<G>& c, int s, int ofs, int len, uint64_t g) {
   for (int i = 0; i < len; ++i) {
     int gs = gsym(I, g + i);
     if (gs == 7) return -1;
@@ -78,7 +125,8 @@ static __device__ __noinline__ int cmp_core_slow(const DevIndex& I, const WarpCt
   return 0;
 }
 
-__device__ __forceinline__ int cmp_core(const DevIndex& I, const WarpCtx& c, int s, int ofs, int len, uint64_t g) {
+template <int G>
+__device__ __forceinline__ int cmp_core(const DevIndex& I, const Grp<G>& c, int s, int ofs, int len, uint64_t g) {
   if (c.hasN || span_has_exc(I, g, (uint32_t)len)) return cmp_core_slow(I, c, s, ofs, len, g);
   uint64_t w = g >> 5;
   unsigned sh = (unsigned)(g & 31) * 2;
@@ -102,7 +150,8 @@ __device__ __forceinline__ int cmp_core(const DevIndex& I, const WarpCtx& c, int
 
 // SA interval [first, first+cnt) of suffixes starting with core (strand s, offset ofs, length len);
 // cnt == 0 if absent.  Equivalent to LocateFirstExact + LocateLastExact over the whole array.
-__device__ __forceinline__ void locate_core(const DevIndex& I, const WarpCtx& c, int s, int ofs, int len,
+template <int G>
+__device__ __forceinline__ void locate_core(const DevIndex& I, const Grp<G>& c, int s, int ofs, int len,
                                             uint64_t& first, uint64_t& cnt) {
   const int k = I.k;
   int eff = len < k ? len : k;  // leading symbols usable as table key
@@ -156,7 +205,8 @@ __device__ __forceinline__ void locate_core(const DevIndex& I, const WarpCtx& c,
 
 // Mismatch count of the whole read (strand s) against the concatenation at p; the window is known
 // to lie inside one chromosome.  Returns 255 once the count exceeds max_mm (SfxArrayV2.cpp:6093-6152).
-__device__ __forceinline__ int hamming(const DevIndex& I, const WarpCtx& c, int s, uint64_t p, int max_mm) {
+template <int G>
+__device__ __forceinline__ int hamming(const DevIndex& I, const Grp<G>& c, int s, uint64_t p, int max_mm) {
   const int L = c.L;
   if (span_has_exc(I, p, (uint32_t)L)) {  // genome N inside the window: symbol-wise (N matches N)
     int mm = 0;
@@ -186,7 +236,8 @@ __device__ __forceinline__ int hamming(const DevIndex& I, const WarpCtx& c, int 
 }
 
 // ---- "already processed" set (SfxArrayV2.cpp:5931-5950): 32-bit keys, reset per strand ----------
-__device__ __forceinline__ bool seen_contains(const WarpCtx& c, uint32_t key) {
+template <int G>
+__device__ __forceinline__ bool seen_contains(const Grp<G>& c, uint32_t key) {
   if (!c.overflow) {
     bool f = false;
     for (int i = 0; i < c.seen_n; ++i) f |= (c.seen[i] == key);
@@ -195,14 +246,15 @@ __device__ __forceinline__ bool seen_contains(const WarpCtx& c, uint32_t key) {
   uint64_t want = ((uint64_t)c.epoch << 32) | key;
   uint32_t h = (key * 2654435761u) & c.hmask;
   for (;;) {
-    uint64_t v = __ldcg(c.hash + h);  // L2 view: other lanes of this warp insert with atomics
+    uint64_t v = __ldcg(c.hash + h);  // L2 view: other lanes of this group insert with atomics
     if (v == want) return true;
     if ((uint32_t)(v >> 32) != c.epoch) return false;
     h = (h + 1) & c.hmask;
   }
 }
 
-__device__ __forceinline__ void hash_insert(WarpCtx& c, uint32_t key) {
+template <int G>
+__device__ __forceinline__ void hash_insert(Grp<G>& c, uint32_t key) {
   uint64_t want = ((uint64_t)c.epoch << 32) | key;
   uint32_t h = (key * 2654435761u) & c.hmask;
   for (;;) {
@@ -217,38 +269,73 @@ __device__ __forceinline__ void hash_insert(WarpCtx& c, uint32_t key) {
   }
 }
 
+// borrow one overflow table from the pool (lane 0 spins on the lock words; holders never wait)
+template <int G>
+__device__ __forceinline__ void hash_acquire(Grp<G>& c, const HashPool& hp, uint32_t salt) {
+  int id = -1;
+  uint32_t ep = 0;
+  if (c.gl == 0) {
+    uint32_t t = salt % hp.n_tables;
+    for (;;) {
+      if (atomicCAS(hp.locks + t, 0u, 1u) == 0u) break;
+      t = (t + 1 == hp.n_tables) ? 0 : t + 1;
+    }
+    __threadfence();
+    id = (int)t;
+    ep = __ldcg(hp.epochs + t) + 1;
+    __stcg(hp.epochs + t, ep);
+  }
+  c.table_id = c.bcast(id, 0);
+  c.epoch = c.bcast(ep, 0);
+  c.hash = hp.tables + (size_t)c.table_id * hp.slots;
+  c.hmask = hp.slots - 1;
+}
+
+template <int G>
+__device__ __forceinline__ void hash_release(Grp<G>& c, const HashPool& hp) {
+  if (c.table_id < 0) return;
+  c.sync();
+  if (c.gl == 0) {
+    __threadfence();
+    atomicExch(hp.locks + c.table_id, 0u);
+  }
+  c.table_id = -1;
+}
+
 // all lanes call; lanes with ins==true add their (distinct) key
-__device__ __forceinline__ void seen_insert(WarpCtx& c, bool ins, uint32_t key) {
-  unsigned m = __ballot_sync(kFull, ins);
+template <int G>
+__device__ __forceinline__ void seen_insert(Grp<G>& c, const HashPool& hp, bool ins, uint32_t key) {
+  unsigned m = c.ballot(ins);
   int cnt = __popc(m);
   if (cnt == 0) return;
   if (!c.overflow && c.seen_n + cnt <= kSeenCap) {
-    if (ins) c.seen[c.seen_n + __popc(m & ((1u << c.lane) - 1))] = key;
+    if (ins) c.seen[c.seen_n + __popc(m & ((1u << c.gl) - 1))] = key;
     c.seen_n += cnt;
-    __syncwarp();
+    c.sync();
     return;
   }
-  if (!c.overflow) {  // migrate the shared-memory list into this warp's global hash set
+  if (!c.overflow) {  // migrate the shared-memory list into a global hash set
     c.overflow = true;
-    c.epoch += 1;
-    __syncwarp();
-    for (int i = c.lane; i < c.seen_n; i += 32) hash_insert(c, c.seen[i]);
-    __syncwarp();
+    hash_acquire(c, hp, key ^ (uint32_t)c.seen_n ^ (uint32_t)(c.hit_p >> 3));
+    c.sync();
+    for (int i = c.gl; i < c.seen_n; i += G) hash_insert(c, c.seen[i]);
+    c.sync();
   }
   if (ins) hash_insert(c, key);
   c.seen_n += cnt;
   __threadfence_block();
-  __syncwarp();
+  c.sync();
 }
 
-// ---- one step of the interval walk: up to 32 SA entries, one per lane, in processing order ------
+// ---- one step of the interval walk: up to G SA entries, one per lane, in processing order ------
 // valid/cofs/sidx are lane-private.  capped => all lanes belong to one core whose interval ends at
 // hi_idx and iter_cnt counts its new candidates so far (the 100th-candidate probe and MaxIter cap
 // of SfxArrayV2.cpp:5857-5875 apply).  Returns the lane at which processing stopped (or -1).
-__device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, WarpCtx& c, int s, int max_mm,
-                                         bool valid, int cofs, uint64_t sidx, bool capped, int& iter_cnt,
+template <int G>
+__device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, const HashPool& hp, Grp<G>& c, int s,
+                                         int max_mm, bool valid, int cofs, uint64_t sidx, bool capped, int& iter_cnt,
                                          uint64_t hi_idx, bool& stop_core, bool& stop_strand, bool& stop_all) {
-  const unsigned lt = (1u << c.lane) - 1;
+  const unsigned lt = (1u << c.gl) - 1;
   uint64_t loci = valid ? sa_get(I, sidx) : 0;
   bool ok = valid && loci >= (uint64_t)cofs;
   uint64_t p = loci - (uint64_t)cofs;
@@ -259,77 +346,73 @@ __device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, Wa
   }
   uint32_t key = (uint32_t)(1u + (uint32_t)loci - (uint32_t)cofs);
   bool dup = ok && seen_contains(c, key);
-  unsigned okm = __ballot_sync(kFull, ok);
-  unsigned same = __match_any_sync(kFull, key);
+  unsigned okm = c.ballot(ok);
+  unsigned same = (__match_any_sync(c.gmask, key) >> c.gshift) & Grp<G>::kLaneMask;
   if (ok && (same & okm & lt)) dup = true;  // an earlier lane of this step already claims the key
   bool isnew = ok && !dup;
-  unsigned newm = __ballot_sync(kFull, isnew);
+  unsigned newm = c.ballot(isnew);
   int stop_lane = -1;
   // caps, in processing order
   if (newm) {
-    int rank = iter_cnt + __popc(newm & (lt | (1u << c.lane)));  // 1-based index among new candidates
-    int cut = 32;
+    int rank = iter_cnt + __popc(newm & (lt | (1u << c.gl)));  // 1-based index among new candidates
+    int cut = G;
     if (capped) {
       bool at100 = isnew && rank == 100 && sidx < hi_idx && (hi_idx - sidx + 2) > (uint64_t)P.max_iter;
       bool atmax = isnew && rank == P.max_iter;
-      unsigned cm = __ballot_sync(kFull, at100 || atmax);
+      unsigned cm = c.ballot(at100 || atmax);
       if (cm) { cut = __ffs(cm) - 1; stop_core = true; }
     }
     // identifier-node budget (cMaxNumIdentNodes): the candidate that fills it is still processed
     int allowed = P.max_nodes - c.nodes;
-    if (__popc(newm & (cut >= 31 ? kFull : ((2u << cut) - 1))) >= allowed) {
+    unsigned upto = (cut >= G - 1) ? Grp<G>::kLaneMask : ((2u << cut) - 1);
+    if (__popc(newm & upto) >= allowed) {
       int nl = (int)__fns(newm, 0, allowed);  // lane of the allowed-th new candidate
-      if (nl < cut || cut == 32) { cut = nl; }
+      if (nl < cut) cut = nl;
       stop_core = true;
       stop_strand = true;
     }
-    if (cut < 32) {
+    if (cut < G) {
       stop_lane = cut;
-      if (c.lane > cut) isnew = false;
-      newm = __ballot_sync(kFull, isnew);
+      if (c.gl > cut) isnew = false;
+      newm = c.ballot(isnew);
     }
   }
   int mm = 255;
   if (isnew) mm = hamming(I, c, s, p, max_mm);
   bool acc = isnew && mm <= max_mm;
   // ordered early exit: the (MaxHits+1)-th exact match ends the whole search (SfxArrayV2.cpp:6206-6214)
-  unsigned zm = __ballot_sync(kFull, acc && mm == 0);
+  unsigned zm = c.ballot(acc && mm == 0);
   if (zm) {
     int before = (c.low == 0) ? c.inst : 0;
     if (before + __popc(zm) > P.max_hits) {
       int need = P.max_hits + 1 - before;
       int el = (int)__fns(zm, 0, need);
-      if (c.lane > el) { isnew = false; acc = false; }
-      newm = __ballot_sync(kFull, isnew);
+      if (c.gl > el) { isnew = false; acc = false; }
+      newm = c.ballot(isnew);
       stop_all = true;
       stop_core = true;
       stop_lane = el;
     }
   }
   int nnew = __popc(newm);
-  seen_insert(c, isnew, key);
+  seen_insert(c, hp, isnew, key);
   c.nodes += nnew;
   iter_cnt += nnew;
   c.cands += (uint32_t)nnew;
   // merge (min, count of min, second distinct min, first lane at min) into the running state
-  unsigned accm = __ballot_sync(kFull, acc);
+  unsigned accm = c.ballot(acc);
   if (accm) {
-    int v = acc ? mm : 255;
-    int bmin = v;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) bmin = min(bmin, __shfl_xor_sync(kFull, bmin, o));
-    unsigned minm = __ballot_sync(kFull, acc && mm == bmin);
-    int v2 = (acc && mm > bmin) ? mm : 255;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v2 = min(v2, __shfl_xor_sync(kFull, v2, o));
+    int bmin = c.gmin(acc ? mm : 255);
+    unsigned minm = c.ballot(acc && mm == bmin);
+    int v2 = c.gmin((acc && mm > bmin) ? mm : 255);
     int bcnt = __popc(minm);
     if (bmin < c.low) {
       int fl = __ffs(minm) - 1;
       c.nxt = min(c.low, v2);
       c.low = bmin;
       c.inst = bcnt;
-      c.hit_p = __shfl_sync(kFull, p, fl);
-      c.hit_ent = __shfl_sync(kFull, ent, fl);
+      c.hit_p = c.bcast(p, fl);
+      c.hit_ent = c.bcast(ent, fl);
       c.hit_mm = bmin;
       c.hit_strand = s;
     } else if (bmin == c.low) {
@@ -342,21 +425,28 @@ __device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, Wa
   return stop_lane;
 }
 
-// Position of core number idx in the slide loop of SfxArrayV2.cpp:5836-5847; false if the loop
-// would have ended before reaching it.
-__device__ __forceinline__ bool core_layout(int L, int CL, int delta, int max_slides, int idx, int& ofs_out) {
-  int cur = delta, ofs = 0;
-  for (int i = 0;; ++i) {
-    if (!(i < max_slides && ofs <= L - CL && cur > CL / 3)) return false;
-    if (ofs + CL + cur > L) cur = L - (ofs + CL);
-    if (i == idx) { ofs_out = ofs; return true; }
-    ofs += cur;
+// Closed form of the slide loop of SfxArrayV2.cpp:5836-5847 for delta >= CL (always true on this
+// path: staged phases use delta == CL, the final phase CoreDelta = max(.., CoreLen)):
+// cores sit at 0, delta, .., K*delta; core K is the one whose step gets shortened to
+// r = L-(K*delta+CL); one more flush-right core at L-CL follows iff r > CL/3.
+struct CoreLayout {
+  int K, n, last_ofs, delta;
+  __device__ __forceinline__ CoreLayout(int L, int CL, int d, int max_slides) {
+    delta = d;
+    K = (L - CL - d >= 0) ? (L - CL - d) / d + 1 : 0;
+    int r = L - (K * d + CL);
+    n = K + 1 + ((r > CL / 3) ? 1 : 0);
+    if (n > max_slides) n = max_slides;
+    if (L < CL) n = 0;  // the loop's `ofs <= L-CL` test fails at once
+    last_ofs = L - CL;
   }
-}
+  __device__ __forceinline__ int ofs(int i) const { return i <= K ? i * delta : last_ofs; }
+};
 
 // One phase = LocateCoreMultiples(max_mm, CL, delta).  Returns tHRslt.
-__device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, WarpCtx& c, int max_mm, int CL,
-                                         int delta, int max_slides) {
+template <int G>
+__device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, const HashPool& hp, Grp<G>& c,
+                                         int max_mm, int CL, int delta, int max_slides) {
   if (c.inst > P.max_hits && c.low == 0) return BKX_HR_HITINSTS;
   if (c.inst >= 1 && c.low == 0 && (c.nxt - c.low) < P.mmd) return BKX_HR_MMDELTA;
   if (c.inst <= 0 || c.low < 0 || c.nxt < 0) {
@@ -364,102 +454,105 @@ __device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, Wa
     c.low = c.nxt = max_mm + P.mmd + 1;
   }
   const int inst0 = c.inst, low0 = c.low, nxt0 = c.nxt;
-  // number of cores of this phase (same for both strands)
-  int n_cores = 0;
-  {
-    int o;
-    bool v = core_layout(c.L, CL, delta, max_slides, c.lane, o);
-    unsigned m = __ballot_sync(kFull, v);
-    n_cores = __popc(m);
-    if (n_cores == 32) {  // long reads: count the rest
-      int i = 32;
-      while (core_layout(c.L, CL, delta, max_slides, i, o)) ++i;
-      n_cores = i;
-    }
-  }
-  bool stop_all = false;
-  const int s_begin = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
-  const int s_end = (P.strand_mode == BKX_STRAND_WATSON) ? 0 : 1;
-  for (int s = s_begin; s <= s_end && !stop_all; ++s) {
-    c.seen_n = 0;
-    c.overflow = false;
-    c.nodes = 0;
-    bool stop_strand = false;
-    for (int base = 0; base < n_cores && !stop_strand && !stop_all; base += 32) {
-      // ---- seeds: lane = core
-      int my = base + c.lane;
-      int cofs = 0;
-      uint64_t first = 0, cnt = 0;
-      bool have = my < n_cores && core_layout(c.L, CL, delta, max_slides, my, cofs);
-      if (have) locate_core(I, c, s, cofs, CL, first, cnt);
-      int nc = min(32, n_cores - base);
-      // ---- walk
-      uint64_t cmax = cnt;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) cmax = max(cmax, __shfl_xor_sync(kFull, cmax, o));
-      int cores_done = nc;  // cores of this chunk whose LocateFirstExact the reference would issue
+  const CoreLayout lay(c.L, CL, delta, max_slides);
+  const int n_cores = lay.n;
+  const int s_first = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
+  const int n_strands = (P.strand_mode == BKX_STRAND_BOTH) ? 2 : 1;
+  const int total = n_cores * n_strands;
+  bool stop_all = false, stop_strand = false;
+  int cur_strand = -1;
+  for (int base = 0; base < total && !stop_all; base += G) {
+    // ---- seeds: lane = (strand, core) of the combined list
+    const int my = base + c.gl;
+    const bool have = my < total;
+    const int my_s = have ? s_first + my / n_cores : 0;
+    const int my_c = have ? my % n_cores : 0;
+    const int cofs = lay.ofs(my_c);
+    uint64_t first = 0, cnt = 0;
+    if (have && !(stop_strand && my_s == cur_strand)) locate_core(I, c, my_s, cofs, CL, first, cnt);
+    const int nc = min(G, total - base);
+    // ---- walk, strand by strand inside the chunk
+    int lane0 = 0;
+    while (lane0 < nc && !stop_all) {
+      const int s = s_first + (base + lane0) / n_cores;
+      const int core0 = (base + lane0) % n_cores;
+      const int lanes = min(nc - lane0, n_cores - core0);  // lanes of this strand in this chunk
+      if (s != cur_strand) {  // strand start: reset the "already processed" set (SfxArrayV2.cpp:5834-5835)
+        hash_release(c, hp);
+        cur_strand = s;
+        c.seen_n = 0;
+        c.overflow = false;
+        c.nodes = 0;
+        stop_strand = false;
+      }
+      if (stop_strand) { lane0 += lanes; continue; }
+      const bool mine = c.gl >= lane0 && c.gl < lane0 + lanes;
+      const uint64_t mycnt = mine ? cnt : 0;
+      const uint64_t cmax = c.gmax64(mycnt);
+      int cores_done = lanes;  // cores of this strand/chunk whose LocateFirstExact the reference issues
       if (cmax == 0) {
         // nothing to walk
       } else if (cmax <= 100) {
         // flattened: every interval is short enough that no cap can trigger
-        int incl = (int)cnt;
+        int incl = (int)mycnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int t = __shfl_up_sync(kFull, incl, o);
-          if (c.lane >= o) incl += t;
+        for (int o = 1; o < G; o <<= 1) {
+          int t = __shfl_up_sync(c.gmask, incl, o, G);
+          if (c.gl >= o) incl += t;
         }
-        int total = __shfl_sync(kFull, incl, 31);
-        c.pre[c.lane + 1] = incl;
-        if (c.lane == 0) c.pre[0] = 0;
-        __syncwarp();
-        for (int e0 = 0; e0 < total; e0 += 32) {
-          int e = e0 + c.lane;
-          bool valid = e < total;
-          int ci = 0;
-          if (valid) {  // core owning flattened entry e: largest ci with pre[ci] <= e
-            int lo = 0, hi = nc - 1;
+        const int tot_e = c.bcast(incl, G - 1);
+        c.pre[c.gl + 1] = incl;
+        if (c.gl == 0) c.pre[0] = 0;
+        c.sync();
+        for (int e0 = 0; e0 < tot_e; e0 += G) {
+          const int e = e0 + c.gl;
+          const bool valid = e < tot_e;
+          int ci = lane0;
+          if (valid) {  // lane owning flattened entry e: largest ci with pre[ci] <= e
+            int lo = lane0, hi = lane0 + lanes - 1;
             while (lo < hi) {
               int mid = (lo + hi + 1) >> 1;
               if (c.pre[mid] <= e) lo = mid; else hi = mid - 1;
             }
             ci = lo;
           }
-          uint64_t cf = __shfl_sync(kFull, first, ci);
-          int co = __shfl_sync(kFull, cofs, ci);
-          uint64_t sidx = cf + (uint64_t)(e - c.pre[ci]);
+          const uint64_t cf = c.bcast(first, ci);
+          const int co = c.bcast(cofs, ci);
+          const uint64_t sidx = cf + (uint64_t)(e - c.pre[ci]);
           int iter_dummy = 0;
           bool sc = false;
-          int sl = walk_step(I, P, c, s, max_mm, valid, co, sidx, false, iter_dummy, 0, sc, stop_strand, stop_all);
+          int sl = walk_step(I, P, hp, c, s, max_mm, valid, co, sidx, false, iter_dummy, 0, sc, stop_strand, stop_all);
           if (stop_all || stop_strand) {
-            cores_done = __shfl_sync(kFull, ci, sl < 0 ? 0 : sl) + 1;
+            cores_done = c.bcast(ci, sl < 0 ? 0 : sl) - lane0 + 1;
             break;
           }
         }
-        __syncwarp();
+        c.sync();
       } else {
-        // some core of this chunk has > 100 copies: strictly core by core
-        for (int ci = 0; ci < nc && !stop_all && !stop_strand; ++ci) {
-          uint64_t cf = __shfl_sync(kFull, first, ci);
-          uint64_t cc = __shfl_sync(kFull, cnt, ci);
-          int co = __shfl_sync(kFull, cofs, ci);
+        // some core of this strand/chunk has > 100 copies: strictly core by core
+        for (int ci = lane0; ci < lane0 + lanes && !stop_all && !stop_strand; ++ci) {
+          const uint64_t cf = c.bcast(first, ci);
+          const uint64_t cc = c.bcast(cnt, ci);
+          const int co = c.bcast(cofs, ci);
           if (cc == 0) continue;
           int iter_cnt = 0;
           bool stop_core = false;
           const uint64_t hi_idx = cf + cc - 1;
-          for (uint64_t e0 = 0; e0 < cc && !stop_core; e0 += 32) {
-            uint64_t e = e0 + (uint64_t)c.lane;
-            walk_step(I, P, c, s, max_mm, e < cc, co, cf + e, true, iter_cnt, hi_idx, stop_core, stop_strand, stop_all);
+          for (uint64_t e0 = 0; e0 < cc && !stop_core; e0 += G) {
+            uint64_t e = e0 + (uint64_t)c.gl;
+            walk_step(I, P, hp, c, s, max_mm, e < cc, co, cf + e, true, iter_cnt, hi_idx, stop_core, stop_strand, stop_all);
           }
-          if (stop_all || stop_strand) cores_done = ci + 1;
+          if (stop_all || stop_strand) cores_done = ci - lane0 + 1;
         }
       }
       c.seeds += (uint32_t)cores_done;
+      lane0 += lanes;
     }
   }
+  hash_release(c, hp);
   // return-code logic, SfxArrayV2.cpp:6237-6261
   if (c.low == low0 && c.inst == inst0) {
     if (nxt0 > c.nxt) return (c.nxt - c.low) < P.mmd ? BKX_HR_MMDELTA : BKX_HR_RMMDELTA;
-    c.nxt = nxt0;
     return BKX_HR_NONE;
   }
   if (c.inst >= 1 && (c.nxt - c.low) < P.mmd) return BKX_HR_MMDELTA;

@@ -62,9 +62,7 @@ struct bkx_index {
   std::mutex mtx;
   Slot slot[2];
   unsigned int* d_cursor[2] = {nullptr, nullptr};
-  uint64_t* hash_pool = nullptr;
-  uint32_t hash_slots = 0;
-  uint32_t* epochs = nullptr;
+  HashPool hp{};
   int grid = 0;
   int grid_W = 0;
   bkx_align_stats* d_stats = nullptr;
@@ -221,8 +219,9 @@ extern "C" void bkx_close_index(bkx_index* x) {
     if (x->slot[s].st) cudaStreamDestroy(x->slot[s].st);
     if (x->d_cursor[s]) cudaFree(x->d_cursor[s]);
   }
-  if (x->hash_pool) cudaFree(x->hash_pool);
-  if (x->epochs) cudaFree(x->epochs);
+  if (x->hp.tables) cudaFree(x->hp.tables);
+  if (x->hp.locks) cudaFree(x->hp.locks);
+  if (x->hp.epochs) cudaFree(x->hp.epochs);
   if (x->d_stats) cudaFree(x->d_stats);
   if (x->d_pe_stats) cudaFree(x->d_pe_stats);
   if (x->d_len_dist) cudaFree(x->d_len_dist);
@@ -513,19 +512,21 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
   uint64_t cap = std::min<uint64_t>((uint64_t)k.max_nodes, (uint64_t)slides * (uint64_t)k.max_iter);
   uint32_t slots = 1024;
   while (slots < 2 * cap) slots <<= 1;
-  uint32_t warps = (uint32_t)x->grid * kWarpsPerBlock;
-  // the pool is sized for the widest grid ever used (grid only shrinks as W grows)
-  static const uint32_t kMaxWarps = 148 * 64 * 2;
-  if (slots > x->hash_slots || !x->hash_pool) {
-    if (x->hash_pool) { cudaFree(x->hash_pool); x->hash_pool = nullptr; }
-    if (x->epochs) { cudaFree(x->epochs); x->epochs = nullptr; }
-    uint32_t pool_warps = std::max(warps, (uint32_t)0);
-    (void)kMaxWarps;
-    CU(cudaMalloc((void**)&x->hash_pool, (size_t)pool_warps * slots * 8));
-    CU(cudaMemset(x->hash_pool, 0, (size_t)pool_warps * slots * 8));
-    CU(cudaMalloc((void**)&x->epochs, (size_t)pool_warps * 4));
-    CU(cudaMemset(x->epochs, 0, (size_t)pool_warps * 4));
-    x->hash_slots = slots;
+  if (slots > x->hp.slots || !x->hp.tables) {
+    // a pool of overflow tables shared by all groups (only reads in high-copy repeats borrow one)
+    if (x->hp.tables) { cudaFree(x->hp.tables); x->hp.tables = nullptr; }
+    if (x->hp.locks) { cudaFree(x->hp.locks); x->hp.locks = nullptr; }
+    if (x->hp.epochs) { cudaFree(x->hp.epochs); x->hp.epochs = nullptr; }
+    uint32_t n_tables = 2048;
+    while (n_tables > 64 && (size_t)n_tables * slots * 8 > ((size_t)4 << 30)) n_tables >>= 1;
+    CU(cudaMalloc((void**)&x->hp.tables, (size_t)n_tables * slots * 8));
+    CU(cudaMemset(x->hp.tables, 0, (size_t)n_tables * slots * 8));
+    CU(cudaMalloc((void**)&x->hp.locks, (size_t)n_tables * 4));
+    CU(cudaMemset(x->hp.locks, 0, (size_t)n_tables * 4));
+    CU(cudaMalloc((void**)&x->hp.epochs, (size_t)n_tables * 4));
+    CU(cudaMemset(x->hp.epochs, 0, (size_t)n_tables * 4));
+    x->hp.n_tables = n_tables;
+    x->hp.slots = slots;
   }
   *W_out = x->grid_W;
   return BKX_OK;
@@ -546,8 +547,7 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : x->slot[0].st;
   Slot& s = x->slot[0];
   CU(cudaEventRecord(s.k0, st));
-  CU(launch_align(x->d, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, x->d_cursor[0], x->hash_pool, x->hash_slots,
-                  x->epochs, x->grid, st));
+  CU(launch_align(x->d, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, x->d_cursor[0], x->hp, x->grid, st));
   CU(cudaEventRecord(s.k1, st));
   s.timed = true;
   x->slot[1].timed = false;
@@ -612,7 +612,7 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
     CU(cudaEventRecord(s.k0, s.st));
     // offsets stay absolute: hand the kernel a base pointer shifted by the slice start
     CU(launch_align(x->d, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, x->d_cursor[b],
-                    x->hash_pool, x->hash_slots, x->epochs, x->grid, s.st));
+                    x->hp, x->grid, s.st));
     CU(cudaEventRecord(s.k1, s.st));
     CU(cudaMemcpyAsync(out + start, s.d_out, (size_t)cnt * sizeof(bkx_read_result), cudaMemcpyDeviceToHost, s.st));
     inflight[b] = true;

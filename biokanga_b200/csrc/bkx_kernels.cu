@@ -153,14 +153,13 @@ cudaError_t build_prefix_table(const DevIndex& I, int k, void* table, bool wide,
 // ------------------------------------------------------------------------------------------------
 // Read alignment
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ size_t warp_smem_bytes(int W) {
-  return (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + 36 * 4;
+constexpr int kGroupsPerBlock = kBlockThreads / kGroup;
+
+__host__ __device__ inline size_t group_smem_bytes(int W) {
+  size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + (kGroup + 2) * 4;
+  return (per + 15) & ~(size_t)15;
 }
-size_t align_smem_bytes(int W) {
-  size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + 36 * 4;
-  per = (per + 15) & ~(size_t)15;
-  return per * kWarpsPerBlock;
-}
+size_t align_smem_bytes(int W) { return group_smem_bytes(W) * kGroupsPerBlock; }
 
 struct BlockStats {
   unsigned int nar[BKX_NAR_COUNT];
@@ -169,74 +168,70 @@ struct BlockStats {
 };
 
 // Per-read driver: ProcCoredApprox body (Aligner.cpp:9027-9504) + AlignReads phase loop
-// (SfxArrayV2.cpp:7666-7760).  One warp per read; reads are claimed from a global cursor.
-__global__ void __launch_bounds__(kBlockThreads) align_reads_kernel(
+// (SfxArrayV2.cpp:7666-7760).  One kGroup-lane group per read; reads are claimed from a global cursor.
+__global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
-    uint64_t* __restrict__ hash_pool, uint32_t hash_slots, uint32_t* __restrict__ epochs) {
+    HashPool hp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockStats bs;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  constexpr int G = kGroup;
+  const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
   __syncthreads();
 
-  size_t per = ((size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + 36 * 4 + 15) & ~(size_t)15;
-  unsigned char* my = smem_raw + per * wib;
-  WarpCtx c;
+  unsigned char* my = smem_raw + group_smem_bytes(W) * (threadIdx.x / G);
+  Grp<G> c;
   c.s2[0] = (uint64_t*)my;
   c.s2[1] = c.s2[0] + W;
   c.sx[0] = (uint32_t*)(c.s2[1] + W);
   c.sx[1] = c.sx[0] + W;
   c.seen = c.sx[1] + W;
   c.pre = (int*)(c.seen + kSeenCap);
-  c.lane = lane;
-  const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + wib;
-  c.hash = hash_pool + (size_t)gwarp * hash_slots;
-  c.hmask = hash_slots - 1;
-  c.epoch = epochs[gwarp];
+  c.gl = lane & (G - 1);
+  c.gshift = lane & ~(G - 1);
+  c.gmask = Grp<G>::kLaneMask << c.gshift;
+  c.table_id = -1;
+  c.hash = nullptr;
+  c.hmask = 0;
+  c.epoch = 0;
+  c.hit_p = 0;
 
   for (;;) {
     unsigned int r = 0;
-    if (lane == 0) r = atomicAdd(cursor, 1u);
-    r = __shfl_sync(kFull, r, 0);
+    if (c.gl == 0) r = atomicAdd(cursor, 1u);
+    r = c.bcast(r, 0);
     if (r >= n_reads) break;
     const uint64_t o0 = __ldg(offs + r);
     const int L = (int)(__ldg(offs + r + 1) - o0);
     const uint8_t* rd = bases + o0;
     c.L = L;
-    // ---- unpack, N filter (Aligner.cpp:9041-9063), 2-bit pack both strands
+    // ---- unpack, N filter (Aligner.cpp:9041-9063), 2-bit pack both strands: one 32-base word per lane
     int nN = 0;
     bool bad = false;
-    const int words = (L + 31) >> 5;
-    for (int w = 0; w <= words && w < W; ++w) {
-      int i = w * 32 + lane;
-      unsigned code = 0, isn = 0;
-      if (i < L) {
-        unsigned b = rd[i] & 0x07;
-        if (b > 4) bad = true;
-        isn = (b == 4);
-        code = isn ? 0 : (b & 3);
+    const int words = (L + 31) >> 5;  // words <= W-1: word `words` is the zero pad the shifts read
+    for (int t = c.gl; t < 2 * (words + 1); t += G) {
+      const int s = t > words ? 1 : 0;
+      const int w = t - s * (words + 1);
+      uint64_t code2 = 0;
+      uint32_t nm = 0;
+      const int i0 = w * 32;
+      const int cntb = min(32, L - i0);
+      for (int j = 0; j < cntb; ++j) {
+        unsigned b = __ldg(rd + (s ? (L - 1 - (i0 + j)) : (i0 + j))) & 0x07;
+        bad |= (b > 4);
+        unsigned isn = (b == 4);
+        unsigned code = (b < 4) ? (s ? 3 - b : b) : 0;
+        code2 |= (uint64_t)code << (2 * j);
+        nm |= isn << j;
       }
-      unsigned b0 = __ballot_sync(kFull, code & 1), b1 = __ballot_sync(kFull, code & 2), bn = __ballot_sync(kFull, isn);
-      // reverse complement: position q of the '-' strand is the complement of base L-1-q
-      int q = w * 32 + lane;
-      unsigned rcode = 0, risn = 0;
-      if (q < L) {
-        unsigned b = rd[L - 1 - q] & 0x07;
-        risn = (b == 4);
-        rcode = (b < 4) ? (3 - b) : 0;
-      }
-      unsigned r0 = __ballot_sync(kFull, rcode & 1), r1 = __ballot_sync(kFull, rcode & 2), rn = __ballot_sync(kFull, risn);
-      if (lane == 0) {
-        c.s2[0][w] = spread32(b0) | (spread32(b1) << 1);
-        c.sx[0][w] = bn;
-        c.s2[1][w] = spread32(r0) | (spread32(r1) << 1);
-        c.sx[1][w] = rn;
-      }
-      nN += __popc(bn);
+      c.s2[s][w] = code2;
+      c.sx[s][w] = nm;
+      if (s == 0) nN += __popc(nm);
     }
-    bad = __any_sync(kFull, bad);
-    __syncwarp();
+    nN = c.gsum(nN);
+    bad = c.ballot(bad) != 0;
+    c.sync();
     c.hasN = nN > 0;
     int max_ns_seq = 0;
     if (P.max_ns) max_ns_seq = max((L * P.max_ns) / 100, P.max_ns);
@@ -264,11 +259,11 @@ __global__ void __launch_bounds__(kBlockThreads) align_reads_kernel(
         for (allow = 0; allow <= max_tot_mm; ++allow) {
           int cl = L / (allow + P.mmd);
           if (cl <= core_len) break;
-          hr = run_phase(I, P, c, allow, cl, cl, slides);
+          hr = run_phase<G>(I, P, hp, c, allow, cl, cl, slides);
           if (hr != 0) break;
         }
       }
-      if (hr == 0 && allow <= max_tot_mm) hr = run_phase(I, P, c, max_tot_mm, core_len, core_delta, slides);
+      if (hr == 0 && allow <= max_tot_mm) hr = run_phase<G>(I, P, hp, c, max_tot_mm, core_len, core_delta, slides);
       int inst = c.inst;
       if (inst > P.max_hits) inst = P.max_hits + 1;  // Aligner.cpp:9241
       res.hit_rslt = (uint8_t)hr;
@@ -303,16 +298,15 @@ __global__ void __launch_bounds__(kBlockThreads) align_reads_kernel(
           break;
       }
     }
-    if (lane == 0) {
+    if (c.gl == 0) {
       out[r] = res;
       atomicAdd(&bs.nar[res.nar], 1u);
       if (res.nar == BKX_NAR_ACCEPTED) atomicAdd(res.strand == '+' ? &bs.plus : &bs.minus, 1u);
       atomicAdd(&bs.seeds, (unsigned long long)res.seeds);
       atomicAdd(&bs.cands, (unsigned long long)res.cands);
     }
-    __syncwarp();
+    c.sync();
   }
-  if (lane == 0) epochs[gwarp] = c.epoch;
   __syncthreads();
   if (stats) {
     for (int i = threadIdx.x; i < BKX_NAR_COUNT; i += blockDim.x)
@@ -338,7 +332,7 @@ __global__ void __launch_bounds__(kBlockThreads) align_reads_kernel(
 
 cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                          uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats, unsigned int* cursor,
-                         uint64_t* hash_pool, uint32_t hash_slots, uint32_t* epochs, int grid, cudaStream_t st) {
+                         const HashPool& hp, int grid, cudaStream_t st) {
   size_t smem = align_smem_bytes(W);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -348,14 +342,15 @@ cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bas
   }
   cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
-  align_reads_kernel<<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hash_pool,
-                                                        hash_slots, epochs);
+  align_reads_kernel<<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hp);
   return cudaGetLastError();
 }
 
 int align_blocks_per_sm(int W) {
+  size_t smem = align_smem_bytes(W);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(align_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_reads_kernel, kBlockThreads, align_smem_bytes(W));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_reads_kernel, kBlockThreads, smem);
   return nb;
 }
 

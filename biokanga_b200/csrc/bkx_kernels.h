@@ -9,6 +9,7 @@
 namespace bkx {
 struct DevIndex;
 struct KParams;
+struct HashPool;
 
 cudaError_t launch_pack_genome(const uint8_t* seq, uint64_t n, uint64_t* g2, uint64_t* gx, uint32_t* gxc,
                                unsigned long long* bad, cudaStream_t st);
@@ -19,7 +20,7 @@ size_t align_smem_bytes(int W);
 int align_blocks_per_sm(int W);
 cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                          uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats, unsigned int* cursor,
-                         uint64_t* hash_pool, uint32_t hash_slots, uint32_t* epochs, int grid, cudaStream_t st);
+                         const HashPool& hp, int grid, cudaStream_t st);
 cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,
                         uint32_t* len_dist, uint8_t* orphan_flag, cudaStream_t st);
 }  // namespace bkx
