@@ -16,6 +16,7 @@
 #include <unistd.h>
 
 #include "bkx_align.cuh"
+#include "bkx_fast.cuh"
 #include "bkx_kernels.h"
 
 using namespace bkx;
@@ -47,6 +48,8 @@ struct Slot {
   size_t bases_cap = 0;
   uint64_t* d_offs = nullptr;
   bkx_read_result* d_out = nullptr;
+  uint32_t* d_hard = nullptr;   // reads the fast kernel deferred to the general kernel
+  size_t hard_cap = 0;
   size_t reads_cap = 0;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
   bool timed = false;
@@ -61,7 +64,9 @@ struct bkx_index {
   // runtime workspace
   std::mutex mtx;
   Slot slot[2];
-  unsigned int* d_cursor[2] = {nullptr, nullptr};
+  unsigned int* d_cursor[2] = {nullptr, nullptr};   // per slot: [0] fast cursor, [1] general cursor, [2] deferred count
+  int fast_grid = 0;
+  int fast_W = 0;
   HashPool hp{};
   int grid = 0;
   int grid_W = 0;
@@ -168,6 +173,23 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
   CU(cudaMemcpy(d_ee, ee.data(), n_ent * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(d_ei, ei.data(), n_ent * 4, cudaMemcpyHostToDevice));
   x->d.ent_start = d_es; x->d.ent_end = d_ee; x->d.ent_id = d_ei; x->d.n_ent = n_ent;
+  {  // coarse offset -> entry table (<= 1M blocks): first entry whose end is at or after the block start
+    uint32_t shift = 8;
+    while (((n >> shift) + 1) > (1u << 20)) ++shift;
+    size_t nb = (size_t)(n >> shift) + 1;
+    std::vector<uint32_t> lut(nb);
+    uint32_t e = 0;
+    for (size_t b = 0; b < nb; ++b) {
+      uint64_t start = (uint64_t)b << shift;
+      while (e < n_ent && ee[e] < start) ++e;
+      lut[b] = e;
+    }
+    uint32_t* d_lut;
+    if ((rc = dev_alloc(x, &d_lut, nb, false)) < 0) return rc;
+    CU(cudaMemcpy(d_lut, lut.data(), nb * 4, cudaMemcpyHostToDevice));
+    x->d.ent_lut = d_lut;
+    x->d.lut_shift = shift;
+  }
   // prefix table
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
@@ -197,7 +219,7 @@ static int new_index(int device, bkx_index** out) {
     CU(cudaStreamCreateWithFlags(&x->slot[s].st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&x->slot[s].k0));
     CU(cudaEventCreate(&x->slot[s].k1));
-    CU(cudaMalloc((void**)&x->d_cursor[s], sizeof(unsigned int)));
+    CU(cudaMalloc((void**)&x->d_cursor[s], 4 * sizeof(unsigned int)));
   }
   CU(cudaMalloc((void**)&x->d_stats, sizeof(bkx_align_stats)));
   CU(cudaMalloc((void**)&x->d_pe_stats, sizeof(bkx_pe_stats)));
@@ -214,6 +236,7 @@ extern "C" void bkx_close_index(bkx_index* x) {
     if (x->slot[s].d_bases) cudaFree(x->slot[s].d_bases);
     if (x->slot[s].d_offs) cudaFree(x->slot[s].d_offs);
     if (x->slot[s].d_out) cudaFree(x->slot[s].d_out);
+    if (x->slot[s].d_hard) cudaFree(x->slot[s].d_hard);
     if (x->slot[s].k0) cudaEventDestroy(x->slot[s].k0);
     if (x->slot[s].k1) cudaEventDestroy(x->slot[s].k1);
     if (x->slot[s].st) cudaStreamDestroy(x->slot[s].st);
@@ -528,7 +551,34 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
     x->hp.n_tables = n_tables;
     x->hp.slots = slots;
   }
+  {
+    int Wf = std::min(W, kFastMaxLen / 32 + 1);
+    if (Wf > x->fast_W || x->fast_grid == 0) {
+      int nb = fast_blocks_per_sm(Wf);
+      if (nb < 1) return fail(BKX_ERR_CUDA, "fast align kernel does not fit on an SM (W=%d)", Wf);
+      int sms = 0;
+      CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, x->device));
+      x->fast_grid = nb * sms;
+      x->fast_W = Wf;
+    }
+  }
   *W_out = x->grid_W;
+  return BKX_OK;
+}
+
+// fast kernel over all reads, then the general kernel over the reads it deferred (same stream)
+static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n,
+                       int W, bkx_read_result* d_out, bkx_align_stats* d_stats, int si, uint32_t* d_hard,
+                       cudaStream_t st) {
+  unsigned int* cur = x->d_cursor[si];
+  if (getenv("BKX_NO_FAST")) {
+    CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, nullptr, nullptr, x->grid, st));
+    x->launches += 1;
+    return BKX_OK;
+  }
+  CU(launch_align_fast(x->d, k, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_grid, st));
+  CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, d_hard, cur + 2, x->grid, st));
+  x->launches += 2;
   return BKX_OK;
 }
 
@@ -546,13 +596,18 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
   if ((rc = prepare_launch(x, k, max_read_len, &W)) < 0) return rc;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : x->slot[0].st;
   Slot& s = x->slot[0];
+  if (n_reads > s.hard_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (s.d_hard) cudaFree(s.d_hard);
+    s.hard_cap = (size_t)n_reads * 5 / 4;
+    CU(cudaMalloc((void**)&s.d_hard, s.hard_cap * 4));
+  }
   CU(cudaEventRecord(s.k0, st));
-  CU(launch_align(x->d, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, x->d_cursor[0], x->hp, x->grid, st));
+  if ((rc = launch_both(x, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, 0, s.d_hard, st)) < 0) return rc;
   CU(cudaEventRecord(s.k1, st));
   s.timed = true;
   x->slot[1].timed = false;
   x->last_ms = -2.f;  // resolved lazily by bkx_last_kernel_ms
-  x->launches += 1;
   return BKX_OK;
 }
 
@@ -607,16 +662,20 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
       CU(cudaMalloc((void**)&s.d_offs, (s.reads_cap + 1) * 8));
       CU(cudaMalloc((void**)&s.d_out, s.reads_cap * sizeof(bkx_read_result)));
     }
+    if (cnt > s.hard_cap) {
+      if (s.d_hard) cudaFree(s.d_hard);
+      s.hard_cap = (size_t)cnt * 5 / 4;
+      CU(cudaMalloc((void**)&s.d_hard, s.hard_cap * 4));
+    }
     CU(cudaMemcpyAsync(s.d_bases, bases + offsets[start], nb, cudaMemcpyHostToDevice, s.st));
     CU(cudaMemcpyAsync(s.d_offs, offsets + start, ((size_t)cnt + 1) * 8, cudaMemcpyHostToDevice, s.st));
     CU(cudaEventRecord(s.k0, s.st));
     // offsets stay absolute: hand the kernel a base pointer shifted by the slice start
-    CU(launch_align(x->d, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, x->d_cursor[b],
-                    x->hp, x->grid, s.st));
+    if ((rc = launch_both(x, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard,
+                          s.st)) < 0) return rc;
     CU(cudaEventRecord(s.k1, s.st));
     CU(cudaMemcpyAsync(out + start, s.d_out, (size_t)cnt * sizeof(bkx_read_result), cudaMemcpyDeviceToHost, s.st));
     inflight[b] = true;
-    x->launches += 1;
     start += cnt;
     b ^= 1;
   }

@@ -9,7 +9,7 @@
 //        elements (n >= 4e9) split into a u32 low plane and a u8 high plane           4n (+n) bytes
 //   pt   k-mer prefix table: pt[x] = number of suffixes whose first-k symbols sort below the ACGT
 //        k-mer x (first base most significant); 4^k+1 entries of u32 (u64 when n >= 2^32)
-//   ent  chromosome table sorted by start offset
+//   ent  chromosome table sorted by start offset + a coarse block -> entry lookup table
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -27,6 +27,8 @@ struct DevIndex {
   const uint64_t* ent_start;
   const uint64_t* ent_end;
   const uint32_t* ent_id;
+  const uint32_t* ent_lut;  // ent_lut[ofs >> lut_shift] = first entry whose end_ofs >= (block start)
+  uint32_t lut_shift;
   uint64_t n;  // ConcatSeqLen
   uint32_t n_ent;
   int k;
@@ -93,15 +95,11 @@ __device__ __forceinline__ uint64_t spread32(uint32_t x) {
 // chromosome (entry) index containing concatenation offset ofs, or -1 (MapChunkHit2Entry,
 // libbiokanga/SfxArrayV2.cpp:2530-2575).
 __device__ __forceinline__ int find_entry(const DevIndex& I, uint64_t ofs) {
-  int lo = 0, hi = (int)I.n_ent - 1;
-  while (hi >= lo) {
-    int mid = (hi + lo) >> 1;
-    uint64_t s = __ldg(I.ent_start + mid);
-    if (s > ofs) { hi = mid - 1; continue; }
-    if (__ldg(I.ent_end + mid) >= ofs) return mid;
-    lo = mid + 1;
-  }
-  return -1;
+  if (ofs >= I.n) return -1;
+  uint32_t e = __ldg(I.ent_lut + (ofs >> I.lut_shift));
+  while (e < I.n_ent && __ldg(I.ent_end + e) < ofs) ++e;
+  if (e >= I.n_ent || __ldg(I.ent_start + e) > ofs) return -1;  // ofs sits on a terminator
+  return (int)e;
 }
 
 }  // namespace bkx

@@ -1,5 +1,6 @@
 // CUDA kernels of the bkx library (sm_100a): index preparation, read alignment, paired-end pairing.
 #include "bkx_align.cuh"
+#include "bkx_fast.cuh"
 #include "bkx_kernels.h"
 
 #include <cub/device/device_scan.cuh>
@@ -172,10 +173,11 @@ struct BlockStats {
 __global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
-    HashPool hp) {
+    HashPool hp, const uint32_t* __restrict__ ids, const unsigned int* __restrict__ n_ids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockStats bs;
   constexpr int G = kGroup;
+  if (ids) n_reads = *n_ids;  // second pass: only the reads the fast kernel deferred
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
   __syncthreads();
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
     if (c.gl == 0) r = atomicAdd(cursor, 1u);
     r = c.bcast(r, 0);
     if (r >= n_reads) break;
+    if (ids) r = ids[r];
     const uint64_t o0 = __ldg(offs + r);
     const int L = (int)(__ldg(offs + r + 1) - o0);
     const uint8_t* rd = bases + o0;
@@ -332,25 +335,395 @@ __global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
 
 cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                          uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats, unsigned int* cursor,
-                         const HashPool& hp, int grid, cudaStream_t st) {
+                         const HashPool& hp, const uint32_t* ids, const unsigned int* n_ids, int grid, cudaStream_t st) {
   size_t smem = align_smem_bytes(W);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 40 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(align_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
-  align_reads_kernel<<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hp);
+  align_reads_kernel<<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hp, ids,
+                                                        n_ids);
   return cudaGetLastError();
 }
 
 int align_blocks_per_sm(int W) {
   size_t smem = align_smem_bytes(W);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(align_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 40 * 1024) cudaFuncSetAttribute(align_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_reads_kernel, kBlockThreads, smem);
+  return nb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: one lane per read (see bkx_fast.cuh)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stats_add(BlockStats& bs, const bkx_read_result& res) {
+  atomicAdd(&bs.nar[res.nar], 1u);
+  if (res.nar == BKX_NAR_ACCEPTED) atomicAdd(res.strand == '+' ? &bs.plus : &bs.minus, 1u);
+  atomicAdd(&bs.seeds, (unsigned long long)res.seeds);
+  atomicAdd(&bs.cands, (unsigned long long)res.cands);
+}
+
+__device__ __forceinline__ void stats_flush(const BlockStats& bs, bkx_align_stats* stats) {
+  for (int i = threadIdx.x; i < BKX_NAR_COUNT; i += blockDim.x)
+    if (bs.nar[i]) atomicAdd((unsigned long long*)&stats->nar[i], (unsigned long long)bs.nar[i]);
+  if (threadIdx.x == 0) {
+    unsigned long long reads = 0;
+    for (int i = 0; i < BKX_NAR_COUNT; ++i) reads += bs.nar[i];
+    atomicAdd((unsigned long long*)&stats->plus_hits, (unsigned long long)bs.plus);
+    atomicAdd((unsigned long long*)&stats->minus_hits, (unsigned long long)bs.minus);
+    atomicAdd((unsigned long long*)&stats->num_sloughed_ns, (unsigned long long)bs.nar[BKX_NAR_NS]);
+    atomicAdd((unsigned long long*)&stats->tot_non_aligned,
+              (unsigned long long)bs.nar[BKX_NAR_NOHIT] + bs.nar[BKX_NAR_MULTIALIGN]);
+    atomicAdd((unsigned long long*)&stats->tot_accepted_unique, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
+    atomicAdd((unsigned long long*)&stats->tot_accepted_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
+    atomicAdd((unsigned long long*)&stats->tot_loci_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
+    atomicAdd((unsigned long long*)&stats->tot_not_accepted_delta, (unsigned long long)bs.nar[BKX_NAR_MMDELTA]);
+    atomicAdd((unsigned long long*)&stats->seeds, bs.seeds);
+    atomicAdd((unsigned long long*)&stats->cands, bs.cands);
+    atomicAdd((unsigned long long*)&stats->reads, reads);
+  }
+}
+
+__global__ void __launch_bounds__(kFastThreads, 2) align_fast_kernel(
+    DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
+    int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
+    uint32_t* __restrict__ hard_ids, unsigned int* __restrict__ n_hard) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BlockStats bs;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
+  __syncthreads();
+
+  uint64_t* region = (uint64_t*)smem_raw + (size_t)wib * ((size_t)2 * W * 32 + (size_t)kFastSeen * 16);
+  uint64_t* wr0 = region + lane;                   // this lane's forward words (stride 32)
+  uint64_t* wr1 = region + (size_t)W * 32 + lane;  // reverse-complement words
+  FastLane f;
+  f.w2[0] = wr0;
+  f.w2[1] = wr1;
+  f.seen = (uint32_t*)(region + (size_t)2 * W * 32) + lane;
+  f.L = 0;
+  const int k = I.k;
+  const int s_first = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
+  const int s_last = (P.strand_mode == BKX_STRAND_WATSON) ? 0 : 1;
+
+  // ---- per-lane state of the read in flight
+  bool active = false, exhausted = false;
+  uint32_t r = 0;
+  int L = 0, max_tot_mm = 0, core_len = 0, core_delta = 0, slides = 0;
+  int allow = 0;
+  bool in_final = false;
+  int mm_max = 0, CL = 0, delta = 0, K = 0, n_cores = 0, last_ofs = 0;
+  int s = 0, ci = 0, seen_n = 0;
+  int inst = 0, low = 0, nxt = 0, hit_strand = 0, hit_ent = -1, hit_mm = 0;
+  uint64_t hit_p = 0;
+  uint32_t seeds = 0, cands = 0;
+
+  // returns false if the read has no further phase (=> eHRnone)
+  auto setup_phase = [&]() -> bool {
+    if (!in_final) {
+      bool staged = false;
+      if (max_tot_mm > 0 && allow <= max_tot_mm) {
+        int cl = L / (allow + P.mmd);
+        if (cl > core_len) { staged = true; CL = cl; delta = cl; mm_max = allow; }
+      }
+      if (!staged) {
+        if (max_tot_mm > 0 && allow > max_tot_mm) return false;  // staged loop ran out: no final phase
+        in_final = true;
+        CL = core_len; delta = core_delta; mm_max = max_tot_mm;
+      }
+    } else {
+      return false;
+    }
+    K = (L - CL - delta >= 0) ? (L - CL - delta) / delta + 1 : 0;
+    int rr = L - (K * delta + CL);
+    n_cores = K + 1 + ((rr > CL / 3) ? 1 : 0);
+    if (n_cores > slides) n_cores = slides;
+    if (L < CL) n_cores = 0;
+    last_ofs = L - CL;
+    inst = 0;
+    low = nxt = mm_max + P.mmd + 1;
+    s = s_first;
+    ci = 0;
+    seen_n = 0;
+    return true;
+  };
+
+  auto finish = [&](int hr) {
+    bkx_read_result res;
+    res.nar = BKX_NAR_NOHIT; res.hit_rslt = (uint8_t)hr; res.strand = 0; res.num_hits = 0; res.low_mm = 0;
+    res.nxt_low_mm = 0; res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0;
+    res.mismatches = 0; res.flags = 0; res.seeds = seeds; res.cands = cands; res.reserved = 0;
+    int ii = inst > P.max_hits ? P.max_hits + 1 : inst;
+    if (hr == BKX_HR_HITS) {
+      res.nar = BKX_NAR_ACCEPTED;
+      res.num_hits = 1;
+      res.strand = hit_strand ? '-' : '+';
+      res.chrom_id = __ldg(I.ent_id + hit_ent);
+      res.match_loci = (uint32_t)(hit_p - __ldg(I.ent_start + hit_ent));
+      res.match_len = (uint16_t)L;
+      res.mismatches = (uint8_t)hit_mm;
+      res.low_hit_instances = 1;
+      res.low_mm = (int8_t)low;
+      res.nxt_low_mm = (int8_t)nxt;
+    } else if (hr == BKX_HR_MMDELTA || hr == BKX_HR_HITINSTS) {
+      res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
+      res.strand = '?';
+      res.match_len = (uint16_t)L;
+      res.low_hit_instances = (int16_t)ii;
+      res.low_mm = (int8_t)low;
+      res.nxt_low_mm = (int8_t)nxt;
+    }
+    out[r] = res;
+    stats_add(bs, res);
+    active = false;
+  };
+
+  auto defer = [&]() {
+    unsigned int at = atomicAdd(n_hard, 1u);
+    hard_ids[at] = r;
+    active = false;
+  };
+
+  for (;;) {
+    // ---- (1) idle lanes claim the next reads (one atomic per warp)
+    const bool want = !active && !exhausted;
+    const unsigned need = __ballot_sync(0xffffffffu, want);
+    if (need) {
+      const int leader = __ffs(need) - 1;
+      unsigned int base_r = 0;
+      if (lane == leader) base_r = atomicAdd(cursor, (unsigned int)__popc(need));
+      base_r = __shfl_sync(0xffffffffu, base_r, leader);
+      if (want) {
+        r = base_r + __popc(need & lt);
+        if (r >= n_reads) {
+          exhausted = true;
+        } else {
+          active = true;
+          const uint64_t o0 = __ldg(offs + r);
+          L = (int)(__ldg(offs + r + 1) - o0);
+          seeds = cands = 0;
+          if (L > kFastMaxLen || ((L + 31) >> 5) + 1 > W) {
+            defer();
+          } else {
+            const uint8_t* rd = bases + o0;
+            int nN = 0;
+            bool bad = false;
+            const int words = (L + 31) >> 5;
+            for (int w = 0; w < words; ++w) {
+              uint64_t code2 = 0;
+              const int i0 = w * 32;
+              const int cntb = min(32, L - i0);
+              for (int j = 0; j < cntb; ++j) {
+                unsigned b = __ldg(rd + i0 + j) & 0x07;
+                bad |= (b > 4);
+                nN += (b == 4);
+                code2 |= (uint64_t)(b & 3) << (2 * j);
+              }
+              wr0[w * 32] = code2;
+            }
+            wr0[words * 32] = 0;
+            int max_ns_seq = 0;
+            if (P.max_ns) max_ns_seq = max((L * P.max_ns) / 100, P.max_ns);
+            if (bad || nN > max_ns_seq || L < 1) {
+              bkx_read_result res;
+              res.nar = BKX_NAR_NS; res.hit_rslt = 0; res.strand = 0; res.num_hits = 0; res.low_mm = 0; res.nxt_low_mm = 0;
+              res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0; res.mismatches = 0;
+              res.flags = 0; res.seeds = 0; res.cands = 0; res.reserved = 0;
+              out[r] = res;
+              stats_add(bs, res);
+              active = false;
+            } else if (nN > 0) {
+              defer();  // N-bearing reads need the symbol-wise compare of the general kernel
+            } else {
+              // reverse complement from the packed forward words
+              f.L = L;
+              for (int w = 0; w < words; ++w) {
+                int t = L - 32 * (w + 1);  // forward position of the last base of this rc word
+                uint64_t fw;
+                if (t >= 0) fw = fl_word(f, 0, t);
+                else fw = wr0[0] << (2 * (-t));
+                uint64_t rc = rev2(~fw);
+                int len = min(32, L - 32 * w);
+                if (len < 32) rc &= (1ull << (2 * len)) - 1;
+                wr1[w * 32] = rc;
+              }
+              wr1[words * 32] = 0;
+              // per-read search parameters, Aligner.cpp:9085-9095
+              max_tot_mm = P.max_subs == 0 ? 0 : max(1, (L * P.max_subs + 50) / 100);
+              if (max_tot_mm > 63) max_tot_mm = 63;
+              core_len = max(P.min_core_len, L / (P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
+              slides = max(1, (P.slides_per100 * L + 99) / 100);
+              core_delta = max(L / slides - 1, core_len);
+              allow = 0;
+              in_final = false;
+              hit_ent = -1;
+              hit_p = 0;
+              inst = low = nxt = 0;
+              while (active) {  // first phase with at least one core
+                if (!setup_phase()) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); break; }
+                if (n_cores > 0) break;
+                if (in_final) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); break; }
+                ++allow;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) {
+      if (__all_sync(0xffffffffu, exhausted)) break;
+      continue;
+    }
+    // ---- (2) one core of the current strand/phase for every active lane
+    if (active) {
+      const int cofs = ci <= K ? ci * delta : last_ofs;
+      ++seeds;
+      bool dfr = false, stop_all = false;
+      // SA interval of the core: prefix-table bucket, then lower / upper bound
+      uint64_t key = rev2(fl_word(f, s, cofs)) >> (64 - 2 * k);
+      uint64_t blo, bhi;
+      if (CL >= k) {
+        blo = pt_get(I, key);
+        bhi = pt_get(I, key + 1);
+      } else {
+        int sh = 2 * (k - CL);
+        uint64_t p = key >> sh;
+        blo = pt_get(I, p << sh);
+        bhi = pt_get(I, (p + 1) << sh);
+      }
+      uint64_t first = 0, cnt = 0;
+      if (blo < bhi) {
+        uint64_t l = blo, h = bhi;
+        bool h_equal = false;
+        while (l < h) {
+          uint64_t m = l + ((h - l) >> 1);
+          uint64_t g = sa_get(I, m);
+          if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
+          int c = fl_cmp(I, f, s, cofs, CL, g);
+          if (c > 0) l = m + 1; else { h = m; h_equal = (c == 0); }
+        }
+        if (!dfr && l < bhi && h_equal) {
+          first = l;
+          // upper bound by stepping: intervals kept in the fast path are short
+          uint64_t ul = l + 1;
+          while (ul < bhi) {
+            if (ul - first >= (uint64_t)kFastMaxCnt) { dfr = true; break; }
+            uint64_t g = sa_get(I, ul);
+            if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
+            if (fl_cmp(I, f, s, cofs, CL, g) != 0) break;
+            ++ul;
+          }
+          cnt = ul - first;
+        }
+      }
+      // interval walk, strictly sequential (SfxArrayV2.cpp:5857-6209)
+      for (uint64_t e = 0; e < cnt && !dfr; ++e) {
+        uint64_t loci = sa_get(I, first + e);
+        if (loci < (uint64_t)cofs) continue;
+        uint64_t p = loci - (uint64_t)cofs;
+        int ent = find_entry(I, p);
+        if (ent < 0 || (p + (uint64_t)L - 1) > __ldg(I.ent_end + ent)) continue;
+        uint32_t kk = (uint32_t)(1u + (uint32_t)loci - (uint32_t)cofs);
+        bool dup = false;
+        for (int i = 0; i < seen_n; ++i) dup |= (f.seen[i * 32] == kk);
+        if (dup) continue;
+        if (seen_n >= kFastSeen) { dfr = true; break; }
+        f.seen[seen_n * 32] = kk;
+        ++seen_n;
+        ++cands;
+        if (span_has_exc(I, p, (uint32_t)L)) { dfr = true; break; }
+        // Hamming over packed words; rejected once > MaxTotMM or >= NxtLowMMCnt (SfxArrayV2.cpp:6148-6151)
+        uint64_t w = p >> 5;
+        unsigned sh = (unsigned)(p & 31) * 2;
+        uint64_t prev = __ldg(I.g2 + w);
+        int mm = 0;
+        const int lim = min(mm_max, nxt - 1);
+        for (int b = 0, wi = 0; b < L; b += 32, ++wi) {
+          uint64_t next = __ldg(I.g2 + (++w));
+          uint64_t gw = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
+          prev = next;
+          uint64_t x = f.w2[s][wi * 32] ^ gw;
+          uint64_t m = (x | (x >> 1)) & 0x5555555555555555ull;
+          int rem = L - b;
+          if (rem < 32) m &= (1ull << (2 * rem)) - 1;
+          mm += __popcll(m);
+          if (mm > lim) break;
+        }
+        if (mm > lim) continue;
+        if (mm < low) {
+          inst = 1; nxt = low; low = mm;
+          hit_p = p; hit_ent = ent; hit_mm = mm; hit_strand = s;
+        } else if (mm == low) {
+          ++inst;
+        } else {
+          nxt = mm;  // low < mm < nxt
+        }
+        if (inst > P.max_hits && low == 0) { stop_all = true; break; }
+      }
+      if (dfr) {
+        defer();
+      } else {
+        // advance: next core / strand / phase
+        ++ci;
+        bool phase_done = stop_all;
+        if (!phase_done && ci >= n_cores) {
+          if (s < s_last) { ++s; ci = 0; seen_n = 0; }
+          else phase_done = true;
+        }
+        if (phase_done) {
+          if (inst == 0) {
+            bool more = true;
+            for (;;) {
+              if (in_final) { more = false; break; }
+              ++allow;
+              if (!setup_phase()) { more = false; break; }
+              if (n_cores > 0) break;
+            }
+            if (!more) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); }
+          } else if ((nxt - low) < P.mmd) {
+            finish(BKX_HR_MMDELTA);
+          } else if (inst > P.max_hits) {
+            finish(BKX_HR_HITINSTS);
+          } else {
+            finish(BKX_HR_HITS);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (stats) stats_flush(bs, stats);
+}
+
+cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
+                              uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
+                              unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, int grid, cudaStream_t st) {
+  size_t smem = fast_smem_bytes(W);
+  static size_t configured = 0;
+  if (smem > 40 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(align_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(n_hard, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  align_fast_kernel<<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids, n_hard);
+  return cudaGetLastError();
+}
+
+int fast_blocks_per_sm(int W) {
+  size_t smem = fast_smem_bytes(W);
+  if (smem > 40 * 1024) cudaFuncSetAttribute(align_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_fast_kernel, kFastThreads, smem);
   return nb;
 }
 

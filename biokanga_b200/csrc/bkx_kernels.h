@@ -20,7 +20,11 @@ size_t align_smem_bytes(int W);
 int align_blocks_per_sm(int W);
 cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                          uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats, unsigned int* cursor,
-                         const HashPool& hp, int grid, cudaStream_t st);
+                         const HashPool& hp, const uint32_t* ids, const unsigned int* n_ids, int grid, cudaStream_t st);
+int fast_blocks_per_sm(int W);
+cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
+                              uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
+                              unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, int grid, cudaStream_t st);
 cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,
                         uint32_t* len_dist, uint8_t* orphan_flag, cudaStream_t st);
 }  // namespace bkx
