@@ -156,6 +156,18 @@ cudaError_t build_prefix_table(const DevIndex& I, int k, void* table, bool wide,
 // ------------------------------------------------------------------------------------------------
 constexpr int kGroupsPerBlock = kBlockThreads / kGroup;
 
+// the dynamic shared-memory opt-in of a kernel is only ever raised (several indexes share the kernels)
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t smem, size_t& configured) {
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  return cudaSuccess;
+}
+static size_t g_smem_general = 0, g_smem_fast = 0;
+
 __host__ __device__ inline size_t group_smem_bytes(int W) {
   size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + (kGroup + 2) * 4;
   return (per + 15) & ~(size_t)15;
@@ -337,13 +349,9 @@ cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bas
                          uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats, unsigned int* cursor,
                          const HashPool& hp, const uint32_t* ids, const unsigned int* n_ids, int grid, cudaStream_t st) {
   size_t smem = align_smem_bytes(W);
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(align_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
+  cudaError_t e = ensure_smem(align_reads_kernel, smem, g_smem_general);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   align_reads_kernel<<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hp, ids,
                                                         n_ids);
@@ -352,7 +360,7 @@ cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bas
 
 int align_blocks_per_sm(int W) {
   size_t smem = align_smem_bytes(W);
-  if (smem > 40 * 1024) cudaFuncSetAttribute(align_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_smem(align_reads_kernel, smem, g_smem_general);
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_reads_kernel, kBlockThreads, smem);
   return nb;
@@ -499,79 +507,89 @@ __global__ void __launch_bounds__(kFastThreads, 2) align_fast_kernel(
       unsigned int base_r = 0;
       if (lane == leader) base_r = atomicAdd(cursor, (unsigned int)__popc(need));
       base_r = __shfl_sync(0xffffffffu, base_r, leader);
+      bool fresh = false;   // this lane just received a read that fits the fast path
+      int nN = 0;
+      bool bad = false;
       if (want) {
         r = base_r + __popc(need & lt);
         if (r >= n_reads) {
           exhausted = true;
         } else {
           active = true;
-          const uint64_t o0 = __ldg(offs + r);
-          L = (int)(__ldg(offs + r + 1) - o0);
           seeds = cands = 0;
-          if (L > kFastMaxLen || ((L + 31) >> 5) + 1 > W) {
-            defer();
-          } else {
-            const uint8_t* rd = bases + o0;
-            int nN = 0;
-            bool bad = false;
-            const int words = (L + 31) >> 5;
-            for (int w = 0; w < words; ++w) {
-              uint64_t code2 = 0;
-              const int i0 = w * 32;
-              const int cntb = min(32, L - i0);
-              for (int j = 0; j < cntb; ++j) {
-                unsigned b = __ldg(rd + i0 + j) & 0x07;
-                bad |= (b > 4);
-                nN += (b == 4);
-                code2 |= (uint64_t)(b & 3) << (2 * j);
-              }
-              wr0[w * 32] = code2;
-            }
-            wr0[words * 32] = 0;
-            int max_ns_seq = 0;
-            if (P.max_ns) max_ns_seq = max((L * P.max_ns) / 100, P.max_ns);
-            if (bad || nN > max_ns_seq || L < 1) {
-              bkx_read_result res;
-              res.nar = BKX_NAR_NS; res.hit_rslt = 0; res.strand = 0; res.num_hits = 0; res.low_mm = 0; res.nxt_low_mm = 0;
-              res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0; res.mismatches = 0;
-              res.flags = 0; res.seeds = 0; res.cands = 0; res.reserved = 0;
-              out[r] = res;
-              stats_add(bs, res);
-              active = false;
-            } else if (nN > 0) {
-              defer();  // N-bearing reads need the symbol-wise compare of the general kernel
-            } else {
-              // reverse complement from the packed forward words
-              f.L = L;
-              for (int w = 0; w < words; ++w) {
-                int t = L - 32 * (w + 1);  // forward position of the last base of this rc word
-                uint64_t fw;
-                if (t >= 0) fw = fl_word(f, 0, t);
-                else fw = wr0[0] << (2 * (-t));
-                uint64_t rc = rev2(~fw);
-                int len = min(32, L - 32 * w);
-                if (len < 32) rc &= (1ull << (2 * len)) - 1;
-                wr1[w * 32] = rc;
-              }
-              wr1[words * 32] = 0;
-              // per-read search parameters, Aligner.cpp:9085-9095
-              max_tot_mm = P.max_subs == 0 ? 0 : max(1, (L * P.max_subs + 50) / 100);
-              if (max_tot_mm > 63) max_tot_mm = 63;
-              core_len = max(P.min_core_len, L / (P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
-              slides = max(1, (P.slides_per100 * L + 99) / 100);
-              core_delta = max(L / slides - 1, core_len);
-              allow = 0;
-              in_final = false;
-              hit_ent = -1;
-              hit_p = 0;
-              inst = low = nxt = 0;
-              while (active) {  // first phase with at least one core
-                if (!setup_phase()) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); break; }
-                if (n_cores > 0) break;
-                if (in_final) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); break; }
-                ++allow;
-              }
-            }
+          L = (int)(__ldg(offs + r + 1) - __ldg(offs + r));
+          if (L > kFastMaxLen || ((L + 31) >> 5) + 1 > W) defer();
+          else fresh = true;
+        }
+      }
+      // ---- the warp packs the new reads together: coalesced 32-byte rows, ballots build the 2-bit words
+      unsigned pk = __ballot_sync(0xffffffffu, fresh);
+      while (pk) {
+        const int j = __ffs(pk) - 1;
+        pk &= pk - 1;
+        const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
+        const int Lj = __shfl_sync(0xffffffffu, L, j);
+        const uint8_t* rd = bases + __ldg(offs + rj);
+        const int words = (Lj + 31) >> 5;
+        int nNj = 0;
+        unsigned badj = 0;
+        for (int w = 0; w < words; ++w) {
+          const int i = w * 32 + lane;
+          unsigned b = (i < Lj) ? (__ldg(rd + i) & 0x07u) : 0u;
+          unsigned b0 = __ballot_sync(0xffffffffu, b & 1u), b1 = __ballot_sync(0xffffffffu, b & 2u);
+          unsigned bn = __ballot_sync(0xffffffffu, b == 4u);
+          badj |= __ballot_sync(0xffffffffu, b > 4u);
+          if (lane == 0) region[w * 32 + j] = spread32(b0) | (spread32(b1) << 1);
+          nNj += __popc(bn);
+        }
+        if (lane == 0) region[words * 32 + j] = 0;
+        if (lane == j) { nN = nNj; bad = badj != 0; }
+      }
+      __syncwarp();
+      if (fresh) {
+        const int words = (L + 31) >> 5;
+        int max_ns_seq = 0;
+        if (P.max_ns) max_ns_seq = max((L * P.max_ns) / 100, P.max_ns);
+        if (bad || nN > max_ns_seq || L < 1) {
+          bkx_read_result res;
+          res.nar = BKX_NAR_NS; res.hit_rslt = 0; res.strand = 0; res.num_hits = 0; res.low_mm = 0; res.nxt_low_mm = 0;
+          res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0; res.mismatches = 0;
+          res.flags = 0; res.seeds = 0; res.cands = 0; res.reserved = 0;
+          out[r] = res;
+          stats_add(bs, res);
+          active = false;
+        } else if (nN > 0) {
+          defer();  // N-bearing reads need the symbol-wise compare of the general kernel
+        } else {
+          // reverse complement from the packed forward words
+          f.L = L;
+          for (int w = 0; w < words; ++w) {
+            int t = L - 32 * (w + 1);  // forward position of the last base of this rc word
+            uint64_t fw;
+            if (t >= 0) fw = fl_word(f, 0, t);
+            else fw = wr0[0] << (2 * (-t));
+            uint64_t rc = rev2(~fw);
+            int len = min(32, L - 32 * w);
+            if (len < 32) rc &= (1ull << (2 * len)) - 1;
+            wr1[w * 32] = rc;
+          }
+          wr1[words * 32] = 0;
+          // per-read search parameters, Aligner.cpp:9085-9095
+          max_tot_mm = P.max_subs == 0 ? 0 : max(1, (L * P.max_subs + 50) / 100);
+          if (max_tot_mm > 63) max_tot_mm = 63;
+          core_len = max(P.min_core_len, L / (P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
+          slides = max(1, (P.slides_per100 * L + 99) / 100);
+          core_delta = max(L / slides - 1, core_len);
+          allow = 0;
+          in_final = false;
+          hit_ent = -1;
+          hit_p = 0;
+          inst = low = nxt = 0;
+          while (active) {  // first phase with at least one core
+            if (!setup_phase()) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); break; }
+            if (n_cores > 0) break;
+            if (in_final) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); break; }
+            ++allow;
           }
         }
       }
@@ -705,13 +723,9 @@ cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t
                               uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
                               unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, int grid, cudaStream_t st) {
   size_t smem = fast_smem_bytes(W);
-  static size_t configured = 0;
-  if (smem > 40 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(align_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
+  cudaError_t e = ensure_smem(align_fast_kernel, smem, g_smem_fast);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(n_hard, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
@@ -721,7 +735,7 @@ cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t
 
 int fast_blocks_per_sm(int W) {
   size_t smem = fast_smem_bytes(W);
-  if (smem > 40 * 1024) cudaFuncSetAttribute(align_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_smem(align_fast_kernel, smem, g_smem_fast);
   int nb = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_fast_kernel, kFastThreads, smem);
   return nb;
