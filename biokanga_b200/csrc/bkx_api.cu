@@ -17,6 +17,7 @@
 
 #include "bkx_align.cuh"
 #include "bkx_fast.cuh"
+#include "bkx_rescue.cuh"
 #include "bkx_kernels.h"
 
 using namespace bkx;
@@ -176,6 +177,17 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
   CU(cudaMemcpy(d_ee, ee.data(), n_ent * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(d_ei, ei.data(), n_ent * 4, cudaMemcpyHostToDevice));
   x->d.ent_start = d_es; x->d.ent_end = d_ee; x->d.ent_id = d_ei; x->d.n_ent = n_ent;
+  {  // entry id -> sorted index
+    uint32_t max_id = 0;
+    for (uint32_t i = 0; i < n_ent; ++i) max_id = std::max(max_id, ei[i]);
+    std::vector<uint32_t> inv((size_t)max_id + 1, 0xffffffffu);
+    for (uint32_t i = 0; i < n_ent; ++i) inv[ei[i]] = i;
+    uint32_t* d_inv;
+    if ((rc = dev_alloc(x, &d_inv, inv.size(), false)) < 0) return rc;
+    CU(cudaMemcpy(d_inv, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+    x->d.ent_of_id = d_inv;
+    x->d.max_ent_id = max_id;
+  }
   {  // coarse offset -> entry table (<= 1M blocks): first entry whose end is at or after the block start
     uint32_t shift = 8;
     while (((n >> shift) + 1) > (1u << 20)) ++shift;
@@ -713,13 +725,17 @@ extern "C" int bkx_align_one(bkx_index* x, const bkx_align_params* p, const uint
 extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, bkx_read_result* results,
                               uint32_t n_pairs, const uint8_t* bases, const uint64_t* offsets, bkx_pe_stats* stats,
                               uint32_t* len_dist) {
-  (void)p; (void)bases; (void)offsets;
   if (!x || !pe || !results) return fail(BKX_ERR_PARAM, "null argument");
   if (pe->pe_proc < BKX_PE_ORPHAN || pe->pe_proc > BKX_PE_UNIQUE_SE) return fail(BKX_ERR_PARAM, "bad pe_proc %d", pe->pe_proc);
-  if (pe->pe_proc == BKX_PE_ORPHAN || pe->pe_proc == BKX_PE_ORPHAN_SE)
-    return fail(BKX_ERR_UNSUPPORTED, "orphan recovery (-U1/-U3) is not built yet");
+  const bool rescue = pe->pe_proc == BKX_PE_ORPHAN || pe->pe_proc == BKX_PE_ORPHAN_SE;
   if (pe->pair_min_len < 25 || pe->pair_max_len > 100000 || pe->pair_min_len > pe->pair_max_len)
     return fail(BKX_ERR_PARAM, "bad insert size range %d..%d", pe->pair_min_len, pe->pair_max_len);
+  KParams k{};
+  if (rescue) {
+    int rc = check_params(p, &k);
+    if (rc < 0) return rc;
+    if (!bases || !offsets) return fail(BKX_ERR_PARAM, "orphan recovery needs the read sequences");
+  }
   if (n_pairs == 0) return BKX_OK;
   std::lock_guard<std::mutex> lk(x->mtx);
   CU(cudaSetDevice(x->device));
@@ -728,10 +744,28 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
   CU(cudaMemsetAsync(x->d_len_dist, 0, 100001 * 4, st));
   CU(cudaMemsetAsync(x->d_pe_stats, 0, sizeof(bkx_pe_stats), st));
   bkx_read_result* d_res = nullptr;
+  uint32_t* d_list = nullptr;
+  uint8_t* d_bases = nullptr;
+  uint64_t* d_offs = nullptr;
+  unsigned int* cnt = x->d_cursor[0];  // [0] rescue cursor, [3] orphan count
   size_t bytes = (size_t)n_pairs * 2 * sizeof(bkx_read_result);
-  CU(cudaMalloc((void**)&d_res, bytes));
-  cudaError_t e = cudaMemcpyAsync(d_res, results, bytes, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = launch_pair(*pe, d_res, n_pairs, x->d_pe_stats, x->d_len_dist, nullptr, st);
+  cudaError_t e = cudaMalloc((void**)&d_res, bytes);
+  int Lmax = 0;
+  if (e == cudaSuccess && rescue) {
+    uint64_t nb = offsets[2 * (uint64_t)n_pairs] - offsets[0];
+    for (uint64_t i = 0; i < 2 * (uint64_t)n_pairs; ++i) Lmax = std::max<int>(Lmax, (int)(offsets[i + 1] - offsets[i]));
+    e = cudaMalloc((void**)&d_list, (size_t)n_pairs * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_bases, nb + 64);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_offs, (2 * (size_t)n_pairs + 1) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_bases, bases + offsets[0], nb, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_offs, offsets, (2 * (size_t)n_pairs + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnt + 3, 0, sizeof(unsigned int), st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_res, results, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = launch_pair(*pe, d_res, n_pairs, x->d_pe_stats, x->d_len_dist, d_list, cnt + 3, st);
+  if (e == cudaSuccess && rescue && Lmax <= kRescueMaxLen)
+    e = launch_rescue(x->d, k, *pe, d_res, d_list, cnt + 3, d_bases - offsets[0], d_offs, std::max(Lmax, 32), x->d_pe_stats,
+                      x->d_len_dist, cnt, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(results, d_res, bytes, cudaMemcpyDeviceToHost, st);
   bkx_pe_stats hs;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, x->d_pe_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
@@ -741,9 +775,10 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
     e = cudaMemcpyAsync(ld.data(), x->d_len_dist, 100001 * 4, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_res);
+  cudaFree(d_res); cudaFree(d_list); cudaFree(d_bases); cudaFree(d_offs);
   if (e != cudaSuccess) return fail(BKX_ERR_CUDA, "bkx_pair_reads: %s", cudaGetErrorString(e));
-  x->launches += 1;
+  if (rescue && Lmax > kRescueMaxLen) return fail(BKX_ERR_PARAM, "read length %d exceeds cMaxSeqLen", Lmax);
+  x->launches += rescue ? 2 : 1;
   if (stats) {
     uint64_t* d = (uint64_t*)stats;
     const uint64_t* s = (const uint64_t*)&hs;

@@ -27,6 +27,8 @@ struct DevIndex {
   const uint64_t* ent_start;
   const uint64_t* ent_end;
   const uint32_t* ent_id;
+  const uint32_t* ent_of_id;  // entry id -> index into the sorted ent_* arrays (0xffffffff if unknown)
+  uint32_t max_ent_id;
   const uint32_t* ent_lut;  // ent_lut[ofs >> lut_shift] = first entry whose end_ofs >= (block start)
   uint32_t lut_shift;
   uint64_t n;  // ConcatSeqLen

@@ -1,6 +1,7 @@
 // CUDA kernels of the bkx library (sm_100a): index preparation, read alignment, paired-end pairing.
 #include "bkx_align.cuh"
 #include "bkx_fast.cuh"
+#include "bkx_rescue.cuh"
 #include "bkx_kernels.h"
 
 #include <cub/device/device_scan.cuh>
@@ -761,7 +762,7 @@ struct PEBlock { unsigned int v[8]; };
 
 __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict__ res, uint32_t n_pairs,
                                   bkx_pe_stats* __restrict__ stats, uint32_t* __restrict__ len_dist,
-                                  uint8_t* __restrict__ orphan_flag) {
+                                  uint32_t* __restrict__ orphan_list, unsigned int* __restrict__ n_orphans) {
   __shared__ PEBlock pb;
   if (threadIdx.x < 8) pb.v[threadIdx.x] = 0;
   __syncthreads();
@@ -769,7 +770,6 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
   const int mode = pe.pe_proc;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
     bkx_read_result f = res[2 * i], r = res[2 * i + 1];
-    if (orphan_flag) orphan_flag[i] = 0;
     f.flags &= (uint8_t)~(BKX_FLG_PE_ALIGNED | BKX_FLG_PE_RECOVERED);
     r.flags &= (uint8_t)~(BKX_FLG_PE_ALIGNED | BKX_FLG_PE_RECOVERED);
     bool f_un = f.nar == BKX_NAR_NS || f.nar == BKX_NAR_NOHIT || f.nar == BKX_NAR_UNALIGNED;
@@ -817,10 +817,10 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
     }
     if (!done) {
       atomicAdd(&pb.v[PUNP], 1u);
-      if ((mode == BKX_PE_ORPHAN || mode == BKX_PE_ORPHAN_SE) && orphan_flag &&
+      if ((mode == BKX_PE_ORPHAN || mode == BKX_PE_ORPHAN_SE) && orphan_list &&
           ((f.num_hits == 1 && !r_un) || (r.num_hits == 1 && !f_un))) {
         // orphan recovery is a separate (warp per orphan) kernel; it finishes this pair
-        orphan_flag[i] = 1;
+        orphan_list[atomicAdd(n_orphans, 1u)] = i;
         res[2 * i] = f;
         res[2 * i + 1] = r;
         continue;
@@ -861,11 +861,305 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
 }
 
 cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,
-                        uint32_t* len_dist, uint8_t* orphan_flag, cudaStream_t st) {
+                        uint32_t* len_dist, uint32_t* orphan_list, unsigned int* n_orphans, cudaStream_t st) {
   int grid = (int)((n_pairs + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   if (grid < 1) grid = 1;
-  pair_reads_kernel<<<grid, 256, 0, st>>>(pe, res, n_pairs, stats, len_dist, orphan_flag);
+  pair_reads_kernel<<<grid, 256, 0, st>>>(pe, res, n_pairs, stats, len_dist, orphan_list, n_orphans);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Orphan-mate recovery (see bkx_rescue.cuh): one warp per orphan pair
+// ------------------------------------------------------------------------------------------------
+struct RescueCtx {
+  uint64_t* rd2;    // oriented mate, 2-bit codes
+  uint32_t* rdx;    // oriented mate, N flags (u32 per 32 bases)
+  uint64_t* win2;   // staged genome window, 2-bit codes
+  uint64_t* winx;   // staged genome window, N/EOS bitmap (64 per word)
+  int lane;
+};
+
+// mismatch bitmap word i (32 bases) of the oriented mate against the concatenation at p, from global memory
+__device__ __forceinline__ uint32_t mm_word_global(const DevIndex& I, const RescueCtx& c, uint64_t p, int i, int L) {
+  uint64_t g = p + 32ull * i;
+  uint64_t gw = gword(I, g);
+  // N/EOS flags of [g, g+32); past the end of the concatenation counts as EOS
+  uint64_t xw = g >> 6;
+  unsigned xs = (unsigned)(g & 63);
+  uint64_t xa = __ldg(I.gx + xw) >> xs;
+  if (xs > 32) xa |= __ldg(I.gx + xw + 1) << (64 - xs);
+  uint32_t gx32 = (uint32_t)xa;
+  if (g + 32 > I.n) gx32 |= (g >= I.n) ? 0xffffffffu : (0xffffffffu << (unsigned)(I.n - g));
+  if (g + 32 > I.n) gw |= (g >= I.n) ? ~0ull : (~0ull << (2 * (unsigned)(I.n - g)));  // EOS code past the end
+  uint64_t x = c.rd2[i] ^ gw;
+  uint32_t m = compress_even(x | (x >> 1)) | (gx32 ^ c.rdx[i]);
+  // a flagged genome base against a flagged read base only matches when both are N (code 0): EOS is code 3
+  int rem = L - 32 * i;
+  if (rem < 32) m &= (1u << rem) - 1;
+  return m;
+}
+
+// AlignPairedRead (SfxArrayV2.cpp:8247-8433), MinChimericLen 0.  All lanes call; returns 1 and the hit in
+// (out_loci, out_mm) when a mate alignment is found.  The oriented mate is already in c.rd2 / c.rdx.
+__device__ __forceinline__ int align_paired_read(const DevIndex& I, const KParams& P, const bkx_pe_params& pe,
+                                                 RescueCtx& c, bool has_n, bool b3, uint32_t chrom_id, uint32_t start_loci,
+                                                 uint32_t end_loci, int L, uint32_t& out_loci, int& out_mm) {
+  const int min_d = pe.pair_min_len, max_d = pe.pair_max_len, max_allowed = P.max_subs;
+  if (min_d < L || min_d > max_d) return 0;
+  if (chrom_id < 1 || chrom_id > I.max_ent_id) return 0;
+  const uint32_t ei = __ldg(I.ent_of_id + chrom_id);
+  if (ei == 0xffffffffu) return 0;
+  const uint64_t cs = __ldg(I.ent_start + ei);
+  const uint32_t targ_len = (uint32_t)(__ldg(I.ent_end + ei) - cs + 1);
+  int targ_loci;
+  if (b3) {
+    targ_loci = (int)start_loci;
+    if ((uint32_t)(targ_loci + min_d) > targ_len) return 0;
+  } else {
+    targ_loci = (int)end_loci;
+    if (targ_loci < min_d || (uint32_t)targ_loci >= targ_len) return 0;
+  }
+  uint32_t sp, ep;
+  if (b3) {
+    sp = (uint32_t)(targ_loci + min_d);
+    if (sp + (uint32_t)L >= targ_len) return 0;
+    ep = (uint32_t)(targ_loci + max_d);
+  } else {
+    sp = end_loci < (uint32_t)max_d ? 0 : end_loci - (uint32_t)max_d;
+    ep = end_loci - (uint32_t)min_d;
+  }
+  const int nw = (L + 31) >> 5;
+  unsigned long long best = ~0ull;  // (mm << 40) | order
+  if (ep - sp >= 1000) {
+    // ---- suffix-array seeded: exact core hits inside the window (no cap, as the reference)
+    int match_len = L - 1;
+    int max_tot_mm = P.max_subs == 0 ? 0 : max(1, (match_len * P.max_subs + 50) / 100);
+    if (max_tot_mm > 63) max_tot_mm = 63;
+    int core_len = max(P.min_core_len, L / (P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
+    int core_delta = max(L / P.slides_per100 - 1, core_len);  // sic: per-100bp value (Aligner.cpp:3266)
+    Grp<32> g;
+    g.s2[0] = c.rd2; g.s2[1] = c.rd2; g.sx[0] = c.rdx; g.sx[1] = c.rdx;
+    g.L = L; g.hasN = has_n; g.gl = c.lane; g.gmask = 0xffffffffu; g.gshift = 0;
+    unsigned long long order = 0;
+    for (int co = 0; co + core_len <= L; co += core_delta) {
+      uint64_t first = 0, cnt = 0;
+      if (c.lane == 0) locate_core<32>(I, g, 0, co, core_len, first, cnt);
+      first = __shfl_sync(0xffffffffu, first, 0);
+      cnt = __shfl_sync(0xffffffffu, cnt, 0);
+      for (uint64_t j0 = 0; j0 < cnt; j0 += 32) {
+        uint64_t j = j0 + (uint64_t)c.lane;
+        if (j < cnt) {
+          uint64_t loci = sa_get(I, first + j);
+          int e2 = find_entry(I, loci);
+          if (e2 >= 0 && (uint32_t)e2 == ei) {
+            uint32_t hl = (uint32_t)(loci - cs);
+            if (hl >= sp && hl <= ep && (uint32_t)co <= hl && (hl + (uint32_t)L - (uint32_t)co) < targ_len) {
+              ATFull at;
+              for (int i = 0; i < nw; ++i) at.push(mm_word_global(I, c, cs + hl - co, i, L), i, L);
+              int mm = at.result(L, max_allowed);
+              if (mm >= 0) {
+                unsigned long long key = ((unsigned long long)mm << 40) | (order + j);
+                if (key < best) { best = key; out_loci = hl - (uint32_t)co; }
+              }
+            }
+          }
+        }
+      }
+      order += cnt;
+    }
+  } else {
+    // ---- linear scan with the window staged in shared memory
+    const uint64_t g0 = cs + sp;                 // first base of the window (concatenation offset)
+    const uint64_t w0 = g0 >> 5;                 // first staged 2-bit word
+    const uint64_t x0 = g0 >> 6;                 // first staged flag word
+    const uint64_t g_last = cs + ep + (uint64_t)L;  // one past the last base any locus touches
+    const int n2 = (int)(((g_last + 31) >> 5) - w0) + 1;
+    const int nx = (int)(((g_last + 63) >> 6) - x0) + 1;
+    const uint64_t lim2 = (I.n + 31) >> 5, limx = (I.n + 63) >> 6;
+    for (int i = c.lane; i < n2; i += 32) {
+      uint64_t wi = w0 + i;
+      uint64_t v2 = wi < lim2 + 2 ? __ldg(I.g2 + wi) : 0ull;
+      uint64_t b2 = wi << 5;
+      if (b2 + 32 > I.n) v2 |= (b2 >= I.n) ? ~0ull : (~0ull << (2 * (unsigned)(I.n - b2)));  // EOS code past the end
+      c.win2[i] = v2;
+    }
+    for (int i = c.lane; i < nx; i += 32) {
+      uint64_t wi = x0 + i;
+      uint64_t v = wi < limx + 1 ? __ldg(I.gx + wi) : 0ull;
+      // past the end of the concatenation behaves as EOS: flagged (codes there are 0, never equal-and-unflagged)
+      uint64_t base = wi << 6;
+      if (base + 64 > I.n) v |= (base >= I.n) ? ~0ull : (~0ull << (unsigned)(I.n - base));
+      c.winx[i] = v;
+    }
+    __syncwarp();
+    const int off2 = (int)(g0 - (w0 << 5)), offx = (int)(g0 - (x0 << 6));
+    for (uint32_t b = 0; b <= ep - sp; b += 32) {
+      uint32_t d = b + (uint32_t)c.lane;
+      if (d <= ep - sp) {
+        ATFull at;
+        for (int i = 0; i < nw; ++i) {
+          uint64_t gw = sm_word2(c.win2, off2 + (int)d + 32 * i);
+          uint32_t gx32 = sm_bits(c.winx, offx + (int)d + 32 * i);
+          uint64_t x = c.rd2[i] ^ gw;
+          uint32_t m = compress_even(x | (x >> 1)) | (gx32 ^ c.rdx[i]);
+          int rem = L - 32 * i;
+          if (rem < 32) m &= (1u << rem) - 1;
+          at.push(m, i, L);
+        }
+        int mm = at.result(L, max_allowed);
+        if (mm >= 0) {
+          unsigned long long key = ((unsigned long long)mm << 40) | d;
+          if (key < best) { best = key; out_loci = sp + d; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // first locus (in processing order) with the fewest mismatches; must beat MaxAllowedMM+1
+  unsigned long long bmin = best;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, bmin, o);
+    bmin = t < bmin ? t : bmin;
+  }
+  if (bmin == ~0ull) return 0;
+  int src = __ffs(__ballot_sync(0xffffffffu, best == bmin)) - 1;
+  out_loci = __shfl_sync(0xffffffffu, out_loci, src);
+  out_mm = (int)(bmin >> 40);
+  return out_mm <= max_allowed ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kRescueThreads) orphan_rescue_kernel(
+    DevIndex I, KParams P, bkx_pe_params pe, bkx_read_result* __restrict__ res, const uint32_t* __restrict__ orphan_list,
+    const unsigned int* __restrict__ n_orphans, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
+    int Lmax, bkx_pe_stats* __restrict__ stats, uint32_t* __restrict__ len_dist, unsigned int* __restrict__ cursor) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned int pb[8];
+  enum { UNAL = 0, ACCP = 1, ACCSE = 2, PPAIRED = 3, PUNP = 4, FILT = 5, UNDER = 6, OVER = 7 };
+  if (threadIdx.x < 8) pb[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint64_t* base = (uint64_t*)(smem_raw + rescue_warp_bytes(Lmax) * wib);
+  RescueCtx c;
+  c.rd2 = base;
+  c.rdx = (uint32_t*)(base + rescue_rw(Lmax));
+  c.win2 = base + rescue_rw(Lmax) + (rescue_rw(Lmax) + 1) / 2;
+  c.winx = c.win2 + rescue_ww(Lmax);
+  c.lane = lane;
+  const unsigned int total = *n_orphans;
+  const int mode = pe.pe_proc;
+  for (;;) {
+    unsigned int q = 0;
+    if (lane == 0) q = atomicAdd(cursor, 1u);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= total) break;
+    const uint32_t i = orphan_list[q];
+    bkx_read_result f = res[2 * i], r = res[2 * i + 1];
+    const bool f_un = f.nar == BKX_NAR_NS || f.nar == BKX_NAR_NOHIT || f.nar == BKX_NAR_UNALIGNED;
+    const bool r_un = r.nar == BKX_NAR_NS || r.nar == BKX_NAR_NOHIT || r.nar == BKX_NAR_UNALIGNED;
+    bool paired = false;
+    for (int side = 0; side < 2 && !paired; ++side) {
+      // side 0: 5' end is the anchor, rescue PE2 (Aligner.cpp:3222-3310); side 1: 3' anchor, rescue PE1 (:3321-3410)
+      const bkx_read_result& anc = side == 0 ? f : r;
+      if (!(anc.num_hits == 1 && !(side == 0 ? r_un : f_un))) continue;
+      bool b3 = anc.strand == '+';
+      bool anti;
+      if (side == 0) anti = pe.pair_strand ? (anc.strand != '+') : (anc.strand == '+');
+      else { anti = anc.strand == '+'; if (pe.pair_strand) { b3 = !b3; anti = !anti; } }
+      if (pe.circularised) b3 = !b3;
+      const uint32_t os = anc.match_loci, oe = anc.match_loci + anc.match_len - 1;
+      const uint32_t mate = 2 * i + (side == 0 ? 1 : 0);
+      const uint64_t o0 = __ldg(offs + mate);
+      const int L = (int)(__ldg(offs + mate + 1) - o0);
+      if (L < 1 || L > kRescueMaxLen || L > Lmax) continue;
+      // pack the mate in the orientation it is expected to align in
+      const uint8_t* rd = bases + o0;
+      const int words = (L + 31) >> 5;
+      int nN = 0;
+      for (int w = 0; w <= words; ++w) {
+        int p = w * 32 + lane;
+        unsigned code = 0, isn = 0;
+        if (p < L) {
+          unsigned b = __ldg(rd + (anti ? (L - 1 - p) : p)) & 0x07;
+          isn = (b >= 4);
+          code = (b < 4) ? (anti ? 3 - b : b) : 0;
+        }
+        unsigned b0 = __ballot_sync(0xffffffffu, code & 1), b1 = __ballot_sync(0xffffffffu, code & 2);
+        unsigned bn = __ballot_sync(0xffffffffu, isn);
+        if (lane == 0) { c.rd2[w] = spread32(b0) | (spread32(b1) << 1); c.rdx[w] = bn; }
+        nN += __popc(bn);
+      }
+      __syncwarp();
+      uint32_t hl = 0;
+      int hmm = 0;
+      int rs = align_paired_read(I, P, pe, c, nN > 0, b3, anc.chrom_id, os, oe, L, hl, hmm);
+      int frag = 0;
+      const uint8_t hstrand = anti ? '-' : '+';
+      if (rs == 1) {
+        if (side == 0) frag = pe_insert_size(pe, anc.strand, os, oe, hstrand, hl, hl + (uint32_t)L - 1);
+        else frag = pe_insert_size(pe, hstrand, hl, hl + (uint32_t)L - 1, anc.strand, os, oe);
+        if (frag <= 0) rs = 0;
+      }
+      if (rs == 1) {
+        bkx_read_result& m = side == 0 ? r : f;
+        m.strand = hstrand; m.chrom_id = anc.chrom_id; m.match_loci = hl; m.match_len = (uint16_t)L;
+        m.mismatches = (uint8_t)hmm; m.num_hits = 1; m.low_mm = (int8_t)hmm; m.low_hit_instances = 1;
+        f.flags |= BKX_FLG_PE_ALIGNED; r.flags |= BKX_FLG_PE_ALIGNED;
+        m.flags |= BKX_FLG_PE_RECOVERED;
+        f.nar = r.nar = BKX_NAR_ACCEPTED;
+        if (lane == 0) {
+          if (len_dist) atomicAdd(len_dist + frag, 1u);
+          atomicAdd(&pb[ACCP], 1u);
+          atomicAdd(&pb[PPAIRED], 1u);
+        }
+        paired = true;
+      }
+    }
+    if (!paired) {  // Aligner.cpp:3421-3477
+      if (lane == 0) {
+        if (f.nar == BKX_NAR_CHROMFILT || r.nar == BKX_NAR_CHROMFILT) atomicAdd(&pb[FILT], 1u);
+        if (f.nar == BKX_NAR_PEINSERTMIN || r.nar == BKX_NAR_PEINSERTMIN) atomicAdd(&pb[UNDER], 1u);
+        if (f.nar == BKX_NAR_PEINSERTMAX || r.nar == BKX_NAR_PEINSERTMAX) atomicAdd(&pb[OVER], 1u);
+      }
+      if (mode != BKX_PE_ORPHAN_SE) {
+        f.num_hits = r.num_hits = 0;
+        f.low_hit_instances = r.low_hit_instances = 0;
+        if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
+        if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
+      } else {
+        if (f.num_hits != 1) { f.num_hits = 0; f.low_hit_instances = 0; if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PEUNALIGN; }
+        else { f.nar = BKX_NAR_ACCEPTED; if (lane == 0) atomicAdd(&pb[ACCSE], 1u); }
+        if (r.num_hits != 1) { r.num_hits = 0; r.low_hit_instances = 0; if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PEUNALIGN; }
+        else { r.nar = BKX_NAR_ACCEPTED; if (lane == 0) atomicAdd(&pb[ACCSE], 1u); }
+      }
+    }
+    if (lane == 0) { res[2 * i] = f; res[2 * i + 1] = r; }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && stats) {
+    atomicAdd((unsigned long long*)&stats->accepted_num_paired, (unsigned long long)pb[ACCP]);
+    atomicAdd((unsigned long long*)&stats->accepted_num_se, (unsigned long long)pb[ACCSE]);
+    atomicAdd((unsigned long long*)&stats->partner_paired, (unsigned long long)pb[PPAIRED]);
+    atomicAdd((unsigned long long*)&stats->num_filtered_by_chrom, (unsigned long long)pb[FILT]);
+    atomicAdd((unsigned long long*)&stats->under_len_pairs, (unsigned long long)pb[UNDER]);
+    atomicAdd((unsigned long long*)&stats->over_len_pairs, (unsigned long long)pb[OVER]);
+  }
+}
+
+cudaError_t launch_rescue(const DevIndex& I, const KParams& P, const bkx_pe_params& pe, bkx_read_result* res,
+                          const uint32_t* orphan_list, const unsigned int* n_orphans, const uint8_t* bases,
+                          const uint64_t* offs, int Lmax, bkx_pe_stats* stats, uint32_t* len_dist, unsigned int* cursor,
+                          cudaStream_t st) {
+  size_t smem = rescue_warp_bytes(Lmax) * kRescueWarps;
+  static size_t configured = 0;
+  cudaError_t e = ensure_smem(orphan_rescue_kernel, smem, configured);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  orphan_rescue_kernel<<<148 * 4, kRescueThreads, smem, st>>>(I, P, pe, res, orphan_list, n_orphans, bases, offs, Lmax,
+                                                               stats, len_dist, cursor);
   return cudaGetLastError();
 }
 

@@ -51,8 +51,6 @@ def test_cuda_matches_oracle_and_reference(case, tag, golden_dir):
     assert_same(names, got, exp)
     assert gst.as_dict() == ost.as_dict()
     if pe is not None:
-        if pe.pe_proc in (abi.PE_ORPHAN, abi.PE_ORPHAN_SE):
-            pytest.skip("orphan recovery kernel not built yet")
         gpe = gidx.pair(p, pe, got, bases, offs)
         ope = oidx.pair(op, pe, exp, bases, offs)
         assert_same(names, got, exp)
