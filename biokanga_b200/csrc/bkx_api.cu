@@ -60,6 +60,8 @@ struct bkx_index {
   int device = 0;
   DevIndex d{};
   std::vector<void*> owned;
+  struct Arr { size_t field_ofs; size_t bytes; };
+  std::vector<Arr> arrs;   // every device array the DevIndex points at (for peer replication)
   std::vector<bkx_entry> entries;
   bkx_index_info info{};
   // runtime workspace
@@ -98,6 +100,8 @@ static int dev_alloc(bkx_index* x, T** p, size_t count, bool zero) {
   *p = (T*)q;
   return BKX_OK;
 }
+
+#define REG_ARR(x, field, nbytes) (x)->arrs.push_back({offsetof(DevIndex, field), (size_t)(nbytes)})
 
 static int choose_k(uint64_t n, int requested, size_t free_bytes, bool wide) {
   if (requested > 0) return std::min(std::max(requested, 4), 17);
@@ -146,6 +150,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
   x->launches += 1;
   if (bad) return fail(BKX_ERR_UNSUPPORTED, "%llu symbols other than A,C,G,T,N,EOS in the index sequence", bad);
   x->d.g2 = g2; x->d.gx = gx; x->d.gxc = gxc; x->d.n = n;
+  REG_ARR(x, g2, g2w * 8); REG_ARR(x, gx, gxw * 8); REG_ARR(x, gxc, gcw * 4);
 
   if (el == 4) {
     if (sa_owned_u32) {
@@ -157,6 +162,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
       x->d.sa_lo = lo;
     }
     x->d.sa_hi = nullptr;
+    REG_ARR(x, sa_lo, n * 4);
   } else {
     uint32_t* lo; uint8_t* hi;
     if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
@@ -164,6 +170,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
     CU(launch_split_sa5((const uint8_t*)d_sa_raw, n, lo, hi, st));
     x->launches += 1;
     x->d.sa_lo = lo; x->d.sa_hi = hi;
+    REG_ARR(x, sa_lo, n * 4); REG_ARR(x, sa_hi, n);
   }
   // chromosome table
   std::vector<uint64_t> es(n_ent), ee(n_ent);
@@ -177,6 +184,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
   CU(cudaMemcpy(d_ee, ee.data(), n_ent * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(d_ei, ei.data(), n_ent * 4, cudaMemcpyHostToDevice));
   x->d.ent_start = d_es; x->d.ent_end = d_ee; x->d.ent_id = d_ei; x->d.n_ent = n_ent;
+  REG_ARR(x, ent_start, (size_t)n_ent * 8); REG_ARR(x, ent_end, (size_t)n_ent * 8); REG_ARR(x, ent_id, (size_t)n_ent * 4);
   {  // entry id -> sorted index
     uint32_t max_id = 0;
     for (uint32_t i = 0; i < n_ent; ++i) max_id = std::max(max_id, ei[i]);
@@ -187,6 +195,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
     CU(cudaMemcpy(d_inv, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
     x->d.ent_of_id = d_inv;
     x->d.max_ent_id = max_id;
+    REG_ARR(x, ent_of_id, inv.size() * 4);
   }
   {  // coarse offset -> entry table (<= 1M blocks): first entry whose end is at or after the block start
     uint32_t shift = 8;
@@ -204,6 +213,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
     CU(cudaMemcpy(d_lut, lut.data(), nb * 4, cudaMemcpyHostToDevice));
     x->d.ent_lut = d_lut;
     x->d.lut_shift = shift;
+    REG_ARR(x, ent_lut, nb * 4);
   }
   // prefix table
   size_t free_b = 0, total_b = 0;
@@ -216,6 +226,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
   else { uint32_t* t; if ((rc = dev_alloc(x, &t, pt_entries, false)) < 0) return rc; pt = t; x->d.pt32 = t; x->d.pt64 = nullptr; }
   x->d.k = k;
   x->info.prefix_k = (uint32_t)k;
+  if (wide) REG_ARR(x, pt64, pt_entries * 8); else REG_ARR(x, pt32, pt_entries * 4);
   CU(build_prefix_table(x->d, k, pt, wide, st));
   x->launches += 2;
   CU(cudaStreamSynchronize(st));
@@ -436,9 +447,42 @@ extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_in
   return BKX_OK;
 }
 
+// Replicate an open index onto another GPU with peer copies (NVLink when the GPUs are peers).
 extern "C" int bkx_clone_index(const bkx_index* src, int device, bkx_index** out) {
-  (void)src; (void)device; (void)out;
-  return fail(BKX_ERR_UNSUPPORTED, "bkx_clone_index: peer replication not built yet (one process per GPU opens its own copy)");
+  if (!src || !out) return fail(BKX_ERR_PARAM, "null argument");
+  bkx_index* x = nullptr;
+  int rc = new_index(device, &x);
+  if (rc < 0) return rc;
+  x->info = src->info;
+  x->info.device = (uint32_t)device;
+  x->info.device_bytes = 0;
+  x->entries = src->entries;
+  x->d = src->d;
+  x->arrs = src->arrs;
+  int can = 0;
+  cudaDeviceCanAccessPeer(&can, device, src->device);
+  if (can) {
+    cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+    cudaGetLastError();
+  }
+  for (const auto& a : src->arrs) {
+    const void* sp = *(const void* const*)((const char*)&src->d + a.field_ofs);
+    void* dp = nullptr;
+    cudaError_t e = cudaMalloc(&dp, a.bytes ? a.bytes : 8);
+    if (e == cudaSuccess) e = cudaMemcpyPeer(dp, device, sp, src->device, a.bytes);
+    if (e != cudaSuccess) {
+      if (dp) cudaFree(dp);
+      bkx_close_index(x);
+      return fail(BKX_ERR_CUDA, "index replication to device %d: %s", device, cudaGetErrorString(e));
+    }
+    x->owned.push_back(dp);
+    x->info.device_bytes += a.bytes;
+    *(const void**)((char*)&x->d + a.field_ofs) = dp;
+  }
+  CU(cudaDeviceSynchronize());
+  *out = x;
+  return BKX_OK;
 }
 
 extern "C" int bkx_index_info_get(const bkx_index* x, bkx_index_info* out) {

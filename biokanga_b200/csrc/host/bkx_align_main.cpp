@@ -1,0 +1,510 @@
+// bkx-align -- host side of the drop-in for `biokanga align`.
+//
+// Same option letters as the reference front-end (biokanga/kanga.cpp:194-294), same on-disk .sfx index,
+// same CSV (-M0) / SAM (-M5, -M6) records and the same alignment-summary log block
+// (biokanga/Aligner.cpp:486-535, 3000-3008, 3726-3769).  The search itself goes through the C ABI of
+// libbkx.so (include/bkx.h); this file holds what the reference keeps in CAligner around that call:
+//   read ingest       CAligner::LoadRawReads / AddEntry   Aligner.cpp:10724-11427, 10572-10677
+//                     CFasta::ReadSequence / Ascii2Sense  libbiokanga/Fasta.cpp:907-1129, 1518-1570
+//   hit ordering      CAligner::SortHitMatch              Aligner.cpp:10067-10114
+//   CSV rows          CAligner::WriteReadHits             Aligner.cpp:6336-6664
+//   SAM records       WriteBAMReadHits / ReportBAMread    Aligner.cpp:5543-5725, 5768-6126
+//                     CSAMfile::AddAlignment (text form)  libbiokanga/SAMfile.cpp:2100-2262
+//   summary           CAligner::ReportAlignStats          Aligner.cpp:3493-3822
+// Written from the behaviour of those functions; no reference code is reused.  Options of the
+// reference that select paths outside SURVEY section 8 (-r/-R multi-loci modes, -c chimeric, -a/-A indel and
+// splice, -p SNP calling, -k PCR dedup, -x flank trimming, -Z/-z filters, -5 constraints, -H contaminants,
+// -b/-C bisulfite/SOLiD, BAM output) are recognised and rejected with a clear message.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <zlib.h>
+
+#include "../../../include/bkx.h"
+
+static FILE* g_log = nullptr;
+static int g_loglevel = 2;
+
+static void diag(const char* fmt, ...) {  // CDiagnostics::DiagOut format: "[Mon DD HH:MM:SS.mmm YYYY](biokanga) text"
+  char msg[4096];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof(msg), fmt, ap);
+  va_end(ap);
+  auto now = std::chrono::system_clock::now();
+  time_t t = std::chrono::system_clock::to_time_t(now);
+  int ms = (int)(std::chrono::duration_cast<std::chrono::milliseconds>(now.time_since_epoch()).count() % 1000);
+  struct tm tmv;
+  localtime_r(&t, &tmv);
+  char ts[64], yr[8];
+  strftime(ts, sizeof(ts), "%b %d %H:%M:%S", &tmv);
+  strftime(yr, sizeof(yr), "%Y", &tmv);
+  char line[4400];
+  snprintf(line, sizeof(line), "[%s.%03d %s](biokanga) %s\n", ts, ms, yr, msg);
+  fputs(line, stdout);
+  if (g_log) { fputs(line, g_log); fflush(g_log); }
+}
+
+// ---- read ingest ---------------------------------------------------------------------------------
+struct Reads {
+  std::vector<uint8_t> bases;     // 1 byte/base, etSeqBase code in the low 3 bits
+  std::vector<uint64_t> offs{0};
+  std::vector<char> names;        // NUL-terminated descriptors, back to back
+  std::vector<uint64_t> name_ofs;
+  uint32_t n() const { return (uint32_t)(offs.size() - 1); }
+  const char* name(uint32_t i) const { return names.data() + name_ofs[i]; }
+  int len(uint32_t i) const { return (int)(offs[i + 1] - offs[i]); }
+};
+
+struct SeqFile {  // FASTA / FASTQ, plain or gzip (zlib reads both)
+  gzFile f = nullptr;
+  std::string path, pending;
+  bool have_pending = false;
+  bool open(const std::string& p) {
+    path = p;
+    f = gzopen(p.c_str(), "rb");
+    if (f) gzbuffer(f, 1 << 20);
+    return f != nullptr;
+  }
+  void close() { if (f) gzclose(f); f = nullptr; }
+  bool getline(std::string& s) {
+    if (have_pending) { s.swap(pending); have_pending = false; return true; }
+    s.clear();
+    char buf[65536];
+    for (;;) {
+      if (!gzgets(f, buf, sizeof(buf))) return !s.empty();
+      size_t n = strlen(buf);
+      bool eol = n && buf[n - 1] == '\n';
+      while (n && (buf[n - 1] == '\n' || buf[n - 1] == '\r')) --n;
+      s.append(buf, n);
+      if (eol) return true;
+    }
+  }
+  // next record: descriptor (text after '>' / '@' up to the first white space, <= 127 chars) and sequence
+  bool next(std::string& descr, std::string& seq) {
+    std::string ln;
+    do { if (!getline(ln)) return false; } while (ln.empty());
+    if (ln[0] != '>' && ln[0] != '@') return false;
+    bool fastq = ln[0] == '@';
+    size_t e = 1;
+    while (e < ln.size() && !isspace((unsigned char)ln[e]) && e - 1 < 127) ++e;
+    descr.assign(ln, 1, e - 1);
+    seq.clear();
+    if (fastq) {
+      if (!getline(seq)) return false;
+      std::string plus, qual;
+      getline(plus);
+      getline(qual);
+    } else {
+      while (getline(ln)) {
+        if (!ln.empty() && ln[0] == '>') { pending.swap(ln); have_pending = true; break; }
+        seq += ln;
+      }
+    }
+    return true;
+  }
+};
+
+static inline uint8_t base_code(char c) {  // CFasta::Ascii2Sense, Fasta.cpp:1518-1570 (soft-mask bit dropped)
+  switch (c) {
+    case 'a': case 'A': return 0;
+    case 'c': case 'C': return 1;
+    case 'g': case 'G': return 2;
+    case 't': case 'T': case 'u': case 'U': return 3;
+    case '-': return 6;
+    default: return 4;
+  }
+}
+
+struct Opts {
+  int pmode = 0, strand = 0, max_subs = 10, edit_delta = 1, max_ns = 1, fmt = 5, pe_mode = 0, pair_min = 100,
+      pair_max = 1000, trim5 = 0, trim3 = 0, min_len = 50, max_len = 500, threads = 0, gpus = 1, sam_seq_thres = 10000;
+  bool pair_strand = false, pe_circ = false;
+  std::vector<std::string> in, pair;
+  std::string sfx, out, logfile, title;
+};
+
+static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (default -g3: qualities ignored)
+  bool pe = o.pe_mode != 0;
+  diag("Loading reads from file...");
+  for (size_t fi = 0; fi < o.in.size(); ++fi) {
+    SeqFile f1, f2;
+    if (!f1.open(o.in[fi])) { diag("Unable to open '%s'", o.in[fi].c_str()); return -1; }
+    if (pe && !f2.open(o.pair[fi])) { diag("Unable to open '%s'", o.pair[fi].c_str()); return -1; }
+    std::string d1, s1, d2, s2;
+    uint32_t accepted = 0, under = 0, over = 0;
+    while (f1.next(d1, s1)) {
+      if (pe && !f2.next(d2, s2)) { diag("Problem parsing sequence after %u reads parsed", accepted); return -1; }
+      auto bad_len = [&](const std::string& s, uint32_t& u, uint32_t& ov) {
+        if (o.trim5 + o.trim3 + o.min_len > (int)s.size()) { ++u; return true; }
+        if (o.trim5 + o.trim3 + o.max_len < (int)s.size()) { ++ov; return true; }
+        return false;
+      };
+      if (bad_len(s1, under, over)) continue;
+      if (pe && bad_len(s2, under, over)) continue;
+      auto add = [&](const std::string& d, const std::string& s) {
+        size_t b = (size_t)o.trim5, e = s.size() - (size_t)o.trim3;
+        for (size_t i = b; i < e; ++i) R.bases.push_back(base_code(s[i]));
+        R.offs.push_back(R.bases.size());
+        R.name_ofs.push_back(R.names.size());
+        R.names.insert(R.names.end(), d.begin(), d.end());
+        R.names.push_back('\0');
+      };
+      add(d1, s1);
+      if (pe) add(d2, s2);
+      ++accepted;
+    }
+    f1.close();
+    if (pe) f2.close();
+    diag("LoadReads: Total of %1.9d reads parsed and loaded from %s", accepted, o.in[fi].c_str());
+    if (under) diag("Load: total of %d under length sequences sloughed from file '%s'", under, o.in[fi].c_str());
+    if (over) diag("Load: total of %d over length sequences sloughed from file '%s'", over, o.in[fi].c_str());
+  }
+  return 0;
+}
+
+// ---- option parsing (kanga.cpp:194-294 letters; values may be attached or separate) ----------------
+static bool takes_value(char c) { return strchr("fFqwWm#QcaAkgryYlLR4esnx6pKGP1MtBiUdDuISo7jJO89H5ZzT", c) != nullptr; }
+
+static int parse(int argc, char** argv, Opts& o) {
+  int i = 1;
+  if (i < argc && (!strcmp(argv[i], "align") || !strcmp(argv[i], "kanga"))) ++i;
+  std::vector<std::string> unsupported;
+  for (; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "--gpus" && i + 1 < argc) { o.gpus = atoi(argv[++i]); continue; }
+    if (a.rfind("--gpus=", 0) == 0) { o.gpus = atoi(a.c_str() + 7); continue; }
+    if (a.size() < 2 || a[0] != '-' || a[1] == '-') { fprintf(stderr, "unrecognised argument '%s'\n", a.c_str()); return -1; }
+    char c = a[1];
+    std::string v;
+    if (takes_value(c)) {
+      if (a.size() > 2) v = a.substr(2);
+      else if (i + 1 < argc) v = argv[++i];
+      else { fprintf(stderr, "option -%c needs a value\n", c); return -1; }
+    }
+    int iv = atoi(v.c_str());
+    switch (c) {
+      case 'f': g_loglevel = iv; break;
+      case 'F': o.logfile = v; break;
+      case 'm': o.pmode = iv; break;
+      case 'Q': o.strand = iv; break;
+      case 's': o.max_subs = iv; break;
+      case 'e': o.edit_delta = iv; break;
+      case 'n': o.max_ns = iv; break;
+      case 'M': o.fmt = iv; break;
+      case 'U': o.pe_mode = iv; break;
+      case 'd': o.pair_min = iv; break;
+      case 'D': o.pair_max = iv; break;
+      case 'E': o.pair_strand = true; break;
+      case '2': o.pe_circ = true; break;
+      case 'y': o.trim5 = iv; break;
+      case 'Y': o.trim3 = iv; break;
+      case 'l': o.min_len = iv; break;
+      case 'L': o.max_len = iv; break;
+      case 'T': o.threads = iv; break;
+      case '4': o.sam_seq_thres = iv; break;
+      case 'i': o.in.push_back(v); break;
+      case 'u': o.pair.push_back(v); break;
+      case 'I': o.sfx = v; break;
+      case 'o': o.out = v; break;
+      case 't': o.title = v; break;
+      case 'g': if (iv != 3) unsupported.push_back("-g (quality scores other than 3=ignore)"); break;
+      case '#': if (iv != 1) unsupported.push_back("-# read sampling"); break;
+      case 'r': if (iv != 0) unsupported.push_back("-r multi-loci modes"); break;
+      case 'R': break;  // only meaningful with -r
+      case 'c': if (iv) unsupported.push_back("-c chimeric trimming"); break;
+      case 'a': if (iv) unsupported.push_back("-a microInDels"); break;
+      case 'A': if (iv) unsupported.push_back("-A splice junctions"); break;
+      case 'k': unsupported.push_back("-k PCR artefact reduction"); break;
+      case 'x': if (iv) unsupported.push_back("-x flank trimming"); break;
+      case 'p': if (iv) unsupported.push_back("-p SNP calling"); break;
+      case '6': if (iv) unsupported.push_back("-6 PCR primer correction"); break;
+      case 'b': unsupported.push_back("-b bisulfite"); break;
+      case 'C': unsupported.push_back("-C colorspace"); break;
+      case 'N': unsupported.push_back("-N best matches"); break;
+      case 'X': unsupported.push_back("-X clamp multi"); break;
+      case 'B': case 'H': case '5': case 'Z': case 'z': case 'j': case 'J': case 'O': case 'S': case '7': case '8':
+      case 'q': unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
+      case 'h':
+        printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -M{0,5,6} -U -d -D -E -y -Y -l -L -i -u -I -o -F "
+               "[--gpus N]\n");
+        return 1;
+      default: break;  // remaining reference options have no effect on this path (-w -W -K -G -P -1 -9 -V -0 -3 -v)
+    }
+  }
+  if (!unsupported.empty()) {
+    for (auto& u : unsupported) fprintf(stderr, "bkx-align: option %s is not supported by the accelerated path\n", u.c_str());
+    return -1;
+  }
+  // validation mirrors kanga.cpp:452-862
+  if (o.sfx.empty() || o.in.empty() || o.out.empty()) { fprintf(stderr, "bkx-align: -I, -i and -o are required\n"); return -1; }
+  if (o.pmode < 0 || o.pmode > 3) { fprintf(stderr, "Error: Processing mode '-m%d' must be in range 0..3\n", o.pmode); return -1; }
+  if (o.max_subs < 0 || o.max_subs > 15) { fprintf(stderr, "Error: max substitutions '-s%d' must be in range 0..15\n", o.max_subs); return -1; }
+  if (o.edit_delta < 1 || o.edit_delta > 2) { fprintf(stderr, "Error: Min Hamming edit distance '-e%d' must be in range 1..2\n", o.edit_delta); return -1; }
+  if (o.max_ns < 0 || o.max_ns > 5) { fprintf(stderr, "Error: Allowed number of indeterminate 'N's '-n%d' must be in range 0..5\n", o.max_ns); return -1; }
+  if (o.fmt != 0 && o.fmt != 5 && o.fmt != 6) { fprintf(stderr, "bkx-align: output format -M%d not supported (0, 5, 6)\n", o.fmt); return -1; }
+  if (o.pe_mode < 0 || o.pe_mode > 4) { fprintf(stderr, "Error: paired end mode '-U%d' must be in range 0..4\n", o.pe_mode); return -1; }
+  if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
+  if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
+  if (o.gpus < 1) o.gpus = 1;
+  return 0;
+}
+
+// ---- ordering: SortHitMatch (Aligner.cpp:10067-10114); ties broken by read id for determinism ------
+static bool hit_less(const bkx_read_result& a, const bkx_read_result& b, uint32_t ia, uint32_t ib) {
+  if (a.nar != b.nar) return a.nar < b.nar;
+  bool a1 = a.num_hits == 1, b1 = b.num_hits == 1;
+  if (a1 != b1) return a1;
+  if (!a1) { if (a.num_hits != b.num_hits) return a.num_hits < b.num_hits; return ia < ib; }
+  if (a.chrom_id != b.chrom_id) return a.chrom_id < b.chrom_id;
+  if (a.match_loci != b.match_loci) return a.match_loci < b.match_loci;
+  if (a.match_len != b.match_len) return a.match_len < b.match_len;
+  if (a.strand != b.strand) return a.strand < b.strand;
+  if (a.low_mm != b.low_mm) return a.low_mm < b.low_mm;
+  return ia < ib;
+}
+
+static const char* kNarCode[] = {"NA", "AA", "EN", "NL", "MH", "ML", "ET", "OJ", "OM", "DP", "DS", "FC", "PR", "UI", "OI", "UP", "IS", "IT", "NP", "LC"};
+static const char* kNarText[] = {
+    "Not processed for alignment", "Alignment accepted", "Excessive indeterminate (Ns) bases", "No potential alignment loci",
+    "Mismatch delta (minimum Hamming) criteria not met", "Aligned to multiloci", "Excessively end trimmed",
+    "Aligned as orphaned splice junction", "Aligned as orphaned microInDel", "Duplicate PCR", "Duplicate read sequence",
+    "Aligned to filtered target sequence", "Aligned to a priority region", "PE under minimum insert size",
+    "PE over maximum insert size", "PE partner not aligned", "PE partner aligned to inconsistent strand",
+    "PE partner aligned to different target sequence", "PE alignment not accepted", "Alignment violated loci base constraints"};
+
+struct OutBuf {
+  FILE* f;
+  std::string s;
+  explicit OutBuf(FILE* ff) : f(ff) { s.reserve(1 << 22); }
+  void flush() { if (!s.empty()) { fwrite(s.data(), 1, s.size(), f); s.clear(); } }
+  void maybe() { if (s.size() > (1 << 22) - 8192) flush(); }
+};
+
+static void append_uint(std::string& s, uint64_t v) { char b[24]; int n = snprintf(b, sizeof(b), "%llu", (unsigned long long)v); s.append(b, n); }
+
+int main(int argc, char** argv) {
+  Opts o;
+  int pr = parse(argc, argv, o);
+  if (pr != 0) return pr < 0 ? 1 : 0;
+  if (!o.logfile.empty()) g_log = fopen(o.logfile.c_str(), "w");
+  auto t_start = std::chrono::steady_clock::now();
+  diag("Subprocess align Version 4.4.2 (bkx B200 path) starting");
+
+  // ---- index: one handle per GPU
+  diag("Loading suffix array file '%s'", o.sfx.c_str());
+  std::vector<bkx_index*> idx((size_t)o.gpus, nullptr);
+  if (bkx_open_index(o.sfx.c_str(), 0, 0, &idx[0]) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+  for (int g = 1; g < o.gpus; ++g)
+    if (bkx_clone_index(idx[0], g, &idx[(size_t)g]) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+  bkx_index_info info;
+  bkx_index_info_get(idx[0], &info);
+  diag("Genome Assembly Name: '%s' Descr: '%s' Title: '%s' Version: %d", info.dataset_name, info.dataset_name, info.dataset_name, info.version);
+  bkx_align_params P;
+  if (bkx_default_params(idx[0], o.pmode, &P) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+  P.max_subs = o.max_subs; P.min_edit_dist = o.edit_delta; P.max_ns = o.max_ns; P.align_strand = o.strand;
+
+  // ---- reads
+  Reads R;
+  if (load_reads(o, R) < 0) return 1;
+  const uint32_t n = R.n();
+  if (n == 0) { diag("Fatal: no reads loaded"); return 1; }
+  diag("Genome assembly suffix array loaded");
+  diag("Now aligning with minimum core size of %dbp...\n", P.min_core_len);
+
+  // ---- align: contiguous, even-sized read ranges, one host thread per GPU (reads shard with no exchange)
+  std::vector<bkx_read_result> res(n);
+  std::vector<bkx_align_stats> st((size_t)o.gpus);
+  std::vector<int> rcs((size_t)o.gpus, 0);
+  std::vector<std::string> errs((size_t)o.gpus);
+  {
+    std::vector<std::thread> th;
+    uint32_t per = ((n + o.gpus - 1) / o.gpus + 1) & ~1u;
+    for (int g = 0; g < o.gpus; ++g) {
+      uint32_t b = std::min<uint64_t>(n, (uint64_t)per * g), e = std::min<uint64_t>(n, (uint64_t)per * (g + 1));
+      memset(&st[(size_t)g], 0, sizeof(bkx_align_stats));
+      th.emplace_back([&, g, b, e]() {
+        if (e > b) {
+          rcs[(size_t)g] = bkx_align_reads(idx[(size_t)g], &P, R.bases.data(), R.offs.data() + b, e - b, res.data() + b, &st[(size_t)g]);
+          if (rcs[(size_t)g] < 0) errs[(size_t)g] = bkx_last_error();
+        }
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+  for (int g = 0; g < o.gpus; ++g)
+    if (rcs[(size_t)g] < 0) { diag("Fatal: %s", errs[(size_t)g].c_str()); return 1; }
+  bkx_align_stats S = st[0];  // the only reduction of the path: element-wise sum of the counters
+  for (int g = 1; g < o.gpus; ++g) {
+    uint64_t* d = (uint64_t*)&S;
+    const uint64_t* s = (const uint64_t*)&st[(size_t)g];
+    for (size_t k = 0; k < sizeof(S) / 8; ++k) d[k] += s[k];
+  }
+  diag("Alignment of %u from %u loaded completed", n, n);
+
+  // ---- read-length summary, Aligner.cpp:486-535
+  uint64_t tot_len = R.bases.size();
+  int minl = R.len(0), maxl = R.len(0);
+  for (uint32_t i = 1; i < n; ++i) { minl = std::min(minl, R.len(i)); maxl = std::max(maxl, R.len(i)); }
+  int avl = (int)(tot_len / n);
+  diag("Average length of all reads was: %d (min: %d, max: %d)", avl, minl, maxl);
+  if (o.max_subs != 0)
+    diag("Typical allowed aligner induced substitutions was: %d (min: %d, max: %d)", std::max(1, avl * o.max_subs / 100),
+         std::max(1, minl * o.max_subs / 100), std::max(1, maxl * o.max_subs / 100));
+  diag("Provisionally accepted %d aligned reads (%d uniquely, %d aligning to multiloci) aligning to a total of %d loci",
+       (int)S.tot_accepted_aligned, (int)S.tot_accepted_unique, (int)S.tot_accepted_multi, (int)S.tot_loci_aligned);
+
+  // ---- paired ends, Aligner.cpp:2876-3049
+  if (o.pe_mode) {
+    diag("Paired end association and partner alignment processing started..");
+    diag("Generating paired reads index over %d paired reads", n / 2);
+    diag("Starting to associate Paired End reads to be within insert size range ...");
+    diag("Processed putative 0 pairs, accepted 0");
+    bkx_pe_params PE;
+    memset(&PE, 0, sizeof(PE));
+    PE.pe_proc = o.pe_mode; PE.pair_min_len = o.pair_min; PE.pair_max_len = o.pair_max; PE.pair_strand = o.pair_strand;
+    PE.circularised = o.pe_circ;
+    bkx_pe_stats ps;
+    memset(&ps, 0, sizeof(ps));
+    if (bkx_pair_reads(idx[0], &P, &PE, res.data(), n / 2, R.bases.data(), R.offs.data(), &ps, nullptr) < 0) {
+      diag("Fatal: %s", bkx_last_error());
+      return 1;
+    }
+    diag("Completed association of Paired End reads from %u pairs, accepted %u pairs", n / 2, (unsigned)ps.accepted_num_paired);
+    diag("From %d Paired End pairs there were %d accepted (of which %d pairs were from recovered orphans)", (int)(n / 2),
+         (int)ps.accepted_num_paired, (int)ps.partner_paired);
+    // the reference adds PartnerUnpaired twice when it joins its threads (Aligner.cpp:2990,2997)
+    diag("%d Paired End pairs unrecoverable as still orphan partnered", (int)(2 * ps.partner_unpaired - ps.partner_paired));
+    diag("%d Paired End pairs were under length, %d over length, not accepted as being paired", (int)ps.under_len_pairs, (int)ps.over_len_pairs);
+    diag("%d Paired End aligned pairs were filtered out by chromosome", (int)ps.num_filtered_by_chrom);
+    diag("%d Paired End pairs have neither end uniquely aligned", (int)ps.unaligned_pairs);
+    if (o.pe_mode == BKX_PE_UNIQUE_SE || o.pe_mode == BKX_PE_ORPHAN_SE)
+      diag("%d Paired End reads were unable to be associated with partner read and accepted as if SE aligned", (int)ps.accepted_num_se);
+    diag("Paired end association and partner alignment processing completed..");
+  }
+
+  // ---- summary, Aligner.cpp:3535-3769
+  uint64_t nar[BKX_NAR_COUNT] = {0};
+  uint64_t plus = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    nar[res[i].nar]++;
+    if (res[i].nar == BKX_NAR_ACCEPTED && res[i].strand == '+') ++plus;
+  }
+  uint64_t no_match = nar[BKX_NAR_NOHIT] + S.num_sloughed_ns;
+  diag("From %u source reads there are %u accepted alignments, %u on '+' strand, %u on '-' strand", n, (unsigned)nar[BKX_NAR_ACCEPTED],
+       (unsigned)plus, (unsigned)(nar[BKX_NAR_ACCEPTED] - plus));
+  diag("A further %u multiloci aligned reads could not accepted as hits because they were unresolvable", (unsigned)nar[BKX_NAR_MULTIALIGN]);
+  diag("A further %u aligned reads were not accepted as hits because of insufficient Hamming edit distance", (unsigned)nar[BKX_NAR_MMDELTA]);
+  diag("A further %u '+' and %u '-' strand aligned reads not accepted because of flank trimming (%d were trimmed) requirements", 0u, 0u, 0);
+  diag("Unable to align %u source reads of which %d were not aligned as they contained excessive number of indeterminate 'N' bases",
+       (unsigned)no_match, (int)S.num_sloughed_ns);
+  diag("Read nonalignment reason summary:");
+  for (int k = 0; k < BKX_NAR_COUNT; ++k) {
+    uint64_t v = nar[k];
+    if (k == BKX_NAR_NS) v = S.num_sloughed_ns;  // the reference substitutes m_NumSloughedNs (Aligner.cpp:3724)
+    diag("   %u (%s) %s", (unsigned)v, kNarCode[k], kNarText[k]);
+  }
+
+  // ---- order and write
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hit_less(res[a], res[b], a, b); });
+  std::vector<bkx_entry> ents(info.num_entries + 1);
+  for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
+  FILE* fo = fopen(o.out.c_str(), "wb");
+  if (!fo) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
+  OutBuf ob(fo);
+  diag("Reporting of aligned result set started...");
+  if (o.fmt == 0) {
+    // ReadID,"ar","species","chrom",start,end,len,"strand",score,0,NumReads,TrimMismatches,"N/A","descriptor"
+    for (uint32_t k = 0; k < n; ++k) {
+      uint32_t i = order[k];
+      const bkx_read_result& r = res[i];
+      if (r.nar != BKX_NAR_ACCEPTED) continue;
+      std::string& s = ob.s;
+      append_uint(s, (uint64_t)i + 1);
+      s += ",\"ar\",\""; s += info.dataset_name; s += "\",\""; s += ents[r.chrom_id].name; s += "\",";
+      append_uint(s, r.match_loci); s += ',';
+      append_uint(s, (uint64_t)r.match_loci + r.match_len - 1); s += ',';
+      append_uint(s, r.match_len); s += ",\""; s += (char)r.strand; s += "\",0,0,1,";
+      append_uint(s, r.mismatches); s += ",\"N/A\",\""; s += R.name(i); s += "\"\n";
+      ob.maybe();
+    }
+  } else {
+    // SAM header: @HD, @SQ for every chromosome (or only those hit if more than -4 threshold), @PG
+    std::vector<char> hit(info.num_entries + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
+    bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
+    ob.s += "@HD\tVN:1.4\tSO:coordinate\n";
+    for (uint32_t e = 1; e <= info.num_entries; ++e)
+      if (all || hit[e]) {
+        ob.s += "@SQ\tAS:"; ob.s += info.dataset_name; ob.s += "\tSN:"; ob.s += ents[e].name; ob.s += "\tLN:";
+        append_uint(ob.s, ents[e].seq_len); ob.s += '\n';
+      }
+    ob.s += "@PG\tID:biokanga\tVN:4.4.2\n";
+    static const char kAsc[] = "ACGTN";
+    for (uint32_t k = 0; k < n; ++k) {
+      uint32_t i = order[k];
+      const bkx_read_result& r = res[i];
+      bool acc = r.nar == BKX_NAR_ACCEPTED;
+      if (!acc && o.fmt != 6) continue;
+      int flags = 0, tlen = 0;
+      long pnext = -1;
+      if (!o.pe_mode) {
+        flags = acc ? (r.strand == '+' ? 0 : 0x10) : 0x04;
+      } else {  // ReportBAMread, Aligner.cpp:5864-5925
+        bool pe2 = i & 1;
+        const bkx_read_result& m = res[pe2 ? i - 1 : i + 1];
+        flags = 0x01 | 0x02 | (pe2 ? 0x80 : 0x40);
+        if (acc) flags |= r.strand == '+' ? 0 : 0x10; else flags |= 0x04;
+        bool both = (r.flags & BKX_FLG_PE_ALIGNED) && (m.flags & BKX_FLG_PE_ALIGNED) && m.nar == BKX_NAR_ACCEPTED;
+        if (both) {
+          flags |= m.strand == '+' ? 0 : 0x20;
+          if (acc) {
+            long se = r.match_loci, pes = m.match_loci;
+            tlen = se <= pes ? (int)(pes - se) + m.match_len : (int)(se - pes) + r.match_len;
+            pnext = m.match_loci;
+          }
+        } else flags |= 0x08;
+      }
+      std::string& s = ob.s;
+      s += R.name(i); s += '\t';
+      append_uint(s, (uint64_t)flags); s += '\t';
+      if (acc) { s += ents[r.chrom_id].name; s += '\t'; append_uint(s, (uint64_t)r.match_loci + 1); }
+      else s += "*\t0";
+      s += "\t255\t";
+      append_uint(s, (uint64_t)R.len(i)); s += "M\t";
+      if (acc && pnext >= 0) { s += "=\t"; append_uint(s, (uint64_t)pnext + 1); s += '\t'; append_uint(s, (uint64_t)tlen); s += '\t'; }
+      else s += "*\t0\t0\t";
+      const uint8_t* b = R.bases.data() + R.offs[i];
+      int L = R.len(i);
+      if (acc && r.strand != '+') {
+        for (int q = L - 1; q >= 0; --q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
+      } else {
+        for (int q = 0; q < L; ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+      }
+      s += "\t*";
+      if (!acc) { s += "\t\tYU:Z:"; s += kNarCode[r.nar]; }
+      s += '\n';
+      ob.maybe();
+    }
+  }
+  ob.flush();
+  fclose(fo);
+  diag("Reporting of aligned result set completed");
+  for (auto* x : idx) bkx_close_index(x);
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  int hh = (int)(secs / 3600), mm = (int)(secs / 60) % 60;
+  diag("Exit code: 0 Total processing time: %3.2d:%2.2d:%06.3f seconds", hh, mm, secs - 3600.0 * hh - 60.0 * mm);
+  if (g_log) fclose(g_log);
+  return 0;
+}

@@ -1,0 +1,75 @@
+"""GPU: the host front-end `bkx-align` (drop-in for `biokanga align`) against the reference's own output
+files: CSV rows, SAM header + records and the alignment-summary log block, for SE and PE runs."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+import goldutil as gu
+from biokanga_b200 import lib as bkx
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(os.path.dirname(bkx.LIB_PATH), "bkx-align")
+
+RUNS = [("tiny", "r100_s3"), ("tiny", "r100_s5_e2"), ("tiny", "mixed_s3"), ("tiny", "r251_s6"), ("tiny", "r100_s3_Q2"),
+        ("tiny", "r100_s4_m2"), ("tiny", "pe_U2"), ("tiny", "pe_U4"), ("tiny", "pe_U1"), ("tiny", "pe_U3"),
+        ("tiny", "pe_U1_far"), ("repeats", "r100_s3_m3"), ("repeats", "r60_s5")]
+
+
+def summary_block(path):
+    keep, on = [], False
+    for ln in open(path, errors="replace"):
+        body = ln.split("](biokanga) ", 1)[1] if "](biokanga) " in ln else ln
+        if "Alignment of" in body and "completed" in body:
+            on = True
+        if on and ("Reporting of aligned result set" in body or "Exit code" in body):
+            continue
+        if on:
+            keep.append(body.rstrip("\n"))
+    return keep
+
+
+@pytest.mark.parametrize("case,tag", RUNS)
+def test_cli_outputs_match_reference(case, tag, golden_dir, tmp_path):
+    assert os.path.exists(CLI), "bkx-align is not built"
+    run = gu.runs(case)[tag]
+    sfx = gu.sfx_path(case, golden_dir)
+    files = [os.path.join(gu.GOLD, case, f) for f in run["reads"]]  # .gz inputs are read directly
+    base = [CLI, "align", "-I", sfx, "-i", files[0]] + (["-u", files[1]] if len(files) > 1 else []) + run["args"]
+    # -M0 CSV + log
+    subprocess.run(base + ["-M0", "-o", str(tmp_path / "o.csv"), "-F", str(tmp_path / "o.log")], check=True,
+                   stdout=subprocess.DEVNULL)
+    ours = sorted(open(tmp_path / "o.csv").read().splitlines())
+    ref = sorted(gzip.open(os.path.join(gu.GOLD, case, tag + ".csv.gz"), "rt").read().splitlines())
+    assert ours == ref
+    exp_log = open(os.path.join(gu.GOLD, case, tag + ".log")).read().splitlines()
+    assert summary_block(tmp_path / "o.log") == exp_log
+    # -M6 SAM: identical header, identical record set
+    subprocess.run(base + ["-M6", "-o", str(tmp_path / "o.sam")], check=True, stdout=subprocess.DEVNULL)
+    ours = open(tmp_path / "o.sam").read().splitlines()
+    ref = gzip.open(os.path.join(gu.GOLD, case, tag + ".sam.gz"), "rt").read().splitlines()
+    assert [x for x in ours if x.startswith("@")] == [x for x in ref if x.startswith("@")]
+    assert sorted(x for x in ours if not x.startswith("@")) == sorted(x for x in ref if not x.startswith("@"))
+    # accepted records come out in the reference's coordinate order
+    def coords(lines, names):
+        out = []
+        for x in lines:
+            c = x.split("\t")
+            if not x.startswith("@") and not int(c[1]) & 4:
+                out.append((names.index(c[2]), int(c[3])))
+        return out
+    names = [x.split("\t")[2][3:] for x in ref if x.startswith("@SQ")]
+    co = coords(ours, names)
+    assert co == sorted(co)
+
+
+def test_cli_rejects_unsupported_and_bad_options(tmp_path, golden_dir):
+    sfx = gu.sfx_path("tiny", golden_dir)
+    rd = os.path.join(gu.GOLD, "tiny", "r100.fa.gz")
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-r3"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not supported" in r.stderr
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-s99"], capture_output=True, text=True)
+    assert r.returncode != 0
+    r = subprocess.run([CLI, "align", "-I", "/nonexistent.sfx", "-i", rd, "-o", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode != 0
