@@ -107,11 +107,11 @@ static int choose_k(uint64_t n, int requested, size_t free_bytes, bool wide) {
   if (requested > 0) return std::min(std::max(requested, 4), 17);
   // ceil(log4 n) + 1: on average 1/4 suffix per bucket, so most absent cores die at the table lookup
   // without touching the suffix array (measured: k=17 beats 16 by 8 % at 3.1 G symbols).  HBM is there
-  // to be used (180 GB): the table may take up to 45 % of what is free.
+  // to be used (180 GB): the table may take up to 55 % of what is free.
   int k = 8;
   while (k < 17 && (1ull << (2 * (k - 1))) < n) ++k;
   size_t el = wide ? 8 : 4;
-  while (k > 8 && (double)((1ull << (2 * k)) + 1) * el > 0.45 * (double)free_bytes) --k;
+  while (k > 8 && (double)((1ull << (2 * k)) + 1) * el > 0.55 * (double)free_bytes) --k;
   return k;
 }
 
