@@ -230,7 +230,7 @@ def run_bkx(args):
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     h_bases = torch.empty(nreads * args.read_len, dtype=torch.uint8).pin_memory()
     h_bases.copy_(d_bases)
-    h_offs = torch.arange(nreads + 1, dtype=torch.int64) * args.read_len
+    h_offs = (torch.arange(nreads + 1, dtype=torch.int64) * args.read_len).pin_memory()
     h_out = torch.empty(nreads * 32, dtype=torch.uint8).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
     hst = abi.AlignStats()

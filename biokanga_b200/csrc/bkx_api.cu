@@ -70,6 +70,7 @@ struct bkx_index {
   unsigned int* d_cursor[2] = {nullptr, nullptr};   // per slot: [0] fast cursor, [1] general cursor, [2] deferred count
   int fast_grid = 0;
   int fast_W = 0;
+  uint64_t max_len_prepared = 0;
   HashPool hp{};
   int grid = 0;
   int grid_W = 0;
@@ -679,13 +680,7 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
   if (n_reads == 0) return BKX_OK;
   std::lock_guard<std::mutex> lk(x->mtx);
   CU(cudaSetDevice(x->device));
-  uint32_t max_len = 0;
-  for (uint32_t i = 0; i < n_reads; ++i) {
-    if (offsets[i + 1] < offsets[i]) return fail(BKX_ERR_PARAM, "offsets not monotonic at read %u", i);
-    max_len = std::max<uint64_t>(max_len, offsets[i + 1] - offsets[i]);
-  }
   int W = 0;
-  if ((rc = prepare_launch(x, k, max_len, &W)) < 0) return rc;
   CU(cudaMemsetAsync(x->d_stats, 0, sizeof(bkx_align_stats), x->slot[0].st));
   CU(cudaStreamSynchronize(x->slot[0].st));
   const uint32_t kBatchReads = 1u << 20;
@@ -707,6 +702,25 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
     uint32_t cnt = std::min(kBatchReads, n_reads - start);
     while (cnt > 1 && offsets[start + cnt] - offsets[start] > kBatchBases) cnt = (cnt + 1) / 2;
     uint64_t nb = offsets[start + cnt] - offsets[start];
+    // longest read of this slice (overlaps with the GPU work of the previous slices)
+    uint64_t max_len = 0;
+    bool mono = true;
+    for (uint32_t i = start; i < start + cnt; ++i) {
+      uint64_t a = offsets[i], z = offsets[i + 1];
+      mono &= (z >= a);
+      uint64_t l = z - a;
+      max_len = l > max_len ? l : max_len;
+    }
+    if (!mono) return fail(BKX_ERR_PARAM, "offsets not monotonic in reads %u..%u", start, start + cnt);
+    if ((int)((max_len + 31) / 32) + 1 > x->grid_W || x->grid == 0 || x->hp.tables == nullptr ||
+        max_len > x->max_len_prepared) {
+      // (re)sizing the grid / overflow pool: let the slices in flight finish first
+      for (int si = 0; si < 2; ++si)
+        if (inflight[si] && (rc = drain(si)) < 0) return rc;
+      if ((rc = prepare_launch(x, k, (uint32_t)std::min<uint64_t>(max_len, 0xffffffffu), &W)) < 0) return rc;
+      x->max_len_prepared = std::max<uint64_t>(x->max_len_prepared, max_len);
+    }
+    W = x->grid_W;
     Slot& s = x->slot[b];
     if (inflight[b] && (rc = drain(b)) < 0) return rc;
     if (nb + 64 > s.bases_cap) {
