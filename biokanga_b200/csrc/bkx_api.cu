@@ -219,7 +219,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
   // prefix table
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
-  bool wide = n >= (1ull << 32);
+  bool wide = n >= (1ull << 32) || getenv("BKX_FORCE_WIDE_PT") != nullptr;  // (env: test hook for the u64 table)
   int k = choose_k(n, prefix_k, free_b, wide);
   uint64_t pt_entries = (1ull << (2 * k)) + 1;
   void* pt = nullptr;
@@ -843,6 +843,20 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
     for (size_t i = 0; i < sizeof(hs) / 8; ++i) d[i] += s[i];
   }
   if (len_dist) for (size_t i = 0; i < ld.size(); ++i) len_dist[i] += ld[i];
+  return BKX_OK;
+}
+
+// Page-lock / unlock caller memory so the library's H2D / D2H copies run asynchronously at full PCIe speed.
+extern "C" int bkx_pin_host(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return BKX_OK;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(BKX_ERR_CUDA, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e)); }
+  return BKX_OK;
+}
+extern "C" int bkx_unpin_host(void* ptr) {
+  if (!ptr) return BKX_OK;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(BKX_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
   return BKX_OK;
 }
 

@@ -323,6 +323,10 @@ int main(int argc, char** argv) {
 
   // ---- align: contiguous, even-sized read ranges, one host thread per GPU (reads shard with no exchange)
   std::vector<bkx_read_result> res(n);
+  // page-lock the read arena and the record array: H2D / D2H then stream asynchronously, double buffered
+  bool pinned = bkx_pin_host(R.bases.data(), R.bases.size()) >= 0 && bkx_pin_host(R.offs.data(), R.offs.size() * 8) >= 0 &&
+                bkx_pin_host(res.data(), res.size() * sizeof(bkx_read_result)) >= 0;
+  if (!pinned) diag("Note: unable to page-lock host buffers (%s); continuing with pageable copies", bkx_last_error());
   std::vector<bkx_align_stats> st((size_t)o.gpus);
   std::vector<int> rcs((size_t)o.gpus, 0);
   std::vector<std::string> errs((size_t)o.gpus);
@@ -349,6 +353,7 @@ int main(int argc, char** argv) {
     const uint64_t* s = (const uint64_t*)&st[(size_t)g];
     for (size_t k = 0; k < sizeof(S) / 8; ++k) d[k] += s[k];
   }
+  bkx_unpin_host(R.bases.data()); bkx_unpin_host(R.offs.data()); bkx_unpin_host(res.data());
   diag("Alignment of %u from %u loaded completed", n, n);
 
   // ---- read-length summary, Aligner.cpp:486-535

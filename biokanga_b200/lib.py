@@ -22,7 +22,7 @@ EXPORTS = [
     "bkx_open_index_dev", "bkx_clone_index", "bkx_close_index", "bkx_index_info_get", "bkx_get_entry",
     "bkx_get_ident", "bkx_get_seq", "bkx_default_params", "bkx_align_reads", "bkx_align_reads_device",
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
-    "bkx_build_suffix_array_device", "bkx_write_sfx",
+    "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
 ]
 
 
@@ -75,6 +75,8 @@ def lib():
                                  C.POINTER(abi.PEStats), vp]
     L.bkx_build_suffix_array_device.argtypes = [vp, u64, vp, i32]
     L.bkx_write_sfx.argtypes = [C.c_char_p, vp, u64, vp, u32, vp, u32, C.c_char_p]
+    L.bkx_pin_host.argtypes = [vp, C.c_size_t]
+    L.bkx_unpin_host.argtypes = [vp]
     L.bkx_last_kernel_ms.argtypes = [vp]
     L.bkx_last_kernel_ms.restype = C.c_float
     L.bkx_kernel_launches.argtypes = [vp]

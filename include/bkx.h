@@ -222,6 +222,12 @@ int bkx_build_suffix_array_device(const uint8_t* d_seq, uint64_t concat_len, uin
 int bkx_write_sfx(const char* path, const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t sfx_el_size,
                   const bkx_entry* entries, uint32_t num_entries, const char* dataset_name);
 
+/* ---- host memory ------------------------------------------------------------------------------
+ * Page-lock caller buffers (read arena, result array) so bkx_align_reads() copies asynchronously at PCIe speed;
+ * the reference keeps its reads in one mmap'd arena (Aligner.cpp:10572-10677) -- pin that arena once. */
+int bkx_pin_host(void* ptr, size_t bytes);
+int bkx_unpin_host(void* ptr);
+
 /* ---- instrumentation -------------------------------------------------------------------------- */
 /* Device time (ms) of the kernels of the last bkx_align_reads* call on this index, measured with
  * CUDA events on the launching stream; <0 if none. */

@@ -154,3 +154,34 @@ def test_device_resident_variant(golden_dir):
     assert_same(names, got, exp)
     assert gidx.last_kernel_ms() > 0
     assert gidx.kernel_launches() > 0
+
+
+def test_five_byte_suffix_elements_and_wide_prefix_table(golden_dir, tmp_path):
+    """5-byte SA elements (what `biokanga index` writes for >= 4e9 symbols) and the u64 prefix table, forced on a
+    small genome: results must equal the 4-byte run.  Also round-trips a 5-byte .sfx through the writer/reader."""
+    import os
+    _, oidx = indexes("tiny", golden_dir)
+    seq = np.array(oidx.seq())
+    sa4 = np.array(oidx.sa_bytes()).view(np.uint32)
+    sa5 = np.zeros((len(sa4), 5), dtype=np.uint8)
+    sa5[:, :4] = sa4.view(np.uint8).reshape(-1, 4)
+    ents = np.zeros(oidx.info.num_entries, dtype=abi.ENTRY_DTYPE)
+    for i, e in enumerate(oidx.entries()):
+        ents[i] = (e.entry_id, e.seq_len, e.start_ofs, e.end_ofs, e.name)
+    run = gu.runs("tiny")["r100_s5_e2"]
+    names, bases, offs = gu.load_reads("tiny", run)
+    exp, _ = oidx.align(gu.params_from_args(oidx, run["args"])[0], bases, offs, nthreads=4)
+    os.environ["BKX_FORCE_WIDE_PT"] = "1"
+    try:
+        g5 = bkx.Index.from_host(seq, sa5.reshape(-1), 5, ents, name="tiny5")
+        bkx.write_sfx(str(tmp_path / "t5.sfx"), seq, sa5.reshape(-1), 5, ents, name="tiny5")
+        g5f = bkx.Index.open(str(tmp_path / "t5.sfx"))
+    finally:
+        del os.environ["BKX_FORCE_WIDE_PT"]
+    assert g5.info.sfx_el_size == 5 and g5f.info.sfx_el_size == 5
+    for g in (g5, g5f):
+        got, _ = g.align(gu.params_from_args(g, run["args"])[0], bases, offs)
+        assert_same(names, got, exp)
+    o5 = po.OracleIndex(str(tmp_path / "t5.sfx"))
+    got, _ = o5.align(gu.params_from_args(o5, run["args"])[0], bases, offs)
+    assert_same(names, got, exp)
