@@ -398,7 +398,7 @@ __device__ __forceinline__ void stats_flush(const BlockStats& bs, bkx_align_stat
   }
 }
 
-__global__ void __launch_bounds__(kFastThreads, 2) align_fast_kernel(
+__global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
     uint32_t* __restrict__ hard_ids, unsigned int* __restrict__ n_hard) {
@@ -523,28 +523,45 @@ __global__ void __launch_bounds__(kFastThreads, 2) align_fast_kernel(
           else fresh = true;
         }
       }
-      // ---- the warp packs the new reads together: coalesced 32-byte rows, ballots build the 2-bit words
+      // ---- the warp packs the new reads together: each lane takes 4 bases (one coalesced 32-bit load),
+      //      a multiply gathers their 2-bit codes into a byte, three shuffles assemble the 64-bit words
       unsigned pk = __ballot_sync(0xffffffffu, fresh);
       while (pk) {
         const int j = __ffs(pk) - 1;
         pk &= pk - 1;
         const uint32_t rj = __shfl_sync(0xffffffffu, r, j);
         const int Lj = __shfl_sync(0xffffffffu, L, j);
-        const uint8_t* rd = bases + __ldg(offs + rj);
-        const int words = (Lj + 31) >> 5;
-        int nNj = 0;
-        unsigned badj = 0;
-        for (int w = 0; w < words; ++w) {
-          const int i = w * 32 + lane;
-          unsigned b = (i < Lj) ? (__ldg(rd + i) & 0x07u) : 0u;
-          unsigned b0 = __ballot_sync(0xffffffffu, b & 1u), b1 = __ballot_sync(0xffffffffu, b & 2u);
-          unsigned bn = __ballot_sync(0xffffffffu, b == 4u);
-          badj |= __ballot_sync(0xffffffffu, b > 4u);
-          if (lane == 0) region[w * 32 + j] = spread32(b0) | (spread32(b1) << 1);
-          nNj += __popc(bn);
+        const uintptr_t a0 = (uintptr_t)(bases + __ldg(offs + rj));
+        const uint32_t* ap = (const uint32_t*)(a0 & ~(uintptr_t)3);
+        const unsigned bsh = (unsigned)(a0 & 3) * 8;
+        const int ngroups = (Lj + 3) >> 2;
+        int cntN = 0;
+        bool badl = false;
+        for (int g0 = 0; g0 < ngroups; g0 += 32) {
+          const int g = g0 + lane;
+          uint32_t x = 0;
+          if (g < ngroups) {
+            x = __funnelshift_r(__ldg(ap + g), __ldg(ap + g + 1), bsh) & 0x07070707u;
+            const int rem = Lj - 4 * g;
+            if (rem < 4) x &= (1u << (8 * rem)) - 1u;
+          }
+          const uint32_t nf = x & 0x04040404u;               // N (4) or an invalid code (5..7)
+          cntN += __popc(nf);
+          badl |= (((nf >> 2) & (x | (x >> 1))) & 0x01010101u) != 0;
+          const uint32_t codes = (((x & 0x03030303u) * 0x00041041u) >> 18) & 0xffu;  // 4 bases -> 8 bits
+          uint64_t v = (uint64_t)codes << (8 * (lane & 7));
+          v |= __shfl_xor_sync(0xffffffffu, v, 1);
+          v |= __shfl_xor_sync(0xffffffffu, v, 2);
+          v |= __shfl_xor_sync(0xffffffffu, v, 4);
+          const int w = (g0 >> 3) + (lane >> 3);
+          if ((lane & 7) == 0 && w < W) region[w * 32 + j] = v;
         }
-        if (lane == 0) region[words * 32 + j] = 0;
-        if (lane == j) { nN = nNj; bad = badj != 0; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) cntN += __shfl_xor_sync(0xffffffffu, cntN, o);
+        const unsigned badm = __ballot_sync(0xffffffffu, badl);
+        const int wordsj = (Lj + 31) >> 5;
+        if (lane == 0) region[wordsj * 32 + j] = 0;   // zero pad word read by the unaligned extracts
+        if (lane == j) { nN = cntN; bad = badm != 0; }
       }
       __syncwarp();
       if (fresh) {
