@@ -126,8 +126,12 @@ def build_workload(args, rank, world, dev, torch, dist):
         torch.cuda.synchronize()
         if rank == 0:
             log("[bench] index broadcast to %d GPUs in %.2fs" % (world, time.time() - tb))
-    d_bases, d_offs = wl.sim_reads(d_seq, ents, args.reads, args.read_len, seed=args.seed + 100 + rank,
-                                   subs=tuple(range(0, args.read_subs + 1)), device=dev)
+    if getattr(args, "workload", "se") == "pe":
+        d_bases, d_offs = wl.sim_pairs(d_seq, ents, args.reads // 2, args.read_len, seed=args.seed + 100 + rank,
+                                       subs=tuple(range(0, args.read_subs + 1)), device=dev)
+    else:
+        d_bases, d_offs = wl.sim_reads(d_seq, ents, args.reads, args.read_len, seed=args.seed + 100 + rank,
+                                       subs=tuple(range(0, args.read_subs + 1)), device=dev)
     torch.cuda.synchronize()
     return d_seq, d_sa, ents, n, d_bases, d_offs
 
@@ -173,10 +177,20 @@ def run_bkx(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
 
+    pe_mode = args.workload == "pe"
+    pe = abi.PEParams()
+    pe.pe_proc, pe.pair_min_len, pe.pair_max_len = args.pe_mode, args.pe_min, args.pe_max
+    d_pst = torch.zeros(C.sizeof(abi.PEStats) // 8, dtype=torch.int64, device=dev)
+    d_ld = torch.zeros(100001, dtype=torch.int32, device=dev)
+
     def step():
         d_stats.zero_()
         idx.align_device(p, d_bases.data_ptr(), d_offs.data_ptr(), nreads, args.read_len, d_out.data_ptr(),
                          d_stats.data_ptr(), stream)
+        if pe_mode:
+            d_pst.zero_()
+            idx.pair_device(p, pe, d_out.data_ptr(), nreads // 2, d_bases.data_ptr(), d_offs.data_ptr(), args.read_len,
+                            d_pst.data_ptr(), d_ld.data_ptr(), stream)
         if world > 1:
             dist.all_reduce(d_stats)  # the only collective of the path: global stats counters
 
@@ -234,11 +248,18 @@ def run_bkx(args):
     h_out = torch.empty(nreads * 32, dtype=torch.uint8).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
     hst = abi.AlignStats()
-    idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)  # warm-up
+    h_res_np = h_out.numpy().view(abi.RESULT_DTYPE)
+
+    def e2e_call():
+        idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
+        if pe_mode:
+            idx.pair(p, pe, h_res_np, h_bases.numpy(), h_offs.numpy().view(np.uint64))
+
+    e2e_call()  # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
+        e2e_call()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -251,9 +272,13 @@ def run_bkx(args):
         "metric": "aligned reads/sec (150bp, <=4 subs)", "value": value, "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "configs[1]: %.1f Gbp synthetic genome + injected repeats, %d x %d bp SE reads per GPU, "
-                               "0..%d subs, -s%d" % (args.genome_mbp / 1e3, nreads, args.read_len, args.read_subs,
-                                                      args.max_subs),
+        "config": {"workload": ("configs[2] shape: %.1f Gbp synthetic genome + injected repeats, %d x 2x%d bp PE pairs per GPU, "
+                                "0..%d subs, -s%d -U%d -d%d -D%d" % (args.genome_mbp / 1e3, nreads // 2, args.read_len,
+                                                                        args.read_subs, args.max_subs, args.pe_mode, args.pe_min,
+                                                                        args.pe_max)) if pe_mode else
+                               ("configs[1]: %.1f Gbp synthetic genome + injected repeats, %d x %d bp SE reads per GPU, "
+                                "0..%d subs, -s%d" % (args.genome_mbp / 1e3, nreads, args.read_len, args.read_subs,
+                                                       args.max_subs)),
                    "genome_symbols": int(n), "reads_per_gpu": nreads, "read_len": args.read_len,
                    "max_subs_per_100bp": args.max_subs, "prefix_k": int(idx.info.prefix_k),
                    "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (
@@ -270,8 +295,12 @@ def run_bkx(args):
         "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]},
         "stats_reads_all_ranks": int(stats[-1]),
     }
+    if pe_mode:
+        pst = d_pst.cpu().numpy()
+        line["pe"] = {"pairs_per_gpu": nreads // 2, "accepted_pairs": int(pst[1]), "recovered_orphans": int(pst[3]),
+                      "unaligned_pairs": int(pst[0]), "pairs_per_s": value / 2}
 
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and not pe_mode:
         line["cpu_baseline"] = cpu_baseline_port(args, host_seq, host_sa, ents, h_bases.numpy(), res)
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -430,6 +459,11 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=4000000)
     ap.add_argument("--ref-port", action="store_true", help="reference arm: use the oracle port even if the binary exists")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="se", choices=["se", "pe"],
+                    help="se: configs[1] (default, the headline); pe: configs[2] shape -- 2x150 bp pairs, pairing + orphan recovery")
+    ap.add_argument("--pe-mode", type=int, default=1, help="-U mode for --workload pe (1 = recover orphans)")
+    ap.add_argument("--pe-min", type=int, default=200)
+    ap.add_argument("--pe-max", type=int, default=1000)
     ap.add_argument("--kernel-times", action="store_true", help="read the kernel's own events after every step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "bkx":

@@ -71,6 +71,8 @@ struct bkx_index {
   int fast_grid = 0;
   int fast_W = 0;
   uint64_t max_len_prepared = 0;
+  uint32_t* d_pe_list = nullptr;
+  size_t pe_list_cap = 0;
   HashPool hp{};
   int grid = 0;
   int grid_W = 0;
@@ -275,6 +277,7 @@ extern "C" void bkx_close_index(bkx_index* x) {
   if (x->d_stats) cudaFree(x->d_stats);
   if (x->d_pe_stats) cudaFree(x->d_pe_stats);
   if (x->d_len_dist) cudaFree(x->d_len_dist);
+  if (x->d_pe_list) cudaFree(x->d_pe_list);
   delete x;
 }
 
@@ -843,6 +846,44 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
     for (size_t i = 0; i < sizeof(hs) / 8; ++i) d[i] += s[i];
   }
   if (len_dist) for (size_t i = 0; i < ld.size(); ++i) len_dist[i] += ld[i];
+  return BKX_OK;
+}
+
+// Device-resident variant of bkx_pair_reads: results / reads / stats / histogram already on idx's GPU;
+// asynchronous on `cuda_stream` (NULL = the index's own stream).  d_len_dist: 100001 u32 or NULL.
+extern "C" int bkx_pair_reads_device(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe,
+                                     bkx_read_result* d_results, uint32_t n_pairs, const uint8_t* d_bases,
+                                     const uint64_t* d_offsets, uint32_t max_read_len, bkx_pe_stats* d_stats,
+                                     uint32_t* d_len_dist, void* cuda_stream) {
+  if (!x || !pe || !d_results) return fail(BKX_ERR_PARAM, "null argument");
+  if (pe->pe_proc < BKX_PE_ORPHAN || pe->pe_proc > BKX_PE_UNIQUE_SE) return fail(BKX_ERR_PARAM, "bad pe_proc %d", pe->pe_proc);
+  const bool rescue = pe->pe_proc == BKX_PE_ORPHAN || pe->pe_proc == BKX_PE_ORPHAN_SE;
+  if (pe->pair_min_len < 25 || pe->pair_max_len > 100000 || pe->pair_min_len > pe->pair_max_len)
+    return fail(BKX_ERR_PARAM, "bad insert size range %d..%d", pe->pair_min_len, pe->pair_max_len);
+  KParams k{};
+  if (rescue) {
+    int rc = check_params(p, &k);
+    if (rc < 0) return rc;
+    if (!d_bases || !d_offsets) return fail(BKX_ERR_PARAM, "orphan recovery needs the read sequences");
+    if (max_read_len > (uint32_t)kRescueMaxLen) return fail(BKX_ERR_PARAM, "read length %u exceeds cMaxSeqLen", max_read_len);
+  }
+  if (n_pairs == 0) return BKX_OK;
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : x->slot[0].st;
+  if (rescue && n_pairs > x->pe_list_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (x->d_pe_list) cudaFree(x->d_pe_list);
+    x->pe_list_cap = (size_t)n_pairs * 5 / 4;
+    CU(cudaMalloc((void**)&x->d_pe_list, x->pe_list_cap * 4));
+  }
+  unsigned int* cnt = x->d_cursor[1];  // [0] rescue cursor, [3] orphan count (slot 1's scalars are free here)
+  CU(cudaMemsetAsync(cnt + 3, 0, sizeof(unsigned int), st));
+  CU(launch_pair(*pe, d_results, n_pairs, d_stats, d_len_dist, rescue ? x->d_pe_list : nullptr, cnt + 3, st));
+  if (rescue)
+    CU(launch_rescue(x->d, k, *pe, d_results, x->d_pe_list, cnt + 3, d_bases, d_offsets, std::max<int>((int)max_read_len, 32),
+                     d_stats, d_len_dist, cnt, st));
+  x->launches += rescue ? 2 : 1;
   return BKX_OK;
 }
 

@@ -23,6 +23,7 @@ EXPORTS = [
     "bkx_get_ident", "bkx_get_seq", "bkx_default_params", "bkx_align_reads", "bkx_align_reads_device",
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
+    "bkx_pair_reads_device",
 ]
 
 
@@ -75,6 +76,8 @@ def lib():
                                  C.POINTER(abi.PEStats), vp]
     L.bkx_build_suffix_array_device.argtypes = [vp, u64, vp, i32]
     L.bkx_write_sfx.argtypes = [C.c_char_p, vp, u64, vp, u32, vp, u32, C.c_char_p]
+    L.bkx_pair_reads_device.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, u32, vp, vp, u32, vp,
+                                        vp, vp]
     L.bkx_pin_host.argtypes = [vp, C.c_size_t]
     L.bkx_unpin_host.argtypes = [vp]
     L.bkx_last_kernel_ms.argtypes = [vp]
@@ -212,6 +215,12 @@ class Index:
         check(lib().bkx_pair_reads(self._h, C.byref(params), C.byref(pe), results.ctypes.data, n_pairs, b, o,
                                    C.byref(st), ld))
         return st
+
+    def pair_device(self, params, pe, d_results, n_pairs, d_bases, d_offsets, max_read_len, d_stats=None,
+                    d_len_dist=None, stream=None):
+        """Device pointers, asynchronous on `stream`."""
+        check(lib().bkx_pair_reads_device(self._h, C.byref(params), C.byref(pe), d_results, n_pairs, d_bases, d_offsets,
+                                          max_read_len, d_stats, d_len_dist, stream))
 
     def last_kernel_ms(self):
         return float(lib().bkx_last_kernel_ms(self._h))

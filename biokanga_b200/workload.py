@@ -105,6 +105,55 @@ def sim_reads(d_seq, ents, n_reads, length, seed=2, subs=(0, 1, 2, 3, 4), device
     return out, offs
 
 
+def sim_pairs(d_seq, ents, n_pairs, length, seed=3, subs=(0, 1, 2, 3, 4), insert=(300, 600), junk_frac=0.02,
+              device="cuda", chunk=1 << 20):
+    """Paired-end reads: returns (d_bases uint8[2*n_pairs*length], d_offsets int64[2*n_pairs+1]) with PE1 / PE2 of a pair
+    adjacent.  PE1 is the first `length` bases of a fragment of length U[insert] (either strand), PE2 the reverse
+    complement of its last `length` bases; junk_frac of the mates are replaced by random sequence (orphans)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lens = torch.from_numpy(ents["seq_len"].astype(np.int64)).to(device)
+    starts = torch.from_numpy(ents["start_ofs"].astype(np.int64)).to(device)
+    w = torch.where(lens >= insert[1], lens.double(), torch.zeros_like(lens, dtype=torch.double))
+    out = torch.empty(2 * n_pairs * length, dtype=torch.uint8, device=device).view(n_pairs, 2, length)
+    subs_t = torch.tensor(subs, device=device)
+    kmax = int(max(subs))
+    ar = torch.arange(length, device=device)
+
+    def mutate(b, m):
+        if kmax == 0:
+            return b
+        k = subs_t[torch.randint(0, len(subs), (m,), device=device, generator=g)]
+        pos = torch.rand(m, length, device=device, generator=g).topk(kmax, dim=1).indices
+        add = torch.randint(1, 4, (m, kmax), dtype=torch.uint8, device=device, generator=g)
+        cur = torch.gather(b, 1, pos)
+        new = torch.where((torch.arange(kmax, device=device)[None, :] < k[:, None]) & (cur < 4), (cur + add) & 3, cur)
+        return b.scatter(1, pos, new)
+
+    def revcomp(b):
+        br = torch.flip(b, dims=[1])
+        return torch.where(br < 4, 3 - br, br)
+
+    for s0 in range(0, n_pairs, chunk):
+        m = min(chunk, n_pairs - s0)
+        c = torch.multinomial(w, m, replacement=True, generator=g)
+        fl = torch.randint(insert[0], insert[1] + 1, (m,), device=device, generator=g)
+        p = starts[c] + (torch.rand(m, device=device, generator=g, dtype=torch.double) * (lens[c] - fl + 1).double()).long()
+        left = d_seq[p[:, None] + ar[None, :]]                      # first `length` bases of the fragment (+ strand)
+        right = d_seq[(p + fl - length)[:, None] + ar[None, :]]     # last `length` bases
+        minus = torch.rand(m, device=device, generator=g) < 0.5     # fragment taken from the - strand
+        pe1 = torch.where(minus[:, None], revcomp(right), left)
+        pe2 = torch.where(minus[:, None], left, revcomp(right))
+        pe1, pe2 = mutate(pe1, m), mutate(pe2, m)
+        junk = torch.rand(m, device=device, generator=g) < junk_frac
+        rnd = torch.randint(0, 4, (m, length), dtype=torch.uint8, device=device, generator=g)
+        pe2 = torch.where(junk[:, None], rnd, pe2)
+        out[s0:s0 + m, 0] = pe1
+        out[s0:s0 + m, 1] = pe2
+    offs = torch.arange(2 * n_pairs + 1, device=device, dtype=torch.int64) * length
+    return out.view(-1), offs
+
+
 def algorithmic_bytes(results, concat_len, el_size, read_len):
     """W(read) = seeds*S*(E+8) + cands*(E+ceil(L/4)) + ceil(L/4) + 32, summed."""
     S = int(np.ceil(np.log2(concat_len)))

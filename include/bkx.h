@@ -213,6 +213,11 @@ int bkx_pair_reads(bkx_index* idx, const bkx_align_params* p, const bkx_pe_param
                    uint32_t n_pairs, const uint8_t* bases, const uint64_t* offsets, bkx_pe_stats* stats,
                    uint32_t* len_dist);
 
+/* Device variant: every pointer is a device pointer on idx's GPU; asynchronous on `cuda_stream`. */
+int bkx_pair_reads_device(bkx_index* idx, const bkx_align_params* p, const bkx_pe_params* pe, bkx_read_result* d_results,
+                          uint32_t n_pairs, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t max_read_len,
+                          bkx_pe_stats* d_stats, uint32_t* d_len_dist, void* cuda_stream);
+
 /* ---- index construction for synthetic / bench genomes: the two halves of `biokanga index` ---------
  * (kangax.cpp:774-926 -> CSfxArrayV3::QSortSeq, SfxArrayV2.cpp:9451-9542; file layout SfxArrayV2.h:79-104,
  * 174-187).  d_seq: device, 1 byte/base incl. one EOS(7) after every entry; d_sa: device, concat_len
