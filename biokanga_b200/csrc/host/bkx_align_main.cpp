@@ -17,6 +17,7 @@
 // -b/-C bisulfite/SOLiD, BAM output) are recognised and rejected with a clear message.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -90,7 +91,7 @@ struct SeqFile {  // FASTA / FASTQ, plain or gzip (zlib reads both)
     }
   }
   // next record: descriptor (text after '>' / '@' up to the first white space, <= 127 chars) and sequence
-  bool next(std::string& descr, std::string& seq) {
+  bool next(std::string& descr, std::string& seq, std::string& qual) {
     std::string ln;
     do { if (!getline(ln)) return false; } while (ln.empty());
     if (ln[0] != '>' && ln[0] != '@') return false;
@@ -99,9 +100,10 @@ struct SeqFile {  // FASTA / FASTQ, plain or gzip (zlib reads both)
     while (e < ln.size() && !isspace((unsigned char)ln[e]) && e - 1 < 127) ++e;
     descr.assign(ln, 1, e - 1);
     seq.clear();
+    qual.clear();
     if (fastq) {
       if (!getline(seq)) return false;
-      std::string plus, qual;
+      std::string plus;
       getline(plus);
       getline(qual);
     } else {
@@ -125,9 +127,32 @@ static inline uint8_t base_code(char c) {  // CFasta::Ascii2Sense, Fasta.cpp:151
   }
 }
 
+// 4-bit quality packed next to the base (bits 4..7), CAligner::LoadRawReads, Aligner.cpp:11130-11196
+static inline unsigned qual4(int qmode, unsigned c) {
+  unsigned q;
+  switch (qmode) {
+    case 0:  // Sanger / Illumina 1.8+
+      if (c < 33) c = 33; else if (c >= 126) c = 125;
+      q = c - 33;
+      break;
+    case 1:  // Illumina 1.3+
+      if (c < 64) c = 64; else if (c >= 126) c = 125;
+      q = c - 64;
+      break;
+    default:  // Solexa < 1.3
+      if (c < 59 || c >= 126) c = c < 64 ? 64 : 125;
+      q = c - 59;
+      q = (uint8_t)(10 * log(1 + pow(10.0, ((double)q / 10.0) / log(10.0))));
+      break;
+  }
+  if (q > 40) q = 40;
+  return ((q + 2) * 15) / 40;
+}
+
 struct Opts {
   int pmode = 0, strand = 0, max_subs = 10, edit_delta = 1, max_ns = 1, fmt = 5, pe_mode = 0, pair_min = 100,
-      pair_max = 1000, trim5 = 0, trim3 = 0, min_len = 50, max_len = 500, threads = 0, gpus = 1, sam_seq_thres = 10000;
+      pair_max = 1000, trim5 = 0, trim3 = 0, min_len = 50, max_len = 500, threads = 0, gpus = 1, sam_seq_thres = 10000,
+      qmode = 3;
   bool pair_strand = false, pe_circ = false;
   std::vector<std::string> in, pair;
   std::string sfx, out, logfile, title;
@@ -140,10 +165,10 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
     SeqFile f1, f2;
     if (!f1.open(o.in[fi])) { diag("Unable to open '%s'", o.in[fi].c_str()); return -1; }
     if (pe && !f2.open(o.pair[fi])) { diag("Unable to open '%s'", o.pair[fi].c_str()); return -1; }
-    std::string d1, s1, d2, s2;
+    std::string d1, s1, d2, s2, q1, q2;
     uint32_t accepted = 0, under = 0, over = 0;
-    while (f1.next(d1, s1)) {
-      if (pe && !f2.next(d2, s2)) { diag("Problem parsing sequence after %u reads parsed", accepted); return -1; }
+    while (f1.next(d1, s1, q1)) {
+      if (pe && !f2.next(d2, s2, q2)) { diag("Problem parsing sequence after %u reads parsed", accepted); return -1; }
       auto bad_len = [&](const std::string& s, uint32_t& u, uint32_t& ov) {
         if (o.trim5 + o.trim3 + o.min_len > (int)s.size()) { ++u; return true; }
         if (o.trim5 + o.trim3 + o.max_len < (int)s.size()) { ++ov; return true; }
@@ -151,16 +176,18 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
       };
       if (bad_len(s1, under, over)) continue;
       if (pe && bad_len(s2, under, over)) continue;
-      auto add = [&](const std::string& d, const std::string& s) {
+      auto add = [&](const std::string& d, const std::string& s, const std::string& q) {
         size_t b = (size_t)o.trim5, e = s.size() - (size_t)o.trim3;
-        for (size_t i = b; i < e; ++i) R.bases.push_back(base_code(s[i]));
+        bool useq = o.qmode != 3 && q.size() == s.size();
+        for (size_t i = b; i < e; ++i)
+          R.bases.push_back((uint8_t)(base_code(s[i]) | (useq ? (qual4(o.qmode, (unsigned char)q[i]) << 4) : 0)));
         R.offs.push_back(R.bases.size());
         R.name_ofs.push_back(R.names.size());
         R.names.insert(R.names.end(), d.begin(), d.end());
         R.names.push_back('\0');
       };
-      add(d1, s1);
-      if (pe) add(d2, s2);
+      add(d1, s1, q1);
+      if (pe) add(d2, s2, q2);
       ++accepted;
     }
     f1.close();
@@ -217,7 +244,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'I': o.sfx = v; break;
       case 'o': o.out = v; break;
       case 't': o.title = v; break;
-      case 'g': if (iv != 3) unsupported.push_back("-g (quality scores other than 3=ignore)"); break;
+      case 'g': o.qmode = iv; break;
       case '#': if (iv != 1) unsupported.push_back("-# read sampling"); break;
       case 'r': if (iv != 0) unsupported.push_back("-r multi-loci modes"); break;
       case 'R': break;  // only meaningful with -r
@@ -251,7 +278,9 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.max_subs < 0 || o.max_subs > 15) { fprintf(stderr, "Error: max substitutions '-s%d' must be in range 0..15\n", o.max_subs); return -1; }
   if (o.edit_delta < 1 || o.edit_delta > 2) { fprintf(stderr, "Error: Min Hamming edit distance '-e%d' must be in range 1..2\n", o.edit_delta); return -1; }
   if (o.max_ns < 0 || o.max_ns > 5) { fprintf(stderr, "Error: Allowed number of indeterminate 'N's '-n%d' must be in range 0..5\n", o.max_ns); return -1; }
-  if (o.fmt != 0 && o.fmt != 5 && o.fmt != 6) { fprintf(stderr, "bkx-align: output format -M%d not supported (0, 5, 6)\n", o.fmt); return -1; }
+  if (o.fmt < 0 || o.fmt > 6) { fprintf(stderr, "Error: Output format mode '-M%d' specified outside of range 0..6\n", o.fmt); return -1; }
+  if (o.qmode < 0 || o.qmode > 3) { fprintf(stderr, "Error: fastq quality scoring method '-g%d' specified outside of range 0..3\n", o.qmode); return -1; }
+  if (o.pe_mode && !(o.fmt == 0 || o.fmt >= 4)) { fprintf(stderr, "Error: paired end processing supports output formats -M0, -M4, -M5 and -M6 only\n"); return -1; }
   if (o.pe_mode < 0 || o.pe_mode > 4) { fprintf(stderr, "Error: paired end mode '-U%d' must be in range 0..4\n", o.pe_mode); return -1; }
   if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
   if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
@@ -282,12 +311,23 @@ static const char* kNarText[] = {
     "PE over maximum insert size", "PE partner not aligned", "PE partner aligned to inconsistent strand",
     "PE partner aligned to different target sequence", "PE alignment not accepted", "Alignment violated loci base constraints"};
 
-struct OutBuf {
-  FILE* f;
+struct OutBuf {  // plain or gzip (when the output name ends in .gz, as the reference does)
+  FILE* f = nullptr;
+  gzFile gz = nullptr;
   std::string s;
-  explicit OutBuf(FILE* ff) : f(ff) { s.reserve(1 << 22); }
-  void flush() { if (!s.empty()) { fwrite(s.data(), 1, s.size(), f); s.clear(); } }
+  bool open(const std::string& path) {
+    s.reserve(1 << 22);
+    if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0) { gz = gzopen(path.c_str(), "wb"); return gz != nullptr; }
+    f = fopen(path.c_str(), "wb");
+    return f != nullptr;
+  }
+  void flush() {
+    if (s.empty()) return;
+    if (gz) gzwrite(gz, s.data(), (unsigned)s.size()); else fwrite(s.data(), 1, s.size(), f);
+    s.clear();
+  }
   void maybe() { if (s.size() > (1 << 22) - 8192) flush(); }
+  void close() { flush(); if (gz) gzclose(gz); if (f) fclose(f); gz = nullptr; f = nullptr; }
 };
 
 static void append_uint(std::string& s, uint64_t v) { char b[24]; int n = snprintf(b, sizeof(b), "%llu", (unsigned long long)v); s.append(b, n); }
@@ -425,12 +465,33 @@ int main(int argc, char** argv) {
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hit_less(res[a], res[b], a, b); });
   std::vector<bkx_entry> ents(info.num_entries + 1);
   for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
-  FILE* fo = fopen(o.out.c_str(), "wb");
-  if (!fo) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
-  OutBuf ob(fo);
+  OutBuf ob;
+  if (!ob.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
   diag("Reporting of aligned result set started...");
-  if (o.fmt == 0) {
+  static const char kAsc[] = "ACGTN";
+  if (o.fmt == 4) {
+    // UCSC BED: track line then chrom, start, end+1, "ar", score, strand (Aligner.cpp:6355-6362, 6463-6466)
+    const char* title = o.title.empty() ? "kanga" : o.title.c_str();
+    ob.s += "track type=bed name=\""; ob.s += title; ob.s += "\" description=\""; ob.s += title; ob.s += "\"\n";
+    for (uint32_t k = 0; k < n; ++k) {
+      uint32_t i = order[k];
+      const bkx_read_result& r = res[i];
+      if (r.nar != BKX_NAR_ACCEPTED) continue;
+      std::string& s = ob.s;
+      s += ents[r.chrom_id].name; s += '\t';
+      append_uint(s, r.match_loci); s += '\t';
+      append_uint(s, (uint64_t)r.match_loci + r.match_len); s += "\tar\t0\t"; s += (char)r.strand; s += '\n';
+      ob.maybe();
+    }
+  } else if (o.fmt <= 3) {
     // ReadID,"ar","species","chrom",start,end,len,"strand",score,0,NumReads,TrimMismatches,"N/A","descriptor"
+    // -M2/-M3 append the read sequence, -M1/-M3 the matched genome sequence in read orientation (Aligner.cpp:6612-6621)
+    std::vector<std::vector<uint8_t>> genome(info.num_entries + 1);
+    if (o.fmt == 1 || o.fmt == 3)
+      for (uint32_t e = 1; e <= info.num_entries; ++e) {
+        genome[e].resize(ents[e].seq_len);
+        if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+      }
     for (uint32_t k = 0; k < n; ++k) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
@@ -441,7 +502,21 @@ int main(int argc, char** argv) {
       append_uint(s, r.match_loci); s += ',';
       append_uint(s, (uint64_t)r.match_loci + r.match_len - 1); s += ',';
       append_uint(s, r.match_len); s += ",\""; s += (char)r.strand; s += "\",0,0,1,";
-      append_uint(s, r.mismatches); s += ",\"N/A\",\""; s += R.name(i); s += "\"\n";
+      append_uint(s, r.mismatches); s += ",\"N/A\",\""; s += R.name(i); s += '"';
+      if (o.fmt >= 2) {
+        s += ",\"";
+        const uint8_t* b = R.bases.data() + R.offs[i];
+        for (int q = 0; q < R.len(i); ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+        s += '"';
+      }
+      if (o.fmt == 1 || o.fmt == 3) {
+        s += ",\"";
+        const uint8_t* g = genome[r.chrom_id].data() + r.match_loci;
+        if (r.strand == '-') for (int q = r.match_len - 1; q >= 0; --q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
+        else for (int q = 0; q < r.match_len; ++q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+        s += '"';
+      }
+      s += '\n';
       ob.maybe();
     }
   } else {
@@ -456,7 +531,6 @@ int main(int argc, char** argv) {
         append_uint(ob.s, ents[e].seq_len); ob.s += '\n';
       }
     ob.s += "@PG\tID:biokanga\tVN:4.4.2\n";
-    static const char kAsc[] = "ACGTN";
     for (uint32_t k = 0; k < n; ++k) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
@@ -497,14 +571,19 @@ int main(int argc, char** argv) {
       } else {
         for (int q = 0; q < L; ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
       }
-      s += "\t*";
+      // QUAL: '*' unless qualities were kept (-g0..2); 33 + q4*40/15, reversed with the sequence (Aligner.cpp:5929-5955)
+      int sumq = 0;
+      for (int q = 0; q < L; ++q) sumq += (b[q] >> 4) & 0x0f;
+      s += '\t';
+      if (sumq == 0) s += '*';
+      else if (acc && r.strand != '+') for (int q = L - 1; q >= 0; --q) s += (char)(33 + (((b[q] >> 4) & 0x0f) * 40) / 15);
+      else for (int q = 0; q < L; ++q) s += (char)(33 + (((b[q] >> 4) & 0x0f) * 40) / 15);
       if (!acc) { s += "\t\tYU:Z:"; s += kNarCode[r.nar]; }
       s += '\n';
       ob.maybe();
     }
   }
-  ob.flush();
-  fclose(fo);
+  ob.close();
   diag("Reporting of aligned result set completed");
   for (auto* x : idx) bkx_close_index(x);
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();

@@ -189,12 +189,50 @@ def case_repeats():
         align_runs(d, tmp, "repeats.sfx", runs)
 
 
+def case_formats():
+    """Output-format runs on the tiny index: CSV variants -M1..3, BED -M4, FASTQ qualities -g0/-g1 in SAM,
+    gzip output.  One FASTQ read set with descriptors that carry trailing words."""
+    d = os.path.join(GOLD, "formats")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        with gzip.open(os.path.join(tiny, "tiny.sfx.gz"), "rb") as f, open(os.path.join(tmp, "tiny.sfx"), "wb") as g:
+            shutil.copyfileobj(f, g)
+        import pyoracle as po
+        names, bases, offs = po.read_fasta_reads(os.path.join(tiny, "r100.fa.gz"))
+        rng = np.random.default_rng(5)
+        with open(os.path.join(tmp, "q.fq"), "wb") as f:
+            for i in range(600):
+                r = bases[offs[i]:offs[i + 1]]
+                q = bytes(rng.integers(66, 105, len(r)).astype(np.uint8))   # valid for Sanger and Illumina 1.3+
+                f.write(b"@" + names[i].encode() + b" extra words\n" + synth.BASES[r].tobytes() + b"\n+\n" + q + b"\n")
+        gz(os.path.join(tmp, "q.fq"), os.path.join(d, "q.fq.gz"))
+        runs = {
+            "m1": (["-s3", "-M1"], "m1.csv"), "m2": (["-s3", "-M2"], "m2.csv"), "m3": (["-s3", "-M3"], "m3.csv"),
+            "m4": (["-s3", "-M4"], "m4.bed"), "m4t": (["-s3", "-M4", "-tmytrack"], "m4t.bed"),
+            "g0": (["-s3", "-M6", "-g0"], "g0.sam"), "g1": (["-s3", "-M5", "-g1"], "g1.sam"),
+            "g2": (["-s3", "-M5", "-g2"], "g2.sam"), "gz": (["-s3", "-M0"], "z.csv.gz"),
+            "trim": (["-s3", "-M0", "-y5", "-Y7", "-l60"], "trim.csv"),
+        }
+        meta = {}
+        for tag, (args, out) in runs.items():
+            run(["align", "-I", "tiny.sfx", "-i", "q.fq", "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+            if out.endswith(".gz"):
+                shutil.copyfile(os.path.join(tmp, out), os.path.join(d, out))
+            else:
+                gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            meta[tag] = {"args": args, "out": out}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
         case_repeats()
+    if "formats" in which:
+        case_formats()
     print("fixtures written under", GOLD)

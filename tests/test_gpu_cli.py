@@ -73,3 +73,29 @@ def test_cli_rejects_unsupported_and_bad_options(tmp_path, golden_dir):
     assert r.returncode != 0
     r = subprocess.run([CLI, "align", "-I", "/nonexistent.sfx", "-i", rd, "-o", str(tmp_path / "x")], capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def _lines(path):
+    op = gzip.open if str(path).endswith(".gz") else open
+    with op(path, "rt") as f:
+        return f.read().splitlines()
+
+
+@pytest.mark.parametrize("tag", ["m1", "m2", "m3", "m4", "m4t", "g0", "g1", "g2", "gz", "trim"])
+def test_cli_output_formats_match_reference(tag, golden_dir, tmp_path):
+    """CSV variants -M1..3, BED -M4 (default and -t title), FASTQ qualities -g0/-g1/-g2 in SAM, gzip output, end trims."""
+    import json
+    fdir = os.path.join(gu.GOLD, "formats")
+    run = json.load(open(os.path.join(fdir, "runs.json")))[tag]
+    sfx = gu.sfx_path("tiny", golden_dir)
+    out = tmp_path / run["out"]
+    subprocess.run([CLI, "align", "-I", sfx, "-i", os.path.join(fdir, "q.fq.gz"), "-o", str(out)] + run["args"], check=True,
+                   stdout=subprocess.DEVNULL)
+    ours = _lines(out)
+    gold = os.path.join(fdir, run["out"] if run["out"].endswith(".gz") else run["out"] + ".gz")
+    ref = _lines(gold)
+    if run["out"].endswith(".gz"):
+        assert open(out, "rb").read(2) == b"\x1f\x8b"  # really gzip
+    head = [x for x in ref if x.startswith("@") or x.startswith("track")]
+    assert [x for x in ours if x.startswith("@") or x.startswith("track")] == head
+    assert sorted(ours) == sorted(ref)
