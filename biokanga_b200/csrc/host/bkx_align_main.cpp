@@ -330,6 +330,130 @@ struct OutBuf {  // plain or gzip (when the output name ends in .gz, as the refe
   void close() { flush(); if (gz) gzclose(gz); if (f) fclose(f); gz = nullptr; f = nullptr; }
 };
 
+// ---- BAM (BGZF) + BAI, as CSAMfile writes them (libbiokanga/SAMfile.cpp:1383-1660, 1839-2030, 2286-2556; bgzf.cpp) ----
+// BGZF: 0xff00-byte blocks, raw deflate level 6 (Aligner.cpp:722), standard 18-byte header / 8-byte footer, an empty
+// block at close.  Virtual address = (file offset of the block << 16) | offset inside the block.
+struct Bgzf {
+  FILE* f = nullptr;
+  std::vector<uint8_t> ubuf, cbuf;
+  size_t uofs = 0;
+  uint64_t block_addr = 0;
+  int level = 6;
+  bool open(const std::string& path) {
+    f = fopen(path.c_str(), "wb");
+    ubuf.resize(0x10000);
+    cbuf.resize(0x10000 + 1024);
+    return f != nullptr;
+  }
+  bool deflate_block(size_t len) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    zs.next_in = ubuf.data();
+    zs.avail_in = (uInt)len;
+    zs.next_out = cbuf.data() + 18;
+    zs.avail_out = (uInt)(cbuf.size() - 18 - 8);
+    if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); return false; }
+    deflateEnd(&zs);
+    size_t dlen = zs.total_out + 18 + 8;
+    static const uint8_t magic[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+    memcpy(cbuf.data(), magic, 18);
+    uint16_t bs = (uint16_t)(dlen - 1);
+    memcpy(cbuf.data() + 16, &bs, 2);
+    uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), ubuf.data(), (uInt)len), isz = (uint32_t)len;
+    memcpy(cbuf.data() + dlen - 8, &crc, 4);
+    memcpy(cbuf.data() + dlen - 4, &isz, 4);
+    if (fwrite(cbuf.data(), 1, dlen, f) != dlen) return false;
+    block_addr += dlen;
+    uofs = 0;
+    return true;
+  }
+  bool flush() { return uofs == 0 || deflate_block(uofs); }
+  bool write(const void* p, size_t len) {
+    const uint8_t* b = (const uint8_t*)p;
+    while (len) {
+      size_t c = std::min(len, (size_t)0xff00 - uofs);
+      memcpy(ubuf.data() + uofs, b, c);
+      uofs += c; b += c; len -= c;
+      if (uofs == 0xff00 && !deflate_block(uofs)) return false;
+    }
+    return true;
+  }
+  uint64_t tell() const { return (block_addr << 16) | (uint64_t)(uofs & 0xffff); }
+  bool close() {
+    bool ok = flush() && deflate_block(0);  // trailing empty block = BGZF EOF marker
+    if (f) fclose(f);
+    f = nullptr;
+    return ok;
+  }
+};
+
+static int bai_reg2bin(int beg, int end) {  // SAM spec section 5.3 (half-open interval)
+  --end;
+  if (beg >> 14 == end >> 14) return ((1 << 15) - 1) / 7 + (beg >> 14);
+  if (beg >> 17 == end >> 17) return ((1 << 12) - 1) / 7 + (beg >> 17);
+  if (beg >> 20 == end >> 20) return ((1 << 9) - 1) / 7 + (beg >> 20);
+  if (beg >> 23 == end >> 23) return ((1 << 6) - 1) / 7 + (beg >> 23);
+  if (beg >> 26 == end >> 26) return ((1 << 3) - 1) / 7 + (beg >> 26);
+  return 0;
+}
+
+// BAI built the way CSAMfile::AddChunk / UpdateSAIIndex do: per reference, bins in ascending number, chunks of a bin
+// merged while the next alignment starts no later than the chunk's last end + 1, a sparse 16 kb linear index
+// (windows in which no alignment starts stay 0), references after the last aligned one get no block.
+struct BaiBuilder {
+  struct Chunk { uint64_t sva, eva; uint32_t start, end; };
+  std::vector<std::pair<int, std::vector<Chunk>>> bins;  // filled through `slot`
+  std::vector<int> slot;                                   // bin number -> index into bins, -1 if empty
+  std::vector<uint64_t> lin;
+  uint32_t n_lin = 0;
+  std::string out;
+  BaiBuilder() : slot(37450, -1) {}
+  void add(uint64_t sva, uint32_t start, uint64_t eva, uint32_t end) {
+    uint32_t k = start / 0x4000;
+    if (lin.size() <= k) lin.resize(k + 1, 0);
+    if (lin[k] == 0) { n_lin = k + 1; lin[k] = sva; }
+    int bin = bai_reg2bin((int)start, (int)end);
+    if (slot[bin] < 0) { slot[bin] = (int)bins.size(); bins.push_back({bin, {}}); bins.back().second.push_back({sva, eva, start, end}); return; }
+    std::vector<Chunk>& cs = bins[slot[bin]].second;
+    Chunk& c = cs.back();
+    if (start > c.end + 1) cs.push_back({sva, eva, start, end});
+    else {
+      if (c.start > start) { c.start = start; c.sva = sva; }
+      if (c.end < end) c.end = end;
+      c.eva = eva;
+    }
+  }
+  void put32(uint32_t v) { out.append((const char*)&v, 4); }
+  void put64(uint64_t v) { out.append((const char*)&v, 8); }
+  void end_ref() {  // UpdateSAIIndex: emit this reference's block and reset
+    put32((uint32_t)bins.size());
+    if (!bins.empty()) {
+      std::sort(bins.begin(), bins.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+      for (auto& b : bins) {
+        put32((uint32_t)b.first);
+        put32((uint32_t)b.second.size());
+        for (auto& c : b.second) { put64(c.sva); put64(c.eva); }
+      }
+      put32(n_lin);
+      for (uint32_t i = 0; i < n_lin; ++i) put64(lin[i]);
+    } else {
+      put32(0);
+    }
+    bins.clear();
+    std::fill(slot.begin(), slot.end(), -1);
+    lin.clear();
+    n_lin = 0;
+  }
+};
+
+static bool is_bam_name(const std::string& p) {  // kanga.cpp:849-857: longer than 5 chars and ending in ".bam"
+  if (p.size() <= 5) return false;
+  std::string e = p.substr(p.size() - 4);
+  for (auto& c : e) c = (char)tolower((unsigned char)c);
+  return e == ".bam";
+}
+
 static void append_uint(std::string& s, uint64_t v) { char b[24]; int n = snprintf(b, sizeof(b), "%llu", (unsigned long long)v); s.append(b, n); }
 
 int main(int argc, char** argv) {
@@ -519,6 +643,106 @@ int main(int argc, char** argv) {
       s += '\n';
       ob.maybe();
     }
+  } else if (is_bam_name(o.out)) {
+    // ---- BAM + BAI (same record content as the SAM branch below, binary form)
+    ob.close();
+    Bgzf bz;
+    if (!bz.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
+    std::vector<char> hit(info.num_entries + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
+    bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
+    std::vector<int> refid(info.num_entries + 1, -1);
+    std::string text = "@HD\tVN:1.4\tSO:coordinate", refs;
+    uint32_t nref = 0;
+    for (uint32_t e = 1; e <= info.num_entries; ++e)
+      if (all || hit[e]) {
+        text += "\n@SQ\tAS:"; text += info.dataset_name; text += "\tSN:"; text += ents[e].name; text += "\tLN:";
+        append_uint(text, ents[e].seq_len);
+        refid[e] = (int)nref++;
+        uint32_t ln = (uint32_t)strlen(ents[e].name) + 1, sl = ents[e].seq_len;
+        refs.append((const char*)&ln, 4); refs.append(ents[e].name, ln); refs.append((const char*)&sl, 4);
+      }
+    text += "\n@PG\tID:biokanga\tVN:4.4.2\n";
+    std::string hdr = "BAM\1";
+    uint32_t lt = (uint32_t)text.size();
+    hdr.append((const char*)&lt, 4); hdr += text; hdr.append((const char*)&nref, 4); hdr += refs;
+    bool ok = bz.write(hdr.data(), hdr.size());
+    BaiBuilder bai;
+    bai.out = "BAI\1";
+    bai.put32(nref);
+    int cur_ref = -1;  // reference whose index block is being accumulated
+    uint32_t n_acc = (uint32_t)nar[BKX_NAR_ACCEPTED], seen_acc = 0;
+    std::string rec;
+    for (uint32_t k = 0; k < n && ok; ++k) {
+      uint32_t i = order[k];
+      const bkx_read_result& r = res[i];
+      bool acc = r.nar == BKX_NAR_ACCEPTED;
+      if (!acc && o.fmt != 6) continue;
+      int flags = 0, tlen = 0;
+      long pnext = -1;
+      if (!o.pe_mode) flags = acc ? (r.strand == '+' ? 0 : 0x10) : 0x04;
+      else {
+        bool pe2 = i & 1;
+        const bkx_read_result& m = res[pe2 ? i - 1 : i + 1];
+        flags = 0x01 | 0x02 | (pe2 ? 0x80 : 0x40);
+        if (acc) flags |= r.strand == '+' ? 0 : 0x10; else flags |= 0x04;
+        bool both = (r.flags & BKX_FLG_PE_ALIGNED) && (m.flags & BKX_FLG_PE_ALIGNED) && m.nar == BKX_NAR_ACCEPTED;
+        if (both) {
+          flags |= m.strand == '+' ? 0 : 0x20;
+          if (acc) {
+            long se = r.match_loci, pes = m.match_loci;
+            tlen = se <= pes ? (int)(pes - se) + m.match_len : (int)(se - pes) + r.match_len;
+            pnext = m.match_loci;
+          }
+        } else flags |= 0x08;
+      }
+      const int L = R.len(i);
+      const uint8_t* b = R.bases.data() + R.offs[i];
+      const char* qn = R.name(i);
+      uint32_t lname = (uint32_t)strlen(qn) + 1;
+      int32_t rid = acc ? refid[r.chrom_id] : -1, pos = acc ? (int32_t)r.match_loci : -1;
+      uint32_t bin = acc ? (uint32_t)bai_reg2bin(pos, pos + L) : 0;
+      uint32_t bmn = bin << 16 | 255u << 8 | lname, fnc = (uint32_t)flags << 16 | 1u;
+      int32_t nrid = (acc && pnext >= 0) ? rid : -1, npos = acc ? (int32_t)pnext : -1, tl = acc ? tlen : 0, lseq = L;
+      uint32_t cigar = (uint32_t)L << 4;
+      rec.assign(4, '\0');
+      auto p32 = [&](const void* v) { rec.append((const char*)v, 4); };
+      p32(&rid); p32(&pos); p32(&bmn); p32(&fnc); p32(&lseq); p32(&nrid); p32(&npos); p32(&tl);
+      rec.append(qn, lname);
+      p32(&cigar);
+      bool rc = acc && r.strand != '+';
+      for (int q = 0; q < L; q += 2) {
+        auto nib = [&](int idx) -> unsigned {
+          if (idx >= L) return 0u;
+          uint8_t c = b[rc ? L - 1 - idx : idx] & 7;
+          if (c < 4) { if (rc) c = 3 - c; return 1u << c; }
+          return 15u;
+        };
+        rec += (char)(nib(q) << 4 | nib(q + 1));
+      }
+      int sumq = 0;
+      for (int q = 0; q < L; ++q) sumq += (b[q] >> 4) & 0x0f;
+      if (sumq == 0) rec.append((size_t)L, (char)0xff);
+      else for (int q = 0; q < L; ++q) rec += (char)(33 + (((b[rc ? L - 1 - q : q] >> 4) & 0x0f) * 40) / 15);
+      if (!acc) { rec += "YUZ"; rec += kNarCode[r.nar]; rec += '\0'; }
+      uint32_t bsz = (uint32_t)rec.size() - 4;
+      memcpy(&rec[0], &bsz, 4);
+      uint64_t sva = 0;
+      if (acc) {
+        while (cur_ref < rid) { if (cur_ref >= 0) bai.end_ref(); ++cur_ref; }
+        sva = bz.tell();
+      }
+      ok = bz.write(rec.data(), rec.size());
+      if (acc) {
+        if (++seen_acc == n_acc) ok = ok && bz.flush();  // bLastAligned: close the block behind the last aligned read
+        bai.add(sva, (uint32_t)pos, bz.tell(), (uint32_t)(pos + L - 1));
+      }
+    }
+    bai.end_ref();  // Close(): the reference in progress (an empty block when nothing aligned)
+    ok = ok && bz.close();
+    FILE* fb = fopen((o.out + ".bai").c_str(), "wb");
+    if (fb) { fwrite(bai.out.data(), 1, bai.out.size(), fb); fclose(fb); } else ok = false;
+    if (!ok) { diag("Fatal: write to '%s' failed", o.out.c_str()); return 1; }
   } else {
     // SAM header: @HD, @SQ for every chromosome (or only those hit if more than -4 threshold), @PG
     std::vector<char> hit(info.num_entries + 1, 0);

@@ -99,3 +99,30 @@ def test_cli_output_formats_match_reference(tag, golden_dir, tmp_path):
     head = [x for x in ref if x.startswith("@") or x.startswith("track")]
     assert [x for x in ours if x.startswith("@") or x.startswith("track")] == head
     assert sorted(ours) == sorted(ref)
+
+
+def _bgzf_blocks(raw):
+    import struct
+    o, out = 0, []
+    while o < len(raw):
+        assert raw[o:o + 4] == b"\x1f\x8b\x08\x04"
+        bsize = struct.unpack_from("<H", raw, o + 16)[0] + 1
+        out.append((bsize, struct.unpack_from("<I", raw, o + bsize - 4)[0]))
+        o += bsize
+    return out
+
+
+@pytest.mark.parametrize("tag,args,out", [("bam5", ["-s3", "-M5"], "out5.bam"), ("bam6", ["-s3", "-M6", "-g0"], "out6.bam"),
+                                          ("bamQ2", ["-s3", "-M6", "-Q2"], "out62.bam")])
+def test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path):
+    """BAM (BGZF) + BAI written for an output name ending in .bam: byte-identical to the reference's files
+    (the read set has no two reads at the same locus, so sort ties cannot reorder records)."""
+    fdir = os.path.join(gu.GOLD, "formats")
+    sfx = gu.sfx_path("tiny", golden_dir)
+    subprocess.run([CLI, "align", "-I", sfx, "-i", os.path.join(fdir, "qu.fq.gz"), "-o", str(tmp_path / out)] + args, check=True,
+                   stdout=subprocess.DEVNULL)
+    ours, ref = open(tmp_path / out, "rb").read(), open(os.path.join(fdir, out), "rb").read()
+    assert gzip.decompress(ours) == gzip.decompress(ref)
+    assert _bgzf_blocks(ours) == _bgzf_blocks(ref)
+    assert ours == ref
+    assert open(str(tmp_path / out) + ".bai", "rb").read() == open(os.path.join(fdir, out + ".bai"), "rb").read()
