@@ -1,7 +1,7 @@
 // bkx-align -- host side of the drop-in for `biokanga align`.
 //
 // Same option letters as the reference front-end (biokanga/kanga.cpp:194-294), same on-disk .sfx index,
-// same CSV (-M0) / SAM (-M5, -M6) records and the same alignment-summary log block
+// same CSV / BED / SAM / BAM records and the same alignment-summary log block
 // (biokanga/Aligner.cpp:486-535, 3000-3008, 3726-3769).  The search itself goes through the C ABI of
 // libbkx.so (include/bkx.h); this file holds what the reference keeps in CAligner around that call:
 //   read ingest       CAligner::LoadRawReads / AddEntry   Aligner.cpp:10724-11427, 10572-10677
@@ -14,7 +14,8 @@
 // Written from the behaviour of those functions; no reference code is reused.  Options of the
 // reference that select paths outside SURVEY section 8 (-r/-R multi-loci modes, -c chimeric, -a/-A indel and
 // splice, -p SNP calling, -k PCR dedup, -x flank trimming, -Z/-z filters, -5 constraints, -H contaminants,
-// -b/-C bisulfite/SOLiD, BAM output) are recognised and rejected with a clear message.
+// -b/-C bisulfite/SOLiD) are recognised and rejected with a clear message.  Output formats: CSV -M0..3, BED -M4,
+// SAM -M5/-M6 (gzip when the name ends in .gz), BAM + BAI when the name ends in .bam (kanga.cpp:849-857).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
