@@ -309,6 +309,70 @@ def run_bkx(args):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """BASELINE.json configs[4]: substitutions 0..8 x read length 50..300 on the configs[1] genome.  One table row per
+    (L, -s): device-resident reads/s, class histogram, algorithmic-bytes roofline and a parity check of a sample of
+    the records against the CPU oracle.  Writes gpurun_out/sweep.json; prints one summary JSON line."""
+    import torch
+    from biokanga_b200 import abi
+    from biokanga_b200 import lib as bkx
+    from biokanga_b200 import workload as wl
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    lens = wl.chrom_layout(int(args.genome_mbp * 1e6))
+    d_seq, ents = wl.make_genome(lens, seed=args.seed, device=dev)
+    n = int(d_seq.numel())
+    d_sa = torch.empty(n, dtype=torch.int32, device=dev)
+    bkx.build_suffix_array_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 0)
+    torch.cuda.synchronize()
+    idx = bkx.Index.from_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 4, ents, name="sweep", device=0, prefix_k=args.prefix_k)
+    oidx = po.OracleIndex(seq=d_seq.cpu().numpy(), sa=d_sa.cpu().numpy().view(np.uint32), el_size=4, entries=ents)
+    del d_sa
+    torch.cuda.empty_cache()
+    peak, _ = measured_peak()
+    nreads = args.sweep_reads
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    rows = []
+    all_ok = True
+    for L in (50, 75, 100, 150, 200, 250, 300):
+        for s_ in range(0, 9):
+            for mmd in ((1, 2) if s_ in (3, 8) else (1,)):
+                max_tot = 0 if s_ == 0 else max(1, (L * s_ + 50) // 100)
+                d_bases, d_offs = wl.sim_reads(d_seq, ents, nreads, L, seed=args.seed + 7 * L + s_, subs=tuple(range(0, max_tot + 2)),
+                                               device=dev)
+                p = idx.default_params(0, max_subs=s_, min_edit_dist=mmd)
+                d_out = torch.empty(nreads * 32, dtype=torch.uint8, device=dev)
+                ms = []
+                for rep in range(3):
+                    idx.align_device(p, d_bases.data_ptr(), d_offs.data_ptr(), nreads, L, d_out.data_ptr(), None, tstream.cuda_stream)
+                    torch.cuda.synchronize()
+                    ms.append(idx.last_kernel_ms())
+                res = d_out.cpu().numpy().view(abi.RESULT_DTYPE)
+                m = min(args.sweep_check, nreads)
+                bases = d_bases[:m * L].cpu().numpy()
+                offs = np.arange(m + 1, dtype=np.uint64) * L
+                exp, _ = oidx.align(oidx.default_params(0, max_subs=s_, min_edit_dist=mmd), bases, offs, nthreads=os.cpu_count() or 1)
+                ok = all(np.array_equal(res[f][:m], exp[f]) for f in abi.RESULT_DTYPE.names)
+                all_ok &= ok
+                nar = np.bincount(res["nar"], minlength=abi.NAR_COUNT)
+                best = min(ms[1:])
+                ab = wl.algorithmic_bytes(res, n, 4, L)
+                rows.append({"L": L, "s": s_, "e": mmd, "max_tot_mm": max_tot, "reads": nreads, "ms": best,
+                             "reads_per_s": nreads / (best / 1e3), "roofline_frac": ab / (best / 1e3) / 1e9 / peak,
+                             "bytes_per_read": ab / nreads, "parity_sample": m, "parity_ok": bool(ok),
+                             "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]}})
+                log("[sweep] L=%d -s%d -e%d: %.1f M reads/s, frac %.2f, parity %s, %s" % (
+                    L, s_, mmd, rows[-1]["reads_per_s"] / 1e6, rows[-1]["roofline_frac"], ok, rows[-1]["classes"]))
+                del d_bases, d_offs, d_out
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)
+    print(json.dumps({"sweep_rows": len(rows), "all_parity_ok": bool(all_ok),
+                      "min_reads_per_s": min(r["reads_per_s"] for r in rows), "max_reads_per_s": max(r["reads_per_s"] for r in rows)}))
+
+
 def cpu_baseline_port(args, host_seq, host_sa, ents, h_bases, gpu_res):
     """The CPU restatement on a bounded sample of the same reads, all host cores; also re-checks parity."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -464,6 +528,9 @@ def main():
     ap.add_argument("--pe-mode", type=int, default=1, help="-U mode for --workload pe (1 = recover orphans)")
     ap.add_argument("--pe-min", type=int, default=200)
     ap.add_argument("--pe-max", type=int, default=1000)
+    ap.add_argument("--sweep", action="store_true", help="configs[4]: substitutions 0..8 x read length 50..300 table")
+    ap.add_argument("--sweep-reads", type=int, default=2_000_000)
+    ap.add_argument("--sweep-check", type=int, default=20000)
     ap.add_argument("--kernel-times", action="store_true", help="read the kernel's own events after every step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "bkx":
@@ -471,7 +538,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus != world and world == 1 and args.gpus > 1:
         raise SystemExit("launch multi-GPU runs with torch.distributed.run --nproc-per-node %d" % args.gpus)
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_bkx(args)
