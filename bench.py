@@ -337,8 +337,10 @@ def run_sweep(args):
     torch.cuda.set_stream(tstream)
     rows = []
     all_ok = True
-    for L in (50, 75, 100, 150, 200, 250, 300):
-        for s_ in range(0, 9):
+    lens_ = [int(v) for v in args.sweep_lens.split(",")]
+    subs_ = [int(v) for v in args.sweep_subs.split(",")]
+    for L in lens_:
+        for s_ in subs_:
             for mmd in ((1, 2) if s_ in (3, 8) else (1,)):
                 max_tot = 0 if s_ == 0 else max(1, (L * s_ + 50) // 100)
                 d_bases, d_offs = wl.sim_reads(d_seq, ents, nreads, L, seed=args.seed + 7 * L + s_, subs=tuple(range(0, max_tot + 2)),
@@ -531,6 +533,8 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="configs[4]: substitutions 0..8 x read length 50..300 table")
     ap.add_argument("--sweep-reads", type=int, default=2_000_000)
     ap.add_argument("--sweep-check", type=int, default=20000)
+    ap.add_argument("--sweep-lens", default="50,75,100,150,200,250,300")
+    ap.add_argument("--sweep-subs", default="0,1,2,3,4,5,6,7,8")
     ap.add_argument("--kernel-times", action="store_true", help="read the kernel's own events after every step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "bkx":

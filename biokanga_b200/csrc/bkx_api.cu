@@ -73,6 +73,9 @@ struct bkx_index {
   uint64_t max_len_prepared = 0;
   uint32_t* d_pe_list = nullptr;
   size_t pe_list_cap = 0;
+  uint64_t* fast_hash = nullptr;   // lane-private overflow sets of the fast kernel (fast_grid x 256 lanes x 1024 slots)
+  size_t fast_hash_lanes = 0;
+  uint32_t fast_epoch = 1;
   HashPool hp{};
   int grid = 0;
   int grid_W = 0;
@@ -278,6 +281,7 @@ extern "C" void bkx_close_index(bkx_index* x) {
   if (x->d_pe_stats) cudaFree(x->d_pe_stats);
   if (x->d_len_dist) cudaFree(x->d_len_dist);
   if (x->d_pe_list) cudaFree(x->d_pe_list);
+  if (x->fast_hash) cudaFree(x->fast_hash);
   delete x;
 }
 
@@ -624,6 +628,15 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
       x->fast_grid = nb * sms;
       x->fast_W = Wf;
     }
+    size_t lanes = (size_t)x->fast_grid * kFastThreads;
+    if (lanes > x->fast_hash_lanes) {
+      CU(cudaDeviceSynchronize());
+      if (x->fast_hash) { cudaFree(x->fast_hash); x->fast_hash = nullptr; }
+      CU(cudaMalloc((void**)&x->fast_hash, lanes * kFastHashSlots * 8));
+      CU(cudaMemset(x->fast_hash, 0, lanes * kFastHashSlots * 8));
+      x->fast_hash_lanes = lanes;
+      x->fast_epoch = 1;
+    }
   }
   *W_out = x->grid_W;
   return BKX_OK;
@@ -639,8 +652,35 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     x->launches += 1;
     return BKX_OK;
   }
-  CU(launch_align_fast(x->d, k, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_grid, st));
+  // every launch gets its own 2^20-wide epoch range for the lane hash sets; wipe them when the 32-bit tag wraps
+  if (x->fast_epoch > 0xfff00000u) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(x->fast_hash, 0, x->fast_hash_lanes * kFastHashSlots * 8));
+    x->fast_epoch = 1;
+  }
+  uint32_t epoch_base = x->fast_epoch;
+  x->fast_epoch += 1u << 20;
+  static const bool trace = getenv("BKX_TRACE") != nullptr;  // diagnostic: split of the two kernels, serialising
+  cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;
+  if (trace) {
+    cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+    cudaEventRecord(t0, st);
+  }
+  CU(launch_align_fast(x->d, k, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash, epoch_base,
+                       x->fast_grid, st));
+  if (trace) cudaEventRecord(t1, st);
   CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, d_hard, cur + 2, x->grid, st));
+  if (trace) {
+    cudaEventRecord(t2, st);
+    cudaStreamSynchronize(st);
+    unsigned int nh = 0;
+    cudaMemcpy(&nh, cur + 2, 4, cudaMemcpyDeviceToHost);
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, t0, t1);
+    cudaEventElapsedTime(&b, t1, t2);
+    fprintf(stderr, "[bkx trace] reads %u: fast %.3f ms, deferred %u (%.2f%%), general %.3f ms\n", n, a, nh, 100.0 * nh / n, b);
+    cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+  }
   x->launches += 2;
   return BKX_OK;
 }

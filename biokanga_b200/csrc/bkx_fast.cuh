@@ -12,7 +12,8 @@
 //   * reads longer than kFastMaxLen, reads holding an N that still pass the N filter;
 //   * a core whose SA interval holds more than kFastMaxCnt suffixes (repeats: the 100th-candidate
 //     probe / MaxIter caps can never trigger below that);
-//   * more than kFastSeen distinct candidate loci in one strand of one phase;
+//   * more than kFastHashCap distinct candidate loci in one strand of one phase (the first kFastSeen live in
+//     shared memory, the rest in a lane-private epoch-tagged hash set in HBM);
 //   * a genome window that touches an N or a chromosome end (symbol-wise compare needed).
 // So the result of a read never depends on which kernel produced it.
 #pragma once
@@ -21,19 +22,22 @@
 namespace bkx {
 
 constexpr int kFastMaxLen = 320;   // bases; 10 words + pad per strand
-constexpr int kFastMaxCnt = 12;    // SA interval size handled in the fast path
-constexpr int kFastSeen = 24;      // "already processed" keys per lane
+constexpr int kFastMaxCnt = 64;    // SA interval size handled in the fast path (must stay below 100, see above)
+constexpr int kFastSeen = 24;      // "already processed" keys per lane kept in shared memory
+constexpr int kFastHashSlots = 1024;  // per-lane overflow set in HBM: (epoch << 32 | key) slots, open addressing
+constexpr int kFastHashCap = 512;     // keys per strand/phase before the read is deferred
 constexpr int kFastWarps = 8;      // warps per block
 constexpr int kFastThreads = kFastWarps * 32;
 
 __host__ __device__ inline size_t fast_smem_bytes(int W) {
-  // per warp: 2 strands x W words x 32 lanes x 8 B (lane-interleaved) + kFastSeen x 32 lanes x 4 B
-  return (size_t)kFastWarps * ((size_t)2 * W * 32 * 8 + (size_t)kFastSeen * 32 * 4);
+  // per warp: 2 strands x W words x 32 lanes x 8 B (lane-interleaved) + (kFastSeen keys + the hash-set epoch) x 32
+  // lanes x 4 B
+  return (size_t)kFastWarps * ((size_t)2 * W * 32 * 8 + (size_t)(kFastSeen + 1) * 32 * 4);
 }
 
 struct FastLane {
   const uint64_t* w2[2];  // this lane's packed read: word w of strand s at w2[s][w * 32]
-  uint32_t* seen;         // this lane's seen keys: key i at seen[i * 32]
+  uint32_t* seen;         // this lane's seen keys: key i at seen[i * 32]; seen[kFastSeen * 32] = hash-set epoch
   int L;
 };
 

@@ -398,10 +398,33 @@ __device__ __forceinline__ void stats_flush(const BlockStats& bs, bkx_align_stat
   }
 }
 
+// Lane-private overflow set of the fast kernel: kFastHashSlots (epoch << 32 | key) slots per lane in HBM, open
+// addressing, emptied by moving to a fresh epoch.  Kept out of line: only reads with many candidate loci get here.
+__device__ __forceinline__ uint64_t* fh_table(uint64_t* lane_hash) {
+  return lane_hash + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kFastHashSlots;
+}
+__device__ __noinline__ bool fh_test_insert(uint64_t* lane_hash, uint32_t epoch, uint32_t key) {
+  uint64_t* t = fh_table(lane_hash);
+  const uint64_t want = ((uint64_t)epoch << 32) | key;
+  uint32_t h = (key * 2654435761u) & (kFastHashSlots - 1);
+  for (;; h = (h + 1) & (kFastHashSlots - 1)) {
+    uint64_t v = t[h];
+    if (v == want) return true;
+    if ((uint32_t)(v >> 32) != epoch) break;
+  }
+  t[h] = want;
+  return false;
+}
+__device__ __noinline__ void fh_spill(uint64_t* lane_hash, uint32_t epoch, const uint32_t* seen, int n, uint32_t key) {
+  for (int i = 0; i < n; ++i) fh_test_insert(lane_hash, epoch, seen[i * 32]);
+  fh_test_insert(lane_hash, epoch, key);
+}
+
 __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
-    uint32_t* __restrict__ hard_ids, unsigned int* __restrict__ n_hard) {
+    uint32_t* __restrict__ hard_ids, unsigned int* __restrict__ n_hard, uint64_t* __restrict__ lane_hash,
+    uint32_t epoch_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockStats bs;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -409,13 +432,14 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
   for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
   __syncthreads();
 
-  uint64_t* region = (uint64_t*)smem_raw + (size_t)wib * ((size_t)2 * W * 32 + (size_t)kFastSeen * 16);
+  uint64_t* region = (uint64_t*)smem_raw + (size_t)wib * ((size_t)2 * W * 32 + (size_t)(kFastSeen + 1) * 16);
   uint64_t* wr0 = region + lane;                   // this lane's forward words (stride 32)
   uint64_t* wr1 = region + (size_t)W * 32 + lane;  // reverse-complement words
   FastLane f;
   f.w2[0] = wr0;
   f.w2[1] = wr1;
   f.seen = (uint32_t*)(region + (size_t)2 * W * 32) + lane;
+  f.seen[kFastSeen * 32] = epoch_base;  // bumped every time this lane spills a strand's keys into its hash set
   f.L = 0;
   const int k = I.k;
   const int s_first = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
@@ -634,7 +658,19 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
         bhi = pt_get(I, (p + 1) << sh);
       }
       uint64_t first = 0, cnt = 0;
-      if (blo < bhi) {
+      bool located = false;
+      if (blo < bhi && CL <= k) {
+        // core no longer than the table key: the bucket IS the interval, except for suffixes holding an N/EOS inside
+        // the core span, which sort at the bucket's end -- so if the last element matches, every element does
+        uint64_t g = sa_get(I, bhi - 1);
+        if (!span_has_exc(I, g, (uint32_t)CL) && fl_cmp(I, f, s, cofs, CL, g) == 0) {
+          first = blo;
+          cnt = bhi - blo;
+          located = true;
+          if (cnt > (uint64_t)kFastMaxCnt) dfr = true;
+        }
+      }
+      if (blo < bhi && !located) {
         uint64_t l = blo, h = bhi;
         bool h_equal = false;
         while (l < h) {
@@ -666,11 +702,20 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
         int ent = find_entry(I, p);
         if (ent < 0 || (p + (uint64_t)L - 1) > __ldg(I.ent_end + ent)) continue;
         uint32_t kk = (uint32_t)(1u + (uint32_t)loci - (uint32_t)cofs);
-        bool dup = false;
-        for (int i = 0; i < seen_n; ++i) dup |= (f.seen[i * 32] == kk);
-        if (dup) continue;
-        if (seen_n >= kFastSeen) { dfr = true; break; }
-        f.seen[seen_n * 32] = kk;
+        if (seen_n <= kFastSeen) {  // beyond that the strand's keys live in the lane's hash set
+          bool dup = false;
+          for (int i = 0; i < seen_n; ++i) dup |= (f.seen[i * 32] == kk);
+          if (dup) continue;
+          if (seen_n < kFastSeen) {
+            f.seen[seen_n * 32] = kk;
+          } else {  // spill this strand's keys into the lane's hash set in HBM
+            const uint32_t epoch = ++f.seen[kFastSeen * 32];
+            fh_spill(lane_hash, epoch, f.seen, seen_n, kk);
+          }
+        } else {
+          if (fh_test_insert(lane_hash, f.seen[kFastSeen * 32], kk)) continue;
+          if (seen_n >= kFastHashCap) { dfr = true; break; }
+        }
         ++seen_n;
         ++cands;
         if (span_has_exc(I, p, (uint32_t)L)) { dfr = true; break; }
@@ -739,7 +784,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
 
 cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                               uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
-                              unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, int grid, cudaStream_t st) {
+                              unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, uint64_t* lane_hash,
+                              uint32_t epoch_base, int grid, cudaStream_t st) {
   size_t smem = fast_smem_bytes(W);
   cudaError_t e = ensure_smem(align_fast_kernel, smem, g_smem_fast);
   if (e != cudaSuccess) return e;
@@ -747,7 +793,8 @@ cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(n_hard, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
-  align_fast_kernel<<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids, n_hard);
+  align_fast_kernel<<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids, n_hard,
+                                                      lane_hash, epoch_base);
   return cudaGetLastError();
 }
 

@@ -24,7 +24,8 @@ cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bas
 int fast_blocks_per_sm(int W);
 cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                               uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
-                              unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, int grid, cudaStream_t st);
+                              unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, uint64_t* lane_hash,
+                              uint32_t epoch_base, int grid, cudaStream_t st);
 cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,
                         uint32_t* len_dist, uint32_t* orphan_list, unsigned int* n_orphans, cudaStream_t st);
 cudaError_t launch_rescue(const DevIndex& I, const KParams& P, const bkx_pe_params& pe, bkx_read_result* res,
