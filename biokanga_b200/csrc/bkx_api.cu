@@ -121,9 +121,17 @@ static int choose_k(uint64_t n, int requested, size_t free_bytes, bool wide) {
   return k;
 }
 
-// Build every derived structure from a device-resident 1-byte/base sequence and raw SA elements.
-static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const void* d_sa_raw, uint32_t el,
-                        bool sa_owned_u32, const bkx_entry* entries, uint32_t n_ent, const char* name, int prefix_k) {
+// Where the suffix array comes from: raw elements as the .sfx stores them (copied / split into planes here), or
+// planes that are already in place on the device (used as they are; the caller settles who frees them).
+struct SaSrc {
+  const void* raw = nullptr;
+  const uint32_t* lo = nullptr;
+  const uint8_t* hi = nullptr;
+};
+
+// Build every derived structure from a device-resident 1-byte/base sequence and the suffix array.
+static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const SaSrc& sa, uint32_t el,
+                        const bkx_entry* entries, uint32_t n_ent, const char* name, int prefix_k) {
   if (el != 4 && el != 5) return fail(BKX_ERR_FORMAT, "unsupported suffix element size %u", el);
   if (n < 2 || n_ent == 0) return fail(BKX_ERR_FORMAT, "empty index");
   x->info.concat_len = n;
@@ -158,22 +166,24 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const vo
   x->d.g2 = g2; x->d.gx = gx; x->d.gxc = gxc; x->d.n = n;
   REG_ARR(x, g2, g2w * 8); REG_ARR(x, gx, gxw * 8); REG_ARR(x, gxc, gcw * 4);
 
-  if (el == 4) {
-    if (sa_owned_u32) {
-      x->d.sa_lo = (const uint32_t*)d_sa_raw;
-    } else {
-      uint32_t* lo;
-      if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
-      CU(cudaMemcpyAsync(lo, d_sa_raw, n * 4, cudaMemcpyDeviceToDevice, st));
-      x->d.sa_lo = lo;
-    }
+  if (sa.lo) {
+    if (el == 5 && !sa.hi) return fail(BKX_ERR_PARAM, "5-byte suffix elements need the high plane");
+    x->d.sa_lo = sa.lo;
+    x->d.sa_hi = el == 5 ? sa.hi : nullptr;
+    REG_ARR(x, sa_lo, n * 4);
+    if (el == 5) REG_ARR(x, sa_hi, n);
+  } else if (el == 4) {
+    uint32_t* lo;
+    if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
+    CU(cudaMemcpyAsync(lo, sa.raw, n * 4, cudaMemcpyDeviceToDevice, st));
+    x->d.sa_lo = lo;
     x->d.sa_hi = nullptr;
     REG_ARR(x, sa_lo, n * 4);
   } else {
     uint32_t* lo; uint8_t* hi;
     if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
     if ((rc = dev_alloc(x, &hi, n, false)) < 0) return rc;
-    CU(launch_split_sa5((const uint8_t*)d_sa_raw, n, lo, hi, st));
+    CU(launch_split_sa5((const uint8_t*)sa.raw, n, lo, hi, st));
     x->launches += 1;
     x->d.sa_lo = lo; x->d.sa_hi = hi;
     REG_ARR(x, sa_lo, n * 4); REG_ARR(x, sa_hi, n);
@@ -293,7 +303,28 @@ extern "C" int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, con
   int rc = new_index(device, &x);
   if (rc < 0) return rc;
   x->info.version = 5;
-  rc = finish_index(x, d_seq, concat_len, d_sa, el, false, entries, n_ent, name, prefix_k);
+  SaSrc src;
+  src.raw = d_sa;
+  rc = finish_index(x, d_seq, concat_len, src, el, entries, n_ent, name, prefix_k);
+  if (rc < 0) { bkx_close_index(x); return rc; }
+  *out = x;
+  return BKX_OK;
+}
+
+extern "C" int bkx_open_index_planes(const uint8_t* d_seq, uint64_t concat_len, const uint32_t* d_sa_lo,
+                                     const uint8_t* d_sa_hi, const bkx_entry* entries, uint32_t n_ent, const char* name,
+                                     int device, int prefix_k, bkx_index** out) {
+  if (!d_seq || !d_sa_lo || !entries || !out) return fail(BKX_ERR_PARAM, "null argument");
+  if (!d_sa_hi && concat_len >= 4000000000ull)
+    return fail(BKX_ERR_PARAM, "%llu symbols use 5-byte suffix elements: the high plane is required", (unsigned long long)concat_len);
+  bkx_index* x = nullptr;
+  int rc = new_index(device, &x);
+  if (rc < 0) return rc;
+  x->info.version = 5;
+  SaSrc src;  // borrowed: not entered in x->owned, so bkx_close_index leaves the planes alone
+  src.lo = d_sa_lo;
+  src.hi = d_sa_hi;
+  rc = finish_index(x, d_seq, concat_len, src, d_sa_hi ? 5 : 4, entries, n_ent, name, prefix_k);
   if (rc < 0) { bkx_close_index(x); return rc; }
   *out = x;
   return BKX_OK;
@@ -307,6 +338,7 @@ extern "C" int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const
   int rc = new_index(device, &x);
   if (rc < 0) return rc;
   x->info.version = 5;
+  if (el != 4 && el != 5) { bkx_close_index(x); return fail(BKX_ERR_FORMAT, "unsupported suffix element size %u", el); }
   uint8_t* d_seq = nullptr;
   void* d_sa = nullptr;
   cudaError_t e = cudaMalloc((void**)&d_seq, concat_len);
@@ -318,8 +350,10 @@ extern "C" int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const
     cudaFree(d_seq); cudaFree(d_sa); bkx_close_index(x);
     return fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e));
   }
-  if (keep_sa) { x->owned.push_back(d_sa); x->info.device_bytes += concat_len * 4; }
-  rc = finish_index(x, d_seq, concat_len, d_sa, el, keep_sa, entries, n_ent, name, prefix_k);
+  SaSrc src;
+  if (keep_sa) { x->owned.push_back(d_sa); x->info.device_bytes += concat_len * 4; src.lo = (const uint32_t*)d_sa; }
+  else src.raw = d_sa;
+  rc = finish_index(x, d_seq, concat_len, src, el, entries, n_ent, name, prefix_k);
   cudaFree(d_seq);
   if (!keep_sa) cudaFree(d_sa);
   if (rc < 0) { bkx_close_index(x); return rc; }
@@ -405,17 +439,23 @@ extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_in
   if (rc < 0) { close(fd); return rc; }
   x->info.version = version;
   x->info.attributes = attributes;
-  // stream the block to the GPU through two pinned staging buffers
+  // Stream the block to the GPU through two pinned staging buffers.  4-byte elements land in their final array;
+  // 5-byte elements pass through a small device staging buffer and are split into the two planes chunk by chunk,
+  // so an 84 GB index never needs more than its final footprint.
   uint8_t* d_seq = nullptr;
-  uint8_t* d_sa = nullptr;
-  const size_t chunk = (size_t)64 << 20;
+  uint32_t* d_lo = nullptr;
+  uint8_t* d_hi = nullptr;
+  uint8_t* d_stage[2] = {nullptr, nullptr};
+  const size_t chunk = (size_t)60 << 20;  // a multiple of 5
   uint8_t* pin[2] = {nullptr, nullptr};
-  cudaEvent_t ev[2];
+  cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaError_t e = cudaMalloc((void**)&d_seq, n);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_sa, n * el);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_lo, n * 4);
+  if (e == cudaSuccess && el == 5) e = cudaMalloc((void**)&d_hi, n);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaMallocHost((void**)&pin[i], chunk);
     if (e == cudaSuccess) e = cudaEventCreate(&ev[i]);
+    if (e == cudaSuccess && el == 5) e = cudaMalloc((void**)&d_stage[i], chunk);
   }
   bool io_ok = true;
   if (e == cudaSuccess) {
@@ -429,8 +469,16 @@ extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_in
       if (done < n && done + len > n) len = (size_t)(n - done);
       if (used[b]) e = cudaEventSynchronize(ev[b]);
       if (!pread_all(fd, pin[b], len, (off_t)(blk_ofs + 20 + done))) { io_ok = false; break; }
-      uint8_t* dst = done < n ? d_seq + done : d_sa + (done - n);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(dst, pin[b], len, cudaMemcpyHostToDevice, st);
+      if (done < n) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_seq + done, pin[b], len, cudaMemcpyHostToDevice, st);
+      } else if (el == 4) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)d_lo + (done - n), pin[b], len, cudaMemcpyHostToDevice, st);
+      } else {
+        uint64_t first = (done - n) / 5;  // chunks inside the array start on element boundaries (chunk % 5 == 0)
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stage[b], pin[b], len, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = launch_split_sa5(d_stage[b], len / 5, d_lo + first, d_hi + first, st);
+        x->launches += 1;
+      }
       if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
       used[b] = true;
       done += len;
@@ -439,17 +487,24 @@ extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_in
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
   close(fd);
-  for (int i = 0; i < 2; ++i) if (pin[i]) { cudaFreeHost(pin[i]); cudaEventDestroy(ev[i]); }
+  for (int i = 0; i < 2; ++i) {
+    if (pin[i]) cudaFreeHost(pin[i]);
+    if (ev[i]) cudaEventDestroy(ev[i]);
+    if (d_stage[i]) cudaFree(d_stage[i]);
+  }
   if (e != cudaSuccess || !io_ok) {
-    cudaFree(d_seq); cudaFree(d_sa); bkx_close_index(x);
+    cudaFree(d_seq); cudaFree(d_lo); cudaFree(d_hi); bkx_close_index(x);
     return e != cudaSuccess ? fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e))
                             : fail(BKX_ERR_FILE, "'%s': short read", path);
   }
-  bool keep_sa = (el == 4);
-  if (keep_sa) { x->owned.push_back(d_sa); x->info.device_bytes += n * 4; }
-  rc = finish_index(x, d_seq, n, d_sa, el, keep_sa, ents.data(), n_ent, dataset, prefix_k);
+  x->owned.push_back(d_lo);
+  x->info.device_bytes += n * 4;
+  if (d_hi) { x->owned.push_back(d_hi); x->info.device_bytes += n; }
+  SaSrc src;
+  src.lo = d_lo;
+  src.hi = d_hi;
+  rc = finish_index(x, d_seq, n, src, el, ents.data(), n_ent, dataset, prefix_k);
   cudaFree(d_seq);
-  if (!keep_sa) cudaFree(d_sa);
   if (rc < 0) { bkx_close_index(x); return rc; }
   *out = x;
   return BKX_OK;

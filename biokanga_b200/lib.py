@@ -23,7 +23,7 @@ EXPORTS = [
     "bkx_get_ident", "bkx_get_seq", "bkx_default_params", "bkx_align_reads", "bkx_align_reads_device",
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
-    "bkx_pair_reads_device",
+    "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes",
 ]
 
 
@@ -59,6 +59,8 @@ def lib():
     L.bkx_open_index.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_open_index_mem.argtypes = [vp, u64, vp, u32, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_open_index_dev.argtypes = [vp, u64, vp, u32, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.bkx_open_index_planes.argtypes = [vp, u64, vp, vp, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.bkx_build_suffix_array_planes.argtypes = [vp, u64, vp, vp, i32, u64]
     L.bkx_clone_index.argtypes = [vp, i32, C.POINTER(vp)]
     L.bkx_close_index.argtypes = [vp]
     L.bkx_close_index.restype = None
@@ -97,6 +99,11 @@ def check(rc):
 def build_suffix_array_device(d_seq_ptr, concat_len, d_sa_ptr, device=0):
     """GPU suffix-array construction (device pointers; u32 elements out)."""
     check(lib().bkx_build_suffix_array_device(d_seq_ptr, concat_len, d_sa_ptr, device))
+
+
+def build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr=None, device=0, max_batch=0):
+    """Bounded-memory builder for any size (the one for >= 4e9 symbols): u32 low plane + u8 high plane out."""
+    check(lib().bkx_build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, device, max_batch))
 
 
 def write_sfx(path, seq, sa, el_size, entries, name="bkx"):
@@ -138,6 +145,15 @@ class Index:
         h = C.c_void_p()
         check(lib().bkx_open_index_dev(d_seq_ptr, concat_len, d_sa_ptr, el_size, entries.ctypes.data, len(entries),
                                        name.encode(), device, prefix_k, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_planes(cls, d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, entries, name="bkx", device=0, prefix_k=0):
+        """Index over suffix-array planes already on the device; they are borrowed and must outlive the index."""
+        entries = np.ascontiguousarray(entries, dtype=abi.ENTRY_DTYPE)
+        h = C.c_void_p()
+        check(lib().bkx_open_index_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, entries.ctypes.data,
+                                          len(entries), name.encode(), device, prefix_k, C.byref(h)))
         return cls(h)
 
     def close(self):

@@ -172,6 +172,12 @@ int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const void* sa, 
 int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, const void* d_sa, uint32_t sfx_el_size,
                        const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
                        int prefix_k, bkx_index** out);
+/* Same, from a suffix array already split into the two device planes DevIndex reads (u32 low words and, for
+ * 5-byte elements, u8 high bytes; d_sa_hi may be NULL below 4e9 symbols).  The planes are BORROWED, not copied --
+ * at 14 G symbols they are 70 GB -- and must outlive the index; bkx_close_index leaves them alone. */
+int bkx_open_index_planes(const uint8_t* d_seq, uint64_t concat_len, const uint32_t* d_sa_lo, const uint8_t* d_sa_hi,
+                          const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
+                          int prefix_k, bkx_index** out);
 /* Replicate an open index onto another GPU by peer copies (multi-GPU read sharding). */
 int bkx_clone_index(const bkx_index* src, int device, bkx_index** out);
 void bkx_close_index(bkx_index* idx); /* CSfxArrayV3::Reset / Close */
@@ -223,6 +229,12 @@ int bkx_pair_reads_device(bkx_index* idx, const bkx_align_params* p, const bkx_p
  * 174-187).  d_seq: device, 1 byte/base incl. one EOS(7) after every entry; d_sa: device, concat_len
  * u32 elements out, sorted like the reference sorts (4-bit symbol order, through the terminators). */
 int bkx_build_suffix_array_device(const uint8_t* d_seq, uint64_t concat_len, uint32_t* d_sa, int device);
+/* Same order, any size up to 2^40 symbols, in bounded device memory (batches of suffixes sharing leading symbols,
+ * ties broken 21 symbols at a time straight from the sequence): the builder for genomes of >= 4e9 symbols, whose
+ * elements take 5 bytes (SfxArrayV2.cpp:33-44).  Output as planes: d_sa_lo[i] = low 32 bits, d_sa_hi[i] = bits 32-39
+ * (d_sa_hi may be NULL when concat_len <= 2^32).  max_batch = 0 sizes the batches from free device memory. */
+int bkx_build_suffix_array_planes(const uint8_t* d_seq, uint64_t concat_len, uint32_t* d_sa_lo, uint8_t* d_sa_hi,
+                                  int device, uint64_t max_batch);
 /* Write host-resident sequence + suffix array as a version-5 .sfx the reference's `biokanga align` loads. */
 int bkx_write_sfx(const char* path, const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t sfx_el_size,
                   const bkx_entry* entries, uint32_t num_entries, const char* dataset_name);

@@ -101,3 +101,52 @@ def test_sa_and_sfx_writer_against_fresh_reference_index(tmp_path):
     exp, _ = oidx.align(oidx.default_params(0, max_subs=3), bases, offs, nthreads=4)
     for f in ("nar", "strand", "chrom_id", "match_loci", "mismatches", "low_hit_instances"):
         assert np.array_equal(got[f], exp[f]), f
+
+
+def gpu_sa_planes(seq, max_batch, with_hi):
+    d_seq = torch.from_numpy(np.ascontiguousarray(seq)).cuda()
+    n = len(seq)
+    d_lo = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_hi = torch.full((n,), 0x5a, dtype=torch.uint8, device="cuda") if with_hi else None
+    bkx.build_suffix_array_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr() if with_hi else None, 0, max_batch)
+    torch.cuda.synchronize()
+    if with_hi:
+        assert int(d_hi.max()) == 0  # every position of a small genome has zero high bits, and all were written
+    return d_lo.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("case", ["tiny", "repeats"])
+def test_bounded_memory_builder_matches_golden_index(case, golden_dir):
+    """The batch-wise builder (the one for >= 4e9 symbols) on the golden genomes, forced into many small batches:
+    same array as `biokanga index` wrote."""
+    oi = po.OracleIndex(gu.sfx_path(case, golden_dir))
+    seq = np.array(oi.seq())
+    ref_sa = np.array(oi.sa_bytes()).view(np.uint32)
+    for max_batch, with_hi in ((0, False), (len(seq) // 13, True)):
+        check_against(seq, ref_sa, gpu_sa_planes(seq, max_batch, with_hi))
+
+
+def test_bounded_memory_builder_equals_doubling_builder_and_serves_an_index():
+    """30 Mbp genome with exact and diverged repeats: the two builders agree element for element; an index opened
+    over the planes (borrowed, 5-byte elements forced) aligns like one opened over the u32 array."""
+    from biokanga_b200 import workload as wl
+    lens = wl.chrom_layout(30_000_000, n_chrom=6)
+    d_seq, ents = wl.make_genome(lens, seed=21, device="cuda")
+    n = int(d_seq.numel())
+    d_sa = torch.empty(n, dtype=torch.int32, device="cuda")
+    bkx.build_suffix_array_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 0)
+    d_lo = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_hi = torch.empty(n, dtype=torch.uint8, device="cuda")
+    bkx.build_suffix_array_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr(), 0, 4_000_000)
+    torch.cuda.synchronize()
+    assert torch.equal(d_sa, d_lo) and int(d_hi.max()) == 0
+    g4 = bkx.Index.from_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 4, ents, name="u32")
+    g5 = bkx.Index.from_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr(), ents, name="planes")
+    assert g5.info.sfx_el_size == 5 and g4.info.sfx_el_size == 4
+    d_bases, d_offs = wl.sim_reads(d_seq, ents, 50_000, 120, seed=5, subs=(0, 1, 2, 3, 5, 7))
+    bases, offs = d_bases.cpu().numpy(), d_offs.cpu().numpy().astype(np.uint64)
+    r4, s4 = g4.align(g4.default_params(0, max_subs=5), bases, offs)
+    r5, s5 = g5.align(g5.default_params(0, max_subs=5), bases, offs)
+    assert r4.tobytes() == r5.tobytes() and s4.as_dict() == s5.as_dict()
+    g5.close()
+    assert int(d_lo[0]) == int(d_sa[0])  # the borrowed planes survive the index
