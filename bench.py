@@ -375,6 +375,174 @@ def run_sweep(args):
                       "min_reads_per_s": min(r["reads_per_s"] for r in rows), "max_reads_per_s": max(r["reads_per_s"] for r in rows)}))
 
 
+def run_hexaploid(args):
+    """BASELINE.json configs[3]: wheat-scale hexaploid (3 sub-genomes x 7 chromosomes, >= 4e9 symbols => 5-byte suffix
+    elements), 150 bp SE reads, one GPU.  The suffix array is built on the device in planes (the reference's own
+    `biokanga index` needs ~6 bytes/symbol of host RAM and hours at this size); everything after that is the same
+    C-ABI path as configs[1].  Prints one JSON line; writes gpurun_out/hexaploid.json."""
+    import torch
+    from biokanga_b200 import abi
+    from biokanga_b200 import lib as bkx
+    from biokanga_b200 import workload as wl
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the bkx path has no CPU fallback")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    chrom_len = int(args.genome_mbp * 1e6) // 21
+    t0 = time.time()
+    d_seq, ents = wl.make_hexaploid(chrom_len, seed=args.seed, device=dev)
+    n = int(d_seq.numel())
+    torch.cuda.synchronize()
+    t1 = time.time()
+    five = n >= 4_000_000_000
+    d_lo = torch.empty(n, dtype=torch.int32, device=dev)
+    d_hi = torch.empty(n, dtype=torch.uint8, device=dev) if five else None
+    torch.cuda.empty_cache()
+    bkx.build_suffix_array_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr() if five else None, 0, 0)
+    torch.cuda.synchronize()
+    t2 = time.time()
+    log("[bench] hexaploid genome %.2f Gsym in %.1fs, suffix array (%d-byte elements) in %.1fs" % (
+        n / 1e9, t1 - t0, 5 if five else 4, t2 - t1))
+    idx = bkx.Index.from_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr() if five else None, ents,
+                                name="hexaploid%dM" % args.genome_mbp, device=0, prefix_k=args.prefix_k)
+    torch.cuda.synchronize()
+    t3 = time.time()
+    log("[bench] index resident: %.1f GB HBM, prefix k=%d, %.1fs" % (idx.info.device_bytes / 1e9, idx.info.prefix_k, t3 - t2))
+    nreads, L = args.reads, args.read_len
+    d_bases, d_offs = wl.sim_reads(d_seq, ents, nreads, L, seed=args.seed + 100, subs=tuple(range(0, args.read_subs + 1)),
+                                   device=dev)
+    torch.cuda.synchronize()
+    el = int(idx.info.sfx_el_size)
+    p = idx.default_params(0, max_subs=args.max_subs)
+    d_out = torch.empty(nreads * 32, dtype=torch.uint8, device=dev)
+    d_stats = torch.zeros(C.sizeof(abi.AlignStats) // 8, dtype=torch.int64, device=dev)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+
+    def step():
+        d_stats.zero_()
+        idx.align_device(p, d_bases.data_ptr(), d_offs.data_ptr(), nreads, L, d_out.data_ptr(), d_stats.data_ptr(),
+                         tstream.cuda_stream)
+
+    l0 = idx.kernel_launches()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = (idx.kernel_launches() - l0) // max(1, args.warmup) if args.warmup else 2
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    step()
+    torch.cuda.synchronize()
+    kms = idx.last_kernel_ms()
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    res = d_out.cpu().numpy().view(abi.RESULT_DTYPE)
+    stats = d_stats.cpu().numpy()
+    alg = wl.algorithmic_bytes(res, n, el, L)
+    peak, peak_src = measured_peak()
+    nar = np.bincount(res["nar"], minlength=abi.NAR_COUNT)
+
+    # e2e through the host-buffer call
+    h_bases = torch.empty(nreads * L, dtype=torch.uint8).pin_memory()
+    h_bases.copy_(d_bases)
+    h_offs = (torch.arange(nreads + 1, dtype=torch.int64) * L).pin_memory()
+    h_out = torch.empty(nreads * 32, dtype=torch.uint8).pin_memory()
+    hst = abi.AlignStats()
+    idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
+    e2e_steps = max(1, min(args.steps, 3))
+    tq = time.perf_counter()
+    for _ in range(e2e_steps):
+        idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - tq) / e2e_steps
+    same = bool(h_out.numpy().view(abi.RESULT_DTYPE).tobytes() == res.tobytes())
+
+    # size-independent check: every accepted record carries exactly the mismatches found at its locus
+    acc = np.nonzero(res["nar"] == abi.NAR_ACCEPTED)[0]
+    pick = acc[:: max(1, len(acc) // 200000)]
+    ofs_of = {int(e["entry_id"]): int(e["start_ofs"]) for e in ents}
+    g0 = torch.from_numpy(np.array([ofs_of[int(c)] for c in res["chrom_id"][pick]], dtype=np.int64) +
+                          res["match_loci"][pick].astype(np.int64)).to(dev)
+    ar = torch.arange(L, device=dev)
+    gw = d_seq[g0[:, None] + ar[None, :]]
+    rd = d_bases.view(-1, L)[torch.from_numpy(pick.astype(np.int64)).to(dev)]
+    minus = torch.from_numpy((res["strand"][pick] == ord("-"))).to(dev)
+    rrc = torch.flip(rd, dims=[1])
+    rrc = torch.where(rrc < 4, 3 - rrc, rrc)
+    rd = torch.where(minus[:, None], rrc, rd)
+    mm = (rd != gw).sum(dim=1).cpu().numpy()
+    loci_ok = bool(np.array_equal(mm, res["mismatches"][pick]))
+
+    line = {
+        "metric": "aligned reads/sec (150bp, <=4 subs)", "value": nreads / (ms_per_step / 1e3), "unit": "reads/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "configs[3]: %.1f Gbp synthetic hexaploid (B, D = A + 2-5 %% substitutions + block shuffles), "
+                               "%d-byte suffix elements, %d x %d bp SE reads per step (x %d steps = %d reads), 0..%d subs, -s%d" % (
+                                   args.genome_mbp / 1e3, el, nreads, L, args.steps, nreads * args.steps, args.read_subs,
+                                   args.max_subs),
+                   "genome_symbols": n, "reads_per_step": nreads, "read_len": L, "prefix_k": int(idx.info.prefix_k),
+                   "index_gb": idx.info.device_bytes / 1e9 + n * el / 1e9,
+                   "build_s": {"genome": t1 - t0, "suffix_array_gpu": t2 - t1, "index_tables": t3 - t2},
+                   "l2_policy": "inputs larger than L2"},
+        "e2e": {"value": nreads / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": int(nreads * L + (nreads + 1) * 8),
+                "d2h_bytes_per_step": int(nreads * 32), "matches_device_run": same},
+        "gpu_launches": int(args.steps * launches_per_step),
+        "roofline": {"bound": "hbm", "achieved": alg / (kms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (kms / 1e3) / 1e9 / peak, "traffic": None,
+                     "kernel": "align_fast_kernel + align_reads_kernel (deferred reads)", "kernel_ms": kms,
+                     "algorithmic_bytes_per_launch": int(alg), "bytes_per_read": alg / nreads, "peak_source": peak_src},
+        "clocks": clocks,
+        "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]},
+        "accepted_loci_verified": {"records": int(len(pick)), "all_mismatch_counts_exact": loci_ok},
+        "stats_reads": int(stats[-1]),
+    }
+    # oracle on a sample, with the whole index copied to host memory (84 GB at 14 G symbols)
+    if not args.no_cpu_baseline:
+        import psutil
+        need = n * (1 + el) + (8 << 30)
+        if psutil.virtual_memory().available < need:
+            line["cpu_baseline"] = {"skipped": "host RAM: %.0f GB needed" % (need / 1e9)}
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import pyoracle as po
+            tc = time.time()
+            host_seq = d_seq.cpu().numpy()
+            if el == 4:
+                host_sa = d_lo.cpu().numpy().view(np.uint32)
+            else:
+                host_sa = np.empty((n, 5), dtype=np.uint8)
+                CHK = 1 << 28
+                for s0 in range(0, n, CHK):
+                    m = min(CHK, n - s0)
+                    blk = torch.cat([d_lo[s0:s0 + m].view(torch.uint8).view(m, 4), d_hi[s0:s0 + m].view(m, 1)], dim=1)
+                    host_sa[s0:s0 + m] = blk.cpu().numpy()
+                    del blk
+                host_sa = host_sa.reshape(-1)
+            log("[bench] index copied to host in %.1fs" % (time.time() - tc))
+            oidx = po.OracleIndex(seq=host_seq, sa=host_sa, el_size=el, entries=ents)
+            m = min(args.cpu_sample, nreads)
+            cores = os.cpu_count() or 1
+            hb = h_bases.numpy()[:m * L]
+            ho = np.arange(m + 1, dtype=np.uint64) * L
+            tq = time.perf_counter()
+            exp, _ = oidx.align(oidx.default_params(0, max_subs=args.max_subs), hb, ho, nthreads=cores)
+            dt = time.perf_counter() - tq
+            ok = all(np.array_equal(exp[f], res[f][:m]) for f in abi.RESULT_DTYPE.names)
+            line["cpu_baseline"] = {"value": m / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d of the %d reads, %.1fs" % (m, nreads, dt), "parity_with_gpu": bool(ok)}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(line, open(os.path.join(ROOT, "gpurun_out", "hexaploid.json"), "w"), indent=1)
+    print(json.dumps(line), flush=True)
+
+
 def cpu_baseline_port(args, host_seq, host_sa, ents, h_bases, gpu_res):
     """The CPU restatement on a bounded sample of the same reads, all host cores; also re-checks parity."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -508,6 +676,87 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_dropin(args):
+    """Full-size drop-in check (SURVEY.md section 8(c) comparison surface + 8(d) "end-to-end wall"): the reference's
+    `biokanga align` and this repo's `bkx-align` front end on the SAME files -- a 3.1 Gbp .sfx and a FASTA of
+    --ref-sample reads -- with the same options; compares the -M0 CSV rows and the alignment-summary block of the
+    logs, and reports both walls (process start to exit).  Needs the GPU box and oracle/_ref."""
+    import hashlib
+    import torch
+    from biokanga_b200 import lib as bkx
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    import synth
+    cli = os.path.join(os.path.dirname(bkx.LIB_PATH), "bkx-align")
+    if not (torch.cuda.is_available() and os.path.exists(po.REF_BIN) and os.path.exists(cli)):
+        print(json.dumps({"dropin": "unavailable", "why": "needs a GPU, oracle/_ref and biokanga_b200/bkx-align"}))
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    cores = os.cpu_count() or 1
+    sample = args.ref_sample
+    args.reads = sample
+    d_seq, d_sa, ents, n, d_bases, d_offs = build_workload(args, 0, 1, dev, torch, None)
+    host_seq = d_seq.cpu().numpy()
+    host_sa = d_sa.cpu().numpy().view(np.uint32)
+    h_bases = d_bases.cpu().numpy()
+    del d_seq, d_sa, d_bases, d_offs
+    torch.cuda.empty_cache()
+    L = args.read_len
+    tmp = tempfile.mkdtemp(prefix="bkxdrop", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+
+    def summary(path):
+        keep, on = [], False
+        for ln in open(path, errors="replace"):
+            body = ln.split("](biokanga) ", 1)[1] if "](biokanga) " in ln else ln
+            if "Alignment of" in body and "completed" in body:
+                on = True
+            if on and ("Reporting of aligned result set" in body or "Exit code" in body or "Total processing time" in body):
+                continue
+            if on:
+                keep.append(body.rstrip("\n"))
+        return keep
+
+    def digest(path):
+        rows = open(path, "rb").read().splitlines()
+        rows.sort()
+        h = hashlib.md5()
+        for r in rows:
+            h.update(r)
+            h.update(b"\n")
+        return len(rows), h.hexdigest()
+
+    try:
+        bkx.write_sfx(os.path.join(tmp, "g.sfx"), host_seq, host_sa, 4, ents, name="synth")
+        del host_seq, host_sa
+        write_fasta_fast(os.path.join(tmp, "r.fa"), h_bases[:sample * L].reshape(sample, L), synth.BASES)
+        common = ["align", "-I", "g.sfx", "-i", "r.fa", "-s%d" % args.max_subs, "-M0"]
+        t0 = time.time()
+        subprocess.run([po.REF_BIN] + common + ["-o", "ref.csv", "-F", "ref.log", "-T%d" % min(cores, 128)], cwd=tmp,
+                       check=True, stdout=subprocess.DEVNULL)
+        t_ref = time.time() - t0
+        t0 = time.time()
+        subprocess.run([cli] + common + ["-o", "bkx.csv", "-F", "bkx.log"], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+        t_bkx = time.time() - t0
+        n_ref, md_ref = digest(os.path.join(tmp, "ref.csv"))
+        n_bkx, md_bkx = digest(os.path.join(tmp, "bkx.csv"))
+        s_ref, s_bkx = summary(os.path.join(tmp, "ref.log")), summary(os.path.join(tmp, "bkx.log"))
+        line = {"dropin": "configs[1] files: %.1f Gbp .sfx (%.1f GB), %d x %d bp reads, -s%d -M0" % (
+                    args.genome_mbp / 1e3, os.path.getsize(os.path.join(tmp, "g.sfx")) / 1e9, sample, L, args.max_subs),
+                "csv_rows": [n_ref, n_bkx], "csv_md5_sorted": [md_ref, md_bkx], "csv_identical": md_ref == md_bkx and n_ref == n_bkx,
+                "summary_lines": [len(s_ref), len(s_bkx)], "summary_identical": s_ref == s_bkx,
+                "wall_s": {"reference": t_ref, "bkx-align": t_bkx, "reference_threads": min(cores, 128)}}
+        if s_ref != s_bkx:
+            line["summary_diff"] = [x for x in zip(s_ref, s_bkx) if x[0] != x[1]][:6]
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        for nm in ("ref.log", "bkx.log"):
+            subprocess.run(["cp", os.path.join(tmp, nm), os.path.join(ROOT, "gpurun_out", "dropin_" + nm)])
+        json.dump(line, open(os.path.join(ROOT, "gpurun_out", "dropin.json"), "w"), indent=1)
+        print(json.dumps(line), flush=True)
+    finally:
+        subprocess.run(["rm", "-rf", tmp])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -525,7 +774,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=4000000)
     ap.add_argument("--ref-port", action="store_true", help="reference arm: use the oracle port even if the binary exists")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="se", choices=["se", "pe"],
+    ap.add_argument("--workload", default="se", choices=["se", "pe", "hexaploid"],
                     help="se: configs[1] (default, the headline); pe: configs[2] shape -- 2x150 bp pairs, pairing + orphan recovery")
     ap.add_argument("--pe-mode", type=int, default=1, help="-U mode for --workload pe (1 = recover orphans)")
     ap.add_argument("--pe-min", type=int, default=200)
@@ -535,6 +784,8 @@ def main():
     ap.add_argument("--sweep-check", type=int, default=20000)
     ap.add_argument("--sweep-lens", default="50,75,100,150,200,250,300")
     ap.add_argument("--sweep-subs", default="0,1,2,3,4,5,6,7,8")
+    ap.add_argument("--dropin", action="store_true",
+                    help="run the reference binary and bkx-align on the same 3.1 Gbp files and compare their outputs")
     ap.add_argument("--kernel-times", action="store_true", help="read the kernel's own events after every step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "bkx":
@@ -544,6 +795,10 @@ def main():
         raise SystemExit("launch multi-GPU runs with torch.distributed.run --nproc-per-node %d" % args.gpus)
     if args.sweep:
         run_sweep(args)
+    elif args.dropin:
+        run_dropin(args)
+    elif args.workload == "hexaploid":
+        run_hexaploid(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -71,6 +71,51 @@ def make_genome(lens, seed=1, device="cuda", repeat_frac=0.05, repeat_len=(300, 
     return seq, ents
 
 
+def make_hexaploid(chrom_len, n_chrom=7, seed=1, device="cuda", divergence=((0.02, 0.035), (0.035, 0.05)),
+                   block=50_000, shuffle_frac=0.05, n_runs=12, n_run_len=60):
+    """Wheat-like hexaploid: sub-genome A is random; B and D are copies of A with
+    2-5 % substitutions (one rate per chromosome, drawn from `divergence`) and local shuffles (neighbouring blocks
+    swapped).  Entries are ordered 1A..7A, 1B..7B, 1D..7D.  Returns (d_seq, entries) like make_genome."""
+    lens = [int(chrom_len)] * (3 * n_chrom)
+    ents, n = entries_for(lens)
+    for i in range(3 * n_chrom):
+        ents[i]["name"] = ("chr%d%s" % (i % n_chrom + 1, "ABD"[i // n_chrom])).encode()
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    seq = torch.empty(n, dtype=torch.uint8, device=device)
+    CH = 1 << 26
+    for c in range(n_chrom):
+        a0 = int(ents[c]["start_ofs"])
+        for s0 in range(0, chrom_len, CH):
+            m = min(CH, chrom_len - s0)
+            seq[a0 + s0:a0 + s0 + m] = torch.randint(0, 4, (m,), dtype=torch.uint8, device=device, generator=g)
+        for sub in (1, 2):
+            d0 = int(ents[sub * n_chrom + c]["start_ofs"])
+            lo, hi = divergence[sub - 1]
+            rate = lo + (hi - lo) * float(torch.rand(1, device=device, generator=g).item())
+            for s0 in range(0, chrom_len, CH):
+                m = min(CH, chrom_len - s0)
+                v = seq[a0 + s0:a0 + s0 + m]
+                mut = torch.rand(m, device=device, generator=g) < rate
+                add = torch.randint(1, 4, (m,), dtype=torch.uint8, device=device, generator=g)
+                seq[d0 + s0:d0 + s0 + m] = torch.where(mut, (v + add) & 3, v)
+            nblk = chrom_len // block
+            if nblk > 2 and shuffle_frac > 0:
+                k = max(1, int(nblk * shuffle_frac))
+                pick = torch.randperm((nblk - 1) // 2, device=device, generator=g)[:k] * 2  # disjoint neighbour pairs
+                for b in pick.tolist():
+                    x = d0 + b * block
+                    t = seq[x:x + block].clone()
+                    seq[x:x + block] = seq[x + block:x + 2 * block]
+                    seq[x + block:x + 2 * block] = t
+    for i in range(n_runs):
+        p = int(torch.randint(0, n - n_run_len, (1,), generator=g, device=device).item())
+        seq[p:p + n_run_len] = 4
+    eos = torch.from_numpy((ents["end_ofs"] + 1).astype(np.int64)).to(device)
+    seq[eos] = 7
+    return seq, ents
+
+
 def sim_reads(d_seq, ents, n_reads, length, seed=2, subs=(0, 1, 2, 3, 4), device="cuda", chunk=1 << 21):
     """Returns (d_bases uint8[n_reads*length], d_offsets int64[n_reads+1]).  Each read is a genome
     substring (either strand) carrying k substitutions, k drawn uniformly from `subs`."""
