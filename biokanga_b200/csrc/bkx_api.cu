@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
@@ -439,59 +440,65 @@ extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_in
   if (rc < 0) { close(fd); return rc; }
   x->info.version = version;
   x->info.attributes = attributes;
-  // Stream the block to the GPU through two pinned staging buffers.  4-byte elements land in their final array;
-  // 5-byte elements pass through a small device staging buffer and are split into the two planes chunk by chunk,
-  // so an 84 GB index never needs more than its final footprint.
+  // Stream the block to the GPU: a few reader threads, each with its own pinned staging buffer and CUDA stream, take
+  // the 60 MB chunks round-robin (the page-cache copy, not PCIe, is the slow half).  4-byte elements land in their final
+  // array; 5-byte elements pass through a device staging buffer and are split into the two planes chunk by chunk, so
+  // an 84 GB index never needs more than its final footprint.
   uint8_t* d_seq = nullptr;
   uint32_t* d_lo = nullptr;
   uint8_t* d_hi = nullptr;
-  uint8_t* d_stage[2] = {nullptr, nullptr};
-  const size_t chunk = (size_t)60 << 20;  // a multiple of 5
-  uint8_t* pin[2] = {nullptr, nullptr};
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  const size_t chunk = (size_t)60 << 20;  // a multiple of 5 and of 4
   cudaError_t e = cudaMalloc((void**)&d_seq, n);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_lo, n * 4);
   if (e == cudaSuccess && el == 5) e = cudaMalloc((void**)&d_hi, n);
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-    e = cudaMallocHost((void**)&pin[i], chunk);
-    if (e == cudaSuccess) e = cudaEventCreate(&ev[i]);
-    if (e == cudaSuccess && el == 5) e = cudaMalloc((void**)&d_stage[i], chunk);
-  }
   bool io_ok = true;
   if (e == cudaSuccess) {
-    cudaStream_t st = x->slot[0].st;
-    uint64_t total = n + n * el, done = 0;
-    int b = 0;
-    bool used[2] = {false, false};
-    while (done < total && e == cudaSuccess) {
-      size_t len = (size_t)std::min<uint64_t>(chunk, total - done);
-      // never let one chunk straddle the sequence / suffix-array boundary
-      if (done < n && done + len > n) len = (size_t)(n - done);
-      if (used[b]) e = cudaEventSynchronize(ev[b]);
-      if (!pread_all(fd, pin[b], len, (off_t)(blk_ofs + 20 + done))) { io_ok = false; break; }
-      if (done < n) {
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_seq + done, pin[b], len, cudaMemcpyHostToDevice, st);
-      } else if (el == 4) {
-        if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)d_lo + (done - n), pin[b], len, cudaMemcpyHostToDevice, st);
-      } else {
-        uint64_t first = (done - n) / 5;  // chunks inside the array start on element boundaries (chunk % 5 == 0)
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_stage[b], pin[b], len, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = launch_split_sa5(d_stage[b], len / 5, d_lo + first, d_hi + first, st);
-        x->launches += 1;
-      }
-      if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
-      used[b] = true;
-      done += len;
-      b ^= 1;
+    const uint64_t seq_chunks = (n + chunk - 1) / chunk, sa_bytes = n * el, sa_chunks = (sa_bytes + chunk - 1) / chunk;
+    const uint64_t n_chunks = seq_chunks + sa_chunks;
+    const int n_workers = (int)std::min<uint64_t>(6, n_chunks);
+    std::vector<cudaError_t> werr((size_t)n_workers, cudaSuccess);
+    std::vector<char> wio((size_t)n_workers, 1);
+    std::vector<uint64_t> wlaunch((size_t)n_workers, 0);
+    std::vector<std::thread> workers;
+    for (int w = 0; w < n_workers; ++w)
+      workers.emplace_back([&, w]() {
+        cudaError_t ce = cudaSetDevice(device);
+        uint8_t* pin = nullptr;
+        uint8_t* stage = nullptr;
+        cudaStream_t st = nullptr;
+        if (ce == cudaSuccess) ce = cudaMallocHost((void**)&pin, chunk);
+        if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (ce == cudaSuccess && el == 5) ce = cudaMalloc((void**)&stage, chunk);
+        for (uint64_t c = (uint64_t)w; c < n_chunks && ce == cudaSuccess && wio[(size_t)w]; c += (uint64_t)n_workers) {
+          const bool is_seq = c < seq_chunks;
+          const uint64_t ofs = is_seq ? c * chunk : (c - seq_chunks) * chunk;
+          const size_t len = (size_t)std::min<uint64_t>(chunk, (is_seq ? n : sa_bytes) - ofs);
+          if (!pread_all(fd, pin, len, (off_t)(blk_ofs + 20 + (is_seq ? ofs : n + ofs)))) { wio[(size_t)w] = 0; break; }
+          if (is_seq) {
+            ce = cudaMemcpyAsync(d_seq + ofs, pin, len, cudaMemcpyHostToDevice, st);
+          } else if (el == 4) {
+            ce = cudaMemcpyAsync((uint8_t*)d_lo + ofs, pin, len, cudaMemcpyHostToDevice, st);
+          } else {
+            const uint64_t first = ofs / 5;  // chunks start on element boundaries (chunk % 5 == 0)
+            ce = cudaMemcpyAsync(stage, pin, len, cudaMemcpyHostToDevice, st);
+            if (ce == cudaSuccess) ce = launch_split_sa5(stage, len / 5, d_lo + first, d_hi + first, st);
+            ++wlaunch[(size_t)w];
+          }
+          if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // the pinned buffer is about to be refilled
+        }
+        if (pin) cudaFreeHost(pin);
+        if (stage) cudaFree(stage);
+        if (st) cudaStreamDestroy(st);
+        werr[(size_t)w] = ce;
+      });
+    for (auto& t : workers) t.join();
+    for (int w = 0; w < n_workers; ++w) {
+      if (werr[(size_t)w] != cudaSuccess && e == cudaSuccess) e = werr[(size_t)w];
+      if (!wio[(size_t)w]) io_ok = false;
+      x->launches += wlaunch[(size_t)w];
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
   close(fd);
-  for (int i = 0; i < 2; ++i) {
-    if (pin[i]) cudaFreeHost(pin[i]);
-    if (ev[i]) cudaEventDestroy(ev[i]);
-    if (d_stage[i]) cudaFree(d_stage[i]);
-  }
   if (e != cudaSuccess || !io_ok) {
     cudaFree(d_seq); cudaFree(d_lo); cudaFree(d_hi); bkx_close_index(x);
     return e != cudaSuccess ? fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e))

@@ -67,56 +67,6 @@ struct Reads {
   int len(uint32_t i) const { return (int)(offs[i + 1] - offs[i]); }
 };
 
-struct SeqFile {  // FASTA / FASTQ, plain or gzip (zlib reads both)
-  gzFile f = nullptr;
-  std::string path, pending;
-  bool have_pending = false;
-  bool open(const std::string& p) {
-    path = p;
-    f = gzopen(p.c_str(), "rb");
-    if (f) gzbuffer(f, 1 << 20);
-    return f != nullptr;
-  }
-  void close() { if (f) gzclose(f); f = nullptr; }
-  bool getline(std::string& s) {
-    if (have_pending) { s.swap(pending); have_pending = false; return true; }
-    s.clear();
-    char buf[65536];
-    for (;;) {
-      if (!gzgets(f, buf, sizeof(buf))) return !s.empty();
-      size_t n = strlen(buf);
-      bool eol = n && buf[n - 1] == '\n';
-      while (n && (buf[n - 1] == '\n' || buf[n - 1] == '\r')) --n;
-      s.append(buf, n);
-      if (eol) return true;
-    }
-  }
-  // next record: descriptor (text after '>' / '@' up to the first white space, <= 127 chars) and sequence
-  bool next(std::string& descr, std::string& seq, std::string& qual) {
-    std::string ln;
-    do { if (!getline(ln)) return false; } while (ln.empty());
-    if (ln[0] != '>' && ln[0] != '@') return false;
-    bool fastq = ln[0] == '@';
-    size_t e = 1;
-    while (e < ln.size() && !isspace((unsigned char)ln[e]) && e - 1 < 127) ++e;
-    descr.assign(ln, 1, e - 1);
-    seq.clear();
-    qual.clear();
-    if (fastq) {
-      if (!getline(seq)) return false;
-      std::string plus;
-      getline(plus);
-      getline(qual);
-    } else {
-      while (getline(ln)) {
-        if (!ln.empty() && ln[0] == '>') { pending.swap(ln); have_pending = true; break; }
-        seq += ln;
-      }
-    }
-    return true;
-  }
-};
-
 static inline uint8_t base_code(char c) {  // CFasta::Ascii2Sense, Fasta.cpp:1518-1570 (soft-mask bit dropped)
   switch (c) {
     case 'a': case 'A': return 0;
@@ -159,40 +109,256 @@ struct Opts {
   std::string sfx, out, logfile, title;
 };
 
+// ---- read files: slurped whole (gzip inflated on the way), split at record boundaries, parsed by all host threads.
+struct RawRec {        // one FASTA / FASTQ record as pointers into the file text
+  const char* name;    // descriptor: text after '>' / '@' up to the first white space, <= 127 chars
+  const char* sb;      // sequence region [sb, se); may hold line breaks (multi-line FASTA)
+  const char* se;
+  const char* q;       // FASTQ quality line or nullptr
+  uint32_t name_n, len, qlen;
+};
+
+static bool slurp(const std::string& path, std::vector<char>& text, unsigned threads) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  unsigned char magic[2] = {0, 0};
+  size_t got = fread(magic, 1, 2, f);
+  fseeko(f, 0, SEEK_END);
+  size_t size = (size_t)ftello(f);
+  fclose(f);
+  if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) return false;
+    gzbuffer(g, 1 << 20);
+    text.resize(std::max<size_t>(size * 4, (size_t)1 << 20));
+    size_t n = 0;
+    for (;;) {
+      if (n == text.size()) text.resize(text.size() * 2);
+      int r = gzread(g, text.data() + n, (unsigned)std::min<size_t>(text.size() - n, (size_t)1 << 30));
+      if (r < 0) { gzclose(g); return false; }
+      if (r == 0) break;
+      n += (size_t)r;
+    }
+    gzclose(g);
+    text.resize(n);
+    return true;
+  }
+  text.resize(size);
+  if (size == 0) return true;
+  threads = std::max(1u, std::min(threads, (unsigned)((size >> 24) + 1)));
+  std::vector<std::thread> th;
+  std::vector<char> okv(threads, 1);
+  for (unsigned t = 0; t < threads; ++t)
+    th.emplace_back([&, t]() {
+      size_t b = size * t / threads, e = size * (t + 1) / threads;
+      FILE* h = fopen(path.c_str(), "rb");
+      if (!h) { okv[t] = 0; return; }
+      fseeko(h, (off_t)b, SEEK_SET);
+      while (b < e) {
+        size_t r = fread(text.data() + b, 1, std::min<size_t>(e - b, (size_t)64 << 20), h);
+        if (r == 0) { okv[t] = 0; break; }
+        b += r;
+      }
+      fclose(h);
+    });
+  for (auto& x : th) x.join();
+  for (char k : okv) if (!k) return false;
+  return true;
+}
+
+static inline const char* line_end(const char* p, const char* end) {
+  const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+  return nl ? nl : end;
+}
+static inline const char* next_line(const char* eol, const char* end) { return eol < end ? eol + 1 : end; }
+
+// first record start at or after `from` (a line start): FASTA '>' lines; FASTQ '@' lines whose line + 2 starts with '+'
+static const char* record_start(const char* text, const char* from, const char* end, bool fastq) {
+  const char* p = from;
+  if (p > text && p[-1] != '\n') p = next_line(line_end(p, end), end);
+  while (p < end) {
+    if (!fastq) {
+      if (*p == '>') return p;
+    } else if (*p == '@') {
+      const char* l1 = next_line(line_end(p, end), end);
+      const char* l2 = next_line(line_end(l1, end), end);
+      if (l2 < end && *l2 == '+' && (l1 >= end || *l1 != '@')) return p;
+    }
+    p = next_line(line_end(p, end), end);
+  }
+  return end;
+}
+
+// parse the records that START inside [b, e); returns false at a malformed record (everything before it is kept)
+static bool parse_records(const char* b, const char* e, const char* end, bool fastq, std::vector<RawRec>& out) {
+  const char* p = b;
+  auto trim_eol = [](const char* s, const char* t) { while (t > s && (t[-1] == '\r' || t[-1] == '\n')) --t; return t; };
+  while (p < e) {
+    const char* le = line_end(p, end);
+    const char* lt = trim_eol(p, le);
+    if (lt == p) { p = next_line(le, end); continue; }  // blank line
+    if (*p != (fastq ? '@' : '>')) return false;
+    RawRec r;
+    const char* d = p + 1;
+    const char* de = d;
+    while (de < lt && !isspace((unsigned char)*de) && de - d < 127) ++de;
+    r.name = d;
+    r.name_n = (uint32_t)(de - d);
+    r.q = nullptr;
+    r.qlen = 0;
+    p = next_line(le, end);
+    if (fastq) {
+      if (p >= end) return true;  // header without a sequence line: end of data
+      const char* se = line_end(p, end);
+      r.sb = p;
+      r.se = trim_eol(p, se);
+      r.len = (uint32_t)(r.se - r.sb);
+      p = next_line(se, end);
+      p = next_line(line_end(p, end), end);  // '+' line
+      if (p < end) {
+        const char* qe = line_end(p, end);
+        r.q = p;
+        r.qlen = (uint32_t)(trim_eol(p, qe) - p);
+        p = next_line(qe, end);
+      }
+    } else {
+      r.sb = p;
+      uint32_t len = 0;
+      while (p < end && *p != '>') {
+        const char* se = line_end(p, end);
+        len += (uint32_t)(trim_eol(p, se) - p);
+        p = next_line(se, end);
+      }
+      r.se = p;
+      r.len = len;
+    }
+    out.push_back(r);
+  }
+  return true;
+}
+
+static bool parse_file(const std::string& path, unsigned threads, std::vector<char>& text, std::vector<RawRec>& recs) {
+  if (!slurp(path, text, threads)) return false;
+  const char* b = text.data();
+  const char* end = b + text.size();
+  const char* first = b;
+  while (first < end && (*first == '\n' || *first == '\r')) ++first;
+  if (first == end) return true;
+  if (*first != '>' && *first != '@') return true;  // not a sequence file: no records (as the line reader behaved)
+  const bool fastq = *first == '@';
+  size_t min_chunk = (size_t)4 << 20;
+  if (const char* ev = getenv("BKX_PARSE_MIN_CHUNK")) min_chunk = std::max<size_t>(64, (size_t)atoll(ev));  // test hook
+  unsigned T = std::max(1u, std::min(threads, (unsigned)(text.size() / min_chunk + 1)));
+  std::vector<const char*> cut(T + 1, end);
+  cut[0] = first;
+  for (unsigned t = 1; t < T; ++t) cut[t] = record_start(b, b + text.size() * t / T, end, fastq);
+  for (unsigned t = 1; t <= T; ++t) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+  std::vector<std::vector<RawRec>> part(T);
+  std::vector<char> good(T, 1);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < T; ++t)
+    th.emplace_back([&, t]() { good[t] = parse_records(cut[t], cut[t + 1], end, fastq, part[t]) ? 1 : 0; });
+  for (auto& x : th) x.join();
+  size_t total = 0;
+  for (unsigned t = 0; t < T; ++t) { total += part[t].size(); if (!good[t]) break; }
+  recs.reserve(total);
+  for (unsigned t = 0; t < T; ++t) {
+    recs.insert(recs.end(), part[t].begin(), part[t].end());
+    if (!good[t]) break;  // a malformed record ends the file there
+  }
+  return true;
+}
+
 static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (default -g3: qualities ignored)
   bool pe = o.pe_mode != 0;
+  uint8_t code_tab[256];
+  for (int c = 0; c < 256; ++c) code_tab[c] = base_code((char)c);
+  const unsigned T = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   diag("Loading reads from file...");
   for (size_t fi = 0; fi < o.in.size(); ++fi) {
-    SeqFile f1, f2;
-    if (!f1.open(o.in[fi])) { diag("Unable to open '%s'", o.in[fi].c_str()); return -1; }
-    if (pe && !f2.open(o.pair[fi])) { diag("Unable to open '%s'", o.pair[fi].c_str()); return -1; }
-    std::string d1, s1, d2, s2, q1, q2;
+    std::vector<char> text[2];
+    std::vector<RawRec> recs[2];
+    bool opened[2] = {true, true};
+    {
+      std::thread t2;
+      if (pe) t2 = std::thread([&]() { opened[1] = parse_file(o.pair[fi], std::max(1u, T / 2), text[1], recs[1]); });
+      opened[0] = parse_file(o.in[fi], pe ? std::max(1u, T / 2) : T, text[0], recs[0]);
+      if (pe) t2.join();
+    }
+    if (!opened[0]) { diag("Unable to open '%s'", o.in[fi].c_str()); return -1; }
+    if (pe && !opened[1]) { diag("Unable to open '%s'", o.pair[fi].c_str()); return -1; }
+    const size_t nrec = recs[0].size();
+    // length filter, pairwise for PE (Aligner.cpp:10895-10935)
     uint32_t accepted = 0, under = 0, over = 0;
-    while (f1.next(d1, s1, q1)) {
-      if (pe && !f2.next(d2, s2, q2)) { diag("Problem parsing sequence after %u reads parsed", accepted); return -1; }
-      auto bad_len = [&](const std::string& s, uint32_t& u, uint32_t& ov) {
-        if (o.trim5 + o.trim3 + o.min_len > (int)s.size()) { ++u; return true; }
-        if (o.trim5 + o.trim3 + o.max_len < (int)s.size()) { ++ov; return true; }
-        return false;
-      };
-      if (bad_len(s1, under, over)) continue;
-      if (pe && bad_len(s2, under, over)) continue;
-      auto add = [&](const std::string& d, const std::string& s, const std::string& q) {
-        size_t b = (size_t)o.trim5, e = s.size() - (size_t)o.trim3;
-        bool useq = o.qmode != 3 && q.size() == s.size();
-        for (size_t i = b; i < e; ++i)
-          R.bases.push_back((uint8_t)(base_code(s[i]) | (useq ? (qual4(o.qmode, (unsigned char)q[i]) << 4) : 0)));
-        R.offs.push_back(R.bases.size());
-        R.name_ofs.push_back(R.names.size());
-        R.names.insert(R.names.end(), d.begin(), d.end());
-        R.names.push_back('\0');
-      };
-      add(d1, s1, q1);
-      if (pe) add(d2, s2, q2);
+    std::vector<uint8_t> keep(nrec, 0);
+    auto bad_len = [&](uint32_t len, uint32_t& u, uint32_t& ov) {
+      if (o.trim5 + o.trim3 + o.min_len > (int)len) { ++u; return true; }
+      if (o.trim5 + o.trim3 + o.max_len < (int)len) { ++ov; return true; }
+      return false;
+    };
+    for (size_t i = 0; i < nrec; ++i) {
+      if (pe && i >= recs[1].size()) { diag("Problem parsing sequence after %u reads parsed", accepted); return -1; }
+      if (bad_len(recs[0][i].len, under, over)) continue;
+      if (pe && bad_len(recs[1][i].len, under, over)) continue;
+      keep[i] = 1;
       ++accepted;
     }
-    f1.close();
-    if (pe) f2.close();
+    // offsets of every accepted read in the arena, then a parallel fill
+    const int per = pe ? 2 : 1;
+    const size_t first_read = R.offs.size() - 1, add_reads = (size_t)accepted * per;
+    R.offs.resize(first_read + add_reads + 1);
+    R.name_ofs.resize(first_read + add_reads);
+    std::vector<size_t> src(add_reads);  // accepted read -> record index (file = read index & 1 for PE)
+    uint64_t bo = R.bases.size(), no = R.names.size();
+    size_t w = first_read;
+    const size_t cut = (size_t)(o.trim5 + o.trim3);
+    for (size_t i = 0; i < nrec; ++i) {
+      if (!keep[i]) continue;
+      for (int f = 0; f < per; ++f) {
+        const RawRec& r = recs[f][i];
+        R.offs[w] = bo;
+        R.name_ofs[w] = no;
+        src[w - first_read] = i;
+        bo += r.len - cut;
+        no += r.name_n + 1;
+        ++w;
+      }
+    }
+    R.offs[w] = bo;
+    R.bases.resize(bo);
+    R.names.resize(no);
+    {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+          size_t b = add_reads * t / T, e = add_reads * (t + 1) / T;
+          std::vector<uint8_t> tmp;
+          for (size_t k = b; k < e; ++k) {
+            const RawRec& r = recs[pe ? (k & 1) : 0][src[k]];
+            uint8_t* dst = R.bases.data() + R.offs[first_read + k];
+            const size_t L = r.len - cut;
+            const bool useq = o.qmode != 3 && r.q && r.qlen == r.len;
+            if ((size_t)(r.se - r.sb) == r.len) {  // one line
+              const char* sp = r.sb + o.trim5;
+              if (useq) {
+                const char* qp = r.q + o.trim5;
+                for (size_t i = 0; i < L; ++i)
+                  dst[i] = (uint8_t)(code_tab[(unsigned char)sp[i]] | (qual4(o.qmode, (unsigned char)qp[i]) << 4));
+              } else {
+                for (size_t i = 0; i < L; ++i) dst[i] = code_tab[(unsigned char)sp[i]];
+              }
+            } else {  // multi-line FASTA: drop the line breaks first
+              tmp.clear();
+              for (const char* c = r.sb; c < r.se; ++c) if (*c != '\n' && *c != '\r') tmp.push_back(code_tab[(unsigned char)*c]);
+              memcpy(dst, tmp.data() + o.trim5, L);
+            }
+            char* nm = R.names.data() + R.name_ofs[first_read + k];
+            memcpy(nm, r.name, r.name_n);
+            nm[r.name_n] = '\0';
+          }
+        });
+      for (auto& x : th) x.join();
+    }
     diag("LoadReads: Total of %1.9d reads parsed and loaded from %s", accepted, o.in[fi].c_str());
     if (under) diag("Load: total of %d under length sequences sloughed from file '%s'", under, o.in[fi].c_str());
     if (over) diag("Load: total of %d over length sequences sloughed from file '%s'", over, o.in[fi].c_str());
@@ -289,19 +455,7 @@ static int parse(int argc, char** argv, Opts& o) {
   return 0;
 }
 
-// ---- ordering: SortHitMatch (Aligner.cpp:10067-10114); ties broken by read id for determinism ------
-static bool hit_less(const bkx_read_result& a, const bkx_read_result& b, uint32_t ia, uint32_t ib) {
-  if (a.nar != b.nar) return a.nar < b.nar;
-  bool a1 = a.num_hits == 1, b1 = b.num_hits == 1;
-  if (a1 != b1) return a1;
-  if (!a1) { if (a.num_hits != b.num_hits) return a.num_hits < b.num_hits; return ia < ib; }
-  if (a.chrom_id != b.chrom_id) return a.chrom_id < b.chrom_id;
-  if (a.match_loci != b.match_loci) return a.match_loci < b.match_loci;
-  if (a.match_len != b.match_len) return a.match_len < b.match_len;
-  if (a.strand != b.strand) return a.strand < b.strand;
-  if (a.low_mm != b.low_mm) return a.low_mm < b.low_mm;
-  return ia < ib;
-}
+// ---- ordering: bkx_sort_hits (SortHitMatch, Aligner.cpp:10067-10114; ties broken by read id for determinism)
 
 static const char* kNarCode[] = {"NA", "AA", "EN", "NL", "MH", "ML", "ET", "OJ", "OM", "DP", "DS", "FC", "PR", "UI", "OI", "UP", "IS", "IT", "NP", "LC"};
 static const char* kNarText[] = {
@@ -328,8 +482,39 @@ struct OutBuf {  // plain or gzip (when the output name ends in .gz, as the refe
     s.clear();
   }
   void maybe() { if (s.size() > (1 << 22) - 8192) flush(); }
+  void write(const std::string& t) {
+    flush();
+    if (t.empty()) return;
+    if (gz) gzwrite(gz, t.data(), (unsigned)t.size()); else fwrite(t.data(), 1, t.size(), f);
+  }
   void close() { flush(); if (gz) gzclose(gz); if (f) fclose(f); gz = nullptr; f = nullptr; }
 };
+
+// Format rows [0, n) with `threads` workers, each filling its own buffer for a contiguous run of rows; the buffers
+// are written in row order.  row(k, out) appends the text of row k (possibly nothing).
+template <class F>
+static void emit_rows(OutBuf& ob, uint32_t n, unsigned threads, F&& row) {
+  const uint32_t chunk = 1u << 16;
+  if (threads < 1) threads = 1;
+  std::vector<std::string> bufs(threads);
+  for (uint64_t base = 0; base < n; base += (uint64_t)chunk * threads) {
+    std::vector<std::thread> th;
+    unsigned used = 0;
+    for (unsigned t = 0; t < threads; ++t) {
+      uint64_t b = base + (uint64_t)t * chunk;
+      if (b >= n) break;
+      uint64_t e = std::min<uint64_t>(n, b + chunk);
+      ++used;
+      th.emplace_back([&row, &bufs, t, b, e]() {
+        std::string& s = bufs[t];
+        s.clear();
+        for (uint64_t k = b; k < e; ++k) row((uint32_t)k, s);
+      });
+    }
+    for (auto& x : th) x.join();
+    for (unsigned t = 0; t < used; ++t) ob.write(bufs[t]);
+  }
+}
 
 // ---- BAM (BGZF) + BAI, as CSAMfile writes them (libbiokanga/SAMfile.cpp:1383-1660, 1839-2030, 2286-2556; bgzf.cpp) ----
 // BGZF: 0xff00-byte blocks, raw deflate level 6 (Aligner.cpp:722), standard 18-byte header / 8-byte footer, an empty
@@ -465,6 +650,12 @@ int main(int argc, char** argv) {
   auto t_start = std::chrono::steady_clock::now();
   diag("Subprocess align Version 4.4.2 (bkx B200 path) starting");
 
+  // ---- reads load on their own thread while the index streams to the GPU (the reference also loads in the background)
+  Reads R;
+  int reads_rc = 0;
+  std::thread reads_thread([&]() { reads_rc = load_reads(o, R); });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } reads_joiner{reads_thread};
+
   // ---- index: one handle per GPU
   diag("Loading suffix array file '%s'", o.sfx.c_str());
   std::vector<bkx_index*> idx((size_t)o.gpus, nullptr);
@@ -478,9 +669,8 @@ int main(int argc, char** argv) {
   if (bkx_default_params(idx[0], o.pmode, &P) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
   P.max_subs = o.max_subs; P.min_edit_dist = o.edit_delta; P.max_ns = o.max_ns; P.align_strand = o.strand;
 
-  // ---- reads
-  Reads R;
-  if (load_reads(o, R) < 0) return 1;
+  reads_thread.join();
+  if (reads_rc < 0) return 1;
   const uint32_t n = R.n();
   if (n == 0) { diag("Fatal: no reads loaded"); return 1; }
   diag("Genome assembly suffix array loaded");
@@ -586,10 +776,10 @@ int main(int argc, char** argv) {
 
   // ---- order and write
   std::vector<uint32_t> order(n);
-  for (uint32_t i = 0; i < n; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hit_less(res[a], res[b], a, b); });
+  if (bkx_sort_hits(res.data(), n, order.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
   std::vector<bkx_entry> ents(info.num_entries + 1);
   for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
+  unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   OutBuf ob;
   if (!ob.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
   diag("Reporting of aligned result set started...");
@@ -598,16 +788,14 @@ int main(int argc, char** argv) {
     // UCSC BED: track line then chrom, start, end+1, "ar", score, strand (Aligner.cpp:6355-6362, 6463-6466)
     const char* title = o.title.empty() ? "kanga" : o.title.c_str();
     ob.s += "track type=bed name=\""; ob.s += title; ob.s += "\" description=\""; ob.s += title; ob.s += "\"\n";
-    for (uint32_t k = 0; k < n; ++k) {
+    emit_rows(ob, n, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
-      if (r.nar != BKX_NAR_ACCEPTED) continue;
-      std::string& s = ob.s;
+      if (r.nar != BKX_NAR_ACCEPTED) return;
       s += ents[r.chrom_id].name; s += '\t';
       append_uint(s, r.match_loci); s += '\t';
       append_uint(s, (uint64_t)r.match_loci + r.match_len); s += "\tar\t0\t"; s += (char)r.strand; s += '\n';
-      ob.maybe();
-    }
+    });
   } else if (o.fmt <= 3) {
     // ReadID,"ar","species","chrom",start,end,len,"strand",score,0,NumReads,TrimMismatches,"N/A","descriptor"
     // -M2/-M3 append the read sequence, -M1/-M3 the matched genome sequence in read orientation (Aligner.cpp:6612-6621)
@@ -617,11 +805,10 @@ int main(int argc, char** argv) {
         genome[e].resize(ents[e].seq_len);
         if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
       }
-    for (uint32_t k = 0; k < n; ++k) {
+    emit_rows(ob, n, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
-      if (r.nar != BKX_NAR_ACCEPTED) continue;
-      std::string& s = ob.s;
+      if (r.nar != BKX_NAR_ACCEPTED) return;
       append_uint(s, (uint64_t)i + 1);
       s += ",\"ar\",\""; s += info.dataset_name; s += "\",\""; s += ents[r.chrom_id].name; s += "\",";
       append_uint(s, r.match_loci); s += ',';
@@ -642,8 +829,7 @@ int main(int argc, char** argv) {
         s += '"';
       }
       s += '\n';
-      ob.maybe();
-    }
+    });
   } else if (is_bam_name(o.out)) {
     // ---- BAM + BAI (same record content as the SAM branch below, binary form)
     ob.close();
@@ -756,11 +942,11 @@ int main(int argc, char** argv) {
         append_uint(ob.s, ents[e].seq_len); ob.s += '\n';
       }
     ob.s += "@PG\tID:biokanga\tVN:4.4.2\n";
-    for (uint32_t k = 0; k < n; ++k) {
+    emit_rows(ob, n, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
       bool acc = r.nar == BKX_NAR_ACCEPTED;
-      if (!acc && o.fmt != 6) continue;
+      if (!acc && o.fmt != 6) return;
       int flags = 0, tlen = 0;
       long pnext = -1;
       if (!o.pe_mode) {
@@ -780,7 +966,6 @@ int main(int argc, char** argv) {
           }
         } else flags |= 0x08;
       }
-      std::string& s = ob.s;
       s += R.name(i); s += '\t';
       append_uint(s, (uint64_t)flags); s += '\t';
       if (acc) { s += ents[r.chrom_id].name; s += '\t'; append_uint(s, (uint64_t)r.match_loci + 1); }
@@ -805,8 +990,7 @@ int main(int argc, char** argv) {
       else for (int q = 0; q < L; ++q) s += (char)(33 + (((b[q] >> 4) & 0x0f) * 40) / 15);
       if (!acc) { s += "\t\tYU:Z:"; s += kNarCode[r.nar]; }
       s += '\n';
-      ob.maybe();
-    }
+    });
   }
   ob.close();
   diag("Reporting of aligned result set completed");

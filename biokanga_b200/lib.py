@@ -23,7 +23,7 @@ EXPORTS = [
     "bkx_get_ident", "bkx_get_seq", "bkx_default_params", "bkx_align_reads", "bkx_align_reads_device",
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
-    "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes",
+    "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits",
 ]
 
 
@@ -61,6 +61,7 @@ def lib():
     L.bkx_open_index_dev.argtypes = [vp, u64, vp, u32, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_open_index_planes.argtypes = [vp, u64, vp, vp, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_build_suffix_array_planes.argtypes = [vp, u64, vp, vp, i32, u64]
+    L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_clone_index.argtypes = [vp, i32, C.POINTER(vp)]
     L.bkx_close_index.argtypes = [vp]
     L.bkx_close_index.restype = None
@@ -104,6 +105,14 @@ def build_suffix_array_device(d_seq_ptr, concat_len, d_sa_ptr, device=0):
 def build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr=None, device=0, max_batch=0):
     """Bounded-memory builder for any size (the one for >= 4e9 symbols): u32 low plane + u8 high plane out."""
     check(lib().bkx_build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, device, max_batch))
+
+
+def sort_hits(results, device=0):
+    """Record indices in the reference's output order (SortHitMatch), ties by index."""
+    results = np.ascontiguousarray(results, dtype=abi.RESULT_DTYPE)
+    order = np.empty(len(results), dtype=np.uint32)
+    check(lib().bkx_sort_hits(results.ctypes.data, len(results), order.ctypes.data, device))
+    return order
 
 
 def write_sfx(path, seq, sa, el_size, entries, name="bkx"):

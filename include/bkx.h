@@ -224,6 +224,13 @@ int bkx_pair_reads_device(bkx_index* idx, const bkx_align_params* p, const bkx_p
                           uint32_t n_pairs, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t max_read_len,
                           bkx_pe_stats* d_stats, uint32_t* d_len_dist, void* cuda_stream);
 
+/* ---- output order: replaces CAligner::SortReadHits(eRSMHitMatch) + SortHitMatch (Aligner.cpp:9917-9991,
+ * 10067-10114).  order_out[k] = index of the k-th record under the reference's hit ordering (NAR class; uniquely
+ * hit records by chromosome id, locus, match length, strand, mismatches; the others by NumHits); ties, which the
+ * reference's unstable quicksort leaves unspecified, go by ascending index.  Host arrays in and out; the sort itself
+ * is two radix passes on `device`. */
+int bkx_sort_hits(const bkx_read_result* results, uint32_t n_reads, uint32_t* order_out, int device);
+
 /* ---- index construction for synthetic / bench genomes: the two halves of `biokanga index` ---------
  * (kangax.cpp:774-926 -> CSfxArrayV3::QSortSeq, SfxArrayV2.cpp:9451-9542; file layout SfxArrayV2.h:79-104,
  * 174-187).  d_seq: device, 1 byte/base incl. one EOS(7) after every entry; d_sa: device, concat_len

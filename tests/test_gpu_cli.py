@@ -126,3 +126,45 @@ def test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path):
     assert _bgzf_blocks(ours) == _bgzf_blocks(ref)
     assert ours == ref
     assert open(str(tmp_path / out) + ".bai", "rb").read() == open(os.path.join(fdir, out + ".bai"), "rb").read()
+
+
+def test_sort_hits_orders_like_the_host_comparator():
+    """bkx_sort_hits (device radix passes) == a host sort on the SortHitMatch key tuple, ties by record index."""
+    import numpy as np
+    from biokanga_b200 import abi
+    rng = np.random.default_rng(5)
+    n = 300_000
+    r = np.zeros(n, dtype=abi.RESULT_DTYPE)
+    r["nar"] = rng.choice([1, 1, 1, 2, 3, 4, 5, 13, 15], n)
+    r["num_hits"] = np.where(r["nar"] == 1, 1, rng.integers(0, 3, n))
+    r["chrom_id"] = rng.integers(1, 40, n)
+    r["match_loci"] = rng.integers(0, 2000, n)          # many ties on purpose
+    r["match_len"] = rng.choice([100, 150], n)
+    r["strand"] = rng.choice([ord("+"), ord("-")], n)
+    r["low_mm"] = rng.integers(0, 4, n)
+    order = bkx.sort_hits(r)
+    uniq = r["num_hits"] == 1
+    keys = np.stack([r["nar"].astype(np.int64), (~uniq).astype(np.int64), np.where(uniq, 0, r["num_hits"]).astype(np.int64),
+                     np.where(uniq, r["chrom_id"], 0).astype(np.int64), np.where(uniq, r["match_loci"], 0).astype(np.int64),
+                     np.where(uniq, r["match_len"], 0).astype(np.int64), np.where(uniq, r["strand"], 0).astype(np.int64),
+                     np.where(uniq, r["low_mm"], 0).astype(np.int64), np.arange(n)], axis=0)
+    exp = np.lexsort(keys[::-1])
+    assert np.array_equal(order, exp.astype(np.uint32))
+
+
+@pytest.mark.parametrize("case,tag", [("tiny", "r100_s3"), ("tiny", "mixed_s3"), ("tiny", "pe_U1"), ("repeats", "r60_s5")])
+def test_cli_chunked_parallel_parse_gives_the_same_files(case, tag, golden_dir, tmp_path):
+    """The read files are split at record boundaries and parsed by several threads; forced here onto tiny files
+    (chunks of ~3 kB, 7 threads): CSV rows identical to the reference's."""
+    run = gu.runs(case)[tag]
+    sfx = gu.sfx_path(case, golden_dir)
+    files = [os.path.join(gu.GOLD, case, f) for f in run["reads"]]
+    base = [CLI, "align", "-I", sfx, "-i", files[0]] + (["-u", files[1]] if len(files) > 1 else []) + run["args"]
+    env = dict(os.environ, BKX_PARSE_MIN_CHUNK="3000")
+    subprocess.run(base + ["-T7", "-M0", "-o", str(tmp_path / "o.csv"), "-F", str(tmp_path / "o.log")], check=True,
+                   stdout=subprocess.DEVNULL, env=env)
+    ours = sorted(open(tmp_path / "o.csv").read().splitlines())
+    ref = sorted(gzip.open(os.path.join(gu.GOLD, case, tag + ".csv.gz"), "rt").read().splitlines())
+    assert ours == ref
+    exp_log = open(os.path.join(gu.GOLD, case, tag + ".log")).read().splitlines()
+    assert summary_block(tmp_path / "o.log") == exp_log
