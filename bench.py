@@ -729,8 +729,15 @@ def run_dropin(args):
     try:
         bkx.write_sfx(os.path.join(tmp, "g.sfx"), host_seq, host_sa, 4, ents, name="synth")
         del host_seq, host_sa
-        write_fasta_fast(os.path.join(tmp, "r.fa"), h_bases[:sample * L].reshape(sample, L), synth.BASES)
-        common = ["align", "-I", "g.sfx", "-i", "r.fa", "-s%d" % args.max_subs, "-M0"]
+        rd = h_bases[:sample * L].reshape(sample, L)
+        if args.workload == "pe":  # PE1 / PE2 of a pair are adjacent in the simulated batch
+            write_fasta_fast(os.path.join(tmp, "r.fa"), rd[0::2], synth.BASES)
+            write_fasta_fast(os.path.join(tmp, "r2.fa"), rd[1::2], synth.BASES)
+            common = ["align", "-I", "g.sfx", "-i", "r.fa", "-u", "r2.fa", "-U%d" % args.pe_mode, "-d%d" % args.pe_min,
+                      "-D%d" % args.pe_max, "-s%d" % args.max_subs, "-M0"]
+        else:
+            write_fasta_fast(os.path.join(tmp, "r.fa"), rd, synth.BASES)
+            common = ["align", "-I", "g.sfx", "-i", "r.fa", "-s%d" % args.max_subs, "-M0"]
         t0 = time.time()
         subprocess.run([po.REF_BIN] + common + ["-o", "ref.csv", "-F", "ref.log", "-T%d" % min(cores, 128)], cwd=tmp,
                        check=True, stdout=subprocess.DEVNULL)
@@ -741,8 +748,9 @@ def run_dropin(args):
         n_ref, md_ref = digest(os.path.join(tmp, "ref.csv"))
         n_bkx, md_bkx = digest(os.path.join(tmp, "bkx.csv"))
         s_ref, s_bkx = summary(os.path.join(tmp, "ref.log")), summary(os.path.join(tmp, "bkx.log"))
-        line = {"dropin": "configs[1] files: %.1f Gbp .sfx (%.1f GB), %d x %d bp reads, -s%d -M0" % (
-                    args.genome_mbp / 1e3, os.path.getsize(os.path.join(tmp, "g.sfx")) / 1e9, sample, L, args.max_subs),
+        line = {"dropin": "%s files: %.1f Gbp .sfx (%.1f GB), %d x %d bp reads, %s" % (
+                    "configs[2] shape" if args.workload == "pe" else "configs[1]", args.genome_mbp / 1e3,
+                    os.path.getsize(os.path.join(tmp, "g.sfx")) / 1e9, sample, L, " ".join(common[6 if args.workload == "pe" else 4:])),
                 "csv_rows": [n_ref, n_bkx], "csv_md5_sorted": [md_ref, md_bkx], "csv_identical": md_ref == md_bkx and n_ref == n_bkx,
                 "summary_lines": [len(s_ref), len(s_bkx)], "summary_identical": s_ref == s_bkx,
                 "wall_s": {"reference": t_ref, "bkx-align": t_bkx, "reference_threads": min(cores, 128)}}
