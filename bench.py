@@ -255,32 +255,50 @@ def run_bkx(args):
     achieved = alg_bytes / (kms / 1e3) / 1e9
     nar = np.bincount(res["nar"], minlength=abi.NAR_COUNT)
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region.  Headline: the 4-bit packed host call
+    # (bkx_align_reads_packed4, the format a loader packs while parsing -- what bkx-align does); the one-byte-per-base
+    # call (the reference's in-memory read layout) is timed beside it.
     h_bases = torch.empty(nreads * args.read_len, dtype=torch.uint8).pin_memory()
     h_bases.copy_(d_bases)
+    h_packed = torch.from_numpy(bkx.pack_bases4(h_bases.numpy())).pin_memory()
     h_offs = (torch.arange(nreads + 1, dtype=torch.int64) * args.read_len).pin_memory()
     h_out = torch.empty(nreads * 32, dtype=torch.uint8).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
     hst = abi.AlignStats()
     h_res_np = h_out.numpy().view(abi.RESULT_DTYPE)
 
-    def e2e_call():
-        idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
+    def e2e_call(packed):
+        if packed:
+            idx.align_packed4_ptr(p, h_packed.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
+        else:
+            idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
         if pe_mode:
             idx.pair(p, pe, h_res_np, h_bases.numpy(), h_offs.numpy().view(np.uint64))
 
-    e2e_call()  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_call()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * nreads / float(te.item())
-    same = bool(np.array_equal(h_out.numpy().view(abi.RESULT_DTYPE)["match_loci"], res["match_loci"]))
+    def time_e2e(packed):
+        e2e_call(packed)  # warm-up
+        barrier()
+        reps = []
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            t1 = time.perf_counter()
+            e2e_call(packed)
+            reps.append(round((time.perf_counter() - t1) * 1e3, 2))
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        log("[bench] e2e %s: per-call ms %s, kernel ms %.2f" % ("packed4" if packed else "bytes", reps, idx.last_kernel_ms()))
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ok = bool(np.array_equal(h_out.numpy().view(abi.RESULT_DTYPE)["match_loci"], res["match_loci"]))
+        return world * nreads / float(te.item()), ok
+
+    e2e_value, same = time_e2e(True)
+    e2e_bytes_value, same_b = time_e2e(False)
+    if os.environ.get("BKX_E2E_AGAIN"):
+        time_e2e(True)
+        time_e2e(False)
+    same = same and same_b
 
     line = {
         "metric": "aligned reads/sec (150bp, <=4 subs)", "value": value, "unit": "reads/s", "n_gpus": world,
@@ -298,8 +316,12 @@ def run_bkx(args):
                    "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (
                        idx.info.device_bytes / 1e9, nreads * args.read_len / 1e9),
                    "parallelism": "reads sharded over %d GPU(s), index replicated" % world},
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(nreads * args.read_len + (nreads + 1) * 8),
-                "d2h_bytes_per_step": int(nreads * 32), "matches_device_run": same},
+        "e2e": {"value": e2e_value, "unit": "reads/s",
+                "h2d_bytes_per_step": int((nreads * args.read_len + 1) // 2 + (nreads + 1) * 8),
+                "d2h_bytes_per_step": int(nreads * 32), "matches_device_run": same,
+                "call": "bkx_align_reads_packed4 (pinned host buffers, reads 4-bit packed)",
+                "byte_per_base_call": {"value": e2e_bytes_value, "call": "bkx_align_reads",
+                                       "h2d_bytes_per_step": int(nreads * args.read_len + (nreads + 1) * 8)}},
         "gpu_launches": int(args.steps * launches_per_step),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(args), "kernel": "align_fast_kernel + align_reads_kernel (deferred reads)",

@@ -44,16 +44,28 @@ int bkx_fail(int code, const char* fmt, ...) {
                                         __FILE__, __LINE__);                                          \
   } while (0)
 
+// Host-buffer calls pipeline slices of reads through this many slots (own stream, staging, cursors, lane hash sets).
+// Three, not two: a slice's general kernel only gets SMs after the NEXT slice's fast kernel (whose blocks move in as
+// this slice's fast blocks retire), so a slice completes one kernel late and two slots would run in lock step.
+constexpr int kSlots = 3;
+// All kernels of the host-buffer calls go down ONE compute stream (bkx_index::cst) in slice order; the slots' own
+// streams only carry their H2D / D2H copies, tied in with events.  (With kernels on the slots' streams the persistent
+// fast kernel of the next slice moves onto the SMs as this slice's fast blocks retire, and this slice's general kernel --
+// stream-ordered behind its fast kernel -- waits a whole kernel for room: measured 72 ms instead of 40 ms per 20 M reads.)
+
 struct Slot {
   cudaStream_t st = nullptr;
   uint8_t* d_bases = nullptr;
   size_t bases_cap = 0;
+  uint8_t* d_packed = nullptr;   // staging for 4-bit packed input (bkx_align_reads_packed4)
+  size_t packed_cap = 0;
   uint64_t* d_offs = nullptr;
   bkx_read_result* d_out = nullptr;
   uint32_t* d_hard = nullptr;   // reads the fast kernel deferred to the general kernel
   size_t hard_cap = 0;
   size_t reads_cap = 0;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
+  cudaEvent_t in_ready = nullptr;   // this slot's H2D copies are done (the compute stream waits on it)
   bool timed = false;
 };
 
@@ -67,14 +79,16 @@ struct bkx_index {
   bkx_index_info info{};
   // runtime workspace
   std::mutex mtx;
-  Slot slot[2];
-  unsigned int* d_cursor[2] = {nullptr, nullptr};   // per slot: [0] fast cursor, [1] general cursor, [2] deferred count
+  Slot slot[kSlots];
+  cudaStream_t cst = nullptr;
+  unsigned int* d_cursor[kSlots] = {};   // per slot: [0] fast cursor, [1] general cursor, [2] deferred count
   int fast_grid = 0;
   int fast_W = 0;
   uint64_t max_len_prepared = 0;
   uint32_t* d_pe_list = nullptr;
   size_t pe_list_cap = 0;
-  uint64_t* fast_hash = nullptr;   // lane-private overflow sets of the fast kernel (fast_grid x 256 lanes x 1024 slots)
+  uint64_t* fast_hash[kSlots] = {};   // per slot (launches of different slots overlap): lane-private overflow sets
+                                      // of the fast kernel, fast_grid x 256 lanes x 1024 slots, allocated on first use
   size_t fast_hash_lanes = 0;
   uint32_t fast_epoch = 1;
   HashPool hp{};
@@ -258,12 +272,14 @@ static int new_index(int device, bkx_index** out) {
   CU(cudaSetDevice(device));
   bkx_index* x = new bkx_index();
   x->device = device;
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kSlots; ++s) {
     CU(cudaStreamCreateWithFlags(&x->slot[s].st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&x->slot[s].k0));
     CU(cudaEventCreate(&x->slot[s].k1));
+    CU(cudaEventCreateWithFlags(&x->slot[s].in_ready, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&x->d_cursor[s], 4 * sizeof(unsigned int)));
   }
+  CU(cudaStreamCreateWithFlags(&x->cst, cudaStreamNonBlocking));
   CU(cudaMalloc((void**)&x->d_stats, sizeof(bkx_align_stats)));
   CU(cudaMalloc((void**)&x->d_pe_stats, sizeof(bkx_pe_stats)));
   *out = x;
@@ -275,16 +291,20 @@ extern "C" void bkx_close_index(bkx_index* x) {
   cudaSetDevice(x->device);
   cudaDeviceSynchronize();
   for (void* p : x->owned) cudaFree(p);
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kSlots; ++s) {
+    if (x->fast_hash[s]) cudaFree(x->fast_hash[s]);
     if (x->slot[s].d_bases) cudaFree(x->slot[s].d_bases);
+    if (x->slot[s].d_packed) cudaFree(x->slot[s].d_packed);
     if (x->slot[s].d_offs) cudaFree(x->slot[s].d_offs);
     if (x->slot[s].d_out) cudaFree(x->slot[s].d_out);
     if (x->slot[s].d_hard) cudaFree(x->slot[s].d_hard);
     if (x->slot[s].k0) cudaEventDestroy(x->slot[s].k0);
     if (x->slot[s].k1) cudaEventDestroy(x->slot[s].k1);
+    if (x->slot[s].in_ready) cudaEventDestroy(x->slot[s].in_ready);
     if (x->slot[s].st) cudaStreamDestroy(x->slot[s].st);
     if (x->d_cursor[s]) cudaFree(x->d_cursor[s]);
   }
+  if (x->cst) cudaStreamDestroy(x->cst);
   if (x->hp.tables) cudaFree(x->hp.tables);
   if (x->hp.locks) cudaFree(x->hp.locks);
   if (x->hp.epochs) cudaFree(x->hp.epochs);
@@ -292,7 +312,6 @@ extern "C" void bkx_close_index(bkx_index* x) {
   if (x->d_pe_stats) cudaFree(x->d_pe_stats);
   if (x->d_len_dist) cudaFree(x->d_len_dist);
   if (x->d_pe_list) cudaFree(x->d_pe_list);
-  if (x->fast_hash) cudaFree(x->fast_hash);
   delete x;
 }
 
@@ -691,11 +710,10 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
       x->fast_W = Wf;
     }
     size_t lanes = (size_t)x->fast_grid * kFastThreads;
-    if (lanes > x->fast_hash_lanes) {
+    if (lanes > x->fast_hash_lanes) {  // grid grew: drop the tables, launch_both re-creates them per slot
       CU(cudaDeviceSynchronize());
-      if (x->fast_hash) { cudaFree(x->fast_hash); x->fast_hash = nullptr; }
-      CU(cudaMalloc((void**)&x->fast_hash, lanes * kFastHashSlots * 8));
-      CU(cudaMemset(x->fast_hash, 0, lanes * kFastHashSlots * 8));
+      for (int s = 0; s < kSlots; ++s)
+        if (x->fast_hash[s]) { cudaFree(x->fast_hash[s]); x->fast_hash[s] = nullptr; }
       x->fast_hash_lanes = lanes;
       x->fast_epoch = 1;
     }
@@ -715,9 +733,14 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     return BKX_OK;
   }
   // every launch gets its own 2^20-wide epoch range for the lane hash sets; wipe them when the 32-bit tag wraps
+  if (!x->fast_hash[si]) {
+    CU(cudaMalloc((void**)&x->fast_hash[si], x->fast_hash_lanes * kFastHashSlots * 8));
+    CU(cudaMemsetAsync(x->fast_hash[si], 0, x->fast_hash_lanes * kFastHashSlots * 8, st));
+  }
   if (x->fast_epoch > 0xfff00000u) {
     CU(cudaDeviceSynchronize());
-    CU(cudaMemset(x->fast_hash, 0, x->fast_hash_lanes * kFastHashSlots * 8));
+    for (int s = 0; s < kSlots; ++s)
+      if (x->fast_hash[s]) CU(cudaMemset(x->fast_hash[s], 0, x->fast_hash_lanes * kFastHashSlots * 8));
     x->fast_epoch = 1;
   }
   uint32_t epoch_base = x->fast_epoch;
@@ -728,7 +751,7 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
     cudaEventRecord(t0, st);
   }
-  CU(launch_align_fast(x->d, k, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash, epoch_base,
+  CU(launch_align_fast(x->d, k, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash[si], epoch_base,
                        x->fast_grid, st));
   if (trace) cudaEventRecord(t1, st);
   CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, d_hard, cur + 2, x->grid, st));
@@ -771,13 +794,13 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
   if ((rc = launch_both(x, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, 0, s.d_hard, st)) < 0) return rc;
   CU(cudaEventRecord(s.k1, st));
   s.timed = true;
-  x->slot[1].timed = false;
+  for (int si = 1; si < kSlots; ++si) x->slot[si].timed = false;
   x->last_ms = -2.f;  // resolved lazily by bkx_last_kernel_ms
   return BKX_OK;
 }
 
-extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
-                               uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
+static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, bool packed4, const uint64_t* offsets,
+                      uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
   if (!x || !bases || !offsets || !out) return fail(BKX_ERR_PARAM, "null argument");
   KParams k;
   int rc = check_params(p, &k);
@@ -788,12 +811,28 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
   int W = 0;
   CU(cudaMemsetAsync(x->d_stats, 0, sizeof(bkx_align_stats), x->slot[0].st));
   CU(cudaStreamSynchronize(x->slot[0].st));
-  const uint32_t kBatchReads = 1u << 20;
-  const uint64_t kBatchBases = 256ull << 20;
+  // Slice sizes: start small (the first H2D is exposed), grow to kMaxSlice (every slice pays ~0.3 ms of persistent-
+  // kernel ramp-up and tail; much larger slices stall on their own H2D), shrink towards the end (the last D2H is
+  // exposed).  Measured on configs[1], 20 M x 150 bp packed: 0.5 M..1.5 M -> 42 ms, fixed 1 M -> 43 ms, 0.125 M..4 M -> 46.5 ms.
+  uint32_t kMinSlice = 1u << 19, kMaxSlice = 3u << 19;
+  if (const char* ev = getenv("BKX_SLICE_READS")) kMinSlice = kMaxSlice = (uint32_t)std::max(1024, atoi(ev));  // tuning hooks
+  if (const char* ev = getenv("BKX_SLICE_MIN")) kMinSlice = (uint32_t)std::max(1024, atoi(ev));
+  if (const char* ev = getenv("BKX_SLICE_MAX")) kMaxSlice = (uint32_t)std::max((int)kMinSlice, atoi(ev));
+  const uint64_t kBatchBases = 1024ull << 20;
+  uint32_t ramp = kMinSlice;
   float ms_total = 0.f;
   uint32_t start = 0;
   int b = 0;
-  bool inflight[2] = {false, false};
+  bool inflight[kSlots] = {};
+  // diagnostic (BKX_TIMELINE=1): device timestamps of every pipeline stage of the first slices
+  static const bool timeline = getenv("BKX_TIMELINE") != nullptr;
+  std::vector<cudaEvent_t> tl;
+  cudaEvent_t tl0 = nullptr;
+  auto mark = [&](cudaStream_t st) {
+    if (!timeline || tl.size() >= 60) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tl.push_back(e);
+  };
+  if (timeline) { cudaEventCreate(&tl0); cudaEventRecord(tl0, x->slot[0].st); }
   auto drain = [&](int si) -> int {
     Slot& s = x->slot[si];
     CU(cudaStreamSynchronize(s.st));
@@ -804,7 +843,10 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
     return BKX_OK;
   };
   while (start < n_reads) {
-    uint32_t cnt = std::min(kBatchReads, n_reads - start);
+    const uint32_t left = n_reads - start;
+    uint32_t cnt = std::min(ramp, std::max(kMinSlice, left / 2));
+    if (cnt > left || left - cnt < kMinSlice / 2) cnt = left;
+    ramp = std::min<uint64_t>(kMaxSlice, (uint64_t)ramp * 2);
     while (cnt > 1 && offsets[start + cnt] - offsets[start] > kBatchBases) cnt = (cnt + 1) / 2;
     uint64_t nb = offsets[start + cnt] - offsets[start];
     // longest read of this slice (overlaps with the GPU work of the previous slices)
@@ -820,7 +862,7 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
     if ((int)((max_len + 31) / 32) + 1 > x->grid_W || x->grid == 0 || x->hp.tables == nullptr ||
         max_len > x->max_len_prepared) {
       // (re)sizing the grid / overflow pool: let the slices in flight finish first
-      for (int si = 0; si < 2; ++si)
+      for (int si = 0; si < kSlots; ++si)
         if (inflight[si] && (rc = drain(si)) < 0) return rc;
       if ((rc = prepare_launch(x, k, (uint32_t)std::min<uint64_t>(max_len, 0xffffffffu), &W)) < 0) return rc;
       x->max_len_prepared = std::max<uint64_t>(x->max_len_prepared, max_len);
@@ -845,22 +887,60 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
       s.hard_cap = (size_t)cnt * 5 / 4;
       CU(cudaMalloc((void**)&s.d_hard, s.hard_cap * 4));
     }
-    CU(cudaMemcpyAsync(s.d_bases, bases + offsets[start], nb, cudaMemcpyHostToDevice, s.st));
+    if (!packed4) {
+      CU(cudaMemcpyAsync(s.d_bases, bases + offsets[start], nb, cudaMemcpyHostToDevice, s.st));
+    } else {
+      // half the PCIe bytes: ship the nibbles, expand to one byte per base on the device (an HBM-speed pass)
+      const uint64_t o0 = offsets[start], o1 = offsets[start + cnt];
+      const uint64_t byte0 = o0 >> 1, nbytes = ((o1 + 1) >> 1) - byte0;
+      if (nbytes + 64 > s.packed_cap) {
+        if (s.d_packed) cudaFree(s.d_packed);
+        s.packed_cap = (size_t)(nbytes + 64) * 5 / 4;
+        CU(cudaMalloc((void**)&s.d_packed, s.packed_cap));
+      }
+      mark(s.st);
+      if (nbytes) CU(cudaMemcpyAsync(s.d_packed, bases + byte0, nbytes, cudaMemcpyHostToDevice, s.st));
+      mark(s.st);
+    }
     CU(cudaMemcpyAsync(s.d_offs, offsets + start, ((size_t)cnt + 1) * 8, cudaMemcpyHostToDevice, s.st));
-    CU(cudaEventRecord(s.k0, s.st));
+    CU(cudaEventRecord(s.in_ready, s.st));
+    CU(cudaStreamWaitEvent(x->cst, s.in_ready, 0));
+    if (packed4 && nb) {
+      CU(launch_unpack4(s.d_packed, (unsigned)(offsets[start] & 1), nb, s.d_bases, x->cst));
+      x->launches += 1;
+    }
+    CU(cudaEventRecord(s.k0, x->cst));
     // offsets stay absolute: hand the kernel a base pointer shifted by the slice start
     if ((rc = launch_both(x, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard,
-                          s.st)) < 0) return rc;
-    CU(cudaEventRecord(s.k1, s.st));
+                          x->cst)) < 0) return rc;
+    CU(cudaEventRecord(s.k1, x->cst));
+    mark(x->cst);
+    CU(cudaStreamWaitEvent(s.st, s.k1, 0));
     CU(cudaMemcpyAsync(out + start, s.d_out, (size_t)cnt * sizeof(bkx_read_result), cudaMemcpyDeviceToHost, s.st));
+    mark(s.st);
     inflight[b] = true;
     start += cnt;
-    b ^= 1;
+    b = (b + 1) % kSlots;
   }
-  for (int si = 0; si < 2; ++si)
+  // drain in submission order (the oldest slice sits in slot b)
+  for (int q = 0; q < kSlots; ++q) {
+    int si = (b + q) % kSlots;
     if (inflight[si] && (rc = drain(si)) < 0) return rc;
+  }
   x->last_ms = ms_total;
-  x->slot[0].timed = x->slot[1].timed = false;
+  for (int si = 0; si < kSlots; ++si) x->slot[si].timed = false;
+  if (timeline) {
+    cudaDeviceSynchronize();
+    fprintf(stderr, "[bkx timeline] ms since call start, per slice: stage marks\n");
+    for (size_t i = 0; i < tl.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tl0, tl[i]);
+      fprintf(stderr, "%s%.2f", (i % 5) ? " " : "\n  ", ms);
+      cudaEventDestroy(tl[i]);
+    }
+    fprintf(stderr, "\n");
+    cudaEventDestroy(tl0);
+  }
   if (stats) {
     bkx_align_stats h;
     CU(cudaMemcpy(&h, x->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
@@ -868,6 +948,23 @@ extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const ui
     const uint64_t* s = (const uint64_t*)&h;
     for (size_t i = 0; i < sizeof(h) / 8; ++i) d[i] += s[i];
   }
+  return BKX_OK;
+}
+
+extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
+                               uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
+  return align_host(x, p, bases, false, offsets, n_reads, out, stats);
+}
+
+extern "C" int bkx_align_reads_packed4(bkx_index* x, const bkx_align_params* p, const uint8_t* packed, const uint64_t* offsets,
+                                       uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
+  return align_host(x, p, packed, true, offsets, n_reads, out, stats);
+}
+
+extern "C" int bkx_pack_bases4(const uint8_t* bases, uint64_t n_bases, uint8_t* packed) {
+  if ((!bases || !packed) && n_bases) return fail(BKX_ERR_PARAM, "null argument");
+  for (uint64_t i = 0; i + 1 < n_bases; i += 2) packed[i >> 1] = (uint8_t)((bases[i] & 0x0f) | (bases[i + 1] << 4));
+  if (n_bases & 1) packed[n_bases >> 1] = (uint8_t)(bases[n_bases - 1] & 0x0f);
   return BKX_OK;
 }
 

@@ -111,6 +111,31 @@ cudaError_t launch_pack_genome(const uint8_t* seq, uint64_t n, uint64_t* g2, uin
   return cudaGetLastError();
 }
 
+// 4-bit packed reads (base 2i in the low nibble of byte i) -> one byte per base; `phase` = 1 when the first wanted
+// base sits in a high nibble.  Four bases (one u32 store) per thread.
+__global__ void unpack4_kernel(const uint8_t* __restrict__ packed, unsigned phase, uint64_t n, uint8_t* __restrict__ out) {
+  const uint64_t quads = (n + 3) >> 2;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t j = 4 * q + phase;  // nibble index of the first base of this quad
+    const uint64_t b = j >> 1;
+    uint32_t w = (uint32_t)__ldg(packed + b) | ((uint32_t)__ldg(packed + b + 1) << 8) | ((uint32_t)__ldg(packed + b + 2) << 16);
+    w >>= (j & 1) * 4;
+    const uint32_t v = (w & 0xf) | ((w & 0xf0) << 4) | ((w & 0xf00) << 8) | ((w & 0xf000) << 12);
+    if (4 * q + 4 <= n) {
+      *(uint32_t*)(out + 4 * q) = v;
+    } else {
+      for (uint64_t i = 4 * q; i < n; ++i) out[i] = (uint8_t)(v >> (8 * (i - 4 * q)));
+    }
+  }
+}
+
+cudaError_t launch_unpack4(const uint8_t* packed, unsigned phase, uint64_t n_bases, uint8_t* out, cudaStream_t st) {
+  const uint64_t quads = (n_bases + 3) >> 2;
+  int grid = (int)std::min<uint64_t>((quads + 255) / 256, 148 * 16);
+  unpack4_kernel<<<grid, 256, 0, st>>>(packed, phase, n_bases, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_split_sa5(const uint8_t* sa5, uint64_t n, uint32_t* lo, uint8_t* hi, cudaStream_t st) {
   split_sa5_kernel<<<148 * 8, 256, 0, st>>>(sa5, n, lo, hi);
   return cudaGetLastError();

@@ -58,6 +58,7 @@ static void diag(const char* fmt, ...) {  // CDiagnostics::DiagOut format: "[Mon
 
 // ---- read ingest ---------------------------------------------------------------------------------
 struct Reads {
+  std::vector<uint8_t> packed;    // the same bases 4-bit packed (what crosses PCIe): base i in nibble i & 1 of byte i / 2
   std::vector<uint8_t> bases;     // 1 byte/base, etSeqBase code in the low 3 bits
   std::vector<uint64_t> offs{0};
   std::vector<char> names;        // NUL-terminated descriptors, back to back
@@ -362,6 +363,21 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
     diag("LoadReads: Total of %1.9d reads parsed and loaded from %s", accepted, o.in[fi].c_str());
     if (under) diag("Load: total of %d under length sequences sloughed from file '%s'", under, o.in[fi].c_str());
     if (over) diag("Load: total of %d over length sequences sloughed from file '%s'", over, o.in[fi].c_str());
+  }
+  {  // nibble-packed copy for the H2D stream; threads own disjoint byte ranges of the packed array
+    const size_t nb = R.bases.size(), np = (nb + 1) / 2;
+    R.packed.resize(np);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+      th.emplace_back([&, t]() {
+        size_t b = np * t / T, e = np * (t + 1) / T;
+        const uint8_t* src = R.bases.data();
+        for (size_t i = b; i < e; ++i) {
+          uint8_t lo = src[2 * i] & 0x0f, hi = 2 * i + 1 < nb ? (uint8_t)(src[2 * i + 1] & 0x0f) : 0;
+          R.packed[i] = (uint8_t)(lo | (hi << 4));
+        }
+      });
+    for (auto& x : th) x.join();
   }
   return 0;
 }
@@ -679,7 +695,7 @@ int main(int argc, char** argv) {
   // ---- align: contiguous, even-sized read ranges, one host thread per GPU (reads shard with no exchange)
   std::vector<bkx_read_result> res(n);
   // page-lock the read arena and the record array: H2D / D2H then stream asynchronously, double buffered
-  bool pinned = bkx_pin_host(R.bases.data(), R.bases.size()) >= 0 && bkx_pin_host(R.offs.data(), R.offs.size() * 8) >= 0 &&
+  bool pinned = bkx_pin_host(R.packed.data(), R.packed.size()) >= 0 && bkx_pin_host(R.offs.data(), R.offs.size() * 8) >= 0 &&
                 bkx_pin_host(res.data(), res.size() * sizeof(bkx_read_result)) >= 0;
   if (!pinned) diag("Note: unable to page-lock host buffers (%s); continuing with pageable copies", bkx_last_error());
   std::vector<bkx_align_stats> st((size_t)o.gpus);
@@ -693,7 +709,8 @@ int main(int argc, char** argv) {
       memset(&st[(size_t)g], 0, sizeof(bkx_align_stats));
       th.emplace_back([&, g, b, e]() {
         if (e > b) {
-          rcs[(size_t)g] = bkx_align_reads(idx[(size_t)g], &P, R.bases.data(), R.offs.data() + b, e - b, res.data() + b, &st[(size_t)g]);
+          rcs[(size_t)g] = bkx_align_reads_packed4(idx[(size_t)g], &P, R.packed.data(), R.offs.data() + b, e - b, res.data() + b,
+                                                   &st[(size_t)g]);
           if (rcs[(size_t)g] < 0) errs[(size_t)g] = bkx_last_error();
         }
       });
@@ -708,7 +725,7 @@ int main(int argc, char** argv) {
     const uint64_t* s = (const uint64_t*)&st[(size_t)g];
     for (size_t k = 0; k < sizeof(S) / 8; ++k) d[k] += s[k];
   }
-  bkx_unpin_host(R.bases.data()); bkx_unpin_host(R.offs.data()); bkx_unpin_host(res.data());
+  bkx_unpin_host(R.packed.data()); bkx_unpin_host(R.offs.data()); bkx_unpin_host(res.data());
   diag("Alignment of %u from %u loaded completed", n, n);
 
   // ---- read-length summary, Aligner.cpp:486-535

@@ -23,7 +23,8 @@ EXPORTS = [
     "bkx_get_ident", "bkx_get_seq", "bkx_default_params", "bkx_align_reads", "bkx_align_reads_device",
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
-    "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits",
+    "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
+    "bkx_pack_bases4",
 ]
 
 
@@ -62,6 +63,8 @@ def lib():
     L.bkx_open_index_planes.argtypes = [vp, u64, vp, vp, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_build_suffix_array_planes.argtypes = [vp, u64, vp, vp, i32, u64]
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
+    L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
+    L.bkx_pack_bases4.argtypes = [vp, u64, vp]
     L.bkx_clone_index.argtypes = [vp, i32, C.POINTER(vp)]
     L.bkx_close_index.argtypes = [vp]
     L.bkx_close_index.restype = None
@@ -105,6 +108,14 @@ def build_suffix_array_device(d_seq_ptr, concat_len, d_sa_ptr, device=0):
 def build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr=None, device=0, max_batch=0):
     """Bounded-memory builder for any size (the one for >= 4e9 symbols): u32 low plane + u8 high plane out."""
     check(lib().bkx_build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, device, max_batch))
+
+
+def pack_bases4(bases):
+    """One-byte base codes -> 4-bit packed (two bases per byte, even base in the low nibble)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    out = np.zeros((bases.size + 1) // 2, dtype=np.uint8)
+    check(lib().bkx_pack_bases4(bases.ctypes.data, bases.size, out.ctypes.data))
+    return out
 
 
 def sort_hits(results, device=0):
@@ -217,6 +228,19 @@ class Index:
         """Same, raw host pointers (pinned buffers owned by the caller)."""
         st = C.byref(stats) if stats is not None else None
         check(lib().bkx_align_reads(self._h, C.byref(params), bases_ptr, offsets_ptr, n_reads, out_ptr, st))
+
+    def align_packed4_ptr(self, params, packed_ptr, offsets_ptr, n_reads, out_ptr, stats=None):
+        """Host buffers with the reads 4-bit packed (see pack_bases4); offsets count bases."""
+        st = C.byref(stats) if stats is not None else None
+        check(lib().bkx_align_reads_packed4(self._h, C.byref(params), packed_ptr, offsets_ptr, n_reads, out_ptr, st))
+
+    def align_packed4(self, params, packed, offsets):
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = np.zeros(len(offsets) - 1, dtype=abi.RESULT_DTYPE)
+        st = abi.AlignStats()
+        self.align_packed4_ptr(params, packed.ctypes.data, offsets.ctypes.data, len(offsets) - 1, out.ctypes.data, st)
+        return out, st
 
     def align_device(self, params, d_bases, d_offsets, n_reads, max_read_len, d_out, d_stats=None, stream=None):
         """Device pointers, asynchronous on `stream` (a raw cudaStream_t value or None)."""

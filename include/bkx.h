@@ -200,6 +200,14 @@ int bkx_default_params(const bkx_index* idx, int pmode, bkx_align_params* out);
  * own streams, double buffered; returns when `out[0..n_reads)` is complete. */
 int bkx_align_reads(bkx_index* idx, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
                     uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats /* may be NULL; accumulated */);
+/* Same call with the reads 4-bit packed on the host: base i of the concatenation in the low (i even) or high (i odd)
+ * nibble of byte i/2, reads back to back at nibble granularity, offsets still counted in BASES.  Halves the bytes
+ * that cross PCIe (and the host-memory traffic of an 8-GPU node); the nibbles are expanded on the device.  Nibble
+ * values are etSeqBase codes 0..4; anything above counts as an N-class symbol.  bkx_pack_bases4 packs n_bases
+ * one-byte codes (low 4 bits kept) into (n_bases + 1) / 2 bytes -- the loop a loader would fuse into its parser. */
+int bkx_align_reads_packed4(bkx_index* idx, const bkx_align_params* params, const uint8_t* packed, const uint64_t* offsets,
+                            uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats);
+int bkx_pack_bases4(const uint8_t* bases, uint64_t n_bases, uint8_t* packed);
 /* Device variant: all pointers are device pointers on idx's GPU; asynchronous on `cuda_stream`
  * (a cudaStream_t, NULL = the index's compute stream).  d_stats (device, may be NULL) is accumulated. */
 int bkx_align_reads_device(bkx_index* idx, const bkx_align_params* p, const uint8_t* d_bases,

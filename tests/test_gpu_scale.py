@@ -92,3 +92,29 @@ def test_long_and_ragged_reads_take_the_general_kernel(world):
     exp, _ = oidx.align(oidx.default_params(0, max_subs=5), bases, offs, nthreads=8)
     for f in abi.RESULT_DTYPE.names:
         assert np.array_equal(got[f], exp[f]), f
+
+
+def test_packed4_host_call_equals_byte_per_base_call(world):
+    """bkx_align_reads_packed4: 1.1 M ragged reads of odd and even lengths (so slices of the internal pipeline start on
+    both nibble phases) give the records of the one-byte-per-base call, bit for bit."""
+    gidx, oidx, d_bases, d_offs, seq = world
+    rng = np.random.default_rng(11)
+    n = 1_100_000
+    lens = rng.choice([51, 64, 75, 100, 33], n).astype(np.uint64)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    ents = oidx.entries()
+    e = ents[0]
+    starts = rng.integers(e.start_ofs, e.start_ofs + e.seq_len - 200, n)
+    total = int(offs[-1])
+    idx = np.repeat(starts - offs[:-1].astype(np.int64), lens.astype(np.int64)) + np.arange(total)
+    bases = seq[idx].copy()
+    flip = rng.random(total) < 0.01
+    bases[flip] = (bases[flip] + 1) & 3
+    p = gidx.default_params(0, max_subs=3)
+    a, sa_ = gidx.align(p, bases, offs)
+    packed = bkx.pack_bases4(bases)
+    assert packed.size == (total + 1) // 2
+    b, sb_ = gidx.align_packed4(p, packed, offs)
+    assert a.tobytes() == b.tobytes() and sa_.as_dict() == sb_.as_dict()
+    assert (a["nar"] == abi.NAR_ACCEPTED).mean() > 0.5
