@@ -39,7 +39,56 @@ constexpr int kGroup = 8;            // lanes per read
 
 struct KParams {
   int max_subs, mmd, max_ns, strand_mode, max_hits, min_core_len, slides_per100, max_iter, max_nodes;
+  int ml_mode, clamp_ml;
 };
+
+// What ProcCoredApprox stores for one read once AlignReads has returned (Aligner.cpp:9239-9245, 9310-9479): shared by
+// both kernels.  `inst`, `low`, `nxt` are the search state, the hit_* values describe the first hit found at `low`.
+static __device__ __noinline__ bkx_read_result make_result(const DevIndex& I, const KParams& P, int hr, int inst, int low,
+                                                       int nxt, int L, int hit_strand, int hit_ent, uint64_t hit_p,
+                                                       int hit_mm, uint32_t seeds, uint32_t cands) {
+  bkx_read_result res;
+  res.nar = BKX_NAR_NOHIT; res.strand = 0; res.num_hits = 0; res.low_mm = 0; res.nxt_low_mm = 0;
+  res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0; res.mismatches = 0;
+  res.flags = 0; res.seeds = seeds; res.cands = cands; res.reserved = 0;
+  if (inst > P.max_hits) inst = P.max_hits + 1;                                   // :9241
+  if (P.clamp_ml && hr == BKX_HR_HITINSTS) { inst = P.max_hits; hr = BKX_HR_HITS; }  // :9243
+  res.hit_rslt = (uint8_t)hr;
+  switch (hr) {
+    case BKX_HR_HITS:
+      if (inst == 1 || P.ml_mode != BKX_ML_DIST) {  // a unique hit (or, outside -r1, the first of several)
+        res.nar = BKX_NAR_ACCEPTED;
+        res.num_hits = 1;
+        res.strand = hit_strand ? '-' : '+';
+        res.chrom_id = __ldg(I.ent_id + hit_ent);
+        res.match_loci = (uint32_t)(hit_p - __ldg(I.ent_start + hit_ent));
+        res.match_len = (uint16_t)L;
+        res.mismatches = (uint8_t)hit_mm;
+        res.low_hit_instances = 1;
+      } else {                                      // -r1: counted, not placed (:9383-9386)
+        res.nar = BKX_NAR_MULTIALIGN;
+        res.low_hit_instances = (int16_t)inst;
+      }
+      res.low_mm = (int8_t)low;
+      res.nxt_low_mm = (int8_t)nxt;
+      break;
+    case BKX_HR_MMDELTA:
+    case BKX_HR_HITINSTS:
+      res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
+      res.strand = '?';
+      res.match_len = (uint16_t)L;
+      res.low_hit_instances = (int16_t)inst;
+      res.low_mm = (int8_t)low;
+      res.nxt_low_mm = (int8_t)nxt;
+      break;
+    case BKX_HR_RMMDELTA:
+      res.nxt_low_mm = (int8_t)nxt;
+      break;
+    default:
+      break;
+  }
+  return res;
+}
 
 // overflow hash sets for groups whose strand/phase sees more than kSeenCap keys (high-copy repeats)
 struct HashPool {

@@ -654,8 +654,14 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   if (p->min_edit_dist < 1 || p->min_edit_dist > 2) return fail(BKX_ERR_PARAM, "min_edit_dist %d out of range 1..2", p->min_edit_dist);
   if (p->max_ns < 0 || p->max_ns > 5) return fail(BKX_ERR_PARAM, "max_ns %d out of range 0..5", p->max_ns);
   if (p->align_strand < 0 || p->align_strand > 2) return fail(BKX_ERR_PARAM, "bad align_strand %d", p->align_strand);
-  if (p->max_ml_matches != 1)
-    return fail(BKX_ERR_UNSUPPORTED, "max_ml_matches %d: multi-loci modes (-r/-R) are not built yet", p->max_ml_matches);
+  if (p->ml_mode == BKX_ML_DEFAULT) {
+    if (p->max_ml_matches != 1) return fail(BKX_ERR_PARAM, "max_ml_matches %d needs a multi-loci mode (ml_mode)", p->max_ml_matches);
+  } else if (p->ml_mode == BKX_ML_DIST) {
+    if (p->max_ml_matches < 2 || p->max_ml_matches > 500)  // cMaxMultiHits, Aligner.h:62
+      return fail(BKX_ERR_PARAM, "max_ml_matches %d out of range 2..500", p->max_ml_matches);
+  } else {
+    return fail(BKX_ERR_UNSUPPORTED, "ml_mode %d: only -r0 and -r1 are built (-r2 is not reproducible, -r3..5 are not built yet)", p->ml_mode);
+  }
   if (p->min_core_len < 4 || p->min_core_len > 100) return fail(BKX_ERR_PARAM, "bad min_core_len %d", p->min_core_len);
   if (p->max_num_slides < 1 || p->max_num_slides > 16) return fail(BKX_ERR_PARAM, "bad max_num_slides %d", p->max_num_slides);
   if (p->max_iter <= 100) return fail(BKX_ERR_PARAM, "max_iter %d must exceed 100", p->max_iter);
@@ -663,6 +669,7 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   k->max_subs = p->max_subs; k->mmd = p->min_edit_dist; k->max_ns = p->max_ns; k->strand_mode = p->align_strand;
   k->max_hits = p->max_ml_matches; k->min_core_len = p->min_core_len; k->slides_per100 = p->max_num_slides;
   k->max_iter = p->max_iter; k->max_nodes = p->max_ident_nodes;
+  k->ml_mode = p->ml_mode; k->clamp_ml = p->clamp_max_ml ? 1 : 0;
   return BKX_OK;
 }
 

@@ -192,7 +192,7 @@ static cudaError_t ensure_smem(K kernel, size_t smem, size_t& configured) {
   }
   return cudaSuccess;
 }
-static size_t g_smem_general = 0, g_smem_fast = 0;
+static size_t g_smem_general = 0, g_smem_fast = 0, g_smem_fast_mlx = 0;
 
 __host__ __device__ inline size_t group_smem_bytes(int W) {
   size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + (kGroup + 2) * 4;
@@ -203,8 +203,47 @@ size_t align_smem_bytes(int W) { return group_smem_bytes(W) * kGroupsPerBlock; }
 struct BlockStats {
   unsigned int nar[BKX_NAR_COUNT];
   unsigned int plus, minus;
+  unsigned int multi, multi_loci;   // -r1: reads whose search ended eHRhits with several loci, and the sum of those loci
   unsigned long long seeds, cands;
 };
+
+__device__ __forceinline__ void stats_add_basic(BlockStats& bs, const bkx_read_result& res) {
+  atomicAdd(&bs.nar[res.nar], 1u);
+  if (res.nar == BKX_NAR_ACCEPTED) atomicAdd(res.strand == '+' ? &bs.plus : &bs.minus, 1u);
+  atomicAdd(&bs.seeds, (unsigned long long)res.seeds);
+  atomicAdd(&bs.cands, (unsigned long long)res.cands);
+}
+__device__ __forceinline__ void stats_add(BlockStats& bs, const bkx_read_result& res) {
+  stats_add_basic(bs, res);
+  if (res.nar == BKX_NAR_MULTIALIGN && res.hit_rslt == BKX_HR_HITS) {
+    atomicAdd(&bs.multi, 1u);
+    atomicAdd(&bs.multi_loci, (unsigned int)res.low_hit_instances);
+  }
+}
+
+// the per-thread counters ProcCoredApprox merges at Aligner.cpp:9507-9516
+__device__ __forceinline__ void stats_flush(const BlockStats& bs, bkx_align_stats* stats) {
+  for (int i = threadIdx.x; i < BKX_NAR_COUNT; i += blockDim.x)
+    if (bs.nar[i]) atomicAdd((unsigned long long*)&stats->nar[i], (unsigned long long)bs.nar[i]);
+  if (threadIdx.x == 0) {
+    unsigned long long reads = 0;
+    for (int i = 0; i < BKX_NAR_COUNT; ++i) reads += bs.nar[i];
+    const unsigned long long acc = bs.nar[BKX_NAR_ACCEPTED];
+    atomicAdd((unsigned long long*)&stats->plus_hits, (unsigned long long)bs.plus);
+    atomicAdd((unsigned long long*)&stats->minus_hits, (unsigned long long)bs.minus);
+    atomicAdd((unsigned long long*)&stats->num_sloughed_ns, (unsigned long long)bs.nar[BKX_NAR_NS]);
+    atomicAdd((unsigned long long*)&stats->tot_non_aligned,
+              (unsigned long long)bs.nar[BKX_NAR_NOHIT] + bs.nar[BKX_NAR_MULTIALIGN] - bs.multi);
+    atomicAdd((unsigned long long*)&stats->tot_accepted_unique, acc);
+    atomicAdd((unsigned long long*)&stats->tot_accepted_multi, (unsigned long long)bs.multi);
+    atomicAdd((unsigned long long*)&stats->tot_accepted_aligned, acc + bs.multi);
+    atomicAdd((unsigned long long*)&stats->tot_loci_aligned, acc + bs.multi_loci);
+    atomicAdd((unsigned long long*)&stats->tot_not_accepted_delta, (unsigned long long)bs.nar[BKX_NAR_MMDELTA]);
+    atomicAdd((unsigned long long*)&stats->seeds, bs.seeds);
+    atomicAdd((unsigned long long*)&stats->cands, bs.cands);
+    atomicAdd((unsigned long long*)&stats->reads, reads);
+  }
+}
 
 // Per-read driver: ProcCoredApprox body (Aligner.cpp:9027-9504) + AlignReads phase loop
 // (SfxArrayV2.cpp:7666-7760).  One kGroup-lane group per read; reads are claimed from a global cursor.
@@ -305,70 +344,16 @@ __global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
         }
       }
       if (hr == 0 && allow <= max_tot_mm) hr = run_phase<G>(I, P, hp, c, max_tot_mm, core_len, core_delta, slides);
-      int inst = c.inst;
-      if (inst > P.max_hits) inst = P.max_hits + 1;  // Aligner.cpp:9241
-      res.hit_rslt = (uint8_t)hr;
-      res.seeds = c.seeds;
-      res.cands = c.cands;
-      switch (hr) {
-        case BKX_HR_HITS:
-          res.nar = BKX_NAR_ACCEPTED;
-          res.num_hits = 1;
-          res.strand = c.hit_strand ? '-' : '+';
-          res.chrom_id = __ldg(I.ent_id + c.hit_ent);
-          res.match_loci = (uint32_t)(c.hit_p - __ldg(I.ent_start + c.hit_ent));
-          res.match_len = (uint16_t)L;
-          res.mismatches = (uint8_t)c.hit_mm;
-          res.low_hit_instances = 1;
-          res.low_mm = (int8_t)c.low;
-          res.nxt_low_mm = (int8_t)c.nxt;
-          break;
-        case BKX_HR_MMDELTA:
-        case BKX_HR_HITINSTS:
-          res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
-          res.strand = '?';
-          res.match_len = (uint16_t)L;
-          res.low_hit_instances = (int16_t)inst;
-          res.low_mm = (int8_t)c.low;
-          res.nxt_low_mm = (int8_t)c.nxt;
-          break;
-        case BKX_HR_RMMDELTA:
-          res.nxt_low_mm = (int8_t)c.nxt;
-          break;
-        default:
-          break;
-      }
+      res = make_result(I, P, hr, c.inst, c.low, c.nxt, L, c.hit_strand, c.hit_ent, c.hit_p, c.hit_mm, c.seeds, c.cands);
     }
     if (c.gl == 0) {
       out[r] = res;
-      atomicAdd(&bs.nar[res.nar], 1u);
-      if (res.nar == BKX_NAR_ACCEPTED) atomicAdd(res.strand == '+' ? &bs.plus : &bs.minus, 1u);
-      atomicAdd(&bs.seeds, (unsigned long long)res.seeds);
-      atomicAdd(&bs.cands, (unsigned long long)res.cands);
+      stats_add(bs, res);
     }
     c.sync();
   }
   __syncthreads();
-  if (stats) {
-    for (int i = threadIdx.x; i < BKX_NAR_COUNT; i += blockDim.x)
-      if (bs.nar[i]) atomicAdd((unsigned long long*)&stats->nar[i], (unsigned long long)bs.nar[i]);
-    if (threadIdx.x == 0) {
-      unsigned long long reads = 0;
-      for (int i = 0; i < BKX_NAR_COUNT; ++i) reads += bs.nar[i];
-      atomicAdd((unsigned long long*)&stats->plus_hits, (unsigned long long)bs.plus);
-      atomicAdd((unsigned long long*)&stats->minus_hits, (unsigned long long)bs.minus);
-      atomicAdd((unsigned long long*)&stats->num_sloughed_ns, (unsigned long long)bs.nar[BKX_NAR_NS]);
-      atomicAdd((unsigned long long*)&stats->tot_non_aligned,
-                (unsigned long long)bs.nar[BKX_NAR_NOHIT] + bs.nar[BKX_NAR_MULTIALIGN]);
-      atomicAdd((unsigned long long*)&stats->tot_accepted_unique, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
-      atomicAdd((unsigned long long*)&stats->tot_accepted_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
-      atomicAdd((unsigned long long*)&stats->tot_loci_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
-      atomicAdd((unsigned long long*)&stats->tot_not_accepted_delta, (unsigned long long)bs.nar[BKX_NAR_MMDELTA]);
-      atomicAdd((unsigned long long*)&stats->seeds, bs.seeds);
-      atomicAdd((unsigned long long*)&stats->cands, bs.cands);
-      atomicAdd((unsigned long long*)&stats->reads, reads);
-    }
-  }
+  if (stats) stats_flush(bs, stats);
 }
 
 cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
@@ -395,34 +380,6 @@ int align_blocks_per_sm(int W) {
 // ------------------------------------------------------------------------------------------------
 // Fast path: one lane per read (see bkx_fast.cuh)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stats_add(BlockStats& bs, const bkx_read_result& res) {
-  atomicAdd(&bs.nar[res.nar], 1u);
-  if (res.nar == BKX_NAR_ACCEPTED) atomicAdd(res.strand == '+' ? &bs.plus : &bs.minus, 1u);
-  atomicAdd(&bs.seeds, (unsigned long long)res.seeds);
-  atomicAdd(&bs.cands, (unsigned long long)res.cands);
-}
-
-__device__ __forceinline__ void stats_flush(const BlockStats& bs, bkx_align_stats* stats) {
-  for (int i = threadIdx.x; i < BKX_NAR_COUNT; i += blockDim.x)
-    if (bs.nar[i]) atomicAdd((unsigned long long*)&stats->nar[i], (unsigned long long)bs.nar[i]);
-  if (threadIdx.x == 0) {
-    unsigned long long reads = 0;
-    for (int i = 0; i < BKX_NAR_COUNT; ++i) reads += bs.nar[i];
-    atomicAdd((unsigned long long*)&stats->plus_hits, (unsigned long long)bs.plus);
-    atomicAdd((unsigned long long*)&stats->minus_hits, (unsigned long long)bs.minus);
-    atomicAdd((unsigned long long*)&stats->num_sloughed_ns, (unsigned long long)bs.nar[BKX_NAR_NS]);
-    atomicAdd((unsigned long long*)&stats->tot_non_aligned,
-              (unsigned long long)bs.nar[BKX_NAR_NOHIT] + bs.nar[BKX_NAR_MULTIALIGN]);
-    atomicAdd((unsigned long long*)&stats->tot_accepted_unique, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
-    atomicAdd((unsigned long long*)&stats->tot_accepted_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
-    atomicAdd((unsigned long long*)&stats->tot_loci_aligned, (unsigned long long)bs.nar[BKX_NAR_ACCEPTED]);
-    atomicAdd((unsigned long long*)&stats->tot_not_accepted_delta, (unsigned long long)bs.nar[BKX_NAR_MMDELTA]);
-    atomicAdd((unsigned long long*)&stats->seeds, bs.seeds);
-    atomicAdd((unsigned long long*)&stats->cands, bs.cands);
-    atomicAdd((unsigned long long*)&stats->reads, reads);
-  }
-}
-
 // Lane-private overflow set of the fast kernel: kFastHashSlots (epoch << 32 | key) slots per lane in HBM, open
 // addressing, emptied by moving to a fresh epoch.  Kept out of line: only reads with many candidate loci get here.
 __device__ __forceinline__ uint64_t* fh_table(uint64_t* lane_hash) {
@@ -445,6 +402,9 @@ __device__ __noinline__ void fh_spill(uint64_t* lane_hash, uint32_t epoch, const
   fh_test_insert(lane_hash, epoch, key);
 }
 
+// MLX: any multi-loci option (-r1 / -X) is on.  A template parameter, not a run-time test: letting the result code vary
+// at run time inside finish() costs the default instantiation its spill-free 64-register allocation (-3 % reads/s).
+template <bool MLX>
 __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
@@ -512,13 +472,19 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     return true;
   };
 
-  auto finish = [&](int hr) {
+  auto finish = [&](int hr) {  // same mapping as make_result (bkx_align.cuh), kept inline: a call here costs 12 % of the kernel
     bkx_read_result res;
-    res.nar = BKX_NAR_NOHIT; res.hit_rslt = (uint8_t)hr; res.strand = 0; res.num_hits = 0; res.low_mm = 0;
+    res.nar = BKX_NAR_NOHIT; res.strand = 0; res.num_hits = 0; res.low_mm = 0;
     res.nxt_low_mm = 0; res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0;
     res.mismatches = 0; res.flags = 0; res.seeds = seeds; res.cands = cands; res.reserved = 0;
     int ii = inst > P.max_hits ? P.max_hits + 1 : inst;
-    if (hr == BKX_HR_HITS) {
+    bool multi = false;
+    if constexpr (MLX) {
+      if (P.clamp_ml && hr == BKX_HR_HITINSTS) { ii = P.max_hits; hr = BKX_HR_HITS; }
+      multi = hr == BKX_HR_HITS && ii > 1 && P.ml_mode == BKX_ML_DIST;
+    }
+    res.hit_rslt = (uint8_t)hr;
+    if (hr == BKX_HR_HITS && !multi) {
       res.nar = BKX_NAR_ACCEPTED;
       res.num_hits = 1;
       res.strand = hit_strand ? '-' : '+';
@@ -529,16 +495,16 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
       res.low_hit_instances = 1;
       res.low_mm = (int8_t)low;
       res.nxt_low_mm = (int8_t)nxt;
-    } else if (hr == BKX_HR_MMDELTA || hr == BKX_HR_HITINSTS) {
+    } else if (hr == BKX_HR_MMDELTA || hr == BKX_HR_HITINSTS || hr == BKX_HR_HITS) {
       res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
-      res.strand = '?';
-      res.match_len = (uint16_t)L;
+      if (!multi) { res.strand = '?'; res.match_len = (uint16_t)L; }
       res.low_hit_instances = (int16_t)ii;
       res.low_mm = (int8_t)low;
       res.nxt_low_mm = (int8_t)nxt;
+      if (multi) { atomicAdd(&bs.multi, 1u); atomicAdd(&bs.multi_loci, (unsigned int)ii); }
     }
     out[r] = res;
-    stats_add(bs, res);
+    stats_add_basic(bs, res);
     active = false;
   };
 
@@ -623,7 +589,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
           res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0; res.mismatches = 0;
           res.flags = 0; res.seeds = 0; res.cands = 0; res.reserved = 0;
           out[r] = res;
-          stats_add(bs, res);
+          stats_add_basic(bs, res);
           active = false;
         } else if (nN > 0) {
           defer();  // N-bearing reads need the symbol-wise compare of the general kernel
@@ -812,23 +778,31 @@ cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t
                               unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, uint64_t* lane_hash,
                               uint32_t epoch_base, int grid, cudaStream_t st) {
   size_t smem = fast_smem_bytes(W);
-  cudaError_t e = ensure_smem(align_fast_kernel, smem, g_smem_fast);
+  const bool mlx = P.ml_mode != 0 || P.clamp_ml != 0;
+  cudaError_t e = mlx ? ensure_smem(align_fast_kernel<true>, smem, g_smem_fast_mlx)
+                      : ensure_smem(align_fast_kernel<false>, smem, g_smem_fast);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(n_hard, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
-  align_fast_kernel<<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids, n_hard,
-                                                      lane_hash, epoch_base);
+  if (mlx)
+    align_fast_kernel<true><<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids,
+                                                              n_hard, lane_hash, epoch_base);
+  else
+    align_fast_kernel<false><<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids,
+                                                               n_hard, lane_hash, epoch_base);
   return cudaGetLastError();
 }
 
 int fast_blocks_per_sm(int W) {
   size_t smem = fast_smem_bytes(W);
-  ensure_smem(align_fast_kernel, smem, g_smem_fast);
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_fast_kernel, kFastThreads, smem);
-  return nb;
+  ensure_smem(align_fast_kernel<false>, smem, g_smem_fast);
+  ensure_smem(align_fast_kernel<true>, smem, g_smem_fast_mlx);
+  int nb = 0, nb2 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_fast_kernel<false>, kFastThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, align_fast_kernel<true>, kFastThreads, smem);
+  return nb < nb2 ? nb : nb2;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@
 //                     CSAMfile::AddAlignment (text form)  libbiokanga/SAMfile.cpp:2100-2262
 //   summary           CAligner::ReportAlignStats          Aligner.cpp:3493-3822
 // Written from the behaviour of those functions; no reference code is reused.  Options of the
-// reference that select paths outside SURVEY section 8 (-r/-R multi-loci modes, -c chimeric, -a/-A indel and
+// reference that select paths outside SURVEY section 8 (-r2..5 multi-loci modes, -c chimeric, -a/-A indel and
 // splice, -p SNP calling, -k PCR dedup, -x flank trimming, -Z/-z filters, -5 constraints, -H contaminants,
 // -b/-C bisulfite/SOLiD) are recognised and rejected with a clear message.  Output formats: CSV -M0..3, BED -M4,
 // SAM -M5/-M6 (gzip when the name ends in .gz), BAM + BAI when the name ends in .bam (kanga.cpp:849-857).
@@ -105,6 +105,8 @@ struct Opts {
   int pmode = 0, strand = 0, max_subs = 10, edit_delta = 1, max_ns = 1, fmt = 5, pe_mode = 0, pair_min = 100,
       pair_max = 1000, trim5 = 0, trim3 = 0, min_len = 50, max_len = 500, threads = 0, gpus = 1, sam_seq_thres = 10000,
       qmode = 3;
+  int ml_mode = 0, max_ml = 0;   // -r / -R (kanga.cpp:482-486, 667-696); max_ml 0 = not given
+  bool clamp_ml = false;         // -X
   bool pair_strand = false, pe_circ = false;
   std::vector<std::string> in, pair;
   std::string sfx, out, logfile, title;
@@ -429,8 +431,8 @@ static int parse(int argc, char** argv, Opts& o) {
       case 't': o.title = v; break;
       case 'g': o.qmode = iv; break;
       case '#': if (iv != 1) unsupported.push_back("-# read sampling"); break;
-      case 'r': if (iv != 0) unsupported.push_back("-r multi-loci modes"); break;
-      case 'R': break;  // only meaningful with -r
+      case 'r': o.ml_mode = iv; if (iv > 1) unsupported.push_back("-r2..5 multi-loci modes (only -r0 slough and -r1 stats are built)"); break;
+      case 'R': o.max_ml = iv; break;  // only meaningful with -r
       case 'c': if (iv) unsupported.push_back("-c chimeric trimming"); break;
       case 'a': if (iv) unsupported.push_back("-a microInDels"); break;
       case 'A': if (iv) unsupported.push_back("-A splice junctions"); break;
@@ -441,7 +443,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'b': unsupported.push_back("-b bisulfite"); break;
       case 'C': unsupported.push_back("-C colorspace"); break;
       case 'N': unsupported.push_back("-N best matches"); break;
-      case 'X': unsupported.push_back("-X clamp multi"); break;
+      case 'X': o.clamp_ml = true; break;
       case 'B': case 'H': case '5': case 'Z': case 'z': case 'j': case 'J': case 'O': case 'S': case '7': case '8':
       case 'q': unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'h':
@@ -468,6 +470,14 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
   if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
   if (o.gpus < 1) o.gpus = 1;
+  if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
+    if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
+    if (o.max_ml == 0) o.max_ml = 5;  // cDfltMaxMultiHits
+    if (o.max_ml < 2 || o.max_ml > 500) { fprintf(stderr, "Error: multiple aligned reads '-R%d' specified outside of range 2..%d\n", o.max_ml, 500); return -1; }
+  } else {
+    o.max_ml = 1;
+    o.clamp_ml = false;  // kanga.cpp:691-694: -X only counts together with -R
+  }
   return 0;
 }
 
@@ -684,6 +694,7 @@ int main(int argc, char** argv) {
   bkx_align_params P;
   if (bkx_default_params(idx[0], o.pmode, &P) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
   P.max_subs = o.max_subs; P.min_edit_dist = o.edit_delta; P.max_ns = o.max_ns; P.align_strand = o.strand;
+  P.ml_mode = o.ml_mode; P.max_ml_matches = o.max_ml; P.clamp_max_ml = o.clamp_ml ? 1 : 0;
 
   reads_thread.join();
   if (reads_rc < 0) return 1;

@@ -57,6 +57,12 @@ enum { BKX_STRAND_BOTH = 0, BKX_STRAND_WATSON = 1, BKX_STRAND_CRICK = 2 };
 /* ---- etPMode: biokanga/Aligner.h:214-220 ------------------------------------------------------ */
 enum { BKX_PMODE_DEFAULT = 0, BKX_PMODE_MORESENS = 1, BKX_PMODE_ULTRASENS = 2, BKX_PMODE_LESSSENS = 3 };
 
+/* ---- etMLMode: biokanga/Aligner.h:224-231.  Built: DEFAULT (max_ml_matches must be 1) and DIST ("-r1", stats only:
+ * reads with 2..max_ml_matches equally good loci are reported eNARMultiAlign with their exact LowHitInstances,
+ * Aligner.cpp:9328-9400).  RAND uses libc rand() in the reference and cannot be reproduced; UNIQ / MULTI / ALL are
+ * SURVEY section 8(f) rows not built yet -- rejected with BKX_ERR_UNSUPPORTED. */
+enum { BKX_ML_DEFAULT = 0, BKX_ML_DIST = 1, BKX_ML_RAND = 2, BKX_ML_UNIQ = 3, BKX_ML_MULTI = 4, BKX_ML_ALL = 5 };
+
 /* ---- etPEproc: biokanga/Aligner.h:252-259 ----------------------------------------------------- */
 enum { BKX_PE_NONE = 0, BKX_PE_ORPHAN = 1, BKX_PE_UNIQUE = 2, BKX_PE_ORPHAN_SE = 3, BKX_PE_UNIQUE_SE = 4 };
 
@@ -97,7 +103,9 @@ typedef struct bkx_align_params {
   int32_t max_num_slides;   /* per 100 bp: 8 default, 9 ultra, 6 less sensitive  */
   int32_t max_iter;         /* CSfxArrayV3::m_MaxIter: 5000/10000/20000/2500     */
   int32_t max_ident_nodes;  /* cMaxNumIdentNodes = 1 024 000 (SfxArrayV2.h:15)   */
-  int32_t reserved[6];
+  int32_t ml_mode;          /* -r  BKX_ML_*: what to do with reads hitting several loci (default slough)  */
+  int32_t clamp_max_ml;     /* -X  treat reads with more than max_ml_matches loci as if exactly that many */
+  int32_t reserved[4];
 } bkx_align_params;
 
 /* Fixed 32-byte per-read record: the tsReadHit fields written by ProcCoredApprox

@@ -467,6 +467,7 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
   memset(hits, 0, sizeof(*hits));
   int hr = align_reads(x, w, p, max_tot_mm, core_len, core_delta, slides, seqbuf, len, &inst, &low, &nxt, hits);
   if (inst > p->max_ml_matches) inst = p->max_ml_matches + 1;                           /* :9241 */
+  if (p->clamp_max_ml && hr == BKX_HR_HITINSTS) { inst = p->max_ml_matches; hr = BKX_HR_HITS; } /* :9243 */
   out->hit_rslt = (uint8_t)hr;
   out->seeds = w->seeds;
   out->cands = w->cands;
@@ -475,11 +476,11 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
       out->nar = BKX_NAR_NOHIT;
       st->tot_non_aligned++;
       break;
-    case BKX_HR_HITS:
+    case BKX_HR_HITS:                                                                   /* :9328-9400 */
       st->tot_accepted_aligned++;
       st->tot_loci_aligned += (uint64_t)inst;
       if (inst == 1) st->tot_accepted_unique++; else st->tot_accepted_multi++;
-      if (inst == 1) {                                                                  /* :9369-9381 */
+      if (inst == 1 || p->ml_mode != BKX_ML_DIST) {  /* unique, or (outside -r1) the first of several: hits[0] */
         out->nar = BKX_NAR_ACCEPTED;
         out->num_hits = 1;
         out->strand = hits[0].strand;
@@ -488,20 +489,14 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
         out->match_len = hits[0].match_len;
         out->mismatches = hits[0].mismatches;
         inst = 1;
-      } else { /* only reachable with max_ml_matches > 1, mode -r0: first hit is taken */
-        out->nar = BKX_NAR_ACCEPTED;
-        out->num_hits = 1;
-        out->strand = hits[0].strand;
-        out->chrom_id = hits[0].chrom_id;
-        out->match_loci = hits[0].match_loci;
-        out->match_len = hits[0].match_len;
-        out->mismatches = hits[0].mismatches;
-        inst = 1;
+        if (out->strand == '+') st->plus_hits++; else st->minus_hits++;
+      } else {                                       /* -r1: counted, not placed (:9383-9386) */
+        out->nar = BKX_NAR_MULTIALIGN;
+        out->num_hits = 0;
       }
       out->low_hit_instances = (int16_t)inst;
       out->low_mm = (int8_t)low;
       out->nxt_low_mm = (int8_t)nxt;
-      if (out->strand == '+') st->plus_hits++; else st->minus_hits++;
       break;
     case BKX_HR_MMDELTA:                                                                /* :9426-9438 */
       st->tot_not_accepted_delta++;

@@ -189,6 +189,49 @@ def case_repeats():
         align_runs(d, tmp, "repeats.sfx", runs)
 
 
+def case_lowcopy():
+    """~260 kbp with LOW-copy repeat families (2..9 copies of 150-400 bp units, exact and ~1 % diverged): the regime of the
+    multi-loci options -- -r1 (distribution only) with -R limits below, at and above the family sizes, and -X."""
+    d = os.path.join(GOLD, "lowcopy")
+    os.makedirs(d, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.default_rng(41)
+        parts = []
+        for fam in range(120):
+            unit = rng.integers(0, 4, int(rng.integers(150, 400)), dtype=np.uint8)
+            copies = int(rng.integers(2, 10))
+            div = (0.0, 0.0, 0.01)[fam % 3]
+            for _ in range(copies):
+                u = unit.copy()
+                if div > 0:
+                    m = rng.random(len(u)) < div
+                    u[m] = (u[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+                if rng.random() < 0.4:
+                    u = (3 - u[::-1]).astype(np.uint8)
+                parts.append(u)
+        for _ in range(300):
+            parts.append(rng.integers(0, 4, int(rng.integers(100, 500)), dtype=np.uint8))
+        order = rng.permutation(len(parts))
+        body = np.concatenate([parts[k] for k in order])
+        third = len(body) // 3
+        g = [("lc1", body[:third]), ("lc2", body[third:2 * third]), ("lc3", body[2 * third:])]
+        synth.write_fasta(os.path.join(tmp, "genome.fa"), g)
+        run(["index", "-i", "genome.fa", "-o", "lowcopy.sfx", "-r", "lowcopy", "-F", "idx.log"], tmp)
+        n, r = synth.sim_reads(g, 5000, 100, seed=42, subs=(0, 0, 1, 2, 3), junk_frac=0.01, n_frac=0.01)
+        synth.write_reads_fasta(os.path.join(tmp, "r100.fa"), n, r)
+        for f in ("r100.fa", "genome.fa"):
+            gz(os.path.join(tmp, f), os.path.join(d, f + ".gz"))
+        gz(os.path.join(tmp, "lowcopy.sfx"), os.path.join(d, "lowcopy.sfx.gz"))
+        runs = {
+            "r0_s3": {"reads": ["r100.fa"], "args": ["-s3"]},
+            "r1_R5_s3": {"reads": ["r100.fa"], "args": ["-s3", "-r1", "-R5"]},
+            "r1_R2_s3": {"reads": ["r100.fa"], "args": ["-s3", "-r1", "-R2"]},
+            "r1_R20_s5_e2": {"reads": ["r100.fa"], "args": ["-s5", "-e2", "-r1", "-R20"]},
+            "r1_R4_X_s3": {"reads": ["r100.fa"], "args": ["-s3", "-r1", "-R4", "-X"]},
+        }
+        align_runs(d, tmp, "lowcopy.sfx", runs)
+
+
 def case_formats():
     """Output-format runs on the tiny index: CSV variants -M1..3, BED -M4, FASTQ qualities -g0/-g1 in SAM,
     gzip output.  One FASTQ read set with descriptors that carry trailing words."""
@@ -247,11 +290,13 @@ def case_formats():
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
         case_repeats()
     if "formats" in which:
         case_formats()
+    if "lowcopy" in which:
+        case_lowcopy()
     print("fixtures written under", GOLD)

@@ -15,7 +15,7 @@ import pyoracle as po
 from biokanga_b200 import abi
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = {"tiny": "tiny.sfx", "repeats": "repeats.sfx"}
+CASES = {"tiny": "tiny.sfx", "repeats": "repeats.sfx", "lowcopy": "lowcopy.sfx"}
 
 
 def sfx_path(case, scratch):
@@ -46,6 +46,10 @@ def params_from_args(index, args):
         opt[a[1]] = int(a[2:]) if len(a) > 2 else 1
     p = index.default_params(opt["m"], max_subs=opt["s"], min_edit_dist=opt["e"], max_ns=opt["n"],
                              align_strand=opt["Q"])
+    if opt.get("r", 0):  # multi-loci modes: -r<mode> -R<limit> [-X]  (kanga.cpp:667-696)
+        p.ml_mode = opt["r"]
+        p.max_ml_matches = opt.get("R", 5)
+        p.clamp_max_ml = 1 if "X" in opt else 0
     pe = None
     if opt["U"]:
         pe = abi.PEParams()

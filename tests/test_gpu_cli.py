@@ -14,7 +14,8 @@ CLI = os.path.join(os.path.dirname(bkx.LIB_PATH), "bkx-align")
 
 RUNS = [("tiny", "r100_s3"), ("tiny", "r100_s5_e2"), ("tiny", "mixed_s3"), ("tiny", "r251_s6"), ("tiny", "r100_s3_Q2"),
         ("tiny", "r100_s4_m2"), ("tiny", "pe_U2"), ("tiny", "pe_U4"), ("tiny", "pe_U1"), ("tiny", "pe_U3"),
-        ("tiny", "pe_U1_far"), ("repeats", "r100_s3_m3"), ("repeats", "r60_s5")]
+        ("tiny", "pe_U1_far"), ("repeats", "r100_s3_m3"), ("repeats", "r60_s5"), ("lowcopy", "r1_R5_s3"),
+        ("lowcopy", "r1_R4_X_s3"), ("lowcopy", "r1_R20_s5_e2")]
 
 
 def summary_block(path):

@@ -28,3 +28,10 @@ def test_oracle_matches_reference(case, tag, golden_dir):
     hist = np.bincount(res["nar"], minlength=abi.NAR_COUNT)
     for code, n in re.findall(r"^\s+(\d+) \((\w\w)\)", log, flags=re.M):
         assert hist[abi.NAR_CODES.index(n)] == int(code), (n, code, hist)
+    # "Provisionally accepted A aligned reads (U uniquely, M aligning to multiloci) aligning to a total of T loci":
+    # with -r1 these carry the exact per-read LowHitInstances (Aligner.cpp:9357-9364, :535)
+    m = re.search(r"Provisionally accepted (\d+) aligned reads \((\d+) uniquely, (\d+) aligning to multiloci\) "
+                  r"aligning to a total of (\d+) loci", log)
+    assert m, "summary line missing"
+    assert (st.tot_accepted_aligned, st.tot_accepted_unique, st.tot_accepted_multi, st.tot_loci_aligned) == tuple(
+        int(v) for v in m.groups())
