@@ -71,6 +71,9 @@ RESULT_DTYPE = np.dtype([
     ("match_len", "<u2"), ("mismatches", "u1"), ("flags", "u1"), ("seeds", "<u4"), ("cands", "<u4"),
     ("reserved", "<u4")])
 assert RESULT_DTYPE.itemsize == 32
+MULTI_DTYPE = np.dtype([("chrom_id", "<u4"), ("match_loci", "<u4"), ("match_len", "<u2"), ("strand", "u1"),
+                        ("mismatches", "u1")])
+assert MULTI_DTYPE.itemsize == 12
 assert C.sizeof(Entry) == 112 and C.sizeof(AlignParams) == 64 and C.sizeof(PEParams) == 32
 
 ENTRY_DTYPE = np.dtype([("entry_id", "<u4"), ("seq_len", "<u4"), ("start_ofs", "<u8"), ("end_ofs", "<u8"),

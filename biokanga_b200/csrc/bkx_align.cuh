@@ -40,6 +40,7 @@ constexpr int kGroup = 8;            // lanes per read
 struct KParams {
   int max_subs, mmd, max_ns, strand_mode, max_hits, min_core_len, slides_per100, max_iter, max_nodes;
   int ml_mode, clamp_ml;
+  bkx_multi_hit* multi;   // -r5: max_hits slots per read of this launch, or nullptr
 };
 
 // What ProcCoredApprox stores for one read once AlignReads has returned (Aligner.cpp:9239-9245, 9310-9479): shared by
@@ -58,13 +59,13 @@ static __device__ __noinline__ bkx_read_result make_result(const DevIndex& I, co
     case BKX_HR_HITS:
       if (inst == 1 || P.ml_mode != BKX_ML_DIST) {  // a unique hit (or, outside -r1, the first of several)
         res.nar = BKX_NAR_ACCEPTED;
-        res.num_hits = 1;
+        res.num_hits = (P.ml_mode == BKX_ML_ALL) ? (uint8_t)inst : 1;
         res.strand = hit_strand ? '-' : '+';
         res.chrom_id = __ldg(I.ent_id + hit_ent);
         res.match_loci = (uint32_t)(hit_p - __ldg(I.ent_start + hit_ent));
         res.match_len = (uint16_t)L;
         res.mismatches = (uint8_t)hit_mm;
-        res.low_hit_instances = 1;
+        res.low_hit_instances = (P.ml_mode == BKX_ML_ALL) ? (int16_t)inst : 1;
       } else {                                      // -r1: counted, not placed (:9383-9386)
         res.nar = BKX_NAR_MULTIALIGN;
         res.low_hit_instances = (int16_t)inst;
@@ -123,6 +124,7 @@ struct Grp {
   int inst, low, nxt;
   int hit_strand, hit_ent, hit_mm;
   uint64_t hit_p;
+  bkx_multi_hit* multi;   // this read's -r5 slots or nullptr
   uint32_t seeds, cands;
 
   __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & kLaneMask; }
@@ -455,6 +457,18 @@ __device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, co
     unsigned minm = c.ballot(acc && mm == bmin);
     int v2 = c.gmin((acc && mm > bmin) ? mm : 255);
     int bcnt = __popc(minm);
+    if (c.multi && bmin <= c.low) {  // -r5: the hit list, in discovery order = lane order within the step (:6157-6205)
+      const int at = (bmin < c.low ? 0 : c.inst) + __popc(minm & ((1u << c.gl) - 1));
+      if (acc && mm == bmin && at < P.max_hits) {
+        bkx_multi_hit h;
+        h.chrom_id = __ldg(I.ent_id + ent);
+        h.match_loci = (uint32_t)(p - __ldg(I.ent_start + ent));
+        h.match_len = (uint16_t)c.L;
+        h.strand = s ? '-' : '+';
+        h.mismatches = (uint8_t)mm;
+        c.multi[at] = h;
+      }
+    }
     if (bmin < c.low) {
       int fl = __ffs(minm) - 1;
       c.nxt = min(c.low, v2);

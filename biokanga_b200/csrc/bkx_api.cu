@@ -59,6 +59,8 @@ struct Slot {
   size_t bases_cap = 0;
   uint8_t* d_packed = nullptr;   // staging for 4-bit packed input (bkx_align_reads_packed4)
   size_t packed_cap = 0;
+  bkx_multi_hit* d_multi = nullptr;   // -r5 loci of the slice's reads
+  size_t multi_cap = 0;
   uint64_t* d_offs = nullptr;
   bkx_read_result* d_out = nullptr;
   uint32_t* d_hard = nullptr;   // reads the fast kernel deferred to the general kernel
@@ -295,6 +297,7 @@ extern "C" void bkx_close_index(bkx_index* x) {
     if (x->fast_hash[s]) cudaFree(x->fast_hash[s]);
     if (x->slot[s].d_bases) cudaFree(x->slot[s].d_bases);
     if (x->slot[s].d_packed) cudaFree(x->slot[s].d_packed);
+    if (x->slot[s].d_multi) cudaFree(x->slot[s].d_multi);
     if (x->slot[s].d_offs) cudaFree(x->slot[s].d_offs);
     if (x->slot[s].d_out) cudaFree(x->slot[s].d_out);
     if (x->slot[s].d_hard) cudaFree(x->slot[s].d_hard);
@@ -659,8 +662,11 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   } else if (p->ml_mode == BKX_ML_DIST) {
     if (p->max_ml_matches < 2 || p->max_ml_matches > 500)  // cMaxMultiHits, Aligner.h:62
       return fail(BKX_ERR_PARAM, "max_ml_matches %d out of range 2..500", p->max_ml_matches);
+  } else if (p->ml_mode == BKX_ML_ALL) {
+    if (p->max_ml_matches < 2 || p->max_ml_matches > 64)  // the reference allows 100000 (cMaxAllHits); the per-read slots here 64
+      return fail(BKX_ERR_UNSUPPORTED, "max_ml_matches %d with -r5: 2..64 loci per read are supported", p->max_ml_matches);
   } else {
-    return fail(BKX_ERR_UNSUPPORTED, "ml_mode %d: only -r0 and -r1 are built (-r2 is not reproducible, -r3..5 are not built yet)", p->ml_mode);
+    return fail(BKX_ERR_UNSUPPORTED, "ml_mode %d: -r0, -r1 and -r5 are built (-r2 is not reproducible, -r3/-r4 are not built yet)", p->ml_mode);
   }
   if (p->min_core_len < 4 || p->min_core_len > 100) return fail(BKX_ERR_PARAM, "bad min_core_len %d", p->min_core_len);
   if (p->max_num_slides < 1 || p->max_num_slides > 16) return fail(BKX_ERR_PARAM, "bad max_num_slides %d", p->max_num_slides);
@@ -670,6 +676,7 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   k->max_hits = p->max_ml_matches; k->min_core_len = p->min_core_len; k->slides_per100 = p->max_num_slides;
   k->max_iter = p->max_iter; k->max_nodes = p->max_ident_nodes;
   k->ml_mode = p->ml_mode; k->clamp_ml = p->clamp_max_ml ? 1 : 0;
+  k->multi = nullptr;
   return BKX_OK;
 }
 
@@ -784,6 +791,7 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
   KParams k;
   int rc = check_params(p, &k);
   if (rc < 0) return rc;
+  if (p->ml_mode == BKX_ML_ALL) return fail(BKX_ERR_UNSUPPORTED, "-r5 needs the host call bkx_align_reads_multi");
   if (n_reads == 0) return BKX_OK;
   std::lock_guard<std::mutex> lk(x->mtx);
   CU(cudaSetDevice(x->device));
@@ -807,11 +815,13 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
 }
 
 static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, bool packed4, const uint64_t* offsets,
-                      uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
+                      uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats, bkx_multi_hit* multi = nullptr) {
   if (!x || !bases || !offsets || !out) return fail(BKX_ERR_PARAM, "null argument");
   KParams k;
   int rc = check_params(p, &k);
   if (rc < 0) return rc;
+  if ((p->ml_mode == BKX_ML_ALL) != (multi != nullptr))
+    return fail(BKX_ERR_PARAM, "ml_mode -r5 and bkx_align_reads_multi go together");
   if (n_reads == 0) return BKX_OK;
   std::lock_guard<std::mutex> lk(x->mtx);
   CU(cudaSetDevice(x->device));
@@ -916,6 +926,16 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
       CU(launch_unpack4(s.d_packed, (unsigned)(offsets[start] & 1), nb, s.d_bases, x->cst));
       x->launches += 1;
     }
+    if (multi) {
+      const size_t need = (size_t)cnt * (size_t)k.max_hits;
+      if (need > s.multi_cap) {
+        if (s.d_multi) cudaFree(s.d_multi);
+        s.multi_cap = need * 5 / 4;
+        CU(cudaMalloc((void**)&s.d_multi, s.multi_cap * sizeof(bkx_multi_hit)));
+      }
+      CU(cudaMemsetAsync(s.d_multi, 0, need * sizeof(bkx_multi_hit), x->cst));
+      k.multi = s.d_multi;
+    }
     CU(cudaEventRecord(s.k0, x->cst));
     // offsets stay absolute: hand the kernel a base pointer shifted by the slice start
     if ((rc = launch_both(x, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard,
@@ -924,6 +944,9 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     mark(x->cst);
     CU(cudaStreamWaitEvent(s.st, s.k1, 0));
     CU(cudaMemcpyAsync(out + start, s.d_out, (size_t)cnt * sizeof(bkx_read_result), cudaMemcpyDeviceToHost, s.st));
+    if (multi)
+      CU(cudaMemcpyAsync(multi + (size_t)start * (size_t)k.max_hits, s.d_multi,
+                         (size_t)cnt * (size_t)k.max_hits * sizeof(bkx_multi_hit), cudaMemcpyDeviceToHost, s.st));
     mark(s.st);
     inflight[b] = true;
     start += cnt;
@@ -961,6 +984,12 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
 extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
                                uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
   return align_host(x, p, bases, false, offsets, n_reads, out, stats);
+}
+
+extern "C" int bkx_align_reads_multi(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
+                                     uint32_t n_reads, bkx_read_result* out, bkx_multi_hit* multi, bkx_align_stats* stats) {
+  if (!multi) return fail(BKX_ERR_PARAM, "null argument");
+  return align_host(x, p, bases, false, offsets, n_reads, out, stats, multi);
 }
 
 extern "C" int bkx_align_reads_packed4(bkx_index* x, const bkx_align_params* p, const uint8_t* packed, const uint64_t* offsets,

@@ -203,7 +203,9 @@ size_t align_smem_bytes(int W) { return group_smem_bytes(W) * kGroupsPerBlock; }
 struct BlockStats {
   unsigned int nar[BKX_NAR_COUNT];
   unsigned int plus, minus;
-  unsigned int multi, multi_loci;   // -r1: reads whose search ended eHRhits with several loci, and the sum of those loci
+  unsigned int multi, multi_loci;   // -r1: reads whose search ended eHRhits with several loci (classed ML); the loci
+                                    // of all multi-loci reads (-r1 and -r5)
+  unsigned int acc_multi;           // -r5: accepted reads carrying several loci
   unsigned long long seeds, cands;
 };
 
@@ -218,6 +220,9 @@ __device__ __forceinline__ void stats_add(BlockStats& bs, const bkx_read_result&
   if (res.nar == BKX_NAR_MULTIALIGN && res.hit_rslt == BKX_HR_HITS) {
     atomicAdd(&bs.multi, 1u);
     atomicAdd(&bs.multi_loci, (unsigned int)res.low_hit_instances);
+  } else if (res.nar == BKX_NAR_ACCEPTED && res.num_hits > 1) {
+    atomicAdd(&bs.acc_multi, 1u);
+    atomicAdd(&bs.multi_loci, (unsigned int)res.num_hits);
   }
 }
 
@@ -234,10 +239,10 @@ __device__ __forceinline__ void stats_flush(const BlockStats& bs, bkx_align_stat
     atomicAdd((unsigned long long*)&stats->num_sloughed_ns, (unsigned long long)bs.nar[BKX_NAR_NS]);
     atomicAdd((unsigned long long*)&stats->tot_non_aligned,
               (unsigned long long)bs.nar[BKX_NAR_NOHIT] + bs.nar[BKX_NAR_MULTIALIGN] - bs.multi);
-    atomicAdd((unsigned long long*)&stats->tot_accepted_unique, acc);
-    atomicAdd((unsigned long long*)&stats->tot_accepted_multi, (unsigned long long)bs.multi);
+    atomicAdd((unsigned long long*)&stats->tot_accepted_unique, acc - bs.acc_multi);
+    atomicAdd((unsigned long long*)&stats->tot_accepted_multi, (unsigned long long)bs.multi + bs.acc_multi);
     atomicAdd((unsigned long long*)&stats->tot_accepted_aligned, acc + bs.multi);
-    atomicAdd((unsigned long long*)&stats->tot_loci_aligned, acc + bs.multi_loci);
+    atomicAdd((unsigned long long*)&stats->tot_loci_aligned, acc - bs.acc_multi + bs.multi_loci);
     atomicAdd((unsigned long long*)&stats->tot_not_accepted_delta, (unsigned long long)bs.nar[BKX_NAR_MMDELTA]);
     atomicAdd((unsigned long long*)&stats->seeds, bs.seeds);
     atomicAdd((unsigned long long*)&stats->cands, bs.cands);
@@ -286,6 +291,7 @@ __global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
     const int L = (int)(__ldg(offs + r + 1) - o0);
     const uint8_t* rd = bases + o0;
     c.L = L;
+    c.multi = P.multi ? P.multi + (size_t)r * P.max_hits : nullptr;
     // ---- unpack, N filter (Aligner.cpp:9041-9063), 2-bit pack both strands: one 32-base word per lane
     int nN = 0;
     bool bad = false;
@@ -479,20 +485,22 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     res.mismatches = 0; res.flags = 0; res.seeds = seeds; res.cands = cands; res.reserved = 0;
     int ii = inst > P.max_hits ? P.max_hits + 1 : inst;
     bool multi = false;
+    int nh = 1;
     if constexpr (MLX) {
       if (P.clamp_ml && hr == BKX_HR_HITINSTS) { ii = P.max_hits; hr = BKX_HR_HITS; }
       multi = hr == BKX_HR_HITS && ii > 1 && P.ml_mode == BKX_ML_DIST;
+      if (P.ml_mode == BKX_ML_ALL) nh = ii;
     }
     res.hit_rslt = (uint8_t)hr;
     if (hr == BKX_HR_HITS && !multi) {
       res.nar = BKX_NAR_ACCEPTED;
-      res.num_hits = 1;
+      res.num_hits = (uint8_t)nh;
       res.strand = hit_strand ? '-' : '+';
       res.chrom_id = __ldg(I.ent_id + hit_ent);
       res.match_loci = (uint32_t)(hit_p - __ldg(I.ent_start + hit_ent));
       res.match_len = (uint16_t)L;
       res.mismatches = (uint8_t)hit_mm;
-      res.low_hit_instances = 1;
+      res.low_hit_instances = (int16_t)nh;
       res.low_mm = (int8_t)low;
       res.nxt_low_mm = (int8_t)nxt;
     } else if (hr == BKX_HR_MMDELTA || hr == BKX_HR_HITINSTS || hr == BKX_HR_HITS) {
@@ -502,6 +510,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
       res.low_mm = (int8_t)low;
       res.nxt_low_mm = (int8_t)nxt;
       if (multi) { atomicAdd(&bs.multi, 1u); atomicAdd(&bs.multi_loci, (unsigned int)ii); }
+    }
+    if constexpr (MLX) {
+      if (res.nar == BKX_NAR_ACCEPTED && nh > 1) { atomicAdd(&bs.acc_multi, 1u); atomicAdd(&bs.multi_loci, (unsigned int)nh); }
     }
     out[r] = res;
     stats_add_basic(bs, res);
@@ -735,6 +746,17 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
           ++inst;
         } else {
           nxt = mm;  // low < mm < nxt
+        }
+        if constexpr (MLX) {  // -r5: keep every locus at the lowest mismatch count, in discovery order
+          if (P.multi && mm == low && inst <= P.max_hits) {
+            bkx_multi_hit h;
+            h.chrom_id = __ldg(I.ent_id + ent);
+            h.match_loci = (uint32_t)(p - __ldg(I.ent_start + ent));
+            h.match_len = (uint16_t)L;
+            h.strand = s ? '-' : '+';
+            h.mismatches = (uint8_t)mm;
+            P.multi[(size_t)r * P.max_hits + (inst - 1)] = h;
+          }
         }
         if (inst > P.max_hits && low == 0) { stop_all = true; break; }
       }

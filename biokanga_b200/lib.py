@@ -24,7 +24,7 @@ EXPORTS = [
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
     "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
-    "bkx_pack_bases4",
+    "bkx_pack_bases4", "bkx_align_reads_multi",
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_pack_bases4.argtypes = [vp, u64, vp]
+    L.bkx_align_reads_multi.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, vp, C.POINTER(abi.AlignStats)]
     L.bkx_clone_index.argtypes = [vp, i32, C.POINTER(vp)]
     L.bkx_close_index.argtypes = [vp]
     L.bkx_close_index.restype = None
@@ -228,6 +229,18 @@ class Index:
         """Same, raw host pointers (pinned buffers owned by the caller)."""
         st = C.byref(stats) if stats is not None else None
         check(lib().bkx_align_reads(self._h, C.byref(params), bases_ptr, offsets_ptr, n_reads, out_ptr, st))
+
+    def align_multi(self, params, bases, offsets):
+        """-r5 (params.ml_mode = 5): (records, loci[n, max_ml_matches], stats)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.zeros(n, dtype=abi.RESULT_DTYPE)
+        multi = np.zeros((n, params.max_ml_matches), dtype=abi.MULTI_DTYPE)
+        st = abi.AlignStats()
+        check(lib().bkx_align_reads_multi(self._h, C.byref(params), bases.ctypes.data, offsets.ctypes.data, n,
+                                          out.ctypes.data, multi.ctypes.data, C.byref(st)))
+        return out, multi, st
 
     def align_packed4_ptr(self, params, packed_ptr, offsets_ptr, n_reads, out_ptr, stats=None):
         """Host buffers with the reads 4-bit packed (see pack_bases4); offsets count bases."""

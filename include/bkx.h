@@ -57,10 +57,11 @@ enum { BKX_STRAND_BOTH = 0, BKX_STRAND_WATSON = 1, BKX_STRAND_CRICK = 2 };
 /* ---- etPMode: biokanga/Aligner.h:214-220 ------------------------------------------------------ */
 enum { BKX_PMODE_DEFAULT = 0, BKX_PMODE_MORESENS = 1, BKX_PMODE_ULTRASENS = 2, BKX_PMODE_LESSSENS = 3 };
 
-/* ---- etMLMode: biokanga/Aligner.h:224-231.  Built: DEFAULT (max_ml_matches must be 1) and DIST ("-r1", stats only:
+/* ---- etMLMode: biokanga/Aligner.h:224-231.  Built: DEFAULT (max_ml_matches must be 1), DIST ("-r1", stats only:
  * reads with 2..max_ml_matches equally good loci are reported eNARMultiAlign with their exact LowHitInstances,
- * Aligner.cpp:9328-9400).  RAND uses libc rand() in the reference and cannot be reproduced; UNIQ / MULTI / ALL are
- * SURVEY section 8(f) rows not built yet -- rejected with BKX_ERR_UNSUPPORTED. */
+ * Aligner.cpp:9328-9400) and ALL ("-r5": every one of up to max_ml_matches <= 64 equally good loci is returned,
+ * through bkx_align_reads_multi).  RAND uses libc rand() in the reference and cannot be reproduced; UNIQ / MULTI
+ * (clustering) are SURVEY section 8(f) rows not built yet -- rejected with BKX_ERR_UNSUPPORTED. */
 enum { BKX_ML_DEFAULT = 0, BKX_ML_DIST = 1, BKX_ML_RAND = 2, BKX_ML_UNIQ = 3, BKX_ML_MULTI = 4, BKX_ML_ALL = 5 };
 
 /* ---- etPEproc: biokanga/Aligner.h:252-259 ----------------------------------------------------- */
@@ -131,6 +132,17 @@ typedef struct bkx_read_result {
 } bkx_read_result;
 
 enum { BKX_FLG_PE_ALIGNED = 1, BKX_FLG_PE_RECOVERED = 2 };
+
+/* One locus of a read under -r5 (BKX_ML_ALL): the tsHitLoci fields CAligner::WriteHitLoci copies into the record it
+ * appends per hit (Aligner.cpp:6723-6790).  bkx_align_reads_multi returns max_ml_matches of these per read; the first
+ * bkx_read_result::num_hits of a read's slots are valid, in the order LocateCoreMultiples found them. */
+typedef struct bkx_multi_hit {
+  uint32_t chrom_id;
+  uint32_t match_loci;
+  uint16_t match_len;
+  uint8_t strand;       /* '+' / '-' */
+  uint8_t mismatches;
+} bkx_multi_hit;
 
 /* Paired-end parameters: CAligner::ProcessPairedEnds arguments, Aligner.cpp:2876-2881. */
 typedef struct bkx_pe_params {
@@ -208,6 +220,12 @@ int bkx_default_params(const bkx_index* idx, int pmode, bkx_align_params* out);
  * own streams, double buffered; returns when `out[0..n_reads)` is complete. */
 int bkx_align_reads(bkx_index* idx, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
                     uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats /* may be NULL; accumulated */);
+/* -r5 (params->ml_mode == BKX_ML_ALL): as bkx_align_reads, plus the loci of every read.  multi holds
+ * n_reads * params->max_ml_matches entries; read i owns multi[i * max_ml_matches ..], of which out[i].num_hits are
+ * valid when out[i].nar == BKX_NAR_ACCEPTED (out[i] itself carries the first one, and low_hit_instances the count).
+ * Replaces the MaxHits > 1 use of CSfxArrayV3::AlignReads (pMultiHits, Aligner.cpp:9220-9238) + WriteHitLoci. */
+int bkx_align_reads_multi(bkx_index* idx, const bkx_align_params* params, const uint8_t* bases, const uint64_t* offsets,
+                          uint32_t n_reads, bkx_read_result* out, bkx_multi_hit* multi, bkx_align_stats* stats);
 /* Same call with the reads 4-bit packed on the host: base i of the concatenation in the low (i even) or high (i odd)
  * nibble of byte i/2, reads back to back at nibble granularity, offsets still counted in BASES.  Halves the bytes
  * that cross PCIe (and the host-memory traffic of an 8-GPU node); the nibbles are expanded on the device.  Nibble

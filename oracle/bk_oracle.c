@@ -434,6 +434,7 @@ int bko_align_reads_one(const bko_index* x, const bkx_align_params* p, int max_t
 /* Per-read driver: ProcCoredApprox body, Aligner.cpp:9027-9504 (default -r0 multi-loci mode). */
 static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p, const uint8_t* rd, int len,
                       bkx_read_result* out, bkx_read_result* hits, uint8_t* seqbuf, bkx_align_stats* st) {
+  memset(hits, 0, ((size_t)p->max_ml_matches + 1) * sizeof(*hits));
   memset(out, 0, sizeof(*out));
   out->nar = BKX_NAR_NOHIT;
   w->seeds = w->cands = 0;
@@ -482,13 +483,13 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
       if (inst == 1) st->tot_accepted_unique++; else st->tot_accepted_multi++;
       if (inst == 1 || p->ml_mode != BKX_ML_DIST) {  /* unique, or (outside -r1) the first of several: hits[0] */
         out->nar = BKX_NAR_ACCEPTED;
-        out->num_hits = 1;
+        out->num_hits = (p->ml_mode == BKX_ML_ALL) ? (uint8_t)inst : 1;  /* -r5: every hit is reported (:9336-9352) */
         out->strand = hits[0].strand;
         out->chrom_id = hits[0].chrom_id;
         out->match_loci = hits[0].match_loci;
         out->match_len = hits[0].match_len;
         out->mismatches = hits[0].mismatches;
-        inst = 1;
+        if (p->ml_mode != BKX_ML_ALL) inst = 1;
         if (out->strand == '+') st->plus_hits++; else st->minus_hits++;
       } else {                                       /* -r1: counted, not placed (:9383-9386) */
         out->nar = BKX_NAR_MULTIALIGN;
@@ -530,6 +531,7 @@ typedef struct {
   const uint64_t* offs;
   uint32_t n;
   bkx_read_result* out;
+  bkx_multi_hit* multi;
   bkx_align_stats st;
   uint32_t* cursor;
   pthread_mutex_t* mtx;
@@ -554,6 +556,15 @@ static void* thr_main(void* a_) {
     for (uint32_t i = s; i < e; i++) {
       int len = (int)(a->offs[i + 1] - a->offs[i]);
       proc_read(a->x, &w, a->p, a->bases + a->offs[i], len, &a->out[i], hits, seqbuf, &a->st);
+      if (a->multi) {  /* -r5: the pMultiHits list WriteHitLoci walks */
+        bkx_multi_hit* m = a->multi + (size_t)i * (size_t)a->p->max_ml_matches;
+        memset(m, 0, (size_t)a->p->max_ml_matches * sizeof(*m));
+        if (a->out[i].nar == BKX_NAR_ACCEPTED)
+          for (int h = 0; h < a->out[i].num_hits && h < a->p->max_ml_matches; h++) {
+            m[h].chrom_id = hits[h].chrom_id; m[h].match_loci = hits[h].match_loci; m[h].match_len = hits[h].match_len;
+            m[h].strand = hits[h].strand; m[h].mismatches = hits[h].mismatches;
+          }
+      }
       a->st.seeds += a->out[i].seeds;
       a->st.cands += a->out[i].cands;
       a->st.reads++;
@@ -565,8 +576,16 @@ static void* thr_main(void* a_) {
   return NULL;
 }
 
+int bko_align_batch_multi(const bko_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offs,
+                          uint32_t n, bkx_read_result* out, bkx_multi_hit* multi, bkx_align_stats* stats, int nthreads);
+
 int bko_align_batch(const bko_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offs,
                     uint32_t n, bkx_read_result* out, bkx_align_stats* stats, int nthreads) {
+  return bko_align_batch_multi(x, p, bases, offs, n, out, NULL, stats, nthreads);
+}
+
+int bko_align_batch_multi(const bko_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offs,
+                          uint32_t n, bkx_read_result* out, bkx_multi_hit* multi, bkx_align_stats* stats, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   pthread_t tid[256];
@@ -575,6 +594,7 @@ int bko_align_batch(const bko_index* x, const bkx_align_params* p, const uint8_t
   uint32_t cursor = 0;
   for (int t = 0; t < nthreads; t++) {
     args[t].x = x; args[t].p = p; args[t].bases = bases; args[t].offs = offs; args[t].n = n; args[t].out = out;
+    args[t].multi = multi;
     args[t].cursor = &cursor; args[t].mtx = &mtx;
     if (nthreads == 1) thr_main(&args[t]); else pthread_create(&tid[t], NULL, thr_main, &args[t]);
   }

@@ -36,6 +36,9 @@ int bko_align_reads_one(const bko_index* idx, const bkx_align_params* p, int max
 int bko_align_batch(const bko_index* idx, const bkx_align_params* p, const uint8_t* bases,
                     const uint64_t* offsets, uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats,
                     int nthreads);
+/* same with the -r5 loci of every read: max_ml_matches slots per read (see bkx_align_reads_multi) */
+int bko_align_batch_multi(const bko_index* idx, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
+                          uint32_t n_reads, bkx_read_result* out, bkx_multi_hit* multi, bkx_align_stats* stats, int nthreads);
 
 /* Aligner.cpp:2726-2850, 3055-3489 (ProcessPairedEnds). */
 int bko_pair_reads(const bko_index* idx, const bkx_align_params* p, const bkx_pe_params* pe,

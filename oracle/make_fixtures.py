@@ -230,6 +230,20 @@ def case_lowcopy():
             "r1_R4_X_s3": {"reads": ["r100.fa"], "args": ["-s3", "-r1", "-R4", "-X"]},
         }
         align_runs(d, tmp, "lowcopy.sfx", runs)
+        # -r5: every locus of a multi-hit read becomes its own record, numbered in arrival order (Aligner.cpp:6668-6716)
+        # -- single-threaded so that the numbering is the read order.  CSV (-M0), SAM incl. unaligned (-M6) and the log.
+        meta = json.load(open(os.path.join(d, "runs.json")))
+        for tag, args in {"r5_R5_s3": ["-s3", "-r5", "-R5"], "r5_R3_X_s3": ["-s3", "-r5", "-R3", "-X"],
+                          "r5_R8_s5_e2": ["-s5", "-e2", "-r5", "-R8"]}.items():
+            common = ["align", "-I", "lowcopy.sfx", "-i", "r100.fa", "-T1"] + args
+            run(common + ["-M6", "-o", tag + ".sam", "-F", tag + ".sam.log"], tmp)
+            run(common + ["-M0", "-o", tag + ".csv", "-F", tag + ".log"], tmp)
+            gz(os.path.join(tmp, tag + ".sam"), os.path.join(d, tag + ".sam.gz"))
+            gz(os.path.join(tmp, tag + ".csv"), os.path.join(d, tag + ".csv.gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            strip_log(os.path.join(tmp, tag + ".sam.log"), os.path.join(d, tag + ".sam.log"))
+            meta[tag] = {"reads": ["r100.fa.gz"], "args": args, "all_loci": True}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
 def case_formats():

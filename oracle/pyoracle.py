@@ -48,6 +48,8 @@ def lib():
         L.bko_locate_last_exact.restype = C.c_int64
         L.bko_align_batch.argtypes = [C.c_void_p, C.POINTER(abi.AlignParams), C.c_void_p, C.c_void_p, C.c_uint32,
                                       C.c_void_p, C.POINTER(abi.AlignStats), C.c_int]
+        L.bko_align_batch_multi.argtypes = [C.c_void_p, C.POINTER(abi.AlignParams), C.c_void_p, C.c_void_p, C.c_uint32,
+                                            C.c_void_p, C.c_void_p, C.POINTER(abi.AlignStats), C.c_int]
         L.bko_pair_reads.argtypes = [C.c_void_p, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), C.c_void_p,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(abi.PEStats), C.c_void_p]
         L.bko_seq.argtypes = [C.c_void_p]
@@ -126,6 +128,20 @@ class OracleIndex:
         if rc < 0:
             raise RuntimeError("bko_align_batch failed: %d" % rc)
         return out, st
+
+    def align_multi(self, params, bases, offsets, nthreads=1):
+        """-r5: (records, loci[n, max_ml_matches], stats)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.zeros(n, dtype=abi.RESULT_DTYPE)
+        multi = np.zeros((n, params.max_ml_matches), dtype=abi.MULTI_DTYPE)
+        st = abi.AlignStats()
+        rc = lib().bko_align_batch_multi(self._h, C.byref(params), bases.ctypes.data, offsets.ctypes.data, n,
+                                         out.ctypes.data, multi.ctypes.data, C.byref(st), nthreads)
+        if rc < 0:
+            raise RuntimeError("bko_align_batch_multi failed: %d" % rc)
+        return out, multi, st
 
     def pair(self, params, pe, results, bases=None, offsets=None, len_dist=None):
         n_pairs = len(results) // 2

@@ -1,0 +1,72 @@
+"""GPU: multi-loci options on the low-copy repeat genome (tests/golden/lowcopy, reads hitting 2..9 equally good loci).
+-r5 (every locus returned, bkx_align_reads_multi) against the oracle field by field, hit lists included and in the
+order LocateCoreMultiples discovers them (libbiokanga/SfxArrayV2.cpp:6157-6205); -r1 counts against the oracle.
+Run the file again with BKX_NO_FAST=1 to put the general kernel on the same inputs (done in the round's GPU runs)."""
+import numpy as np
+import pytest
+
+import goldutil as gu
+import pyoracle as po
+from biokanga_b200 import abi
+from biokanga_b200 import lib as bkx
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lowcopy(golden_dir):
+    sfx = gu.sfx_path("lowcopy", golden_dir)
+    run = gu.runs("lowcopy")["r0_s3"]
+    names, bases, offs = gu.load_reads("lowcopy", run)
+    return bkx.Index.open(sfx), po.OracleIndex(sfx), bases, offs
+
+
+@pytest.mark.parametrize("max_subs,mmd,limit,clamp", [(3, 1, 5, 0), (3, 1, 3, 1), (5, 2, 8, 0), (3, 1, 2, 0), (10, 1, 64, 0),
+                                                     (3, 1, 9, 1)])
+def test_all_loci_match_oracle(lowcopy, max_subs, mmd, limit, clamp):
+    gidx, oidx, bases, offs = lowcopy
+    kw = dict(max_subs=max_subs, min_edit_dist=mmd, ml_mode=5, max_ml_matches=limit, clamp_max_ml=clamp)
+    got, gm, gst = gidx.align_multi(gidx.default_params(0, **kw), bases, offs)
+    exp, em, est = oidx.align_multi(oidx.default_params(0, **kw), bases, offs, nthreads=4)
+    for f in abi.RESULT_DTYPE.names:
+        assert np.array_equal(got[f], exp[f]), f
+    acc = got["nar"] == abi.NAR_ACCEPTED
+    # slots [0, num_hits) of accepted reads are defined (the rest may hold candidates of an abandoned higher level)
+    valid = acc[:, None] & (np.arange(limit)[None, :] < got["num_hits"][:, None])
+    assert gm[valid].tobytes() == em[valid].tobytes()
+    assert gst.as_dict() == est.as_dict()
+    assert (got["num_hits"][acc] > 1).sum() > 100        # the regime: many reads with several loci
+    assert got["num_hits"][acc].max() <= limit
+    # every returned locus really carries the read with the stated mismatches
+    seq = np.array(oidx.seq())
+    ents = {e.entry_id: e for e in oidx.entries()}
+    comp = np.array([3, 2, 1, 0, 4], np.uint8)
+    for i in np.nonzero(acc)[0][:400]:
+        rd = bases[offs[i]:offs[i + 1]]
+        for h in gm[i][:got["num_hits"][i]]:
+            e = ents[int(h["chrom_id"])]
+            g = seq[e.start_ofs + int(h["match_loci"]): e.start_ofs + int(h["match_loci"]) + len(rd)]
+            q = comp[rd[::-1]] if chr(int(h["strand"])) == "-" else rd
+            assert int((q != g).sum()) == int(h["mismatches"]) == int(got["low_mm"][i])
+
+
+def test_all_loci_mode_needs_its_own_call(lowcopy):
+    gidx, oidx, bases, offs = lowcopy
+    with pytest.raises(bkx.BkxError):
+        gidx.align(gidx.default_params(0, ml_mode=5, max_ml_matches=5), bases, offs)
+    with pytest.raises(bkx.BkxError):
+        gidx.align_multi(gidx.default_params(0, ml_mode=5, max_ml_matches=100), bases, offs)
+    with pytest.raises(bkx.BkxError):
+        gidx.align(gidx.default_params(0, ml_mode=3, max_ml_matches=5), bases, offs)
+
+
+@pytest.mark.parametrize("limit,clamp", [(5, 0), (2, 0), (4, 1), (20, 0)])
+def test_distribution_mode_matches_oracle(lowcopy, limit, clamp):
+    gidx, oidx, bases, offs = lowcopy
+    kw = dict(max_subs=3, ml_mode=1, max_ml_matches=limit, clamp_max_ml=clamp)
+    got, gst = gidx.align(gidx.default_params(0, **kw), bases, offs)
+    exp, est = oidx.align(oidx.default_params(0, **kw), bases, offs, nthreads=4)
+    for f in abi.RESULT_DTYPE.names:
+        assert np.array_equal(got[f], exp[f]), f
+    assert gst.as_dict() == est.as_dict()
+    assert gst.tot_accepted_multi > 100 and gst.tot_loci_aligned > gst.tot_accepted_aligned
