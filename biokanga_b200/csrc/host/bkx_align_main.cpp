@@ -431,7 +431,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 't': o.title = v; break;
       case 'g': o.qmode = iv; break;
       case '#': if (iv != 1) unsupported.push_back("-# read sampling"); break;
-      case 'r': o.ml_mode = iv; if (iv > 1) unsupported.push_back("-r2..5 multi-loci modes (only -r0 slough and -r1 stats are built)"); break;
+      case 'r': o.ml_mode = iv; if (iv >= 2 && iv <= 4) unsupported.push_back("-r2..4 multi-loci modes (-r0 slough, -r1 stats and -r5 all loci are built)"); break;
       case 'R': o.max_ml = iv; break;  // only meaningful with -r
       case 'c': if (iv) unsupported.push_back("-c chimeric trimming"); break;
       case 'a': if (iv) unsupported.push_back("-a microInDels"); break;
@@ -473,7 +473,12 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
     if (o.max_ml == 0) o.max_ml = 5;  // cDfltMaxMultiHits
-    if (o.max_ml < 2 || o.max_ml > 500) { fprintf(stderr, "Error: multiple aligned reads '-R%d' specified outside of range 2..%d\n", o.max_ml, 500); return -1; }
+    const int lim = o.ml_mode == 5 ? 64 : 500;  // the reference takes up to 100000 with -r5; the per-read slots here hold 64
+    if (o.max_ml < 2 || o.max_ml > lim) { fprintf(stderr, "Error: multiple aligned reads '-R%d' specified outside of range 2..%d\n", o.max_ml, lim); return -1; }
+    if (o.ml_mode == 5 && !(o.fmt == 0 || o.fmt == 4 || o.fmt == 5 || o.fmt == 6)) {  // kanga.cpp:830
+      fprintf(stderr, "Error: '-r5' is only reported as -M0, -M4, -M5 or -M6\n");
+      return -1;
+    }
   } else {
     o.max_ml = 1;
     o.clamp_ml = false;  // kanga.cpp:691-694: -X only counts together with -R
@@ -709,6 +714,9 @@ int main(int argc, char** argv) {
   bool pinned = bkx_pin_host(R.packed.data(), R.packed.size()) >= 0 && bkx_pin_host(R.offs.data(), R.offs.size() * 8) >= 0 &&
                 bkx_pin_host(res.data(), res.size() * sizeof(bkx_read_result)) >= 0;
   if (!pinned) diag("Note: unable to page-lock host buffers (%s); continuing with pageable copies", bkx_last_error());
+  const bool all_loci = o.ml_mode == BKX_ML_ALL;   // -r5: every locus of a read becomes a record of its own
+  std::vector<bkx_multi_hit> multi;
+  if (all_loci) multi.resize((size_t)n * (size_t)o.max_ml);
   std::vector<bkx_align_stats> st((size_t)o.gpus);
   std::vector<int> rcs((size_t)o.gpus, 0);
   std::vector<std::string> errs((size_t)o.gpus);
@@ -720,8 +728,12 @@ int main(int argc, char** argv) {
       memset(&st[(size_t)g], 0, sizeof(bkx_align_stats));
       th.emplace_back([&, g, b, e]() {
         if (e > b) {
-          rcs[(size_t)g] = bkx_align_reads_packed4(idx[(size_t)g], &P, R.packed.data(), R.offs.data() + b, e - b, res.data() + b,
-                                                   &st[(size_t)g]);
+          if (all_loci)
+            rcs[(size_t)g] = bkx_align_reads_multi(idx[(size_t)g], &P, R.bases.data(), R.offs.data() + b, e - b, res.data() + b,
+                                                   multi.data() + (size_t)b * (size_t)o.max_ml, &st[(size_t)g]);
+          else
+            rcs[(size_t)g] = bkx_align_reads_packed4(idx[(size_t)g], &P, R.packed.data(), R.offs.data() + b, e - b, res.data() + b,
+                                                     &st[(size_t)g]);
           if (rcs[(size_t)g] < 0) errs[(size_t)g] = bkx_last_error();
         }
       });
@@ -750,6 +762,41 @@ int main(int argc, char** argv) {
          std::max(1, minl * o.max_subs / 100), std::max(1, maxl * o.max_subs / 100));
   diag("Provisionally accepted %d aligned reads (%d uniquely, %d aligning to multiloci) aligning to a total of %d loci",
        (int)S.tot_accepted_aligned, (int)S.tot_accepted_unique, (int)S.tot_accepted_multi, (int)S.tot_loci_aligned);
+
+  // ---- -r5: the record array is replaced by one record per reported locus, numbered in read order (the reference
+  //      numbers them in arrival order, which is the read order with one thread; WriteHitLoci / AddMultiHit,
+  //      Aligner.cpp:6668-6790, and the swap at :538-560).  Reads without a hit only stay for -M6; reads rejected for
+  //      their Hamming margin or for Ns leave no record at all.
+  std::vector<uint32_t> src;   // record -> read (empty: identity)
+  if (all_loci) {
+    diag("Treating accepted %d multialigned reads as uniquely aligned %d source reads in subsequent processing",
+         (int)S.tot_accepted_multi, (int)(S.tot_loci_aligned - S.tot_accepted_unique));
+    std::vector<bkx_read_result> rec;
+    rec.reserve((size_t)S.tot_loci_aligned + 16);
+    for (uint32_t i = 0; i < n; ++i) {
+      const bkx_read_result& r = res[i];
+      if (r.nar == BKX_NAR_ACCEPTED) {
+        for (int h = 0; h < r.num_hits; ++h) {
+          const bkx_multi_hit& m = multi[(size_t)i * (size_t)o.max_ml + (size_t)h];
+          bkx_read_result q = r;
+          q.num_hits = 1;
+          q.chrom_id = m.chrom_id; q.match_loci = m.match_loci; q.match_len = m.match_len; q.strand = m.strand;
+          q.mismatches = m.mismatches;
+          rec.push_back(q);
+          src.push_back(i);
+        }
+      } else if (o.fmt == 6 && (r.hit_rslt == BKX_HR_NONE || r.hit_rslt == BKX_HR_HITINSTS) && r.nar != BKX_NAR_NS) {
+        bkx_read_result q = r;
+        q.num_hits = 0;
+        rec.push_back(q);
+        src.push_back(i);
+      }
+    }
+    res.swap(rec);
+    std::vector<bkx_multi_hit>().swap(multi);
+  }
+  const uint32_t nrec = (uint32_t)res.size();
+  auto rix = [&](uint32_t i) -> uint32_t { return src.empty() ? i : src[i]; };
 
   // ---- paired ends, Aligner.cpp:2876-3049
   if (o.pe_mode) {
@@ -783,11 +830,15 @@ int main(int argc, char** argv) {
   // ---- summary, Aligner.cpp:3535-3769
   uint64_t nar[BKX_NAR_COUNT] = {0};
   uint64_t plus = 0;
-  for (uint32_t i = 0; i < n; ++i) {
+  for (uint32_t i = 0; i < nrec; ++i) {
     nar[res[i].nar]++;
     if (res[i].nar == BKX_NAR_ACCEPTED && res[i].strand == '+') ++plus;
   }
   uint64_t no_match = nar[BKX_NAR_NOHIT] + S.num_sloughed_ns;
+  if (all_loci) {  // Aligner.cpp:3706-3708, 3727-3730: the non-aligned total of the search stands in for the record count
+    no_match = S.tot_non_aligned + S.num_sloughed_ns;
+    nar[BKX_NAR_NOHIT] = no_match;
+  }
   diag("From %u source reads there are %u accepted alignments, %u on '+' strand, %u on '-' strand", n, (unsigned)nar[BKX_NAR_ACCEPTED],
        (unsigned)plus, (unsigned)(nar[BKX_NAR_ACCEPTED] - plus));
   diag("A further %u multiloci aligned reads could not accepted as hits because they were unresolvable", (unsigned)nar[BKX_NAR_MULTIALIGN]);
@@ -803,8 +854,8 @@ int main(int argc, char** argv) {
   }
 
   // ---- order and write
-  std::vector<uint32_t> order(n);
-  if (bkx_sort_hits(res.data(), n, order.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+  std::vector<uint32_t> order(nrec);
+  if (nrec && bkx_sort_hits(res.data(), nrec, order.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
   std::vector<bkx_entry> ents(info.num_entries + 1);
   for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
   unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
@@ -816,7 +867,7 @@ int main(int argc, char** argv) {
     // UCSC BED: track line then chrom, start, end+1, "ar", score, strand (Aligner.cpp:6355-6362, 6463-6466)
     const char* title = o.title.empty() ? "kanga" : o.title.c_str();
     ob.s += "track type=bed name=\""; ob.s += title; ob.s += "\" description=\""; ob.s += title; ob.s += "\"\n";
-    emit_rows(ob, n, fmt_threads, [&](uint32_t k, std::string& s) {
+    emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
       if (r.nar != BKX_NAR_ACCEPTED) return;
@@ -833,7 +884,7 @@ int main(int argc, char** argv) {
         genome[e].resize(ents[e].seq_len);
         if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
       }
-    emit_rows(ob, n, fmt_threads, [&](uint32_t k, std::string& s) {
+    emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
       if (r.nar != BKX_NAR_ACCEPTED) return;
@@ -842,11 +893,12 @@ int main(int argc, char** argv) {
       append_uint(s, r.match_loci); s += ',';
       append_uint(s, (uint64_t)r.match_loci + r.match_len - 1); s += ',';
       append_uint(s, r.match_len); s += ",\""; s += (char)r.strand; s += "\",0,0,1,";
-      append_uint(s, r.mismatches); s += ",\"N/A\",\""; s += R.name(i); s += '"';
+      const uint32_t ri = rix(i);
+      append_uint(s, r.mismatches); s += ",\"N/A\",\""; s += R.name(ri); s += '"';
       if (o.fmt >= 2) {
         s += ",\"";
-        const uint8_t* b = R.bases.data() + R.offs[i];
-        for (int q = 0; q < R.len(i); ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+        const uint8_t* b = R.bases.data() + R.offs[ri];
+        for (int q = 0; q < R.len(ri); ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
         s += '"';
       }
       if (o.fmt == 1 || o.fmt == 3) {
@@ -864,7 +916,7 @@ int main(int argc, char** argv) {
     Bgzf bz;
     if (!bz.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
     std::vector<char> hit(info.num_entries + 1, 0);
-    for (uint32_t i = 0; i < n; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
+    for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
     bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
     std::vector<int> refid(info.num_entries + 1, -1);
     std::string text = "@HD\tVN:1.4\tSO:coordinate", refs;
@@ -888,7 +940,7 @@ int main(int argc, char** argv) {
     int cur_ref = -1;  // reference whose index block is being accumulated
     uint32_t n_acc = (uint32_t)nar[BKX_NAR_ACCEPTED], seen_acc = 0;
     std::string rec;
-    for (uint32_t k = 0; k < n && ok; ++k) {
+    for (uint32_t k = 0; k < nrec && ok; ++k) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
       bool acc = r.nar == BKX_NAR_ACCEPTED;
@@ -911,9 +963,10 @@ int main(int argc, char** argv) {
           }
         } else flags |= 0x08;
       }
-      const int L = R.len(i);
-      const uint8_t* b = R.bases.data() + R.offs[i];
-      const char* qn = R.name(i);
+      const uint32_t ri = rix(i);
+      const int L = R.len(ri);
+      const uint8_t* b = R.bases.data() + R.offs[ri];
+      const char* qn = R.name(ri);
       uint32_t lname = (uint32_t)strlen(qn) + 1;
       int32_t rid = acc ? refid[r.chrom_id] : -1, pos = acc ? (int32_t)r.match_loci : -1;
       uint32_t bin = acc ? (uint32_t)bai_reg2bin(pos, pos + L) : 0;
@@ -961,7 +1014,7 @@ int main(int argc, char** argv) {
   } else {
     // SAM header: @HD, @SQ for every chromosome (or only those hit if more than -4 threshold), @PG
     std::vector<char> hit(info.num_entries + 1, 0);
-    for (uint32_t i = 0; i < n; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
+    for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
     bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
     ob.s += "@HD\tVN:1.4\tSO:coordinate\n";
     for (uint32_t e = 1; e <= info.num_entries; ++e)
@@ -970,7 +1023,7 @@ int main(int argc, char** argv) {
         append_uint(ob.s, ents[e].seq_len); ob.s += '\n';
       }
     ob.s += "@PG\tID:biokanga\tVN:4.4.2\n";
-    emit_rows(ob, n, fmt_threads, [&](uint32_t k, std::string& s) {
+    emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
       bool acc = r.nar == BKX_NAR_ACCEPTED;
@@ -994,16 +1047,17 @@ int main(int argc, char** argv) {
           }
         } else flags |= 0x08;
       }
-      s += R.name(i); s += '\t';
+      const uint32_t ri = rix(i);
+      s += R.name(ri); s += '\t';
       append_uint(s, (uint64_t)flags); s += '\t';
       if (acc) { s += ents[r.chrom_id].name; s += '\t'; append_uint(s, (uint64_t)r.match_loci + 1); }
       else s += "*\t0";
       s += "\t255\t";
-      append_uint(s, (uint64_t)R.len(i)); s += "M\t";
+      append_uint(s, (uint64_t)R.len(ri)); s += "M\t";
       if (acc && pnext >= 0) { s += "=\t"; append_uint(s, (uint64_t)pnext + 1); s += '\t'; append_uint(s, (uint64_t)tlen); s += '\t'; }
       else s += "*\t0\t0\t";
-      const uint8_t* b = R.bases.data() + R.offs[i];
-      int L = R.len(i);
+      const uint8_t* b = R.bases.data() + R.offs[ri];
+      int L = R.len(ri);
       if (acc && r.strand != '+') {
         for (int q = L - 1; q >= 0; --q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
       } else {

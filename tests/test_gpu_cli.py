@@ -15,7 +15,8 @@ CLI = os.path.join(os.path.dirname(bkx.LIB_PATH), "bkx-align")
 RUNS = [("tiny", "r100_s3"), ("tiny", "r100_s5_e2"), ("tiny", "mixed_s3"), ("tiny", "r251_s6"), ("tiny", "r100_s3_Q2"),
         ("tiny", "r100_s4_m2"), ("tiny", "pe_U2"), ("tiny", "pe_U4"), ("tiny", "pe_U1"), ("tiny", "pe_U3"),
         ("tiny", "pe_U1_far"), ("repeats", "r100_s3_m3"), ("repeats", "r60_s5"), ("lowcopy", "r1_R5_s3"),
-        ("lowcopy", "r1_R4_X_s3"), ("lowcopy", "r1_R20_s5_e2")]
+        ("lowcopy", "r1_R4_X_s3"), ("lowcopy", "r1_R20_s5_e2"), ("lowcopy", "r5_R5_s3"), ("lowcopy", "r5_R3_X_s3"),
+        ("lowcopy", "r5_R8_s5_e2")]
 
 
 def summary_block(path):
@@ -169,3 +170,23 @@ def test_cli_chunked_parallel_parse_gives_the_same_files(case, tag, golden_dir, 
     assert ours == ref
     exp_log = open(os.path.join(gu.GOLD, case, tag + ".log")).read().splitlines()
     assert summary_block(tmp_path / "o.log") == exp_log
+
+
+@pytest.mark.parametrize("tag", ["r5_R5_s3", "r5_R3_X_s3", "r5_R8_s5_e2"])
+def test_cli_all_loci_mode_sam_log_and_numbering(tag, golden_dir, tmp_path):
+    """-r5 with -M6: reads without a locus stay in the record set, so the summary differs from the -M0 run -- compared
+    with the reference's own -M6 log; and the CSV keeps the reference's record numbering (one record per locus, in
+    read order) when compared line by line, not just as a set."""
+    run = gu.runs("lowcopy")[tag]
+    sfx = gu.sfx_path("lowcopy", golden_dir)
+    rd = os.path.join(gu.GOLD, "lowcopy", run["reads"][0])
+    base = [CLI, "align", "-I", sfx, "-i", rd] + run["args"]
+    subprocess.run(base + ["-M6", "-o", str(tmp_path / "o.sam"), "-F", str(tmp_path / "o.log")], check=True,
+                   stdout=subprocess.DEVNULL)
+    exp = [x for x in open(os.path.join(gu.GOLD, "lowcopy", tag + ".sam.log")).read().splitlines()
+           if not x.startswith(("Sorting alignments", "Header written", "Reported SAM", "Completed reporting SAM"))]
+    assert summary_block(tmp_path / "o.log") == exp
+    subprocess.run(base + ["-M0", "-o", str(tmp_path / "o.csv")], check=True, stdout=subprocess.DEVNULL)
+    ours = {ln.split(",", 1)[0]: ln for ln in open(tmp_path / "o.csv").read().splitlines()}
+    ref = {ln.split(",", 1)[0]: ln for ln in gzip.open(os.path.join(gu.GOLD, "lowcopy", tag + ".csv.gz"), "rt").read().splitlines()}
+    assert ours == ref
