@@ -30,11 +30,14 @@ def runs(case):
     return json.load(open(os.path.join(GOLD, case, "runs.json")))
 
 
-def all_runs():
+def all_runs(all_loci=True):
+    """Every (case, tag); all_loci=False leaves out the -r5 runs (one record per locus: they have their own checks)."""
     out = []
     for case in CASES:
-        for tag in sorted(runs(case)):
-            out.append((case, tag))
+        rs = runs(case)
+        for tag in sorted(rs):
+            if all_loci or not rs[tag].get("all_loci"):
+                out.append((case, tag))
     return out
 
 

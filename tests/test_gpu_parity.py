@@ -38,7 +38,7 @@ def indexes(case, golden_dir):
     return _CACHE[case]
 
 
-@pytest.mark.parametrize("case,tag", gu.all_runs())
+@pytest.mark.parametrize("case,tag", gu.all_runs(all_loci=False))
 def test_cuda_matches_oracle_and_reference(case, tag, golden_dir):
     run = gu.runs(case)[tag]
     gidx, oidx = indexes(case, golden_dir)

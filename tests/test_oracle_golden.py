@@ -15,6 +15,8 @@ def test_oracle_matches_reference(case, tag, golden_dir):
     idx = po.OracleIndex(gu.sfx_path(case, golden_dir))
     p, pe = gu.params_from_args(idx, run["args"])
     names, bases, offs = gu.load_reads(case, run)
+    if run.get("all_loci"):
+        return check_all_loci(case, tag, idx, p, names, bases, offs)
     res, st = idx.align(p, bases, offs, nthreads=4)
     if pe is not None:
         idx.pair(p, pe, res, bases, offs)
@@ -35,3 +37,30 @@ def test_oracle_matches_reference(case, tag, golden_dir):
     assert m, "summary line missing"
     assert (st.tot_accepted_aligned, st.tot_accepted_unique, st.tot_accepted_multi, st.tot_loci_aligned) == tuple(
         int(v) for v in m.groups())
+
+
+def check_all_loci(case, tag, idx, p, names, bases, offs):
+    """-r5 runs: one CSV row per reported locus, numbered in read order (the fixtures were made with one thread)."""
+    import csv
+    import gzip
+    import os
+    res, multi, st = idx.align_multi(p, bases, offs, nthreads=4)
+    ents = {e.entry_id: e.name.decode() if isinstance(e.name, bytes) else e.name for e in idx.entries()}
+    got = []
+    for i in range(len(names)):
+        if res["nar"][i] == abi.NAR_ACCEPTED:
+            for h in multi[i][:res["num_hits"][i]]:
+                got.append((names[i], ents[int(h["chrom_id"])], int(h["match_loci"]), chr(int(h["strand"])), int(h["mismatches"])))
+    exp = {}
+    with gzip.open(os.path.join(gu.GOLD, case, tag + ".csv.gz"), "rt") as f:
+        for row in csv.reader(f):
+            exp[int(row[0])] = (row[13], row[3], int(row[4]), row[7], int(row[11]))
+    assert len(got) == len(exp)
+    assert got == [exp[k] for k in sorted(exp)]          # same loci, same order, same numbering
+    log = gu.log_stats(case, tag)
+    m = re.search(r"Provisionally accepted (\d+) aligned reads \((\d+) uniquely, (\d+) aligning to multiloci\) "
+                  r"aligning to a total of (\d+) loci", log)
+    assert (st.tot_accepted_aligned, st.tot_accepted_unique, st.tot_accepted_multi, st.tot_loci_aligned) == tuple(
+        int(v) for v in m.groups())
+    m = re.search(r"Unable to align (\d+) source reads of which (\d+)", log)
+    assert (st.tot_non_aligned + st.num_sloughed_ns, st.num_sloughed_ns) == tuple(int(v) for v in m.groups())
