@@ -267,13 +267,16 @@ def run_bkx(args):
     hst = abi.AlignStats()
     h_res_np = h_out.numpy().view(abi.RESULT_DTYPE)
 
+    h_pst = abi.PEStats()
+
     def e2e_call(packed):
-        if packed:
+        if pe_mode:  # align + pair fused: every slice is paired (orphans recovered) while it is still on the GPU
+            idx.align_pairs_ptr(p, pe, (h_packed if packed else h_bases).data_ptr(), h_offs.data_ptr(), nreads // 2,
+                                h_out.data_ptr(), hst, h_pst, None, packed=packed)
+        elif packed:
             idx.align_packed4_ptr(p, h_packed.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
         else:
             idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
-        if pe_mode:
-            idx.pair(p, pe, h_res_np, h_bases.numpy(), h_offs.numpy().view(np.uint64))
 
     def time_e2e(packed):
         e2e_call(packed)  # warm-up
@@ -319,8 +322,9 @@ def run_bkx(args):
         "e2e": {"value": e2e_value, "unit": "reads/s",
                 "h2d_bytes_per_step": int((nreads * args.read_len + 1) // 2 + (nreads + 1) * 8),
                 "d2h_bytes_per_step": int(nreads * 32), "matches_device_run": same,
-                "call": "bkx_align_reads_packed4 (pinned host buffers, reads 4-bit packed)",
-                "byte_per_base_call": {"value": e2e_bytes_value, "call": "bkx_align_reads",
+                "call": ("bkx_align_pairs_packed4" if pe_mode else "bkx_align_reads_packed4") +
+                        " (pinned host buffers, reads 4-bit packed)",
+                "byte_per_base_call": {"value": e2e_bytes_value, "call": "bkx_align_pairs" if pe_mode else "bkx_align_reads",
                                        "h2d_bytes_per_step": int(nreads * args.read_len + (nreads + 1) * 8)}},
         "gpu_launches": int(args.steps * launches_per_step),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

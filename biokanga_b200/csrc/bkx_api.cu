@@ -61,6 +61,8 @@ struct Slot {
   size_t packed_cap = 0;
   bkx_multi_hit* d_multi = nullptr;   // -r5 loci of the slice's reads
   size_t multi_cap = 0;
+  uint32_t* d_orphans = nullptr;      // fused PE call: pairs of the slice whose mate needs recovery
+  size_t orphans_cap = 0;
   uint64_t* d_offs = nullptr;
   bkx_read_result* d_out = nullptr;
   uint32_t* d_hard = nullptr;   // reads the fast kernel deferred to the general kernel
@@ -298,6 +300,7 @@ extern "C" void bkx_close_index(bkx_index* x) {
     if (x->slot[s].d_bases) cudaFree(x->slot[s].d_bases);
     if (x->slot[s].d_packed) cudaFree(x->slot[s].d_packed);
     if (x->slot[s].d_multi) cudaFree(x->slot[s].d_multi);
+    if (x->slot[s].d_orphans) cudaFree(x->slot[s].d_orphans);
     if (x->slot[s].d_offs) cudaFree(x->slot[s].d_offs);
     if (x->slot[s].d_out) cudaFree(x->slot[s].d_out);
     if (x->slot[s].d_hard) cudaFree(x->slot[s].d_hard);
@@ -814,12 +817,30 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
   return BKX_OK;
 }
 
+struct PeCall {   // the pairing half of a fused align + pair call
+  const bkx_pe_params* pe = nullptr;
+  bkx_pe_stats* stats = nullptr;
+  uint32_t* len_dist = nullptr;
+};
+
 static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, bool packed4, const uint64_t* offsets,
-                      uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats, bkx_multi_hit* multi = nullptr) {
+                      uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats, bkx_multi_hit* multi = nullptr,
+                      const PeCall* pec = nullptr) {
   if (!x || !bases || !offsets || !out) return fail(BKX_ERR_PARAM, "null argument");
   KParams k;
   int rc = check_params(p, &k);
   if (rc < 0) return rc;
+  bool rescue = false;
+  if (pec) {
+    const bkx_pe_params* pe = pec->pe;
+    if (!pe) return fail(BKX_ERR_PARAM, "null argument");
+    if (pe->pe_proc < BKX_PE_ORPHAN || pe->pe_proc > BKX_PE_UNIQUE_SE) return fail(BKX_ERR_PARAM, "bad pe_proc %d", pe->pe_proc);
+    if (pe->pair_min_len < 25 || pe->pair_max_len > 100000 || pe->pair_min_len > pe->pair_max_len)
+      return fail(BKX_ERR_PARAM, "bad insert size range %d..%d", pe->pair_min_len, pe->pair_max_len);
+    if (n_reads & 1) return fail(BKX_ERR_PARAM, "paired reads come in twos");
+    if (p->ml_mode != BKX_ML_DEFAULT) return fail(BKX_ERR_PARAM, "multi-loci modes do not combine with paired ends (kanga.cpp:535)");
+    rescue = pe->pe_proc == BKX_PE_ORPHAN || pe->pe_proc == BKX_PE_ORPHAN_SE;
+  }
   if ((p->ml_mode == BKX_ML_ALL) != (multi != nullptr))
     return fail(BKX_ERR_PARAM, "ml_mode -r5 and bkx_align_reads_multi go together");
   if (n_reads == 0) return BKX_OK;
@@ -827,6 +848,11 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
   CU(cudaSetDevice(x->device));
   int W = 0;
   CU(cudaMemsetAsync(x->d_stats, 0, sizeof(bkx_align_stats), x->slot[0].st));
+  if (pec) {
+    if (!x->d_len_dist) CU(cudaMalloc((void**)&x->d_len_dist, 100001 * 4));
+    CU(cudaMemsetAsync(x->d_len_dist, 0, 100001 * 4, x->slot[0].st));
+    CU(cudaMemsetAsync(x->d_pe_stats, 0, sizeof(bkx_pe_stats), x->slot[0].st));
+  }
   CU(cudaStreamSynchronize(x->slot[0].st));
   // Slice sizes: start small (the first H2D is exposed), grow to kMaxSlice (every slice pays ~0.3 ms of persistent-
   // kernel ramp-up and tail; much larger slices stall on their own H2D), shrink towards the end (the last D2H is
@@ -865,6 +891,7 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     if (cnt > left || left - cnt < kMinSlice / 2) cnt = left;
     ramp = std::min<uint64_t>(kMaxSlice, (uint64_t)ramp * 2);
     while (cnt > 1 && offsets[start + cnt] - offsets[start] > kBatchBases) cnt = (cnt + 1) / 2;
+    if (pec && (cnt & 1)) cnt += (cnt < left) ? 1 : 0;  // PE1 / PE2 of a pair stay in one slice
     uint64_t nb = offsets[start + cnt] - offsets[start];
     // longest read of this slice (overlaps with the GPU work of the previous slices)
     uint64_t max_len = 0;
@@ -940,6 +967,22 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     // offsets stay absolute: hand the kernel a base pointer shifted by the slice start
     if ((rc = launch_both(x, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard,
                           x->cst)) < 0) return rc;
+    if (pec) {  // pair the slice's reads while they are still on the device (ProcessPairedEnds, Aligner.cpp:2876-3049)
+      unsigned int* cur = x->d_cursor[b];
+      if ((size_t)cnt / 2 > s.orphans_cap) {
+        if (s.d_orphans) cudaFree(s.d_orphans);
+        s.orphans_cap = (size_t)cnt / 2 * 5 / 4 + 16;
+        CU(cudaMalloc((void**)&s.d_orphans, s.orphans_cap * 4));
+      }
+      CU(cudaMemsetAsync(cur + 3, 0, sizeof(unsigned int), x->cst));
+      CU(launch_pair(*pec->pe, s.d_out, cnt / 2, x->d_pe_stats, x->d_len_dist, s.d_orphans, cur + 3, x->cst));
+      x->launches += 1;
+      if (rescue) {
+        CU(launch_rescue(x->d, k, *pec->pe, s.d_out, s.d_orphans, cur + 3, s.d_bases - offsets[start], s.d_offs,
+                         std::max<int>((int)max_len, 32), x->d_pe_stats, x->d_len_dist, cur, x->cst));
+        x->launches += 1;
+      }
+    }
     CU(cudaEventRecord(s.k1, x->cst));
     mark(x->cst);
     CU(cudaStreamWaitEvent(s.st, s.k1, 0));
@@ -978,7 +1021,37 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     const uint64_t* s = (const uint64_t*)&h;
     for (size_t i = 0; i < sizeof(h) / 8; ++i) d[i] += s[i];
   }
+  if (pec && pec->stats) {
+    bkx_pe_stats h;
+    CU(cudaMemcpy(&h, x->d_pe_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    uint64_t* d = (uint64_t*)pec->stats;
+    const uint64_t* s = (const uint64_t*)&h;
+    for (size_t i = 0; i < sizeof(h) / 8; ++i) d[i] += s[i];
+  }
+  if (pec && pec->len_dist) {
+    std::vector<uint32_t> ld(100001);
+    CU(cudaMemcpy(ld.data(), x->d_len_dist, 100001 * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ld.size(); ++i) pec->len_dist[i] += ld[i];
+  }
   return BKX_OK;
+}
+
+extern "C" int bkx_align_pairs(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, const uint8_t* bases,
+                               const uint64_t* offsets, uint32_t n_pairs, bkx_read_result* out, bkx_align_stats* stats,
+                               bkx_pe_stats* pe_stats, uint32_t* len_dist) {
+  if (n_pairs > 0x7fffffffu) return fail(BKX_ERR_PARAM, "too many pairs");
+  PeCall pc;
+  pc.pe = pe; pc.stats = pe_stats; pc.len_dist = len_dist;
+  return align_host(x, p, bases, false, offsets, 2 * n_pairs, out, stats, nullptr, &pc);
+}
+
+extern "C" int bkx_align_pairs_packed4(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, const uint8_t* packed,
+                                       const uint64_t* offsets, uint32_t n_pairs, bkx_read_result* out, bkx_align_stats* stats,
+                                       bkx_pe_stats* pe_stats, uint32_t* len_dist) {
+  if (n_pairs > 0x7fffffffu) return fail(BKX_ERR_PARAM, "too many pairs");
+  PeCall pc;
+  pc.pe = pe; pc.stats = pe_stats; pc.len_dist = len_dist;
+  return align_host(x, p, packed, true, offsets, 2 * n_pairs, out, stats, nullptr, &pc);
 }
 
 extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,

@@ -717,6 +717,13 @@ int main(int argc, char** argv) {
   const bool all_loci = o.ml_mode == BKX_ML_ALL;   // -r5: every locus of a read becomes a record of its own
   std::vector<bkx_multi_hit> multi;
   if (all_loci) multi.resize((size_t)n * (size_t)o.max_ml);
+  // paired ends: aligned and paired in one pass over the data (each GPU pairs its own contiguous, even-sized range)
+  bkx_pe_params PE;
+  memset(&PE, 0, sizeof(PE));
+  PE.pe_proc = o.pe_mode; PE.pair_min_len = o.pair_min; PE.pair_max_len = o.pair_max; PE.pair_strand = o.pair_strand;
+  PE.circularised = o.pe_circ;
+  std::vector<bkx_pe_stats> pst((size_t)o.gpus);
+  for (auto& q : pst) memset(&q, 0, sizeof(q));
   std::vector<bkx_align_stats> st((size_t)o.gpus);
   std::vector<int> rcs((size_t)o.gpus, 0);
   std::vector<std::string> errs((size_t)o.gpus);
@@ -728,7 +735,10 @@ int main(int argc, char** argv) {
       memset(&st[(size_t)g], 0, sizeof(bkx_align_stats));
       th.emplace_back([&, g, b, e]() {
         if (e > b) {
-          if (all_loci)
+          if (o.pe_mode)
+            rcs[(size_t)g] = bkx_align_pairs_packed4(idx[(size_t)g], &P, &PE, R.packed.data(), R.offs.data() + b, (e - b) / 2,
+                                                     res.data() + b, &st[(size_t)g], &pst[(size_t)g], nullptr);
+          else if (all_loci)
             rcs[(size_t)g] = bkx_align_reads_multi(idx[(size_t)g], &P, R.bases.data(), R.offs.data() + b, e - b, res.data() + b,
                                                    multi.data() + (size_t)b * (size_t)o.max_ml, &st[(size_t)g]);
           else
@@ -804,15 +814,11 @@ int main(int argc, char** argv) {
     diag("Generating paired reads index over %d paired reads", n / 2);
     diag("Starting to associate Paired End reads to be within insert size range ...");
     diag("Processed putative 0 pairs, accepted 0");
-    bkx_pe_params PE;
-    memset(&PE, 0, sizeof(PE));
-    PE.pe_proc = o.pe_mode; PE.pair_min_len = o.pair_min; PE.pair_max_len = o.pair_max; PE.pair_strand = o.pair_strand;
-    PE.circularised = o.pe_circ;
-    bkx_pe_stats ps;
-    memset(&ps, 0, sizeof(ps));
-    if (bkx_pair_reads(idx[0], &P, &PE, res.data(), n / 2, R.bases.data(), R.offs.data(), &ps, nullptr) < 0) {
-      diag("Fatal: %s", bkx_last_error());
-      return 1;
+    bkx_pe_stats ps = pst[0];
+    for (int g = 1; g < o.gpus; ++g) {
+      uint64_t* d = (uint64_t*)&ps;
+      const uint64_t* q = (const uint64_t*)&pst[(size_t)g];
+      for (size_t k = 0; k < sizeof(ps) / 8; ++k) d[k] += q[k];
     }
     diag("Completed association of Paired End reads from %u pairs, accepted %u pairs", n / 2, (unsigned)ps.accepted_num_paired);
     diag("From %d Paired End pairs there were %d accepted (of which %d pairs were from recovered orphans)", (int)(n / 2),

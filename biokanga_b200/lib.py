@@ -24,7 +24,7 @@ EXPORTS = [
     "bkx_align_one", "bkx_pair_reads", "bkx_last_kernel_ms", "bkx_kernel_launches",
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
     "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
-    "bkx_pack_bases4", "bkx_align_reads_multi",
+    "bkx_pack_bases4", "bkx_align_reads_multi", "bkx_align_pairs", "bkx_align_pairs_packed4",
 ]
 
 
@@ -65,6 +65,9 @@ def lib():
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_pack_bases4.argtypes = [vp, u64, vp]
+    for fn in (L.bkx_align_pairs, L.bkx_align_pairs_packed4):
+        fn.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats),
+                       C.POINTER(abi.PEStats), vp]
     L.bkx_align_reads_multi.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, vp, C.POINTER(abi.AlignStats)]
     L.bkx_clone_index.argtypes = [vp, i32, C.POINTER(vp)]
     L.bkx_close_index.argtypes = [vp]
@@ -229,6 +232,25 @@ class Index:
         """Same, raw host pointers (pinned buffers owned by the caller)."""
         st = C.byref(stats) if stats is not None else None
         check(lib().bkx_align_reads(self._h, C.byref(params), bases_ptr, offsets_ptr, n_reads, out_ptr, st))
+
+    def align_pairs_ptr(self, params, pe, reads_ptr, offsets_ptr, n_pairs, out_ptr, stats=None, pe_stats=None,
+                        len_dist_ptr=None, packed=False):
+        """Fused align + pair on raw host pointers; reads one byte per base, or 4-bit packed with packed=True."""
+        fn = lib().bkx_align_pairs_packed4 if packed else lib().bkx_align_pairs
+        check(fn(self._h, C.byref(params), C.byref(pe), reads_ptr, offsets_ptr, n_pairs, out_ptr,
+                 C.byref(stats) if stats is not None else None, C.byref(pe_stats) if pe_stats is not None else None,
+                 len_dist_ptr))
+
+    def align_pairs(self, params, pe, bases, offsets, packed=False, len_dist=None):
+        """Fused align + pair: (records, align stats, PE stats)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.zeros(n, dtype=abi.RESULT_DTYPE)
+        st, ps = abi.AlignStats(), abi.PEStats()
+        self.align_pairs_ptr(params, pe, bases.ctypes.data, offsets.ctypes.data, n // 2, out.ctypes.data, st, ps,
+                             len_dist.ctypes.data if len_dist is not None else None, packed)
+        return out, st, ps
 
     def align_multi(self, params, bases, offsets):
         """-r5 (params.ml_mode = 5): (records, loci[n, max_ml_matches], stats)."""

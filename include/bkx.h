@@ -258,6 +258,18 @@ int bkx_pair_reads_device(bkx_index* idx, const bkx_align_params* p, const bkx_p
                           uint32_t n_pairs, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t max_read_len,
                           bkx_pe_stats* d_stats, uint32_t* d_len_dist, void* cuda_stream);
 
+/* Alignment and pairing of paired-end reads in ONE pass over the data: reads 2i / 2i+1 are PE1 / PE2 of pair i; each
+ * slice of the internal pipeline is aligned and then paired (and its orphans recovered) while it is still on the GPU, so
+ * the reads cross PCIe once.  Same records, counters and histogram as bkx_align_reads followed by bkx_pair_reads
+ * (CAligner::ProcCoredApprox then ProcessPairedEnds, Aligner.cpp:8943-9527, 2876-3049).  The _packed4 form takes the
+ * reads 4-bit packed (see bkx_align_reads_packed4).  stats / pe_stats / len_dist (100001 u32) are accumulated into. */
+int bkx_align_pairs(bkx_index* idx, const bkx_align_params* params, const bkx_pe_params* pe, const uint8_t* bases,
+                    const uint64_t* offsets, uint32_t n_pairs, bkx_read_result* out, bkx_align_stats* stats,
+                    bkx_pe_stats* pe_stats, uint32_t* len_dist);
+int bkx_align_pairs_packed4(bkx_index* idx, const bkx_align_params* params, const bkx_pe_params* pe, const uint8_t* packed,
+                            const uint64_t* offsets, uint32_t n_pairs, bkx_read_result* out, bkx_align_stats* stats,
+                            bkx_pe_stats* pe_stats, uint32_t* len_dist);
+
 /* ---- output order: replaces CAligner::SortReadHits(eRSMHitMatch) + SortHitMatch (Aligner.cpp:9917-9991,
  * 10067-10114).  order_out[k] = index of the k-th record under the reference's hit ordering (NAR class; uniquely
  * hit records by chromosome id, locus, match length, strand, mismatches; the others by NumHits); ties, which the

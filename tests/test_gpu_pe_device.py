@@ -53,3 +53,12 @@ def test_device_pe_pipeline_matches_oracle(mode, dmin, dmax):
     if mode in (abi.PE_ORPHAN, abi.PE_ORPHAN_SE):
         assert ost.partner_paired > 0  # recovery really ran
     assert ost.accepted_num_paired > 0.25 * n_pairs
+    # the fused host calls (align + pair per pipeline slice, reads cross PCIe once): same records, counters, histogram
+    for packed in (False, True):
+        ld2 = np.zeros(100001, dtype=np.uint32)
+        rd = bkx.pack_bases4(bases) if packed else bases
+        fused, fst, fps = gidx.align_pairs(p, pe, rd, offs, packed=packed, len_dist=ld2)
+        assert fused.tobytes() == got.tobytes()
+        assert bytes(fps) == bytes(ost)
+        assert np.array_equal(ld2, ld)
+        assert fst.reads == 2 * n_pairs
