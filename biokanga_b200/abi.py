@@ -47,6 +47,11 @@ class PEParams(C.Structure):
                 ("pair_strand", C.c_int32), ("circularised", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class ClusterStats(C.Structure):
+    _fields_ = [("multi_reads", C.c_uint32), ("putative", C.c_uint32), ("assigned", C.c_uint32),
+                ("near_unique", C.c_uint32), ("near_multi", C.c_uint32), ("reserved", C.c_uint32 * 3)]
+
+
 class PEStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("unaligned_pairs", "accepted_num_paired", "accepted_num_se",
                                           "partner_paired", "partner_unpaired", "num_filtered_by_chrom",

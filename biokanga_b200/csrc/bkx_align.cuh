@@ -57,7 +57,7 @@ static __device__ __noinline__ bkx_read_result make_result(const DevIndex& I, co
   res.hit_rslt = (uint8_t)hr;
   switch (hr) {
     case BKX_HR_HITS:
-      if (inst == 1 || P.ml_mode != BKX_ML_DIST) {  // a unique hit (or, outside -r1, the first of several)
+      if (inst == 1 || P.ml_mode == BKX_ML_DEFAULT || P.ml_mode == BKX_ML_ALL) {  // unique, or every locus is wanted
         res.nar = BKX_NAR_ACCEPTED;
         res.num_hits = (P.ml_mode == BKX_ML_ALL) ? (uint8_t)inst : 1;
         res.strand = hit_strand ? '-' : '+';
@@ -66,7 +66,7 @@ static __device__ __noinline__ bkx_read_result make_result(const DevIndex& I, co
         res.match_len = (uint16_t)L;
         res.mismatches = (uint8_t)hit_mm;
         res.low_hit_instances = (P.ml_mode == BKX_ML_ALL) ? (int16_t)inst : 1;
-      } else {                                      // -r1: counted, not placed (:9383-9386)
+      } else {                                      // -r1 / -r3 / -r4: counted, not placed (:9383-9397)
         res.nar = BKX_NAR_MULTIALIGN;
         res.low_hit_instances = (int16_t)inst;
       }

@@ -665,11 +665,11 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   } else if (p->ml_mode == BKX_ML_DIST) {
     if (p->max_ml_matches < 2 || p->max_ml_matches > 500)  // cMaxMultiHits, Aligner.h:62
       return fail(BKX_ERR_PARAM, "max_ml_matches %d out of range 2..500", p->max_ml_matches);
-  } else if (p->ml_mode == BKX_ML_ALL) {
-    if (p->max_ml_matches < 2 || p->max_ml_matches > 64)  // the reference allows 100000 (cMaxAllHits); the per-read slots here 64
-      return fail(BKX_ERR_UNSUPPORTED, "max_ml_matches %d with -r5: 2..64 loci per read are supported", p->max_ml_matches);
+  } else if (p->ml_mode == BKX_ML_ALL || p->ml_mode == BKX_ML_UNIQ || p->ml_mode == BKX_ML_MULTI) {
+    if (p->max_ml_matches < 2 || p->max_ml_matches > 64)  // the reference allows 500 (100000 with -r5); the per-read slots here 64
+      return fail(BKX_ERR_UNSUPPORTED, "max_ml_matches %d with -r3..5: 2..64 loci per read are supported", p->max_ml_matches);
   } else {
-    return fail(BKX_ERR_UNSUPPORTED, "ml_mode %d: -r0, -r1 and -r5 are built (-r2 is not reproducible, -r3/-r4 are not built yet)", p->ml_mode);
+    return fail(BKX_ERR_UNSUPPORTED, "ml_mode %d: -r2 picks a locus with libc rand() in the reference and is not reproducible", p->ml_mode);
   }
   if (p->min_core_len < 4 || p->min_core_len > 100) return fail(BKX_ERR_PARAM, "bad min_core_len %d", p->min_core_len);
   if (p->max_num_slides < 1 || p->max_num_slides > 16) return fail(BKX_ERR_PARAM, "bad max_num_slides %d", p->max_num_slides);
@@ -794,7 +794,7 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
   KParams k;
   int rc = check_params(p, &k);
   if (rc < 0) return rc;
-  if (p->ml_mode == BKX_ML_ALL) return fail(BKX_ERR_UNSUPPORTED, "-r5 needs the host call bkx_align_reads_multi");
+  if (p->ml_mode >= BKX_ML_UNIQ) return fail(BKX_ERR_UNSUPPORTED, "-r3..5 need the host call bkx_align_reads_multi");
   if (n_reads == 0) return BKX_OK;
   std::lock_guard<std::mutex> lk(x->mtx);
   CU(cudaSetDevice(x->device));
@@ -841,8 +841,8 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     if (p->ml_mode != BKX_ML_DEFAULT) return fail(BKX_ERR_PARAM, "multi-loci modes do not combine with paired ends (kanga.cpp:535)");
     rescue = pe->pe_proc == BKX_PE_ORPHAN || pe->pe_proc == BKX_PE_ORPHAN_SE;
   }
-  if ((p->ml_mode == BKX_ML_ALL) != (multi != nullptr))
-    return fail(BKX_ERR_PARAM, "ml_mode -r5 and bkx_align_reads_multi go together");
+  if ((p->ml_mode >= BKX_ML_UNIQ) != (multi != nullptr))
+    return fail(BKX_ERR_PARAM, "ml_mode -r3..5 and bkx_align_reads_multi go together");
   if (n_reads == 0) return BKX_OK;
   std::lock_guard<std::mutex> lk(x->mtx);
   CU(cudaSetDevice(x->device));

@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     int nh = 1;
     if constexpr (MLX) {
       if (P.clamp_ml && hr == BKX_HR_HITINSTS) { ii = P.max_hits; hr = BKX_HR_HITS; }
-      multi = hr == BKX_HR_HITS && ii > 1 && P.ml_mode == BKX_ML_DIST;
+      multi = hr == BKX_HR_HITS && ii > 1 && P.ml_mode != BKX_ML_ALL && P.ml_mode != BKX_ML_DEFAULT;
       if (P.ml_mode == BKX_ML_ALL) nh = ii;
     }
     res.hit_rslt = (uint8_t)hr;

@@ -431,7 +431,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 't': o.title = v; break;
       case 'g': o.qmode = iv; break;
       case '#': if (iv != 1) unsupported.push_back("-# read sampling"); break;
-      case 'r': o.ml_mode = iv; if (iv >= 2 && iv <= 4) unsupported.push_back("-r2..4 multi-loci modes (-r0 slough, -r1 stats and -r5 all loci are built)"); break;
+      case 'r': o.ml_mode = iv; if (iv == 2) unsupported.push_back("-r2 (random locus: libc rand() in the reference, not reproducible)"); break;
       case 'R': o.max_ml = iv; break;  // only meaningful with -r
       case 'c': if (iv) unsupported.push_back("-c chimeric trimming"); break;
       case 'a': if (iv) unsupported.push_back("-a microInDels"); break;
@@ -473,7 +473,7 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
     if (o.max_ml == 0) o.max_ml = 5;  // cDfltMaxMultiHits
-    const int lim = o.ml_mode == 5 ? 64 : 500;  // the reference takes up to 100000 with -r5; the per-read slots here hold 64
+    const int lim = o.ml_mode >= 3 ? 64 : 500;  // the reference takes 500 (100000 with -r5); the per-read slots here hold 64
     if (o.max_ml < 2 || o.max_ml > lim) { fprintf(stderr, "Error: multiple aligned reads '-R%d' specified outside of range 2..%d\n", o.max_ml, lim); return -1; }
     if (o.ml_mode == 5 && !(o.fmt == 0 || o.fmt == 4 || o.fmt == 5 || o.fmt == 6)) {  // kanga.cpp:830
       fprintf(stderr, "Error: '-r5' is only reported as -M0, -M4, -M5 or -M6\n");
@@ -715,8 +715,9 @@ int main(int argc, char** argv) {
                 bkx_pin_host(res.data(), res.size() * sizeof(bkx_read_result)) >= 0;
   if (!pinned) diag("Note: unable to page-lock host buffers (%s); continuing with pageable copies", bkx_last_error());
   const bool all_loci = o.ml_mode == BKX_ML_ALL;   // -r5: every locus of a read becomes a record of its own
+  const bool clustered = o.ml_mode == BKX_ML_UNIQ || o.ml_mode == BKX_ML_MULTI;   // -r3 / -r4: one locus by clustering
   std::vector<bkx_multi_hit> multi;
-  if (all_loci) multi.resize((size_t)n * (size_t)o.max_ml);
+  if (all_loci || clustered) multi.resize((size_t)n * (size_t)o.max_ml);
   // paired ends: aligned and paired in one pass over the data (each GPU pairs its own contiguous, even-sized range)
   bkx_pe_params PE;
   memset(&PE, 0, sizeof(PE));
@@ -738,7 +739,7 @@ int main(int argc, char** argv) {
           if (o.pe_mode)
             rcs[(size_t)g] = bkx_align_pairs_packed4(idx[(size_t)g], &P, &PE, R.packed.data(), R.offs.data() + b, (e - b) / 2,
                                                      res.data() + b, &st[(size_t)g], &pst[(size_t)g], nullptr);
-          else if (all_loci)
+          else if (all_loci || clustered)
             rcs[(size_t)g] = bkx_align_reads_multi(idx[(size_t)g], &P, R.bases.data(), R.offs.data() + b, e - b, res.data() + b,
                                                    multi.data() + (size_t)b * (size_t)o.max_ml, &st[(size_t)g]);
           else
@@ -807,6 +808,27 @@ int main(int argc, char** argv) {
   }
   const uint32_t nrec = (uint32_t)res.size();
   auto rix = [&](uint32_t i) -> uint32_t { return src.empty() ? i : src[i]; };
+
+  // ---- -r3 / -r4: AssignMultiMatches, Aligner.cpp:583-592, 5108-5270
+  if (clustered) {
+    diag("Multialignment processing started..");
+    uint32_t longest = 0;
+    for (uint32_t i = 0; i < n; ++i) longest = std::max<uint32_t>(longest, (uint32_t)R.len(i));
+    bkx_cluster_stats cs;
+    diag("Assigning %d reads which aligned to multiple loci to a single loci", (int)S.tot_accepted_multi);
+    diag("Sorting...");
+    diag("Sorting completed, now clustering...");
+    diag("Assigning...");
+    if (bkx_assign_multi_matches(res.data(), n, multi.data(), o.max_ml, o.ml_mode, longest, &cs) < 0) {
+      diag("Fatal: %s", bkx_last_error());
+      return 1;
+    }
+    diag("Checking for orphans (unclustered) from %d putative assignments..", (int)cs.putative);
+    diag("Clustering completed, removed %d unclustered orphans from %d putative resulting in %d (%d clustered near unique, %d clustered near other multiloci reads) multihit reads accepted as assigned",
+         (int)(cs.putative - cs.assigned), (int)cs.putative, (int)cs.assigned, (int)cs.near_unique, (int)cs.near_multi);
+    diag("Multialignment processing completed");
+    std::vector<bkx_multi_hit>().swap(multi);
+  }
 
   // ---- paired ends, Aligner.cpp:2876-3049
   if (o.pe_mode) {

@@ -25,6 +25,7 @@ EXPORTS = [
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
     "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
     "bkx_pack_bases4", "bkx_align_reads_multi", "bkx_align_pairs", "bkx_align_pairs_packed4",
+    "bkx_assign_multi_matches",
 ]
 
 
@@ -65,6 +66,7 @@ def lib():
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_pack_bases4.argtypes = [vp, u64, vp]
+    L.bkx_assign_multi_matches.argtypes = [vp, u32, vp, i32, i32, u32, C.POINTER(abi.ClusterStats)]
     for fn in (L.bkx_align_pairs, L.bkx_align_pairs_packed4):
         fn.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats),
                        C.POINTER(abi.PEStats), vp]
@@ -120,6 +122,15 @@ def pack_bases4(bases):
     out = np.zeros((bases.size + 1) // 2, dtype=np.uint8)
     check(lib().bkx_pack_bases4(bases.ctypes.data, bases.size, out.ctypes.data))
     return out
+
+
+def assign_multi_matches(results, multi, ml_mode, max_read_len):
+    """-r3 / -r4 clustering (host code): rewrites `results` in place, returns the counters of the reference's log."""
+    assert results.dtype == abi.RESULT_DTYPE and results.flags.c_contiguous and multi.flags.c_contiguous
+    cs = abi.ClusterStats()
+    check(lib().bkx_assign_multi_matches(results.ctypes.data, len(results), multi.ctypes.data, multi.shape[1], ml_mode,
+                                         max_read_len, C.byref(cs)))
+    return cs
 
 
 def sort_hits(results, device=0):

@@ -59,9 +59,10 @@ enum { BKX_PMODE_DEFAULT = 0, BKX_PMODE_MORESENS = 1, BKX_PMODE_ULTRASENS = 2, B
 
 /* ---- etMLMode: biokanga/Aligner.h:224-231.  Built: DEFAULT (max_ml_matches must be 1), DIST ("-r1", stats only:
  * reads with 2..max_ml_matches equally good loci are reported eNARMultiAlign with their exact LowHitInstances,
- * Aligner.cpp:9328-9400) and ALL ("-r5": every one of up to max_ml_matches <= 64 equally good loci is returned,
- * through bkx_align_reads_multi).  RAND uses libc rand() in the reference and cannot be reproduced; UNIQ / MULTI
- * (clustering) are SURVEY section 8(f) rows not built yet -- rejected with BKX_ERR_UNSUPPORTED. */
+ * Aligner.cpp:9328-9400), ALL ("-r5": every one of up to max_ml_matches <= 64 equally good loci is returned, through
+ * bkx_align_reads_multi) and UNIQ / MULTI ("-r3" / "-r4": the same call returns the loci, records of multi-loci reads
+ * stay eNARMultiAlign until bkx_assign_multi_matches picks a locus by clustering).  RAND uses libc rand() in the
+ * reference and cannot be reproduced -- rejected with BKX_ERR_UNSUPPORTED. */
 enum { BKX_ML_DEFAULT = 0, BKX_ML_DIST = 1, BKX_ML_RAND = 2, BKX_ML_UNIQ = 3, BKX_ML_MULTI = 4, BKX_ML_ALL = 5 };
 
 /* ---- etPEproc: biokanga/Aligner.h:252-259 ----------------------------------------------------- */
@@ -269,6 +270,23 @@ int bkx_align_pairs(bkx_index* idx, const bkx_align_params* params, const bkx_pe
 int bkx_align_pairs_packed4(bkx_index* idx, const bkx_align_params* params, const bkx_pe_params* pe, const uint8_t* packed,
                             const uint64_t* offsets, uint32_t n_pairs, bkx_read_result* out, bkx_align_stats* stats,
                             bkx_pe_stats* pe_stats, uint32_t* len_dist);
+
+/* ---- -r3 / -r4: one locus for reads that hit several, by clustering with the loci of other reads.  Replaces
+ * CAligner::AssignMultiMatches + ProcAssignMultiMatches (Aligner.cpp:5108-5270, 4961-5105).  Host code (no device
+ * work).  results / multi are what bkx_align_reads_multi returned under ml_mode BKX_ML_UNIQ or BKX_ML_MULTI: records of
+ * reads with several loci are eNARMultiAlign with their count in low_hit_instances and their loci in multi; records of
+ * reads that get a locus assigned are rewritten in place (accepted, one hit).  max_read_len: longest read of the run.
+ * The counters are the ones of the reference's log lines (:5125, :5195, :5264). */
+typedef struct bkx_cluster_stats {
+  uint32_t multi_reads;   /* reads that aligned to several loci (m_NumProvMultiAligned)            */
+  uint32_t putative;      /* reads considered for assignment                                        */
+  uint32_t assigned;      /* reads given a locus                                                    */
+  uint32_t near_unique;   /* ... because uniquely aligned reads overlap it                          */
+  uint32_t near_multi;    /* ... because loci of other multi-loci reads overlap it (-r4 only)       */
+  uint32_t reserved[3];
+} bkx_cluster_stats;
+int bkx_assign_multi_matches(bkx_read_result* results, uint32_t n_reads, const bkx_multi_hit* multi, int max_ml_matches,
+                             int ml_mode, uint32_t max_read_len, bkx_cluster_stats* out);
 
 /* ---- output order: replaces CAligner::SortReadHits(eRSMHitMatch) + SortHitMatch (Aligner.cpp:9917-9991,
  * 10067-10114).  order_out[k] = index of the k-th record under the reference's hit ordering (NAR class; uniquely

@@ -481,7 +481,7 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
       st->tot_accepted_aligned++;
       st->tot_loci_aligned += (uint64_t)inst;
       if (inst == 1) st->tot_accepted_unique++; else st->tot_accepted_multi++;
-      if (inst == 1 || p->ml_mode != BKX_ML_DIST) {  /* unique, or (outside -r1) the first of several: hits[0] */
+      if (inst == 1 || p->ml_mode == BKX_ML_DEFAULT || p->ml_mode == BKX_ML_ALL) {  /* unique, or every locus is wanted */
         out->nar = BKX_NAR_ACCEPTED;
         out->num_hits = (p->ml_mode == BKX_ML_ALL) ? (uint8_t)inst : 1;  /* -r5: every hit is reported (:9336-9352) */
         out->strand = hits[0].strand;
@@ -491,7 +491,7 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
         out->mismatches = hits[0].mismatches;
         if (p->ml_mode != BKX_ML_ALL) inst = 1;
         if (out->strand == '+') st->plus_hits++; else st->minus_hits++;
-      } else {                                       /* -r1: counted, not placed (:9383-9386) */
+      } else {                                       /* -r1 / -r3 / -r4: counted, not placed (:9383-9397) */
         out->nar = BKX_NAR_MULTIALIGN;
         out->num_hits = 0;
       }
@@ -559,8 +559,10 @@ static void* thr_main(void* a_) {
       if (a->multi) {  /* -r5: the pMultiHits list WriteHitLoci walks */
         bkx_multi_hit* m = a->multi + (size_t)i * (size_t)a->p->max_ml_matches;
         memset(m, 0, (size_t)a->p->max_ml_matches * sizeof(*m));
-        if (a->out[i].nar == BKX_NAR_ACCEPTED)
-          for (int h = 0; h < a->out[i].num_hits && h < a->p->max_ml_matches; h++) {
+        int nh = a->out[i].nar == BKX_NAR_ACCEPTED ? a->out[i].num_hits
+                 : (a->out[i].nar == BKX_NAR_MULTIALIGN && a->out[i].hit_rslt == BKX_HR_HITS) ? a->out[i].low_hit_instances : 0;
+        if (nh > 0)
+          for (int h = 0; h < nh && h < a->p->max_ml_matches; h++) {
             m[h].chrom_id = hits[h].chrom_id; m[h].match_loci = hits[h].match_loci; m[h].match_len = hits[h].match_len;
             m[h].strand = hits[h].strand; m[h].mismatches = hits[h].mismatches;
           }

@@ -243,6 +243,20 @@ def case_lowcopy():
             strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
             strip_log(os.path.join(tmp, tag + ".sam.log"), os.path.join(d, tag + ".sam.log"))
             meta[tag] = {"reads": ["r100.fa.gz"], "args": args, "all_loci": True}
+        # -r3 / -r4: multi-loci reads are assigned one locus by clustering with other reads' loci -- needs depth, so a second
+        # read set drawn from the first chromosome only (~14x): CSV + log (the clustering counters are in it)
+        n, r = synth.sim_reads(g[:1], 12000, 100, seed=43, subs=(0, 0, 1, 2), junk_frac=0.0, n_frac=0.0)
+        synth.write_reads_fasta(os.path.join(tmp, "deep.fa"), n, r)
+        gz(os.path.join(tmp, "deep.fa"), os.path.join(d, "deep.fa.gz"))
+        for tag, args in {"r3_R5_s3": ["-s3", "-r3", "-R5"], "r4_R5_s3": ["-s3", "-r4", "-R5"],
+                          "r4_R8_X_s5": ["-s5", "-r4", "-R8", "-X"]}.items():
+            common = ["align", "-I", "lowcopy.sfx", "-i", "deep.fa", "-T4"] + args
+            run(common + ["-M6", "-o", tag + ".sam", "-F", tag + ".sam.log"], tmp)
+            run(common + ["-M0", "-o", tag + ".csv", "-F", tag + ".log"], tmp)
+            gz(os.path.join(tmp, tag + ".sam"), os.path.join(d, tag + ".sam.gz"))
+            gz(os.path.join(tmp, tag + ".csv"), os.path.join(d, tag + ".csv.gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"reads": ["deep.fa.gz"], "args": args, "clustered": True}
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 

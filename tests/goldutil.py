@@ -31,12 +31,12 @@ def runs(case):
 
 
 def all_runs(all_loci=True):
-    """Every (case, tag); all_loci=False leaves out the -r5 runs (one record per locus: they have their own checks)."""
+    """Every (case, tag); all_loci=False leaves out the -r3..5 runs (hit lists / clustering: they have their own checks)."""
     out = []
     for case in CASES:
         rs = runs(case)
         for tag in sorted(rs):
-            if all_loci or not rs[tag].get("all_loci"):
+            if all_loci or not (rs[tag].get("all_loci") or rs[tag].get("clustered")):
                 out.append((case, tag))
     return out
 

@@ -16,7 +16,7 @@ RUNS = [("tiny", "r100_s3"), ("tiny", "r100_s5_e2"), ("tiny", "mixed_s3"), ("tin
         ("tiny", "r100_s4_m2"), ("tiny", "pe_U2"), ("tiny", "pe_U4"), ("tiny", "pe_U1"), ("tiny", "pe_U3"),
         ("tiny", "pe_U1_far"), ("repeats", "r100_s3_m3"), ("repeats", "r60_s5"), ("lowcopy", "r1_R5_s3"),
         ("lowcopy", "r1_R4_X_s3"), ("lowcopy", "r1_R20_s5_e2"), ("lowcopy", "r5_R5_s3"), ("lowcopy", "r5_R3_X_s3"),
-        ("lowcopy", "r5_R8_s5_e2")]
+        ("lowcopy", "r5_R8_s5_e2"), ("lowcopy", "r3_R5_s3"), ("lowcopy", "r4_R5_s3"), ("lowcopy", "r4_R8_X_s5")]
 
 
 def summary_block(path):
@@ -69,7 +69,7 @@ def test_cli_outputs_match_reference(case, tag, golden_dir, tmp_path):
 def test_cli_rejects_unsupported_and_bad_options(tmp_path, golden_dir):
     sfx = gu.sfx_path("tiny", golden_dir)
     rd = os.path.join(gu.GOLD, "tiny", "r100.fa.gz")
-    r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-r3"], capture_output=True, text=True)
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-r2", "-R5"], capture_output=True, text=True)
     assert r.returncode != 0 and "not supported" in r.stderr
     r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-s99"], capture_output=True, text=True)
     assert r.returncode != 0

@@ -50,6 +50,28 @@ def test_all_loci_match_oracle(lowcopy, max_subs, mmd, limit, clamp):
             assert int((q != g).sum()) == int(h["mismatches"]) == int(got["low_mm"][i])
 
 
+@pytest.mark.parametrize("mode,limit,clamp,max_subs", [(3, 5, 0, 3), (4, 5, 0, 3), (4, 8, 1, 5)])
+def test_clustering_modes_match_oracle(lowcopy, mode, limit, clamp, max_subs):
+    """-r3 / -r4: records and hit lists of the search equal the oracle's; the host-side assignment then gives the same
+    records whichever side produced its input."""
+    gidx, oidx, bases, offs = lowcopy
+    kw = dict(max_subs=max_subs, ml_mode=mode, max_ml_matches=limit, clamp_max_ml=clamp)
+    got, gm, gst = gidx.align_multi(gidx.default_params(0, **kw), bases, offs)
+    exp, em, est = oidx.align_multi(oidx.default_params(0, **kw), bases, offs, nthreads=4)
+    for f in abi.RESULT_DTYPE.names:
+        assert np.array_equal(got[f], exp[f]), f
+    assert gst.as_dict() == est.as_dict()
+    multi = (got["nar"] == abi.NAR_MULTIALIGN) & (got["hit_rslt"] == 1)
+    cnt = np.where(multi, got["low_hit_instances"], np.where(got["nar"] == abi.NAR_ACCEPTED, 1, 0))
+    valid = np.arange(limit)[None, :] < cnt[:, None]
+    assert gm[valid].tobytes() == em[valid].tobytes()
+    assert multi.sum() > 100
+    a, b = got.copy(), exp.copy()
+    ca = bkx.assign_multi_matches(a, gm, mode, 100)
+    cb = bkx.assign_multi_matches(b, em, mode, 100)
+    assert a.tobytes() == b.tobytes() and bytes(ca) == bytes(cb)
+
+
 def test_all_loci_mode_needs_its_own_call(lowcopy):
     gidx, oidx, bases, offs = lowcopy
     with pytest.raises(bkx.BkxError):
@@ -58,6 +80,8 @@ def test_all_loci_mode_needs_its_own_call(lowcopy):
         gidx.align_multi(gidx.default_params(0, ml_mode=5, max_ml_matches=100), bases, offs)
     with pytest.raises(bkx.BkxError):
         gidx.align(gidx.default_params(0, ml_mode=3, max_ml_matches=5), bases, offs)
+    with pytest.raises(bkx.BkxError):
+        gidx.align(gidx.default_params(0, ml_mode=2, max_ml_matches=5), bases, offs)
 
 
 @pytest.mark.parametrize("limit,clamp", [(5, 0), (2, 0), (4, 1), (20, 0)])

@@ -17,6 +17,8 @@ def test_oracle_matches_reference(case, tag, golden_dir):
     names, bases, offs = gu.load_reads(case, run)
     if run.get("all_loci"):
         return check_all_loci(case, tag, idx, p, names, bases, offs)
+    if run.get("clustered"):
+        return check_clustered(case, tag, idx, p, names, bases, offs)
     res, st = idx.align(p, bases, offs, nthreads=4)
     if pe is not None:
         idx.pair(p, pe, res, bases, offs)
@@ -64,3 +66,24 @@ def check_all_loci(case, tag, idx, p, names, bases, offs):
         int(v) for v in m.groups())
     m = re.search(r"Unable to align (\d+) source reads of which (\d+)", log)
     assert (st.tot_non_aligned + st.num_sloughed_ns, st.num_sloughed_ns) == tuple(int(v) for v in m.groups())
+
+
+def check_clustered(case, tag, idx, p, names, bases, offs):
+    """-r3 / -r4 runs: the oracle's records and hit lists go through the PRODUCT's host-side clustering
+    (bkx_assign_multi_matches, no GPU involved) and must give the reference's CSV rows and log counters."""
+    from biokanga_b200 import lib as bkx
+    res, multi, st = idx.align_multi(p, bases, offs, nthreads=4)
+    max_len = int((offs[1:] - offs[:-1]).max())
+    cs = bkx.assign_multi_matches(res, multi, p.ml_mode, max_len)
+    got = gu.results_to_tuples(idx.entries(), names, res)
+    exp = gu.expected(case, tag)
+    assert len(got) == len(exp)
+    bad = [(n, got[n], exp[n][:5]) for n in names if got[n] != exp[n][:5]]
+    assert not bad, "%d reads differ, first: %r" % (len(bad), bad[:5])
+    log = gu.log_stats(case, tag)
+    m = re.search(r"Assigning (\d+) reads which aligned to multiple loci", log)
+    assert cs.multi_reads == int(m.group(1))
+    m = re.search(r"removed (\d+) unclustered orphans from (\d+) putative resulting in (\d+) \((\d+) clustered near unique, "
+                  r"(\d+) clustered near other multiloci reads\)", log)
+    assert (cs.putative - cs.assigned, cs.putative, cs.assigned, cs.near_unique, cs.near_multi) == tuple(
+        int(v) for v in m.groups())
