@@ -102,6 +102,27 @@ __global__ void kmer_hist_kernel(DevIndex I, int k, CntT* __restrict__ cnt) {
   }
 }
 
+// Self-check of a finished index: every suffix-array element must sit inside the prefix-table bucket of the suffix it
+// names.  Ties the three big arrays together (genome words -> key, table, suffix array): a damaged page in any of them
+// shows up as elements outside their bucket.
+__global__ void verify_index_kernel(DevIndex I, int k, unsigned long long* __restrict__ n_bad) {
+  unsigned long long bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < I.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t p = sa_get(I, i);
+    if (p >= I.n) { ++bad; continue; }
+    if (p + (uint64_t)k > I.n) continue;  // the last k suffixes: the reference's comparator runs off its buffer there
+    const uint64_t key = suffix_key(I, p, k);
+    if (!(pt_get(I, key) <= i && i < pt_get(I, key + 1))) ++bad;
+  }
+  for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, bad);
+}
+
+cudaError_t launch_verify_index(const DevIndex& I, int k, unsigned long long* n_bad, cudaStream_t st) {
+  verify_index_kernel<<<148 * 16, 256, 0, st>>>(I, k, n_bad);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_genome(const uint8_t* seq, uint64_t n, uint64_t* g2, uint64_t* gx, uint32_t* gxc,
                                unsigned long long* bad, cudaStream_t st) {
   uint64_t nblk = (n + 63) >> 6;

@@ -13,6 +13,7 @@ struct HashPool;
 
 cudaError_t launch_pack_genome(const uint8_t* seq, uint64_t n, uint64_t* g2, uint64_t* gx, uint32_t* gxc,
                                unsigned long long* bad, cudaStream_t st);
+cudaError_t launch_verify_index(const DevIndex& I, int k, unsigned long long* n_bad, cudaStream_t st);
 cudaError_t launch_unpack4(const uint8_t* packed, unsigned phase, uint64_t n_bases, uint8_t* out, cudaStream_t st);
 cudaError_t launch_split_sa5(const uint8_t* sa5, uint64_t n, uint32_t* lo, uint8_t* hi, cudaStream_t st);
 cudaError_t build_prefix_table(const DevIndex& I, int k, void* table, bool wide, cudaStream_t st);
