@@ -142,6 +142,8 @@ static int choose_k(uint64_t n, int requested, size_t free_bytes, bool wide) {
 
 // Where the suffix array comes from: raw elements as the .sfx stores them (copied / split into planes here), or
 // planes that are already in place on the device (used as they are; the caller settles who frees them).
+static thread_local bool g_selfcheck_failed = false;   // set by finish_index, read by bkx_open_index's retry loop
+
 struct SaSrc {
   const void* raw = nullptr;
   const uint32_t* lo = nullptr;
@@ -277,6 +279,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
     CU(cudaStreamSynchronize(st));
     cudaFree(d_bad);
     x->launches += 1;
+    g_selfcheck_failed = n_bad != 0;
     if (n_bad)
       return fail(BKX_ERR_FORMAT, "index self-check failed: %llu of %llu suffix-array elements lie outside the bucket of their suffix",
                   n_bad, (unsigned long long)n);
@@ -417,7 +420,7 @@ static bool pread_all(int fd, void* buf, size_t len, off_t ofs) {
 static uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
-extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_index** out) {
+static int open_index_once(const char* path, int device, int prefix_k, bkx_index** out) {
   if (!path || !out) return fail(BKX_ERR_PARAM, "null argument");
   int fd = open(path, O_RDONLY);
   if (fd < 0) return fail(BKX_ERR_FILE, "unable to open '%s'", path);
@@ -556,6 +559,19 @@ extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_in
   if (rc < 0) { bkx_close_index(x); return rc; }
   *out = x;
   return BKX_OK;
+}
+
+// A failed self-check of an index that came from a file is retried from the file: if the file is sound the damage
+// happened on the way to (or on) the device, and a second upload is the remedy; each retry is reported.
+extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_index** out) {
+  int rc = BKX_OK;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    g_selfcheck_failed = false;
+    rc = open_index_once(path, device, prefix_k, out);
+    if (rc >= 0 || !g_selfcheck_failed) return rc;
+    fprintf(stderr, "[bkx] warning: %s -- uploading '%s' again (attempt %d of 3)\n", bkx_last_error(), path, attempt + 2);
+  }
+  return rc;
 }
 
 // Replicate an open index onto another GPU with peer copies (NVLink when the GPUs are peers).

@@ -185,3 +185,27 @@ def test_five_byte_suffix_elements_and_wide_prefix_table(golden_dir, tmp_path):
     o5 = po.OracleIndex(str(tmp_path / "t5.sfx"))
     got, _ = o5.align(gu.params_from_args(o5, run["args"])[0], bases, offs)
     assert_same(names, got, exp)
+
+
+def test_index_self_check_rejects_a_damaged_suffix_array(golden_dir):
+    """Opening an index ends with a device self-check (every suffix-array element inside the prefix-table bucket of its
+    suffix): a suffix array with one 4 kB page zeroed, or belonging to another sequence, is refused -- unless
+    BKX_NO_VERIFY asks for it."""
+    import os
+    oi = po.OracleIndex(gu.sfx_path("repeats", golden_dir))
+    seq = np.array(oi.seq())
+    sa = np.array(oi.sa_bytes()).view(np.uint32).copy()
+    ents = np.zeros(len(oi.entries()), dtype=abi.ENTRY_DTYPE)
+    for i, e in enumerate(oi.entries()):
+        ents[i] = (e.entry_id, e.seq_len, e.start_ofs, e.end_ofs, e.name if isinstance(e.name, bytes) else e.name.encode())
+    good = bkx.Index.from_host(seq, sa, 4, ents, name="ok")
+    good.close()
+    bad = sa.copy()
+    bad[50_000:51_024] = 0
+    with pytest.raises(bkx.BkxError, match="self-check"):
+        bkx.Index.from_host(seq, bad, 4, ents, name="damaged")
+    os.environ["BKX_NO_VERIFY"] = "1"
+    try:
+        bkx.Index.from_host(seq, bad, 4, ents, name="unchecked").close()
+    finally:
+        os.environ.pop("BKX_NO_VERIFY", None)
