@@ -561,6 +561,23 @@ static int open_index_once(const char* path, int device, int prefix_k, bkx_index
   return BKX_OK;
 }
 
+// Re-run the self-check of finish_index on a live index: number of suffix-array elements outside their bucket.
+extern "C" int64_t bkx_self_check(bkx_index* x) {
+  if (!x) return fail(BKX_ERR_PARAM, "null argument");
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  CU(cudaDeviceSynchronize());
+  unsigned long long* d_bad = nullptr;
+  unsigned long long n_bad = 0;
+  CU(cudaMalloc((void**)&d_bad, 8));
+  CU(cudaMemset(d_bad, 0, 8));
+  CU(launch_verify_index(x->d, x->d.k, d_bad, x->slot[0].st));
+  CU(cudaMemcpyAsync(&n_bad, d_bad, 8, cudaMemcpyDeviceToHost, x->slot[0].st));
+  CU(cudaStreamSynchronize(x->slot[0].st));
+  cudaFree(d_bad);
+  return (int64_t)n_bad;
+}
+
 // A failed self-check of an index that came from a file is retried from the file: if the file is sound the damage
 // happened on the way to (or on) the device, and a second upload is the remedy; each retry is reported.
 extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_index** out) {
@@ -715,6 +732,16 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   return BKX_OK;
 }
 
+// Slots an overflow table needs so that one strand of one phase fits at a load factor <= 1/2: at most
+// min(cMaxNumIdentNodes, slides x MaxIter) new candidates (both depend on the run's parameters, not only on the reads).
+static uint32_t pool_slots_needed(const KParams& k, uint64_t max_len) {
+  int slides = std::max(1, (int)((k.slides_per100 * std::max<uint64_t>(max_len, 100) + 99) / 100));
+  uint64_t cap = std::min<uint64_t>((uint64_t)k.max_nodes, (uint64_t)slides * (uint64_t)k.max_iter);
+  uint32_t slots = 1024;
+  while (slots < 2 * cap) slots <<= 1;
+  return slots;
+}
+
 // Size the persistent grid and the per-warp overflow hash sets for reads up to max_len bases.
 static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int* W_out) {
   if (max_len > 2000) return fail(BKX_ERR_PARAM, "read length %u exceeds cMaxSeqLen 2000", max_len);
@@ -728,10 +755,7 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
     x->grid = nb * sms;
     x->grid_W = W;
   }
-  int slides = std::max(1, (int)((k.slides_per100 * (uint64_t)std::max<uint32_t>(max_len, 100) + 99) / 100));
-  uint64_t cap = std::min<uint64_t>((uint64_t)k.max_nodes, (uint64_t)slides * (uint64_t)k.max_iter);
-  uint32_t slots = 1024;
-  while (slots < 2 * cap) slots <<= 1;
+  const uint32_t slots = pool_slots_needed(k, max_len);
   if (slots > x->hp.slots || !x->hp.tables) {
     // a pool of overflow tables shared by all groups (only reads in high-copy repeats borrow one)
     if (x->hp.tables) { cudaFree(x->hp.tables); x->hp.tables = nullptr; }
@@ -936,7 +960,7 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     }
     if (!mono) return fail(BKX_ERR_PARAM, "offsets not monotonic in reads %u..%u", start, start + cnt);
     if ((int)((max_len + 31) / 32) + 1 > x->grid_W || x->grid == 0 || x->hp.tables == nullptr ||
-        max_len > x->max_len_prepared) {
+        max_len > x->max_len_prepared || pool_slots_needed(k, max_len) > x->hp.slots) {
       // (re)sizing the grid / overflow pool: let the slices in flight finish first
       for (int si = 0; si < kSlots; ++si)
         if (inflight[si] && (rc = drain(si)) < 0) return rc;

@@ -25,7 +25,7 @@ EXPORTS = [
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
     "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
     "bkx_pack_bases4", "bkx_align_reads_multi", "bkx_align_pairs", "bkx_align_pairs_packed4",
-    "bkx_assign_multi_matches",
+    "bkx_assign_multi_matches", "bkx_self_check",
 ]
 
 
@@ -66,6 +66,8 @@ def lib():
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_pack_bases4.argtypes = [vp, u64, vp]
+    L.bkx_self_check.argtypes = [vp]
+    L.bkx_self_check.restype = C.c_int64
     L.bkx_assign_multi_matches.argtypes = [vp, u32, vp, i32, i32, u32, C.POINTER(abi.ClusterStats)]
     for fn in (L.bkx_align_pairs, L.bkx_align_pairs_packed4):
         fn.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats),
@@ -190,6 +192,10 @@ class Index:
         check(lib().bkx_open_index_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, entries.ctypes.data,
                                           len(entries), name.encode(), device, prefix_k, C.byref(h)))
         return cls(h)
+
+    def self_check(self):
+        """Suffix-array elements outside the prefix-table bucket of their suffix (0 = the device index is sound)."""
+        return check(lib().bkx_self_check(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

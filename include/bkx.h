@@ -199,6 +199,10 @@ int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, const void* d_
 int bkx_open_index_planes(const uint8_t* d_seq, uint64_t concat_len, const uint32_t* d_sa_lo, const uint8_t* d_sa_hi,
                           const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
                           int prefix_k, bkx_index** out);
+/* Every bkx_open_index* ends with a device self-check: each suffix-array element must lie inside the prefix-table bucket
+ * of the suffix it names (ties genome words, table and suffix array together; BKX_NO_VERIFY=1 skips it).  This re-runs
+ * it on a live index and returns the number of elements that fail (0 = sound), < 0 on error. */
+int64_t bkx_self_check(bkx_index* idx);
 /* Replicate an open index onto another GPU by peer copies (multi-GPU read sharding). */
 int bkx_clone_index(const bkx_index* src, int device, bkx_index** out);
 void bkx_close_index(bkx_index* idx); /* CSfxArrayV3::Reset / Close */

@@ -129,6 +129,7 @@ def test_random_paired_end_options(seed, golden_dir):
             import subprocess
             print("DIAG GPU", subprocess.run(["nvidia-smi", "--query-gpu=serial,uuid,driver_version", "--format=csv,noheader"],
                                              capture_output=True, text=True).stdout.strip())
+            print("DIAG self-check of the live index: %d elements outside their bucket" % gidx.self_check())
             print("DIAG field %s read %d: fused %r, fused again %r, plain GPU align %r, oracle align only %r, oracle align+pair %r" % (
                 f, i, got[f][i], again[f][i], plain[f][i], oalign[f][i], exp[f][i]))
             raise AssertionError("%s L=%d %r U%d d%d D%d E%d field %s read %d (mate %d)\n got  %r\n exp  %r\n mate got %r\n mate exp %r" % (
