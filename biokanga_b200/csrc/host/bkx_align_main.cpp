@@ -597,6 +597,81 @@ struct Bgzf {
     return true;
   }
   uint64_t tell() const { return (block_addr << 16) | (uint64_t)(uofs & 0xffff); }
+  // Whole-stream form of write(): the blocks a sequence of write() calls would have produced -- a cut every 0xff00
+  // bytes and one more at *flush_at (an explicit flush()) -- deflated by `threads` workers and written in order.  A
+  // trailing partial block stays pending for close(), as it would after write().  vaddr() then maps stream offsets to
+  // the virtual addresses tell() would have returned at those points.
+  std::vector<uint64_t> cut_u, cut_c;   // block starts in the stream / in the file, plus the end sentinel
+  bool write_stream(const uint8_t* data, uint64_t len, const uint64_t* flush_at, unsigned threads) {
+    if (uofs) return false;  // only from a block boundary
+    cut_u.clear(); cut_c.clear();
+    uint64_t pos = 0;
+    while (pos < len) {
+      cut_u.push_back(pos);
+      uint64_t nxt = std::min<uint64_t>(pos + 0xff00, len);
+      if (flush_at && *flush_at > pos && *flush_at < nxt) nxt = *flush_at;
+      pos = nxt;
+    }
+    const size_t nblk = cut_u.size();
+    cut_u.push_back(len);
+    // the last block stays in ubuf unless it is full or ends at the explicit flush
+    size_t nfull = nblk;
+    if (nblk) {
+      uint64_t lb = cut_u[nblk - 1], le = len;
+      bool closed = (le - lb == 0xff00) || (flush_at && *flush_at == le);
+      if (!closed) nfull = nblk - 1;
+    }
+    std::vector<std::vector<uint8_t>> comp(nfull);
+    std::vector<char> good(std::max<unsigned>(threads, 1), 1);
+    {
+      std::vector<std::thread> th;
+      unsigned T = std::max<unsigned>(threads, 1);
+      for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+          for (size_t j = t; j < nfull; j += T) {
+            size_t ulen = (size_t)(cut_u[j + 1] - cut_u[j]);
+            std::vector<uint8_t>& out = comp[j];
+            out.resize(ulen + 1024 + 26);
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            zs.next_in = const_cast<uint8_t*>(data + cut_u[j]);
+            zs.avail_in = (uInt)ulen;
+            zs.next_out = out.data() + 18;
+            zs.avail_out = (uInt)(out.size() - 18 - 8);
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { good[t] = 0; return; }
+            if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); good[t] = 0; return; }
+            deflateEnd(&zs);
+            size_t dlen = zs.total_out + 18 + 8;
+            static const uint8_t magic[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+            memcpy(out.data(), magic, 18);
+            uint16_t bs = (uint16_t)(dlen - 1);
+            memcpy(out.data() + 16, &bs, 2);
+            uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data + cut_u[j], (uInt)ulen), isz = (uint32_t)ulen;
+            memcpy(out.data() + dlen - 8, &crc, 4);
+            memcpy(out.data() + dlen - 4, &isz, 4);
+            out.resize(dlen);
+          }
+        });
+      for (auto& x : th) x.join();
+    }
+    for (char g : good) if (!g) return false;
+    for (size_t j = 0; j < nfull; ++j) {
+      cut_c.push_back(block_addr);
+      if (fwrite(comp[j].data(), 1, comp[j].size(), f) != comp[j].size()) return false;
+      block_addr += comp[j].size();
+    }
+    cut_c.push_back(block_addr);  // address of the block that follows (pending or next)
+    if (nfull < nblk) {           // pending partial block
+      uofs = (size_t)(len - cut_u[nblk - 1]);
+      memcpy(ubuf.data(), data + cut_u[nblk - 1], uofs);
+    }
+    return true;
+  }
+  uint64_t vaddr(uint64_t u) const {  // what tell() returned when the stream stood at offset u (after any flush due there)
+    if (u >= cut_u.back()) return (cut_c.back() << 16) | (uint64_t)(uofs & 0xffff);  // end of stream: pending bytes, if any
+    size_t j = (size_t)(std::upper_bound(cut_u.begin(), cut_u.end(), u) - cut_u.begin()) - 1;  // block with start <= u
+    return (cut_c[j] << 16) | (uint64_t)((u - cut_u[j]) & 0xffff);
+  }
   bool close() {
     bool ok = flush() && deflate_block(0);  // trailing empty block = BGZF EOF marker
     if (f) fclose(f);
@@ -961,18 +1036,43 @@ int main(int argc, char** argv) {
     std::string hdr = "BAM\1";
     uint32_t lt = (uint32_t)text.size();
     hdr.append((const char*)&lt, 4); hdr += text; hdr.append((const char*)&nref, 4); hdr += refs;
-    bool ok = bz.write(hdr.data(), hdr.size());
+    // The whole uncompressed BAM stream is laid out first (record sizes -> offsets -> records written in place by all
+    // threads), then cut into BGZF blocks exactly where the reference's sequential writer cuts them (every 0xff00
+    // bytes, plus once behind the last aligned record), the blocks are deflated in parallel and written in order; the
+    // BAI follows from the record offsets and the block addresses.
     BaiBuilder bai;
     bai.out = "BAI\1";
     bai.put32(nref);
-    int cur_ref = -1;  // reference whose index block is being accumulated
-    uint32_t n_acc = (uint32_t)nar[BKX_NAR_ACCEPTED], seen_acc = 0;
-    std::string rec;
-    for (uint32_t k = 0; k < nrec && ok; ++k) {
+    struct RecMeta { uint64_t uofs; uint32_t len; int32_t rid, pos; int32_t L; uint8_t acc; };
+    std::vector<RecMeta> meta;
+    meta.reserve(nrec);
+    uint64_t utotal = hdr.size();
+    for (uint32_t k = 0; k < nrec; ++k) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
       bool acc = r.nar == BKX_NAR_ACCEPTED;
       if (!acc && o.fmt != 6) continue;
+      const uint32_t ri = rix(i);
+      const int L = R.len(ri);
+      uint32_t lname = (uint32_t)strlen(R.name(ri)) + 1;
+      uint32_t len = 4 + 32 + lname + 4 + (uint32_t)((L + 1) / 2) + (uint32_t)L + (acc ? 0u : 6u);
+      meta.push_back({utotal, len, acc ? refid[r.chrom_id] : -1, acc ? (int32_t)r.match_loci : -1, L, (uint8_t)acc});
+      utotal += len;
+    }
+    std::vector<uint8_t> U(utotal);
+    memcpy(U.data(), hdr.data(), hdr.size());
+    // record k' (index into meta) <- sorted record; meta and the sorted walk advance together
+    std::vector<uint32_t> kept;
+    kept.reserve(meta.size());
+    for (uint32_t k = 0; k < nrec; ++k) {
+      const bkx_read_result& r = res[order[k]];
+      if (r.nar == BKX_NAR_ACCEPTED || o.fmt == 6) kept.push_back(order[k]);
+    }
+    auto write_record = [&](size_t mi) {
+      const uint32_t i = kept[mi];
+      const RecMeta& M = meta[mi];
+      const bkx_read_result& r = res[i];
+      const bool acc = M.acc != 0;
       int flags = 0, tlen = 0;
       long pnext = -1;
       if (!o.pe_mode) flags = acc ? (r.strand == '+' ? 0 : 0x10) : 0x04;
@@ -992,19 +1092,20 @@ int main(int argc, char** argv) {
         } else flags |= 0x08;
       }
       const uint32_t ri = rix(i);
-      const int L = R.len(ri);
+      const int L = M.L;
       const uint8_t* b = R.bases.data() + R.offs[ri];
       const char* qn = R.name(ri);
       uint32_t lname = (uint32_t)strlen(qn) + 1;
-      int32_t rid = acc ? refid[r.chrom_id] : -1, pos = acc ? (int32_t)r.match_loci : -1;
+      int32_t rid = M.rid, pos = M.pos;
       uint32_t bin = acc ? (uint32_t)bai_reg2bin(pos, pos + L) : 0;
       uint32_t bmn = bin << 16 | 255u << 8 | lname, fnc = (uint32_t)flags << 16 | 1u;
       int32_t nrid = (acc && pnext >= 0) ? rid : -1, npos = acc ? (int32_t)pnext : -1, tl = acc ? tlen : 0, lseq = L;
       uint32_t cigar = (uint32_t)L << 4;
-      rec.assign(4, '\0');
-      auto p32 = [&](const void* v) { rec.append((const char*)v, 4); };
-      p32(&rid); p32(&pos); p32(&bmn); p32(&fnc); p32(&lseq); p32(&nrid); p32(&npos); p32(&tl);
-      rec.append(qn, lname);
+      uint8_t* w = U.data() + M.uofs;
+      uint32_t bsz = M.len - 4;
+      auto p32 = [&](const void* v) { memcpy(w, v, 4); w += 4; };
+      p32(&bsz); p32(&rid); p32(&pos); p32(&bmn); p32(&fnc); p32(&lseq); p32(&nrid); p32(&npos); p32(&tl);
+      memcpy(w, qn, lname); w += lname;
       p32(&cigar);
       bool rc = acc && r.strand != '+';
       for (int q = 0; q < L; q += 2) {
@@ -1014,25 +1115,35 @@ int main(int argc, char** argv) {
           if (c < 4) { if (rc) c = 3 - c; return 1u << c; }
           return 15u;
         };
-        rec += (char)(nib(q) << 4 | nib(q + 1));
+        *w++ = (uint8_t)(nib(q) << 4 | nib(q + 1));
       }
       int sumq = 0;
       for (int q = 0; q < L; ++q) sumq += (b[q] >> 4) & 0x0f;
-      if (sumq == 0) rec.append((size_t)L, (char)0xff);
-      else for (int q = 0; q < L; ++q) rec += (char)(33 + (((b[rc ? L - 1 - q : q] >> 4) & 0x0f) * 40) / 15);
-      if (!acc) { rec += "YUZ"; rec += kNarCode[r.nar]; rec += '\0'; }
-      uint32_t bsz = (uint32_t)rec.size() - 4;
-      memcpy(&rec[0], &bsz, 4);
-      uint64_t sva = 0;
-      if (acc) {
-        while (cur_ref < rid) { if (cur_ref >= 0) bai.end_ref(); ++cur_ref; }
-        sva = bz.tell();
-      }
-      ok = bz.write(rec.data(), rec.size());
-      if (acc) {
-        if (++seen_acc == n_acc) ok = ok && bz.flush();  // bLastAligned: close the block behind the last aligned read
-        bai.add(sva, (uint32_t)pos, bz.tell(), (uint32_t)(pos + L - 1));
-      }
+      if (sumq == 0) { memset(w, 0xff, (size_t)L); w += L; }
+      else for (int q = 0; q < L; ++q) *w++ = (uint8_t)(33 + (((b[rc ? L - 1 - q : q] >> 4) & 0x0f) * 40) / 15);
+      if (!acc) { memcpy(w, "YUZ", 3); w += 3; memcpy(w, kNarCode[r.nar], 2); w += 2; *w++ = 0; }
+    };
+    {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < fmt_threads; ++t)
+        th.emplace_back([&, t]() {
+          size_t b0 = meta.size() * t / fmt_threads, e0 = meta.size() * (t + 1) / fmt_threads;
+          for (size_t mi = b0; mi < e0; ++mi) write_record(mi);
+        });
+      for (auto& x : th) x.join();
+    }
+    // explicit flush behind the last aligned record (bLastAligned, SAMfile.cpp), if any
+    uint64_t flush_at = 0;
+    bool have_flush = false;
+    for (size_t mi = meta.size(); mi-- > 0;)
+      if (meta[mi].acc) { flush_at = meta[mi].uofs + meta[mi].len; have_flush = true; break; }
+    bool ok = bz.write_stream(U.data(), U.size(), have_flush ? &flush_at : nullptr, fmt_threads);
+    int cur_ref = -1;  // reference whose index block is being accumulated
+    for (size_t mi = 0; mi < meta.size() && ok; ++mi) {
+      const RecMeta& M = meta[mi];
+      if (!M.acc) continue;
+      while (cur_ref < M.rid) { if (cur_ref >= 0) bai.end_ref(); ++cur_ref; }
+      bai.add(bz.vaddr(M.uofs), (uint32_t)M.pos, bz.vaddr(M.uofs + M.len), (uint32_t)(M.pos + M.L - 1));
     }
     bai.end_ref();  // Close(): the reference in progress (an empty block when nothing aligned)
     ok = ok && bz.close();
