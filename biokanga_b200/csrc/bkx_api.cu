@@ -578,6 +578,34 @@ extern "C" int64_t bkx_self_check(bkx_index* x) {
   return (int64_t)n_bad;
 }
 
+// Diagnostic hook for the open issue in DESIGN.md section 4: bring parts of an index's run-time state back to what a
+// freshly opened index has.  what: 1 = overflow pool (tables, locks, epochs), 2 = lane hash sets of the fast kernel,
+// 4 = launch geometry (grids, word counts; re-derived at the next call).
+extern "C" int bkx_debug_reset(bkx_index* x, int what) {
+  if (!x) return fail(BKX_ERR_PARAM, "null argument");
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  CU(cudaDeviceSynchronize());
+  if ((what & 1) && x->hp.tables) {
+    CU(cudaMemset(x->hp.tables, 0, (size_t)x->hp.n_tables * x->hp.slots * 8));
+    CU(cudaMemset(x->hp.locks, 0, (size_t)x->hp.n_tables * 4));
+    CU(cudaMemset(x->hp.epochs, 0, (size_t)x->hp.n_tables * 4));
+  }
+  if (what & 2) {
+    for (int s = 0; s < kSlots; ++s)
+      if (x->fast_hash[s]) CU(cudaMemset(x->fast_hash[s], 0, x->fast_hash_lanes * kFastHashSlots * 8));
+    x->fast_epoch = 1;
+  }
+  if (what & 4) {
+    for (int s = 0; s < kSlots; ++s)
+      if (x->fast_hash[s]) { cudaFree(x->fast_hash[s]); x->fast_hash[s] = nullptr; }
+    x->fast_hash_lanes = 0;
+    x->fast_epoch = 1;
+    x->grid = 0; x->grid_W = 0; x->fast_grid = 0; x->fast_W = 0; x->max_len_prepared = 0;
+  }
+  return BKX_OK;
+}
+
 // A failed self-check of an index that came from a file is retried from the file: if the file is sound the damage
 // happened on the way to (or on) the device, and a second upload is the remedy; each retry is reported.
 extern "C" int bkx_open_index(const char* path, int device, int prefix_k, bkx_index** out) {

@@ -25,7 +25,7 @@ EXPORTS = [
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
     "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
     "bkx_pack_bases4", "bkx_align_reads_multi", "bkx_align_pairs", "bkx_align_pairs_packed4",
-    "bkx_assign_multi_matches", "bkx_self_check",
+    "bkx_assign_multi_matches", "bkx_self_check", "bkx_debug_reset",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_pack_bases4.argtypes = [vp, u64, vp]
+    L.bkx_debug_reset.argtypes = [vp, i32]
     L.bkx_self_check.argtypes = [vp]
     L.bkx_self_check.restype = C.c_int64
     L.bkx_assign_multi_matches.argtypes = [vp, u32, vp, i32, i32, u32, C.POINTER(abi.ClusterStats)]
@@ -192,6 +193,9 @@ class Index:
         check(lib().bkx_open_index_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, entries.ctypes.data,
                                           len(entries), name.encode(), device, prefix_k, C.byref(h)))
         return cls(h)
+
+    def debug_reset(self, what):
+        check(lib().bkx_debug_reset(self._h, what))
 
     def self_check(self):
         """Suffix-array elements outside the prefix-table bucket of their suffix (0 = the device index is sound)."""

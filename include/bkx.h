@@ -203,6 +203,10 @@ int bkx_open_index_planes(const uint8_t* d_seq, uint64_t concat_len, const uint3
  * of the suffix it names (ties genome words, table and suffix array together; BKX_NO_VERIFY=1 skips it).  This re-runs
  * it on a live index and returns the number of elements that fail (0 = sound), < 0 on error. */
 int64_t bkx_self_check(bkx_index* idx);
+/* Diagnostic: reset run-time state of an index to that of a freshly opened one (1 overflow pool, 2 lane hash sets,
+ * 4 launch geometry; OR-able).  Results never depend on that state by design; tests/test_gpu_fuzz.py uses this to
+ * narrow down the open issue described in DESIGN.md section 4. */
+int bkx_debug_reset(bkx_index* idx, int what);
 /* Replicate an open index onto another GPU by peer copies (multi-GPU read sharding). */
 int bkx_clone_index(const bkx_index* src, int device, bkx_index** out);
 void bkx_close_index(bkx_index* idx); /* CSfxArrayV3::Reset / Close */

@@ -143,6 +143,11 @@ def test_random_paired_end_options(seed, golden_dir):
                 return int(sum((a[q] != oalign[q]).sum() for q in ("nar", "cands", "nxt_low_mm", "match_loci")))
             print("DIAG mismatching fields vs oracle align: old index fast+general %d, old index general only %d, FRESH index object %d" % (
                 nbad(plain), nbad(gen_only), nbad(fresh)))
+            print("DIAG info old index: prefix_k %d device_bytes %d" % (gidx.info.prefix_k, gidx.info.device_bytes))
+            for what, label in ((1, "overflow pool"), (2, "lane hash sets"), (4, "launch geometry")):
+                gidx.debug_reset(what)
+                again2, _ = gidx.align(gidx.default_params(0, **kw), bases, offs)
+                print("DIAG after resetting %s of the old index: %d mismatching fields" % (label, nbad(again2)))
             print("DIAG field %s read %d: fused %r, fused again %r, plain GPU align %r, oracle align only %r, oracle align+pair %r" % (
                 f, i, got[f][i], again[f][i], plain[f][i], oalign[f][i], exp[f][i]))
             raise AssertionError("%s L=%d %r U%d d%d D%d E%d field %s read %d (mate %d)\n got  %r\n exp  %r\n mate got %r\n mate exp %r" % (
