@@ -119,7 +119,9 @@ static int dev_alloc(bkx_index* x, T** p, size_t count, bool zero) {
   size_t bytes = count * sizeof(T);
   if (bytes == 0) bytes = sizeof(T);
   CU(cudaMalloc(&q, bytes));
-  if (zero) CU(cudaMemset(q, 0, bytes));
+  // NOT cudaMemset: that is asynchronous on the legacy default stream, which the library's non-blocking streams do
+  // not wait for -- the kernels that fill these arrays run on slot[0].st
+  if (zero) CU(cudaMemsetAsync(q, 0, bytes, x->slot[0].st));
   x->owned.push_back(q);
   x->info.device_bytes += bytes;
   *p = (T*)q;
@@ -279,6 +281,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
     CU(cudaStreamSynchronize(st));
     cudaFree(d_bad);
     x->launches += 1;
+    CU(cudaDeviceSynchronize());
     g_selfcheck_failed = n_bad != 0;
     if (n_bad)
       return fail(BKX_ERR_FORMAT, "index self-check failed: %llu of %llu suffix-array elements lie outside the bucket of their suffix",
@@ -570,7 +573,7 @@ extern "C" int64_t bkx_self_check(bkx_index* x) {
   unsigned long long* d_bad = nullptr;
   unsigned long long n_bad = 0;
   CU(cudaMalloc((void**)&d_bad, 8));
-  CU(cudaMemset(d_bad, 0, 8));
+  CU(cudaMemsetAsync(d_bad, 0, 8, x->slot[0].st));
   CU(launch_verify_index(x->d, x->d.k, d_bad, x->slot[0].st));
   CU(cudaMemcpyAsync(&n_bad, d_bad, 8, cudaMemcpyDeviceToHost, x->slot[0].st));
   CU(cudaStreamSynchronize(x->slot[0].st));
@@ -603,6 +606,7 @@ extern "C" int bkx_debug_reset(bkx_index* x, int what) {
     x->fast_epoch = 1;
     x->grid = 0; x->grid_W = 0; x->fast_grid = 0; x->fast_W = 0; x->max_len_prepared = 0;
   }
+  CU(cudaDeviceSynchronize());  // cudaMemset runs on the legacy stream; the work streams do not wait for it
   return BKX_OK;
 }
 
@@ -797,6 +801,11 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
     CU(cudaMemset(x->hp.locks, 0, (size_t)n_tables * 4));
     CU(cudaMalloc((void**)&x->hp.epochs, (size_t)n_tables * 4));
     CU(cudaMemset(x->hp.epochs, 0, (size_t)n_tables * 4));
+    // cudaMemset on device memory is ASYNCHRONOUS (legacy default stream) and the library's streams are non-blocking,
+    // i.e. they do not wait for that stream: without this barrier the first kernels could acquire tables while the
+    // 2 GiB clear -- and the clear of the epoch counters behind it -- was still on its way, after which epochs repeated
+    // and candidates looked "already seen" (the intermittent lost candidates of round 1)
+    CU(cudaDeviceSynchronize());
     x->hp.n_tables = n_tables;
     x->hp.slots = slots;
   }
@@ -842,6 +851,7 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     CU(cudaDeviceSynchronize());
     for (int s = 0; s < kSlots; ++s)
       if (x->fast_hash[s]) CU(cudaMemset(x->fast_hash[s], 0, x->fast_hash_lanes * kFastHashSlots * 8));
+    CU(cudaDeviceSynchronize());
     x->fast_epoch = 1;
   }
   uint32_t epoch_base = x->fast_epoch;
