@@ -281,12 +281,15 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
     CU(cudaStreamSynchronize(st));
     cudaFree(d_bad);
     x->launches += 1;
-    CU(cudaDeviceSynchronize());
     g_selfcheck_failed = n_bad != 0;
-    if (n_bad)
+    if (n_bad) {
+      cudaDeviceSynchronize();
       return fail(BKX_ERR_FORMAT, "index self-check failed: %llu of %llu suffix-array elements lie outside the bucket of their suffix",
                   n_bad, (unsigned long long)n);
+    }
   }
+  // the small tables above went up with cudaMemcpy on the legacy stream, which the work streams do not wait for
+  CU(cudaDeviceSynchronize());
   return BKX_OK;
 }
 
@@ -398,6 +401,7 @@ extern "C" int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const
     cudaFree(d_seq); cudaFree(d_sa); bkx_close_index(x);
     return fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e));
   }
+  if (cudaDeviceSynchronize() != cudaSuccess) { /* the uploads above ran on the legacy stream */ }
   SaSrc src;
   if (keep_sa) { x->owned.push_back(d_sa); x->info.device_bytes += concat_len * 4; src.lo = (const uint32_t*)d_sa; }
   else src.raw = d_sa;
