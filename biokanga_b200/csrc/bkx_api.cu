@@ -661,6 +661,9 @@ extern "C" int bkx_clone_index(const bkx_index* src, int device, bkx_index** out
     *(const void**)((char*)&x->d + a.field_ofs) = dp;
   }
   CU(cudaDeviceSynchronize());
+  CU(cudaSetDevice(src->device));   // the peer copies involve both devices' legacy streams
+  CU(cudaDeviceSynchronize());
+  CU(cudaSetDevice(device));
   *out = x;
   return BKX_OK;
 }

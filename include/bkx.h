@@ -189,7 +189,8 @@ int bkx_open_index(const char* sfx_path, int device, int prefix_k, bkx_index** o
 int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t sfx_el_size,
                        const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
                        int prefix_k, bkx_index** out);
-/* Same, from buffers already resident on `device` (bench / GPU-built suffix arrays). */
+/* Same, from buffers already resident on `device` (bench / GPU-built suffix arrays).  The buffers must be complete when
+ * the call is made (synchronise the stream that produced them): the library works on its own non-blocking streams. */
 int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, const void* d_sa, uint32_t sfx_el_size,
                        const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
                        int prefix_k, bkx_index** out);
