@@ -284,8 +284,8 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
     g_selfcheck_failed = n_bad != 0;
     if (n_bad) {
       cudaDeviceSynchronize();
-      return fail(BKX_ERR_FORMAT, "index self-check failed: %llu of %llu suffix-array elements lie outside the bucket of their suffix",
-                  n_bad, (unsigned long long)n);
+      return fail(BKX_ERR_FORMAT, "index self-check failed: %llu inconsistencies (suffix-array elements outside the bucket of their suffix, or "
+                  "exception-map blocks that disagree) in an index of %llu symbols", n_bad, (unsigned long long)n);
     }
   }
   // the small tables above went up with cudaMemcpy on the legacy stream, which the work streams do not wait for

@@ -104,7 +104,7 @@ __global__ void kmer_hist_kernel(DevIndex I, int k, CntT* __restrict__ cnt) {
 
 // Self-check of a finished index: every suffix-array element must sit inside the prefix-table bucket of the suffix it
 // names.  Ties the three big arrays together (genome words -> key, table, suffix array): a damaged page in any of them
-// shows up as elements outside their bucket.
+// shows up as elements outside their bucket.  The coarse exception map is checked against the fine one as well.
 __global__ void verify_index_kernel(DevIndex I, int k, unsigned long long* __restrict__ n_bad) {
   unsigned long long bad = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < I.n; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -113,6 +113,14 @@ __global__ void verify_index_kernel(DevIndex I, int k, unsigned long long* __res
     if (p + (uint64_t)k > I.n) continue;  // the last k suffixes: the reference's comparator runs off its buffer there
     const uint64_t key = suffix_key(I, p, k);
     if (!(pt_get(I, key) <= i && i < pt_get(I, key + 1))) ++bad;
+  }
+  // ... and the coarse exception map must say exactly which 64-base blocks hold an N / EOS (pack_genome_kernel sets
+  // bit b of gxc whenever gx[b] != 0)
+  const uint64_t nblk = (I.n + 63) >> 6;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (uint64_t)gridDim.x * blockDim.x) {
+    const bool any = __ldg(I.gx + b) != 0;
+    const bool bit = ((__ldg(I.gxc + (b >> 5)) >> (unsigned)(b & 31)) & 1u) != 0;
+    if (any != bit) ++bad;
   }
   for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_bad, bad);
