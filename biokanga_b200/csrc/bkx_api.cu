@@ -354,6 +354,7 @@ extern "C" int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, con
   int rc = new_index(device, &x);
   if (rc < 0) return rc;
   x->info.version = 5;
+  CU(cudaDeviceSynchronize());  // the caller's buffers may come from any stream; the library's streams are non-blocking
   SaSrc src;
   src.raw = d_sa;
   rc = finish_index(x, d_seq, concat_len, src, el, entries, n_ent, name, prefix_k);
@@ -372,6 +373,7 @@ extern "C" int bkx_open_index_planes(const uint8_t* d_seq, uint64_t concat_len, 
   int rc = new_index(device, &x);
   if (rc < 0) return rc;
   x->info.version = 5;
+  CU(cudaDeviceSynchronize());  // the caller's buffers may come from any stream; the library's streams are non-blocking
   SaSrc src;  // borrowed: not entered in x->owned, so bkx_close_index leaves the planes alone
   src.lo = d_sa_lo;
   src.hi = d_sa_hi;

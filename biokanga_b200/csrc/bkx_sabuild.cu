@@ -228,6 +228,7 @@ extern "C" int bkx_build_suffix_array_device(const uint8_t* d_seq, uint64_t n, u
   uint8_t *head = nullptr, *unres = nullptr;
   uint64_t m = 0;
   SA_CU(cudaSetDevice(device));
+  SA_CU(cudaDeviceSynchronize());  // whatever stream produced d_seq: this call works on its own non-blocking stream
   SA_CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   SA_CU(cudaMalloc((void**)&k0, n * 8));
   SA_CU(cudaMalloc((void**)&k1, n * 8));

@@ -241,6 +241,7 @@ extern "C" int bkx_build_suffix_array_planes(const uint8_t* d_seq, uint64_t n, u
   uint64_t rounds_total = 0;
 
   SL_CU(cudaSetDevice(device));
+  SL_CU(cudaDeviceSynchronize());  // whatever stream produced d_seq: this call works on its own non-blocking stream
   SL_CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   SL_CU(cudaMalloc((void**)&d_hist, (size_t)kBins * 8));
   SL_CU(cudaMalloc((void**)&d_count, 8));
