@@ -1,0 +1,62 @@
+"""CPU: the host side of `bkx-align` (option parsing, read parsing / packing, post-alignment passes, summary block,
+CSV / BED / SAM / BAM writers) against the reference's own output files, with the C ABI answered by a test double built
+on the oracle (tests/bkx_cpu_double.cpp).  The test bodies are the ones of tests/test_gpu_cli.py, which run the real
+binary on the GPU box; only the executable differs.  Test infrastructure: the double is never shipped."""
+import os
+import subprocess
+
+import pytest
+
+import pyoracle as po
+import test_gpu_cli as g
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="session")
+def cpu_cli(tmp_path_factory):
+    po.build()
+    odir = os.path.join(ROOT, "oracle", "_build")
+    exe = tmp_path_factory.mktemp("cpucli") / "bkx-align-cpu"
+    csrc = os.path.join(ROOT, "biokanga_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(csrc, "host", "bkx_align_main.cpp"),
+                    os.path.join(HERE, "bkx_cpu_double.cpp"), "-x", "c++", os.path.join(csrc, "bkx_cluster.cu"), "-x", "none",
+                    "-L" + odir, "-lbkoracle", "-lz", "-lpthread", "-Wl,-rpath," + odir], check=True)
+    return str(exe)
+
+
+@pytest.fixture
+def cli(cpu_cli, monkeypatch):
+    monkeypatch.setattr(g, "CLI", cpu_cli)
+    return cpu_cli
+
+
+@pytest.mark.parametrize("case,tag", g.RUNS)
+def test_host_outputs_match_reference(case, tag, cli, golden_dir, tmp_path):
+    g.test_cli_outputs_match_reference(case, tag, golden_dir, tmp_path)
+
+
+def test_host_rejects_unsupported_and_bad_options(cli, golden_dir, tmp_path):
+    g.test_cli_rejects_unsupported_and_bad_options(tmp_path, golden_dir)
+
+
+@pytest.mark.parametrize("tag", ["m1", "m2", "m3", "m4", "m4t", "g0", "g1", "g2", "gz", "trim"])
+def test_host_output_formats_match_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_output_formats_match_reference(tag, golden_dir, tmp_path)
+
+
+@pytest.mark.parametrize("tag,args,out", [("bam5", ["-s3", "-M5"], "out5.bam"), ("bam6", ["-s3", "-M6", "-g0"], "out6.bam"),
+                                          ("bamQ2", ["-s3", "-M6", "-Q2"], "out62.bam")])
+def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
+    g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
+
+
+@pytest.mark.parametrize("case,tag", [("tiny", "mixed_s3"), ("tiny", "pe_U1")])
+def test_host_chunked_parallel_parse_gives_the_same_files(case, tag, cli, golden_dir, tmp_path):
+    g.test_cli_chunked_parallel_parse_gives_the_same_files(case, tag, golden_dir, tmp_path)
+
+
+@pytest.mark.parametrize("tag", ["r5_R5_s3", "r5_R3_X_s3", "r5_R8_s5_e2"])
+def test_host_all_loci_mode_sam_log_and_numbering(tag, cli, golden_dir, tmp_path):
+    g.test_cli_all_loci_mode_sam_log_and_numbering(tag, golden_dir, tmp_path)
