@@ -11,11 +11,14 @@
 //   SAM records       WriteBAMReadHits / ReportBAMread    Aligner.cpp:5543-5725, 5768-6126
 //                     CSAMfile::AddAlignment (text form)  libbiokanga/SAMfile.cpp:2100-2262
 //   summary           CAligner::ReportAlignStats          Aligner.cpp:3493-3822
+//   post-alignment    AutoTrimFlanks (-x)                 Aligner.cpp:1608-1812
+//                     FiltByChroms (-Z / -z)              Aligner.cpp:4019-4124, 4736-4798
+//                     ReportNoneAligned / ReportMultiAlign (-j / -J)   Aligner.cpp:3826-4016
 // Written from the behaviour of those functions; no reference code is reused.  Options of the
-// reference that select paths outside SURVEY section 8 (-r2..5 multi-loci modes, -c chimeric, -a/-A indel and
-// splice, -p SNP calling, -k PCR dedup, -x flank trimming, -Z/-z filters, -5 constraints, -H contaminants,
-// -b/-C bisulfite/SOLiD) are recognised and rejected with a clear message.  Output formats: CSV -M0..3, BED -M4,
-// SAM -M5/-M6 (gzip when the name ends in .gz), BAM + BAI when the name ends in .bam (kanga.cpp:849-857).
+// reference that select paths outside SURVEY section 8 (-r2 random locus, -N best matches, -c chimeric, -a/-A indel
+// and splice, -p SNP calling, -k PCR dedup, -5 constraints, -H contaminants, -b/-C bisulfite/SOLiD) are recognised
+// and rejected with a clear message.  Output formats: CSV -M0..3, BED -M4, SAM -M5/-M6 (gzip when the name ends in
+// .gz), BAM + BAI when the name ends in .bam (kanga.cpp:849-857).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -29,6 +32,7 @@
 #include <thread>
 #include <vector>
 
+#include <regex.h>
 #include <zlib.h>
 
 #include "../../../include/bkx.h"
@@ -108,6 +112,9 @@ struct Opts {
   int ml_mode = 0, max_ml = 0;   // -r / -R (kanga.cpp:482-486, 667-696); max_ml 0 = not given
   bool clamp_ml = false;         // -X
   bool pair_strand = false, pe_circ = false;
+  int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
+  std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
+  std::string none_file, multi_file;     // -j / -J: FASTA of the reads without a locus / with too many loci
   std::vector<std::string> in, pair;
   std::string sfx, out, logfile, title;
 };
@@ -437,18 +444,22 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'a': if (iv) unsupported.push_back("-a microInDels"); break;
       case 'A': if (iv) unsupported.push_back("-A splice junctions"); break;
       case 'k': unsupported.push_back("-k PCR artefact reduction"); break;
-      case 'x': if (iv) unsupported.push_back("-x flank trimming"); break;
+      case 'x': o.min_flank = iv; break;
+      case 'Z': o.excl.push_back(v); break;
+      case 'z': o.incl.push_back(v); break;
+      case 'j': o.none_file = v; break;
+      case 'J': o.multi_file = v; break;
       case 'p': if (iv) unsupported.push_back("-p SNP calling"); break;
       case '6': if (iv) unsupported.push_back("-6 PCR primer correction"); break;
       case 'b': unsupported.push_back("-b bisulfite"); break;
       case 'C': unsupported.push_back("-C colorspace"); break;
       case 'N': unsupported.push_back("-N best matches"); break;
       case 'X': o.clamp_ml = true; break;
-      case 'B': case 'H': case '5': case 'Z': case 'z': case 'j': case 'J': case 'O': case 'S': case '7': case '8':
+      case 'B': case 'H': case '5': case 'O': case 'S': case '7': case '8':
       case 'q': unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'h':
-        printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -M{0,5,6} -U -d -D -E -y -Y -l -L -i -u -I -o -F "
-               "[--gpus N]\n");
+        printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -M0..6 -g -t -U -d -D -E "
+               "-y -Y -l -L -x -Z -z -j -J -4 -T -i -u -I -o -F [--gpus N]\n");
         return 1;
       default: break;  // remaining reference options have no effect on this path (-w -W -K -G -P -1 -9 -V -0 -3 -v)
     }
@@ -469,6 +480,14 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.pe_mode < 0 || o.pe_mode > 4) { fprintf(stderr, "Error: paired end mode '-U%d' must be in range 0..4\n", o.pe_mode); return -1; }
   if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
   if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
+  if (o.min_flank < 0 || o.min_flank > 7) { fprintf(stderr, "Error: Max flank trimming '-x%d' specified outside of range 0..7\n", o.min_flank); return -1; }  // kanga.cpp:804-808
+  if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
+  if (o.pe_mode && (o.min_flank || !o.excl.empty() || !o.incl.empty())) {
+    // paired ends: the filters act inside the pairing (AcceptThisChromID, Aligner.cpp:2651) and the trimming keeps a
+    // central core (AutoTrimFlanks, :1700-1745); the pairing kernels do neither
+    fprintf(stderr, "bkx-align: options -x / -Z / -z are not supported together with paired end processing '-U%d'\n", o.pe_mode);
+    return -1;
+  }
   if (o.gpus < 1) o.gpus = 1;
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
@@ -756,6 +775,25 @@ int main(int argc, char** argv) {
   auto t_start = std::chrono::steady_clock::now();
   diag("Subprocess align Version 4.4.2 (bkx B200 path) starting");
 
+  // ---- chromosome filter expressions are compiled up front, so that a malformed one stops the run before any work
+  //      (CompileChromRegExprs, Aligner.cpp:4736-4798: POSIX extended, case insensitive)
+  std::vector<regex_t> rin(o.incl.size()), rex(o.excl.size());
+  {
+    auto compile = [&](const std::vector<std::string>& src, std::vector<regex_t>& dst, const char* what) -> bool {
+      for (size_t k = 0; k < src.size(); ++k) {
+        int e = regcomp(&dst[k], src[k].c_str(), REG_EXTENDED | REG_ICASE);
+        if (e) {
+          char msg[128];
+          regerror(e, &dst[k], msg, sizeof(msg));
+          diag("Unable to process %s chrom '%s' error: %s", what, src[k].c_str(), msg);
+          return false;
+        }
+      }
+      return true;
+    };
+    if (!compile(o.incl, rin, "include") || !compile(o.excl, rex, "exclude")) return 1;
+  }
+
   // ---- reads load on their own thread while the index streams to the GPU (the reference also loads in the background)
   Reads R;
   int reads_rc = 0;
@@ -930,6 +968,150 @@ int main(int argc, char** argv) {
     diag("Paired end association and partner alignment processing completed..");
   }
 
+  std::vector<bkx_entry> ents(info.num_entries + 1);
+  for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
+  unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  // host copy of the chromosomes (1 byte/base) for the passes and writers that compare with / print the target sequence
+  std::vector<std::vector<uint8_t>> genome(info.num_entries + 1);
+  if (o.fmt == 1 || o.fmt == 3 || o.min_flank > 0)
+    for (uint32_t e = 1; e <= info.num_entries; ++e) {
+      genome[e].resize(ents[e].seq_len);
+      if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+    }
+
+  // ---- -x: AutoTrimFlanks, Aligner.cpp:1608-1812 (single-end form).  Each accepted alignment is cut back from both
+  //      ends to the first run of MinFlankExacts matching bases; the rest must keep at least half the read (>= 15 bp)
+  //      or the read is sloughed as eNARTrim.  TrimLeft / TrimRight are in READ orientation (Aligner.cpp:1528-1549).
+  std::vector<uint16_t> trim_l, trim_r;
+  std::vector<uint8_t> trim_mm;   // Seg[0].TrimMismatches: mismatches left inside the trimmed alignment
+  uint32_t elim_plus = 0, elim_minus = 0, num_trimmed = 0;
+  if (o.min_flank > 0) {
+    diag("Autotrim aligned read flank processing started..");
+    diag("Starting 5' and 3' flank sequence autotrim processing...");
+    trim_l.assign(nrec, 0); trim_r.assign(nrec, 0); trim_mm.assign(nrec, 0);
+    std::vector<uint32_t> ep(fmt_threads, 0), em(fmt_threads, 0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < fmt_threads; ++t)
+      th.emplace_back([&, t]() {
+        std::vector<uint8_t> rd, tg;
+        const uint32_t b0 = (uint32_t)((uint64_t)nrec * t / fmt_threads), e0 = (uint32_t)((uint64_t)nrec * (t + 1) / fmt_threads);
+        for (uint32_t i = b0; i < e0; ++i) {
+          bkx_read_result& r = res[i];
+          trim_mm[i] = r.mismatches;
+          if (r.nar != BKX_NAR_ACCEPTED) continue;
+          const int L = r.match_len, minlen = std::max(15, (L + 1) / 2), X = o.min_flank;
+          const uint8_t* b = R.bases.data() + R.offs[rix(i)];
+          const uint8_t* g = genome[r.chrom_id].data() + r.match_loci;
+          rd.resize(L); tg.resize(L);
+          for (int q = 0; q < L; ++q) rd[q] = b[q] & 7;
+          if (r.strand == '-') for (int q = 0; q < L; ++q) { uint8_t c = g[L - 1 - q] & 7; tg[q] = c < 4 ? 3 - c : c; }
+          else for (int q = 0; q < L; ++q) tg[q] = g[q] & 7;
+          auto slough = [&]() { r.num_hits = 0; r.nar = BKX_NAR_TRIM; ++(r.strand == '+' ? ep[t] : em[t]); };
+          int exact = 0, tmm = 0, k;
+          for (k = 0; k <= L - minlen && k < L; ++k) {       // 5' -> 3'
+            if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
+            if (++exact == X) break;
+          }
+          if (k + minlen > L || exact < X) { slough(); continue; }
+          const int left = k - (X - 1);
+          exact = 0;
+          for (k = L - 1; k >= left + minlen && k > 0; --k) {  // 3' -> 5'
+            if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
+            if (++exact == X) break;
+          }
+          if (exact != X || k < left + minlen) { slough(); continue; }
+          const int right = k + X;
+          trim_l[i] = (uint16_t)left; trim_r[i] = (uint16_t)(L - right);
+          if (left || L - right) trim_mm[i] = (uint8_t)(r.mismatches - tmm);
+        }
+      });
+    for (auto& x : th) x.join();
+    for (unsigned t = 0; t < fmt_threads; ++t) { elim_plus += ep[t]; elim_minus += em[t]; }
+    diag("Finished 5' and 3' flank sequence autotriming, %d plus strand and %d minus strand aligned reads removed", (int)elim_plus, (int)elim_minus);
+    diag("Autotrim aligned read flank processing completed");
+  }
+  // the alignment as reported: AdjStartLoci / AdjHitLen / TrimMismatches (Aligner.cpp:1528-1552)
+  auto tleft = [&](uint32_t i) -> uint32_t { return trim_l.empty() ? 0u : trim_l[i]; };
+  auto tright = [&](uint32_t i) -> uint32_t { return trim_r.empty() ? 0u : trim_r[i]; };
+  auto adj_start = [&](uint32_t i) -> uint32_t { return res[i].match_loci + (res[i].strand == '+' ? tleft(i) : tright(i)); };
+  auto adj_len = [&](uint32_t i) -> uint32_t { return (uint32_t)res[i].match_len - tleft(i) - tright(i); };
+  auto adj_mm = [&](uint32_t i) -> uint32_t { return trim_mm.empty() ? res[i].mismatches : trim_mm[i]; };
+
+  // ---- -Z / -z: FiltByChroms, Aligner.cpp:4019-4124.  A chromosome matching an include expression stays; with no
+  //      include expressions given it stays unless an exclude expression matches; otherwise its alignments become
+  //      eNARChromFilt.  (Exclude expressions are not consulted once include expressions exist -- as in the reference.)
+  if (!o.excl.empty() || !o.incl.empty()) {
+    diag("Filtering aligned reads by chromosome started..");
+    diag("Now filtering matches by chromosome");
+    std::vector<char> keep(info.num_entries + 1, 1);
+    for (uint32_t e = 1; e <= info.num_entries; ++e) {
+      regmatch_t mc;
+      bool ok = false;
+      for (auto& re : rin) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = true; break; }
+      if (!ok && rin.empty()) {
+        ok = true;
+        for (auto& re : rex) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = false; break; }
+      }
+      keep[e] = ok;
+    }
+    for (auto& re : rin) regfree(&re);
+    for (auto& re : rex) regfree(&re);
+    int removed = 0;
+    for (uint32_t i = 0; i < nrec; ++i) {
+      bkx_read_result& r = res[i];
+      if (r.nar == BKX_NAR_ACCEPTED && !keep[r.chrom_id]) { r.nar = BKX_NAR_CHROMFILT; r.num_hits = 0; r.low_hit_instances = 0; ++removed; }
+    }
+    diag("Filtering by chromosome completed - removed %d  matches", removed);
+    diag("Filtering aligned reads by chromosome completed");
+  }
+
+  // "were trimmed" of the summary: FlagTR of the alignments still accepted at this point (Aligner.cpp:3558)
+  if (!trim_l.empty())
+    for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED && (trim_l[i] || trim_r[i])) ++num_trimmed;
+
+  // ---- order (SortReadHits(eRSMHitMatch): on the alignment as reported, i.e. after trimming)
+  std::vector<uint32_t> order(nrec);
+  {
+    std::vector<bkx_read_result> keyed;
+    if (!trim_l.empty()) {
+      keyed = res;
+      for (uint32_t i = 0; i < nrec; ++i) { keyed[i].match_loci = adj_start(i); keyed[i].match_len = (uint16_t)adj_len(i); }
+    }
+    if (nrec && bkx_sort_hits(keyed.empty() ? res.data() : keyed.data(), nrec, order.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+  }
+
+  // ---- -j / -J: ReportNoneAligned / ReportMultiAlign, Aligner.cpp:3826-4016 -- FASTA, 70 columns, in hit order
+  auto report_reads = [&](const std::string& path, const char* cls, auto&& want) -> bool {
+    OutBuf fb;
+    if (!fb.open(path)) { diag("Fatal: unable to create '%s'", path.c_str()); return false; }
+    emit_rows(fb, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
+      const uint32_t i = order[k];
+      if (!want(res[i])) return;
+      const uint32_t ri = rix(i);
+      const int L = R.len(ri);
+      s += ">lcl|"; s += cls; s += '|'; append_uint(s, (uint64_t)i + 1); s += ' '; s += R.name(ri); s += ' ';
+      append_uint(s, (uint64_t)i + 1); s += "|1|"; append_uint(s, (uint64_t)L); s += '\n';
+      const uint8_t* b = R.bases.data() + R.offs[ri];
+      for (int q = 0; q < L; ++q) {
+        uint8_t c = b[q] & 7;
+        s += c < 4 ? "ACGT"[c] : 'N';
+        if (q + 1 == L || (q + 1) % 70 == 0) s += '\n';
+      }
+    });
+    fb.close();
+    return true;
+  };
+  if (!o.none_file.empty()) {
+    diag("Reporting of non-aligned reads started..");
+    if (!report_reads(o.none_file, "na", [](const bkx_read_result& r) { return r.nar == BKX_NAR_NS || r.nar == BKX_NAR_NOHIT; })) return 1;
+    diag("Reporting of non-aligned reads completed");
+  }
+  if (!o.multi_file.empty()) {
+    diag("Reporting of multialigned reads started..");
+    if (!report_reads(o.multi_file, "ml", [](const bkx_read_result& r) { return r.nar == BKX_NAR_MULTIALIGN; })) return 1;
+    diag("Reporting of multialigned reads completed");
+  }
+
   // ---- summary, Aligner.cpp:3535-3769
   uint64_t nar[BKX_NAR_COUNT] = {0};
   uint64_t plus = 0;
@@ -946,7 +1128,7 @@ int main(int argc, char** argv) {
        (unsigned)plus, (unsigned)(nar[BKX_NAR_ACCEPTED] - plus));
   diag("A further %u multiloci aligned reads could not accepted as hits because they were unresolvable", (unsigned)nar[BKX_NAR_MULTIALIGN]);
   diag("A further %u aligned reads were not accepted as hits because of insufficient Hamming edit distance", (unsigned)nar[BKX_NAR_MMDELTA]);
-  diag("A further %u '+' and %u '-' strand aligned reads not accepted because of flank trimming (%d were trimmed) requirements", 0u, 0u, 0);
+  diag("A further %u '+' and %u '-' strand aligned reads not accepted because of flank trimming (%d were trimmed) requirements", (unsigned)elim_plus, (unsigned)elim_minus, (int)num_trimmed);
   diag("Unable to align %u source reads of which %d were not aligned as they contained excessive number of indeterminate 'N' bases",
        (unsigned)no_match, (int)S.num_sloughed_ns);
   diag("Read nonalignment reason summary:");
@@ -956,12 +1138,7 @@ int main(int argc, char** argv) {
     diag("   %u (%s) %s", (unsigned)v, kNarCode[k], kNarText[k]);
   }
 
-  // ---- order and write
-  std::vector<uint32_t> order(nrec);
-  if (nrec && bkx_sort_hits(res.data(), nrec, order.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
-  std::vector<bkx_entry> ents(info.num_entries + 1);
-  for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
-  unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  // ---- write
   OutBuf ob;
   if (!ob.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
   diag("Reporting of aligned result set started...");
@@ -975,40 +1152,35 @@ int main(int argc, char** argv) {
       const bkx_read_result& r = res[i];
       if (r.nar != BKX_NAR_ACCEPTED) return;
       s += ents[r.chrom_id].name; s += '\t';
-      append_uint(s, r.match_loci); s += '\t';
-      append_uint(s, (uint64_t)r.match_loci + r.match_len); s += "\tar\t0\t"; s += (char)r.strand; s += '\n';
+      append_uint(s, adj_start(i)); s += '\t';
+      append_uint(s, (uint64_t)adj_start(i) + adj_len(i)); s += "\tar\t0\t"; s += (char)r.strand; s += '\n';
     });
   } else if (o.fmt <= 3) {
     // ReadID,"ar","species","chrom",start,end,len,"strand",score,0,NumReads,TrimMismatches,"N/A","descriptor"
     // -M2/-M3 append the read sequence, -M1/-M3 the matched genome sequence in read orientation (Aligner.cpp:6612-6621)
-    std::vector<std::vector<uint8_t>> genome(info.num_entries + 1);
-    if (o.fmt == 1 || o.fmt == 3)
-      for (uint32_t e = 1; e <= info.num_entries; ++e) {
-        genome[e].resize(ents[e].seq_len);
-        if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
-      }
     emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
       if (r.nar != BKX_NAR_ACCEPTED) return;
       append_uint(s, (uint64_t)i + 1);
       s += ",\"ar\",\""; s += info.dataset_name; s += "\",\""; s += ents[r.chrom_id].name; s += "\",";
-      append_uint(s, r.match_loci); s += ',';
-      append_uint(s, (uint64_t)r.match_loci + r.match_len - 1); s += ',';
-      append_uint(s, r.match_len); s += ",\""; s += (char)r.strand; s += "\",0,0,1,";
+      const uint32_t start = adj_start(i), alen = adj_len(i);   // the alignment as trimmed by -x, if at all
+      append_uint(s, start); s += ',';
+      append_uint(s, (uint64_t)start + alen - 1); s += ',';
+      append_uint(s, alen); s += ",\""; s += (char)r.strand; s += "\",0,0,1,";
       const uint32_t ri = rix(i);
-      append_uint(s, r.mismatches); s += ",\"N/A\",\""; s += R.name(ri); s += '"';
+      append_uint(s, adj_mm(i)); s += ",\"N/A\",\""; s += R.name(ri); s += '"';
       if (o.fmt >= 2) {
         s += ",\"";
-        const uint8_t* b = R.bases.data() + R.offs[ri];
-        for (int q = 0; q < R.len(ri); ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+        const uint8_t* b = R.bases.data() + R.offs[ri] + tleft(i);
+        for (uint32_t q = 0; q < alen; ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
         s += '"';
       }
       if (o.fmt == 1 || o.fmt == 3) {
         s += ",\"";
-        const uint8_t* g = genome[r.chrom_id].data() + r.match_loci;
-        if (r.strand == '-') for (int q = r.match_len - 1; q >= 0; --q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
-        else for (int q = 0; q < r.match_len; ++q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+        const uint8_t* g = genome[r.chrom_id].data() + start;
+        if (r.strand == '-') for (int q = (int)alen - 1; q >= 0; --q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
+        else for (uint32_t q = 0; q < alen; ++q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
         s += '"';
       }
       s += '\n';
@@ -1043,7 +1215,7 @@ int main(int argc, char** argv) {
     BaiBuilder bai;
     bai.out = "BAI\1";
     bai.put32(nref);
-    struct RecMeta { uint64_t uofs; uint32_t len; int32_t rid, pos; int32_t L; uint8_t acc; };
+    struct RecMeta { uint64_t uofs; uint32_t len; int32_t rid, pos; int32_t L, alen; uint8_t acc, lead, trail; };
     std::vector<RecMeta> meta;
     meta.reserve(nrec);
     uint64_t utotal = hdr.size();
@@ -1055,8 +1227,12 @@ int main(int argc, char** argv) {
       const uint32_t ri = rix(i);
       const int L = R.len(ri);
       uint32_t lname = (uint32_t)strlen(R.name(ri)) + 1;
-      uint32_t len = 4 + 32 + lname + 4 + (uint32_t)((L + 1) / 2) + (uint32_t)L + (acc ? 0u : 6u);
-      meta.push_back({utotal, len, acc ? refid[r.chrom_id] : -1, acc ? (int32_t)r.match_loci : -1, L, (uint8_t)acc});
+      // -x trims become soft clips either side of the M operation (Aligner.cpp:5960-5985)
+      const uint32_t lead = !acc ? 0u : r.strand == '+' ? tleft(i) : tright(i), trail = !acc ? 0u : r.strand == '+' ? tright(i) : tleft(i);
+      const uint32_t ncig = 1 + (lead ? 1 : 0) + (trail ? 1 : 0);
+      uint32_t len = 4 + 32 + lname + 4 * ncig + (uint32_t)((L + 1) / 2) + (uint32_t)L + (acc ? 0u : 6u);
+      meta.push_back({utotal, len, acc ? refid[r.chrom_id] : -1, acc ? (int32_t)adj_start(i) : -1, L, acc ? (int32_t)adj_len(i) : L,
+                      (uint8_t)acc, (uint8_t)lead, (uint8_t)trail});
       utotal += len;
     }
     std::vector<uint8_t> U(utotal);
@@ -1097,16 +1273,19 @@ int main(int argc, char** argv) {
       const char* qn = R.name(ri);
       uint32_t lname = (uint32_t)strlen(qn) + 1;
       int32_t rid = M.rid, pos = M.pos;
-      uint32_t bin = acc ? (uint32_t)bai_reg2bin(pos, pos + L) : 0;
-      uint32_t bmn = bin << 16 | 255u << 8 | lname, fnc = (uint32_t)flags << 16 | 1u;
+      const uint32_t ncig = 1 + (M.lead ? 1 : 0) + (M.trail ? 1 : 0);
+      uint32_t bin = acc ? (uint32_t)bai_reg2bin(pos, pos + M.alen) : 0;
+      uint32_t bmn = bin << 16 | 255u << 8 | lname, fnc = (uint32_t)flags << 16 | ncig;
       int32_t nrid = (acc && pnext >= 0) ? rid : -1, npos = acc ? (int32_t)pnext : -1, tl = acc ? tlen : 0, lseq = L;
-      uint32_t cigar = (uint32_t)L << 4;
+      uint32_t cigar = (uint32_t)M.alen << 4, clip_lead = (uint32_t)M.lead << 4 | 4u, clip_trail = (uint32_t)M.trail << 4 | 4u;
       uint8_t* w = U.data() + M.uofs;
       uint32_t bsz = M.len - 4;
       auto p32 = [&](const void* v) { memcpy(w, v, 4); w += 4; };
       p32(&bsz); p32(&rid); p32(&pos); p32(&bmn); p32(&fnc); p32(&lseq); p32(&nrid); p32(&npos); p32(&tl);
       memcpy(w, qn, lname); w += lname;
+      if (M.lead) p32(&clip_lead);
       p32(&cigar);
+      if (M.trail) p32(&clip_trail);
       bool rc = acc && r.strand != '+';
       for (int q = 0; q < L; q += 2) {
         auto nib = [&](int idx) -> unsigned {
@@ -1143,7 +1322,7 @@ int main(int argc, char** argv) {
       const RecMeta& M = meta[mi];
       if (!M.acc) continue;
       while (cur_ref < M.rid) { if (cur_ref >= 0) bai.end_ref(); ++cur_ref; }
-      bai.add(bz.vaddr(M.uofs), (uint32_t)M.pos, bz.vaddr(M.uofs + M.len), (uint32_t)(M.pos + M.L - 1));
+      bai.add(bz.vaddr(M.uofs), (uint32_t)M.pos, bz.vaddr(M.uofs + M.len), (uint32_t)(M.pos + M.alen - 1));
     }
     bai.end_ref();  // Close(): the reference in progress (an empty block when nothing aligned)
     ok = ok && bz.close();
@@ -1189,10 +1368,16 @@ int main(int argc, char** argv) {
       const uint32_t ri = rix(i);
       s += R.name(ri); s += '\t';
       append_uint(s, (uint64_t)flags); s += '\t';
-      if (acc) { s += ents[r.chrom_id].name; s += '\t'; append_uint(s, (uint64_t)r.match_loci + 1); }
+      if (acc) { s += ents[r.chrom_id].name; s += '\t'; append_uint(s, (uint64_t)adj_start(i) + 1); }
       else s += "*\t0";
       s += "\t255\t";
-      append_uint(s, (uint64_t)R.len(ri)); s += "M\t";
+      if (acc) {  // flanks trimmed by -x are soft clipped, in reference orientation (Aligner.cpp:5960-5985)
+        const uint32_t lead = r.strand == '+' ? tleft(i) : tright(i), trail = r.strand == '+' ? tright(i) : tleft(i);
+        if (lead) { append_uint(s, lead); s += 'S'; }
+        append_uint(s, adj_len(i)); s += 'M';
+        if (trail) { append_uint(s, trail); s += 'S'; }
+        s += '\t';
+      } else { append_uint(s, (uint64_t)R.len(ri)); s += "M\t"; }
       if (acc && pnext >= 0) { s += "=\t"; append_uint(s, (uint64_t)pnext + 1); s += '\t'; append_uint(s, (uint64_t)tlen); s += '\t'; }
       else s += "*\t0\t0\t";
       const uint8_t* b = R.bases.data() + R.offs[ri];

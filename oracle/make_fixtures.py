@@ -315,10 +315,69 @@ def case_formats():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_post():
+    """Post-alignment host passes on the tiny index: chromosome filters -Z / -z, flank
+    auto-trimming -x (CSV variants, BED, SAM, BAM + BAI), and the non-aligned / multi-aligned read reports -j / -J."""
+    d = os.path.join(GOLD, "post")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        with gzip.open(os.path.join(tiny, "tiny.sfx.gz"), "rb") as f, open(os.path.join(tmp, "tiny.sfx"), "wb") as g:
+            shutil.copyfileobj(f, g)
+        import pyoracle as po
+        names, bases, offs = po.read_fasta_reads(os.path.join(tiny, "r100.fa.gz"))
+        # no two reads from the same (chromosome, position): byte-comparable BAM / BAI (see case_formats)
+        seen, keep = set(), []
+        for i in range(len(names)):
+            key = tuple(names[i].split("|")[1:3])
+            if key not in seen and len(keep) < 1200:
+                seen.add(key)
+                keep.append(i)
+        synth.write_reads_fasta(os.path.join(tmp, "p.fa"), [names[i] for i in keep], [bases[offs[i]:offs[i + 1]] for i in keep])
+        gz(os.path.join(tmp, "p.fa"), os.path.join(d, "p.fa.gz"))
+        runs = {
+            "Z2": (["-s3", "-M0", "-Zchr2"], "Z2.csv"), "Z2sam": (["-s3", "-M6", "-Zchr2"], "Z2.sam"),
+            "z13": (["-s3", "-M0", "-zchr[13]"], "z13.csv"), "zZ": (["-s3", "-M0", "-zCHR[12]", "-Zchr2", "-Zchr4"], "zZ.csv"),
+            "ZZ": (["-s3", "-M5", "-Zchr1$", "-Z^chr3"], "ZZ.sam"),
+            "x5": (["-s5", "-M0", "-x5"], "x5.csv"), "x5m3": (["-s5", "-M3", "-x5"], "x5m3.csv"),
+            "x5bed": (["-s5", "-M4", "-x5"], "x5.bed"), "x5sam": (["-s5", "-M6", "-x5"], "x5.sam"),
+            "x7": (["-s8", "-M0", "-x7"], "x7.csv"), "x3Q1": (["-s6", "-M5", "-x3", "-Q1"], "x3Q1.sam"),
+            "x6Z": (["-s6", "-M0", "-x6", "-Zchr3"], "x6Z.csv"),
+            "jJ": (["-s3", "-M0", "-jnone.fa", "-Jmulti.fa"], "jJ.csv"),
+            "jJr1": (["-s3", "-M0", "-r1", "-R3", "-jnone1.fa", "-Jmulti1.fa.gz"], "jJr1.csv"),
+        }
+        meta = {}
+        for tag, (args, out) in runs.items():
+            run(["align", "-I", "tiny.sfx", "-i", "p.fa", "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out}
+            for a in args:
+                if a[:2] in ("-j", "-J"):
+                    if a.endswith(".gz"):
+                        shutil.copyfile(os.path.join(tmp, a[2:]), os.path.join(d, a[2:]))
+                    else:
+                        gz(os.path.join(tmp, a[2:]), os.path.join(d, a[2:] + ".gz"))
+        # 50 bp reads with up to 4 substitutions: some cannot keep half their length between two 7-base exact flanks (eNARTrim)
+        with gzip.open(os.path.join(tiny, "r50.fa.gz"), "rb") as f, open(os.path.join(tmp, "r50.fa"), "wb") as g:
+            shutil.copyfileobj(f, g)
+        for tag, args, out in (("x7r50", ["-s10", "-M0", "-x7"], "x7r50.csv"), ("x7r50sam", ["-s10", "-M6", "-x7"], "x7r50.sam")):
+            run(["align", "-I", "tiny.sfx", "-i", "r50.fa", "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": "../tiny/r50.fa.gz"}
+        for tag, args, out in (("x5bam", ["-s5", "-M5", "-x5"], "x5.bam"), ("x5bam6", ["-s5", "-M6", "-x5", "-Zchr2"], "x56.bam")):
+            run(["align", "-I", "tiny.sfx", "-i", "p.fa", "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+            shutil.copyfile(os.path.join(tmp, out), os.path.join(d, out))
+            shutil.copyfile(os.path.join(tmp, out + ".bai"), os.path.join(d, out + ".bai"))
+            meta[tag] = {"args": args, "out": out}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -327,4 +386,6 @@ if __name__ == "__main__":
         case_formats()
     if "lowcopy" in which:
         case_lowcopy()
+    if "post" in which:
+        case_post()
     print("fixtures written under", GOLD)

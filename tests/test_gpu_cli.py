@@ -75,6 +75,15 @@ def test_cli_rejects_unsupported_and_bad_options(tmp_path, golden_dir):
     assert r.returncode != 0
     r = subprocess.run([CLI, "align", "-I", "/nonexistent.sfx", "-i", rd, "-o", str(tmp_path / "x")], capture_output=True, text=True)
     assert r.returncode != 0
+    pe = ["-u", os.path.join(gu.GOLD, "tiny", "pe2.fa.gz"), "-U2"]   # the pairing kernels neither filter nor trim
+    for extra in (["-x5"], ["-Zchr1"], ["-zchr1"]):
+        r = subprocess.run([CLI, "align", "-I", sfx, "-i", os.path.join(gu.GOLD, "tiny", "pe1.fa.gz"), "-o", str(tmp_path / "x")] + pe + extra,
+                           capture_output=True, text=True)
+        assert r.returncode != 0 and "not supported together with paired end" in r.stderr
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-x8"], capture_output=True, text=True)
+    assert r.returncode != 0 and "0..7" in r.stderr
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-Zchr[1"], capture_output=True, text=True)
+    assert r.returncode != 0     # malformed expression: refused like the reference's regcomp failure
 
 
 def _lines(path):
@@ -103,6 +112,38 @@ def test_cli_output_formats_match_reference(tag, golden_dir, tmp_path):
     assert sorted(ours) == sorted(ref)
 
 
+POST_TAGS = ["Z2", "Z2sam", "z13", "zZ", "ZZ", "x5", "x5m3", "x5bed", "x5sam", "x7", "x3Q1", "x6Z", "jJ", "jJr1", "x7r50", "x7r50sam"]
+
+
+@pytest.mark.parametrize("tag", POST_TAGS)
+def test_cli_post_alignment_passes_match_reference(tag, golden_dir, tmp_path):
+    """Post-alignment host passes: chromosome filters -Z / -z, flank auto-trimming -x in every output
+    format (trimmed coordinates, soft clips, eNARTrim), the -j / -J read reports; records, header and summary block."""
+    import json
+    fdir = os.path.join(gu.GOLD, "post")
+    run = json.load(open(os.path.join(fdir, "runs.json")))[tag]
+    sfx = gu.sfx_path("tiny", golden_dir)
+    reads = os.path.join(fdir, run.get("reads", "p.fa.gz"))
+    subprocess.run([CLI, "align", "-I", sfx, "-i", reads, "-o", run["out"], "-F", "o.log"] + run["args"], check=True,
+                   stdout=subprocess.DEVNULL, cwd=tmp_path)
+    ours, ref = _lines(tmp_path / run["out"]), _lines(os.path.join(fdir, run["out"] + ".gz"))
+    head = [x for x in ref if x.startswith("@") or x.startswith("track")]
+    assert [x for x in ours if x.startswith("@") or x.startswith("track")] == head
+    assert sorted(ours) == sorted(ref)
+    exp_log = [x for x in open(os.path.join(fdir, tag + ".log")).read().splitlines()
+               if not x.startswith(("Sorting alignments", "Header written", "Reported SAM", "Completed reporting SAM"))]
+    assert summary_block(tmp_path / "o.log") == exp_log
+    for a in run["args"]:          # -j / -J: same FASTA records (the reference's order among equal sort keys is unspecified)
+        if a[:2] in ("-j", "-J"):
+            name = a[2:]
+            got = _lines(tmp_path / name)
+            exp = _lines(os.path.join(fdir, name if name.endswith(".gz") else name + ".gz"))
+            recs = lambda ls: sorted("\n".join(ls).split(">")[1:])
+            assert recs(got) == recs(exp) and len(got) == len(exp)
+            if name.endswith(".gz"):
+                assert open(tmp_path / name, "rb").read(2) == b"\x1f\x8b"
+
+
 def _bgzf_blocks(raw):
     import struct
     o, out = 0, []
@@ -114,14 +155,19 @@ def _bgzf_blocks(raw):
     return out
 
 
-@pytest.mark.parametrize("tag,args,out", [("bam5", ["-s3", "-M5"], "out5.bam"), ("bam6", ["-s3", "-M6", "-g0"], "out6.bam"),
-                                          ("bamQ2", ["-s3", "-M6", "-Q2"], "out62.bam")])
+BAM_RUNS = [("bam5", ["-s3", "-M5"], "out5.bam"), ("bam6", ["-s3", "-M6", "-g0"], "out6.bam"), ("bamQ2", ["-s3", "-M6", "-Q2"], "out62.bam"),
+            ("x5bam", ["-s5", "-M5", "-x5"], "x5.bam"), ("x5bam6", ["-s5", "-M6", "-x5", "-Zchr2"], "x56.bam")]
+
+
+@pytest.mark.parametrize("tag,args,out", BAM_RUNS)
 def test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path):
     """BAM (BGZF) + BAI written for an output name ending in .bam: byte-identical to the reference's files
-    (the read set has no two reads at the same locus, so sort ties cannot reorder records)."""
-    fdir = os.path.join(gu.GOLD, "formats")
+    (the read sets have no two reads at the same locus, so sort ties cannot reorder records); the x5* runs carry
+    soft clips from -x trimming and records filtered by -Z."""
+    fdir = os.path.join(gu.GOLD, "post" if tag.startswith("x5") else "formats")
     sfx = gu.sfx_path("tiny", golden_dir)
-    subprocess.run([CLI, "align", "-I", sfx, "-i", os.path.join(fdir, "qu.fq.gz"), "-o", str(tmp_path / out)] + args, check=True,
+    reads = os.path.join(fdir, "p.fa.gz" if tag.startswith("x5") else "qu.fq.gz")
+    subprocess.run([CLI, "align", "-I", sfx, "-i", reads, "-o", str(tmp_path / out)] + args, check=True,
                    stdout=subprocess.DEVNULL)
     ours, ref = open(tmp_path / out, "rb").read(), open(os.path.join(fdir, out), "rb").read()
     assert gzip.decompress(ours) == gzip.decompress(ref)

@@ -46,8 +46,12 @@ def test_host_output_formats_match_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_output_formats_match_reference(tag, golden_dir, tmp_path)
 
 
-@pytest.mark.parametrize("tag,args,out", [("bam5", ["-s3", "-M5"], "out5.bam"), ("bam6", ["-s3", "-M6", "-g0"], "out6.bam"),
-                                          ("bamQ2", ["-s3", "-M6", "-Q2"], "out62.bam")])
+@pytest.mark.parametrize("tag", g.POST_TAGS)
+def test_host_post_alignment_passes_match_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_post_alignment_passes_match_reference(tag, golden_dir, tmp_path)
+
+
+@pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
 
