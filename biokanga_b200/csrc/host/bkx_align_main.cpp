@@ -112,6 +112,7 @@ struct Opts {
   int ml_mode = 0, max_ml = 0;   // -r / -R (kanga.cpp:482-486, 667-696); max_ml 0 = not given
   bool clamp_ml = false;         // -X
   bool pair_strand = false, pe_circ = false;
+  int pcr_win = -1;              // -k: PCR artefact reduction window, -1 = off (kanga.cpp:719-724)
   int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
   std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
   std::string none_file, multi_file;     // -j / -J: FASTA of the reads without a locus / with too many loci
@@ -443,7 +444,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'c': if (iv) unsupported.push_back("-c chimeric trimming"); break;
       case 'a': if (iv) unsupported.push_back("-a microInDels"); break;
       case 'A': if (iv) unsupported.push_back("-A splice junctions"); break;
-      case 'k': unsupported.push_back("-k PCR artefact reduction"); break;
+      case 'k': o.pcr_win = iv; if (iv < 0 || iv > 250) { fprintf(stderr, "Error: PCR differential amplification artefacts window length '-k%d' specified outside of range 0..250\n", iv); return -1; } break;
       case 'x': o.min_flank = iv; break;
       case 'Z': o.excl.push_back(v); break;
       case 'z': o.incl.push_back(v); break;
@@ -966,6 +967,73 @@ int main(int argc, char** argv) {
     if (o.pe_mode == BKX_PE_UNIQUE_SE || o.pe_mode == BKX_PE_ORPHAN_SE)
       diag("%d Paired End reads were unable to be associated with partner read and accepted as if SE aligned", (int)ps.accepted_num_se);
     diag("Paired end association and partner alignment processing completed..");
+  }
+
+  // ---- -k: ReducePCRduplicates, Aligner.cpp:2184-2282 (single-end runs only, :599).  In hit order, alignments that
+  //      share chromosome, start, strand and length with an earlier one are dropped as eNARPCRdup once the allowance
+  //      is used up; with a window the allowance grows with the number of distinct start loci within WinLen either
+  //      side (NumUpUniques / NumDnUniques, :9817-9914).  Which of several reads with identical sort keys survives is
+  //      left open by the reference's unstable sort; here it is the one loaded first.
+  if (o.pcr_win >= 0 && !o.pe_mode) {
+    diag("Processing to reduce PCR differential amplification artefacts processing started..");
+    std::vector<uint32_t> ord(nrec);
+    if (nrec && bkx_sort_hits(res.data(), nrec, ord.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+    const int W = o.pcr_win;
+    auto acc = [&](uint32_t k) { return res[ord[k]].nar == BKX_NAR_ACCEPTED; };
+    auto dn_uniques = [&](uint32_t k) -> int {
+      const bkx_read_result& c = res[ord[k]];
+      int n_u = 0;
+      uint32_t prv = c.match_loci;
+      for (uint32_t j = k + 1; j < nrec; ++j) {
+        const bkx_read_result& x = res[ord[j]];
+        if (x.chrom_id != c.chrom_id) break;
+        if (!acc(j)) continue;
+        if ((int64_t)c.match_loci + W < (int64_t)x.match_loci) break;
+        if (x.strand != c.strand) continue;
+        if (x.match_loci != prv) { ++n_u; prv = x.match_loci; }
+      }
+      return n_u;
+    };
+    auto up_uniques = [&](uint32_t k) -> int {
+      if (k == 0) return 0;
+      const bkx_read_result& c = res[ord[k]];
+      int n_u = 0;
+      uint32_t prv = c.match_loci;
+      for (uint32_t j = k + 1; j-- > 0;) {   // starts at the current record itself, as the reference does
+        const bkx_read_result& x = res[ord[j]];
+        if (x.chrom_id != c.chrom_id) break;
+        if (!acc(j)) continue;
+        if ((int64_t)c.match_loci > W && (int64_t)c.match_loci - W > (int64_t)x.match_loci) break;
+        if (x.strand != c.strand) continue;
+        if (x.match_loci != prv) { ++n_u; prv = x.match_loci; }
+      }
+      return n_u;
+    };
+    int removed = 0;
+    for (uint32_t k = 0; k < nrec; ++k) {
+      if (!acc(k)) continue;
+      int limit = 0;
+      if (W > 0) {
+        limit = std::max(up_uniques(k), dn_uniques(k));
+        const int prop = (int)(((double)limit / W) * 100.0);
+        limit = prop < 5 ? 1 : prop <= 10 ? 2 : prop <= 20 ? 3 : prop <= 40 ? 4 : prop <= 60 ? 5 : prop <= 80 ? 10 : 50;
+      }
+      const bkx_read_result c = res[ord[k]];
+      uint32_t mark = k;
+      for (uint32_t j = k + 1; j < nrec; ++j) {
+        bkx_read_result& x = res[ord[j]];
+        if (x.nar != BKX_NAR_ACCEPTED) continue;
+        if (x.chrom_id != c.chrom_id || x.match_loci != c.match_loci || x.strand != c.strand) break;
+        if (x.match_len != c.match_len) continue;
+        if (limit > 0) { --limit; continue; }
+        x.num_hits = 0; x.low_hit_instances = 0; x.nar = BKX_NAR_PCRDUP;
+        mark = j;
+        ++removed;
+      }
+      k = mark;
+    }
+    diag("Removed %d potential PCR artefact reads", removed);
+    diag("PCR differential amplification artefacts processing completed");
   }
 
   std::vector<bkx_entry> ents(info.num_entries + 1);

@@ -374,10 +374,47 @@ def case_post():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_dups():
+    """PCR artefact reduction -k on the tiny index: a read set in which many reads stack on the same start locus (copies of
+    a read, some with one more substitution so that the copies differ in LowMMCnt).  Which of several identical copies
+    survives depends on the reference's unstable sort: compare rows without read id / name."""
+    d = os.path.join(GOLD, "dups")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        with gzip.open(os.path.join(tiny, "tiny.sfx.gz"), "rb") as f, open(os.path.join(tmp, "tiny.sfx"), "wb") as g:
+            shutil.copyfileobj(f, g)
+        import pyoracle as po
+        names, bases, offs = po.read_fasta_reads(os.path.join(tiny, "r100.fa.gz"))
+        rng = np.random.default_rng(77)
+        out_n, out_r = [], []
+        for i in range(700):
+            r = bases[offs[i]:offs[i + 1]].copy()
+            out_n.append(names[i]); out_r.append(r)
+            if rng.random() < 0.5:
+                for c in range(int(rng.integers(1, 8))):
+                    v = r.copy()
+                    if rng.random() < 0.3 and v[50] < 4:
+                        v[50] = (v[50] + 1) & 3
+                    out_n.append("d%d_%s" % (c, names[i])); out_r.append(v)
+        perm = rng.permutation(len(out_n))
+        synth.write_reads_fasta(os.path.join(tmp, "dup.fa"), [out_n[k] for k in perm], [out_r[k] for k in perm])
+        gz(os.path.join(tmp, "dup.fa"), os.path.join(d, "dup.fa.gz"))
+        meta = {}
+        for tag, args, out in (("k0", ["-s3", "-M0", "-k0"], "k0.csv"), ("k50", ["-s3", "-M0", "-k50"], "k50.csv"),
+                               ("k250", ["-s3", "-M0", "-k250"], "k250.csv"), ("k20sam", ["-s3", "-M6", "-k20"], "k20.sam"),
+                               ("k0x4", ["-s3", "-M0", "-k0", "-x4", "-Zchr3"], "k0x4.csv")):
+            run(["align", "-I", "tiny.sfx", "-i", "dup.fa", "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -388,4 +425,6 @@ if __name__ == "__main__":
         case_lowcopy()
     if "post" in which:
         case_post()
+    if "dups" in which:
+        case_dups()
     print("fixtures written under", GOLD)

@@ -51,6 +51,11 @@ def test_host_post_alignment_passes_match_reference(tag, cli, golden_dir, tmp_pa
     g.test_cli_post_alignment_passes_match_reference(tag, golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", ["k0", "k50", "k250", "k20sam", "k0x4"])
+def test_host_pcr_artefact_reduction_matches_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_pcr_artefact_reduction_matches_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
