@@ -115,6 +115,7 @@ struct Opts {
   int pcr_win = -1;              // -k: PCR artefact reduction window, -1 = off (kanga.cpp:719-724)
   int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
   std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
+  std::string constraints_file;          // -5: loci base constraints CSV (chrom, start, end, bases)
   std::string none_file, multi_file;     // -j / -J: FASTA of the reads without a locus / with too many loci
   std::vector<std::string> in, pair;
   std::string sfx, out, logfile, title;
@@ -456,7 +457,8 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'C': unsupported.push_back("-C colorspace"); break;
       case 'N': unsupported.push_back("-N best matches"); break;
       case 'X': o.clamp_ml = true; break;
-      case 'B': case 'H': case '5': case 'O': case 'S': case '7': case '8':
+      case '5': o.constraints_file = v; break;
+      case 'B': case 'H': case 'O': case 'S': case '7': case '8':
       case 'q': unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'h':
         printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -M0..6 -g -t -U -d -D -E "
@@ -768,6 +770,83 @@ static bool is_bam_name(const std::string& p) {  // kanga.cpp:849-857: longer th
 
 static void append_uint(std::string& s, uint64_t v) { char b[24]; int n = snprintf(b, sizeof(b), "%llu", (unsigned long long)v); s.append(b, n); }
 
+// ---- -5: loci base constraints, CAligner::LoadLociConstraints, Aligner.cpp:1245-1441.  CSV rows chrom,start,end,bases:
+//      reads aligned over [start, end] of chrom are only kept if their base there is one of `bases` (A C G T; R = the
+//      target's own base).  An all-text first row is taken for a title row (CCSVFile::IsLikelyHeaderLine).
+struct LociConstraint { uint32_t chrom, start, end; uint8_t mask; };
+
+static int load_constraints(const std::string& path, const std::vector<bkx_entry>& ents, std::vector<LociConstraint>& out) {
+  diag("Loading loci base constraints from CSV file '%s' ...", path.c_str());
+  std::vector<char> text;
+  if (!slurp(path, text, 1)) { diag("Unable to open '%s' for processing", path.c_str()); return -1; }
+  const char *p = text.data(), *end = p + text.size();
+  int line_no = 0, rows = 0;
+  std::vector<uint32_t> chroms;
+  while (p < end) {
+    const char* eol = line_end(p, end);
+    std::string line(p, eol);
+    p = next_line(eol, end);
+    ++line_no;
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+    if (line.empty()) continue;
+    std::vector<std::string> f;
+    std::vector<char> quoted;
+    for (size_t b = 0; b <= line.size();) {
+      size_t c = line.find(',', b);
+      if (c == std::string::npos) c = line.size();
+      std::string v = line.substr(b, c - b);
+      size_t l = v.find_first_not_of(" \t"), r = v.find_last_not_of(" \t");
+      v = l == std::string::npos ? std::string() : v.substr(l, r - l + 1);
+      bool q = v.size() >= 2 && (v.front() == '"' || v.front() == '\'') && v.back() == v.front();
+      if (q) v = v.substr(1, v.size() - 2);
+      f.push_back(v);
+      quoted.push_back(q);
+      b = c + 1;
+    }
+    if (f.size() < 4) { diag("Expected at least 4 fields at line %d in '%s', GetCurFields() returned '%d'", line_no, path.c_str(), (int)f.size()); return -1; }
+    if (++rows == 1) {  // title row: no unquoted field that parses as a number, at most two empty ones
+      bool header = true;
+      int empties = 0;
+      for (size_t k = 0; k < f.size() && header; ++k) {
+        if (quoted[k]) continue;
+        if (f[k].empty()) { if (++empties > 2) header = false; continue; }
+        char* term = nullptr;
+        strtod(f[k].c_str(), &term);
+        if (term && *term == 0) header = false;
+      }
+      if (header) continue;
+    }
+    uint32_t chrom = 0;
+    for (uint32_t e = 1; e < ents.size(); ++e) if (!strcasecmp(f[0].c_str(), ents[e].name)) { chrom = e; break; }   // GetIdent: case insensitive
+    if (!chrom) { diag("Unable to find matching indexed identifier for '%s' at line %d in '%s'", f[0].c_str(), line_no, path.c_str()); return -1; }
+    const int start = atoi(f[1].c_str()), stop = atoi(f[2].c_str());
+    if (start < 0 || start > stop) { diag("Start loci must be >= 0 and <= end loci for '%s' at line %d in '%s'", f[0].c_str(), line_no, path.c_str()); return -1; }
+    if ((uint32_t)stop >= ents[chrom].seq_len) { diag("End loci must be > targeted sequence length for '%s' at line %d in '%s'", f[0].c_str(), line_no, path.c_str()); return -1; }
+    uint8_t mask = 0;
+    bool bad = false;
+    for (char c : f[3]) switch (c) {
+      case 'a': case 'A': mask |= 0x01; break;
+      case 'c': case 'C': mask |= 0x02; break;
+      case 'g': case 'G': mask |= 0x04; break;
+      case 't': case 'T': mask |= 0x08; break;
+      case 'r': case 'R': mask |= 0x10; break;
+      case ' ': case '\t': break;
+      default: bad = true;
+    }
+    if (bad || !mask) { diag("Illegal base specifiers for '%s' at line %d in '%s'", f[0].c_str(), line_no, path.c_str()); return -1; }
+    if (std::find(chroms.begin(), chroms.end(), chrom) == chroms.end()) {
+      if (chroms.size() == 64) { diag("Number of constrained chroms would be more than max (64) allowed for '%s' at line %d in '%s'", f[0].c_str(), line_no, path.c_str()); return -1; }
+      chroms.push_back(chrom);
+    }
+    out.push_back({chrom, (uint32_t)start, (uint32_t)stop, mask});
+  }
+  std::sort(out.begin(), out.end(), [](const LociConstraint& a, const LociConstraint& b) {
+    return a.chrom != b.chrom ? a.chrom < b.chrom : a.start != b.start ? a.start < b.start : a.end < b.end;
+  });
+  diag("Completed loading %d loci base constraints for %d target sequences from CSV file '%s'", (int)out.size(), (int)chroms.size(), path.c_str());
+  return (int)out.size();
+}
+
 int main(int argc, char** argv) {
   Opts o;
   int pr = parse(argc, argv, o);
@@ -814,6 +893,11 @@ int main(int argc, char** argv) {
   if (bkx_default_params(idx[0], o.pmode, &P) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
   P.max_subs = o.max_subs; P.min_edit_dist = o.edit_delta; P.max_ns = o.max_ns; P.align_strand = o.strand;
   P.ml_mode = o.ml_mode; P.max_ml_matches = o.max_ml; P.clamp_max_ml = o.clamp_ml ? 1 : 0;
+
+  std::vector<bkx_entry> ents(info.num_entries + 1);
+  for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
+  std::vector<LociConstraint> constraints;
+  if (!o.constraints_file.empty() && load_constraints(o.constraints_file, ents, constraints) < 0) return 1;
 
   reads_thread.join();
   if (reads_rc < 0) return 1;
@@ -969,6 +1053,67 @@ int main(int argc, char** argv) {
     diag("Paired end association and partner alignment processing completed..");
   }
 
+  unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  // host copy of the chromosomes (1 byte/base) for the passes and writers that compare with / print the target sequence
+  std::vector<std::vector<uint8_t>> genome(info.num_entries + 1);
+  bool need_genome = o.fmt == 1 || o.fmt == 3 || o.min_flank > 0;
+  for (auto& c : constraints) need_genome = need_genome || (c.mask & 0x10);
+  if (need_genome)
+    for (uint32_t e = 1; e <= info.num_entries; ++e) {
+      genome[e].resize(ents[e].seq_len);
+      if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+    }
+
+  // ---- -5: IdentifyConstraintViolations / AcceptLociConstraints / AcceptBaseConstraint, Aligner.cpp:2480-2647.  An accepted
+  //      alignment becomes eNARLociConstrained when, at some constrained locus it covers, the read's base (as aligned:
+  //      complemented on '-') is none of the bases that constraint allows; in paired-end runs the mate goes with it.
+  if (!constraints.empty()) {
+    diag("Identifying %s loci base constraint violations ...", o.pe_mode ? "PE" : "SE");
+    std::vector<std::pair<size_t, size_t>> span(info.num_entries + 2, {0, 0});   // constraints of a chromosome: [first, last)
+    for (size_t k = 0; k < constraints.size(); ++k) {
+      auto& sp = span[constraints[k].chrom];
+      if (sp.second == 0) sp.first = k;
+      sp.second = k + 1;
+    }
+    auto violates = [&](const bkx_read_result& r, uint32_t ri) -> bool {
+      const auto sp = span[r.chrom_id];
+      if (sp.second == 0) return false;
+      const uint8_t* b = R.bases.data() + R.offs[ri];
+      const uint32_t L = r.match_len, lo = r.match_loci, hi = r.match_loci + L - 1;
+      for (size_t k = sp.first; k < sp.second; ++k) {
+        const LociConstraint& c = constraints[k];
+        if (c.end < lo || c.start > hi) continue;
+        for (uint32_t l = std::max(lo, c.start); l <= std::min(hi, c.end); ++l) {
+          uint8_t base = r.strand == '-' ? b[L - 1 - (l - lo)] & 7 : b[l - lo] & 7;
+          if (r.strand == '-' && base < 4) base = 3 - base;
+          if ((c.mask & 0x10) && (genome[r.chrom_id][l] & 0x0f) == base) continue;
+          if (base < 4 && (c.mask & (1u << base))) continue;
+          return true;
+        }
+      }
+      return false;
+    };
+    std::vector<uint8_t> bad(nrec, 0);
+    {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < fmt_threads; ++t)
+        th.emplace_back([&, t]() {
+          const uint32_t b0 = (uint32_t)((uint64_t)nrec * t / fmt_threads), e0 = (uint32_t)((uint64_t)nrec * (t + 1) / fmt_threads);
+          for (uint32_t i = b0; i < e0; ++i) bad[i] = res[i].nar == BKX_NAR_ACCEPTED && violates(res[i], rix(i));
+        });
+      for (auto& x : th) x.join();
+    }
+    int identified = 0;
+    auto mark = [&](uint32_t i) {
+      if (res[i].nar == BKX_NAR_LOCICONSTRAINED) return;
+      res[i].nar = BKX_NAR_LOCICONSTRAINED; res[i].num_hits = 0; res[i].low_hit_instances = 0;
+      ++identified;
+    };
+    for (uint32_t i = 0; i < nrec; ++i)
+      if (bad[i]) { mark(i); if (o.pe_mode) mark(i ^ 1u); }
+    diag("Identified %d %s loci base constraint violations", identified, o.pe_mode ? "PE" : "SE");
+  }
+
   // ---- -k: ReducePCRduplicates, Aligner.cpp:2184-2282 (single-end runs only, :599).  In hit order, alignments that
   //      share chromosome, start, strand and length with an earlier one are dropped as eNARPCRdup once the allowance
   //      is used up; with a window the allowance grows with the number of distinct start loci within WinLen either
@@ -1036,16 +1181,6 @@ int main(int argc, char** argv) {
     diag("PCR differential amplification artefacts processing completed");
   }
 
-  std::vector<bkx_entry> ents(info.num_entries + 1);
-  for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
-  unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  // host copy of the chromosomes (1 byte/base) for the passes and writers that compare with / print the target sequence
-  std::vector<std::vector<uint8_t>> genome(info.num_entries + 1);
-  if (o.fmt == 1 || o.fmt == 3 || o.min_flank > 0)
-    for (uint32_t e = 1; e <= info.num_entries; ++e) {
-      genome[e].resize(ents[e].seq_len);
-      if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
-    }
 
   // ---- -x: AutoTrimFlanks, Aligner.cpp:1608-1812 (single-end form).  Each accepted alignment is cut back from both
   //      ends to the first run of MinFlankExacts matching bases; the rest must keep at least half the read (>= 15 bp)

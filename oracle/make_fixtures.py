@@ -411,10 +411,36 @@ def case_dups():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_constraints():
+    """Loci base constraints -5 on the tiny index: single-end and paired-end runs (the mate of a violating read goes with it)."""
+    d = os.path.join(GOLD, "constraints")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("tiny.sfx", "r100.fa", "pe1.fa", "pe2.fa"):
+            with gzip.open(os.path.join(tiny, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        rows = ['"Chrom","Start","End","Bases"', '"chr1",1000,1010,R', "chr1,5000,5000,AC", 'chr2,3000,3200,"R"', "chr2,7000,7003,ACGT",
+                "chr3,100,4000,R", "CHR1,12000,12100,RA", "chr1,15000,15050, g t", "chr2,9000,9400,R", "chr2,9100,9150,CG"]
+        open(os.path.join(tmp, "cons.csv"), "w").write("\n".join(rows) + "\n")
+        shutil.copyfile(os.path.join(tmp, "cons.csv"), os.path.join(d, "cons.csv"))
+        meta = {}
+        for tag, reads, args, out in (("c5", ["r100.fa"], ["-s3", "-M0", "-5cons.csv"], "c5.csv"),
+                                      ("c5sam", ["r100.fa"], ["-s3", "-M6", "-5cons.csv"], "c5.sam"),
+                                      ("c5k", ["r100.fa"], ["-s5", "-M0", "-5cons.csv", "-k0", "-x4"], "c5k.csv"),
+                                      ("c5pe", ["pe1.fa", "pe2.fa"], ["-s3", "-M0", "-U2", "-5cons.csv"], "c5pe.csv"),
+                                      ("c5pesam", ["pe1.fa", "pe2.fa"], ["-s3", "-M6", "-U1", "-D600", "-5cons.csv"], "c5pe.sam")):
+            run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [r + ".gz" for r in reads]}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -427,4 +453,6 @@ if __name__ == "__main__":
         case_post()
     if "dups" in which:
         case_dups()
+    if "constraints" in which:
+        case_constraints()
     print("fixtures written under", GOLD)

@@ -56,6 +56,11 @@ def test_host_pcr_artefact_reduction_matches_reference(tag, cli, golden_dir, tmp
     g.test_cli_pcr_artefact_reduction_matches_reference(tag, golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", ["c5", "c5sam", "c5k", "c5pe", "c5pesam"])
+def test_host_loci_base_constraints_match_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
