@@ -112,6 +112,7 @@ struct Opts {
   int ml_mode = 0, max_ml = 0;   // -r / -R (kanga.cpp:482-486, 667-696); max_ml 0 = not given
   bool clamp_ml = false;         // -X
   bool pair_strand = false, pe_circ = false;
+  int sample_nth = 1;            // -#: sample every Nth raw read or read pair
   int pcr_win = -1;              // -k: PCR artefact reduction window, -1 = off (kanga.cpp:719-724)
   int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
   std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
@@ -310,6 +311,7 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
     };
     for (size_t i = 0; i < nrec; ++i) {
       if (pe && i >= recs[1].size()) { diag("Problem parsing sequence after %u reads parsed", accepted); return -1; }
+      if (o.sample_nth > 1 && i % (size_t)o.sample_nth) continue;   // -#: every Nth raw read / pair of a file, from its first (Aligner.cpp:10943, 11027-11033)
       if (bad_len(recs[0][i].len, under, over)) continue;
       if (pe && bad_len(recs[1][i].len, under, over)) continue;
       keep[i] = 1;
@@ -439,7 +441,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'o': o.out = v; break;
       case 't': o.title = v; break;
       case 'g': o.qmode = iv; break;
-      case '#': if (iv != 1) unsupported.push_back("-# read sampling"); break;
+      case '#': o.sample_nth = std::min(10000, std::max(1, iv)); break;   // clamped like kanga.cpp:459-464
       case 'r': o.ml_mode = iv; if (iv == 2) unsupported.push_back("-r2 (random locus: libc rand() in the reference, not reproducible)"); break;
       case 'R': o.max_ml = iv; break;  // only meaningful with -r
       case 'c': if (iv) unsupported.push_back("-c chimeric trimming"); break;

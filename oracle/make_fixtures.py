@@ -437,10 +437,29 @@ def case_constraints():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_sample():
+    """Read sampling -# on the tiny index: every Nth raw read (single-end) / read pair (paired-end) of a file."""
+    d = os.path.join(GOLD, "sample")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("tiny.sfx", "r100.fa", "pe1.fa", "pe2.fa"):
+            with gzip.open(os.path.join(tiny, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        meta = {}
+        for tag, reads, args, out in (("s7", ["r100.fa"], ["-s3", "-M0", "-#7"], "s7.csv"),
+                                      ("s3pe", ["pe1.fa", "pe2.fa"], ["-s3", "-M6", "-U1", "-D600", "-#3"], "s3pe.sam")):
+            run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [r + ".gz" for r in reads]}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -455,4 +474,6 @@ if __name__ == "__main__":
         case_dups()
     if "constraints" in which:
         case_constraints()
+    if "sample" in which:
+        case_sample()
     print("fixtures written under", GOLD)

@@ -174,10 +174,10 @@ def test_cli_pcr_artefact_reduction_matches_reference(tag, golden_dir, tmp_path)
 
 
 @pytest.mark.parametrize("tag", ["c5", "c5sam", "c5k", "c5pe", "c5pesam"])
-def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path):
+def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="constraints"):
     """-5 (LoadLociConstraints + IdentifyConstraintViolations): single-end, with -k / -x behind it, and paired-end runs."""
     import json
-    fdir = os.path.join(gu.GOLD, "constraints")
+    fdir = os.path.join(gu.GOLD, case)
     run = json.load(open(os.path.join(fdir, "runs.json")))[tag]
     sfx = gu.sfx_path("tiny", golden_dir)
     files = [os.path.join(gu.GOLD, "tiny", f) for f in run["reads"]]
@@ -194,6 +194,12 @@ def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path):
     exp_log = [x for x in open(os.path.join(fdir, tag + ".log")).read().splitlines()
                if not x.startswith(("Sorting alignments", "Header written", "Reported SAM", "Completed reporting SAM"))]
     assert summary_block(tmp_path / "o.log") == exp_log
+
+
+@pytest.mark.parametrize("tag", ["s7", "s3pe"])
+def test_cli_read_sampling_matches_reference(tag, golden_dir, tmp_path):
+    """-# (every Nth raw read / read pair of each file, taken before the length filter)."""
+    test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="sample")
 
 
 def _bgzf_blocks(raw):
