@@ -117,6 +117,7 @@ struct Opts {
   int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
   std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
   std::string constraints_file;          // -5: loci base constraints CSV (chrom, start, end, bases)
+  std::string stats_file;                // -O: substitution / quality / multi-hit / insert-length distributions (CSV)
   std::string none_file, multi_file;     // -j / -J: FASTA of the reads without a locus / with too many loci
   std::vector<std::string> in, pair;
   std::string sfx, out, logfile, title;
@@ -460,7 +461,8 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'N': unsupported.push_back("-N best matches"); break;
       case 'X': o.clamp_ml = true; break;
       case '5': o.constraints_file = v; break;
-      case 'B': case 'H': case 'O': case 'S': case '7': case '8':
+      case 'O': o.stats_file = v; break;
+      case 'B': case 'H': case 'S': case '7': case '8':
       case 'q': unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'h':
         printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -M0..6 -g -t -U -d -D -E "
@@ -486,6 +488,7 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
   if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
   if (o.min_flank < 0 || o.min_flank > 7) { fprintf(stderr, "Error: Max flank trimming '-x%d' specified outside of range 0..7\n", o.min_flank); return -1; }  // kanga.cpp:804-808
+  if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
   if (o.pe_mode && (o.min_flank || !o.excl.empty() || !o.incl.empty())) {
     // paired ends: the filters act inside the pairing (AcceptThisChromID, Aligner.cpp:2651) and the trimming keeps a
@@ -876,6 +879,9 @@ int main(int argc, char** argv) {
     if (!compile(o.incl, rin, "include") || !compile(o.excl, rex, "exclude")) return 1;
   }
 
+  FILE* stats_fp = nullptr;   // created up front like every result file (CreateOrTruncResultFiles, Aligner.cpp:4351)
+  if (!o.stats_file.empty() && !(stats_fp = fopen(o.stats_file.c_str(), "wb"))) { diag("Fatal: unable to create '%s'", o.stats_file.c_str()); return 1; }
+
   // ---- reads load on their own thread while the index streams to the GPU (the reference also loads in the background)
   Reads R;
   int reads_rc = 0;
@@ -923,6 +929,10 @@ int main(int argc, char** argv) {
   memset(&PE, 0, sizeof(PE));
   PE.pe_proc = o.pe_mode; PE.pair_min_len = o.pair_min; PE.pair_max_len = o.pair_max; PE.pair_strand = o.pair_strand;
   PE.circularised = o.pe_circ;
+  // -O with paired ends: the insert-size histogram m_pLenDist[0..100000] (Aligner.cpp:2908-2915), one per GPU, summed below
+  const size_t kLenDist = 100001;
+  std::vector<std::vector<uint32_t>> len_dist((size_t)o.gpus);
+  if (o.pe_mode && !o.stats_file.empty()) for (auto& v : len_dist) v.assign(kLenDist, 0);
   std::vector<bkx_pe_stats> pst((size_t)o.gpus);
   for (auto& q : pst) memset(&q, 0, sizeof(q));
   std::vector<bkx_align_stats> st((size_t)o.gpus);
@@ -938,7 +948,8 @@ int main(int argc, char** argv) {
         if (e > b) {
           if (o.pe_mode)
             rcs[(size_t)g] = bkx_align_pairs_packed4(idx[(size_t)g], &P, &PE, R.packed.data(), R.offs.data() + b, (e - b) / 2,
-                                                     res.data() + b, &st[(size_t)g], &pst[(size_t)g], nullptr);
+                                                     res.data() + b, &st[(size_t)g], &pst[(size_t)g],
+                                                     len_dist[(size_t)g].empty() ? nullptr : len_dist[(size_t)g].data());
           else if (all_loci || clustered)
             rcs[(size_t)g] = bkx_align_reads_multi(idx[(size_t)g], &P, R.bases.data(), R.offs.data() + b, e - b, res.data() + b,
                                                    multi.data() + (size_t)b * (size_t)o.max_ml, &st[(size_t)g]);
@@ -961,6 +972,14 @@ int main(int argc, char** argv) {
   }
   bkx_unpin_host(R.packed.data()); bkx_unpin_host(R.offs.data()); bkx_unpin_host(res.data());
   diag("Alignment of %u from %u loaded completed", n, n);
+
+  // -O: m_MultiHitDist (Aligner.cpp:9364, 9521) -- reads whose search ended eHRhits, by their number of equally good loci;
+  //     taken now, before clustering / filters rewrite the records (not counted under -r5, :9336-9352)
+  std::vector<uint32_t> multi_dist((size_t)std::max(1, o.max_ml), 0);
+  if (!o.stats_file.empty() && o.ml_mode != BKX_ML_DEFAULT && o.ml_mode != BKX_ML_ALL)
+    for (uint32_t i = 0; i < n; ++i)
+      if (res[i].hit_rslt == BKX_HR_HITS && res[i].low_hit_instances >= 1 && res[i].low_hit_instances <= o.max_ml)
+        ++multi_dist[(size_t)res[i].low_hit_instances - 1];
 
   // ---- read-length summary, Aligner.cpp:486-535
   uint64_t tot_len = R.bases.size();
@@ -1052,13 +1071,20 @@ int main(int argc, char** argv) {
     diag("%d Paired End pairs have neither end uniquely aligned", (int)ps.unaligned_pairs);
     if (o.pe_mode == BKX_PE_UNIQUE_SE || o.pe_mode == BKX_PE_ORPHAN_SE)
       diag("%d Paired End reads were unable to be associated with partner read and accepted as if SE aligned", (int)ps.accepted_num_se);
+    if (stats_fp) {   // Aligner.cpp:3024-3041: "<insert length>,<pairs>" for 0..cPairMaxLen
+      std::vector<uint32_t> tot(kLenDist, 0);
+      for (auto& v : len_dist) for (size_t k = 0; k < v.size(); ++k) tot[k] += v[k];
+      std::string s;
+      for (size_t k = 0; k < kLenDist; ++k) { append_uint(s, k); s += ','; append_uint(s, tot[k]); s += '\n'; }
+      fwrite(s.data(), 1, s.size(), stats_fp);
+    }
     diag("Paired end association and partner alignment processing completed..");
   }
 
   unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   // host copy of the chromosomes (1 byte/base) for the passes and writers that compare with / print the target sequence
   std::vector<std::vector<uint8_t>> genome(info.num_entries + 1);
-  bool need_genome = o.fmt == 1 || o.fmt == 3 || o.min_flank > 0;
+  bool need_genome = o.fmt == 1 || o.fmt == 3 || o.min_flank > 0 || stats_fp;
   for (auto& c : constraints) need_genome = need_genome || (c.mask & 0x10);
   if (need_genome)
     for (uint32_t e = 1; e <= info.num_entries; ++e) {
@@ -1605,6 +1631,67 @@ int main(int argc, char** argv) {
   }
   ob.close();
   diag("Reporting of aligned result set completed");
+
+  // ---- -O: WriteSubDist per reported alignment (Aligner.cpp:6275-6331), then WriteBasicCountStats (:4191-4332) and
+  //      ReportTargHitCnts (:5475-5537): per read offset the bases seen and the aligner induced substitutions by Phred
+  //      band of the 4-bit quality, the number of substitutions per alignment, alignments per target sequence.
+  if (stats_fp) {
+    uint32_t max_len = 0;
+    uint64_t n_acc = 0;
+    for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) { ++n_acc; max_len = std::max<uint32_t>(max_len, (uint32_t)R.len(rix(i))); }
+    if (n_acc && max_len) {
+      diag("Writing out basic count stats to file");
+      std::vector<uint32_t> qinst(4 * (size_t)max_len, 0), qsubs(4 * (size_t)max_len, 0), msub((size_t)max_len + 1, 0), per_chrom(info.num_entries + 1, 0);
+      for (uint32_t i = 0; i < nrec; ++i) {
+        const bkx_read_result& r = res[i];
+        if (r.nar != BKX_NAR_ACCEPTED || r.chrom_id == 0) continue;
+        ++per_chrom[r.chrom_id];
+        const uint32_t ri = rix(i), L = (uint32_t)R.len(ri), start = adj_start(i), alen = adj_len(i);
+        const uint8_t* b = R.bases.data() + R.offs[ri];
+        const uint8_t* g = genome[r.chrom_id].data() + start;
+        uint32_t subs = 0;
+        for (uint32_t q = tleft(i), k = 0; q < L - tright(i); ++q, ++k) {
+          const unsigned q4 = (b[q] >> 4) & 0x0f, band = q4 <= 3 ? 0 : q4 <= 7 ? 1 : q4 <= 11 ? 2 : 3;
+          uint8_t t = r.strand == '-' ? g[alen - 1 - k] & 7 : g[k] & 7;
+          if (r.strand == '-' && t < 4) t = 3 - t;
+          ++qinst[band * (size_t)max_len + q];
+          if ((b[q] & 7) != t) { ++qsubs[band * (size_t)max_len + q]; ++subs; }
+        }
+        ++msub[std::min<uint32_t>(subs, max_len)];
+      }
+      std::string s;
+      auto row = [&](const char* label, auto&& value, uint32_t cnt) {
+        s += label;
+        for (uint32_t k = 0; k < cnt; ++k) { s += ','; append_uint(s, value(k)); }
+      };
+      if (o.ml_mode != BKX_ML_DEFAULT) {
+        row("\"Multihit distribution\",", [](uint32_t k) { return (uint64_t)k + 1; }, (uint32_t)o.max_ml);
+        row("\n,\"Instances\"", [&](uint32_t k) { return (uint64_t)multi_dist[k]; }, (uint32_t)o.max_ml);
+        s += '\n';
+      }
+      static const char* kInstBand[4] = {"\n,\"Phred 0..9\"", "\n,\"Phred 10..19\"", "\n,\"Phred 20..29\"", "\n,\"Phred 30+\""};
+      static const char* kSubsBand[4] = {"\n,\"Phred 0..8\"", "\n,\"Phred 9..19\"", "\n,\"Phred 20..29\"", "\n,\"Phred 30+\""};
+      row("\"Phred Score Instances\",", [](uint32_t k) { return (uint64_t)k + 1; }, max_len);
+      for (int band = 0; band < 4; ++band) row(kInstBand[band], [&](uint32_t k) { return (uint64_t)qinst[band * (size_t)max_len + k]; }, max_len);
+      row("\n\n\"Aligner Induced Subs\",", [](uint32_t k) { return (uint64_t)k + 1; }, max_len);
+      for (int band = 0; band < 4; ++band) row(kSubsBand[band], [&](uint32_t k) { return (uint64_t)qsubs[band * (size_t)max_len + k]; }, max_len);
+      row("\n\n\"Multiple substitutions\",", [](uint32_t k) { return (uint64_t)k; }, max_len);
+      row("\n,\"Instances\"", [&](uint32_t k) { return (uint64_t)msub[k]; }, max_len);
+      s += '\n';
+      diag("Reporting accepted read alignment counts on to targeted transcripts or sequences, sorting reads");
+      diag("Completed sort");
+      s += "\"TargSeq\",\"TargLen\",\"NumHits\"\n";
+      int n_targ = 0;
+      for (uint32_t e = 1; e <= info.num_entries; ++e)
+        if (per_chrom[e]) {
+          s += '"'; s += ents[e].name; s += "\","; append_uint(s, ents[e].seq_len); s += ','; append_uint(s, per_chrom[e]); s += '\n';
+          ++n_targ;
+        }
+      fwrite(s.data(), 1, s.size(), stats_fp);
+      diag("Completed reporting read alignment counts on to %d targeted transcripts or sequences", n_targ);
+    }
+    fclose(stats_fp);
+  }
   for (auto* x : idx) bkx_close_index(x);
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   int hh = (int)(secs / 3600), mm = (int)(secs / 60) % 60;

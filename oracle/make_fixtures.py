@@ -456,10 +456,32 @@ def case_sample():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_stats():
+    """Statistics file -O on the tiny index: quality-band / substitution / multi-hit distributions and hits per target
+    (single-end, FASTQ qualities kept with -g0, also behind -x trimming), insert-length histogram first in paired-end runs."""
+    d = os.path.join(GOLD, "stats")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("tiny.sfx", "pe1.fa", "pe2.fa", "mixed.fq"):
+            with gzip.open(os.path.join(tiny, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        meta = {}
+        for tag, reads, args, out in (("o1", ["mixed.fq"], ["-s3", "-n2", "-M0", "-g0", "-r1", "-R4", "-Ost.csv"], "o1.csv"),
+                                      ("o2", ["mixed.fq"], ["-s5", "-n2", "-M5", "-g1", "-x4", "-Zchr3", "-Ost.csv"], "o2.sam"),
+                                      ("o3pe", ["pe1.fa", "pe2.fa"], ["-s3", "-M0", "-U1", "-D600", "-Ost.csv"], "o3pe.csv")):
+            run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            gz(os.path.join(tmp, "st.csv"), os.path.join(d, tag + ".st.csv.gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [r + ".gz" for r in reads]}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -476,4 +498,6 @@ if __name__ == "__main__":
         case_constraints()
     if "sample" in which:
         case_sample()
+    if "stats" in which:
+        case_stats()
     print("fixtures written under", GOLD)

@@ -84,6 +84,8 @@ def test_cli_rejects_unsupported_and_bad_options(tmp_path, golden_dir):
     assert r.returncode != 0 and "0..7" in r.stderr
     r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-Zchr[1"], capture_output=True, text=True)
     assert r.returncode != 0     # malformed expression: refused like the reference's regcomp failure
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", rd, "-o", str(tmp_path / "x"), "-M6", "-O", str(tmp_path / "st")], capture_output=True, text=True)
+    assert r.returncode != 0 and "not available in '-M6'" in r.stderr
     for k, body in enumerate(("chrX,1,2,A\n", "chr1,5,2,A\n", "chr1,1,2,Q\n", "chr1,1,99999999,A\n", "chr1,1,2\n")):
         cf = tmp_path / ("bad%d.csv" % k)     # unknown chromosome / start > end / bad base letter / end beyond the sequence / too few fields
         cf.write_text(body)
@@ -200,6 +202,14 @@ def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, ca
 def test_cli_read_sampling_matches_reference(tag, golden_dir, tmp_path):
     """-# (every Nth raw read / read pair of each file, taken before the length filter)."""
     test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="sample")
+
+
+@pytest.mark.parametrize("tag", ["o1", "o2", "o3pe"])
+def test_cli_statistics_file_matches_reference(tag, golden_dir, tmp_path):
+    """-O: the statistics CSV (insert-length histogram in paired-end runs, multi-hit distribution, bases and aligner induced
+    substitutions per read offset and Phred band, substitutions per alignment, hits per target) is the reference's file."""
+    test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="stats")
+    assert _lines(tmp_path / "st.csv") == _lines(os.path.join(gu.GOLD, "stats", tag + ".st.csv.gz"))
 
 
 def _bgzf_blocks(raw):

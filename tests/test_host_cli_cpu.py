@@ -66,6 +66,11 @@ def test_host_read_sampling_matches_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_read_sampling_matches_reference(tag, golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", ["o1", "o2", "o3pe"])
+def test_host_statistics_file_matches_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_statistics_file_matches_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
