@@ -490,10 +490,10 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.min_flank < 0 || o.min_flank > 7) { fprintf(stderr, "Error: Max flank trimming '-x%d' specified outside of range 0..7\n", o.min_flank); return -1; }  // kanga.cpp:804-808
   if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
-  if (o.pe_mode && (o.min_flank || !o.excl.empty() || !o.incl.empty())) {
-    // paired ends: the filters act inside the pairing (AcceptThisChromID, Aligner.cpp:2651) and the trimming keeps a
-    // central core (AutoTrimFlanks, :1700-1745); the pairing kernels do neither
-    fprintf(stderr, "bkx-align: options -x / -Z / -z are not supported together with paired end processing '-U%d'\n", o.pe_mode);
+  if (o.pe_mode && (!o.excl.empty() || !o.incl.empty())) {
+    // paired ends: the chromosome filters act inside the pairing (AcceptThisChromID in AcceptProvPE, Aligner.cpp:2651, 2775);
+    // the pairing kernel does not take them
+    fprintf(stderr, "bkx-align: options -Z / -z are not supported together with paired end processing '-U%d'\n", o.pe_mode);
     return -1;
   }
   if (o.gpus < 1) o.gpus = 1;
@@ -1210,9 +1210,11 @@ int main(int argc, char** argv) {
   }
 
 
-  // ---- -x: AutoTrimFlanks, Aligner.cpp:1608-1812 (single-end form).  Each accepted alignment is cut back from both
-  //      ends to the first run of MinFlankExacts matching bases; the rest must keep at least half the read (>= 15 bp)
-  //      or the read is sloughed as eNARTrim.  TrimLeft / TrimRight are in READ orientation (Aligner.cpp:1528-1549).
+  // ---- -x: AutoTrimFlanks, Aligner.cpp:1608-1812.  Each accepted alignment is cut back from both ends to the first run
+  //      of MinFlankExacts matching bases; the rest must keep at least half the read (>= 15 bp) or the read is sloughed
+  //      as eNARTrim.  In paired-end runs the 5' scan stays inside the first third of the read and the 3' scan inside
+  //      the last third, and nothing is sloughed (the pairing stands).  TrimLeft / TrimRight are in READ orientation
+  //      (Aligner.cpp:1528-1549).
   std::vector<uint16_t> trim_l, trim_r;
   std::vector<uint8_t> trim_mm;   // Seg[0].TrimMismatches: mismatches left inside the trimmed alignment
   uint32_t elim_plus = 0, elim_minus = 0, num_trimmed = 0;
@@ -1238,19 +1240,20 @@ int main(int argc, char** argv) {
           if (r.strand == '-') for (int q = 0; q < L; ++q) { uint8_t c = g[L - 1 - q] & 7; tg[q] = c < 4 ? 3 - c : c; }
           else for (int q = 0; q < L; ++q) tg[q] = g[q] & 7;
           auto slough = [&]() { r.num_hits = 0; r.nar = BKX_NAR_TRIM; ++(r.strand == '+' ? ep[t] : em[t]); };
+          const bool pe = o.pe_mode != 0;
           int exact = 0, tmm = 0, k;
-          for (k = 0; k <= L - minlen && k < L; ++k) {       // 5' -> 3'
+          for (k = 0; k <= L - minlen && k < (pe ? L / 3 : L); ++k) {       // 5' -> 3'
             if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
             if (++exact == X) break;
           }
-          if (k + minlen > L || exact < X) { slough(); continue; }
+          if (!pe && (k + minlen > L || exact < X)) { slough(); continue; }
           const int left = k - (X - 1);
           exact = 0;
-          for (k = L - 1; k >= left + minlen && k > 0; --k) {  // 3' -> 5'
+          for (k = L - 1; k >= left + minlen && k > (pe ? (L * 2) / 3 : 0); --k) {  // 3' -> 5'
             if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
             if (++exact == X) break;
           }
-          if (exact != X || k < left + minlen) { slough(); continue; }
+          if (!pe && (exact != X || k < left + minlen)) { slough(); continue; }
           const int right = k + X;
           trim_l[i] = (uint16_t)left; trim_r[i] = (uint16_t)(L - right);
           if (left || L - right) trim_mm[i] = (uint8_t)(r.mismatches - tmm);
@@ -1492,9 +1495,10 @@ int main(int argc, char** argv) {
         if (both) {
           flags |= m.strand == '+' ? 0 : 0x20;
           if (acc) {
-            long se = r.match_loci, pes = m.match_loci;
-            tlen = se <= pes ? (int)(pes - se) + m.match_len : (int)(se - pes) + r.match_len;
-            pnext = m.match_loci;
+            const uint32_t mi2 = pe2 ? i - 1 : i + 1;   // both alignments as trimmed by -x, if at all
+            long se = adj_start(i), pes = adj_start(mi2);
+            tlen = se <= pes ? (int)(pes - se) + (int)adj_len(mi2) : (int)(se - pes) + (int)adj_len(i);
+            pnext = pes;
           }
         } else flags |= 0x08;
       }
@@ -1548,8 +1552,16 @@ int main(int argc, char** argv) {
     for (size_t mi = meta.size(); mi-- > 0;)
       if (meta[mi].acc) { flush_at = meta[mi].uofs + meta[mi].len; have_flush = true; break; }
     bool ok = bz.write_stream(U.data(), U.size(), have_flush ? &flush_at : nullptr, fmt_threads);
+    // BAI bins end at 512 Mbp.  For longer reference sequences the reference switches to a CSI index (SAMfile.cpp:1602-1622)
+    // but never opens that file -- the branch that would (:1664) hangs off `if (type >= BAI)` and is unreachable -- so its
+    // first index flush fails (WriteIdxToDisk, :1812).  Here the BAM is written complete and the index is left to
+    // `samtools index -c`, with a note in the log, rather than an index with overflowing bins.
+    uint32_t longest_ref = 0;
+    for (uint32_t e = 1; e <= info.num_entries; ++e) if (refid[e] >= 0) longest_ref = std::max(longest_ref, ents[e].seq_len);
+    const bool write_bai = longest_ref < 0x20000000u;
+    if (!write_bai) diag("Note: reference sequences of 512Mbp or more (max %u): no BAI index written for '%s', index it with a CSI indexer", longest_ref, o.out.c_str());
     int cur_ref = -1;  // reference whose index block is being accumulated
-    for (size_t mi = 0; mi < meta.size() && ok; ++mi) {
+    for (size_t mi = 0; mi < meta.size() && ok && write_bai; ++mi) {
       const RecMeta& M = meta[mi];
       if (!M.acc) continue;
       while (cur_ref < M.rid) { if (cur_ref >= 0) bai.end_ref(); ++cur_ref; }
@@ -1557,8 +1569,10 @@ int main(int argc, char** argv) {
     }
     bai.end_ref();  // Close(): the reference in progress (an empty block when nothing aligned)
     ok = ok && bz.close();
-    FILE* fb = fopen((o.out + ".bai").c_str(), "wb");
-    if (fb) { fwrite(bai.out.data(), 1, bai.out.size(), fb); fclose(fb); } else ok = false;
+    if (write_bai) {
+      FILE* fb = fopen((o.out + ".bai").c_str(), "wb");
+      if (fb) { fwrite(bai.out.data(), 1, bai.out.size(), fb); fclose(fb); } else ok = false;
+    }
     if (!ok) { diag("Fatal: write to '%s' failed", o.out.c_str()); return 1; }
   } else {
     // SAM header: @HD, @SQ for every chromosome (or only those hit if more than -4 threshold), @PG
@@ -1590,9 +1604,10 @@ int main(int argc, char** argv) {
         if (both) {
           flags |= m.strand == '+' ? 0 : 0x20;
           if (acc) {
-            long se = r.match_loci, pes = m.match_loci;
-            tlen = se <= pes ? (int)(pes - se) + m.match_len : (int)(se - pes) + r.match_len;
-            pnext = m.match_loci;
+            const uint32_t mi2 = pe2 ? i - 1 : i + 1;   // both alignments as trimmed by -x, if at all
+            long se = adj_start(i), pes = adj_start(mi2);
+            tlen = se <= pes ? (int)(pes - se) + (int)adj_len(mi2) : (int)(se - pes) + (int)adj_len(i);
+            pnext = pes;
           }
         } else flags |= 0x08;
       }

@@ -76,7 +76,7 @@ def test_cli_rejects_unsupported_and_bad_options(tmp_path, golden_dir):
     r = subprocess.run([CLI, "align", "-I", "/nonexistent.sfx", "-i", rd, "-o", str(tmp_path / "x")], capture_output=True, text=True)
     assert r.returncode != 0
     pe = ["-u", os.path.join(gu.GOLD, "tiny", "pe2.fa.gz"), "-U2"]   # the pairing kernels neither filter nor trim
-    for extra in (["-x5"], ["-Zchr1"], ["-zchr1"]):
+    for extra in (["-Zchr1"], ["-zchr1"]):
         r = subprocess.run([CLI, "align", "-I", sfx, "-i", os.path.join(gu.GOLD, "tiny", "pe1.fa.gz"), "-o", str(tmp_path / "x")] + pe + extra,
                            capture_output=True, text=True)
         assert r.returncode != 0 and "not supported together with paired end" in r.stderr
@@ -198,9 +198,10 @@ def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, ca
     assert summary_block(tmp_path / "o.log") == exp_log
 
 
-@pytest.mark.parametrize("tag", ["s7", "s3pe"])
+@pytest.mark.parametrize("tag", ["s7", "s3pe", "pex0", "pex6"])
 def test_cli_read_sampling_matches_reference(tag, golden_dir, tmp_path):
-    """-# (every Nth raw read / read pair of each file, taken before the length filter)."""
+    """-# (every Nth raw read / read pair of each file, taken before the length filter); pex*: -x in paired-end runs
+    (trimmed POS / CIGAR / PNEXT / TLEN, nothing sloughed)."""
     test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="sample")
 
 
