@@ -502,6 +502,12 @@ static int parse(int argc, char** argv, Opts& o) {
     if (o.max_ml == 0) o.max_ml = 5;  // cDfltMaxMultiHits
     const int lim = o.ml_mode >= 3 ? 64 : 500;  // the reference takes 500 (100000 with -r5); the per-read slots here hold 64
     if (o.max_ml < 2 || o.max_ml > lim) { fprintf(stderr, "Error: multiple aligned reads '-R%d' specified outside of range 2..%d\n", o.max_ml, lim); return -1; }
+    if (o.ml_mode == 5) { o.none_file.clear(); o.multi_file.clear(); }   // kanga.cpp:1045-1069: -j / -J are dropped under -r5
+    if (o.ml_mode == 5 && o.fmt == 6 && (!o.excl.empty() || !o.incl.empty())) {
+      // the reference then turns reads whose loci were all filtered into accepted records without a locus (WriteHitLoci, Aligner.cpp:6755-6771)
+      fprintf(stderr, "bkx-align: options -Z / -z are not supported together with '-r5' in output format '-M6'\n");
+      return -1;
+    }
     if (o.ml_mode == 5 && !(o.fmt == 0 || o.fmt == 4 || o.fmt == 5 || o.fmt == 6)) {  // kanga.cpp:830
       fprintf(stderr, "Error: '-r5' is only reported as -M0, -M4, -M5 or -M6\n");
       return -1;
@@ -981,6 +987,34 @@ int main(int argc, char** argv) {
       if (res[i].hit_rslt == BKX_HR_HITS && res[i].low_hit_instances >= 1 && res[i].low_hit_instances <= o.max_ml)
         ++multi_dist[(size_t)res[i].low_hit_instances - 1];
 
+  // -r5 with -Z / -z: the loci of a read are filtered as they are recorded (WriteHitLoci -> AcceptThisChromID, Aligner.cpp:6737-6757,
+  // 2651-2710: exclude expressions first, then -- if any -- the include expressions), so the provisional totals count the
+  // loci that stay; reads left without a locus leave no record.
+  std::vector<char> r5_keep;
+  if (all_loci && (!rin.empty() || !rex.empty())) {
+    r5_keep.assign(info.num_entries + 1, 1);
+    for (uint32_t e = 1; e <= info.num_entries; ++e) {
+      regmatch_t mc;
+      bool ok = true;
+      for (auto& re : rex) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = false; break; }
+      if (ok && !rin.empty()) {
+        ok = false;
+        for (auto& re : rin) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = true; break; }
+      }
+      r5_keep[e] = ok;
+    }
+    S.tot_accepted_aligned = S.tot_accepted_unique = S.tot_accepted_multi = S.tot_loci_aligned = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (res[i].nar != BKX_NAR_ACCEPTED) continue;
+      int kept = 0;
+      for (int h = 0; h < res[i].num_hits; ++h) kept += r5_keep[multi[(size_t)i * (size_t)o.max_ml + (size_t)h].chrom_id];
+      if (!kept) continue;
+      ++S.tot_accepted_aligned;
+      S.tot_loci_aligned += (uint64_t)kept;
+      ++(kept == 1 ? S.tot_accepted_unique : S.tot_accepted_multi);
+    }
+  }
+
   // ---- read-length summary, Aligner.cpp:486-535
   uint64_t tot_len = R.bases.size();
   int minl = R.len(0), maxl = R.len(0);
@@ -1006,8 +1040,23 @@ int main(int argc, char** argv) {
     for (uint32_t i = 0; i < n; ++i) {
       const bkx_read_result& r = res[i];
       if (r.nar == BKX_NAR_ACCEPTED) {
-        for (int h = 0; h < r.num_hits; ++h) {
-          const bkx_multi_hit& m = multi[(size_t)i * (size_t)o.max_ml + (size_t)h];
+        // loci that pass the chromosome filter.  The reference compacts the hit list in place with a cursor that only
+        // advances when it copies (WriteHitLoci, Aligner.cpp:6744-6754: `if (pAcceptHit != pHit) *pAcceptHit++ = *pHit`):
+        // a kept FIRST locus leaves the cursor behind, the following kept loci overwrite it, and the tail of the reported
+        // list (its length is the number of kept loci) is whatever the slots held before -- a repeated or even a filtered
+        // locus, which FiltByChroms then removes as eNARChromFilt.  Reproduced by running the same compaction.
+        int kept[64], nk = 0;
+        const int nh = std::min<int>(r.num_hits, 64);
+        for (int h = 0; h < nh; ++h) kept[h] = h;
+        if (r5_keep.empty()) nk = nh;
+        else
+          for (int h = 0, cursor = 0; h < nh; ++h)
+            if (r5_keep[multi[(size_t)i * (size_t)o.max_ml + (size_t)h].chrom_id]) {
+              ++nk;
+              if (cursor != h) kept[cursor++] = h;
+            }
+        for (int k = 0; k < nk; ++k) {
+          const bkx_multi_hit& m = multi[(size_t)i * (size_t)o.max_ml + (size_t)kept[k]];
           bkx_read_result q = r;
           q.num_hits = 1;
           q.chrom_id = m.chrom_id; q.match_loci = m.match_loci; q.match_len = m.match_len; q.strand = m.strand;
@@ -1380,7 +1429,8 @@ int main(int argc, char** argv) {
   if (o.fmt == 4) {
     // UCSC BED: track line then chrom, start, end+1, "ar", score, strand (Aligner.cpp:6355-6362, 6463-6466)
     const char* title = o.title.empty() ? "kanga" : o.title.c_str();
-    ob.s += "track type=bed name=\""; ob.s += title; ob.s += "\" description=\""; ob.s += title; ob.s += "\"\n";
+    // under -r5 the reference writes the track line twice: when it creates the file and when it reports (Aligner.cpp:4405, 6358)
+    for (int rep = 0; rep < (all_loci ? 2 : 1); ++rep) { ob.s += "track type=bed name=\""; ob.s += title; ob.s += "\" description=\""; ob.s += title; ob.s += "\"\n"; }
     emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
       uint32_t i = order[k];
       const bkx_read_result& r = res[i];
@@ -1654,6 +1704,7 @@ int main(int argc, char** argv) {
     uint32_t max_len = 0;
     uint64_t n_acc = 0;
     for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) { ++n_acc; max_len = std::max<uint32_t>(max_len, (uint32_t)R.len(rix(i))); }
+    if (o.fmt == 4) max_len = 0;   // the BED branch of WriteReadHits never reaches WriteSubDist (Aligner.cpp:6448-6556): nothing beyond the histogram
     if (n_acc && max_len) {
       diag("Writing out basic count stats to file");
       std::vector<uint32_t> qinst(4 * (size_t)max_len, 0), qsubs(4 * (size_t)max_len, 0), msub((size_t)max_len + 1, 0), per_chrom(info.num_entries + 1, 0);

@@ -481,10 +481,36 @@ def case_stats():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_interplay():
+    """Option combinations found by tests/fuzz_host_cli.py, on the lowcopy index (many reads with several loci): -r5 with
+    chromosome filters (loci filtered as they are recorded, incl. the reference's compaction quirk), -r5 with BED (track line
+    twice), -j / -J dropped under -r5, -O with BED (histogram only)."""
+    d = os.path.join(GOLD, "interplay")
+    os.makedirs(d, exist_ok=True)
+    low = os.path.join(GOLD, "lowcopy")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("lowcopy.sfx", "r100.fa"):
+            with gzip.open(os.path.join(low, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        meta = {}
+        for tag, args, out in (("i1", ["-s3", "-M0", "-r5", "-R5", "-Zlc2"], "i1.csv"),
+                               ("i2", ["-s3", "-M4", "-r5", "-R5", "-jn.fa", "-Jm.fa", "-Ost.csv"], "i2.bed"),
+                               ("i3", ["-s3", "-M5", "-r5", "-R8", "-X", "-zLC[13]", "-x4"], "i3.sam"),
+                               ("i4", ["-s3", "-M0", "-r5", "-R3", "-zlc[12]", "-Zlc1", "-k0"], "i4.csv"),
+                               ("i5", ["-s3", "-M4", "-r1", "-R4", "-Ost.csv"], "i5.bed")):
+            run(["align", "-I", "lowcopy.sfx", "-i", "r100.fa", "-T1", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": ["r100.fa.gz"], "index": "lowcopy"}
+            if "-Ost.csv" in args:
+                gz(os.path.join(tmp, "st.csv"), os.path.join(d, tag + ".st.csv.gz"))
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -503,4 +529,6 @@ if __name__ == "__main__":
         case_sample()
     if "stats" in which:
         case_stats()
+    if "interplay" in which:
+        case_interplay()
     print("fixtures written under", GOLD)

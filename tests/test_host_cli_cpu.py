@@ -71,6 +71,11 @@ def test_host_statistics_file_matches_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_statistics_file_matches_reference(tag, golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", ["i1", "i2", "i3", "i4", "i5"])
+def test_host_option_interplay_matches_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_option_interplay_matches_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
