@@ -1402,6 +1402,7 @@ int main(int argc, char** argv) {
     nar[res[i].nar]++;
     if (res[i].nar == BKX_NAR_ACCEPTED && res[i].strand == '+') ++plus;
   }
+  if (nrec == 0) nar[BKX_NAR_UNALIGNED] = 1;   // with no record left (-r5, every locus filtered) the reference's walk still classes one empty slot
   uint64_t no_match = nar[BKX_NAR_NOHIT] + S.num_sloughed_ns;
   if (all_loci) {  // Aligner.cpp:3706-3708, 3727-3730: the non-aligned total of the search stands in for the record count
     no_match = S.tot_non_aligned + S.num_sloughed_ns;
