@@ -858,6 +858,247 @@ static int load_constraints(const std::string& path, const std::vector<bkx_entry
   return (int)out.size();
 }
 
+// ---- what the post-alignment passes and the writers share about a run ----------------------------------
+struct Records {
+  const Opts& o;
+  const Reads& R;
+  std::vector<bkx_read_result>& res;                 // one per record: per read, or per reported locus under -r5
+  const std::vector<uint32_t>& src;                  // record -> read (empty: identity)
+  const std::vector<bkx_entry>& ents;                // [1 .. num_entries]
+  const std::vector<std::vector<uint8_t>>& genome;   // host copy of the chromosomes (1 byte/base), filled when a pass or writer needs it
+  unsigned threads;
+  // -x: Seg[0].TrimLeft / TrimRight (in READ orientation) and TrimMismatches per record; empty unless the trimming ran
+  std::vector<uint16_t> trim_l, trim_r;
+  std::vector<uint8_t> trim_mm;
+  uint32_t elim_plus = 0, elim_minus = 0;            // alignments sloughed by the trimming, per strand
+
+  uint32_t n() const { return (uint32_t)res.size(); }
+  uint32_t rix(uint32_t i) const { return src.empty() ? i : src[i]; }
+  // the alignment as reported: AdjStartLoci / AdjHitLen / TrimMismatches (Aligner.cpp:1528-1552)
+  uint32_t tleft(uint32_t i) const { return trim_l.empty() ? 0u : trim_l[i]; }
+  uint32_t tright(uint32_t i) const { return trim_r.empty() ? 0u : trim_r[i]; }
+  uint32_t adj_start(uint32_t i) const { return res[i].match_loci + (res[i].strand == '+' ? tleft(i) : tright(i)); }
+  uint32_t adj_len(uint32_t i) const { return (uint32_t)res[i].match_len - tleft(i) - tright(i); }
+  uint32_t adj_mm(uint32_t i) const { return trim_mm.empty() ? res[i].mismatches : trim_mm[i]; }
+};
+
+// ---- -5: IdentifyConstraintViolations / AcceptLociConstraints / AcceptBaseConstraint, Aligner.cpp:2480-2647.  An accepted
+//      alignment becomes eNARLociConstrained when, at some constrained locus it covers, the read's base (as aligned:
+//      complemented on '-') is none of the bases that constraint allows; in paired-end runs the mate goes with it.
+static void identify_constraint_violations(Records& rc, const std::vector<LociConstraint>& constraints) {
+  const Opts& o = rc.o;
+  const Reads& R = rc.R;
+  auto& res = rc.res;
+  const uint32_t nrec = rc.n();
+  const auto& genome = rc.genome;
+  diag("Identifying %s loci base constraint violations ...", o.pe_mode ? "PE" : "SE");
+  std::vector<std::pair<size_t, size_t>> span(rc.ents.size() + 1, {0, 0});   // constraints of a chromosome: [first, last)
+  for (size_t k = 0; k < constraints.size(); ++k) {
+    auto& sp = span[constraints[k].chrom];
+    if (sp.second == 0) sp.first = k;
+    sp.second = k + 1;
+  }
+  auto violates = [&](const bkx_read_result& r, uint32_t ri) -> bool {
+    const auto sp = span[r.chrom_id];
+    if (sp.second == 0) return false;
+    const uint8_t* b = R.bases.data() + R.offs[ri];
+    const uint32_t L = r.match_len, lo = r.match_loci, hi = r.match_loci + L - 1;
+    for (size_t k = sp.first; k < sp.second; ++k) {
+      const LociConstraint& c = constraints[k];
+      if (c.end < lo || c.start > hi) continue;
+      for (uint32_t l = std::max(lo, c.start); l <= std::min(hi, c.end); ++l) {
+        uint8_t base = r.strand == '-' ? b[L - 1 - (l - lo)] & 7 : b[l - lo] & 7;
+        if (r.strand == '-' && base < 4) base = 3 - base;
+        if ((c.mask & 0x10) && (genome[r.chrom_id][l] & 0x0f) == base) continue;
+        if (base < 4 && (c.mask & (1u << base))) continue;
+        return true;
+      }
+    }
+    return false;
+  };
+  std::vector<uint8_t> bad(nrec, 0);
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < rc.threads; ++t)
+      th.emplace_back([&, t]() {
+        const uint32_t b0 = (uint32_t)((uint64_t)nrec * t / rc.threads), e0 = (uint32_t)((uint64_t)nrec * (t + 1) / rc.threads);
+        for (uint32_t i = b0; i < e0; ++i) bad[i] = res[i].nar == BKX_NAR_ACCEPTED && violates(res[i], rc.rix(i));
+      });
+    for (auto& x : th) x.join();
+  }
+  int identified = 0;
+  auto mark = [&](uint32_t i) {
+    if (res[i].nar == BKX_NAR_LOCICONSTRAINED) return;
+    res[i].nar = BKX_NAR_LOCICONSTRAINED; res[i].num_hits = 0; res[i].low_hit_instances = 0;
+    ++identified;
+  };
+  for (uint32_t i = 0; i < nrec; ++i)
+    if (bad[i]) { mark(i); if (o.pe_mode) mark(i ^ 1u); }
+  diag("Identified %d %s loci base constraint violations", identified, o.pe_mode ? "PE" : "SE");
+}
+
+// ---- -k: ReducePCRduplicates, Aligner.cpp:2184-2282 (single-end runs only, :599).  In hit order, alignments that
+//      share chromosome, start, strand and length with an earlier one are dropped as eNARPCRdup once the allowance
+//      is used up; with a window the allowance grows with the number of distinct start loci within WinLen either
+//      side (NumUpUniques / NumDnUniques, :9817-9914).  Which of several reads with identical sort keys survives is
+//      left open by the reference's unstable sort; here it is the one loaded first.
+static int reduce_pcr_duplicates(Records& rc) {
+  const Opts& o = rc.o;
+  auto& res = rc.res;
+  const uint32_t nrec = rc.n();
+  diag("Processing to reduce PCR differential amplification artefacts processing started..");
+  std::vector<uint32_t> ord(nrec);
+  if (nrec && bkx_sort_hits(res.data(), nrec, ord.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return -1; }
+  const int W = o.pcr_win;
+  auto acc = [&](uint32_t k) { return res[ord[k]].nar == BKX_NAR_ACCEPTED; };
+  auto dn_uniques = [&](uint32_t k) -> int {
+    const bkx_read_result& c = res[ord[k]];
+    int n_u = 0;
+    uint32_t prv = c.match_loci;
+    for (uint32_t j = k + 1; j < nrec; ++j) {
+      const bkx_read_result& x = res[ord[j]];
+      if (x.chrom_id != c.chrom_id) break;
+      if (!acc(j)) continue;
+      if ((int64_t)c.match_loci + W < (int64_t)x.match_loci) break;
+      if (x.strand != c.strand) continue;
+      if (x.match_loci != prv) { ++n_u; prv = x.match_loci; }
+    }
+    return n_u;
+  };
+  auto up_uniques = [&](uint32_t k) -> int {
+    if (k == 0) return 0;
+    const bkx_read_result& c = res[ord[k]];
+    int n_u = 0;
+    uint32_t prv = c.match_loci;
+    for (uint32_t j = k + 1; j-- > 0;) {   // starts at the current record itself, as the reference does
+      const bkx_read_result& x = res[ord[j]];
+      if (x.chrom_id != c.chrom_id) break;
+      if (!acc(j)) continue;
+      if ((int64_t)c.match_loci > W && (int64_t)c.match_loci - W > (int64_t)x.match_loci) break;
+      if (x.strand != c.strand) continue;
+      if (x.match_loci != prv) { ++n_u; prv = x.match_loci; }
+    }
+    return n_u;
+  };
+  int removed = 0;
+  for (uint32_t k = 0; k < nrec; ++k) {
+    if (!acc(k)) continue;
+    int limit = 0;
+    if (W > 0) {
+      limit = std::max(up_uniques(k), dn_uniques(k));
+      const int prop = (int)(((double)limit / W) * 100.0);
+      limit = prop < 5 ? 1 : prop <= 10 ? 2 : prop <= 20 ? 3 : prop <= 40 ? 4 : prop <= 60 ? 5 : prop <= 80 ? 10 : 50;
+    }
+    const bkx_read_result c = res[ord[k]];
+    uint32_t mark = k;
+    for (uint32_t j = k + 1; j < nrec; ++j) {
+      bkx_read_result& x = res[ord[j]];
+      if (x.nar != BKX_NAR_ACCEPTED) continue;
+      if (x.chrom_id != c.chrom_id || x.match_loci != c.match_loci || x.strand != c.strand) break;
+      if (x.match_len != c.match_len) continue;
+      if (limit > 0) { --limit; continue; }
+      x.num_hits = 0; x.low_hit_instances = 0; x.nar = BKX_NAR_PCRDUP;
+      mark = j;
+      ++removed;
+    }
+    k = mark;
+  }
+  diag("Removed %d potential PCR artefact reads", removed);
+  diag("PCR differential amplification artefacts processing completed");
+  return 0;
+}
+
+// ---- -x: AutoTrimFlanks, Aligner.cpp:1608-1812.  Each accepted alignment is cut back from both ends to the first run
+//      of MinFlankExacts matching bases; the rest must keep at least half the read (>= 15 bp) or the read is sloughed
+//      as eNARTrim.  In paired-end runs the 5' scan stays inside the first third of the read and the 3' scan inside
+//      the last third, and nothing is sloughed (the pairing stands).  TrimLeft / TrimRight are in READ orientation
+//      (Aligner.cpp:1528-1549).
+static void auto_trim_flanks(Records& rc) {
+  const Opts& o = rc.o;
+  const Reads& R = rc.R;
+  auto& res = rc.res;
+  const uint32_t nrec = rc.n();
+  const auto& genome = rc.genome;
+  auto &trim_l = rc.trim_l, &trim_r = rc.trim_r;
+  auto& trim_mm = rc.trim_mm;
+  const unsigned fmt_threads = rc.threads;
+  diag("Autotrim aligned read flank processing started..");
+  diag("Starting 5' and 3' flank sequence autotrim processing...");
+  trim_l.assign(nrec, 0); trim_r.assign(nrec, 0); trim_mm.assign(nrec, 0);
+  std::vector<uint32_t> ep(fmt_threads, 0), em(fmt_threads, 0);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < fmt_threads; ++t)
+    th.emplace_back([&, t]() {
+      std::vector<uint8_t> rd, tg;
+      const uint32_t b0 = (uint32_t)((uint64_t)nrec * t / fmt_threads), e0 = (uint32_t)((uint64_t)nrec * (t + 1) / fmt_threads);
+      for (uint32_t i = b0; i < e0; ++i) {
+        bkx_read_result& r = res[i];
+        trim_mm[i] = r.mismatches;
+        if (r.nar != BKX_NAR_ACCEPTED) continue;
+        const int L = r.match_len, minlen = std::max(15, (L + 1) / 2), X = o.min_flank;
+        const uint8_t* b = R.bases.data() + R.offs[rc.rix(i)];
+        const uint8_t* g = genome[r.chrom_id].data() + r.match_loci;
+        rd.resize(L); tg.resize(L);
+        for (int q = 0; q < L; ++q) rd[q] = b[q] & 7;
+        if (r.strand == '-') for (int q = 0; q < L; ++q) { uint8_t c = g[L - 1 - q] & 7; tg[q] = c < 4 ? 3 - c : c; }
+        else for (int q = 0; q < L; ++q) tg[q] = g[q] & 7;
+        auto slough = [&]() { r.num_hits = 0; r.nar = BKX_NAR_TRIM; ++(r.strand == '+' ? ep[t] : em[t]); };
+        const bool pe = o.pe_mode != 0;
+        int exact = 0, tmm = 0, k;
+        for (k = 0; k <= L - minlen && k < (pe ? L / 3 : L); ++k) {       // 5' -> 3'
+          if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
+          if (++exact == X) break;
+        }
+        if (!pe && (k + minlen > L || exact < X)) { slough(); continue; }
+        const int left = k - (X - 1);
+        exact = 0;
+        for (k = L - 1; k >= left + minlen && k > (pe ? (L * 2) / 3 : 0); --k) {  // 3' -> 5'
+          if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
+          if (++exact == X) break;
+        }
+        if (!pe && (exact != X || k < left + minlen)) { slough(); continue; }
+        const int right = k + X;
+        trim_l[i] = (uint16_t)left; trim_r[i] = (uint16_t)(L - right);
+        if (left || L - right) trim_mm[i] = (uint8_t)(r.mismatches - tmm);
+      }
+    });
+  for (auto& x : th) x.join();
+  for (unsigned t = 0; t < fmt_threads; ++t) { rc.elim_plus += ep[t]; rc.elim_minus += em[t]; }
+  diag("Finished 5' and 3' flank sequence autotriming, %d plus strand and %d minus strand aligned reads removed", (int)rc.elim_plus, (int)rc.elim_minus);
+  diag("Autotrim aligned read flank processing completed");
+}
+
+// ---- -Z / -z: FiltByChroms, Aligner.cpp:4019-4124.  A chromosome matching an include expression stays; with no
+//      include expressions given it stays unless an exclude expression matches; otherwise its alignments become
+//      eNARChromFilt.  (Exclude expressions are not consulted once include expressions exist -- as in the reference.)
+static void filter_by_chroms(Records& rc, std::vector<regex_t>& rin, std::vector<regex_t>& rex) {
+  auto& res = rc.res;
+  const auto& ents = rc.ents;
+  const uint32_t nrec = rc.n(), num_entries = (uint32_t)ents.size() - 1;
+  diag("Filtering aligned reads by chromosome started..");
+  diag("Now filtering matches by chromosome");
+  std::vector<char> keep(num_entries + 1, 1);
+  for (uint32_t e = 1; e <= num_entries; ++e) {
+    regmatch_t mc;
+    bool ok = false;
+    for (auto& re : rin) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = true; break; }
+    if (!ok && rin.empty()) {
+      ok = true;
+      for (auto& re : rex) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = false; break; }
+    }
+    keep[e] = ok;
+  }
+  for (auto& re : rin) regfree(&re);
+  for (auto& re : rex) regfree(&re);
+  int removed = 0;
+  for (uint32_t i = 0; i < nrec; ++i) {
+    bkx_read_result& r = res[i];
+    if (r.nar == BKX_NAR_ACCEPTED && !keep[r.chrom_id]) { r.nar = BKX_NAR_CHROMFILT; r.num_hits = 0; r.low_hit_instances = 0; ++removed; }
+  }
+  diag("Filtering by chromosome completed - removed %d  matches", removed);
+  diag("Filtering aligned reads by chromosome completed");
+}
+
 int main(int argc, char** argv) {
   Opts o;
   int pr = parse(argc, argv, o);
@@ -1141,212 +1382,21 @@ int main(int argc, char** argv) {
       if (bkx_get_seq(idx[0], e, 0, ents[e].seq_len, genome[e].data()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
     }
 
-  // ---- -5: IdentifyConstraintViolations / AcceptLociConstraints / AcceptBaseConstraint, Aligner.cpp:2480-2647.  An accepted
-  //      alignment becomes eNARLociConstrained when, at some constrained locus it covers, the read's base (as aligned:
-  //      complemented on '-') is none of the bases that constraint allows; in paired-end runs the mate goes with it.
-  if (!constraints.empty()) {
-    diag("Identifying %s loci base constraint violations ...", o.pe_mode ? "PE" : "SE");
-    std::vector<std::pair<size_t, size_t>> span(info.num_entries + 2, {0, 0});   // constraints of a chromosome: [first, last)
-    for (size_t k = 0; k < constraints.size(); ++k) {
-      auto& sp = span[constraints[k].chrom];
-      if (sp.second == 0) sp.first = k;
-      sp.second = k + 1;
-    }
-    auto violates = [&](const bkx_read_result& r, uint32_t ri) -> bool {
-      const auto sp = span[r.chrom_id];
-      if (sp.second == 0) return false;
-      const uint8_t* b = R.bases.data() + R.offs[ri];
-      const uint32_t L = r.match_len, lo = r.match_loci, hi = r.match_loci + L - 1;
-      for (size_t k = sp.first; k < sp.second; ++k) {
-        const LociConstraint& c = constraints[k];
-        if (c.end < lo || c.start > hi) continue;
-        for (uint32_t l = std::max(lo, c.start); l <= std::min(hi, c.end); ++l) {
-          uint8_t base = r.strand == '-' ? b[L - 1 - (l - lo)] & 7 : b[l - lo] & 7;
-          if (r.strand == '-' && base < 4) base = 3 - base;
-          if ((c.mask & 0x10) && (genome[r.chrom_id][l] & 0x0f) == base) continue;
-          if (base < 4 && (c.mask & (1u << base))) continue;
-          return true;
-        }
-      }
-      return false;
-    };
-    std::vector<uint8_t> bad(nrec, 0);
-    {
-      std::vector<std::thread> th;
-      for (unsigned t = 0; t < fmt_threads; ++t)
-        th.emplace_back([&, t]() {
-          const uint32_t b0 = (uint32_t)((uint64_t)nrec * t / fmt_threads), e0 = (uint32_t)((uint64_t)nrec * (t + 1) / fmt_threads);
-          for (uint32_t i = b0; i < e0; ++i) bad[i] = res[i].nar == BKX_NAR_ACCEPTED && violates(res[i], rix(i));
-        });
-      for (auto& x : th) x.join();
-    }
-    int identified = 0;
-    auto mark = [&](uint32_t i) {
-      if (res[i].nar == BKX_NAR_LOCICONSTRAINED) return;
-      res[i].nar = BKX_NAR_LOCICONSTRAINED; res[i].num_hits = 0; res[i].low_hit_instances = 0;
-      ++identified;
-    };
-    for (uint32_t i = 0; i < nrec; ++i)
-      if (bad[i]) { mark(i); if (o.pe_mode) mark(i ^ 1u); }
-    diag("Identified %d %s loci base constraint violations", identified, o.pe_mode ? "PE" : "SE");
-  }
-
-  // ---- -k: ReducePCRduplicates, Aligner.cpp:2184-2282 (single-end runs only, :599).  In hit order, alignments that
-  //      share chromosome, start, strand and length with an earlier one are dropped as eNARPCRdup once the allowance
-  //      is used up; with a window the allowance grows with the number of distinct start loci within WinLen either
-  //      side (NumUpUniques / NumDnUniques, :9817-9914).  Which of several reads with identical sort keys survives is
-  //      left open by the reference's unstable sort; here it is the one loaded first.
-  if (o.pcr_win >= 0 && !o.pe_mode) {
-    diag("Processing to reduce PCR differential amplification artefacts processing started..");
-    std::vector<uint32_t> ord(nrec);
-    if (nrec && bkx_sort_hits(res.data(), nrec, ord.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
-    const int W = o.pcr_win;
-    auto acc = [&](uint32_t k) { return res[ord[k]].nar == BKX_NAR_ACCEPTED; };
-    auto dn_uniques = [&](uint32_t k) -> int {
-      const bkx_read_result& c = res[ord[k]];
-      int n_u = 0;
-      uint32_t prv = c.match_loci;
-      for (uint32_t j = k + 1; j < nrec; ++j) {
-        const bkx_read_result& x = res[ord[j]];
-        if (x.chrom_id != c.chrom_id) break;
-        if (!acc(j)) continue;
-        if ((int64_t)c.match_loci + W < (int64_t)x.match_loci) break;
-        if (x.strand != c.strand) continue;
-        if (x.match_loci != prv) { ++n_u; prv = x.match_loci; }
-      }
-      return n_u;
-    };
-    auto up_uniques = [&](uint32_t k) -> int {
-      if (k == 0) return 0;
-      const bkx_read_result& c = res[ord[k]];
-      int n_u = 0;
-      uint32_t prv = c.match_loci;
-      for (uint32_t j = k + 1; j-- > 0;) {   // starts at the current record itself, as the reference does
-        const bkx_read_result& x = res[ord[j]];
-        if (x.chrom_id != c.chrom_id) break;
-        if (!acc(j)) continue;
-        if ((int64_t)c.match_loci > W && (int64_t)c.match_loci - W > (int64_t)x.match_loci) break;
-        if (x.strand != c.strand) continue;
-        if (x.match_loci != prv) { ++n_u; prv = x.match_loci; }
-      }
-      return n_u;
-    };
-    int removed = 0;
-    for (uint32_t k = 0; k < nrec; ++k) {
-      if (!acc(k)) continue;
-      int limit = 0;
-      if (W > 0) {
-        limit = std::max(up_uniques(k), dn_uniques(k));
-        const int prop = (int)(((double)limit / W) * 100.0);
-        limit = prop < 5 ? 1 : prop <= 10 ? 2 : prop <= 20 ? 3 : prop <= 40 ? 4 : prop <= 60 ? 5 : prop <= 80 ? 10 : 50;
-      }
-      const bkx_read_result c = res[ord[k]];
-      uint32_t mark = k;
-      for (uint32_t j = k + 1; j < nrec; ++j) {
-        bkx_read_result& x = res[ord[j]];
-        if (x.nar != BKX_NAR_ACCEPTED) continue;
-        if (x.chrom_id != c.chrom_id || x.match_loci != c.match_loci || x.strand != c.strand) break;
-        if (x.match_len != c.match_len) continue;
-        if (limit > 0) { --limit; continue; }
-        x.num_hits = 0; x.low_hit_instances = 0; x.nar = BKX_NAR_PCRDUP;
-        mark = j;
-        ++removed;
-      }
-      k = mark;
-    }
-    diag("Removed %d potential PCR artefact reads", removed);
-    diag("PCR differential amplification artefacts processing completed");
-  }
-
-
-  // ---- -x: AutoTrimFlanks, Aligner.cpp:1608-1812.  Each accepted alignment is cut back from both ends to the first run
-  //      of MinFlankExacts matching bases; the rest must keep at least half the read (>= 15 bp) or the read is sloughed
-  //      as eNARTrim.  In paired-end runs the 5' scan stays inside the first third of the read and the 3' scan inside
-  //      the last third, and nothing is sloughed (the pairing stands).  TrimLeft / TrimRight are in READ orientation
-  //      (Aligner.cpp:1528-1549).
-  std::vector<uint16_t> trim_l, trim_r;
-  std::vector<uint8_t> trim_mm;   // Seg[0].TrimMismatches: mismatches left inside the trimmed alignment
-  uint32_t elim_plus = 0, elim_minus = 0, num_trimmed = 0;
-  if (o.min_flank > 0) {
-    diag("Autotrim aligned read flank processing started..");
-    diag("Starting 5' and 3' flank sequence autotrim processing...");
-    trim_l.assign(nrec, 0); trim_r.assign(nrec, 0); trim_mm.assign(nrec, 0);
-    std::vector<uint32_t> ep(fmt_threads, 0), em(fmt_threads, 0);
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < fmt_threads; ++t)
-      th.emplace_back([&, t]() {
-        std::vector<uint8_t> rd, tg;
-        const uint32_t b0 = (uint32_t)((uint64_t)nrec * t / fmt_threads), e0 = (uint32_t)((uint64_t)nrec * (t + 1) / fmt_threads);
-        for (uint32_t i = b0; i < e0; ++i) {
-          bkx_read_result& r = res[i];
-          trim_mm[i] = r.mismatches;
-          if (r.nar != BKX_NAR_ACCEPTED) continue;
-          const int L = r.match_len, minlen = std::max(15, (L + 1) / 2), X = o.min_flank;
-          const uint8_t* b = R.bases.data() + R.offs[rix(i)];
-          const uint8_t* g = genome[r.chrom_id].data() + r.match_loci;
-          rd.resize(L); tg.resize(L);
-          for (int q = 0; q < L; ++q) rd[q] = b[q] & 7;
-          if (r.strand == '-') for (int q = 0; q < L; ++q) { uint8_t c = g[L - 1 - q] & 7; tg[q] = c < 4 ? 3 - c : c; }
-          else for (int q = 0; q < L; ++q) tg[q] = g[q] & 7;
-          auto slough = [&]() { r.num_hits = 0; r.nar = BKX_NAR_TRIM; ++(r.strand == '+' ? ep[t] : em[t]); };
-          const bool pe = o.pe_mode != 0;
-          int exact = 0, tmm = 0, k;
-          for (k = 0; k <= L - minlen && k < (pe ? L / 3 : L); ++k) {       // 5' -> 3'
-            if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
-            if (++exact == X) break;
-          }
-          if (!pe && (k + minlen > L || exact < X)) { slough(); continue; }
-          const int left = k - (X - 1);
-          exact = 0;
-          for (k = L - 1; k >= left + minlen && k > (pe ? (L * 2) / 3 : 0); --k) {  // 3' -> 5'
-            if (rd[k] != tg[k]) { exact = 0; ++tmm; continue; }
-            if (++exact == X) break;
-          }
-          if (!pe && (exact != X || k < left + minlen)) { slough(); continue; }
-          const int right = k + X;
-          trim_l[i] = (uint16_t)left; trim_r[i] = (uint16_t)(L - right);
-          if (left || L - right) trim_mm[i] = (uint8_t)(r.mismatches - tmm);
-        }
-      });
-    for (auto& x : th) x.join();
-    for (unsigned t = 0; t < fmt_threads; ++t) { elim_plus += ep[t]; elim_minus += em[t]; }
-    diag("Finished 5' and 3' flank sequence autotriming, %d plus strand and %d minus strand aligned reads removed", (int)elim_plus, (int)elim_minus);
-    diag("Autotrim aligned read flank processing completed");
-  }
-  // the alignment as reported: AdjStartLoci / AdjHitLen / TrimMismatches (Aligner.cpp:1528-1552)
-  auto tleft = [&](uint32_t i) -> uint32_t { return trim_l.empty() ? 0u : trim_l[i]; };
-  auto tright = [&](uint32_t i) -> uint32_t { return trim_r.empty() ? 0u : trim_r[i]; };
-  auto adj_start = [&](uint32_t i) -> uint32_t { return res[i].match_loci + (res[i].strand == '+' ? tleft(i) : tright(i)); };
-  auto adj_len = [&](uint32_t i) -> uint32_t { return (uint32_t)res[i].match_len - tleft(i) - tright(i); };
-  auto adj_mm = [&](uint32_t i) -> uint32_t { return trim_mm.empty() ? res[i].mismatches : trim_mm[i]; };
-
-  // ---- -Z / -z: FiltByChroms, Aligner.cpp:4019-4124.  A chromosome matching an include expression stays; with no
-  //      include expressions given it stays unless an exclude expression matches; otherwise its alignments become
-  //      eNARChromFilt.  (Exclude expressions are not consulted once include expressions exist -- as in the reference.)
-  if (!o.excl.empty() || !o.incl.empty()) {
-    diag("Filtering aligned reads by chromosome started..");
-    diag("Now filtering matches by chromosome");
-    std::vector<char> keep(info.num_entries + 1, 1);
-    for (uint32_t e = 1; e <= info.num_entries; ++e) {
-      regmatch_t mc;
-      bool ok = false;
-      for (auto& re : rin) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = true; break; }
-      if (!ok && rin.empty()) {
-        ok = true;
-        for (auto& re : rex) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = false; break; }
-      }
-      keep[e] = ok;
-    }
-    for (auto& re : rin) regfree(&re);
-    for (auto& re : rex) regfree(&re);
-    int removed = 0;
-    for (uint32_t i = 0; i < nrec; ++i) {
-      bkx_read_result& r = res[i];
-      if (r.nar == BKX_NAR_ACCEPTED && !keep[r.chrom_id]) { r.nar = BKX_NAR_CHROMFILT; r.num_hits = 0; r.low_hit_instances = 0; ++removed; }
-    }
-    diag("Filtering by chromosome completed - removed %d  matches", removed);
-    diag("Filtering aligned reads by chromosome completed");
-  }
+  Records rc{o, R, res, src, ents, genome, fmt_threads, {}, {}, {}};
+  // the passes, in the order of CAligner::Align (Aligner.cpp:596-655)
+  if (!constraints.empty()) identify_constraint_violations(rc, constraints);
+  if (o.pcr_win >= 0 && !o.pe_mode && reduce_pcr_duplicates(rc) < 0) return 1;
+  if (o.min_flank > 0) auto_trim_flanks(rc);
+  if (!o.excl.empty() || !o.incl.empty()) filter_by_chroms(rc, rin, rex);
+  const auto& trim_l = rc.trim_l;
+  const auto& trim_r = rc.trim_r;
+  const uint32_t elim_plus = rc.elim_plus, elim_minus = rc.elim_minus;
+  uint32_t num_trimmed = 0;
+  auto tleft = [&](uint32_t i) { return rc.tleft(i); };
+  auto tright = [&](uint32_t i) { return rc.tright(i); };
+  auto adj_start = [&](uint32_t i) { return rc.adj_start(i); };
+  auto adj_len = [&](uint32_t i) { return rc.adj_len(i); };
+  auto adj_mm = [&](uint32_t i) { return rc.adj_mm(i); };
 
   // "were trimmed" of the summary: FlagTR of the alignments still accepted at this point (Aligner.cpp:3558)
   if (!trim_l.empty())
