@@ -1099,6 +1099,421 @@ static void filter_by_chroms(Records& rc, std::vector<regex_t>& rin, std::vector
   diag("Filtering aligned reads by chromosome completed");
 }
 
+// ---- writers.  Rows go out in hit order (`order`); every writer reports the alignment as trimmed by -x, if at all.
+static const char kAsc[] = "ACGTN";
+
+static void write_bed(const Records& rc, const std::vector<uint32_t>& order, const bkx_index_info& info, OutBuf& ob) {
+  const Opts& o = rc.o;
+  const auto& res = rc.res;
+  const auto& ents = rc.ents;
+  const uint32_t nrec = rc.n();
+  const unsigned fmt_threads = rc.threads;
+  auto adj_start = [&](uint32_t i) { return rc.adj_start(i); };
+  auto adj_len = [&](uint32_t i) { return rc.adj_len(i); };
+  // UCSC BED: track line then chrom, start, end+1, "ar", score, strand (Aligner.cpp:6355-6362, 6463-6466)
+  const char* title = o.title.empty() ? "kanga" : o.title.c_str();
+  // under -r5 the reference writes the track line twice: when it creates the file and when it reports (Aligner.cpp:4405, 6358)
+  for (int rep = 0; rep < ((o.ml_mode == BKX_ML_ALL) ? 2 : 1); ++rep) { ob.s += "track type=bed name=\""; ob.s += title; ob.s += "\" description=\""; ob.s += title; ob.s += "\"\n"; }
+  emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
+    uint32_t i = order[k];
+    const bkx_read_result& r = res[i];
+    if (r.nar != BKX_NAR_ACCEPTED) return;
+    s += ents[r.chrom_id].name; s += '\t';
+    append_uint(s, adj_start(i)); s += '\t';
+    append_uint(s, (uint64_t)adj_start(i) + adj_len(i)); s += "\tar\t0\t"; s += (char)r.strand; s += '\n';
+  });
+}
+
+
+static void write_csv(const Records& rc, const std::vector<uint32_t>& order, const bkx_index_info& info, OutBuf& ob) {
+  const Opts& o = rc.o;
+  const Reads& R = rc.R;
+  const auto& res = rc.res;
+  const auto& ents = rc.ents;
+  const auto& genome = rc.genome;
+  const uint32_t nrec = rc.n();
+  const unsigned fmt_threads = rc.threads;
+  auto rix = [&](uint32_t i) { return rc.rix(i); };
+  auto tleft = [&](uint32_t i) { return rc.tleft(i); };
+  auto adj_start = [&](uint32_t i) { return rc.adj_start(i); };
+  auto adj_len = [&](uint32_t i) { return rc.adj_len(i); };
+  auto adj_mm = [&](uint32_t i) { return rc.adj_mm(i); };
+  // ReadID,"ar","species","chrom",start,end,len,"strand",score,0,NumReads,TrimMismatches,"N/A","descriptor"
+  // -M2/-M3 append the read sequence, -M1/-M3 the matched genome sequence in read orientation (Aligner.cpp:6612-6621)
+  emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
+    uint32_t i = order[k];
+    const bkx_read_result& r = res[i];
+    if (r.nar != BKX_NAR_ACCEPTED) return;
+    append_uint(s, (uint64_t)i + 1);
+    s += ",\"ar\",\""; s += info.dataset_name; s += "\",\""; s += ents[r.chrom_id].name; s += "\",";
+    const uint32_t start = adj_start(i), alen = adj_len(i);   // the alignment as trimmed by -x, if at all
+    append_uint(s, start); s += ',';
+    append_uint(s, (uint64_t)start + alen - 1); s += ',';
+    append_uint(s, alen); s += ",\""; s += (char)r.strand; s += "\",0,0,1,";
+    const uint32_t ri = rix(i);
+    append_uint(s, adj_mm(i)); s += ",\"N/A\",\""; s += R.name(ri); s += '"';
+    if (o.fmt >= 2) {
+      s += ",\"";
+      const uint8_t* b = R.bases.data() + R.offs[ri] + tleft(i);
+      for (uint32_t q = 0; q < alen; ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+      s += '"';
+    }
+    if (o.fmt == 1 || o.fmt == 3) {
+      s += ",\"";
+      const uint8_t* g = genome[r.chrom_id].data() + start;
+      if (r.strand == '-') for (int q = (int)alen - 1; q >= 0; --q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
+      else for (uint32_t q = 0; q < alen; ++q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+      s += '"';
+    }
+    s += '\n';
+  });
+}
+
+
+static bool write_bam(const Records& rc, const std::vector<uint32_t>& order, const bkx_index_info& info, OutBuf& ob) {
+  const Opts& o = rc.o;
+  const Reads& R = rc.R;
+  const auto& res = rc.res;
+  const auto& ents = rc.ents;
+  const uint32_t nrec = rc.n();
+  const unsigned fmt_threads = rc.threads;
+  auto rix = [&](uint32_t i) { return rc.rix(i); };
+  auto tleft = [&](uint32_t i) { return rc.tleft(i); };
+  auto tright = [&](uint32_t i) { return rc.tright(i); };
+  auto adj_start = [&](uint32_t i) { return rc.adj_start(i); };
+  auto adj_len = [&](uint32_t i) { return rc.adj_len(i); };
+  // ---- BAM + BAI (same record content as the SAM branch below, binary form)
+  ob.close();
+  Bgzf bz;
+  if (!bz.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return false; }
+  std::vector<char> hit(info.num_entries + 1, 0);
+  for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
+  bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
+  std::vector<int> refid(info.num_entries + 1, -1);
+  std::string text = "@HD\tVN:1.4\tSO:coordinate", refs;
+  uint32_t nref = 0;
+  for (uint32_t e = 1; e <= info.num_entries; ++e)
+    if (all || hit[e]) {
+      text += "\n@SQ\tAS:"; text += info.dataset_name; text += "\tSN:"; text += ents[e].name; text += "\tLN:";
+      append_uint(text, ents[e].seq_len);
+      refid[e] = (int)nref++;
+      uint32_t ln = (uint32_t)strlen(ents[e].name) + 1, sl = ents[e].seq_len;
+      refs.append((const char*)&ln, 4); refs.append(ents[e].name, ln); refs.append((const char*)&sl, 4);
+    }
+  text += "\n@PG\tID:biokanga\tVN:4.4.2\n";
+  std::string hdr = "BAM\1";
+  uint32_t lt = (uint32_t)text.size();
+  hdr.append((const char*)&lt, 4); hdr += text; hdr.append((const char*)&nref, 4); hdr += refs;
+  // The whole uncompressed BAM stream is laid out first (record sizes -> offsets -> records written in place by all
+  // threads), then cut into BGZF blocks exactly where the reference's sequential writer cuts them (every 0xff00
+  // bytes, plus once behind the last aligned record), the blocks are deflated in parallel and written in order; the
+  // BAI follows from the record offsets and the block addresses.
+  BaiBuilder bai;
+  bai.out = "BAI\1";
+  bai.put32(nref);
+  struct RecMeta { uint64_t uofs; uint32_t len; int32_t rid, pos; int32_t L, alen; uint8_t acc, lead, trail; };
+  std::vector<RecMeta> meta;
+  meta.reserve(nrec);
+  uint64_t utotal = hdr.size();
+  for (uint32_t k = 0; k < nrec; ++k) {
+    uint32_t i = order[k];
+    const bkx_read_result& r = res[i];
+    bool acc = r.nar == BKX_NAR_ACCEPTED;
+    if (!acc && o.fmt != 6) continue;
+    const uint32_t ri = rix(i);
+    const int L = R.len(ri);
+    uint32_t lname = (uint32_t)strlen(R.name(ri)) + 1;
+    // -x trims become soft clips either side of the M operation (Aligner.cpp:5960-5985)
+    const uint32_t lead = !acc ? 0u : r.strand == '+' ? tleft(i) : tright(i), trail = !acc ? 0u : r.strand == '+' ? tright(i) : tleft(i);
+    const uint32_t ncig = 1 + (lead ? 1 : 0) + (trail ? 1 : 0);
+    uint32_t len = 4 + 32 + lname + 4 * ncig + (uint32_t)((L + 1) / 2) + (uint32_t)L + (acc ? 0u : 6u);
+    meta.push_back({utotal, len, acc ? refid[r.chrom_id] : -1, acc ? (int32_t)adj_start(i) : -1, L, acc ? (int32_t)adj_len(i) : L,
+                    (uint8_t)acc, (uint8_t)lead, (uint8_t)trail});
+    utotal += len;
+  }
+  std::vector<uint8_t> U(utotal);
+  memcpy(U.data(), hdr.data(), hdr.size());
+  // record k' (index into meta) <- sorted record; meta and the sorted walk advance together
+  std::vector<uint32_t> kept;
+  kept.reserve(meta.size());
+  for (uint32_t k = 0; k < nrec; ++k) {
+    const bkx_read_result& r = res[order[k]];
+    if (r.nar == BKX_NAR_ACCEPTED || o.fmt == 6) kept.push_back(order[k]);
+  }
+  auto write_record = [&](size_t mi) {
+    const uint32_t i = kept[mi];
+    const RecMeta& M = meta[mi];
+    const bkx_read_result& r = res[i];
+    const bool acc = M.acc != 0;
+    int flags = 0, tlen = 0;
+    long pnext = -1;
+    if (!o.pe_mode) flags = acc ? (r.strand == '+' ? 0 : 0x10) : 0x04;
+    else {
+      bool pe2 = i & 1;
+      const bkx_read_result& m = res[pe2 ? i - 1 : i + 1];
+      flags = 0x01 | 0x02 | (pe2 ? 0x80 : 0x40);
+      if (acc) flags |= r.strand == '+' ? 0 : 0x10; else flags |= 0x04;
+      bool both = (r.flags & BKX_FLG_PE_ALIGNED) && (m.flags & BKX_FLG_PE_ALIGNED) && m.nar == BKX_NAR_ACCEPTED;
+      if (both) {
+        flags |= m.strand == '+' ? 0 : 0x20;
+        if (acc) {
+          const uint32_t mi2 = pe2 ? i - 1 : i + 1;   // both alignments as trimmed by -x, if at all
+          long se = adj_start(i), pes = adj_start(mi2);
+          tlen = se <= pes ? (int)(pes - se) + (int)adj_len(mi2) : (int)(se - pes) + (int)adj_len(i);
+          pnext = pes;
+        }
+      } else flags |= 0x08;
+    }
+    const uint32_t ri = rix(i);
+    const int L = M.L;
+    const uint8_t* b = R.bases.data() + R.offs[ri];
+    const char* qn = R.name(ri);
+    uint32_t lname = (uint32_t)strlen(qn) + 1;
+    int32_t rid = M.rid, pos = M.pos;
+    const uint32_t ncig = 1 + (M.lead ? 1 : 0) + (M.trail ? 1 : 0);
+    uint32_t bin = acc ? (uint32_t)bai_reg2bin(pos, pos + M.alen) : 0;
+    uint32_t bmn = bin << 16 | 255u << 8 | lname, fnc = (uint32_t)flags << 16 | ncig;
+    int32_t nrid = (acc && pnext >= 0) ? rid : -1, npos = acc ? (int32_t)pnext : -1, tl = acc ? tlen : 0, lseq = L;
+    uint32_t cigar = (uint32_t)M.alen << 4, clip_lead = (uint32_t)M.lead << 4 | 4u, clip_trail = (uint32_t)M.trail << 4 | 4u;
+    uint8_t* w = U.data() + M.uofs;
+    uint32_t bsz = M.len - 4;
+    auto p32 = [&](const void* v) { memcpy(w, v, 4); w += 4; };
+    p32(&bsz); p32(&rid); p32(&pos); p32(&bmn); p32(&fnc); p32(&lseq); p32(&nrid); p32(&npos); p32(&tl);
+    memcpy(w, qn, lname); w += lname;
+    if (M.lead) p32(&clip_lead);
+    p32(&cigar);
+    if (M.trail) p32(&clip_trail);
+    bool rc = acc && r.strand != '+';
+    for (int q = 0; q < L; q += 2) {
+      auto nib = [&](int idx) -> unsigned {
+        if (idx >= L) return 0u;
+        uint8_t c = b[rc ? L - 1 - idx : idx] & 7;
+        if (c < 4) { if (rc) c = 3 - c; return 1u << c; }
+        return 15u;
+      };
+      *w++ = (uint8_t)(nib(q) << 4 | nib(q + 1));
+    }
+    int sumq = 0;
+    for (int q = 0; q < L; ++q) sumq += (b[q] >> 4) & 0x0f;
+    if (sumq == 0) { memset(w, 0xff, (size_t)L); w += L; }
+    else for (int q = 0; q < L; ++q) *w++ = (uint8_t)(33 + (((b[rc ? L - 1 - q : q] >> 4) & 0x0f) * 40) / 15);
+    if (!acc) { memcpy(w, "YUZ", 3); w += 3; memcpy(w, kNarCode[r.nar], 2); w += 2; *w++ = 0; }
+  };
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < fmt_threads; ++t)
+      th.emplace_back([&, t]() {
+        size_t b0 = meta.size() * t / fmt_threads, e0 = meta.size() * (t + 1) / fmt_threads;
+        for (size_t mi = b0; mi < e0; ++mi) write_record(mi);
+      });
+    for (auto& x : th) x.join();
+  }
+  // explicit flush behind the last aligned record (bLastAligned, SAMfile.cpp), if any
+  uint64_t flush_at = 0;
+  bool have_flush = false;
+  for (size_t mi = meta.size(); mi-- > 0;)
+    if (meta[mi].acc) { flush_at = meta[mi].uofs + meta[mi].len; have_flush = true; break; }
+  bool ok = bz.write_stream(U.data(), U.size(), have_flush ? &flush_at : nullptr, fmt_threads);
+  // BAI bins end at 512 Mbp.  For longer reference sequences the reference switches to a CSI index (SAMfile.cpp:1602-1622)
+  // but never opens that file -- the branch that would (:1664) hangs off `if (type >= BAI)` and is unreachable -- so its
+  // first index flush fails (WriteIdxToDisk, :1812).  Here the BAM is written complete and the index is left to
+  // `samtools index -c`, with a note in the log, rather than an index with overflowing bins.
+  uint32_t longest_ref = 0;
+  for (uint32_t e = 1; e <= info.num_entries; ++e) if (refid[e] >= 0) longest_ref = std::max(longest_ref, ents[e].seq_len);
+  const bool write_bai = longest_ref < 0x20000000u;
+  if (!write_bai) diag("Note: reference sequences of 512Mbp or more (max %u): no BAI index written for '%s', index it with a CSI indexer", longest_ref, o.out.c_str());
+  int cur_ref = -1;  // reference whose index block is being accumulated
+  for (size_t mi = 0; mi < meta.size() && ok && write_bai; ++mi) {
+    const RecMeta& M = meta[mi];
+    if (!M.acc) continue;
+    while (cur_ref < M.rid) { if (cur_ref >= 0) bai.end_ref(); ++cur_ref; }
+    bai.add(bz.vaddr(M.uofs), (uint32_t)M.pos, bz.vaddr(M.uofs + M.len), (uint32_t)(M.pos + M.alen - 1));
+  }
+  bai.end_ref();  // Close(): the reference in progress (an empty block when nothing aligned)
+  ok = ok && bz.close();
+  if (write_bai) {
+    FILE* fb = fopen((o.out + ".bai").c_str(), "wb");
+    if (fb) { fwrite(bai.out.data(), 1, bai.out.size(), fb); fclose(fb); } else ok = false;
+  }
+  if (!ok) { diag("Fatal: write to '%s' failed", o.out.c_str()); return false; }
+  return true;
+}
+
+
+static void write_sam(const Records& rc, const std::vector<uint32_t>& order, const bkx_index_info& info, OutBuf& ob) {
+  const Opts& o = rc.o;
+  const Reads& R = rc.R;
+  const auto& res = rc.res;
+  const auto& ents = rc.ents;
+  const uint32_t nrec = rc.n();
+  const unsigned fmt_threads = rc.threads;
+  auto rix = [&](uint32_t i) { return rc.rix(i); };
+  auto tleft = [&](uint32_t i) { return rc.tleft(i); };
+  auto tright = [&](uint32_t i) { return rc.tright(i); };
+  auto adj_start = [&](uint32_t i) { return rc.adj_start(i); };
+  auto adj_len = [&](uint32_t i) { return rc.adj_len(i); };
+  // SAM header: @HD, @SQ for every chromosome (or only those hit if more than -4 threshold), @PG
+  std::vector<char> hit(info.num_entries + 1, 0);
+  for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
+  bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
+  ob.s += "@HD\tVN:1.4\tSO:coordinate\n";
+  for (uint32_t e = 1; e <= info.num_entries; ++e)
+    if (all || hit[e]) {
+      ob.s += "@SQ\tAS:"; ob.s += info.dataset_name; ob.s += "\tSN:"; ob.s += ents[e].name; ob.s += "\tLN:";
+      append_uint(ob.s, ents[e].seq_len); ob.s += '\n';
+    }
+  ob.s += "@PG\tID:biokanga\tVN:4.4.2\n";
+  emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
+    uint32_t i = order[k];
+    const bkx_read_result& r = res[i];
+    bool acc = r.nar == BKX_NAR_ACCEPTED;
+    if (!acc && o.fmt != 6) return;
+    int flags = 0, tlen = 0;
+    long pnext = -1;
+    if (!o.pe_mode) {
+      flags = acc ? (r.strand == '+' ? 0 : 0x10) : 0x04;
+    } else {  // ReportBAMread, Aligner.cpp:5864-5925
+      bool pe2 = i & 1;
+      const bkx_read_result& m = res[pe2 ? i - 1 : i + 1];
+      flags = 0x01 | 0x02 | (pe2 ? 0x80 : 0x40);
+      if (acc) flags |= r.strand == '+' ? 0 : 0x10; else flags |= 0x04;
+      bool both = (r.flags & BKX_FLG_PE_ALIGNED) && (m.flags & BKX_FLG_PE_ALIGNED) && m.nar == BKX_NAR_ACCEPTED;
+      if (both) {
+        flags |= m.strand == '+' ? 0 : 0x20;
+        if (acc) {
+          const uint32_t mi2 = pe2 ? i - 1 : i + 1;   // both alignments as trimmed by -x, if at all
+          long se = adj_start(i), pes = adj_start(mi2);
+          tlen = se <= pes ? (int)(pes - se) + (int)adj_len(mi2) : (int)(se - pes) + (int)adj_len(i);
+          pnext = pes;
+        }
+      } else flags |= 0x08;
+    }
+    const uint32_t ri = rix(i);
+    s += R.name(ri); s += '\t';
+    append_uint(s, (uint64_t)flags); s += '\t';
+    if (acc) { s += ents[r.chrom_id].name; s += '\t'; append_uint(s, (uint64_t)adj_start(i) + 1); }
+    else s += "*\t0";
+    s += "\t255\t";
+    if (acc) {  // flanks trimmed by -x are soft clipped, in reference orientation (Aligner.cpp:5960-5985)
+      const uint32_t lead = r.strand == '+' ? tleft(i) : tright(i), trail = r.strand == '+' ? tright(i) : tleft(i);
+      if (lead) { append_uint(s, lead); s += 'S'; }
+      append_uint(s, adj_len(i)); s += 'M';
+      if (trail) { append_uint(s, trail); s += 'S'; }
+      s += '\t';
+    } else { append_uint(s, (uint64_t)R.len(ri)); s += "M\t"; }
+    if (acc && pnext >= 0) { s += "=\t"; append_uint(s, (uint64_t)pnext + 1); s += '\t'; append_uint(s, (uint64_t)tlen); s += '\t'; }
+    else s += "*\t0\t0\t";
+    const uint8_t* b = R.bases.data() + R.offs[ri];
+    int L = R.len(ri);
+    if (acc && r.strand != '+') {
+      for (int q = L - 1; q >= 0; --q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
+    } else {
+      for (int q = 0; q < L; ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
+    }
+    // QUAL: '*' unless qualities were kept (-g0..2); 33 + q4*40/15, reversed with the sequence (Aligner.cpp:5929-5955)
+    int sumq = 0;
+    for (int q = 0; q < L; ++q) sumq += (b[q] >> 4) & 0x0f;
+    s += '\t';
+    if (sumq == 0) s += '*';
+    else if (acc && r.strand != '+') for (int q = L - 1; q >= 0; --q) s += (char)(33 + (((b[q] >> 4) & 0x0f) * 40) / 15);
+    else for (int q = 0; q < L; ++q) s += (char)(33 + (((b[q] >> 4) & 0x0f) * 40) / 15);
+    if (!acc) { s += "\t\tYU:Z:"; s += kNarCode[r.nar]; }
+    s += '\n';
+  });
+}
+
+// ---- -j / -J: ReportNoneAligned / ReportMultiAlign, Aligner.cpp:3826-4016 -- FASTA, 70 columns, in hit order
+template <class Want>
+static bool report_reads(const Records& rc, const std::vector<uint32_t>& order, const std::string& path, const char* cls, Want&& want) {
+  const Reads& R = rc.R;
+  const auto& res = rc.res;
+  OutBuf fb;
+  if (!fb.open(path)) { diag("Fatal: unable to create '%s'", path.c_str()); return false; }
+  emit_rows(fb, rc.n(), rc.threads, [&](uint32_t k, std::string& s) {
+    const uint32_t i = order[k];
+    if (!want(res[i])) return;
+    const uint32_t ri = rc.rix(i);
+    const int L = R.len(ri);
+    s += ">lcl|"; s += cls; s += '|'; append_uint(s, (uint64_t)i + 1); s += ' '; s += R.name(ri); s += ' ';
+    append_uint(s, (uint64_t)i + 1); s += "|1|"; append_uint(s, (uint64_t)L); s += '\n';
+    const uint8_t* b = R.bases.data() + R.offs[ri];
+    for (int q = 0; q < L; ++q) {
+      uint8_t c = b[q] & 7;
+      s += c < 4 ? "ACGT"[c] : 'N';
+      if (q + 1 == L || (q + 1) % 70 == 0) s += '\n';
+    }
+  });
+  fb.close();
+  return true;
+}
+
+// ---- -O: WriteSubDist per reported alignment (Aligner.cpp:6275-6331), then WriteBasicCountStats (:4191-4332) and
+//      ReportTargHitCnts (:5475-5537): per read offset the bases seen and the aligner induced substitutions by Phred
+//      band of the 4-bit quality, the number of substitutions per alignment, alignments per target sequence.
+static void write_statistics(const Records& rc, const std::vector<uint32_t>& multi_dist, FILE* stats_fp) {
+  const Opts& o = rc.o;
+  const Reads& R = rc.R;
+  const auto& res = rc.res;
+  const auto& ents = rc.ents;
+  const auto& genome = rc.genome;
+  const uint32_t nrec = rc.n(), num_entries = (uint32_t)ents.size() - 1;
+  uint32_t max_len = 0;
+  uint64_t n_acc = 0;
+  for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) { ++n_acc; max_len = std::max<uint32_t>(max_len, (uint32_t)R.len(rc.rix(i))); }
+  if (o.fmt == 4) max_len = 0;   // the BED branch of WriteReadHits never reaches WriteSubDist (Aligner.cpp:6448-6556): nothing beyond the histogram
+  if (n_acc && max_len) {
+    diag("Writing out basic count stats to file");
+    std::vector<uint32_t> qinst(4 * (size_t)max_len, 0), qsubs(4 * (size_t)max_len, 0), msub((size_t)max_len + 1, 0), per_chrom(num_entries + 1, 0);
+    for (uint32_t i = 0; i < nrec; ++i) {
+      const bkx_read_result& r = res[i];
+      if (r.nar != BKX_NAR_ACCEPTED || r.chrom_id == 0) continue;
+      ++per_chrom[r.chrom_id];
+      const uint32_t ri = rc.rix(i), L = (uint32_t)R.len(ri), start = rc.adj_start(i), alen = rc.adj_len(i);
+      const uint8_t* b = R.bases.data() + R.offs[ri];
+      const uint8_t* g = genome[r.chrom_id].data() + start;
+      uint32_t subs = 0;
+      for (uint32_t q = rc.tleft(i), k = 0; q < L - rc.tright(i); ++q, ++k) {
+        const unsigned q4 = (b[q] >> 4) & 0x0f, band = q4 <= 3 ? 0 : q4 <= 7 ? 1 : q4 <= 11 ? 2 : 3;
+        uint8_t t = r.strand == '-' ? g[alen - 1 - k] & 7 : g[k] & 7;
+        if (r.strand == '-' && t < 4) t = 3 - t;
+        ++qinst[band * (size_t)max_len + q];
+        if ((b[q] & 7) != t) { ++qsubs[band * (size_t)max_len + q]; ++subs; }
+      }
+      ++msub[std::min<uint32_t>(subs, max_len)];
+    }
+    std::string s;
+    auto row = [&](const char* label, auto&& value, uint32_t cnt) {
+      s += label;
+      for (uint32_t k = 0; k < cnt; ++k) { s += ','; append_uint(s, value(k)); }
+    };
+    if (o.ml_mode != BKX_ML_DEFAULT) {
+      row("\"Multihit distribution\",", [](uint32_t k) { return (uint64_t)k + 1; }, (uint32_t)o.max_ml);
+      row("\n,\"Instances\"", [&](uint32_t k) { return (uint64_t)multi_dist[k]; }, (uint32_t)o.max_ml);
+      s += '\n';
+    }
+    static const char* kInstBand[4] = {"\n,\"Phred 0..9\"", "\n,\"Phred 10..19\"", "\n,\"Phred 20..29\"", "\n,\"Phred 30+\""};
+    static const char* kSubsBand[4] = {"\n,\"Phred 0..8\"", "\n,\"Phred 9..19\"", "\n,\"Phred 20..29\"", "\n,\"Phred 30+\""};
+    row("\"Phred Score Instances\",", [](uint32_t k) { return (uint64_t)k + 1; }, max_len);
+    for (int band = 0; band < 4; ++band) row(kInstBand[band], [&](uint32_t k) { return (uint64_t)qinst[band * (size_t)max_len + k]; }, max_len);
+    row("\n\n\"Aligner Induced Subs\",", [](uint32_t k) { return (uint64_t)k + 1; }, max_len);
+    for (int band = 0; band < 4; ++band) row(kSubsBand[band], [&](uint32_t k) { return (uint64_t)qsubs[band * (size_t)max_len + k]; }, max_len);
+    row("\n\n\"Multiple substitutions\",", [](uint32_t k) { return (uint64_t)k; }, max_len);
+    row("\n,\"Instances\"", [&](uint32_t k) { return (uint64_t)msub[k]; }, max_len);
+    s += '\n';
+    diag("Reporting accepted read alignment counts on to targeted transcripts or sequences, sorting reads");
+    diag("Completed sort");
+    s += "\"TargSeq\",\"TargLen\",\"NumHits\"\n";
+    int n_targ = 0;
+    for (uint32_t e = 1; e <= num_entries; ++e)
+      if (per_chrom[e]) {
+        s += '"'; s += ents[e].name; s += "\","; append_uint(s, ents[e].seq_len); s += ','; append_uint(s, per_chrom[e]); s += '\n';
+        ++n_targ;
+      }
+    fwrite(s.data(), 1, s.size(), stats_fp);
+    diag("Completed reporting read alignment counts on to %d targeted transcripts or sequences", n_targ);
+  }
+}
+
 int main(int argc, char** argv) {
   Opts o;
   int pr = parse(argc, argv, o);
@@ -1316,7 +1731,6 @@ int main(int argc, char** argv) {
     std::vector<bkx_multi_hit>().swap(multi);
   }
   const uint32_t nrec = (uint32_t)res.size();
-  auto rix = [&](uint32_t i) -> uint32_t { return src.empty() ? i : src[i]; };
 
   // ---- -r3 / -r4: AssignMultiMatches, Aligner.cpp:583-592, 5108-5270
   if (clustered) {
@@ -1392,11 +1806,6 @@ int main(int argc, char** argv) {
   const auto& trim_r = rc.trim_r;
   const uint32_t elim_plus = rc.elim_plus, elim_minus = rc.elim_minus;
   uint32_t num_trimmed = 0;
-  auto tleft = [&](uint32_t i) { return rc.tleft(i); };
-  auto tright = [&](uint32_t i) { return rc.tright(i); };
-  auto adj_start = [&](uint32_t i) { return rc.adj_start(i); };
-  auto adj_len = [&](uint32_t i) { return rc.adj_len(i); };
-  auto adj_mm = [&](uint32_t i) { return rc.adj_mm(i); };
 
   // "were trimmed" of the summary: FlagTR of the alignments still accepted at this point (Aligner.cpp:3558)
   if (!trim_l.empty())
@@ -1408,40 +1817,19 @@ int main(int argc, char** argv) {
     std::vector<bkx_read_result> keyed;
     if (!trim_l.empty()) {
       keyed = res;
-      for (uint32_t i = 0; i < nrec; ++i) { keyed[i].match_loci = adj_start(i); keyed[i].match_len = (uint16_t)adj_len(i); }
+      for (uint32_t i = 0; i < nrec; ++i) { keyed[i].match_loci = rc.adj_start(i); keyed[i].match_len = (uint16_t)rc.adj_len(i); }
     }
     if (nrec && bkx_sort_hits(keyed.empty() ? res.data() : keyed.data(), nrec, order.data(), 0) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
   }
 
-  // ---- -j / -J: ReportNoneAligned / ReportMultiAlign, Aligner.cpp:3826-4016 -- FASTA, 70 columns, in hit order
-  auto report_reads = [&](const std::string& path, const char* cls, auto&& want) -> bool {
-    OutBuf fb;
-    if (!fb.open(path)) { diag("Fatal: unable to create '%s'", path.c_str()); return false; }
-    emit_rows(fb, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
-      const uint32_t i = order[k];
-      if (!want(res[i])) return;
-      const uint32_t ri = rix(i);
-      const int L = R.len(ri);
-      s += ">lcl|"; s += cls; s += '|'; append_uint(s, (uint64_t)i + 1); s += ' '; s += R.name(ri); s += ' ';
-      append_uint(s, (uint64_t)i + 1); s += "|1|"; append_uint(s, (uint64_t)L); s += '\n';
-      const uint8_t* b = R.bases.data() + R.offs[ri];
-      for (int q = 0; q < L; ++q) {
-        uint8_t c = b[q] & 7;
-        s += c < 4 ? "ACGT"[c] : 'N';
-        if (q + 1 == L || (q + 1) % 70 == 0) s += '\n';
-      }
-    });
-    fb.close();
-    return true;
-  };
   if (!o.none_file.empty()) {
     diag("Reporting of non-aligned reads started..");
-    if (!report_reads(o.none_file, "na", [](const bkx_read_result& r) { return r.nar == BKX_NAR_NS || r.nar == BKX_NAR_NOHIT; })) return 1;
+    if (!report_reads(rc, order, o.none_file, "na", [](const bkx_read_result& r) { return r.nar == BKX_NAR_NS || r.nar == BKX_NAR_NOHIT; })) return 1;
     diag("Reporting of non-aligned reads completed");
   }
   if (!o.multi_file.empty()) {
     diag("Reporting of multialigned reads started..");
-    if (!report_reads(o.multi_file, "ml", [](const bkx_read_result& r) { return r.nar == BKX_NAR_MULTIALIGN; })) return 1;
+    if (!report_reads(rc, order, o.multi_file, "ml", [](const bkx_read_result& r) { return r.nar == BKX_NAR_MULTIALIGN; })) return 1;
     diag("Reporting of multialigned reads completed");
   }
 
@@ -1476,337 +1864,15 @@ int main(int argc, char** argv) {
   OutBuf ob;
   if (!ob.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
   diag("Reporting of aligned result set started...");
-  static const char kAsc[] = "ACGTN";
-  if (o.fmt == 4) {
-    // UCSC BED: track line then chrom, start, end+1, "ar", score, strand (Aligner.cpp:6355-6362, 6463-6466)
-    const char* title = o.title.empty() ? "kanga" : o.title.c_str();
-    // under -r5 the reference writes the track line twice: when it creates the file and when it reports (Aligner.cpp:4405, 6358)
-    for (int rep = 0; rep < (all_loci ? 2 : 1); ++rep) { ob.s += "track type=bed name=\""; ob.s += title; ob.s += "\" description=\""; ob.s += title; ob.s += "\"\n"; }
-    emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
-      uint32_t i = order[k];
-      const bkx_read_result& r = res[i];
-      if (r.nar != BKX_NAR_ACCEPTED) return;
-      s += ents[r.chrom_id].name; s += '\t';
-      append_uint(s, adj_start(i)); s += '\t';
-      append_uint(s, (uint64_t)adj_start(i) + adj_len(i)); s += "\tar\t0\t"; s += (char)r.strand; s += '\n';
-    });
-  } else if (o.fmt <= 3) {
-    // ReadID,"ar","species","chrom",start,end,len,"strand",score,0,NumReads,TrimMismatches,"N/A","descriptor"
-    // -M2/-M3 append the read sequence, -M1/-M3 the matched genome sequence in read orientation (Aligner.cpp:6612-6621)
-    emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
-      uint32_t i = order[k];
-      const bkx_read_result& r = res[i];
-      if (r.nar != BKX_NAR_ACCEPTED) return;
-      append_uint(s, (uint64_t)i + 1);
-      s += ",\"ar\",\""; s += info.dataset_name; s += "\",\""; s += ents[r.chrom_id].name; s += "\",";
-      const uint32_t start = adj_start(i), alen = adj_len(i);   // the alignment as trimmed by -x, if at all
-      append_uint(s, start); s += ',';
-      append_uint(s, (uint64_t)start + alen - 1); s += ',';
-      append_uint(s, alen); s += ",\""; s += (char)r.strand; s += "\",0,0,1,";
-      const uint32_t ri = rix(i);
-      append_uint(s, adj_mm(i)); s += ",\"N/A\",\""; s += R.name(ri); s += '"';
-      if (o.fmt >= 2) {
-        s += ",\"";
-        const uint8_t* b = R.bases.data() + R.offs[ri] + tleft(i);
-        for (uint32_t q = 0; q < alen; ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
-        s += '"';
-      }
-      if (o.fmt == 1 || o.fmt == 3) {
-        s += ",\"";
-        const uint8_t* g = genome[r.chrom_id].data() + start;
-        if (r.strand == '-') for (int q = (int)alen - 1; q >= 0; --q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
-        else for (uint32_t q = 0; q < alen; ++q) { uint8_t c = g[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
-        s += '"';
-      }
-      s += '\n';
-    });
-  } else if (is_bam_name(o.out)) {
-    // ---- BAM + BAI (same record content as the SAM branch below, binary form)
-    ob.close();
-    Bgzf bz;
-    if (!bz.open(o.out)) { diag("Fatal: unable to create '%s'", o.out.c_str()); return 1; }
-    std::vector<char> hit(info.num_entries + 1, 0);
-    for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
-    bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
-    std::vector<int> refid(info.num_entries + 1, -1);
-    std::string text = "@HD\tVN:1.4\tSO:coordinate", refs;
-    uint32_t nref = 0;
-    for (uint32_t e = 1; e <= info.num_entries; ++e)
-      if (all || hit[e]) {
-        text += "\n@SQ\tAS:"; text += info.dataset_name; text += "\tSN:"; text += ents[e].name; text += "\tLN:";
-        append_uint(text, ents[e].seq_len);
-        refid[e] = (int)nref++;
-        uint32_t ln = (uint32_t)strlen(ents[e].name) + 1, sl = ents[e].seq_len;
-        refs.append((const char*)&ln, 4); refs.append(ents[e].name, ln); refs.append((const char*)&sl, 4);
-      }
-    text += "\n@PG\tID:biokanga\tVN:4.4.2\n";
-    std::string hdr = "BAM\1";
-    uint32_t lt = (uint32_t)text.size();
-    hdr.append((const char*)&lt, 4); hdr += text; hdr.append((const char*)&nref, 4); hdr += refs;
-    // The whole uncompressed BAM stream is laid out first (record sizes -> offsets -> records written in place by all
-    // threads), then cut into BGZF blocks exactly where the reference's sequential writer cuts them (every 0xff00
-    // bytes, plus once behind the last aligned record), the blocks are deflated in parallel and written in order; the
-    // BAI follows from the record offsets and the block addresses.
-    BaiBuilder bai;
-    bai.out = "BAI\1";
-    bai.put32(nref);
-    struct RecMeta { uint64_t uofs; uint32_t len; int32_t rid, pos; int32_t L, alen; uint8_t acc, lead, trail; };
-    std::vector<RecMeta> meta;
-    meta.reserve(nrec);
-    uint64_t utotal = hdr.size();
-    for (uint32_t k = 0; k < nrec; ++k) {
-      uint32_t i = order[k];
-      const bkx_read_result& r = res[i];
-      bool acc = r.nar == BKX_NAR_ACCEPTED;
-      if (!acc && o.fmt != 6) continue;
-      const uint32_t ri = rix(i);
-      const int L = R.len(ri);
-      uint32_t lname = (uint32_t)strlen(R.name(ri)) + 1;
-      // -x trims become soft clips either side of the M operation (Aligner.cpp:5960-5985)
-      const uint32_t lead = !acc ? 0u : r.strand == '+' ? tleft(i) : tright(i), trail = !acc ? 0u : r.strand == '+' ? tright(i) : tleft(i);
-      const uint32_t ncig = 1 + (lead ? 1 : 0) + (trail ? 1 : 0);
-      uint32_t len = 4 + 32 + lname + 4 * ncig + (uint32_t)((L + 1) / 2) + (uint32_t)L + (acc ? 0u : 6u);
-      meta.push_back({utotal, len, acc ? refid[r.chrom_id] : -1, acc ? (int32_t)adj_start(i) : -1, L, acc ? (int32_t)adj_len(i) : L,
-                      (uint8_t)acc, (uint8_t)lead, (uint8_t)trail});
-      utotal += len;
-    }
-    std::vector<uint8_t> U(utotal);
-    memcpy(U.data(), hdr.data(), hdr.size());
-    // record k' (index into meta) <- sorted record; meta and the sorted walk advance together
-    std::vector<uint32_t> kept;
-    kept.reserve(meta.size());
-    for (uint32_t k = 0; k < nrec; ++k) {
-      const bkx_read_result& r = res[order[k]];
-      if (r.nar == BKX_NAR_ACCEPTED || o.fmt == 6) kept.push_back(order[k]);
-    }
-    auto write_record = [&](size_t mi) {
-      const uint32_t i = kept[mi];
-      const RecMeta& M = meta[mi];
-      const bkx_read_result& r = res[i];
-      const bool acc = M.acc != 0;
-      int flags = 0, tlen = 0;
-      long pnext = -1;
-      if (!o.pe_mode) flags = acc ? (r.strand == '+' ? 0 : 0x10) : 0x04;
-      else {
-        bool pe2 = i & 1;
-        const bkx_read_result& m = res[pe2 ? i - 1 : i + 1];
-        flags = 0x01 | 0x02 | (pe2 ? 0x80 : 0x40);
-        if (acc) flags |= r.strand == '+' ? 0 : 0x10; else flags |= 0x04;
-        bool both = (r.flags & BKX_FLG_PE_ALIGNED) && (m.flags & BKX_FLG_PE_ALIGNED) && m.nar == BKX_NAR_ACCEPTED;
-        if (both) {
-          flags |= m.strand == '+' ? 0 : 0x20;
-          if (acc) {
-            const uint32_t mi2 = pe2 ? i - 1 : i + 1;   // both alignments as trimmed by -x, if at all
-            long se = adj_start(i), pes = adj_start(mi2);
-            tlen = se <= pes ? (int)(pes - se) + (int)adj_len(mi2) : (int)(se - pes) + (int)adj_len(i);
-            pnext = pes;
-          }
-        } else flags |= 0x08;
-      }
-      const uint32_t ri = rix(i);
-      const int L = M.L;
-      const uint8_t* b = R.bases.data() + R.offs[ri];
-      const char* qn = R.name(ri);
-      uint32_t lname = (uint32_t)strlen(qn) + 1;
-      int32_t rid = M.rid, pos = M.pos;
-      const uint32_t ncig = 1 + (M.lead ? 1 : 0) + (M.trail ? 1 : 0);
-      uint32_t bin = acc ? (uint32_t)bai_reg2bin(pos, pos + M.alen) : 0;
-      uint32_t bmn = bin << 16 | 255u << 8 | lname, fnc = (uint32_t)flags << 16 | ncig;
-      int32_t nrid = (acc && pnext >= 0) ? rid : -1, npos = acc ? (int32_t)pnext : -1, tl = acc ? tlen : 0, lseq = L;
-      uint32_t cigar = (uint32_t)M.alen << 4, clip_lead = (uint32_t)M.lead << 4 | 4u, clip_trail = (uint32_t)M.trail << 4 | 4u;
-      uint8_t* w = U.data() + M.uofs;
-      uint32_t bsz = M.len - 4;
-      auto p32 = [&](const void* v) { memcpy(w, v, 4); w += 4; };
-      p32(&bsz); p32(&rid); p32(&pos); p32(&bmn); p32(&fnc); p32(&lseq); p32(&nrid); p32(&npos); p32(&tl);
-      memcpy(w, qn, lname); w += lname;
-      if (M.lead) p32(&clip_lead);
-      p32(&cigar);
-      if (M.trail) p32(&clip_trail);
-      bool rc = acc && r.strand != '+';
-      for (int q = 0; q < L; q += 2) {
-        auto nib = [&](int idx) -> unsigned {
-          if (idx >= L) return 0u;
-          uint8_t c = b[rc ? L - 1 - idx : idx] & 7;
-          if (c < 4) { if (rc) c = 3 - c; return 1u << c; }
-          return 15u;
-        };
-        *w++ = (uint8_t)(nib(q) << 4 | nib(q + 1));
-      }
-      int sumq = 0;
-      for (int q = 0; q < L; ++q) sumq += (b[q] >> 4) & 0x0f;
-      if (sumq == 0) { memset(w, 0xff, (size_t)L); w += L; }
-      else for (int q = 0; q < L; ++q) *w++ = (uint8_t)(33 + (((b[rc ? L - 1 - q : q] >> 4) & 0x0f) * 40) / 15);
-      if (!acc) { memcpy(w, "YUZ", 3); w += 3; memcpy(w, kNarCode[r.nar], 2); w += 2; *w++ = 0; }
-    };
-    {
-      std::vector<std::thread> th;
-      for (unsigned t = 0; t < fmt_threads; ++t)
-        th.emplace_back([&, t]() {
-          size_t b0 = meta.size() * t / fmt_threads, e0 = meta.size() * (t + 1) / fmt_threads;
-          for (size_t mi = b0; mi < e0; ++mi) write_record(mi);
-        });
-      for (auto& x : th) x.join();
-    }
-    // explicit flush behind the last aligned record (bLastAligned, SAMfile.cpp), if any
-    uint64_t flush_at = 0;
-    bool have_flush = false;
-    for (size_t mi = meta.size(); mi-- > 0;)
-      if (meta[mi].acc) { flush_at = meta[mi].uofs + meta[mi].len; have_flush = true; break; }
-    bool ok = bz.write_stream(U.data(), U.size(), have_flush ? &flush_at : nullptr, fmt_threads);
-    // BAI bins end at 512 Mbp.  For longer reference sequences the reference switches to a CSI index (SAMfile.cpp:1602-1622)
-    // but never opens that file -- the branch that would (:1664) hangs off `if (type >= BAI)` and is unreachable -- so its
-    // first index flush fails (WriteIdxToDisk, :1812).  Here the BAM is written complete and the index is left to
-    // `samtools index -c`, with a note in the log, rather than an index with overflowing bins.
-    uint32_t longest_ref = 0;
-    for (uint32_t e = 1; e <= info.num_entries; ++e) if (refid[e] >= 0) longest_ref = std::max(longest_ref, ents[e].seq_len);
-    const bool write_bai = longest_ref < 0x20000000u;
-    if (!write_bai) diag("Note: reference sequences of 512Mbp or more (max %u): no BAI index written for '%s', index it with a CSI indexer", longest_ref, o.out.c_str());
-    int cur_ref = -1;  // reference whose index block is being accumulated
-    for (size_t mi = 0; mi < meta.size() && ok && write_bai; ++mi) {
-      const RecMeta& M = meta[mi];
-      if (!M.acc) continue;
-      while (cur_ref < M.rid) { if (cur_ref >= 0) bai.end_ref(); ++cur_ref; }
-      bai.add(bz.vaddr(M.uofs), (uint32_t)M.pos, bz.vaddr(M.uofs + M.len), (uint32_t)(M.pos + M.alen - 1));
-    }
-    bai.end_ref();  // Close(): the reference in progress (an empty block when nothing aligned)
-    ok = ok && bz.close();
-    if (write_bai) {
-      FILE* fb = fopen((o.out + ".bai").c_str(), "wb");
-      if (fb) { fwrite(bai.out.data(), 1, bai.out.size(), fb); fclose(fb); } else ok = false;
-    }
-    if (!ok) { diag("Fatal: write to '%s' failed", o.out.c_str()); return 1; }
-  } else {
-    // SAM header: @HD, @SQ for every chromosome (or only those hit if more than -4 threshold), @PG
-    std::vector<char> hit(info.num_entries + 1, 0);
-    for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) hit[res[i].chrom_id] = 1;
-    bool all = (uint32_t)o.sam_seq_thres >= info.num_entries;
-    ob.s += "@HD\tVN:1.4\tSO:coordinate\n";
-    for (uint32_t e = 1; e <= info.num_entries; ++e)
-      if (all || hit[e]) {
-        ob.s += "@SQ\tAS:"; ob.s += info.dataset_name; ob.s += "\tSN:"; ob.s += ents[e].name; ob.s += "\tLN:";
-        append_uint(ob.s, ents[e].seq_len); ob.s += '\n';
-      }
-    ob.s += "@PG\tID:biokanga\tVN:4.4.2\n";
-    emit_rows(ob, nrec, fmt_threads, [&](uint32_t k, std::string& s) {
-      uint32_t i = order[k];
-      const bkx_read_result& r = res[i];
-      bool acc = r.nar == BKX_NAR_ACCEPTED;
-      if (!acc && o.fmt != 6) return;
-      int flags = 0, tlen = 0;
-      long pnext = -1;
-      if (!o.pe_mode) {
-        flags = acc ? (r.strand == '+' ? 0 : 0x10) : 0x04;
-      } else {  // ReportBAMread, Aligner.cpp:5864-5925
-        bool pe2 = i & 1;
-        const bkx_read_result& m = res[pe2 ? i - 1 : i + 1];
-        flags = 0x01 | 0x02 | (pe2 ? 0x80 : 0x40);
-        if (acc) flags |= r.strand == '+' ? 0 : 0x10; else flags |= 0x04;
-        bool both = (r.flags & BKX_FLG_PE_ALIGNED) && (m.flags & BKX_FLG_PE_ALIGNED) && m.nar == BKX_NAR_ACCEPTED;
-        if (both) {
-          flags |= m.strand == '+' ? 0 : 0x20;
-          if (acc) {
-            const uint32_t mi2 = pe2 ? i - 1 : i + 1;   // both alignments as trimmed by -x, if at all
-            long se = adj_start(i), pes = adj_start(mi2);
-            tlen = se <= pes ? (int)(pes - se) + (int)adj_len(mi2) : (int)(se - pes) + (int)adj_len(i);
-            pnext = pes;
-          }
-        } else flags |= 0x08;
-      }
-      const uint32_t ri = rix(i);
-      s += R.name(ri); s += '\t';
-      append_uint(s, (uint64_t)flags); s += '\t';
-      if (acc) { s += ents[r.chrom_id].name; s += '\t'; append_uint(s, (uint64_t)adj_start(i) + 1); }
-      else s += "*\t0";
-      s += "\t255\t";
-      if (acc) {  // flanks trimmed by -x are soft clipped, in reference orientation (Aligner.cpp:5960-5985)
-        const uint32_t lead = r.strand == '+' ? tleft(i) : tright(i), trail = r.strand == '+' ? tright(i) : tleft(i);
-        if (lead) { append_uint(s, lead); s += 'S'; }
-        append_uint(s, adj_len(i)); s += 'M';
-        if (trail) { append_uint(s, trail); s += 'S'; }
-        s += '\t';
-      } else { append_uint(s, (uint64_t)R.len(ri)); s += "M\t"; }
-      if (acc && pnext >= 0) { s += "=\t"; append_uint(s, (uint64_t)pnext + 1); s += '\t'; append_uint(s, (uint64_t)tlen); s += '\t'; }
-      else s += "*\t0\t0\t";
-      const uint8_t* b = R.bases.data() + R.offs[ri];
-      int L = R.len(ri);
-      if (acc && r.strand != '+') {
-        for (int q = L - 1; q >= 0; --q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[3 - c] : 'N'; }
-      } else {
-        for (int q = 0; q < L; ++q) { uint8_t c = b[q] & 7; s += c < 4 ? kAsc[c] : 'N'; }
-      }
-      // QUAL: '*' unless qualities were kept (-g0..2); 33 + q4*40/15, reversed with the sequence (Aligner.cpp:5929-5955)
-      int sumq = 0;
-      for (int q = 0; q < L; ++q) sumq += (b[q] >> 4) & 0x0f;
-      s += '\t';
-      if (sumq == 0) s += '*';
-      else if (acc && r.strand != '+') for (int q = L - 1; q >= 0; --q) s += (char)(33 + (((b[q] >> 4) & 0x0f) * 40) / 15);
-      else for (int q = 0; q < L; ++q) s += (char)(33 + (((b[q] >> 4) & 0x0f) * 40) / 15);
-      if (!acc) { s += "\t\tYU:Z:"; s += kNarCode[r.nar]; }
-      s += '\n';
-    });
-  }
+  if (o.fmt == 4) write_bed(rc, order, info, ob);
+  else if (o.fmt <= 3) write_csv(rc, order, info, ob);
+  else if (is_bam_name(o.out)) { if (!write_bam(rc, order, info, ob)) return 1; }
+  else write_sam(rc, order, info, ob);
   ob.close();
   diag("Reporting of aligned result set completed");
 
-  // ---- -O: WriteSubDist per reported alignment (Aligner.cpp:6275-6331), then WriteBasicCountStats (:4191-4332) and
-  //      ReportTargHitCnts (:5475-5537): per read offset the bases seen and the aligner induced substitutions by Phred
-  //      band of the 4-bit quality, the number of substitutions per alignment, alignments per target sequence.
   if (stats_fp) {
-    uint32_t max_len = 0;
-    uint64_t n_acc = 0;
-    for (uint32_t i = 0; i < nrec; ++i) if (res[i].nar == BKX_NAR_ACCEPTED) { ++n_acc; max_len = std::max<uint32_t>(max_len, (uint32_t)R.len(rix(i))); }
-    if (o.fmt == 4) max_len = 0;   // the BED branch of WriteReadHits never reaches WriteSubDist (Aligner.cpp:6448-6556): nothing beyond the histogram
-    if (n_acc && max_len) {
-      diag("Writing out basic count stats to file");
-      std::vector<uint32_t> qinst(4 * (size_t)max_len, 0), qsubs(4 * (size_t)max_len, 0), msub((size_t)max_len + 1, 0), per_chrom(info.num_entries + 1, 0);
-      for (uint32_t i = 0; i < nrec; ++i) {
-        const bkx_read_result& r = res[i];
-        if (r.nar != BKX_NAR_ACCEPTED || r.chrom_id == 0) continue;
-        ++per_chrom[r.chrom_id];
-        const uint32_t ri = rix(i), L = (uint32_t)R.len(ri), start = adj_start(i), alen = adj_len(i);
-        const uint8_t* b = R.bases.data() + R.offs[ri];
-        const uint8_t* g = genome[r.chrom_id].data() + start;
-        uint32_t subs = 0;
-        for (uint32_t q = tleft(i), k = 0; q < L - tright(i); ++q, ++k) {
-          const unsigned q4 = (b[q] >> 4) & 0x0f, band = q4 <= 3 ? 0 : q4 <= 7 ? 1 : q4 <= 11 ? 2 : 3;
-          uint8_t t = r.strand == '-' ? g[alen - 1 - k] & 7 : g[k] & 7;
-          if (r.strand == '-' && t < 4) t = 3 - t;
-          ++qinst[band * (size_t)max_len + q];
-          if ((b[q] & 7) != t) { ++qsubs[band * (size_t)max_len + q]; ++subs; }
-        }
-        ++msub[std::min<uint32_t>(subs, max_len)];
-      }
-      std::string s;
-      auto row = [&](const char* label, auto&& value, uint32_t cnt) {
-        s += label;
-        for (uint32_t k = 0; k < cnt; ++k) { s += ','; append_uint(s, value(k)); }
-      };
-      if (o.ml_mode != BKX_ML_DEFAULT) {
-        row("\"Multihit distribution\",", [](uint32_t k) { return (uint64_t)k + 1; }, (uint32_t)o.max_ml);
-        row("\n,\"Instances\"", [&](uint32_t k) { return (uint64_t)multi_dist[k]; }, (uint32_t)o.max_ml);
-        s += '\n';
-      }
-      static const char* kInstBand[4] = {"\n,\"Phred 0..9\"", "\n,\"Phred 10..19\"", "\n,\"Phred 20..29\"", "\n,\"Phred 30+\""};
-      static const char* kSubsBand[4] = {"\n,\"Phred 0..8\"", "\n,\"Phred 9..19\"", "\n,\"Phred 20..29\"", "\n,\"Phred 30+\""};
-      row("\"Phred Score Instances\",", [](uint32_t k) { return (uint64_t)k + 1; }, max_len);
-      for (int band = 0; band < 4; ++band) row(kInstBand[band], [&](uint32_t k) { return (uint64_t)qinst[band * (size_t)max_len + k]; }, max_len);
-      row("\n\n\"Aligner Induced Subs\",", [](uint32_t k) { return (uint64_t)k + 1; }, max_len);
-      for (int band = 0; band < 4; ++band) row(kSubsBand[band], [&](uint32_t k) { return (uint64_t)qsubs[band * (size_t)max_len + k]; }, max_len);
-      row("\n\n\"Multiple substitutions\",", [](uint32_t k) { return (uint64_t)k; }, max_len);
-      row("\n,\"Instances\"", [&](uint32_t k) { return (uint64_t)msub[k]; }, max_len);
-      s += '\n';
-      diag("Reporting accepted read alignment counts on to targeted transcripts or sequences, sorting reads");
-      diag("Completed sort");
-      s += "\"TargSeq\",\"TargLen\",\"NumHits\"\n";
-      int n_targ = 0;
-      for (uint32_t e = 1; e <= info.num_entries; ++e)
-        if (per_chrom[e]) {
-          s += '"'; s += ents[e].name; s += "\","; append_uint(s, ents[e].seq_len); s += ','; append_uint(s, per_chrom[e]); s += '\n';
-          ++n_targ;
-        }
-      fwrite(s.data(), 1, s.size(), stats_fp);
-      diag("Completed reporting read alignment counts on to %d targeted transcripts or sequences", n_targ);
-    }
+    write_statistics(rc, multi_dist, stats_fp);
     fclose(stats_fp);
   }
   for (auto* x : idx) bkx_close_index(x);
