@@ -113,6 +113,7 @@ struct Opts {
   bool clamp_ml = false;         // -X
   bool pair_strand = false, pe_circ = false;
   int sample_nth = 1;            // -#: sample every Nth raw read or read pair
+  int pcr_primer = 0;            // -6: align with -s + this many substitutions, then correct 5' primer artefacts back to -s
   int pcr_win = -1;              // -k: PCR artefact reduction window, -1 = off (kanga.cpp:719-724)
   int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
   std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
@@ -455,7 +456,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'j': o.none_file = v; break;
       case 'J': o.multi_file = v; break;
       case 'p': if (iv) unsupported.push_back("-p SNP calling"); break;
-      case '6': if (iv) unsupported.push_back("-6 PCR primer correction"); break;
+      case '6': o.pcr_primer = iv; break;
       case 'b': unsupported.push_back("-b bisulfite"); break;
       case 'C': unsupported.push_back("-C colorspace"); break;
       case 'N': unsupported.push_back("-N best matches"); break;
@@ -487,6 +488,12 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.pe_mode < 0 || o.pe_mode > 4) { fprintf(stderr, "Error: paired end mode '-U%d' must be in range 0..4\n", o.pe_mode); return -1; }
   if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
   if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
+  if (o.pcr_primer < 0 || o.pcr_primer > 5) { fprintf(stderr, "Error: PCR primer correction subs '-6%d' specified outside of range 0..5\n", o.pcr_primer); return -1; }  // kanga.cpp:784-789
+  if (o.pcr_primer && o.pe_mode) {
+    // orphan recovery would have to take its mismatch limit from -s and its acceptance from -s plus -6 (Aligner.cpp:3256, 3275)
+    fprintf(stderr, "bkx-align: option -6 is not supported together with paired end processing '-U%d'\n", o.pe_mode);
+    return -1;
+  }
   if (o.min_flank < 0 || o.min_flank > 7) { fprintf(stderr, "Error: Max flank trimming '-x%d' specified outside of range 0..7\n", o.min_flank); return -1; }  // kanga.cpp:804-808
   if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
@@ -506,6 +513,10 @@ static int parse(int argc, char** argv, Opts& o) {
     if (o.ml_mode == 5 && o.fmt == 6 && (!o.excl.empty() || !o.incl.empty())) {
       // the reference then turns reads whose loci were all filtered into accepted records without a locus (WriteHitLoci, Aligner.cpp:6755-6771)
       fprintf(stderr, "bkx-align: options -Z / -z are not supported together with '-r5' in output format '-M6'\n");
+      return -1;
+    }
+    if (o.ml_mode == 5 && o.pcr_primer) {   // there every record owns a copy of its read; here the loci of a read share one
+      fprintf(stderr, "bkx-align: option -6 is not supported together with '-r5'\n");
       return -1;
     }
     if (o.ml_mode == 5 && !(o.fmt == 0 || o.fmt == 4 || o.fmt == 5 || o.fmt == 6)) {  // kanga.cpp:830
@@ -861,7 +872,7 @@ static int load_constraints(const std::string& path, const std::vector<bkx_entry
 // ---- what the post-alignment passes and the writers share about a run ----------------------------------
 struct Records {
   const Opts& o;
-  const Reads& R;
+  Reads& R;                                          // -6 rewrites read bases
   std::vector<bkx_read_result>& res;                 // one per record: per read, or per reported locus under -r5
   const std::vector<uint32_t>& src;                  // record -> read (empty: identity)
   const std::vector<bkx_entry>& ents;                // [1 .. num_entries]
@@ -1008,6 +1019,50 @@ static int reduce_pcr_duplicates(Records& rc) {
   return 0;
 }
 
+// ---- -6: PCR5PrimerCorrect, Aligner.cpp:1996-2107.  The search ran with -s raised by -6; an accepted alignment with more
+//      mismatches than -s allows is kept only if replacing mismatching bases among the first 12 of the read by the
+//      target's (5' random-primer artefacts) brings it within -s: the read is rewritten and LowMMCnt / Mismatches
+//      lowered; otherwise it becomes eNARNoHit.  Seg[0].TrimMismatches -- what the CSV reports -- keeps its value.
+static void pcr_5prime_correct(Records& rc) {
+  const Opts& o = rc.o;
+  auto& res = rc.res;
+  const uint32_t nrec = rc.n();
+  const int KLen = 12;
+  diag("Starting PCR 5' %dbp primer correction processing targeting substitution rate of %d ...", KLen, o.max_subs);
+  rc.trim_mm.resize(nrec);
+  for (uint32_t i = 0; i < nrec; ++i) rc.trim_mm[i] = res[i].mismatches;
+  int reads_fixed = 0, bases_fixed = 0, rejected = 0;
+  for (uint32_t i = 0; i < nrec; ++i) {
+    bkx_read_result& r = res[i];
+    if (r.nar != BKX_NAR_ACCEPTED) continue;
+    const uint32_t ri = rc.rix(i);
+    const int L = rc.R.len(ri), max_mm = (o.max_subs * L + 50) / 100;
+    if (r.low_mm <= max_mm || r.match_len != L) continue;
+    uint8_t* b = rc.R.bases.data() + rc.R.offs[ri];
+    const uint8_t* g = rc.genome[r.chrom_id].data() + r.match_loci;
+    auto targ = [&](int q) -> uint8_t {
+      if (r.strand != '-') return g[q];
+      const uint8_t c = g[L - 1 - q];
+      return c < 4 ? (uint8_t)(3 - c) : c;
+    };
+    int cur = r.low_mm;
+    for (int q = 0; q < KLen && q < L; ++q)
+      if ((b[q] & 7) != targ(q) && --cur <= max_mm) break;
+    if (cur > max_mm) { r.num_hits = 0; r.nar = BKX_NAR_NOHIT; ++rejected; continue; }
+    cur = r.low_mm;
+    for (int q = 0; q < KLen && q < L; ++q)
+      if ((b[q] & 7) != targ(q)) {
+        b[q] = (uint8_t)((b[q] & 0xf8) | targ(q));
+        ++bases_fixed;
+        if (--cur <= max_mm) break;
+      }
+    r.low_mm = (int8_t)cur;
+    r.mismatches = (uint8_t)cur;
+    ++reads_fixed;
+  }
+  diag("Completed PCR 5' primer correction, %d reads with %d bases corrected, %d reads with excessive substitutions rejected", reads_fixed, bases_fixed, rejected);
+}
+
 // ---- -x: AutoTrimFlanks, Aligner.cpp:1608-1812.  Each accepted alignment is cut back from both ends to the first run
 //      of MinFlankExacts matching bases; the rest must keep at least half the read (>= 15 bp) or the read is sloughed
 //      as eNARTrim.  In paired-end runs the 5' scan stays inside the first third of the read and the 3' scan inside
@@ -1024,7 +1079,9 @@ static void auto_trim_flanks(Records& rc) {
   const unsigned fmt_threads = rc.threads;
   diag("Autotrim aligned read flank processing started..");
   diag("Starting 5' and 3' flank sequence autotrim processing...");
-  trim_l.assign(nrec, 0); trim_r.assign(nrec, 0); trim_mm.assign(nrec, 0);
+  trim_l.assign(nrec, 0); trim_r.assign(nrec, 0);
+  const bool fresh_mm = trim_mm.empty();   // after -6 TrimMismatches already holds the count from before the correction
+  if (fresh_mm) trim_mm.assign(nrec, 0);
   std::vector<uint32_t> ep(fmt_threads, 0), em(fmt_threads, 0);
   std::vector<std::thread> th;
   for (unsigned t = 0; t < fmt_threads; ++t)
@@ -1033,7 +1090,7 @@ static void auto_trim_flanks(Records& rc) {
       const uint32_t b0 = (uint32_t)((uint64_t)nrec * t / fmt_threads), e0 = (uint32_t)((uint64_t)nrec * (t + 1) / fmt_threads);
       for (uint32_t i = b0; i < e0; ++i) {
         bkx_read_result& r = res[i];
-        trim_mm[i] = r.mismatches;
+        if (fresh_mm) trim_mm[i] = r.mismatches;
         if (r.nar != BKX_NAR_ACCEPTED) continue;
         const int L = r.match_len, minlen = std::max(15, (L + 1) / 2), X = o.min_flank;
         const uint8_t* b = R.bases.data() + R.offs[rc.rix(i)];
@@ -1561,7 +1618,8 @@ int main(int argc, char** argv) {
   diag("Genome Assembly Name: '%s' Descr: '%s' Title: '%s' Version: %d", info.dataset_name, info.dataset_name, info.dataset_name, info.version);
   bkx_align_params P;
   if (bkx_default_params(idx[0], o.pmode, &P) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
-  P.max_subs = o.max_subs; P.min_edit_dist = o.edit_delta; P.max_ns = o.max_ns; P.align_strand = o.strand;
+  const int align_subs = o.pcr_primer > 0 ? std::min(o.max_subs + o.pcr_primer, 15) : o.max_subs;   // m_InitalAlignSubs, Aligner.cpp:208-213
+  P.max_subs = align_subs; P.min_edit_dist = o.edit_delta; P.max_ns = o.max_ns; P.align_strand = o.strand;
   P.ml_mode = o.ml_mode; P.max_ml_matches = o.max_ml; P.clamp_max_ml = o.clamp_ml ? 1 : 0;
 
   std::vector<bkx_entry> ents(info.num_entries + 1);
@@ -1677,9 +1735,9 @@ int main(int argc, char** argv) {
   for (uint32_t i = 1; i < n; ++i) { minl = std::min(minl, R.len(i)); maxl = std::max(maxl, R.len(i)); }
   int avl = (int)(tot_len / n);
   diag("Average length of all reads was: %d (min: %d, max: %d)", avl, minl, maxl);
-  if (o.max_subs != 0)
-    diag("Typical allowed aligner induced substitutions was: %d (min: %d, max: %d)", std::max(1, avl * o.max_subs / 100),
-         std::max(1, minl * o.max_subs / 100), std::max(1, maxl * o.max_subs / 100));
+  if (align_subs != 0)
+    diag("Typical allowed aligner induced substitutions was: %d (min: %d, max: %d)", std::max(1, avl * align_subs / 100),
+         std::max(1, minl * align_subs / 100), std::max(1, maxl * align_subs / 100));
   diag("Provisionally accepted %d aligned reads (%d uniquely, %d aligning to multiloci) aligning to a total of %d loci",
        (int)S.tot_accepted_aligned, (int)S.tot_accepted_unique, (int)S.tot_accepted_multi, (int)S.tot_loci_aligned);
 
@@ -1788,7 +1846,7 @@ int main(int argc, char** argv) {
   unsigned fmt_threads = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   // host copy of the chromosomes (1 byte/base) for the passes and writers that compare with / print the target sequence
   std::vector<std::vector<uint8_t>> genome(info.num_entries + 1);
-  bool need_genome = o.fmt == 1 || o.fmt == 3 || o.min_flank > 0 || stats_fp;
+  bool need_genome = o.fmt == 1 || o.fmt == 3 || o.min_flank > 0 || o.pcr_primer > 0 || stats_fp;
   for (auto& c : constraints) need_genome = need_genome || (c.mask & 0x10);
   if (need_genome)
     for (uint32_t e = 1; e <= info.num_entries; ++e) {
@@ -1800,6 +1858,11 @@ int main(int argc, char** argv) {
   // the passes, in the order of CAligner::Align (Aligner.cpp:596-655)
   if (!constraints.empty()) identify_constraint_violations(rc, constraints);
   if (o.pcr_win >= 0 && !o.pe_mode && reduce_pcr_duplicates(rc) < 0) return 1;
+  if (o.pcr_primer > 0) {
+    diag("PCR 5' Primer correction processing started..");
+    pcr_5prime_correct(rc);
+    diag("PCR 5' Primer correction processing completed");
+  }
   if (o.min_flank > 0) auto_trim_flanks(rc);
   if (!o.excl.empty() || !o.incl.empty()) filter_by_chroms(rc, rin, rex);
   const auto& trim_l = rc.trim_l;

@@ -450,6 +450,8 @@ def case_sample():
         # ... and the paired-end form of the -x flank trimming (scans kept inside the outer thirds, nothing sloughed)
         for tag, reads, args, out in (("s7", ["r100.fa"], ["-s3", "-M0", "-#7"], "s7.csv"),
                                       ("s3pe", ["pe1.fa", "pe2.fa"], ["-s3", "-M6", "-U1", "-D600", "-#3"], "s3pe.sam"),
+                                      ("p6", ["r100.fa"], ["-s2", "-M0", "-63"], "p6.csv"),          # -6: 5' primer artefact correction
+                                      ("p6sam", ["r100.fa"], ["-s2", "-M6", "-63", "-x3", "-k0"], "p6.sam"),
                                       ("pex0", ["pe1.fa", "pe2.fa"], ["-s5", "-M0", "-U1", "-D600", "-x5"], "pex0.csv"),
                                       ("pex6", ["pe1.fa", "pe2.fa"], ["-s5", "-M6", "-U3", "-D500", "-x7", "-#2"], "pex6.sam")):
             run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)
