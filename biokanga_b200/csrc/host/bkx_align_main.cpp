@@ -11,13 +11,17 @@
 //   SAM records       WriteBAMReadHits / ReportBAMread    Aligner.cpp:5543-5725, 5768-6126
 //                     CSAMfile::AddAlignment (text form)  libbiokanga/SAMfile.cpp:2100-2262
 //   summary           CAligner::ReportAlignStats          Aligner.cpp:3493-3822
-//   post-alignment    AutoTrimFlanks (-x)                 Aligner.cpp:1608-1812
+//   post-alignment    IdentifyConstraintViolations (-5)   Aligner.cpp:1245-1441, 2480-2647
+//                     ReducePCRduplicates (-k)            Aligner.cpp:2184-2282
+//                     PCR5PrimerCorrect (-6)              Aligner.cpp:1996-2107
+//                     AutoTrimFlanks (-x)                 Aligner.cpp:1608-1812
 //                     FiltByChroms (-Z / -z)              Aligner.cpp:4019-4124, 4736-4798
 //                     ReportNoneAligned / ReportMultiAlign (-j / -J)   Aligner.cpp:3826-4016
+//                     WriteSubDist / WriteBasicCountStats / ReportTargHitCnts (-O)   Aligner.cpp:6275-6331, 4191-4332, 5475-5537
 // Written from the behaviour of those functions; no reference code is reused.  Options of the
 // reference that select paths outside SURVEY section 8 (-r2 random locus, -N best matches, -c chimeric, -a/-A indel
-// and splice, -p SNP calling, -k PCR dedup, -5 constraints, -H contaminants, -b/-C bisulfite/SOLiD) are recognised
-// and rejected with a clear message.  Output formats: CSV -M0..3, BED -M4, SAM -M5/-M6 (gzip when the name ends in
+// and splice, -p SNP calling, -B priority regions, -H contaminants, -b/-C bisulfite/SOLiD) are recognised and
+// rejected with a clear message.  Output formats: CSV -M0..3, BED -M4, SAM -M5/-M6 (gzip when the name ends in
 // .gz), BAM + BAI when the name ends in .bam (kanga.cpp:849-857).
 #include <algorithm>
 #include <chrono>
@@ -467,7 +471,7 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'q': unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'h':
         printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -M0..6 -g -t -U -d -D -E "
-               "-y -Y -l -L -x -Z -z -j -J -4 -T -i -u -I -o -F [--gpus N]\n");
+               "-y -Y -l -L -# -5 -k -6 -x -Z -z -j -J -O -4 -T -i -u -I -o -F [--gpus N]\n");
         return 1;
       default: break;  // remaining reference options have no effect on this path (-w -W -K -G -P -1 -9 -V -0 -3 -v)
     }
