@@ -569,7 +569,7 @@ def run_hexaploid(args):
                 host_sa = host_sa.reshape(-1)
             log("[bench] index copied to host in %.1fs" % (time.time() - tc))
             oidx = po.OracleIndex(seq=host_seq, sa=host_sa, el_size=el, entries=ents)
-            m = min(args.cpu_sample, nreads)
+            m = min(args.cpu_sample, 300000, nreads)   # the 14 G-symbol search is several times slower per read
             cores = os.cpu_count() or 1
             hb = h_bases.numpy()[:m * L]
             ho = np.arange(m + 1, dtype=np.uint64) * L
@@ -819,7 +819,8 @@ def main():
     ap.add_argument("--max-subs", type=int, default=3, help="-s: allowed substitutions per 100 bp")
     ap.add_argument("--prefix-k", type=int, default=0)
     ap.add_argument("--seed", type=int, default=20261017)
-    ap.add_argument("--cpu-sample", type=int, default=300000)
+    ap.add_argument("--cpu-sample", type=int, default=4000000,
+                    help="reads of the workload the CPU baseline aligns (about 10-30 s of host time on 16 cores at configs[1])")
     ap.add_argument("--ref-sample", type=int, default=4000000)
     ap.add_argument("--ref-port", action="store_true", help="reference arm: use the oracle port even if the binary exists")
     ap.add_argument("--no-cpu-baseline", action="store_true")
