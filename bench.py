@@ -176,7 +176,7 @@ def run_bkx(args):
     log("[bench] rank %d index resident: %.1f GB HBM, prefix k=%d, %.1fs" % (rank, idx.info.device_bytes / 1e9,
                                                                           idx.info.prefix_k, time.time() - t0))
     host_seq = host_sa = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         host_seq = d_seq.cpu().numpy()
         host_sa = d_sa.cpu().numpy().view(np.uint32)
     del d_seq, d_sa
@@ -341,7 +341,7 @@ def run_bkx(args):
         line["pe"] = {"pairs_per_gpu": nreads // 2, "accepted_pairs": int(pst[1]), "recovered_orphans": int(pst[3]),
                       "unaligned_pairs": int(pst[0]), "pairs_per_s": value / 2}
 
-    if rank == 0 and not args.no_cpu_baseline and not pe_mode:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not pe_mode:   # reported once: rank 0 of the single-GPU run
         line["cpu_baseline"] = cpu_baseline_port(args, host_seq, host_sa, ents, h_bases.numpy(), res)
     if rank == 0:
         print(json.dumps(line), flush=True)
