@@ -630,9 +630,18 @@ static int pe_insert_size(const bkx_pe_params* pe, uint8_t s1, uint32_t st1, uin
   return frag;
 }
 
-static int accept_prov_pe(const bkx_pe_params* pe, const bkx_read_result* f, const bkx_read_result* r) {
+/* keep: AcceptThisChromID per entry id (Aligner.cpp:2651-2710: exclude expressions first, then the include ones), NULL = no
+ * -Z / -z filters; -3 both ends on a filtered chromosome, -4 the 5' end, -5 the 3' end (:2771-2786). */
+static int accept_prov_pe(const bkx_pe_params* pe, const bkx_read_result* f, const bkx_read_result* r, const uint8_t* keep) {
   if (!(f->num_hits == 1 && r->num_hits == 1)) return 0;
-  if (f->chrom_id != r->chrom_id) return -2;
+  int bf = keep ? keep[f->chrom_id] : 1;
+  if (f->chrom_id != r->chrom_id) {
+    int br = keep ? keep[r->chrom_id] : 1;
+    if (br && bf) return -2;
+    if (!br && !bf) return -3;
+    return !bf ? -4 : -5;
+  }
+  if (!bf) return -3;
   return pe_insert_size(pe, f->strand, f->match_loci, f->match_loci + f->match_len - 1, r->strand, r->match_loci,
                         r->match_loci + r->match_len - 1);
 }
@@ -648,6 +657,12 @@ static int align_paired_read(const bko_index* x, const bkx_pe_params* pe, const 
 
 int bko_pair_reads(const bko_index* x, const bkx_align_params* p, const bkx_pe_params* pe, bkx_read_result* res,
                    uint32_t n_pairs, const uint8_t* bases, const uint64_t* offs, bkx_pe_stats* st, uint32_t* len_dist) {
+  return bko_pair_reads_filtered(x, p, pe, res, n_pairs, bases, offs, st, len_dist, NULL);
+}
+
+int bko_pair_reads_filtered(const bko_index* x, const bkx_align_params* p, const bkx_pe_params* pe, bkx_read_result* res,
+                            uint32_t n_pairs, const uint8_t* bases, const uint64_t* offs, bkx_pe_stats* st, uint32_t* len_dist,
+                            const uint8_t* keep) {
   bkx_pe_stats z;
   memset(&z, 0, sizeof(z));
   int mode = pe->pe_proc;
@@ -668,7 +683,7 @@ int bko_pair_reads(const bko_index* x, const bkx_align_params* p, const bkx_pe_p
       continue;
     }
     if (f->nar == BKX_NAR_ACCEPTED && r->nar == BKX_NAR_ACCEPTED) {
-      int frag = accept_prov_pe(pe, f, r);
+      int frag = accept_prov_pe(pe, f, r, keep);
       if (frag > 0) {
         f->flags |= BKX_FLG_PE_ALIGNED;
         r->flags |= BKX_FLG_PE_ALIGNED;
@@ -681,8 +696,17 @@ int bko_pair_reads(const bko_index* x, const bkx_align_params* p, const bkx_pe_p
         case -2: f->nar = r->nar = BKX_NAR_PECHROM; break;
         case -6: f->nar = r->nar = BKX_NAR_PEINSERTMIN; break;
         case -7: f->nar = r->nar = BKX_NAR_PEINSERTMAX; break;
-        default: break; /* 0 cannot happen: both accepted => NumHits == 1; -3..-5 need a chrom filter */
+        case -3:                                                                        /* :3170 */
+          z.num_filtered_by_chrom++;
+          f->num_hits = r->num_hits = 0;
+          f->low_hit_instances = r->low_hit_instances = 0;
+          f->nar = r->nar = BKX_NAR_CHROMFILT;
+          break;
+        case -4: f->nar = BKX_NAR_CHROMFILT; f->low_hit_instances = 0; f->num_hits = 0; break;
+        case -5: r->nar = BKX_NAR_CHROMFILT; r->low_hit_instances = 0; r->num_hits = 0; break;
+        default: break; /* 0 cannot happen: both accepted => NumHits == 1 */
       }
+      if (frag == -3) continue;
       if (mode == BKX_PE_UNIQUE) {                                                      /* :3203 */
         f->num_hits = r->num_hits = 0;
         f->low_hit_instances = r->low_hit_instances = 0;
@@ -695,7 +719,9 @@ int bko_pair_reads(const bko_index* x, const bkx_align_params* p, const bkx_pe_p
     z.partner_unpaired++;                                                               /* :3219 */
     if (mode == BKX_PE_ORPHAN || mode == BKX_PE_ORPHAN_SE) {
       int done = 0;
-      if (f->num_hits == 1 && !r_un) {                                                  /* 5' anchor :3222 */
+      if (f->num_hits == 1 && !r_un && keep && !keep[f->chrom_id]) {                    /* :3224, :3296-3302 */
+        if (f->nar == BKX_NAR_ACCEPTED) { f->num_hits = 0; f->low_hit_instances = 0; f->nar = BKX_NAR_CHROMFILT; }
+      } else if (f->num_hits == 1 && !r_un) {                                           /* 5' anchor :3222 */
         int b3 = f->strand == '+';
         int anti = pe->pair_strand ? (f->strand == '+' ? 0 : 1) : (f->strand == '+' ? 1 : 0);
         if (pe->circularised) b3 = !b3;
@@ -723,7 +749,9 @@ int bko_pair_reads(const bko_index* x, const bkx_align_params* p, const bkx_pe_p
           done = 1;
         }
       }
-      if (!done && r->num_hits == 1 && !f_un) {                                         /* 3' anchor :3321 */
+      if (!done && r->num_hits == 1 && !f_un && keep && !keep[r->chrom_id]) {           /* :3323, :3411-3417: the 5' end is marked */
+        if (r->nar == BKX_NAR_ACCEPTED) { f->num_hits = 0; f->low_hit_instances = 0; f->nar = BKX_NAR_CHROMFILT; }
+      } else if (!done && r->num_hits == 1 && !f_un) {                                  /* 3' anchor :3321 */
         int b3 = r->strand == '+';
         int anti = r->strand == '+';
         if (pe->pair_strand) { b3 = !b3; anti = !anti; }
@@ -764,11 +792,12 @@ int bko_pair_reads(const bko_index* x, const bkx_align_params* p, const bkx_pe_p
       if (r->nar == BKX_NAR_ACCEPTED) r->nar = BKX_NAR_PENOHIT;
       continue;
     }
-    /* SE fallback :3442-3477 (AcceptThisChromID is always true without -Z/-z filters) */
+    /* SE fallback :3442-3477: an end counts when it has its one locus and that chromosome passes AcceptThisChromID (the
+     * eNARChromFilt arm of the reference's ternary is unreachable) */
     bkx_read_result* ends[2] = {f, r};
     for (int k = 0; k < 2; k++) {
       bkx_read_result* e = ends[k];
-      int ok = e->num_hits == 1;
+      int ok = e->num_hits == 1 && (!keep || keep[e->chrom_id]);
       if (!ok) {
         e->num_hits = 0;
         e->low_hit_instances = 0;

@@ -45,6 +45,13 @@ int bko_pair_reads(const bko_index* idx, const bkx_align_params* p, const bkx_pe
                    bkx_read_result* results, uint32_t n_pairs, const uint8_t* bases, const uint64_t* offsets,
                    bkx_pe_stats* stats, uint32_t* len_dist);
 
+/* Same with the -Z / -z chromosome filters acting inside the pairing (AcceptThisChromID in AcceptProvPE and around the
+ * orphan recovery, Aligner.cpp:2771-2786, 3170-3190, 3224, 3296-3302, 3323, 3411-3417, 3442-3477): keep[entry id] != 0
+ * for chromosomes that pass, NULL for none.  Ahead of the CUDA path, which does not take the filter yet. */
+int bko_pair_reads_filtered(const bko_index* idx, const bkx_align_params* p, const bkx_pe_params* pe,
+                            bkx_read_result* results, uint32_t n_pairs, const uint8_t* bases, const uint64_t* offsets,
+                            bkx_pe_stats* stats, uint32_t* len_dist, const uint8_t* keep);
+
 #ifdef __cplusplus
 }
 #endif

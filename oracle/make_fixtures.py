@@ -509,10 +509,31 @@ def case_interplay():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_pefilter():
+    """Chromosome filters -Z / -z in paired-end runs on the tiny index: they act inside the pairing (AcceptThisChromID) and
+    again afterwards (FiltByChroms, which gives the include expressions priority).  Pins the ORACLE's filtered pairing; the
+    CUDA pairing kernel does not take the filter yet."""
+    d = os.path.join(GOLD, "pefilter")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("tiny.sfx", "pe1.fa", "pe2.fa"):
+            with gzip.open(os.path.join(tiny, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        runs = {
+            "U1_Z2": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U1", "-d100", "-D600", "-Zchr2"]},
+            "U2_z13": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U2", "-d100", "-D1000", "-zchr[13]"]},
+            "U3_ZZ": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U3", "-d120", "-D500", "-Zchr1$", "-Zchr3"]},
+            "U4_zZ": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U4", "-d100", "-D400", "-zchr[12]", "-Zchr2"]},
+            "U1far_z2": {"reads": ["pe1.fa", "pe2.fa"], "args": ["-s3", "-U1", "-d100", "-D1500", "-zchr2"]},
+        }
+        align_runs(d, tmp, "tiny.sfx", runs)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -533,4 +554,6 @@ if __name__ == "__main__":
         case_stats()
     if "interplay" in which:
         case_interplay()
+    if "pefilter" in which:
+        case_pefilter()
     print("fixtures written under", GOLD)

@@ -52,6 +52,8 @@ def lib():
                                             C.c_void_p, C.c_void_p, C.POINTER(abi.AlignStats), C.c_int]
         L.bko_pair_reads.argtypes = [C.c_void_p, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), C.c_void_p,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(abi.PEStats), C.c_void_p]
+        L.bko_pair_reads_filtered.argtypes = [C.c_void_p, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), C.c_void_p,
+                                              C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(abi.PEStats), C.c_void_p, C.c_void_p]
         L.bko_seq.argtypes = [C.c_void_p]
         L.bko_seq.restype = C.c_void_p
         L.bko_sa.argtypes = [C.c_void_p]
@@ -143,14 +145,16 @@ class OracleIndex:
             raise RuntimeError("bko_align_batch_multi failed: %d" % rc)
         return out, multi, st
 
-    def pair(self, params, pe, results, bases=None, offsets=None, len_dist=None):
+    def pair(self, params, pe, results, bases=None, offsets=None, len_dist=None, keep=None):
+        """keep: uint8 per entry id (index 0 unused), chromosomes that pass the -Z / -z filters inside the pairing."""
         n_pairs = len(results) // 2
         st = abi.PEStats()
         b = np.ascontiguousarray(bases, dtype=np.uint8).ctypes.data if bases is not None else None
         o = np.ascontiguousarray(offsets, dtype=np.uint64).ctypes.data if offsets is not None else None
         ld = len_dist.ctypes.data if len_dist is not None else None
-        rc = lib().bko_pair_reads(self._h, C.byref(params), C.byref(pe), results.ctypes.data, n_pairs, b, o,
-                                  C.byref(st), ld)
+        kp = np.ascontiguousarray(keep, dtype=np.uint8) if keep is not None else None
+        rc = lib().bko_pair_reads_filtered(self._h, C.byref(params), C.byref(pe), results.ctypes.data, n_pairs, b, o,
+                                           C.byref(st), ld, kp.ctypes.data if kp is not None else None)
         if rc < 0:
             raise RuntimeError("bko_pair_reads failed: %d" % rc)
         return st

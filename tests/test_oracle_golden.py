@@ -87,3 +87,44 @@ def check_clustered(case, tag, idx, p, names, bases, offs):
                   r"(\d+) clustered near other multiloci reads\)", log)
     assert (cs.putative - cs.assigned, cs.putative, cs.assigned, cs.near_unique, cs.near_multi) == tuple(
         int(v) for v in m.groups())
+
+
+@pytest.mark.parametrize("tag", ["U1_Z2", "U2_z13", "U3_ZZ", "U4_zZ", "U1far_z2"])
+def test_oracle_pairing_with_chromosome_filters(tag, golden_dir):
+    """-Z / -z in paired-end runs act inside the pairing (AcceptThisChromID: exclude expressions first, then the include
+    ones) and once more afterwards (FiltByChroms: include expressions first).  Pins bko_pair_reads_filtered -- the oracle is
+    ahead of the CUDA pairing kernel here, which does not take the filter yet (bkx-align refuses the combination)."""
+    import json
+    import os
+    run = json.load(open(os.path.join(gu.GOLD, "pefilter", "runs.json")))[tag]
+    excl = [a[2:] for a in run["args"] if a.startswith("-Z")]
+    incl = [a[2:] for a in run["args"] if a.startswith("-z")]
+    idx = po.OracleIndex(gu.sfx_path("tiny", golden_dir))
+    p, pe = gu.params_from_args(idx, [a for a in run["args"] if a[1] not in "Zz"])
+    names, bases, offs = gu.load_reads("tiny", run)
+    ents = idx.entries()
+    hit = lambda pats, name: any(re.search(x, name, re.I) for x in pats)
+    keep = np.ones(len(ents) + 1, dtype=np.uint8)            # AcceptThisChromID, Aligner.cpp:2651-2710
+    post = np.ones(len(ents) + 1, dtype=np.uint8)            # FiltByChroms, Aligner.cpp:4019-4124
+    for e in ents:
+        nm = e.name.decode()
+        keep[e.entry_id] = (not hit(excl, nm)) and (not incl or hit(incl, nm))
+        post[e.entry_id] = hit(incl, nm) or (not incl and not hit(excl, nm))
+    res, st = idx.align(p, bases, offs, nthreads=4)
+    pst = idx.pair(p, pe, res, bases, offs, keep=keep)
+    drop = (res["nar"] == abi.NAR_ACCEPTED) & (post[res["chrom_id"]] == 0)
+    res["nar"][drop] = abi.NAR_CODES.index("FC")
+    got = gu.results_to_tuples(ents, names, res)
+    exp = gu.expected("pefilter", tag)
+    bad = [(n, got[n], exp[n][:5]) for n in names if got[n] != exp[n][:5]]
+    assert not bad, "%d reads differ, first: %r" % (len(bad), bad[:5])
+    log = gu.log_stats("pefilter", tag)
+    hist = np.bincount(res["nar"], minlength=abi.NAR_COUNT)
+    for code, n in re.findall(r"^\s+(\d+) \((\w\w)\)", log, flags=re.M):
+        assert hist[abi.NAR_CODES.index(n)] == int(code), (n, code, hist)
+    m = re.search(r"(\d+) Paired End aligned pairs were filtered out by chromosome", log)
+    assert m and int(m.group(1)) == pst.num_filtered_by_chrom
+    m = re.search(r"From \d+ Paired End pairs there were (\d+) accepted \(of which (\d+) pairs were from recovered orphans\)", log)
+    assert m and (int(m.group(1)), int(m.group(2))) == (pst.accepted_num_paired, pst.partner_paired)
+    m = re.search(r"Filtering by chromosome completed - removed (\d+)  matches", log)
+    assert m and int(m.group(1)) == int(drop.sum())
