@@ -1272,7 +1272,7 @@ static bool write_bam(const Records& rc, const std::vector<uint32_t>& order, con
   BaiBuilder bai;
   bai.out = "BAI\1";
   bai.put32(nref);
-  struct RecMeta { uint64_t uofs; uint32_t len; int32_t rid, pos; int32_t L, alen; uint8_t acc, lead, trail; };
+  struct RecMeta { uint64_t uofs; uint32_t len; int32_t rid, pos; int32_t L, alen; uint16_t lead, trail; uint8_t acc; };
   std::vector<RecMeta> meta;
   meta.reserve(nrec);
   uint64_t utotal = hdr.size();
@@ -1289,7 +1289,7 @@ static bool write_bam(const Records& rc, const std::vector<uint32_t>& order, con
     const uint32_t ncig = 1 + (lead ? 1 : 0) + (trail ? 1 : 0);
     uint32_t len = 4 + 32 + lname + 4 * ncig + (uint32_t)((L + 1) / 2) + (uint32_t)L + (acc ? 0u : 6u);
     meta.push_back({utotal, len, acc ? refid[r.chrom_id] : -1, acc ? (int32_t)adj_start(i) : -1, L, acc ? (int32_t)adj_len(i) : L,
-                    (uint8_t)acc, (uint8_t)lead, (uint8_t)trail});
+                    (uint16_t)lead, (uint16_t)trail, (uint8_t)acc});
     utotal += len;
   }
   std::vector<uint8_t> U(utotal);
