@@ -91,6 +91,7 @@ struct bkx_index {
   uint64_t max_len_prepared = 0;
   uint32_t* d_pe_list = nullptr;
   size_t pe_list_cap = 0;
+  uint8_t* d_chrom_keep = nullptr;   // bkx_set_chrom_filter: AcceptThisChromID per chromosome id, NULL = no -Z / -z
   uint64_t* fast_hash[kSlots] = {};   // per slot (launches of different slots overlap): lane-private overflow sets
                                       // of the fast kernel, fast_grid x 256 lanes x 1024 slots, allocated on first use
   size_t fast_hash_lanes = 0;
@@ -343,6 +344,7 @@ extern "C" void bkx_close_index(bkx_index* x) {
   if (x->d_pe_stats) cudaFree(x->d_pe_stats);
   if (x->d_len_dist) cudaFree(x->d_len_dist);
   if (x->d_pe_list) cudaFree(x->d_pe_list);
+  if (x->d_chrom_keep) cudaFree(x->d_chrom_keep);
   delete x;
 }
 
@@ -1078,11 +1080,11 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
         CU(cudaMalloc((void**)&s.d_orphans, s.orphans_cap * 4));
       }
       CU(cudaMemsetAsync(cur + 3, 0, sizeof(unsigned int), x->cst));
-      CU(launch_pair(*pec->pe, s.d_out, cnt / 2, x->d_pe_stats, x->d_len_dist, s.d_orphans, cur + 3, x->cst));
+      CU(launch_pair(*pec->pe, s.d_out, cnt / 2, x->d_pe_stats, x->d_len_dist, s.d_orphans, cur + 3, x->d_chrom_keep, x->cst));
       x->launches += 1;
       if (rescue) {
         CU(launch_rescue(x->d, k, *pec->pe, s.d_out, s.d_orphans, cur + 3, s.d_bases - offsets[start], s.d_offs,
-                         std::max<int>((int)max_len, 32), x->d_pe_stats, x->d_len_dist, cur, x->cst));
+                         std::max<int>((int)max_len, 32), x->d_pe_stats, x->d_len_dist, cur, x->d_chrom_keep, x->cst));
         x->launches += 1;
       }
     }
@@ -1234,10 +1236,10 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
     if (e == cudaSuccess) e = cudaMemsetAsync(cnt + 3, 0, sizeof(unsigned int), st);
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_res, results, bytes, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = launch_pair(*pe, d_res, n_pairs, x->d_pe_stats, x->d_len_dist, d_list, cnt + 3, st);
+  if (e == cudaSuccess) e = launch_pair(*pe, d_res, n_pairs, x->d_pe_stats, x->d_len_dist, d_list, cnt + 3, x->d_chrom_keep, st);
   if (e == cudaSuccess && rescue && Lmax <= kRescueMaxLen)
     e = launch_rescue(x->d, k, *pe, d_res, d_list, cnt + 3, d_bases - offsets[0], d_offs, std::max(Lmax, 32), x->d_pe_stats,
-                      x->d_len_dist, cnt, st);
+                      x->d_len_dist, cnt, x->d_chrom_keep, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(results, d_res, bytes, cudaMemcpyDeviceToHost, st);
   bkx_pe_stats hs;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, x->d_pe_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
@@ -1257,6 +1259,24 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
     for (size_t i = 0; i < sizeof(hs) / 8; ++i) d[i] += s[i];
   }
   if (len_dist) for (size_t i = 0; i < ld.size(); ++i) len_dist[i] += ld[i];
+  return BKX_OK;
+}
+
+// -Z / -z in paired-end runs: the keep map the pairing kernels consult (AcceptThisChromID, Aligner.cpp:2651-2710).
+// keep[id] != 0: alignments to chromosome id (1..num_entries) stay; keep[0] is not read.  NULL / 0 clears the filter.
+extern "C" int bkx_set_chrom_filter(bkx_index* x, const uint8_t* keep, uint32_t n_keep) {
+  if (!x) return fail(BKX_ERR_PARAM, "null argument");
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  CU(cudaDeviceSynchronize());   // no pairing launch of this index may still be reading the old map
+  if (x->d_chrom_keep) { cudaFree(x->d_chrom_keep); x->d_chrom_keep = nullptr; }
+  if (!keep || n_keep == 0) return BKX_OK;
+  if (n_keep != x->info.num_entries + 1)
+    return fail(BKX_ERR_PARAM, "chromosome filter has %u entries, the index needs %u (ids 0..%u)", n_keep,
+                x->info.num_entries + 1, x->info.num_entries);
+  CU(cudaMalloc((void**)&x->d_chrom_keep, n_keep));
+  CU(cudaMemcpy(x->d_chrom_keep, keep, n_keep, cudaMemcpyHostToDevice));
+  CU(cudaDeviceSynchronize());   // the library's streams are non-blocking: the map is in place before any of them runs
   return BKX_OK;
 }
 
@@ -1290,10 +1310,10 @@ extern "C" int bkx_pair_reads_device(bkx_index* x, const bkx_align_params* p, co
   }
   unsigned int* cnt = x->d_cursor[1];  // [0] rescue cursor, [3] orphan count (slot 1's scalars are free here)
   CU(cudaMemsetAsync(cnt + 3, 0, sizeof(unsigned int), st));
-  CU(launch_pair(*pe, d_results, n_pairs, d_stats, d_len_dist, rescue ? x->d_pe_list : nullptr, cnt + 3, st));
+  CU(launch_pair(*pe, d_results, n_pairs, d_stats, d_len_dist, rescue ? x->d_pe_list : nullptr, cnt + 3, x->d_chrom_keep, st));
   if (rescue)
     CU(launch_rescue(x->d, k, *pe, d_results, x->d_pe_list, cnt + 3, d_bases, d_offsets, std::max<int>((int)max_read_len, 32),
-                     d_stats, d_len_dist, cnt, st));
+                     d_stats, d_len_dist, cnt, x->d_chrom_keep, st));
   x->launches += rescue ? 2 : 1;
   return BKX_OK;
 }

@@ -858,7 +858,8 @@ int fast_blocks_per_sm(int W) {
 
 // ------------------------------------------------------------------------------------------------
 // Paired ends: AcceptProvPE / PEInsertSize and the per-pair state machine without orphan recovery
-// (Aligner.cpp:2726-2850, 3107-3216, 3421-3477).  One thread per pair.
+// (Aligner.cpp:2726-2850, 3107-3216, 3421-3477).  One thread per pair.  keep: AcceptThisChromID per chromosome id
+// (-Z / -z, Aligner.cpp:2651-2710), NULL when no filter is set.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int pe_insert_size(const bkx_pe_params& pe, uint8_t s1, uint32_t st1, uint32_t en1,
                                               uint8_t s2, uint32_t st2, uint32_t en2) {
@@ -876,7 +877,8 @@ struct PEBlock { unsigned int v[8]; };
 
 __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict__ res, uint32_t n_pairs,
                                   bkx_pe_stats* __restrict__ stats, uint32_t* __restrict__ len_dist,
-                                  uint32_t* __restrict__ orphan_list, unsigned int* __restrict__ n_orphans) {
+                                  uint32_t* __restrict__ orphan_list, unsigned int* __restrict__ n_orphans,
+                                  const uint8_t* __restrict__ keep) {
   __shared__ PEBlock pb;
   if (threadIdx.x < 8) pb.v[threadIdx.x] = 0;
   __syncthreads();
@@ -902,9 +904,15 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
     } else if (f.nar == BKX_NAR_ACCEPTED && r.nar == BKX_NAR_ACCEPTED) {
       int frag;
       if (!(f.num_hits == 1 && r.num_hits == 1)) frag = 0;
-      else if (f.chrom_id != r.chrom_id) frag = -2;
-      else frag = pe_insert_size(pe, f.strand, f.match_loci, f.match_loci + f.match_len - 1, r.strand, r.match_loci,
-                                 r.match_loci + r.match_len - 1);
+      else {
+        const bool bf = keep ? __ldg(keep + f.chrom_id) != 0 : true;
+        if (f.chrom_id != r.chrom_id) {  // Aligner.cpp:2771-2786: -3 both ends filtered, -4 the 5' end, -5 the 3' end
+          const bool br = keep ? __ldg(keep + r.chrom_id) != 0 : true;
+          frag = (bf && br) ? -2 : (!bf && !br) ? -3 : !bf ? -4 : -5;
+        } else if (!bf) frag = -3;
+        else frag = pe_insert_size(pe, f.strand, f.match_loci, f.match_loci + f.match_len - 1, r.strand, r.match_loci,
+                                   r.match_loci + r.match_len - 1);
+      }
       if (frag > 0) {
         f.flags |= BKX_FLG_PE_ALIGNED;
         r.flags |= BKX_FLG_PE_ALIGNED;
@@ -917,9 +925,18 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
           case -2: f.nar = r.nar = BKX_NAR_PECHROM; break;
           case -6: f.nar = r.nar = BKX_NAR_PEINSERTMIN; break;
           case -7: f.nar = r.nar = BKX_NAR_PEINSERTMAX; break;
+          case -3:  // Aligner.cpp:3170
+            atomicAdd(&pb.v[FILT], 1u);
+            f.num_hits = r.num_hits = 0;
+            f.low_hit_instances = r.low_hit_instances = 0;
+            f.nar = r.nar = BKX_NAR_CHROMFILT;
+            done = true;
+            break;
+          case -4: f.nar = BKX_NAR_CHROMFILT; f.low_hit_instances = 0; f.num_hits = 0; break;
+          case -5: r.nar = BKX_NAR_CHROMFILT; r.low_hit_instances = 0; r.num_hits = 0; break;
           default: break;
         }
-        if (mode == BKX_PE_UNIQUE) {
+        if (!done && mode == BKX_PE_UNIQUE) {
           f.num_hits = r.num_hits = 0;
           f.low_hit_instances = r.low_hit_instances = 0;
           if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
@@ -948,11 +965,12 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
         if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
         if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
       } else {
-        if (f.num_hits != 1) {
+        // an end counts when it has its one locus on a chromosome that passes the filter (Aligner.cpp:3442-3477)
+        if (f.num_hits != 1 || (keep && !__ldg(keep + f.chrom_id))) {
           f.num_hits = 0; f.low_hit_instances = 0;
           if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PEUNALIGN;
         } else { f.nar = BKX_NAR_ACCEPTED; atomicAdd(&pb.v[ACCSE], 1u); }
-        if (r.num_hits != 1) {
+        if (r.num_hits != 1 || (keep && !__ldg(keep + r.chrom_id))) {
           r.num_hits = 0; r.low_hit_instances = 0;
           if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PEUNALIGN;
         } else { r.nar = BKX_NAR_ACCEPTED; atomicAdd(&pb.v[ACCSE], 1u); }
@@ -975,11 +993,12 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
 }
 
 cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,
-                        uint32_t* len_dist, uint32_t* orphan_list, unsigned int* n_orphans, cudaStream_t st) {
+                        uint32_t* len_dist, uint32_t* orphan_list, unsigned int* n_orphans, const uint8_t* keep,
+                        cudaStream_t st) {
   int grid = (int)((n_pairs + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   if (grid < 1) grid = 1;
-  pair_reads_kernel<<<grid, 256, 0, st>>>(pe, res, n_pairs, stats, len_dist, orphan_list, n_orphans);
+  pair_reads_kernel<<<grid, 256, 0, st>>>(pe, res, n_pairs, stats, len_dist, orphan_list, n_orphans, keep);
   return cudaGetLastError();
 }
 
@@ -1147,7 +1166,8 @@ __device__ __forceinline__ int align_paired_read(const DevIndex& I, const KParam
 __global__ void __launch_bounds__(kRescueThreads) orphan_rescue_kernel(
     DevIndex I, KParams P, bkx_pe_params pe, bkx_read_result* __restrict__ res, const uint32_t* __restrict__ orphan_list,
     const unsigned int* __restrict__ n_orphans, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
-    int Lmax, bkx_pe_stats* __restrict__ stats, uint32_t* __restrict__ len_dist, unsigned int* __restrict__ cursor) {
+    int Lmax, bkx_pe_stats* __restrict__ stats, uint32_t* __restrict__ len_dist, unsigned int* __restrict__ cursor,
+    const uint8_t* __restrict__ keep) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned int pb[8];
   enum { UNAL = 0, ACCP = 1, ACCSE = 2, PPAIRED = 3, PUNP = 4, FILT = 5, UNDER = 6, OVER = 7 };
@@ -1177,6 +1197,12 @@ __global__ void __launch_bounds__(kRescueThreads) orphan_rescue_kernel(
       // side 0: 5' end is the anchor, rescue PE2 (Aligner.cpp:3222-3310); side 1: 3' anchor, rescue PE1 (:3321-3410)
       const bkx_read_result& anc = side == 0 ? f : r;
       if (!(anc.num_hits == 1 && !(side == 0 ? r_un : f_un))) continue;
+      if (keep && !__ldg(keep + anc.chrom_id)) {
+        // anchor on a filtered chromosome: no recovery; the reference marks the 5' end in both arms (Aligner.cpp:3296-3302,
+        // 3411-3417 -- the second one tests the 3' end and writes the 5' end)
+        if (anc.nar == BKX_NAR_ACCEPTED) { f.num_hits = 0; f.low_hit_instances = 0; f.nar = BKX_NAR_CHROMFILT; }
+        continue;
+      }
       bool b3 = anc.strand == '+';
       bool anti;
       if (side == 0) anti = pe.pair_strand ? (anc.strand != '+') : (anc.strand == '+');
@@ -1242,9 +1268,9 @@ __global__ void __launch_bounds__(kRescueThreads) orphan_rescue_kernel(
         if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
         if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
       } else {
-        if (f.num_hits != 1) { f.num_hits = 0; f.low_hit_instances = 0; if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PEUNALIGN; }
+        if (f.num_hits != 1 || (keep && !__ldg(keep + f.chrom_id))) { f.num_hits = 0; f.low_hit_instances = 0; if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PEUNALIGN; }
         else { f.nar = BKX_NAR_ACCEPTED; if (lane == 0) atomicAdd(&pb[ACCSE], 1u); }
-        if (r.num_hits != 1) { r.num_hits = 0; r.low_hit_instances = 0; if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PEUNALIGN; }
+        if (r.num_hits != 1 || (keep && !__ldg(keep + r.chrom_id))) { r.num_hits = 0; r.low_hit_instances = 0; if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PEUNALIGN; }
         else { r.nar = BKX_NAR_ACCEPTED; if (lane == 0) atomicAdd(&pb[ACCSE], 1u); }
       }
     }
@@ -1265,7 +1291,7 @@ __global__ void __launch_bounds__(kRescueThreads) orphan_rescue_kernel(
 cudaError_t launch_rescue(const DevIndex& I, const KParams& P, const bkx_pe_params& pe, bkx_read_result* res,
                           const uint32_t* orphan_list, const unsigned int* n_orphans, const uint8_t* bases,
                           const uint64_t* offs, int Lmax, bkx_pe_stats* stats, uint32_t* len_dist, unsigned int* cursor,
-                          cudaStream_t st) {
+                          const uint8_t* keep, cudaStream_t st) {
   size_t smem = rescue_warp_bytes(Lmax) * kRescueWarps;
   static size_t configured = 0;
   cudaError_t e = ensure_smem(orphan_rescue_kernel, smem, configured);
@@ -1273,7 +1299,7 @@ cudaError_t launch_rescue(const DevIndex& I, const KParams& P, const bkx_pe_para
   e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   orphan_rescue_kernel<<<148 * 4, kRescueThreads, smem, st>>>(I, P, pe, res, orphan_list, n_orphans, bases, offs, Lmax,
-                                                               stats, len_dist, cursor);
+                                                               stats, len_dist, cursor, keep);
   return cudaGetLastError();
 }
 

@@ -29,9 +29,10 @@ cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t
                               unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, uint64_t* lane_hash,
                               uint32_t epoch_base, int grid, cudaStream_t st);
 cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,
-                        uint32_t* len_dist, uint32_t* orphan_list, unsigned int* n_orphans, cudaStream_t st);
+                        uint32_t* len_dist, uint32_t* orphan_list, unsigned int* n_orphans, const uint8_t* keep,
+                        cudaStream_t st);
 cudaError_t launch_rescue(const DevIndex& I, const KParams& P, const bkx_pe_params& pe, bkx_read_result* res,
                           const uint32_t* orphan_list, const unsigned int* n_orphans, const uint8_t* bases,
                           const uint64_t* offs, int Lmax, bkx_pe_stats* stats, uint32_t* len_dist, unsigned int* cursor,
-                          cudaStream_t st);
+                          const uint8_t* keep, cudaStream_t st);
 }  // namespace bkx

@@ -501,12 +501,6 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.min_flank < 0 || o.min_flank > 7) { fprintf(stderr, "Error: Max flank trimming '-x%d' specified outside of range 0..7\n", o.min_flank); return -1; }  // kanga.cpp:804-808
   if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
-  if (o.pe_mode && (!o.excl.empty() || !o.incl.empty())) {
-    // paired ends: the chromosome filters act inside the pairing (AcceptThisChromID in AcceptProvPE, Aligner.cpp:2651, 2775);
-    // the pairing kernel does not take them
-    fprintf(stderr, "bkx-align: options -Z / -z are not supported together with paired end processing '-U%d'\n", o.pe_mode);
-    return -1;
-  }
   if (o.gpus < 1) o.gpus = 1;
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
@@ -1631,6 +1625,28 @@ int main(int argc, char** argv) {
   std::vector<LociConstraint> constraints;
   if (!o.constraints_file.empty() && load_constraints(o.constraints_file, ents, constraints) < 0) return 1;
 
+  // -Z / -z as AcceptThisChromID evaluates them (Aligner.cpp:2651-2710: exclude expressions first, then -- if any -- the
+  // include expressions).  Two callers in the reference: the pairing of paired-end runs (AcceptProvPE, the orphan-recovery
+  // arms and the SE fallback), which the library's pairing kernels reproduce from this map, and WriteHitLoci under -r5.
+  // FiltByChroms (include expressions first) still runs over the records afterwards, in every mode.
+  std::vector<uint8_t> accept_keep;
+  if (!rin.empty() || !rex.empty()) {
+    accept_keep.assign(info.num_entries + 1, 1);
+    for (uint32_t e = 1; e <= info.num_entries; ++e) {
+      regmatch_t mc;
+      bool ok = true;
+      for (auto& re : rex) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = false; break; }
+      if (ok && !rin.empty()) {
+        ok = false;
+        for (auto& re : rin) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = true; break; }
+      }
+      accept_keep[e] = ok;
+    }
+    if (o.pe_mode)
+      for (int g = 0; g < o.gpus; ++g)
+        if (bkx_set_chrom_filter(idx[(size_t)g], accept_keep.data(), (uint32_t)accept_keep.size()) < 0) { diag("Fatal: %s", bkx_last_error()); return 1; }
+  }
+
   reads_thread.join();
   if (reads_rc < 0) return 1;
   const uint32_t n = R.n();
@@ -1708,19 +1724,9 @@ int main(int argc, char** argv) {
   // -r5 with -Z / -z: the loci of a read are filtered as they are recorded (WriteHitLoci -> AcceptThisChromID, Aligner.cpp:6737-6757,
   // 2651-2710: exclude expressions first, then -- if any -- the include expressions), so the provisional totals count the
   // loci that stay; reads left without a locus leave no record.
-  std::vector<char> r5_keep;
-  if (all_loci && (!rin.empty() || !rex.empty())) {
-    r5_keep.assign(info.num_entries + 1, 1);
-    for (uint32_t e = 1; e <= info.num_entries; ++e) {
-      regmatch_t mc;
-      bool ok = true;
-      for (auto& re : rex) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = false; break; }
-      if (ok && !rin.empty()) {
-        ok = false;
-        for (auto& re : rin) if (!regexec(&re, ents[e].name, 1, &mc, 0)) { ok = true; break; }
-      }
-      r5_keep[e] = ok;
-    }
+  std::vector<uint8_t> r5_keep;
+  if (all_loci && !accept_keep.empty()) {
+    r5_keep = accept_keep;
     S.tot_accepted_aligned = S.tot_accepted_unique = S.tot_accepted_multi = S.tot_loci_aligned = 0;
     for (uint32_t i = 0; i < n; ++i) {
       if (res[i].nar != BKX_NAR_ACCEPTED) continue;

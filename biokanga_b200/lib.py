@@ -25,7 +25,7 @@ EXPORTS = [
     "bkx_build_suffix_array_device", "bkx_write_sfx", "bkx_pin_host", "bkx_unpin_host",
     "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
     "bkx_pack_bases4", "bkx_align_reads_multi", "bkx_align_pairs", "bkx_align_pairs_packed4",
-    "bkx_assign_multi_matches", "bkx_self_check", "bkx_debug_reset",
+    "bkx_assign_multi_matches", "bkx_self_check", "bkx_debug_reset", "bkx_set_chrom_filter",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
     L.bkx_write_sfx.argtypes = [C.c_char_p, vp, u64, vp, u32, vp, u32, C.c_char_p]
     L.bkx_pair_reads_device.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, u32, vp, vp, u32, vp,
                                         vp, vp]
+    L.bkx_set_chrom_filter.argtypes = [vp, vp, u32]
     L.bkx_pin_host.argtypes = [vp, C.c_size_t]
     L.bkx_unpin_host.argtypes = [vp]
     L.bkx_last_kernel_ms.argtypes = [vp]
@@ -310,6 +311,15 @@ class Index:
         hr = check(lib().bkx_align_one(self._h, C.byref(params), probe.ctypes.data, len(probe), C.byref(a),
                                        C.byref(b), C.byref(c), hit.ctypes.data))
         return hr, (a.value, b.value, c.value), hit[0]
+
+    def set_chrom_filter(self, keep):
+        """-Z / -z inside the pairing (AcceptThisChromID, Aligner.cpp:2651-2710): keep[id] != 0 for the chromosomes whose
+        alignments stay, one uint8 per entry id 0..num_entries (index 0 unused); None clears the filter."""
+        if keep is None:
+            check(lib().bkx_set_chrom_filter(self._h, None, 0))
+            return
+        kp = np.ascontiguousarray(keep, dtype=np.uint8)
+        check(lib().bkx_set_chrom_filter(self._h, kp.ctypes.data, len(kp)))
 
     def pair(self, params, pe, results, bases=None, offsets=None, len_dist=None):
         n_pairs = len(results) // 2

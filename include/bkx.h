@@ -268,6 +268,15 @@ int bkx_pair_reads_device(bkx_index* idx, const bkx_align_params* p, const bkx_p
                           uint32_t n_pairs, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t max_read_len,
                           bkx_pe_stats* d_stats, uint32_t* d_len_dist, void* cuda_stream);
 
+/* -Z / -z chromosome filters of a paired-end run: in the reference they act INSIDE the pairing (AcceptThisChromID called
+ * from AcceptProvPE, the orphan-recovery arms and the SE fallback of ProcessPairedEnds: Aligner.cpp:2651-2710, 2771-2786,
+ * 3296-3302, 3411-3417, 3442-3477), so the pairing kernels take them as a per-chromosome keep map held by the index:
+ * keep[id] != 0 -- alignments to chromosome id stay (ids 1..num_entries; keep[0] is not read); n_keep must be
+ * num_entries + 1.  The caller evaluates the expressions (exclude first, then -- if any -- the include ones).
+ * keep = NULL clears the filter.  Consulted by bkx_pair_reads, bkx_pair_reads_device and bkx_align_pairs[_packed4] on
+ * this index (not copied by bkx_clone_index); single-end filtering (FiltByChroms, Aligner.cpp:4019-4124) stays host work. */
+int bkx_set_chrom_filter(bkx_index* idx, const uint8_t* keep, uint32_t n_keep);
+
 /* Alignment and pairing of paired-end reads in ONE pass over the data: reads 2i / 2i+1 are PE1 / PE2 of pair i; each
  * slice of the internal pipeline is aligned and then paired (and its orphans recovered) while it is still on the GPU, so
  * the reads cross PCIe once.  Same records, counters and histogram as bkx_align_reads followed by bkx_pair_reads

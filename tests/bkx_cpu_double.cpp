@@ -16,7 +16,7 @@
 
 #include "../oracle/bk_oracle.h"
 
-struct bkx_index { bko_index* o; };
+struct bkx_index { bko_index* o; std::vector<uint8_t> keep; };
 
 static thread_local std::string g_err;
 
@@ -44,7 +44,7 @@ int bkx_open_index(const char* sfx_path, int, int, bkx_index** out) {
   bko_index* o = nullptr;
   int rc = bko_open(sfx_path, &o);
   if (rc < 0) return bkx_fail(rc, "unable to open '%s' (oracle code %d)", sfx_path, rc);
-  *out = new bkx_index{o};
+  *out = new bkx_index{o, {}};
   return BKX_OK;
 }
 int bkx_clone_index(const bkx_index*, int, bkx_index**) { return bkx_fail(BKX_ERR_UNSUPPORTED, "test double: one device only"); }
@@ -78,7 +78,17 @@ int bkx_align_pairs_packed4(bkx_index* x, const bkx_align_params* p, const bkx_p
   std::vector<uint8_t> b = unpack4(packed, offs[2 * (uint64_t)n_pairs]);
   int rc = bko_align_batch(x->o, p, b.data(), offs, 2 * n_pairs, out, st, 4);
   if (rc < 0) return rc;
-  return bko_pair_reads(x->o, p, pe, out, n_pairs, b.data(), offs, pst, len_dist);
+  return bko_pair_reads_filtered(x->o, p, pe, out, n_pairs, b.data(), offs, pst, len_dist,
+                                 x->keep.empty() ? nullptr : x->keep.data());
+}
+int bkx_set_chrom_filter(bkx_index* x, const uint8_t* keep, uint32_t n_keep) {
+  bkx_index_info info;
+  bko_info(x->o, &info);
+  x->keep.clear();
+  if (!keep || n_keep == 0) return BKX_OK;
+  if (n_keep != info.num_entries + 1) return bkx_fail(BKX_ERR_PARAM, "chromosome filter has %u entries", n_keep);
+  x->keep.assign(keep, keep + n_keep);
+  return BKX_OK;
 }
 
 // SortHitMatch order (Aligner.cpp:10067-10114) with ties by record index -- the contract of bkx_sort_hits.

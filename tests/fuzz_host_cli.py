@@ -79,7 +79,7 @@ def draw(rng):
     if not pe and rng.random() < 0.3:
         a.append("-k%d" % rng.choice([0, 20, 100, 250]))
         dedup = True
-    if not pe and rng.random() < 0.3:
+    if rng.random() < 0.3:
         a += rng.choice([["-Zchr2"], ["-zchr[13]"], ["-Zchr1$", "-Z4"], ["-zCHR2", "-Zchr2"]])
     if rng.random() < 0.3:
         a.append("-5cons.csv")

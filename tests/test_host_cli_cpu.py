@@ -9,6 +9,7 @@ import pytest
 
 import pyoracle as po
 import test_gpu_cli as g
+import test_gpu_zpefilter as gz
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -35,6 +36,11 @@ def cli(cpu_cli, monkeypatch):
 @pytest.mark.parametrize("case,tag", g.RUNS)
 def test_host_outputs_match_reference(case, tag, cli, golden_dir, tmp_path):
     g.test_cli_outputs_match_reference(case, tag, golden_dir, tmp_path)
+
+
+@pytest.mark.parametrize("tag", gz.PE_FILTER_RUNS)
+def test_host_paired_end_chromosome_filters_match_reference(tag, cli, golden_dir, tmp_path):
+    gz.test_cli_paired_end_chromosome_filters_match_reference(tag, golden_dir, tmp_path)
 
 
 def test_host_rejects_unsupported_and_bad_options(cli, golden_dir, tmp_path):
