@@ -73,6 +73,57 @@ def test_pairing_kernels_with_chromosome_filters_match_oracle_and_reference(tag,
     assert m and int(m.group(1)) == gpe.num_filtered_by_chrom
 
 
+def draw_filtered_pairing_case(seed, chroms):
+    """Random paired-end reads, -U mode, insert range, -E and a random keep map (at least one chromosome filtered)."""
+    import synth
+    rng = np.random.default_rng(9000 + seed)
+    L = int(rng.choice([50, 75, 100, 150]))
+    ins_lo = int(rng.choice([L + 20, 150, 300]))
+    usable = [c for c in chroms if len(c[1]) >= 1200]
+    _, r1, _, r2 = synth.sim_reads(usable, int(rng.integers(400, 1000)), L, seed=int(rng.integers(1, 1 << 30)),
+                                   subs=tuple(range(0, int(rng.integers(1, 5)))), junk_frac=0.08, n_frac=0.0, pe=True,
+                                   insert=(ins_lo, ins_lo + int(rng.choice([50, 300, 900]))))
+    # every seventh pair gets a mate from another pair: ends on different chromosomes, and orphans to recover
+    r2 = [r2[(i + 1) % len(r2)] if i % 7 == 0 else r2[i] for i in range(len(r2))]
+    reads = [x for pair in zip(r1, r2) for x in pair]
+    bases = np.concatenate(reads)
+    offs = np.arange(len(reads) + 1, dtype=np.uint64) * L
+    pe = abi.PEParams()
+    pe.pe_proc = 1 + seed % 4
+    pe.pair_min_len = int(rng.choice([100, 150, 200]))
+    pe.pair_max_len = pe.pair_min_len + int(rng.choice([300, 800, 1500]))
+    pe.pair_strand = int(rng.random() < 0.15)
+    keep = (rng.random(len(chroms) + 1) < 0.6).astype(np.uint8)
+    keep[1 + int(rng.integers(0, len(chroms)))] = 0
+    kw = dict(max_subs=int(rng.choice([3, 5, 8])), min_edit_dist=1)
+    return bases, offs, pe, keep, kw
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_pairing_with_keep_maps_matches_oracle(seed, golden_dir):
+    """The pairing and orphan-recovery kernels alone: the GPU's own alignment records go into both the CUDA pairing
+    (bkx_pair_reads with a keep map set) and the oracle's (bko_pair_reads_filtered); records, counters and the insert-length
+    histogram must agree.  Random modes -U1..4, insert ranges, -E, keep maps, swapped mates."""
+    from test_gpu_fuzz import index_pair
+    case = ["tiny", "repeats", "lowcopy"][seed % 3]
+    gidx, oidx, chroms = index_pair(case, golden_dir)
+    bases, offs, pe, keep, kw = draw_filtered_pairing_case(seed, chroms)
+    p = gidx.default_params(0, **kw)
+    rec, _ = gidx.align(p, bases, offs)
+    exp = rec.copy()
+    ld_o = np.zeros(100001, dtype=np.uint32)
+    ost = oidx.pair(p, pe, exp, bases, offs, len_dist=ld_o, keep=keep)
+    ld_g = np.zeros(100001, dtype=np.uint32)
+    try:
+        gidx.set_chrom_filter(keep)
+        gst = gidx.pair(p, pe, rec, bases, offs, len_dist=ld_g)
+    finally:
+        gidx.set_chrom_filter(None)
+    assert_same(None, rec, exp)
+    assert bytes(gst) == bytes(ost)
+    assert (ld_g == ld_o).all()
+
+
 def test_chromosome_filter_argument_checks(golden_dir):
     gidx, _ = indexes("tiny", golden_dir)
     with pytest.raises(bkx.BkxError):
