@@ -493,9 +493,10 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
   if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
   if (o.pcr_primer < 0 || o.pcr_primer > 5) { fprintf(stderr, "Error: PCR primer correction subs '-6%d' specified outside of range 0..5\n", o.pcr_primer); return -1; }  // kanga.cpp:784-789
-  if (o.pcr_primer && o.pe_mode) {
-    // orphan recovery would have to take its mismatch limit from -s and its acceptance from -s plus -6 (Aligner.cpp:3256, 3275)
-    fprintf(stderr, "bkx-align: option -6 is not supported together with paired end processing '-U%d'\n", o.pe_mode);
+  if (o.pcr_primer && (o.pe_mode == BKX_PE_ORPHAN || o.pe_mode == BKX_PE_ORPHAN_SE)) {
+    // orphan recovery would have to take its core lengths from -s and its acceptance from -s plus -6 (Aligner.cpp:3256, 3275);
+    // -U2 / -U4 recover nothing: there -6 is the same host pass as in single-end runs (Aligner.cpp:608-616)
+    fprintf(stderr, "bkx-align: option -6 is not supported together with paired end orphan recovery '-U%d'\n", o.pe_mode);
     return -1;
   }
   if (o.min_flank < 0 || o.min_flank > 7) { fprintf(stderr, "Error: Max flank trimming '-x%d' specified outside of range 0..7\n", o.min_flank); return -1; }  // kanga.cpp:804-808

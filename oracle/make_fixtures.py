@@ -452,6 +452,9 @@ def case_sample():
                                       ("s3pe", ["pe1.fa", "pe2.fa"], ["-s3", "-M6", "-U1", "-D600", "-#3"], "s3pe.sam"),
                                       ("p6", ["r100.fa"], ["-s2", "-M0", "-63"], "p6.csv"),          # -6: 5' primer artefact correction
                                       ("p6sam", ["r100.fa"], ["-s2", "-M6", "-63", "-x3", "-k0"], "p6.sam"),
+                                      # -6 in paired-end runs without orphan recovery (-U2 / -U4): pairing at -s plus -6, then the correction
+                                      ("p6pe", ["pe1.fa", "pe2.fa"], ["-s2", "-M0", "-U2", "-D600", "-63"], "p6pe.csv"),
+                                      ("p6pesam", ["pe1.fa", "pe2.fa"], ["-s2", "-M6", "-U4", "-D1500", "-65", "-x3"], "p6pe.sam"),
                                       ("pex0", ["pe1.fa", "pe2.fa"], ["-s5", "-M0", "-U1", "-D600", "-x5"], "pex0.csv"),
                                       ("pex6", ["pe1.fa", "pe2.fa"], ["-s5", "-M6", "-U3", "-D500", "-x7", "-#2"], "pex6.sam")):
             run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)

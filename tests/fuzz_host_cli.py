@@ -62,7 +62,8 @@ def draw(rng):
     fmt = rng.choice([0, 0, 1, 2, 3, 4, 5, 6])
     ml = 0
     if pe:
-        a += ["-U%d" % rng.choice([1, 2, 3, 4]), "-d%d" % rng.choice([100, 120]), "-D%d" % rng.choice([400, 600, 1500])]
+        umode = rng.choice([1, 2, 3, 4])
+        a += ["-U%d" % umode, "-d%d" % rng.choice([100, 120]), "-D%d" % rng.choice([400, 600, 1500])]
         if fmt in (1, 2, 3):
             fmt = 0
     elif rng.random() < 0.35:
@@ -74,7 +75,7 @@ def draw(rng):
     dedup = False
     if rng.random() < 0.4:
         a.append("-x%d" % rng.choice([2, 4, 5, 7]))
-    if not pe and ml != 5 and rng.random() < 0.2:
+    if (not pe or umode in (2, 4)) and ml != 5 and rng.random() < 0.2:    # -U1 / -U3 with -6: refused (orphan recovery)
         a.append("-6%d" % rng.choice([1, 3, 5]))
     if not pe and rng.random() < 0.3:
         a.append("-k%d" % rng.choice([0, 20, 100, 250]))
