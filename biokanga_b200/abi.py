@@ -44,7 +44,8 @@ class AlignParams(C.Structure):
 
 class PEParams(C.Structure):
     _fields_ = [("pe_proc", C.c_int32), ("pair_min_len", C.c_int32), ("pair_max_len", C.c_int32),
-                ("pair_strand", C.c_int32), ("circularised", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("pair_strand", C.c_int32), ("circularised", C.c_int32), ("rescue_core_subs_p1", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class ClusterStats(C.Structure):

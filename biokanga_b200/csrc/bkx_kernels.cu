@@ -1067,7 +1067,8 @@ __device__ __forceinline__ int align_paired_read(const DevIndex& I, const KParam
   if (ep - sp >= 1000) {
     // ---- suffix-array seeded: exact core hits inside the window (no cap, as the reference)
     int match_len = L - 1;
-    int max_tot_mm = P.max_subs == 0 ? 0 : max(1, (match_len * P.max_subs + 50) / 100);
+    const int core_subs = pe.rescue_core_subs_p1 > 0 ? pe.rescue_core_subs_p1 - 1 : P.max_subs;  // -6 runs: m_MaxSubs, Aligner.cpp:3256
+    int max_tot_mm = core_subs == 0 ? 0 : max(1, (match_len * core_subs + 50) / 100);
     if (max_tot_mm > 63) max_tot_mm = 63;
     int core_len = max(P.min_core_len, L / (P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
     int core_delta = max(L / P.slides_per100 - 1, core_len);  // sic: per-100bp value (Aligner.cpp:3266)

@@ -493,12 +493,6 @@ static int parse(int argc, char** argv, Opts& o) {
   if (o.pe_mode && o.pair.size() != o.in.size()) { fprintf(stderr, "Error: Paired end processing '-U%d' requested but number of PE1 files not same as PE2 files\n", o.pe_mode); return -1; }
   if (o.min_len < 15 || o.min_len > 2000 || o.max_len < o.min_len || o.max_len > 2000) { fprintf(stderr, "Error: read length limits out of range\n"); return -1; }
   if (o.pcr_primer < 0 || o.pcr_primer > 5) { fprintf(stderr, "Error: PCR primer correction subs '-6%d' specified outside of range 0..5\n", o.pcr_primer); return -1; }  // kanga.cpp:784-789
-  if (o.pcr_primer && (o.pe_mode == BKX_PE_ORPHAN || o.pe_mode == BKX_PE_ORPHAN_SE)) {
-    // orphan recovery would have to take its core lengths from -s and its acceptance from -s plus -6 (Aligner.cpp:3256, 3275);
-    // -U2 / -U4 recover nothing: there -6 is the same host pass as in single-end runs (Aligner.cpp:608-616)
-    fprintf(stderr, "bkx-align: option -6 is not supported together with paired end orphan recovery '-U%d'\n", o.pe_mode);
-    return -1;
-  }
   if (o.min_flank < 0 || o.min_flank > 7) { fprintf(stderr, "Error: Max flank trimming '-x%d' specified outside of range 0..7\n", o.min_flank); return -1; }  // kanga.cpp:804-808
   if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
@@ -1670,6 +1664,9 @@ int main(int argc, char** argv) {
   memset(&PE, 0, sizeof(PE));
   PE.pe_proc = o.pe_mode; PE.pair_min_len = o.pair_min; PE.pair_max_len = o.pair_max; PE.pair_strand = o.pair_strand;
   PE.circularised = o.pe_circ;
+  // -6: search, pairing and the recovery's acceptance run at -s plus -6, the recovery's core lengths still come from -s
+  // (m_MaxSubs at Aligner.cpp:3256 against pPars->MaxSubs at :3275)
+  PE.rescue_core_subs_p1 = o.pcr_primer > 0 ? o.max_subs + 1 : 0;
   // -O with paired ends: the insert-size histogram m_pLenDist[0..100000] (Aligner.cpp:2908-2915), one per GPU, summed below
   const size_t kLenDist = 100001;
   std::vector<std::vector<uint32_t>> len_dist((size_t)o.gpus);

@@ -152,7 +152,10 @@ typedef struct bkx_pe_params {
   int32_t pair_max_len;     /* -D (default 1000)                   */
   int32_t pair_strand;      /* -E: 1 = both ends on same strand    */
   int32_t circularised;     /* -c PE circularised fragments        */
-  int32_t reserved[3];
+  int32_t rescue_core_subs_p1; /* 0: orphan recovery derives its core length from the run's max_subs.  s + 1: from the rate s
+                                * instead -- a -6 run searches and accepts at -s plus -6 (m_InitalAlignSubs) while the recovery's
+                                * cores are still sized from -s (m_MaxSubs), Aligner.cpp:3256 vs :3275 */
+  int32_t reserved[2];
 } bkx_pe_params;
 
 /* The eight PE counters of tsPEThreadPars (Aligner.cpp:3479-3486).  partner_unpaired is the plain

@@ -455,6 +455,9 @@ def case_sample():
                                       # -6 in paired-end runs without orphan recovery (-U2 / -U4): pairing at -s plus -6, then the correction
                                       ("p6pe", ["pe1.fa", "pe2.fa"], ["-s2", "-M0", "-U2", "-D600", "-63"], "p6pe.csv"),
                                       ("p6pesam", ["pe1.fa", "pe2.fa"], ["-s2", "-M6", "-U4", "-D1500", "-65", "-x3"], "p6pe.sam"),
+                                      # ... and with it (-U1 / -U3, -D1500: suffix-array seeded recovery, cores sized from -s, acceptance at -s plus -6)
+                                      ("p6u1", ["pe1.fa", "pe2.fa"], ["-s2", "-M0", "-U1", "-D1500", "-63"], "p6u1.csv"),
+                                      ("p6u3sam", ["pe1.fa", "pe2.fa"], ["-s5", "-M6", "-U3", "-d120", "-D1500", "-61", "-x4"], "p6u3.sam"),
                                       ("pex0", ["pe1.fa", "pe2.fa"], ["-s5", "-M0", "-U1", "-D600", "-x5"], "pex0.csv"),
                                       ("pex6", ["pe1.fa", "pe2.fa"], ["-s5", "-M6", "-U3", "-D500", "-x7", "-#2"], "pex6.sam")):
             run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)

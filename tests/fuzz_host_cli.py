@@ -75,7 +75,7 @@ def draw(rng):
     dedup = False
     if rng.random() < 0.4:
         a.append("-x%d" % rng.choice([2, 4, 5, 7]))
-    if (not pe or umode in (2, 4)) and ml != 5 and rng.random() < 0.2:    # -U1 / -U3 with -6: refused (orphan recovery)
+    if ml != 5 and rng.random() < 0.2:
         a.append("-6%d" % rng.choice([1, 3, 5]))
     if not pe and rng.random() < 0.3:
         a.append("-k%d" % rng.choice([0, 20, 100, 250]))

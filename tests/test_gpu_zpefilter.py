@@ -124,6 +124,28 @@ def test_random_pairing_with_keep_maps_matches_oracle(seed, golden_dir):
     assert (ld_g == ld_o).all()
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_orphan_recovery_with_core_lengths_from_a_lower_rate_matches_oracle(seed, golden_dir):
+    """-6 runs: search and acceptance at -s plus -6, the recovery's core lengths from -s (bkx_pe_params.rescue_core_subs_p1;
+    Aligner.cpp:3256 against :3275).  Wide insert ranges, so that the suffix-array seeded branch of the recovery runs (on these draws the
+    oracle recovers up to 68 fewer pairs with the field than without: the cases are sensitive to it)."""
+    from test_gpu_fuzz import index_pair
+    case = ["tiny", "repeats", "lowcopy"][seed % 3]
+    gidx, oidx, chroms = index_pair(case, golden_dir)
+    bases, offs, pe, _, kw = draw_filtered_pairing_case(100 + seed, chroms)
+    pe.pe_proc = 1 if seed & 1 else 3
+    pe.pair_max_len = pe.pair_min_len + 1400
+    s = [2, 3, 5][seed % 3]
+    pe.rescue_core_subs_p1 = s + 1
+    p = gidx.default_params(0, max_subs=s + [1, 3, 5][(seed // 3) % 3], min_edit_dist=kw["min_edit_dist"])
+    rec, _ = gidx.align(p, bases, offs)
+    exp = rec.copy()
+    ost = oidx.pair(p, pe, exp, bases, offs)
+    gst = gidx.pair(p, pe, rec, bases, offs)
+    assert_same(None, rec, exp)
+    assert bytes(gst) == bytes(ost)
+
+
 def test_chromosome_filter_argument_checks(golden_dir):
     gidx, _ = indexes("tiny", golden_dir)
     with pytest.raises(bkx.BkxError):

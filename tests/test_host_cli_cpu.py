@@ -67,7 +67,7 @@ def test_host_loci_base_constraints_match_reference(tag, cli, golden_dir, tmp_pa
     g.test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path)
 
 
-@pytest.mark.parametrize("tag", ["s7", "s3pe", "pex0", "pex6", "p6", "p6sam", "p6pe", "p6pesam"])
+@pytest.mark.parametrize("tag", ["s7", "s3pe", "pex0", "pex6", "p6", "p6sam", "p6pe", "p6pesam", "p6u1", "p6u3sam"])
 def test_host_read_sampling_matches_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_read_sampling_matches_reference(tag, golden_dir, tmp_path)
 
