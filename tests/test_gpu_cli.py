@@ -198,7 +198,7 @@ def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, ca
     assert summary_block(tmp_path / "o.log") == exp_log
 
 
-@pytest.mark.parametrize("tag", ["s7", "s3pe", "pex0", "pex6", "p6", "p6sam", "p6pe", "p6pesam", "p6u1", "p6u3sam"])
+@pytest.mark.parametrize("tag", ["s7", "s3pe", "pex0", "pex6", "p6", "p6sam", "p6pe", "p6pesam"])
 def test_cli_read_sampling_matches_reference(tag, golden_dir, tmp_path):
     """-# (every Nth raw read / read pair of each file, taken before the length filter); pex*: -x in paired-end runs
     (trimmed POS / CIGAR / PNEXT / TLEN, nothing sloughed); p6*: -6 correction of 5' primer artefacts (p6pe*: behind -U2 / -U4 pairing)."""

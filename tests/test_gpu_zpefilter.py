@@ -159,3 +159,10 @@ def test_cli_paired_end_chromosome_filters_match_reference(tag, golden_dir, tmp_
     chromosome' and FiltByChroms' own count) against the reference's files.  The CPU suite runs the same check through the
     oracle-backed test double (tests/test_host_cli_cpu.py)."""
     cli.test_cli_outputs_match_reference("pefilter", tag, golden_dir, tmp_path, src_case="tiny")
+
+
+@pytest.mark.parametrize("tag", ["p6u1", "p6u3sam"])
+def test_cli_primer_correction_with_orphan_recovery_matches_reference(tag, golden_dir, tmp_path):
+    """bkx-align -6 with -U1 / -U3 and a wide insert range (the run that needs rescue_core_subs_p1) against the reference's
+    files; the CPU suite runs the same check through the oracle-backed test double."""
+    cli.test_cli_read_sampling_matches_reference(tag, golden_dir, tmp_path)
