@@ -875,6 +875,10 @@ struct Records {
   std::vector<uint16_t> trim_l, trim_r;
   std::vector<uint8_t> trim_mm;
   uint32_t elim_plus = 0, elim_minus = 0;            // alignments sloughed by the trimming, per strand
+  // HitLoci.FlagIA: accepted alignment of a `simreads` read that is not where its descriptor says (sim_truth_check); empty
+  // unless the read set carries such descriptors
+  std::vector<uint8_t> flag_ia;
+  const char* align_type(uint32_t i) const { return !flag_ia.empty() && flag_ia[i] ? "iar" : "ar"; }   // Aligner.cpp:6391-6430
 
   uint32_t n() const { return (uint32_t)res.size(); }
   uint32_t rix(uint32_t i) const { return src.empty() ? i : src[i]; }
@@ -1149,6 +1153,45 @@ static void filter_by_chroms(Records& rc, std::vector<regex_t>& rin, std::vector
   diag("Filtering aligned reads by chromosome completed");
 }
 
+// ---- simulated-read truth check of ReportAlignStats, Aligner.cpp:3556-3657.  Reads written by `biokanga simreads` name
+//      their origin in the descriptor: <type>|usimreads|<n>|<chrom>|<start>|<end>|<len>|<strand>|<errs>..., where <chrom> may
+//      itself be three '|' separated parts (gnl|UG|Ta#S58887126).  Records are walked in load order; the first accepted one
+//      decides whether the set is simulated, and from then on every accepted record is parsed -- until one does not parse,
+//      which ends the checking for good (later records are skipped because they are not the first accepted one any more).
+//      An accepted alignment on another chromosome, or with neither edge on the source's edges, is flagged (HitLoci.FlagIA)
+//      and reported as "iar" by the CSV / BED writers; the edges compared are the untrimmed ones.
+struct SimTruth { bool sim = false; uint32_t edge2 = 0, edge1 = 0, misaligned = 0; };
+
+static SimTruth sim_truth_check(Records& rc) {
+  SimTruth t;
+  const uint32_t nrec = rc.n();
+  uint32_t accepted = 0;
+  for (uint32_t i = 0; i < nrec; ++i) {
+    const bkx_read_result& r = rc.res[i];
+    if (r.nar != BKX_NAR_ACCEPTED) continue;
+    ++accepted;
+    if (!t.sim && accepted != 1) continue;
+    const char* d = rc.R.name(rc.rix(i));
+    char type[100], c0[100], c1[100], c2[100], strand;
+    int seq, start = 0, end = 0, len, errs;
+    std::string chrom;
+    int its = sscanf(d, "%99[^|]|usimreads|%d|%99[^|]|%d|%d|%d|%c|%d", type, &seq, c0, &start, &end, &len, &strand, &errs);
+    if (its >= 6) { t.sim = true; chrom = c0; }
+    else {
+      its = sscanf(d, "%99[^|]|usimreads|%d|%99[^|]|%99[^|]|%99[^|]|%d|%d|%d|%c|%d", type, &seq, c0, c1, c2, &start, &end, &len, &strand, &errs);
+      t.sim = its >= 8;
+      if (t.sim) { chrom = c0; chrom += '|'; chrom += c1; chrom += '|'; chrom += c2; }
+    }
+    if (!t.sim) continue;
+    if (rc.flag_ia.empty()) rc.flag_ia.assign(nrec, 0);
+    const int left = (int32_t)r.match_loci, right = left + (int)r.match_len - 1;
+    if (strcasecmp(rc.ents[r.chrom_id].name, chrom.c_str())) { ++t.misaligned; rc.flag_ia[i] = 1; }
+    else if (left == start || right == end) ++(left == start && right == end ? t.edge2 : t.edge1);
+    else { ++t.misaligned; rc.flag_ia[i] = 1; }
+  }
+  return t;
+}
+
 // ---- writers.  Rows go out in hit order (`order`); every writer reports the alignment as trimmed by -x, if at all.
 static const char kAsc[] = "ACGTN";
 
@@ -1170,7 +1213,7 @@ static void write_bed(const Records& rc, const std::vector<uint32_t>& order, con
     if (r.nar != BKX_NAR_ACCEPTED) return;
     s += ents[r.chrom_id].name; s += '\t';
     append_uint(s, adj_start(i)); s += '\t';
-    append_uint(s, (uint64_t)adj_start(i) + adj_len(i)); s += "\tar\t0\t"; s += (char)r.strand; s += '\n';
+    append_uint(s, (uint64_t)adj_start(i) + adj_len(i)); s += '\t'; s += rc.align_type(i); s += "\t0\t"; s += (char)r.strand; s += '\n';
   });
 }
 
@@ -1195,7 +1238,7 @@ static void write_csv(const Records& rc, const std::vector<uint32_t>& order, con
     const bkx_read_result& r = res[i];
     if (r.nar != BKX_NAR_ACCEPTED) return;
     append_uint(s, (uint64_t)i + 1);
-    s += ",\"ar\",\""; s += info.dataset_name; s += "\",\""; s += ents[r.chrom_id].name; s += "\",";
+    s += ",\""; s += rc.align_type(i); s += "\",\""; s += info.dataset_name; s += "\",\""; s += ents[r.chrom_id].name; s += "\",";
     const uint32_t start = adj_start(i), alen = adj_len(i);   // the alignment as trimmed by -x, if at all
     append_uint(s, start); s += ',';
     append_uint(s, (uint64_t)start + alen - 1); s += ',';
@@ -1919,6 +1962,10 @@ int main(int argc, char** argv) {
   }
   diag("From %u source reads there are %u accepted alignments, %u on '+' strand, %u on '-' strand", n, (unsigned)nar[BKX_NAR_ACCEPTED],
        (unsigned)plus, (unsigned)(nar[BKX_NAR_ACCEPTED] - plus));
+  const SimTruth truth = sim_truth_check(rc);
+  if (truth.sim)
+    diag("There are %u (%u 2 edge, %u 1 edge) high confidence aligned simulated reads with %u misaligned", truth.edge2 + truth.edge1,
+         truth.edge2, truth.edge1, truth.misaligned);
   diag("A further %u multiloci aligned reads could not accepted as hits because they were unresolvable", (unsigned)nar[BKX_NAR_MULTIALIGN]);
   diag("A further %u aligned reads were not accepted as hits because of insufficient Hamming edit distance", (unsigned)nar[BKX_NAR_MMDELTA]);
   diag("A further %u '+' and %u '-' strand aligned reads not accepted because of flank trimming (%d were trimmed) requirements", (unsigned)elim_plus, (unsigned)elim_minus, (int)num_trimmed);

@@ -536,10 +536,74 @@ def case_pefilter():
         align_runs(d, tmp, "tiny.sfx", runs)
 
 
+def case_simreads():
+    """Reads made by the reference's own `biokanga simreads` (descriptors lcl|usimreads|<n>|<chrom>|<start>|<end>|<len>|<strand>|...):
+    `align` checks every accepted alignment against the origin named in the descriptor (ReportAlignStats, Aligner.cpp:3556-3657),
+    logs "There are N (a 2 edge, b 1 edge) high confidence aligned simulated reads with M misaligned" and writes misaligned
+    reads as "iar" in CSV / BED (Aligner.cpp:6405-6418).  On the `repeats` genome (so that misaligned reads occur), on the
+    `lowcopy` genome under -r5, and on a small genome whose chromosome names hold '|' (the second descriptor form).
+    simreads seeds itself from the clock: the read files it wrote are committed, not re-creatable."""
+    d = os.path.join(GOLD, "simreads")
+    os.makedirs(d, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        for case, f in (("repeats", "repeats.sfx"), ("repeats", "genome.fa"), ("repeats", "r100.fa"), ("lowcopy", "lowcopy.sfx"),
+                        ("lowcopy", "genome.fa")):
+            dst = f if f != "genome.fa" else case + ".fa"
+            with gzip.open(os.path.join(GOLD, case, f + ".gz"), "rb") as a, open(os.path.join(tmp, dst), "wb") as b:
+                shutil.copyfileobj(a, b)
+        # a genome whose chromosome names are three '|' separated parts
+        g = synth.make_genome([9000, 7000, 5000], seed=71, repeat_frac=0.2, repeat_len=(100, 600), n_runs=0)
+        g = [("gnl|UG|Ta%d" % (k + 1), seq) for k, (_, seq) in enumerate(g)]
+        synth.write_fasta(os.path.join(tmp, "piped.fa"), g)
+        run(["index", "-i", "piped.fa", "-o", "piped.sfx", "-r", "piped", "-F", "idx.log"], tmp)
+        gz(os.path.join(tmp, "piped.sfx"), os.path.join(d, "piped.sfx.gz"))
+        sim = lambda genome, out, extra: run(["simreads", "-i", genome, "-o", out, "-T1", "-F", out + ".log"] + extra, tmp)
+        sim("repeats.fa", "se_g1.fa", ["-n", "3000", "-l", "100", "-g1", "-z2"])
+        sim("repeats.fa", "se_g3.fa", ["-n", "2000", "-l", "80", "-g3", "-z0.15"])
+        sim("repeats.fa", "pe1.fa", ["-O", "pe2.fa", "-p", "-n", "3000", "-l", "100", "-j", "250", "-J", "450", "-g1", "-z1"])
+        sim("lowcopy.fa", "lc.fa", ["-n", "2000", "-l", "100", "-g1", "-z1"])
+        sim("piped.fa", "piped_se.fa", ["-n", "1500", "-l", "100", "-g1", "-z2"])
+
+        def fasta_records(path):
+            return [">" + x for x in open(path).read().split(">")[1:]]
+        plain = fasta_records(os.path.join(tmp, "r100.fa"))
+        simr = fasta_records(os.path.join(tmp, "se_g1.fa"))
+        # not simulated first: the first accepted read decides, nothing is checked; simulated first, then plain reads: the check
+        # stops for good at the first accepted read whose descriptor does not parse
+        open(os.path.join(tmp, "mix_a.fa"), "w").write("".join(plain[:300] + simr[:700]))
+        open(os.path.join(tmp, "mix_b.fa"), "w").write("".join(simr[:500] + plain[:200] + simr[500:900]))
+        reads = ["se_g1.fa", "se_g3.fa", "pe1.fa", "pe2.fa", "lc.fa", "piped_se.fa", "mix_a.fa", "mix_b.fa"]
+        for f in reads:
+            gz(os.path.join(tmp, f), os.path.join(d, f + ".gz"))
+        meta = {}
+        for tag, index, rds, args, out in (
+                ("se_g1", "repeats", ["se_g1.fa"], ["-s3", "-M0"], "se_g1.csv"),
+                ("se_g1bed", "repeats", ["se_g1.fa"], ["-s3", "-M4"], "se_g1.bed"),
+                ("se_g1sam", "repeats", ["se_g1.fa"], ["-s3", "-M6"], "se_g1.sam"),
+                ("se_g1x", "repeats", ["se_g1.fa"], ["-s5", "-M0", "-x6"], "se_g1x.csv"),
+                ("se_g3", "repeats", ["se_g3.fa"], ["-s8", "-M0", "-e2"], "se_g3.csv"),
+                ("se_g3r1", "repeats", ["se_g3.fa"], ["-s8", "-M2", "-r1", "-R4", "-Zrep1"], "se_g3r1.csv"),
+                ("pe_U1", "repeats", ["pe1.fa", "pe2.fa"], ["-s3", "-M0", "-U1", "-d100", "-D600"], "pe_U1.csv"),
+                ("pe_U2", "repeats", ["pe1.fa", "pe2.fa"], ["-s3", "-M0", "-U2", "-d100", "-D400"], "pe_U2.csv"),
+                ("pe_U3sam", "repeats", ["pe1.fa", "pe2.fa"], ["-s3", "-M6", "-U3", "-d100", "-D600"], "pe_U3.sam"),
+                ("lc_r5", "lowcopy", ["lc.fa"], ["-s3", "-M0", "-r5", "-R5"], "lc_r5.csv"),
+                ("lc_r3", "lowcopy", ["lc.fa"], ["-s3", "-M0", "-r3", "-R5"], "lc_r3.csv"),
+                ("piped", "piped", ["piped_se.fa"], ["-s3", "-M0"], "piped.csv"),
+                ("pipedbed", "piped", ["piped_se.fa"], ["-s5", "-M4", "-x4"], "piped.bed"),
+                ("mix_a", "repeats", ["mix_a.fa"], ["-s3", "-M0"], "mix_a.csv"),
+                ("mix_b", "repeats", ["mix_b.fa"], ["-s3", "-M0"], "mix_b.csv")):
+            threads = "-T1" if "-r5" in args else "-T4"
+            run(["align", "-I", index + ".sfx", "-i", rds[0], threads, "-o", out, "-F", tag + ".log"] + (["-u", rds[1]] if len(rds) > 1 else []) + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [r + ".gz" for r in rds], "index": index}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -562,4 +626,6 @@ if __name__ == "__main__":
         case_interplay()
     if "pefilter" in which:
         case_pefilter()
+    if "simreads" in which:
+        case_simreads()
     print("fixtures written under", GOLD)

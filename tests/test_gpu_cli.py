@@ -225,6 +225,43 @@ def test_cli_option_interplay_matches_reference(tag, golden_dir, tmp_path):
     assert not os.path.exists(tmp_path / "n.fa") and not os.path.exists(tmp_path / "m.fa")
 
 
+SIM_TAGS = ["se_g1", "se_g1bed", "se_g1sam", "se_g1x", "se_g3", "se_g3r1", "pe_U1", "pe_U2", "pe_U3sam", "lc_r5", "lc_r3", "piped",
+            "pipedbed", "mix_a", "mix_b"]
+
+
+@pytest.mark.parametrize("tag", SIM_TAGS)
+def test_cli_simulated_read_truth_check_matches_reference(tag, golden_dir, tmp_path):
+    """Reads written by the reference's own `simreads` carry their origin in the descriptor; `align` checks every accepted
+    alignment against it (ReportAlignStats, Aligner.cpp:3556-3657): the summary gains "There are N (a 2 edge, b 1 edge) high
+    confidence aligned simulated reads with M misaligned" and misaligned reads are written as "iar" (CSV, BED).  SE / PE,
+    behind -x / -r1 / -r3 / -r5 / -Z, chromosome names holding '|' (second descriptor form), and read sets that mix simulated
+    and plain reads (the first accepted read decides; the first one that does not parse ends the checking)."""
+    import json
+    import shutil
+    fdir = os.path.join(gu.GOLD, "simreads")
+    run = json.load(open(os.path.join(fdir, "runs.json")))[tag]
+    if run["index"] in gu.CASES:
+        sfx = gu.sfx_path(run["index"], golden_dir)
+    else:
+        sfx = os.path.join(str(golden_dir), run["index"] + ".sfx")
+        if not os.path.exists(sfx):
+            with gzip.open(os.path.join(fdir, run["index"] + ".sfx.gz"), "rb") as a, open(sfx, "wb") as b:
+                shutil.copyfileobj(a, b)
+    files = [os.path.join(fdir, f) for f in run["reads"]]
+    subprocess.run([CLI, "align", "-I", sfx, "-i", files[0]] + (["-u", files[1]] if len(files) > 1 else []) + run["args"] +
+                   ["-o", run["out"], "-F", "o.log"], check=True, stdout=subprocess.DEVNULL, cwd=tmp_path)
+    ours, ref = _lines(tmp_path / run["out"]), _lines(os.path.join(fdir, run["out"] + ".gz"))
+    assert [x for x in ours if x.startswith(("@", "track"))] == [x for x in ref if x.startswith(("@", "track"))]
+    if tag == "lc_r5":   # one record per locus, numbered in read order: line for line
+        assert {ln.split(",", 1)[0]: ln for ln in ours} == {ln.split(",", 1)[0]: ln for ln in ref}
+    assert sorted(ours) == sorted(ref)
+    if tag in ("lc_r5", "lc_r3", "se_g3", "piped", "pipedbed"):   # the fixtures that hold misaligned reads
+        assert any('"iar"' in x or "\tiar\t" in x for x in ref)
+    exp_log = [x for x in open(os.path.join(fdir, tag + ".log")).read().splitlines()
+               if not x.startswith(("Sorting alignments", "Header written", "Reported SAM", "Completed reporting SAM"))]
+    assert summary_block(tmp_path / "o.log") == exp_log
+
+
 def _bgzf_blocks(raw):
     import struct
     o, out = 0, []

@@ -82,6 +82,11 @@ def test_host_option_interplay_matches_reference(tag, cli, golden_dir, tmp_path)
     g.test_cli_option_interplay_matches_reference(tag, golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", g.SIM_TAGS)
+def test_host_simulated_read_truth_check_matches_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_simulated_read_truth_check_matches_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
