@@ -639,13 +639,15 @@ def run_reference(args):
     dev = torch.device("cuda", 0)
     cores = os.cpu_count() or 1
     total_steps = args.steps + args.warmup
-    # the reference sleeps 5 s while its workers run (Aligner.cpp:8799): a step must take well over 5 s of
-    # alignment for its log timestamps to measure work, hence millions of reads per step
-    sample = args.ref_sample
-    if total_steps > 4:
-        sample = max(2500000, int(sample * 4 / total_steps))
+    # The reference's main thread sleeps a fixed 5 s after starting its workers and only then joins them
+    # (Aligner.cpp:8797-8801): an align phase that its log times at ~5.0 s measured the sleep, not the work.  So every
+    # step must keep the workers busy well beyond that: the sample grows with the core count, every step is checked
+    # against a 7 s floor, and a step that lands under it doubles the sample (up to the pool generated here) and is redone.
+    pool = int(min(48_000_000, max(args.ref_sample, 400_000 * cores)))
+    sample = int(min(pool, max(args.ref_sample, 250_000 * cores)))
+    floor_s = 7.0
     saved_reads = args.reads
-    args.reads = sample * total_steps
+    args.reads = pool
     d_seq, d_sa, ents, n, d_bases, d_offs = build_workload(args, 0, 1, dev, torch, None)
     host_seq = d_seq.cpu().numpy()
     host_sa = d_sa.cpu().numpy().view(np.uint32)
@@ -655,6 +657,8 @@ def run_reference(args):
     L = args.read_len
     use_bin = os.path.exists(po.REF_BIN) and not args.ref_port
     times = []
+    floor_hit = False
+    ref_counts = None
     if use_bin:
         tmp = tempfile.mkdtemp(prefix="bkxref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
@@ -662,34 +666,53 @@ def run_reference(args):
             bkx.write_sfx(os.path.join(tmp, "g.sfx"), host_seq, host_sa, 4, ents, name="synth")
             log("[bench] wrote %.1f GB .sfx in %.1fs" % (os.path.getsize(os.path.join(tmp, "g.sfx")) / 1e9, time.time() - t0))
             del host_seq, host_sa
-            for s in range(total_steps):
-                rd = h_bases[s * sample * L:(s + 1) * sample * L].reshape(sample, L)
-                write_fasta_fast(os.path.join(tmp, "r.fa"), rd, synth.BASES)
+
+            def one_step(m):
+                """One unmodified `biokanga align` over the first m reads of the pool: (align-phase seconds from its own log
+                timestamps, reads it says it aligned)."""
+                write_fasta_fast(os.path.join(tmp, "r.fa"), h_bases[:m * L].reshape(m, L), synth.BASES)
                 subprocess.run([po.REF_BIN, "align", "-I", "g.sfx", "-i", "r.fa", "-s%d" % args.max_subs, "-M0", "-o",
                                 "out.csv", "-F", "run.log", "-T%d" % min(cores, 128)], cwd=tmp, check=True,
                                stdout=subprocess.DEVNULL)
-                ts = {}
+                ts, done = {}, None
                 for ln in open(os.path.join(tmp, "run.log"), errors="replace"):
-                    m = re.match(r"\[\w+ +\d+ (\d+):(\d+):(\d+)\.(\d+) \d+\]", ln)
-                    if not m:
+                    mt = re.match(r"\[\w+ +\d+ (\d+):(\d+):(\d+)\.(\d+) \d+\]", ln)
+                    if not mt:
                         continue
-                    t = int(m.group(1)) * 3600 + int(m.group(2)) * 60 + int(m.group(3)) + int(m.group(4)) / 1000.0
+                    t = int(mt.group(1)) * 3600 + int(mt.group(2)) * 60 + int(mt.group(3)) + int(mt.group(4)) / 1000.0
                     if "Now aligning with minimum core size" in ln:
                         ts["a"] = t
-                    if "Alignment of" in ln and "completed" in ln:
+                    md = re.search(r"Alignment of (\d+) from (\d+) loaded completed", ln)
+                    if md:
                         ts["b"] = t
-                dt = (ts["b"] - ts["a"]) % 86400
-                log("[bench] reference step %d: %d reads, align phase %.2fs" % (s, sample, dt))
+                        done = (int(md.group(1)), int(md.group(2)))
+                return (ts["b"] - ts["a"]) % 86400, done
+
+            s = 0
+            while s < total_steps:
+                dt, done = one_step(sample)
+                log("[bench] reference step %d: %d reads, align phase %.2fs (its log: aligned %s of %s loaded)" % (
+                    s, sample, dt, done[0] if done else "?", done[1] if done else "?"))
+                if dt < floor_s:
+                    if sample < pool:   # the 5 s sleep, not the work: more reads, start over
+                        sample = int(min(pool, sample * 2))
+                        times, s = [], 0
+                        log("[bench] reference step under the %.0f s floor of its fixed sleep: sample raised to %d reads" % (floor_s, sample))
+                        continue
+                    floor_hit = True
                 if s >= args.warmup:
                     times.append(dt)
+                    ref_counts = done
+                s += 1
         finally:
             subprocess.run(["rm", "-rf", tmp])
         kind = "reference"
     else:
         oidx = po.OracleIndex(seq=host_seq, sa=host_sa, el_size=4, entries=ents)
         p = oidx.default_params(0, max_subs=args.max_subs)
+        sample = int(min(sample, args.ref_sample))   # the port has no sleep: the plain bounded sample
         for s in range(total_steps):
-            bases = h_bases[s * sample * L:(s + 1) * sample * L]
+            bases = h_bases[:sample * L]
             offs = np.arange(sample + 1, dtype=np.uint64) * L
             t0 = time.perf_counter()
             oidx.align(p, bases, offs, nthreads=cores)
@@ -708,8 +731,12 @@ def run_reference(args):
                                                                                  args.read_subs, args.max_subs, sample),
                    "genome_symbols": int(n), "read_len": L, "max_subs_per_100bp": args.max_subs},
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind,
-                         "sample": "%d reads per step; align phase from the reference's log timestamps" % sample
-                         if kind == "reference" else "%d reads per step, %d threads" % (sample, cores)},
+                         "sample": "%d reads per step (one unmodified `biokanga align -T%d` run per step); align phase from the "
+                                   "reference's own log timestamps, every step above the %.0f s floor of its fixed 5 s sleep: %s" % (
+                                       sample, min(cores, 128), floor_s, not floor_hit)
+                         if kind == "reference" else "%d reads per step, %d threads" % (sample, cores),
+                         "step_seconds": [round(t, 2) for t in times], "floor_hit": floor_hit,
+                         "reference_log_reads_aligned": ref_counts[0] if ref_counts else None},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

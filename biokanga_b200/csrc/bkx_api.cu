@@ -1211,6 +1211,14 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
     if (!bases || !offsets) return fail(BKX_ERR_PARAM, "orphan recovery needs the read sequences");
   }
   if (n_pairs == 0) return BKX_OK;
+  int Lmax = 0;
+  if (rescue) {  // checked before anything is copied or launched: the caller's records stay untouched on error
+    for (uint64_t i = 0; i < 2 * (uint64_t)n_pairs; ++i) {
+      if (offsets[i + 1] < offsets[i]) return fail(BKX_ERR_PARAM, "offsets not monotonic at read %llu", (unsigned long long)i);
+      Lmax = std::max<int>(Lmax, (int)std::min<uint64_t>(offsets[i + 1] - offsets[i], 1u << 30));
+    }
+    if (Lmax > kRescueMaxLen) return fail(BKX_ERR_PARAM, "read length %d exceeds cMaxSeqLen", Lmax);
+  }
   std::lock_guard<std::mutex> lk(x->mtx);
   CU(cudaSetDevice(x->device));
   cudaStream_t st = x->slot[0].st;
@@ -1224,10 +1232,8 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
   unsigned int* cnt = x->d_cursor[0];  // [0] rescue cursor, [3] orphan count
   size_t bytes = (size_t)n_pairs * 2 * sizeof(bkx_read_result);
   cudaError_t e = cudaMalloc((void**)&d_res, bytes);
-  int Lmax = 0;
   if (e == cudaSuccess && rescue) {
     uint64_t nb = offsets[2 * (uint64_t)n_pairs] - offsets[0];
-    for (uint64_t i = 0; i < 2 * (uint64_t)n_pairs; ++i) Lmax = std::max<int>(Lmax, (int)(offsets[i + 1] - offsets[i]));
     e = cudaMalloc((void**)&d_list, (size_t)n_pairs * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_bases, nb + 64);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_offs, (2 * (size_t)n_pairs + 1) * 8);
@@ -1237,7 +1243,7 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_res, results, bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = launch_pair(*pe, d_res, n_pairs, x->d_pe_stats, x->d_len_dist, d_list, cnt + 3, x->d_chrom_keep, st);
-  if (e == cudaSuccess && rescue && Lmax <= kRescueMaxLen)
+  if (e == cudaSuccess && rescue)
     e = launch_rescue(x->d, k, *pe, d_res, d_list, cnt + 3, d_bases - offsets[0], d_offs, std::max(Lmax, 32), x->d_pe_stats,
                       x->d_len_dist, cnt, x->d_chrom_keep, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(results, d_res, bytes, cudaMemcpyDeviceToHost, st);
@@ -1251,7 +1257,6 @@ extern "C" int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(d_res); cudaFree(d_list); cudaFree(d_bases); cudaFree(d_offs);
   if (e != cudaSuccess) return fail(BKX_ERR_CUDA, "bkx_pair_reads: %s", cudaGetErrorString(e));
-  if (rescue && Lmax > kRescueMaxLen) return fail(BKX_ERR_PARAM, "read length %d exceeds cMaxSeqLen", Lmax);
   x->launches += rescue ? 2 : 1;
   if (stats) {
     uint64_t* d = (uint64_t*)stats;

@@ -6,6 +6,8 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <mutex>
+
 namespace bkx {
 
 // ------------------------------------------------------------------------------------------------
@@ -211,17 +213,28 @@ cudaError_t build_prefix_table(const DevIndex& I, int k, void* table, bool wide,
 // ------------------------------------------------------------------------------------------------
 constexpr int kGroupsPerBlock = kBlockThreads / kGroup;
 
-// the dynamic shared-memory opt-in of a kernel is only ever raised (several indexes share the kernels)
+// The dynamic shared-memory opt-in of a kernel (cudaFuncAttributeMaxDynamicSharedMemorySize) belongs to the CURRENT
+// DEVICE, so what has been configured is remembered per device; within a device it is only ever raised (several indexes
+// and several host threads -- `bkx-align --gpus N` drives one thread per GPU -- share the kernels), under a lock.
+struct SmemOptIn {
+  std::mutex mtx;
+  size_t configured[64] = {};
+};
 template <typename K>
-static cudaError_t ensure_smem(K kernel, size_t smem, size_t& configured) {
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t ensure_smem(K kernel, size_t smem, SmemOptIn& cfg) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  std::lock_guard<std::mutex> lk(cfg.mtx);
+  if (smem > cfg.configured[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    cfg.configured[dev] = smem;
   }
   return cudaSuccess;
 }
-static size_t g_smem_general = 0, g_smem_fast = 0, g_smem_fast_mlx = 0;
+static SmemOptIn g_smem_general, g_smem_fast, g_smem_fast_mlx, g_smem_rescue;
 
 __host__ __device__ inline size_t group_smem_bytes(int W) {
   size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + (kGroup + 2) * 4;
@@ -1294,8 +1307,7 @@ cudaError_t launch_rescue(const DevIndex& I, const KParams& P, const bkx_pe_para
                           const uint64_t* offs, int Lmax, bkx_pe_stats* stats, uint32_t* len_dist, unsigned int* cursor,
                           const uint8_t* keep, cudaStream_t st) {
   size_t smem = rescue_warp_bytes(Lmax) * kRescueWarps;
-  static size_t configured = 0;
-  cudaError_t e = ensure_smem(orphan_rescue_kernel, smem, configured);
+  cudaError_t e = ensure_smem(orphan_rescue_kernel, smem, g_smem_rescue);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;

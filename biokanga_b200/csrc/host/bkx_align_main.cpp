@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cerrno>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -36,7 +37,9 @@
 #include <thread>
 #include <vector>
 
+#include <glob.h>
 #include <regex.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "../../../include/bkx.h"
@@ -126,6 +129,7 @@ struct Opts {
   std::string none_file, multi_file;     // -j / -J: FASTA of the reads without a locus / with too many loci
   std::vector<std::string> in, pair;
   std::string sfx, out, logfile, title;
+  std::string sqlite_file, exp_name, exp_descr;   // -q / -w / -W: SQLite results-summary database (validated, not written)
 };
 
 // ---- read files: slurped whole (gzip inflated on the way), split at record boundaries, parsed by all host threads.
@@ -288,6 +292,31 @@ static bool parse_file(const std::string& path, unsigned threads, std::vector<ch
   return true;
 }
 
+// Single-end runs: every -i is a file specification that may hold wildcards (CSimpleGlob with SG_GLOB_FULLSORT,
+// ProcLoadReadFiles, Aligner.cpp:10474-10520): the matches of one specification are loaded in case-insensitive name
+// order; a specification without a match ends the run.  Paired-end file names are taken as they are.
+static int expand_input_specs(Opts& o) {
+  if (o.pe_mode) return 0;
+  std::vector<std::string> files;
+  for (const std::string& spec : o.in) {
+    std::vector<std::string> found;
+    if (spec.find('*') == std::string::npos && spec.find('?') == std::string::npos) {
+      if (access(spec.c_str(), F_OK) == 0) found.push_back(spec);
+    } else {
+      glob_t g;
+      memset(&g, 0, sizeof(g));
+      if (glob(spec.c_str(), GLOB_MARK | GLOB_NOSORT, nullptr, &g) == 0)
+        for (size_t k = 0; k < g.gl_pathc; ++k) found.push_back(g.gl_pathv[k]);
+      globfree(&g);
+      std::sort(found.begin(), found.end(), [](const std::string& a, const std::string& b) { return strcasecmp(a.c_str(), b.c_str()) < 0; });
+    }
+    if (found.empty()) { diag("Unable to glob '%s", spec.c_str()); return -1; }
+    files.insert(files.end(), found.begin(), found.end());
+  }
+  o.in.swap(files);
+  return 0;
+}
+
 static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (default -g3: qualities ignored)
   bool pe = o.pe_mode != 0;
   uint8_t code_tab[256];
@@ -401,24 +430,97 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
   return 0;
 }
 
-// ---- option parsing (kanga.cpp:194-294 letters; values may be attached or separate) ----------------
+// ---- option parsing: the option table of kanga.cpp:194-294 -- short letters (values attached or separate, literal flags
+//      may be bundled), the long names (--name=value or --name value), and parameter files: an argument "@file" is replaced
+//      by the options read from that file, one or more per line, white space separated unless quoted, lines starting with
+//      '#', ';' or "//" skipped (CUtility::arg_parsefromfile, libbiokanga/Utility.cpp:793-912; called at kanga.cpp:298).
 static bool takes_value(char c) { return strchr("fFqwWm#QcaAkgryYlLR4esnx6pKGP1MtBiUdDuISo7jJO89H5ZzT", c) != nullptr; }
 
-static int parse(int argc, char** argv, Opts& o) {
+static const struct { const char* name; char letter; } kLongOpts[] = {
+    {"help", 'h'}, {"version", 'v'}, {"ver", 'v'}, {"FileLogLevel", 'f'}, {"log", 'F'}, {"mode", 'm'}, {"format", 'M'}, {"pemode", 'U'},
+    {"bisulfite", 'b'}, {"colorspace", 'C'}, {"pcrwin", 'k'}, {"in", 'i'}, {"pair", 'u'}, {"priorityregionfile", 'B'},
+    {"nofiltpriority", 'V'}, {"pairminlen", 'd'}, {"pairmaxlen", 'D'}, {"pairstrand", 'E'}, {"alignstrand", 'Q'},
+    {"samplenthrawread", '#'}, {"minchimeric", 'c'}, {"chimericrpt", '0'}, {"quality", 'g'}, {"sfx", 'I'}, {"out", 'o'},
+    {"microindellen", 'a'}, {"splicejunctlen", 'A'}, {"stats", 'O'}, {"nonealign", 'j'}, {"multialign", 'J'}, {"siteprefs", '8'},
+    {"siteprefsofs", '9'}, {"lociconstraints", '5'}, {"contaminants", 'H'}, {"snpfile", 'S'}, {"snpcentroid", '7'},
+    {"markerlen", 'K'}, {"markerpolythres", 'G'}, {"editdelta", 'e'}, {"substitutions", 's'}, {"minflankexacts", 'x'},
+    {"pcrprimersubs", '6'}, {"maxns", 'n'}, {"title", 't'}, {"chromexclude", 'Z'}, {"chromeinclude", 'z'}, {"threads", 'T'},
+    {"maxmulti", 'R'}, {"clampmaxmulti", 'X'}, {"bestmatches", 'N'}, {"mlmode", 'r'}, {"snpreadsmin", 'p'}, {"snpnonrefpcnt", '1'},
+    {"pecircularised", '2'}, {"petranslendist", '3'}, {"rptsamseqsthres", '4'}, {"qvalue", 'P'}, {"trim5", 'y'}, {"trim3", 'Y'},
+    {"minacceptreadlen", 'l'}, {"maxacceptreadlen", 'L'}, {"sumrslts", 'q'}, {"experimentname", 'w'}, {"experimentdescr", 'W'}};
+
+// "@file" arguments replaced by the options the file holds
+static bool expand_param_files(int argc, char** argv, std::vector<std::string>& out) {
+  for (int i = 0; i < argc; ++i) {
+    if (argv[i][0] != '@') { out.push_back(argv[i]); continue; }
+    std::string path = argv[i] + 1;
+    while (!path.empty() && isspace((unsigned char)path.front())) path.erase(path.begin());
+    while (!path.empty() && isspace((unsigned char)path.back())) path.pop_back();
+    if (path.empty()) { printf("No options file specified following '@' switch"); return false; }
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) { printf("Unable to open options file '%s'\nError: %s", path.c_str(), strerror(errno)); return false; }
+    char line[8196];
+    while (fgets(line, sizeof(line), f)) {
+      char* b = line;
+      while (*b && isspace((unsigned char)*b)) ++b;
+      char* e = b + strlen(b);
+      while (e > b && isspace((unsigned char)e[-1])) --e;
+      *e = '\0';
+      if (!*b || *b == '#' || *b == ';' || (b[0] == '/' && b[1] == '/')) continue;
+      std::string opt;
+      bool in_quotes = false, in_param = false;
+      for (const char* c = b;; ++c) {
+        char ch = *c == 0x16 ? '-' : *c;   // "on some systems '-' is represented as 0x16"
+        if (ch == '"' || ch == '\'') { in_quotes = !in_quotes; in_param = true; opt += ch; continue; }
+        if (ch && ((ch != ' ' && ch != '\t') || in_quotes)) { in_param = true; opt += ch; continue; }
+        if (in_param) { out.push_back(opt); opt.clear(); in_param = false; in_quotes = false; }
+        if (!ch) break;
+      }
+    }
+    fclose(f);
+  }
+  return true;
+}
+
+static int parse(int argc0, char** argv0, Opts& o) {
+  std::vector<std::string> args;
+  if (!expand_param_files(argc0, argv0, args)) return -1;
+  const int argc = (int)args.size();
   int i = 1;
-  if (i < argc && (!strcmp(argv[i], "align") || !strcmp(argv[i], "kanga"))) ++i;
+  if (i < argc && (args[i] == "align" || args[i] == "kanga")) ++i;
   std::vector<std::string> unsupported;
   for (; i < argc; ++i) {
-    std::string a = argv[i];
-    if (a == "--gpus" && i + 1 < argc) { o.gpus = atoi(argv[++i]); continue; }
+    std::string a = args[i];
+    if (a == "--gpus" && i + 1 < argc) { o.gpus = atoi(args[++i].c_str()); continue; }
     if (a.rfind("--gpus=", 0) == 0) { o.gpus = atoi(a.c_str() + 7); continue; }
-    if (a.size() < 2 || a[0] != '-' || a[1] == '-') { fprintf(stderr, "unrecognised argument '%s'\n", a.c_str()); return -1; }
-    char c = a[1];
+    // one argument may hold several short options (-EX, -Xs3); a long option is rewritten into its short form first
+    std::string shorts;
+    std::string attached;
+    bool have_attached = false;
+    if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+      const size_t eq = a.find('=');
+      const std::string name = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+      char letter = 0;
+      for (const auto& lo : kLongOpts) if (name == lo.name) letter = lo.letter;
+      if (!letter) { fprintf(stderr, "unrecognised argument '%s'\n", a.c_str()); return -1; }
+      shorts = std::string(1, letter);
+      if (eq != std::string::npos) { attached = a.substr(eq + 1); have_attached = true; }
+    } else if (a.size() >= 2 && a[0] == '-' && a[1] != '-') {
+      shorts = a.substr(1);
+    } else {
+      fprintf(stderr, "unrecognised argument '%s'\n", a.c_str());
+      return -1;
+    }
+   for (size_t ci = 0; ci < shorts.size(); ++ci) {
+    char c = shorts[ci];
     std::string v;
     if (takes_value(c)) {
-      if (a.size() > 2) v = a.substr(2);
-      else if (i + 1 < argc) v = argv[++i];
+      if (have_attached) v = attached;
+      else if (ci + 1 < shorts.size()) v = shorts.substr(ci + 1);
+      else if (i + 1 < argc) v = args[++i];
       else { fprintf(stderr, "option -%c needs a value\n", c); return -1; }
+      ci = shorts.size();
+      if (v.size() >= 2 && (v.front() == '"' || v.front() == '\'') && v.back() == v.front()) v = v.substr(1, v.size() - 2);
     }
     int iv = atoi(v.c_str());
     switch (c) {
@@ -467,14 +569,22 @@ static int parse(int argc, char** argv, Opts& o) {
       case 'X': o.clamp_ml = true; break;
       case '5': o.constraints_file = v; break;
       case 'O': o.stats_file = v; break;
+      case 'q': o.sqlite_file = v; break;   // results-summary database: accepted, see below
+      case 'w': o.exp_name = v; break;
+      case 'W': o.exp_descr = v; break;
       case 'B': case 'H': case 'S': case '7': case '8':
-      case 'q': unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
+        unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
+      case 'v':
+        printf("\nbiokanga align Version 4.4.2 (bkx B200 path)\n");
+        return 1;
       case 'h':
         printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -M0..6 -g -t -U -d -D -E "
-               "-y -Y -l -L -# -5 -k -6 -x -Z -z -j -J -O -4 -T -i -u -I -o -F [--gpus N]\n");
+               "-y -Y -l -L -# -5 -k -6 -x -Z -z -j -J -O -4 -T -i -u -I -o -F -q -w -W [--gpus N], the reference's long option names, "
+               "and @file parameter files\n");
         return 1;
-      default: break;  // remaining reference options have no effect on this path (-w -W -K -G -P -1 -9 -V -0 -3 -v)
+      default: break;  // remaining reference options have no effect on this path (-K -G -P -1 -9 -V -0 -3)
     }
+   }
   }
   if (!unsupported.empty()) {
     for (auto& u : unsupported) fprintf(stderr, "bkx-align: option %s is not supported by the accelerated path\n", u.c_str());
@@ -482,6 +592,10 @@ static int parse(int argc, char** argv, Opts& o) {
   }
   // validation mirrors kanga.cpp:452-862
   if (o.sfx.empty() || o.in.empty() || o.out.empty()) { fprintf(stderr, "bkx-align: -I, -i and -o are required\n"); return -1; }
+  if (!o.sqlite_file.empty()) {   // kanga.cpp:381-404: the summary database needs an experiment name and description
+    if (o.exp_name.empty()) { fprintf(stderr, "Error: After removal of whitespace, no SQLite experiment name specified with '-w<str>' option\n"); return -1; }
+    if (o.exp_descr.empty()) { fprintf(stderr, "Error: After removal of whitespace, no SQLite experiment description specified with '-W<str>' option\n"); return -1; }
+  }
   if (o.pmode < 0 || o.pmode > 3) { fprintf(stderr, "Error: Processing mode '-m%d' must be in range 0..3\n", o.pmode); return -1; }
   if (o.max_subs < 0 || o.max_subs > 15) { fprintf(stderr, "Error: max substitutions '-s%d' must be in range 0..15\n", o.max_subs); return -1; }
   if (o.edit_delta < 1 || o.edit_delta > 2) { fprintf(stderr, "Error: Min Hamming edit distance '-e%d' must be in range 1..2\n", o.edit_delta); return -1; }
@@ -1614,6 +1728,9 @@ int main(int argc, char** argv) {
   if (!o.logfile.empty()) g_log = fopen(o.logfile.c_str(), "w");
   auto t_start = std::chrono::steady_clock::now();
   diag("Subprocess align Version 4.4.2 (bkx B200 path) starting");
+  if (!o.sqlite_file.empty())
+    diag("Note: results summary database '%s' (-q, experiment '%s') is outside the accelerated path and is not written", o.sqlite_file.c_str(), o.exp_name.c_str());
+  if (expand_input_specs(o) < 0) return 1;
 
   // ---- chromosome filter expressions are compiled up front, so that a malformed one stops the run before any work
   //      (CompileChromRegExprs, Aligner.cpp:4736-4798: POSIX extended, case insensitive)

@@ -600,10 +600,35 @@ def case_simreads():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_grammar():
+    """Option grammar of the front end (kanga.cpp:194-298): a parameter file (@file: several options per line, comments,
+    quoted values), long option names, and a single-end input specification with wildcards -- three read files whose
+    case-insensitive name order (A_, b_, C_) differs from their byte order, so the read ids in the CSV pin the load order."""
+    d = os.path.join(GOLD, "grammar")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("tiny.sfx", "r100.fa"):
+            with gzip.open(os.path.join(tiny, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        recs = [">" + x for x in open(os.path.join(tmp, "r100.fa")).read().split(">")[1:]]
+        parts = {"b_part.fa": recs[:400], "A_part.fa": recs[400:900], "C_part.fa": recs[900:1300]}
+        for nm, rr in parts.items():
+            open(os.path.join(tmp, nm), "w").write("".join(rr))
+            gz(os.path.join(tmp, nm), os.path.join(d, nm + ".gz"))
+        params = ["# parameter file for the grammar fixture", "", "-s3 --format=0", "; another comment", "// and another",
+                  "--editdelta 1   -T4", '-t "my track"', "--in=*_part.fa"]
+        open(os.path.join(tmp, "params.txt"), "w").write("\n".join(params) + "\n")
+        shutil.copyfile(os.path.join(tmp, "params.txt"), os.path.join(d, "params.txt"))
+        run(["align", "@params.txt", "-I", "tiny.sfx", "--out", "g1.csv", "--log=g1.log"], tmp)
+        gz(os.path.join(tmp, "g1.csv"), os.path.join(d, "g1.csv.gz"))
+        strip_log(os.path.join(tmp, "g1.log"), os.path.join(d, "g1.log"))
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -628,4 +653,6 @@ if __name__ == "__main__":
         case_pefilter()
     if "simreads" in which:
         case_simreads()
+    if "grammar" in which:
+        case_grammar()
     print("fixtures written under", GOLD)

@@ -262,6 +262,38 @@ def test_cli_simulated_read_truth_check_matches_reference(tag, golden_dir, tmp_p
     assert summary_block(tmp_path / "o.log") == exp_log
 
 
+def test_cli_parameter_file_long_options_and_wildcards_match_reference(golden_dir, tmp_path):
+    """Option grammar (kanga.cpp:194-298, Utility.cpp:793-912): "@file" parameter files (several options per line, comment
+    lines, a quoted value), the long option names (--name=value and --name value), bundled flags, and a single-end input
+    specification with wildcards, whose matches load in case-insensitive name order (the read ids of the CSV pin it)."""
+    import shutil
+    fdir = os.path.join(gu.GOLD, "grammar")
+    sfx = gu.sfx_path("tiny", golden_dir)
+    for nm in ("A_part.fa", "b_part.fa", "C_part.fa"):
+        with gzip.open(os.path.join(fdir, nm + ".gz"), "rb") as a, open(tmp_path / nm, "wb") as b:
+            shutil.copyfileobj(a, b)
+    shutil.copyfile(os.path.join(fdir, "params.txt"), tmp_path / "params.txt")
+    subprocess.run([CLI, "align", "@params.txt", "-I", sfx, "--out", "g1.csv", "--log=g1.log"], check=True, stdout=subprocess.DEVNULL,
+                   cwd=tmp_path)
+    ref = _lines(os.path.join(fdir, "g1.csv.gz"))
+    assert sorted(_lines(tmp_path / "g1.csv")) == sorted(ref)
+    assert summary_block(tmp_path / "g1.log") == open(os.path.join(fdir, "g1.log")).read().splitlines()
+    # the same run spelled with short options, the three files named one by one in load order
+    subprocess.run([CLI, "align", "-I", sfx, "-i", "A_part.fa", "-i", "b_part.fa", "-iC_part.fa", "-s", "3", "-M0", "-o", "g2.csv"],
+                   check=True, stdout=subprocess.DEVNULL, cwd=tmp_path)
+    assert _lines(tmp_path / "g2.csv") == _lines(tmp_path / "g1.csv")
+    # bundled literal flags (-XE is -X -E), -q / -w / -W accepted (the summary database itself is not written)
+    subprocess.run([CLI, "align", "-I", sfx, "-i", "?_part.fa", "-Xs3", "-M0", "-o", "g3.csv", "-q", "sum.db", "-w", "exp", "-W", "descr"],
+                   check=True, stdout=subprocess.DEVNULL, cwd=tmp_path)
+    assert _lines(tmp_path / "g3.csv") == _lines(tmp_path / "g1.csv")
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", "A_part.fa", "-o", "x.csv", "-q", "sum.db"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "-w<str>" in r.stderr
+    r = subprocess.run([CLI, "align", "-I", sfx, "-i", "nomatch*.fa", "-o", "x.csv"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "Unable to glob" in r.stdout
+    r = subprocess.run([CLI, "align", "@missing.txt", "-I", sfx, "-o", "x.csv"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "Unable to open options file" in r.stdout
+
+
 def _bgzf_blocks(raw):
     import struct
     o, out = 0, []

@@ -83,9 +83,6 @@ def test_random_options_and_reads(seed, golden_dir):
             assert gm[valid].tobytes() == em[valid].tobytes(), (case, pmode, kw, general_only)
 
 
-@pytest.mark.xfail(strict=False, reason="open issue, DESIGN.md section 4: in about one GPU session out of seven a few loci of the "
-                   "`repeats` index become invisible for the life of the process (first seen through this test); the "
-                   "failure branch prints the GPU serial, a self-check of the live index and a fresh-index comparison")
 @pytest.mark.parametrize("seed", range(int(os.environ.get("BKX_FUZZ_PE_SEEDS", "30"))))
 def test_random_paired_end_options(seed, golden_dir):
     """Paired ends: random -U mode, insert range, -E, read length and substitutions; the fused host call (align + pair

@@ -87,6 +87,10 @@ def test_host_simulated_read_truth_check_matches_reference(tag, cli, golden_dir,
     g.test_cli_simulated_read_truth_check_matches_reference(tag, golden_dir, tmp_path)
 
 
+def test_host_parameter_file_long_options_and_wildcards_match_reference(cli, golden_dir, tmp_path):
+    g.test_cli_parameter_file_long_options_and_wildcards_match_reference(golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
