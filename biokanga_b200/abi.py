@@ -77,6 +77,10 @@ RESULT_DTYPE = np.dtype([
     ("match_len", "<u2"), ("mismatches", "u1"), ("flags", "u1"), ("seeds", "<u4"), ("cands", "<u4"),
     ("reserved", "<u4")])
 assert RESULT_DTYPE.itemsize == 32
+# bkx_read_result16: the record as it crosses PCIe in the compact host interface
+RESULT16_DTYPE = np.dtype([("nar_hr", "u1"), ("strand_flags", "u1"), ("num_hits", "u1"), ("mismatches", "u1"), ("low_mm", "i1"),
+                           ("nxt_low_mm", "i1"), ("low_hit_instances", "<i2"), ("chrom_id", "<u4"), ("match_loci", "<u4")])
+assert RESULT16_DTYPE.itemsize == 16
 MULTI_DTYPE = np.dtype([("chrom_id", "<u4"), ("match_loci", "<u4"), ("match_len", "<u2"), ("strand", "u1"),
                         ("mismatches", "u1")])
 assert MULTI_DTYPE.itemsize == 12

@@ -40,7 +40,17 @@ constexpr int kGroup = 8;            // lanes per read
 struct KParams {
   int max_subs, mmd, max_ns, strand_mode, max_hits, min_core_len, slides_per100, max_iter, max_nodes;
   int ml_mode, clamp_ml;
+  int prefetch;           // fast kernel: prefetch the next core's prefix-table entry into L2 (1) or not (0)
+  int scan_iters;         // fast kernel: cores a lane may run down per step looking for a non-empty bucket (0: one core per step)
   bkx_multi_hit* multi;   // -r5: max_hits slots per read of this launch, or nullptr
+};
+
+// The reads of a launch once more, 2-bit packed (base i of the launch's concatenation at bits [2((i + phase) % 32), +2) of
+// word (i + phase) / 32): the fast kernel takes a read from here when flags says it holds nothing but A C G T.
+struct Packed2Src {
+  const uint64_t* words = nullptr;   // 8-byte aligned, 16 readable bytes beyond the last base; nullptr: not given
+  const uint8_t* flags = nullptr;    // per read: != 0 -- take the read from the one-byte-per-base copy; nullptr: no such read
+  uint32_t phase = 0;
 };
 
 // What ProcCoredApprox stores for one read once AlignReads has returned (Aligner.cpp:9239-9245, 9310-9479): shared by

@@ -65,6 +65,15 @@ struct Slot {
   size_t orphans_cap = 0;
   uint64_t* d_offs = nullptr;
   bkx_read_result* d_out = nullptr;
+  // compact host interface (bkx_align_reads_packed2): 16-byte records out, u16 lengths / exception list in
+  bkx_read_result16* d_out16 = nullptr;
+  uint16_t* d_lens = nullptr;
+  uint64_t* d_exc_pos = nullptr;
+  uint8_t* d_exc_code = nullptr;
+  size_t exc_cap = 0;
+  void* d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  uint8_t* d_rflags = nullptr;   // per read of the slice: holds a non-ACGT base
   uint32_t* d_hard = nullptr;   // reads the fast kernel deferred to the general kernel
   size_t hard_cap = 0;
   size_t reads_cap = 0;
@@ -329,6 +338,12 @@ extern "C" void bkx_close_index(bkx_index* x) {
     if (x->slot[s].d_orphans) cudaFree(x->slot[s].d_orphans);
     if (x->slot[s].d_offs) cudaFree(x->slot[s].d_offs);
     if (x->slot[s].d_out) cudaFree(x->slot[s].d_out);
+    if (x->slot[s].d_out16) cudaFree(x->slot[s].d_out16);
+    if (x->slot[s].d_lens) cudaFree(x->slot[s].d_lens);
+    if (x->slot[s].d_exc_pos) cudaFree(x->slot[s].d_exc_pos);
+    if (x->slot[s].d_exc_code) cudaFree(x->slot[s].d_exc_code);
+    if (x->slot[s].d_scan_tmp) cudaFree(x->slot[s].d_scan_tmp);
+    if (x->slot[s].d_rflags) cudaFree(x->slot[s].d_rflags);
     if (x->slot[s].d_hard) cudaFree(x->slot[s].d_hard);
     if (x->slot[s].k0) cudaEventDestroy(x->slot[s].k0);
     if (x->slot[s].k1) cudaEventDestroy(x->slot[s].k1);
@@ -772,6 +787,10 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   k->max_iter = p->max_iter; k->max_nodes = p->max_ident_nodes;
   k->ml_mode = p->ml_mode; k->clamp_ml = p->clamp_max_ml ? 1 : 0;
   k->multi = nullptr;
+  k->prefetch = 0;   // measured: 31.5 ms without, 33.9 ms with (configs[1])
+  if (const char* ev = getenv("BKX_PREFETCH")) k->prefetch = atoi(ev) != 0;   // tuning hook
+  k->scan_iters = 0;
+  if (const char* ev = getenv("BKX_SCAN_ITERS")) k->scan_iters = std::max(0, std::min(64, atoi(ev)));   // tuning hook; 0 = one core per step
   return BKX_OK;
 }
 
@@ -846,7 +865,7 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
 // fast kernel over all reads, then the general kernel over the reads it deferred (same stream)
 static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n,
                        int W, bkx_read_result* d_out, bkx_align_stats* d_stats, int si, uint32_t* d_hard,
-                       cudaStream_t st) {
+                       cudaStream_t st, const Packed2Src& p2 = Packed2Src()) {
   unsigned int* cur = x->d_cursor[si];
   if (getenv("BKX_NO_FAST")) {
     CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, nullptr, nullptr, x->grid, st));
@@ -873,8 +892,9 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
     cudaEventRecord(t0, st);
   }
+  static const bool no_direct = getenv("BKX_NO_DIRECT2") != nullptr;   // tuning hook: ignore the 2-bit copy of the reads
   CU(launch_align_fast(x->d, k, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash[si], epoch_base,
-                       x->fast_grid, st));
+                       x->fast_grid, st, no_direct ? Packed2Src() : p2));
   if (trace) cudaEventRecord(t1, st);
   CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, d_hard, cur + 2, x->grid, st));
   if (trace) {
@@ -922,16 +942,70 @@ extern "C" int bkx_align_reads_device(bkx_index* x, const bkx_align_params* p, c
   return BKX_OK;
 }
 
+// Device-resident reads with a 2-bit copy beside the one-byte-per-base layout (see include/bkx.h)
+extern "C" int bkx_align_reads_device_packed2(bkx_index* x, const bkx_align_params* p, const uint8_t* d_bases,
+                                              const uint64_t* d_packed2, const uint8_t* d_read_flags, const uint64_t* d_offsets,
+                                              uint32_t n_reads, uint32_t max_read_len, bkx_read_result* d_out,
+                                              bkx_align_stats* d_stats, void* cuda_stream) {
+  if (!x || !d_bases || !d_packed2 || !d_offsets || !d_out) return fail(BKX_ERR_PARAM, "null argument");
+  if ((uintptr_t)d_packed2 & 7) return fail(BKX_ERR_PARAM, "the 2-bit stream must start on an 8-byte boundary");
+  KParams k;
+  int rc = check_params(p, &k);
+  if (rc < 0) return rc;
+  if (p->ml_mode >= BKX_ML_UNIQ) return fail(BKX_ERR_UNSUPPORTED, "-r3..5 need the host call bkx_align_reads_multi");
+  if (n_reads == 0) return BKX_OK;
+  std::lock_guard<std::mutex> lk(x->mtx);
+  CU(cudaSetDevice(x->device));
+  int W = 0;
+  if ((rc = prepare_launch(x, k, max_read_len, &W)) < 0) return rc;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : x->slot[0].st;
+  Slot& s = x->slot[0];
+  if (n_reads > s.hard_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (s.d_hard) cudaFree(s.d_hard);
+    s.hard_cap = (size_t)n_reads * 5 / 4;
+    CU(cudaMalloc((void**)&s.d_hard, s.hard_cap * 4));
+  }
+  Packed2Src psrc;
+  psrc.words = d_packed2; psrc.flags = d_read_flags; psrc.phase = 0;
+  CU(cudaEventRecord(s.k0, st));
+  if ((rc = launch_both(x, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, 0, s.d_hard, st, psrc)) < 0) return rc;
+  CU(cudaEventRecord(s.k1, st));
+  s.timed = true;
+  for (int si = 1; si < kSlots; ++si) x->slot[si].timed = false;
+  x->last_ms = -2.f;
+  return BKX_OK;
+}
+
 struct PeCall {   // the pairing half of a fused align + pair call
   const bkx_pe_params* pe = nullptr;
   bkx_pe_stats* stats = nullptr;
   uint32_t* len_dist = nullptr;
 };
 
-static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, bool packed4, const uint64_t* offsets,
-                      uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats, bkx_multi_hit* multi = nullptr,
-                      const PeCall* pec = nullptr) {
-  if (!x || !bases || !offsets || !out) return fail(BKX_ERR_PARAM, "null argument");
+// The reads of a host-buffer call, in one of the three layouts the ABI takes
+struct HostReads {
+  enum { BYTES = 0, PACKED4 = 1, PACKED2 = 2 };
+  int fmt = BYTES;
+  const uint8_t* data = nullptr;      // one byte per base / two bases per byte / four bases per byte
+  const uint64_t* offsets = nullptr;  // BYTES, PACKED4: start of every read, n_reads + 1 entries
+  const uint16_t* lens = nullptr;     // PACKED2: read lengths, or NULL with
+  uint32_t fixed_len = 0;             //          every read this long
+  const uint64_t* exc_pos = nullptr;  // PACKED2: bases that are not A C G T
+  const uint8_t* exc_code = nullptr;
+  uint64_t n_exc = 0;
+};
+
+static int align_host(bkx_index* x, const bkx_align_params* p, const HostReads& hr, uint32_t n_reads, void* out_any,
+                      bool compact_out, bkx_align_stats* stats, bkx_multi_hit* multi = nullptr, const PeCall* pec = nullptr) {
+  if (!x || !hr.data || !out_any) return fail(BKX_ERR_PARAM, "null argument");
+  const bool p2 = hr.fmt == HostReads::PACKED2, packed4 = hr.fmt == HostReads::PACKED4;
+  if (!p2 && !hr.offsets) return fail(BKX_ERR_PARAM, "null argument");
+  if (p2 && !hr.lens && (hr.fixed_len < 1 || hr.fixed_len > 2000)) return fail(BKX_ERR_PARAM, "fixed read length %u out of range 1..2000", hr.fixed_len);
+  if (p2 && hr.n_exc && (!hr.exc_pos || !hr.exc_code)) return fail(BKX_ERR_PARAM, "null exception list");
+  const uint64_t* offsets = hr.offsets;
+  bkx_read_result* out = compact_out ? nullptr : (bkx_read_result*)out_any;
+  bkx_read_result16* out16 = compact_out ? (bkx_read_result16*)out_any : nullptr;
   KParams k;
   int rc = check_params(p, &k);
   if (rc < 0) return rc;
@@ -970,6 +1044,8 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
   uint32_t ramp = kMinSlice;
   float ms_total = 0.f;
   uint32_t start = 0;
+  uint64_t base_pos = 0;   // PACKED2: position of read `start` in the concatenation
+  uint64_t exc_next = 0;   // PACKED2: first exception at or after base_pos
   int b = 0;
   bool inflight[kSlots] = {};
   // diagnostic (BKX_TIMELINE=1): device timestamps of every pipeline stage of the first slices
@@ -990,24 +1066,36 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     inflight[si] = false;
     return BKX_OK;
   };
+  // bases, longest read and soundness of reads [from, from + cnt)
+  auto measure = [&](uint32_t from, uint32_t cnt, uint64_t& nb, uint64_t& max_len) -> bool {
+    if (p2 && !hr.lens) { nb = (uint64_t)cnt * hr.fixed_len; max_len = hr.fixed_len; return true; }
+    nb = 0; max_len = 0;
+    bool mono = true;
+    if (p2) {
+      for (uint32_t i = from; i < from + cnt; ++i) { const uint64_t l = hr.lens[i]; nb += l; max_len = l > max_len ? l : max_len; }
+    } else {
+      for (uint32_t i = from; i < from + cnt; ++i) {
+        const uint64_t a = offsets[i], z = offsets[i + 1];
+        mono &= (z >= a);
+        const uint64_t l = z - a;
+        max_len = l > max_len ? l : max_len;
+      }
+      nb = offsets[from + cnt] - offsets[from];
+    }
+    return mono;
+  };
   while (start < n_reads) {
     const uint32_t left = n_reads - start;
     uint32_t cnt = std::min(ramp, std::max(kMinSlice, left / 2));
     if (cnt > left || left - cnt < kMinSlice / 2) cnt = left;
     ramp = std::min<uint64_t>(kMaxSlice, (uint64_t)ramp * 2);
-    while (cnt > 1 && offsets[start + cnt] - offsets[start] > kBatchBases) cnt = (cnt + 1) / 2;
-    if (pec && (cnt & 1)) cnt += (cnt < left) ? 1 : 0;  // PE1 / PE2 of a pair stay in one slice
-    uint64_t nb = offsets[start + cnt] - offsets[start];
+    uint64_t nb = 0, max_len = 0;
     // longest read of this slice (overlaps with the GPU work of the previous slices)
-    uint64_t max_len = 0;
-    bool mono = true;
-    for (uint32_t i = start; i < start + cnt; ++i) {
-      uint64_t a = offsets[i], z = offsets[i + 1];
-      mono &= (z >= a);
-      uint64_t l = z - a;
-      max_len = l > max_len ? l : max_len;
-    }
+    bool mono = measure(start, cnt, nb, max_len);
+    while (cnt > 1 && mono && nb > kBatchBases) { cnt = (cnt + 1) / 2; mono = measure(start, cnt, nb, max_len); }
+    if (pec && (cnt & 1)) { cnt += (cnt < left) ? 1 : 0; mono = measure(start, cnt, nb, max_len); }  // PE1 / PE2 of a pair stay in one slice
     if (!mono) return fail(BKX_ERR_PARAM, "offsets not monotonic in reads %u..%u", start, start + cnt);
+    const uint64_t o0 = p2 ? base_pos : offsets[start];
     if ((int)((max_len + 31) / 32) + 1 > x->grid_W || x->grid == 0 || x->hp.tables == nullptr ||
         max_len > x->max_len_prepared || pool_slots_needed(k, max_len) > x->hp.slots) {
       // (re)sizing the grid / overflow pool: let the slices in flight finish first
@@ -1019,44 +1107,85 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
     W = x->grid_W;
     Slot& s = x->slot[b];
     if (inflight[b] && (rc = drain(b)) < 0) return rc;
-    if (nb + 64 > s.bases_cap) {
+    if (nb + 128 > s.bases_cap) {
       if (s.d_bases) cudaFree(s.d_bases);
-      s.bases_cap = (size_t)(nb + 64) * 5 / 4;
+      s.bases_cap = (size_t)(nb + 128) * 5 / 4;
       CU(cudaMalloc((void**)&s.d_bases, s.bases_cap));
     }
     if (cnt > s.reads_cap) {
       if (s.d_offs) cudaFree(s.d_offs);
       if (s.d_out) cudaFree(s.d_out);
+      if (s.d_out16) cudaFree(s.d_out16);
+      if (s.d_lens) cudaFree(s.d_lens);
+      if (s.d_rflags) cudaFree(s.d_rflags);
       s.reads_cap = (size_t)cnt * 5 / 4;
+      CU(cudaMalloc((void**)&s.d_rflags, s.reads_cap + 8));
       CU(cudaMalloc((void**)&s.d_offs, (s.reads_cap + 1) * 8));
       CU(cudaMalloc((void**)&s.d_out, s.reads_cap * sizeof(bkx_read_result)));
+      CU(cudaMalloc((void**)&s.d_out16, s.reads_cap * sizeof(bkx_read_result16)));
+      CU(cudaMalloc((void**)&s.d_lens, (s.reads_cap + 8) * 2));
+      if (s.d_scan_tmp) { cudaFree(s.d_scan_tmp); s.d_scan_tmp = nullptr; }
+      size_t tb = 0;
+      CU(launch_len_offsets(s.d_lens, (uint32_t)s.reads_cap, s.d_offs, nullptr, &tb, s.st));
+      s.scan_tmp_bytes = tb + 256;
+      CU(cudaMalloc(&s.d_scan_tmp, s.scan_tmp_bytes));
     }
     if (cnt > s.hard_cap) {
       if (s.d_hard) cudaFree(s.d_hard);
       s.hard_cap = (size_t)cnt * 5 / 4;
       CU(cudaMalloc((void**)&s.d_hard, s.hard_cap * 4));
     }
-    if (!packed4) {
-      CU(cudaMemcpyAsync(s.d_bases, bases + offsets[start], nb, cudaMemcpyHostToDevice, s.st));
+    uint32_t n_exc_slice = 0;
+    if (hr.fmt == HostReads::BYTES) {
+      CU(cudaMemcpyAsync(s.d_bases, hr.data + o0, nb, cudaMemcpyHostToDevice, s.st));
     } else {
-      // half the PCIe bytes: ship the nibbles, expand to one byte per base on the device (an HBM-speed pass)
-      const uint64_t o0 = offsets[start], o1 = offsets[start + cnt];
-      const uint64_t byte0 = o0 >> 1, nbytes = ((o1 + 1) >> 1) - byte0;
-      if (nbytes + 64 > s.packed_cap) {
+      // a half / a quarter of the PCIe bytes: ship the packed codes, expand to one byte per base on the device (an
+      // HBM-speed pass)
+      const int per = packed4 ? 2 : 4, sh = packed4 ? 1 : 2;
+      const uint64_t o1 = o0 + nb;
+      const uint64_t byte0 = o0 >> sh, nbytes = ((o1 + per - 1) >> sh) - byte0;
+      if (nbytes + 128 > s.packed_cap) {
         if (s.d_packed) cudaFree(s.d_packed);
-        s.packed_cap = (size_t)(nbytes + 64) * 5 / 4;
+        s.packed_cap = (size_t)(nbytes + 128) * 5 / 4;
         CU(cudaMalloc((void**)&s.d_packed, s.packed_cap));
       }
       mark(s.st);
-      if (nbytes) CU(cudaMemcpyAsync(s.d_packed, bases + byte0, nbytes, cudaMemcpyHostToDevice, s.st));
+      if (nbytes) CU(cudaMemcpyAsync(s.d_packed, hr.data + byte0, nbytes, cudaMemcpyHostToDevice, s.st));
       mark(s.st);
+      if (p2) {  // the slice's share of the exception list (positions ascend)
+        uint64_t e1 = exc_next;
+        while (e1 < hr.n_exc && hr.exc_pos[e1] < o1) ++e1;
+        if (e1 - exc_next > 0x7fffffffu) return fail(BKX_ERR_PARAM, "too many non-ACGT bases in one slice");
+        n_exc_slice = (uint32_t)(e1 - exc_next);
+        if (n_exc_slice > s.exc_cap) {
+          if (s.d_exc_pos) cudaFree(s.d_exc_pos);
+          if (s.d_exc_code) cudaFree(s.d_exc_code);
+          s.exc_cap = (size_t)n_exc_slice * 5 / 4 + 1024;
+          CU(cudaMalloc((void**)&s.d_exc_pos, s.exc_cap * 8));
+          CU(cudaMalloc((void**)&s.d_exc_code, s.exc_cap));
+        }
+        if (n_exc_slice) {
+          CU(cudaMemcpyAsync(s.d_exc_pos, hr.exc_pos + exc_next, (size_t)n_exc_slice * 8, cudaMemcpyHostToDevice, s.st));
+          CU(cudaMemcpyAsync(s.d_exc_code, hr.exc_code + exc_next, (size_t)n_exc_slice, cudaMemcpyHostToDevice, s.st));
+        }
+        exc_next = e1;
+        if (hr.lens) CU(cudaMemcpyAsync(s.d_lens, hr.lens + start, (size_t)cnt * 2, cudaMemcpyHostToDevice, s.st));
+      }
     }
-    CU(cudaMemcpyAsync(s.d_offs, offsets + start, ((size_t)cnt + 1) * 8, cudaMemcpyHostToDevice, s.st));
+    if (!p2) CU(cudaMemcpyAsync(s.d_offs, offsets + start, ((size_t)cnt + 1) * 8, cudaMemcpyHostToDevice, s.st));
     CU(cudaEventRecord(s.in_ready, s.st));
     CU(cudaStreamWaitEvent(x->cst, s.in_ready, 0));
     if (packed4 && nb) {
-      CU(launch_unpack4(s.d_packed, (unsigned)(offsets[start] & 1), nb, s.d_bases, x->cst));
+      CU(launch_unpack4(s.d_packed, (unsigned)(o0 & 1), nb, s.d_bases, x->cst));
       x->launches += 1;
+    }
+    if (p2) {
+      if (nb) CU(launch_unpack2(s.d_packed, (unsigned)(o0 & 3), nb, s.d_bases, x->cst));
+      if (n_exc_slice) CU(launch_scatter_exceptions(s.d_exc_pos, s.d_exc_code, n_exc_slice, o0, nb, s.d_bases, x->cst));
+      if (hr.lens) CU(launch_len_offsets(s.d_lens, cnt, s.d_offs, s.d_scan_tmp, &s.scan_tmp_bytes, x->cst));
+      else CU(launch_fixed_offsets(s.d_offs, cnt, hr.fixed_len, x->cst));
+      CU(launch_flag_exception_reads(s.d_exc_pos, n_exc_slice, o0, s.d_offs, cnt, s.d_rflags, x->cst));
+      x->launches += 2 + (n_exc_slice ? 2 : 0);
     }
     if (multi) {
       const size_t need = (size_t)cnt * (size_t)k.max_hits;
@@ -1069,9 +1198,12 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
       k.multi = s.d_multi;
     }
     CU(cudaEventRecord(s.k0, x->cst));
-    // offsets stay absolute: hand the kernel a base pointer shifted by the slice start
-    if ((rc = launch_both(x, k, s.d_bases - offsets[start], s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard,
-                          x->cst)) < 0) return rc;
+    // BYTES / PACKED4: the offsets stay absolute, so the kernels get a base pointer shifted by the slice start;
+    // PACKED2: the device made offsets relative to the slice
+    const uint8_t* kbases = p2 ? s.d_bases : s.d_bases - o0;
+    Packed2Src psrc;   // PACKED2: the fast kernel takes its reads straight from the 2-bit stream that came over PCIe
+    if (p2) { psrc.words = (const uint64_t*)s.d_packed; psrc.flags = s.d_rflags; psrc.phase = (uint32_t)(o0 & 3); }
+    if ((rc = launch_both(x, k, kbases, s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard, x->cst, psrc)) < 0) return rc;
     if (pec) {  // pair the slice's reads while they are still on the device (ProcessPairedEnds, Aligner.cpp:2876-3049)
       unsigned int* cur = x->d_cursor[b];
       if ((size_t)cnt / 2 > s.orphans_cap) {
@@ -1083,21 +1215,29 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
       CU(launch_pair(*pec->pe, s.d_out, cnt / 2, x->d_pe_stats, x->d_len_dist, s.d_orphans, cur + 3, x->d_chrom_keep, x->cst));
       x->launches += 1;
       if (rescue) {
-        CU(launch_rescue(x->d, k, *pec->pe, s.d_out, s.d_orphans, cur + 3, s.d_bases - offsets[start], s.d_offs,
+        CU(launch_rescue(x->d, k, *pec->pe, s.d_out, s.d_orphans, cur + 3, kbases, s.d_offs,
                          std::max<int>((int)max_len, 32), x->d_pe_stats, x->d_len_dist, cur, x->d_chrom_keep, x->cst));
         x->launches += 1;
       }
     }
+    if (compact_out) {
+      CU(launch_compact_results(s.d_out, cnt, s.d_out16, x->cst));
+      x->launches += 1;
+    }
     CU(cudaEventRecord(s.k1, x->cst));
     mark(x->cst);
     CU(cudaStreamWaitEvent(s.st, s.k1, 0));
-    CU(cudaMemcpyAsync(out + start, s.d_out, (size_t)cnt * sizeof(bkx_read_result), cudaMemcpyDeviceToHost, s.st));
+    if (compact_out)
+      CU(cudaMemcpyAsync(out16 + start, s.d_out16, (size_t)cnt * sizeof(bkx_read_result16), cudaMemcpyDeviceToHost, s.st));
+    else
+      CU(cudaMemcpyAsync(out + start, s.d_out, (size_t)cnt * sizeof(bkx_read_result), cudaMemcpyDeviceToHost, s.st));
     if (multi)
       CU(cudaMemcpyAsync(multi + (size_t)start * (size_t)k.max_hits, s.d_multi,
                          (size_t)cnt * (size_t)k.max_hits * sizeof(bkx_multi_hit), cudaMemcpyDeviceToHost, s.st));
     mark(s.st);
     inflight[b] = true;
     start += cnt;
+    base_pos += nb;
     b = (b + 1) % kSlots;
   }
   // drain in submission order (the oldest slice sits in slot b)
@@ -1141,13 +1281,28 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const uint8_t* ba
   return BKX_OK;
 }
 
+static HostReads reads_bytes(const uint8_t* bases, const uint64_t* offsets, bool packed4) {
+  HostReads h;
+  h.fmt = packed4 ? HostReads::PACKED4 : HostReads::BYTES;
+  h.data = bases;
+  h.offsets = offsets;
+  return h;
+}
+static HostReads reads_packed2(const uint8_t* packed2, const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos,
+                               const uint8_t* exc_code, uint64_t n_exc) {
+  HostReads h;
+  h.fmt = HostReads::PACKED2;
+  h.data = packed2; h.lens = lens; h.fixed_len = fixed_len; h.exc_pos = exc_pos; h.exc_code = exc_code; h.n_exc = n_exc;
+  return h;
+}
+
 extern "C" int bkx_align_pairs(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, const uint8_t* bases,
                                const uint64_t* offsets, uint32_t n_pairs, bkx_read_result* out, bkx_align_stats* stats,
                                bkx_pe_stats* pe_stats, uint32_t* len_dist) {
   if (n_pairs > 0x7fffffffu) return fail(BKX_ERR_PARAM, "too many pairs");
   PeCall pc;
   pc.pe = pe; pc.stats = pe_stats; pc.len_dist = len_dist;
-  return align_host(x, p, bases, false, offsets, 2 * n_pairs, out, stats, nullptr, &pc);
+  return align_host(x, p, reads_bytes(bases, offsets, false), 2 * n_pairs, out, false, stats, nullptr, &pc);
 }
 
 extern "C" int bkx_align_pairs_packed4(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, const uint8_t* packed,
@@ -1156,23 +1311,81 @@ extern "C" int bkx_align_pairs_packed4(bkx_index* x, const bkx_align_params* p, 
   if (n_pairs > 0x7fffffffu) return fail(BKX_ERR_PARAM, "too many pairs");
   PeCall pc;
   pc.pe = pe; pc.stats = pe_stats; pc.len_dist = len_dist;
-  return align_host(x, p, packed, true, offsets, 2 * n_pairs, out, stats, nullptr, &pc);
+  return align_host(x, p, reads_bytes(packed, offsets, true), 2 * n_pairs, out, false, stats, nullptr, &pc);
 }
 
 extern "C" int bkx_align_reads(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
                                uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
-  return align_host(x, p, bases, false, offsets, n_reads, out, stats);
+  return align_host(x, p, reads_bytes(bases, offsets, false), n_reads, out, false, stats);
 }
 
 extern "C" int bkx_align_reads_multi(bkx_index* x, const bkx_align_params* p, const uint8_t* bases, const uint64_t* offsets,
                                      uint32_t n_reads, bkx_read_result* out, bkx_multi_hit* multi, bkx_align_stats* stats) {
   if (!multi) return fail(BKX_ERR_PARAM, "null argument");
-  return align_host(x, p, bases, false, offsets, n_reads, out, stats, multi);
+  return align_host(x, p, reads_bytes(bases, offsets, false), n_reads, out, false, stats, multi);
 }
 
 extern "C" int bkx_align_reads_packed4(bkx_index* x, const bkx_align_params* p, const uint8_t* packed, const uint64_t* offsets,
                                        uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats) {
-  return align_host(x, p, packed, true, offsets, n_reads, out, stats);
+  return align_host(x, p, reads_bytes(packed, offsets, true), n_reads, out, false, stats);
+}
+
+extern "C" int bkx_align_reads_packed2(bkx_index* x, const bkx_align_params* p, const uint8_t* packed2, const uint16_t* lens,
+                                       uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code, uint64_t n_exc,
+                                       uint32_t n_reads, bkx_read_result16* out, bkx_align_stats* stats) {
+  if (p && p->ml_mode >= BKX_ML_UNIQ) return fail(BKX_ERR_UNSUPPORTED, "-r3..5 need bkx_align_reads_multi");
+  return align_host(x, p, reads_packed2(packed2, lens, fixed_len, exc_pos, exc_code, n_exc), n_reads, out, true, stats);
+}
+
+extern "C" int bkx_align_pairs_packed2(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, const uint8_t* packed2,
+                                       const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code,
+                                       uint64_t n_exc, uint32_t n_pairs, bkx_read_result16* out, bkx_align_stats* stats,
+                                       bkx_pe_stats* pe_stats, uint32_t* len_dist) {
+  if (n_pairs > 0x7fffffffu) return fail(BKX_ERR_PARAM, "too many pairs");
+  PeCall pc;
+  pc.pe = pe; pc.stats = pe_stats; pc.len_dist = len_dist;
+  return align_host(x, p, reads_packed2(packed2, lens, fixed_len, exc_pos, exc_code, n_exc), 2 * n_pairs, out, true, stats, nullptr, &pc);
+}
+
+// One-byte codes -> 2-bit stream + exception list (the loop a loader fuses into its parser).  A code above T goes into the
+// list with its low 3 bits (N = 4 and the InDel / undefined codes the search rejects as eNARNs) and leaves 0 in the stream.
+extern "C" int64_t bkx_pack_bases2(const uint8_t* bases, uint64_t n_bases, uint8_t* packed2, uint64_t* exc_pos, uint8_t* exc_code,
+                                   uint64_t exc_cap) {
+  if ((!bases || !packed2) && n_bases) return fail(BKX_ERR_PARAM, "null argument");
+  uint64_t ne = 0;
+  const uint64_t nbytes = (n_bases + 3) / 4;
+  for (uint64_t b = 0; b < nbytes; ++b) {
+    unsigned v = 0;
+    for (unsigned j = 0; j < 4; ++j) {
+      const uint64_t i = 4 * b + j;
+      if (i >= n_bases) break;
+      const unsigned c = bases[i] & 7u;
+      if (c > 3) {
+        if (ne >= exc_cap || !exc_pos || !exc_code) return fail(BKX_ERR_MEM, "exception list too small (%llu entries)", (unsigned long long)exc_cap);
+        exc_pos[ne] = i; exc_code[ne] = (uint8_t)c; ++ne;
+      } else v |= c << (2 * j);
+    }
+    packed2[b] = (uint8_t)v;
+  }
+  return (int64_t)ne;
+}
+
+extern "C" int bkx_expand_results16(const bkx_read_result16* in, uint32_t n_reads, const uint16_t* lens, uint32_t fixed_len,
+                                    bkx_read_result* out) {
+  if ((!in || !out) && n_reads) return fail(BKX_ERR_PARAM, "null argument");
+  static const uint8_t kStrand[4] = {0, '+', '-', '?'};
+  for (uint32_t i = 0; i < n_reads; ++i) {
+    const bkx_read_result16 c = in[i];
+    bkx_read_result r;
+    memset(&r, 0, sizeof(r));
+    r.nar = c.nar_hr & 0x1f; r.hit_rslt = c.nar_hr >> 5;
+    r.strand = kStrand[c.strand_flags & 3]; r.flags = (c.strand_flags >> 2) & 3;
+    r.num_hits = c.num_hits; r.mismatches = c.mismatches; r.low_mm = c.low_mm; r.nxt_low_mm = c.nxt_low_mm;
+    r.low_hit_instances = c.low_hit_instances; r.chrom_id = c.chrom_id; r.match_loci = c.match_loci;
+    r.match_len = r.strand ? (uint16_t)(lens ? lens[i] : fixed_len) : 0;
+    out[i] = r;
+  }
+  return BKX_OK;
 }
 
 extern "C" int bkx_pack_bases4(const uint8_t* bases, uint64_t n_bases, uint8_t* packed) {

@@ -64,18 +64,20 @@ __device__ __forceinline__ int gsym(const DevIndex& I, uint64_t i) {
   return ex ? (code == 3 ? 7 : 4) : code;
 }
 
-// true if any base in [g, g+len) is N/EOS or lies past the end of the concatenation.
+// true if any base in [g, g+len) is N/EOS or lies past the end of the concatenation.  len <= 2000 (cMaxSeqLen): the
+// 64-base blocks of the span are at most 33 bits of the coarse map, taken as one 64-bit window (gxc has two words of slack).
 __device__ __forceinline__ bool span_has_exc(const DevIndex& I, uint64_t g, uint32_t len) {
   if (g + len > I.n) return true;
-  uint64_t b0 = g >> 6, b1 = (g + len - 1) >> 6;
-  for (uint64_t w = b0 >> 5; w <= (b1 >> 5); ++w) {
-    uint32_t v = __ldg(I.gxc + w);
-    uint32_t lo = (w == (b0 >> 5)) ? (0xffffffffu << (b0 & 31)) : 0xffffffffu;
-    uint32_t hi = (w == (b1 >> 5)) ? (0xffffffffu >> (31 - (b1 & 31))) : 0xffffffffu;
-    if (v & lo & hi) return true;
-  }
-  return false;
+  const uint64_t b0 = g >> 6, b1 = (g + len - 1) >> 6;
+  const uint64_t w = b0 >> 5;
+  const uint64_t v = ((uint64_t)__ldg(I.gxc + w) | ((uint64_t)__ldg(I.gxc + w + 1) << 32)) >> (unsigned)(b0 & 31);
+  const unsigned nb = (unsigned)(b1 - b0) + 1;   // 1..33 blocks, all inside the 64 - (b0 & 31) >= 33 bits of the window
+  return (v & ((1ull << nb) - 1)) != 0;
 }
+
+// a / b for 0 <= a, 1 <= b, both below 2^15: exact through one float division ((a + 0.5) / b is at least 0.5 / b away from an
+// integer, the division's error is far below that)
+__device__ __forceinline__ int small_div(int a, int b) { return (int)__fdividef((float)a + 0.5f, (float)b); }
 
 // reverse the order of the 32 two-bit groups of a word (first base becomes most significant).
 __device__ __forceinline__ uint64_t rev2(uint64_t w) {

@@ -5,6 +5,7 @@
 #include "bkx_kernels.h"
 
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <mutex>
 
@@ -167,6 +168,131 @@ cudaError_t launch_unpack4(const uint8_t* packed, unsigned phase, uint64_t n_bas
   return cudaGetLastError();
 }
 
+// ---- compact host interface (bkx_align_reads_packed2): 2 bits per base in, 16 bytes per read out -------------------------
+// 2-bit packed reads (base i at bits [2(i%4), +2) of byte i/4) -> one byte per base.  `phase` = position of the first
+// wanted base inside its byte.  Sixteen bases (one 16-byte store) per thread; `packed` and `out` start on 16-byte
+// boundaries and are over-allocated by the caller, so whole words are read and written at both ends.
+__global__ void unpack2_kernel(const uint32_t* __restrict__ packed, unsigned phase, uint64_t n, uint8_t* __restrict__ out) {
+  const uint64_t groups = (n + 15) >> 4;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t w = __funnelshift_r(__ldg(packed + g), __ldg(packed + g + 1), 2 * phase);
+    uint4 v;
+    uint32_t* vo = &v.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t b = (w >> (8 * q)) & 0xffu;
+      vo[q] = (b & 3u) | ((b & 0xcu) << 6) | ((b & 0x30u) << 12) | ((b & 0xc0u) << 18);
+    }
+    *reinterpret_cast<uint4*>(out + 16 * g) = v;
+  }
+}
+
+// the bases that are not A C G T (stored as code 0 in the 2-bit stream) get their etSeqBase code back
+__global__ void scatter_exceptions_kernel(const uint64_t* __restrict__ pos, const uint8_t* __restrict__ code, uint32_t n_exc,
+                                          uint64_t first_base, uint64_t n_bases, uint8_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_exc; i += gridDim.x * blockDim.x) {
+    const uint64_t p = __ldg(pos + i) - first_base;
+    if (p < n_bases) out[p] = __ldg(code + i);
+  }
+}
+
+// read offsets of a slice of fixed-length reads: offs[i] = i * len, i = 0..n_reads
+__global__ void fixed_offsets_kernel(uint64_t* __restrict__ offs, uint32_t n_reads, uint32_t len) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_reads; i += (uint64_t)gridDim.x * blockDim.x)
+    offs[i] = i * len;
+}
+
+// 32-byte records -> the 16-byte form that crosses PCIe (bkx_read_result16, include/bkx.h)
+__global__ void compact_results_kernel(const bkx_read_result* __restrict__ in, uint32_t n, bkx_read_result16* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + i);
+    const uint4 a = __ldg(src), b = __ldg(src + 1);
+    bkx_read_result r;
+    memcpy(&r, &a, 16);
+    memcpy(reinterpret_cast<char*>(&r) + 16, &b, 16);
+    bkx_read_result16 c;
+    c.nar_hr = (uint8_t)((r.nar & 0x1f) | (r.hit_rslt << 5));
+    const unsigned sc = r.strand == '+' ? 1u : r.strand == '-' ? 2u : r.strand == '?' ? 3u : 0u;
+    c.strand_flags = (uint8_t)(sc | ((r.flags & 3u) << 2));
+    c.num_hits = r.num_hits;
+    c.mismatches = r.mismatches;
+    c.low_mm = r.low_mm;
+    c.nxt_low_mm = r.nxt_low_mm;
+    c.low_hit_instances = r.low_hit_instances;
+    c.chrom_id = r.chrom_id;
+    c.match_loci = r.match_loci;
+    uint4 o;
+    memcpy(&o, &c, 16);
+    *reinterpret_cast<uint4*>(out + i) = o;
+  }
+}
+
+// flags[read] = 1 for every read that holds a non-ACGT base: the read of exception k is found by bisection of the slice's
+// offsets (offs[0] = 0 .. offs[n_reads] = bases of the slice)
+__global__ void flag_exception_reads_kernel(const uint64_t* __restrict__ pos, uint32_t n_exc, uint64_t first_base,
+                                            const uint64_t* __restrict__ offs, uint32_t n_reads, uint8_t* __restrict__ flags) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_exc; i += gridDim.x * blockDim.x) {
+    const uint64_t p = __ldg(pos + i) - first_base;
+    if (p >= __ldg(offs + n_reads)) continue;
+    uint32_t lo = 0, hi = n_reads;   // last read with offs[read] <= p
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldg(offs + mid) <= p) lo = mid; else hi = mid;
+    }
+    flags[lo] = 1;
+  }
+}
+
+cudaError_t launch_flag_exception_reads(const uint64_t* pos, uint32_t n_exc, uint64_t first_base, const uint64_t* offs,
+                                        uint32_t n_reads, uint8_t* flags, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(flags, 0, n_reads, st);
+  if (e != cudaSuccess || n_exc == 0) return e;
+  int grid = (int)std::min<uint32_t>((n_exc + 255) / 256, 148 * 8);
+  flag_exception_reads_kernel<<<grid, 256, 0, st>>>(pos, n_exc, first_base, offs, n_reads, flags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack2(const uint8_t* packed, unsigned phase, uint64_t n_bases, uint8_t* out, cudaStream_t st) {
+  const uint64_t groups = (n_bases + 15) >> 4;
+  int grid = (int)std::min<uint64_t>((groups + 255) / 256, 148 * 16);
+  if (grid < 1) grid = 1;
+  unpack2_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(packed), phase, n_bases, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_exceptions(const uint64_t* pos, const uint8_t* code, uint32_t n_exc, uint64_t first_base,
+                                      uint64_t n_bases, uint8_t* out, cudaStream_t st) {
+  if (n_exc == 0) return cudaSuccess;
+  int grid = (int)std::min<uint32_t>((n_exc + 255) / 256, 148 * 8);
+  scatter_exceptions_kernel<<<grid, 256, 0, st>>>(pos, code, n_exc, first_base, n_bases, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fixed_offsets(uint64_t* offs, uint32_t n_reads, uint32_t len, cudaStream_t st) {
+  int grid = (int)std::min<uint32_t>(n_reads / 256 + 1, 148 * 8);
+  fixed_offsets_kernel<<<grid, 256, 0, st>>>(offs, n_reads, len);
+  return cudaGetLastError();
+}
+
+// offs[0] = 0, offs[i + 1] = lens[0] + .. + lens[i]
+struct U16ToU64 {
+  __host__ __device__ __forceinline__ uint64_t operator()(const uint16_t& v) const { return (uint64_t)v; }
+};
+cudaError_t launch_len_offsets(const uint16_t* lens, uint32_t n_reads, uint64_t* offs, void* tmp, size_t* tmp_bytes, cudaStream_t st) {
+  cub::TransformInputIterator<uint64_t, U16ToU64, const uint16_t*> it(lens, U16ToU64());
+  if (!tmp) return cub::DeviceScan::InclusiveSum(nullptr, *tmp_bytes, it, offs + 1, (int)n_reads, st);
+  cudaError_t e = cudaMemsetAsync(offs, 0, 8, st);
+  if (e != cudaSuccess) return e;
+  return cub::DeviceScan::InclusiveSum(tmp, *tmp_bytes, it, offs + 1, (int)n_reads, st);
+}
+
+cudaError_t launch_compact_results(const bkx_read_result* in, uint32_t n, bkx_read_result16* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)std::min<uint32_t>((n + 255) / 256, 148 * 16);
+  compact_results_kernel<<<grid, 256, 0, st>>>(in, n, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_split_sa5(const uint8_t* sa5, uint64_t n, uint32_t* lo, uint8_t* hi, cudaStream_t st) {
   split_sa5_kernel<<<148 * 8, 256, 0, st>>>(sa5, n, lo, hi);
   return cudaGetLastError();
@@ -234,7 +360,7 @@ static cudaError_t ensure_smem(K kernel, size_t smem, SmemOptIn& cfg) {
   }
   return cudaSuccess;
 }
-static SmemOptIn g_smem_general, g_smem_fast, g_smem_fast_mlx, g_smem_rescue;
+static SmemOptIn g_smem_general, g_smem_fast, g_smem_fast_mlx, g_smem_fast_scan, g_smem_fast_mlx_scan, g_smem_rescue;
 
 __host__ __device__ inline size_t group_smem_bytes(int W) {
   size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + (kGroup + 2) * 4;
@@ -452,12 +578,18 @@ __device__ __noinline__ void fh_spill(uint64_t* lane_hash, uint32_t epoch, const
 
 // MLX: any multi-loci option (-r1 / -X) is on.  A template parameter, not a run-time test: letting the result code vary
 // at run time inside finish() costs the default instantiation its spill-free 64-register allocation (-3 % reads/s).
-template <bool MLX>
+// SCAN: the step is split in two.  Most cores of a read are absent from the genome and die at the prefix-table lookup (an
+// empty bucket); with one core per step those cheap lanes sat idle while a few lanes of the warp searched and walked a
+// bucket (11 of 32 lanes active on average, profiles/r01_final_align_fast_ncu.md).  Now every lane first runs down its
+// cores -- two table lookups in flight at a time -- until it stands on a non-empty bucket (or its read is finished), and
+// only then the warp enters the search / walk / Hamming part, with most lanes having work there.  Skipping over empty
+// buckets changes nothing the reference can observe: they yield no candidate, only the seed count moves on.
+template <bool MLX, bool SCAN>
 __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
     uint32_t* __restrict__ hard_ids, unsigned int* __restrict__ n_hard, uint64_t* __restrict__ lane_hash,
-    uint32_t epoch_base) {
+    uint32_t epoch_base, Packed2Src p2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockStats bs;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -495,7 +627,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     if (!in_final) {
       bool staged = false;
       if (max_tot_mm > 0 && allow <= max_tot_mm) {
-        int cl = L / (allow + P.mmd);
+        int cl = small_div(L, allow + P.mmd);
         if (cl > core_len) { staged = true; CL = cl; delta = cl; mm_max = allow; }
       }
       if (!staged) {
@@ -506,7 +638,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     } else {
       return false;
     }
-    K = (L - CL - delta >= 0) ? (L - CL - delta) / delta + 1 : 0;
+    K = (L - CL - delta >= 0) ? small_div(L - CL - delta, delta) + 1 : 0;
     int rr = L - (K * delta + CL);
     n_cores = K + 1 + ((rr > CL / 3) ? 1 : 0);
     if (n_cores > slides) n_cores = slides;
@@ -567,6 +699,42 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     active = false;
   };
 
+  // the end of a phase (both strands done, or the global early exit): next phase, or the read's result
+  auto phase_end = [&]() {
+    if (inst == 0) {
+      bool more = true;
+      for (;;) {
+        if (in_final) { more = false; break; }
+        ++allow;
+        if (!setup_phase()) { more = false; break; }
+        if (n_cores > 0) break;
+      }
+      if (!more) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); }
+    } else if ((nxt - low) < P.mmd) {
+      finish(BKX_HR_MMDELTA);
+    } else if (inst > P.max_hits) {
+      finish(BKX_HR_HITINSTS);
+    } else {
+      finish(BKX_HR_HITS);
+    }
+  };
+  // SCAN state: `have` -- the lane stands on core (s, ci) whose bucket [blo, bhi) is not empty; `pend_end` -- its phase
+  // is over and phase_end() is due
+  bool have = false, pend_end = false;
+  uint64_t blo = 0, bhi = 0;
+  auto bucket_of = [&](int strand, int ofs, uint64_t& lo, uint64_t& hi) {
+    const uint64_t key = rev2(fl_word(f, strand, ofs)) >> (64 - 2 * k);
+    if (CL >= k) {
+      lo = pt_get(I, key);
+      hi = pt_get(I, key + 1);
+    } else {
+      const int sh = 2 * (k - CL);
+      const uint64_t pfx = key >> sh;
+      lo = pt_get(I, pfx << sh);
+      hi = pt_get(I, (pfx + 1) << sh);
+    }
+  };
+
   for (;;) {
     // ---- (1) idle lanes claim the next reads (one atomic per warp)
     const bool want = !active && !exhausted;
@@ -591,9 +759,28 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
           else fresh = true;
         }
       }
-      // ---- the warp packs the new reads together: each lane takes 4 bases (one coalesced 32-bit load),
+      // ---- reads that arrive 2-bit packed (and hold nothing but A C G T) are taken as they are: a few unaligned 64-bit
+      //      extracts per lane instead of the cooperative packing below (which was 15 % of the kernel's instructions)
+      const bool direct = fresh && p2.words != nullptr && !(p2.flags && __ldg(p2.flags + r));
+      if (direct) {
+        const uint64_t bo = __ldg(offs + r) + p2.phase;
+        const uint64_t* src = p2.words + (bo >> 5);
+        const unsigned sh = (unsigned)(bo & 31) * 2;
+        const int words = (L + 31) >> 5;
+        uint64_t prev = __ldg(src);
+        for (int w = 0; w < words; ++w) {
+          const uint64_t next = __ldg(src + w + 1);
+          uint64_t v = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
+          prev = next;
+          const int len = L - 32 * w;
+          if (len < 32) v &= (1ull << (2 * len)) - 1;
+          wr0[w * 32] = v;
+        }
+        wr0[words * 32] = 0;
+      }
+      // ---- the warp packs the other new reads together: each lane takes 4 bases (one coalesced 32-bit load),
       //      a multiply gathers their 2-bit codes into a byte, three shuffles assemble the 64-bit words
-      unsigned pk = __ballot_sync(0xffffffffu, fresh);
+      unsigned pk = __ballot_sync(0xffffffffu, fresh && !direct);
       while (pk) {
         const int j = __ffs(pk) - 1;
         pk &= pk - 1;
@@ -663,9 +850,9 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
           // per-read search parameters, Aligner.cpp:9085-9095
           max_tot_mm = P.max_subs == 0 ? 0 : max(1, (L * P.max_subs + 50) / 100);
           if (max_tot_mm > 63) max_tot_mm = 63;
-          core_len = max(P.min_core_len, L / (P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
+          core_len = max(P.min_core_len, small_div(L, P.mmd == 1 ? max_tot_mm + 1 : max_tot_mm + 2));
           slides = max(1, (P.slides_per100 * L + 99) / 100);
-          core_delta = max(L / slides - 1, core_len);
+          core_delta = max(small_div(L, slides) - 1, core_len);
           allow = 0;
           in_final = false;
           hit_ent = -1;
@@ -684,23 +871,62 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
       if (__all_sync(0xffffffffu, exhausted)) break;
       continue;
     }
-    // ---- (2) one core of the current strand/phase for every active lane
-    if (active) {
+    if constexpr (SCAN) {
+      // ---- (2a) every lane runs down its cores until it stands on a non-empty bucket
+      const int scan_iters = P.scan_iters;
+      for (int it = 0; it < scan_iters; ++it) {
+        if (active && pend_end) { pend_end = false; phase_end(); }
+        if (active && !have) {
+          // this core and the one after it (same phase): both lookups are issued before either is looked at
+          const int c0 = ci <= K ? ci * delta : last_ofs;
+          int s1 = s, ci1 = ci + 1;
+          bool has1 = true;
+          if (ci1 >= n_cores) {
+            if (s < s_last) { s1 = s + 1; ci1 = 0; } else { has1 = false; s1 = s; ci1 = ci; }
+          }
+          const int c1 = ci1 <= K ? ci1 * delta : last_ofs;
+          uint64_t lo0, hi0, lo1, hi1;
+          bucket_of(s, c0, lo0, hi0);
+          bucket_of(s1, c1, lo1, hi1);
+          ++seeds;
+          if (lo0 < hi0) { have = true; blo = lo0; bhi = hi0; }
+          else if (!has1) pend_end = true;
+          else {
+            if (s1 != s) seen_n = 0;
+            s = s1; ci = ci1;
+            ++seeds;
+            if (lo1 < hi1) { have = true; blo = lo1; bhi = hi1; }
+            else if (ci + 1 < n_cores) ++ci;
+            else if (s < s_last) { ++s; ci = 0; seen_n = 0; }
+            else pend_end = true;
+          }
+        }
+        if (!__any_sync(0xffffffffu, active && !have)) break;
+      }
+    }
+    // ---- (2) one core of the current strand/phase for every active lane (SCAN: for the lanes standing on a bucket)
+    if (SCAN ? (active && have) : active) {
       const int cofs = ci <= K ? ci * delta : last_ofs;
-      ++seeds;
       bool dfr = false, stop_all = false;
       // SA interval of the core: prefix-table bucket, then lower / upper bound
-      uint64_t key = rev2(fl_word(f, s, cofs)) >> (64 - 2 * k);
-      uint64_t blo, bhi;
-      if (CL >= k) {
-        blo = pt_get(I, key);
-        bhi = pt_get(I, key + 1);
-      } else {
-        int sh = 2 * (k - CL);
-        uint64_t p = key >> sh;
-        blo = pt_get(I, p << sh);
-        bhi = pt_get(I, (p + 1) << sh);
+      if constexpr (!SCAN) {
+        ++seeds;
+        if (P.prefetch) {
+          // the next core of this phase is known now: ask L2 for its table entry, so that the next step's lookup -- 14 of the
+          // ~30 DRAM line fetches of a read are such lookups -- finds it there
+          int s1 = s, ci1 = ci + 1;
+          if (ci1 >= n_cores) { s1 = s + 1; ci1 = 0; }
+          if (s1 <= s_last) {
+            const int c1 = ci1 <= K ? ci1 * delta : last_ofs;
+            uint64_t key1 = rev2(fl_word(f, s1, c1)) >> (64 - 2 * k);
+            if (CL < k) { const int sh1 = 2 * (k - CL); key1 = (key1 >> sh1) << sh1; }
+            const void* pa = I.pt32 ? (const void*)(I.pt32 + key1) : (const void*)(I.pt64 + key1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+          }
+        }
+        bucket_of(s, cofs, blo, bhi);
       }
+      have = false;
       uint64_t first = 0, cnt = 0;
       bool located = false;
       if (blo < bhi && CL <= k) {
@@ -804,6 +1030,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
       }
       if (dfr) {
         defer();
+        pend_end = false;
       } else {
         // advance: next core / strand / phase
         ++ci;
@@ -813,22 +1040,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
           else phase_done = true;
         }
         if (phase_done) {
-          if (inst == 0) {
-            bool more = true;
-            for (;;) {
-              if (in_final) { more = false; break; }
-              ++allow;
-              if (!setup_phase()) { more = false; break; }
-              if (n_cores > 0) break;
-            }
-            if (!more) { inst = 0; low = 0; nxt = 0; finish(BKX_HR_NONE); }
-          } else if ((nxt - low) < P.mmd) {
-            finish(BKX_HR_MMDELTA);
-          } else if (inst > P.max_hits) {
-            finish(BKX_HR_HITINSTS);
-          } else {
-            finish(BKX_HR_HITS);
-          }
+          if constexpr (SCAN) pend_end = true;   // handled at the top of the next scan step
+          else phase_end();
         }
       }
     }
@@ -840,33 +1053,40 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
 cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                               uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
                               unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, uint64_t* lane_hash,
-                              uint32_t epoch_base, int grid, cudaStream_t st) {
+                              uint32_t epoch_base, int grid, cudaStream_t st, const Packed2Src& p2) {
   size_t smem = fast_smem_bytes(W);
   const bool mlx = P.ml_mode != 0 || P.clamp_ml != 0;
-  cudaError_t e = mlx ? ensure_smem(align_fast_kernel<true>, smem, g_smem_fast_mlx)
-                      : ensure_smem(align_fast_kernel<false>, smem, g_smem_fast);
+  const bool scan = P.scan_iters > 0;
+  cudaError_t e = mlx ? (scan ? ensure_smem(align_fast_kernel<true, true>, smem, g_smem_fast_mlx_scan)
+                              : ensure_smem(align_fast_kernel<true, false>, smem, g_smem_fast_mlx))
+                      : (scan ? ensure_smem(align_fast_kernel<false, true>, smem, g_smem_fast_scan)
+                              : ensure_smem(align_fast_kernel<false, false>, smem, g_smem_fast));
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(n_hard, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
-  if (mlx)
-    align_fast_kernel<true><<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids,
-                                                              n_hard, lane_hash, epoch_base);
-  else
-    align_fast_kernel<false><<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids,
-                                                               n_hard, lane_hash, epoch_base);
+#define BKX_LAUNCH_FAST(M, S)                                                                                              \
+  align_fast_kernel<M, S><<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids, \
+                                                            n_hard, lane_hash, epoch_base, p2)
+  if (mlx) { if (scan) BKX_LAUNCH_FAST(true, true); else BKX_LAUNCH_FAST(true, false); }
+  else { if (scan) BKX_LAUNCH_FAST(false, true); else BKX_LAUNCH_FAST(false, false); }
+#undef BKX_LAUNCH_FAST
   return cudaGetLastError();
 }
 
 int fast_blocks_per_sm(int W) {
   size_t smem = fast_smem_bytes(W);
-  ensure_smem(align_fast_kernel<false>, smem, g_smem_fast);
-  ensure_smem(align_fast_kernel<true>, smem, g_smem_fast_mlx);
-  int nb = 0, nb2 = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_fast_kernel<false>, kFastThreads, smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, align_fast_kernel<true>, kFastThreads, smem);
-  return nb < nb2 ? nb : nb2;
+  ensure_smem(align_fast_kernel<false, false>, smem, g_smem_fast);
+  ensure_smem(align_fast_kernel<true, false>, smem, g_smem_fast_mlx);
+  ensure_smem(align_fast_kernel<false, true>, smem, g_smem_fast_scan);
+  ensure_smem(align_fast_kernel<true, true>, smem, g_smem_fast_mlx_scan);
+  int nb[4] = {0, 0, 0, 0};
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[0], align_fast_kernel<false, false>, kFastThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[1], align_fast_kernel<true, false>, kFastThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[2], align_fast_kernel<false, true>, kFastThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[3], align_fast_kernel<true, true>, kFastThreads, smem);
+  return std::min(std::min(nb[0], nb[1]), std::min(nb[2], nb[3]));
 }
 
 // ------------------------------------------------------------------------------------------------

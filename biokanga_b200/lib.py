@@ -26,6 +26,8 @@ EXPORTS = [
     "bkx_pair_reads_device", "bkx_open_index_planes", "bkx_build_suffix_array_planes", "bkx_sort_hits", "bkx_align_reads_packed4",
     "bkx_pack_bases4", "bkx_align_reads_multi", "bkx_align_pairs", "bkx_align_pairs_packed4",
     "bkx_assign_multi_matches", "bkx_self_check", "bkx_debug_reset", "bkx_set_chrom_filter",
+    "bkx_align_reads_packed2", "bkx_align_pairs_packed2", "bkx_pack_bases2", "bkx_expand_results16",
+    "bkx_align_reads_device_packed2",
 ]
 
 
@@ -66,6 +68,12 @@ def lib():
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_pack_bases4.argtypes = [vp, u64, vp]
+    L.bkx_align_reads_packed2.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, vp, u64, u32, vp, C.POINTER(abi.AlignStats)]
+    L.bkx_align_pairs_packed2.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, vp, u32, vp, vp, u64, u32, vp,
+                                          C.POINTER(abi.AlignStats), C.POINTER(abi.PEStats), vp]
+    L.bkx_pack_bases2.argtypes = [vp, u64, vp, vp, vp, u64]
+    L.bkx_pack_bases2.restype = C.c_int64
+    L.bkx_expand_results16.argtypes = [vp, u32, vp, u32, vp]
     L.bkx_debug_reset.argtypes = [vp, i32]
     L.bkx_self_check.argtypes = [vp]
     L.bkx_self_check.restype = C.c_int64
@@ -85,6 +93,7 @@ def lib():
     L.bkx_default_params.argtypes = [vp, i32, C.POINTER(abi.AlignParams)]
     L.bkx_align_reads.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_align_reads_device.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, u32, vp, vp, vp]
+    L.bkx_align_reads_device_packed2.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, vp, vp, u32, u32, vp, vp, vp]
     L.bkx_align_one.argtypes = [vp, C.POINTER(abi.AlignParams), vp, i32, C.POINTER(i32), C.POINTER(i32),
                                 C.POINTER(i32), vp]
     L.bkx_pair_reads.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, u32, vp, vp,
@@ -125,6 +134,27 @@ def pack_bases4(bases):
     bases = np.ascontiguousarray(bases, dtype=np.uint8)
     out = np.zeros((bases.size + 1) // 2, dtype=np.uint8)
     check(lib().bkx_pack_bases4(bases.ctypes.data, bases.size, out.ctypes.data))
+    return out
+
+
+def pack_bases2(bases):
+    """One-byte base codes -> (2-bit stream [+ 8 bytes of slack], exception positions u64, exception codes u8)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    out = np.zeros((bases.size + 3) // 4 + 8, dtype=np.uint8)
+    cap = int((bases & 7 > 3).sum()) + 1
+    pos = np.zeros(cap, dtype=np.uint64)
+    code = np.zeros(cap, dtype=np.uint8)
+    n = check(lib().bkx_pack_bases2(bases.ctypes.data, bases.size, out.ctypes.data, pos.ctypes.data, code.ctypes.data, cap))
+    return out, pos[:n].copy(), code[:n].copy()
+
+
+def expand_results16(res16, lens=None, fixed_len=0):
+    """16-byte records -> 32-byte records (seeds / cands 0)."""
+    res16 = np.ascontiguousarray(res16, dtype=abi.RESULT16_DTYPE)
+    out = np.zeros(len(res16), dtype=abi.RESULT_DTYPE)
+    lp = np.ascontiguousarray(lens, dtype=np.uint16) if lens is not None else None
+    check(lib().bkx_expand_results16(res16.ctypes.data, len(res16), lp.ctypes.data if lp is not None else None, fixed_len,
+                                     out.ctypes.data))
     return out
 
 
@@ -299,10 +329,48 @@ class Index:
         self.align_packed4_ptr(params, packed.ctypes.data, offsets.ctypes.data, len(offsets) - 1, out.ctypes.data, st)
         return out, st
 
+    def align_packed2_ptr(self, params, packed2_ptr, lens_ptr, fixed_len, exc_pos_ptr, exc_code_ptr, n_exc, n_reads, out16_ptr,
+                          stats=None, pe=None, pe_stats=None, len_dist_ptr=None):
+        """The compact host interface on raw host pointers: 2 bits per base in, 16-byte records out (n_reads = reads, also
+        for paired ends)."""
+        st = C.byref(stats) if stats is not None else None
+        if pe is None:
+            check(lib().bkx_align_reads_packed2(self._h, C.byref(params), packed2_ptr, lens_ptr, fixed_len, exc_pos_ptr,
+                                                exc_code_ptr, n_exc, n_reads, out16_ptr, st))
+        else:
+            check(lib().bkx_align_pairs_packed2(self._h, C.byref(params), C.byref(pe), packed2_ptr, lens_ptr, fixed_len,
+                                                exc_pos_ptr, exc_code_ptr, n_exc, n_reads // 2, out16_ptr, st,
+                                                C.byref(pe_stats) if pe_stats is not None else None, len_dist_ptr))
+
+    def align_packed2(self, params, bases, offsets, pe=None, len_dist=None, fixed=None):
+        """Packs `bases` / `offsets` (one byte per base) into the compact layout, aligns, expands the records again:
+        (records, stats[, PE stats]).  fixed=None picks the fixed-length form when every read has the same length."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        lens = np.diff(offsets).astype(np.uint16)
+        o0 = int(offsets[0])
+        packed, pos, code = pack_bases2(bases[o0:int(offsets[-1])])
+        if fixed is None:
+            fixed = n > 0 and bool((lens == lens[0]).all())
+        out16 = np.zeros(n, dtype=abi.RESULT16_DTYPE)
+        st, ps = abi.AlignStats(), abi.PEStats()
+        self.align_packed2_ptr(params, packed.ctypes.data, None if fixed else lens.ctypes.data, int(lens[0]) if fixed else 0,
+                               pos.ctypes.data if len(pos) else None, code.ctypes.data if len(code) else None, len(pos), n,
+                               out16.ctypes.data, st, pe, ps, len_dist.ctypes.data if len_dist is not None else None)
+        res = expand_results16(out16, None if fixed else lens, int(lens[0]) if fixed else 0)
+        return (res, st) if pe is None else (res, st, ps)
+
     def align_device(self, params, d_bases, d_offsets, n_reads, max_read_len, d_out, d_stats=None, stream=None):
         """Device pointers, asynchronous on `stream` (a raw cudaStream_t value or None)."""
         check(lib().bkx_align_reads_device(self._h, C.byref(params), d_bases, d_offsets, n_reads, max_read_len,
                                            d_out, d_stats, stream))
+
+    def align_device_packed2(self, params, d_bases, d_packed2, d_read_flags, d_offsets, n_reads, max_read_len, d_out,
+                             d_stats=None, stream=None):
+        """Device pointers; the reads are resident one byte per base AND 2-bit packed (see include/bkx.h)."""
+        check(lib().bkx_align_reads_device_packed2(self._h, C.byref(params), d_bases, d_packed2, d_read_flags, d_offsets, n_reads,
+                                                   max_read_len, d_out, d_stats, stream))
 
     def align_one(self, params, probe):
         probe = np.ascontiguousarray(probe, dtype=np.uint8)

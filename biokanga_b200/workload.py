@@ -206,3 +206,27 @@ def algorithmic_bytes(results, concat_len, el_size, read_len):
     seeds = int(results["seeds"].astype(np.int64).sum())
     cands = int(results["cands"].astype(np.int64).sum())
     return seeds * S * (el_size + 8) + cands * (el_size + q) + len(results) * (q + 32)
+
+
+def pack2_device(d_bases, d_offs):
+    """The 2-bit copy of device-resident reads that bkx_align_reads_device_packed2 takes beside the one-byte-per-base layout:
+    (uint8 tensor of the packed stream with 16 bytes of slack -- base i at bits [2(i%4), +2) of byte i/4, non-ACGT bases as
+    0 --, uint8 per-read flags: the read holds a non-ACGT base)."""
+    import torch
+    nb = int(d_bases.numel())
+    codes = d_bases & 7
+    exc = codes > 3
+    c2 = torch.where(exc, torch.zeros_like(codes), codes)
+    pad = (-nb) % 4
+    if pad:
+        c2 = torch.cat([c2, torch.zeros(pad, dtype=c2.dtype, device=c2.device)])
+    q = c2.view(-1, 4)
+    pk = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).to(torch.uint8)
+    out = torch.zeros(((pk.numel() + 16 + 7) // 8) * 8, dtype=torch.uint8, device=d_bases.device)
+    out[:pk.numel()] = pk
+    # per-read flag: any exception inside [offs[r], offs[r + 1])
+    csum = torch.cumsum(exc.to(torch.int32), 0, dtype=torch.int64)
+    csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=d_bases.device), csum])
+    o = d_offs.to(torch.int64)
+    flags = ((csum[o[1:]] - csum[o[:-1]]) > 0).to(torch.uint8)
+    return out, flags

@@ -134,6 +134,21 @@ typedef struct bkx_read_result {
 
 enum { BKX_FLG_PE_ALIGNED = 1, BKX_FLG_PE_RECOVERED = 2 };
 
+/* The same record as it crosses PCIe in the compact host interface (bkx_align_reads_packed2 / bkx_align_pairs_packed2):
+ * 16 bytes.  Left out: seeds / cands (their sums are in bkx_align_stats) and match_len, which is the read's length
+ * whenever the record names a strand and 0 otherwise.  bkx_expand_results16 rebuilds the 32-byte form. */
+typedef struct bkx_read_result16 {
+  uint8_t nar_hr;             /* BKX_NAR_* in bits 0..4, BKX_HR_* in bits 5..7            */
+  uint8_t strand_flags;       /* bits 0..1: 0 none, 1 '+', 2 '-', 3 '?'; bits 2..3: BKX_FLG_* */
+  uint8_t num_hits;
+  uint8_t mismatches;
+  int8_t low_mm;
+  int8_t nxt_low_mm;
+  int16_t low_hit_instances;
+  uint32_t chrom_id;
+  uint32_t match_loci;
+} bkx_read_result16;
+
 /* One locus of a read under -r5 (BKX_ML_ALL): the tsHitLoci fields CAligner::WriteHitLoci copies into the record it
  * appends per hit (Aligner.cpp:6723-6790).  bkx_align_reads_multi returns max_ml_matches of these per read; the first
  * bkx_read_result::num_hits of a read's slots are valid, in the order LocateCoreMultiples found them. */
@@ -247,11 +262,39 @@ int bkx_align_reads_multi(bkx_index* idx, const bkx_align_params* params, const 
 int bkx_align_reads_packed4(bkx_index* idx, const bkx_align_params* params, const uint8_t* packed, const uint64_t* offsets,
                             uint32_t n_reads, bkx_read_result* out, bkx_align_stats* stats);
 int bkx_pack_bases4(const uint8_t* bases, uint64_t n_bases, uint8_t* packed);
+/* The compact host interface: what crosses PCIe per read is 2 bits per base in and 16 bytes out (the 4-bit call moves 4 bits
+ * + 8 bytes of offset in and 32 bytes out) -- on a multi-GPU node the host memory system, not the GPUs, bounds the
+ * host-buffer calls.
+ *   packed2   base i of the concatenated reads at bits [2(i%4), +2) of byte i/4, codes A0 C1 G2 T3; reads back to back at
+ *             base granularity.  Bases that are not A C G T are stored as 0 and listed in
+ *   exc_pos / exc_code   (n_exc entries, exc_pos ascending): position in the concatenation and etSeqBase code (4 = N, ...).
+ *   lens      read lengths (n_reads u16; cMaxSeqLen is 2000), or NULL when every read has fixed_len bases.
+ *   out       n_reads 16-byte records.
+ * Same search, same results as bkx_align_reads (the device expands the reads to the layout the kernels take).
+ * bkx_pack_bases2 packs n_bases one-byte codes (low 3 bits) that way: packed2 needs (n_bases + 3) / 4 bytes (+ 8 bytes of
+ * slack so that device copies may run in words); returns the number of exceptions, or BKX_ERR_MEM if exc_cap is too small. */
+int bkx_align_reads_packed2(bkx_index* idx, const bkx_align_params* params, const uint8_t* packed2, const uint16_t* lens,
+                            uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code, uint64_t n_exc,
+                            uint32_t n_reads, bkx_read_result16* out, bkx_align_stats* stats);
+int64_t bkx_pack_bases2(const uint8_t* bases, uint64_t n_bases, uint8_t* packed2, uint64_t* exc_pos, uint8_t* exc_code,
+                        uint64_t exc_cap);
+/* 16-byte records -> 32-byte records (seeds / cands 0); lens / fixed_len as above. */
+int bkx_expand_results16(const bkx_read_result16* in, uint32_t n_reads, const uint16_t* lens, uint32_t fixed_len,
+                         bkx_read_result* out);
 /* Device variant: all pointers are device pointers on idx's GPU; asynchronous on `cuda_stream`
  * (a cudaStream_t, NULL = the index's compute stream).  d_stats (device, may be NULL) is accumulated. */
 int bkx_align_reads_device(bkx_index* idx, const bkx_align_params* p, const uint8_t* d_bases,
                            const uint64_t* d_offsets, uint32_t n_reads, uint32_t max_read_len,
                            bkx_read_result* d_out, bkx_align_stats* d_stats, void* cuda_stream);
+/* Same, for reads that are resident in BOTH layouts: d_bases / d_offsets as above, and d_packed2 -- the same concatenation 2
+ * bits per base (base i at bits [2(i%32), +2) of 64-bit word i/32; 8-byte aligned, 16 readable bytes beyond the last base;
+ * non-ACGT bases stored as 0).  d_read_flags (one byte per read, or NULL when no read holds a non-ACGT base) marks the reads
+ * that must be taken from d_bases.  The search takes every other read straight from the 2-bit words (no packing pass in the
+ * kernel); reads it hands to the general kernel, and paired-end recovery, still use d_bases.  Same records as
+ * bkx_align_reads_device. */
+int bkx_align_reads_device_packed2(bkx_index* idx, const bkx_align_params* p, const uint8_t* d_bases, const uint64_t* d_packed2,
+                                   const uint8_t* d_read_flags, const uint64_t* d_offsets, uint32_t n_reads,
+                                   uint32_t max_read_len, bkx_read_result* d_out, bkx_align_stats* d_stats, void* cuda_stream);
 /* Per-read shim with the exact CSfxArrayV3::AlignReads contract (SfxArrayV2.h:585-606) for unit
  * parity tests: one read in, tHRslt out, In/Out (LowHitInstances, LowMMCnt, NxtLowMMCnt). */
 int bkx_align_one(bkx_index* idx, const bkx_align_params* p, const uint8_t* probe, int probe_len,
@@ -290,6 +333,12 @@ int bkx_align_pairs(bkx_index* idx, const bkx_align_params* params, const bkx_pe
                     bkx_pe_stats* pe_stats, uint32_t* len_dist);
 int bkx_align_pairs_packed4(bkx_index* idx, const bkx_align_params* params, const bkx_pe_params* pe, const uint8_t* packed,
                             const uint64_t* offsets, uint32_t n_pairs, bkx_read_result* out, bkx_align_stats* stats,
+                            bkx_pe_stats* pe_stats, uint32_t* len_dist);
+
+/* Paired ends through the compact host interface (see bkx_align_reads_packed2): reads 2i / 2i+1 are PE1 / PE2 of pair i. */
+int bkx_align_pairs_packed2(bkx_index* idx, const bkx_align_params* params, const bkx_pe_params* pe, const uint8_t* packed2,
+                            const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code,
+                            uint64_t n_exc, uint32_t n_pairs, bkx_read_result16* out, bkx_align_stats* stats,
                             bkx_pe_stats* pe_stats, uint32_t* len_dist);
 
 /* ---- -r3 / -r4: one locus for reads that hit several, by clustering with the loci of other reads.  Replaces

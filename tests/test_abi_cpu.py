@@ -52,3 +52,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert "pyoracle" not in txt and "bk_oracle" not in txt and "libbkoracle" not in txt, f
+
+
+def test_pack_bases2_and_expand_results16_are_host_functions():
+    """The two host-side helpers of the compact interface need no device: 2-bit stream + exception list, and the
+    16-byte -> 32-byte record expansion."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 3, 4, 5, 1003):
+        b = rng.integers(0, 4, n).astype(np.uint8)
+        if n > 5:
+            b[[0, 5, n - 1]] = [4, 6, 4]
+        pk, pos, code = bkx.pack_bases2(b | 0x30)   # quality bits in the high nibble are ignored
+        dec = np.array([(pk[i // 4] >> (2 * (i % 4))) & 3 for i in range(n)], dtype=np.uint8)
+        exp = b.copy()
+        exp[b > 3] = 0
+        assert np.array_equal(dec, exp)
+        assert np.array_equal(pos, np.nonzero(b > 3)[0]) and np.array_equal(code, b[b > 3])
+    r16 = np.zeros(3, dtype=abi.RESULT16_DTYPE)
+    r16["nar_hr"] = [1 | (1 << 5), 5 | (3 << 5), 3]
+    r16["strand_flags"] = [2 | (1 << 2), 3, 0]
+    r16["chrom_id"], r16["match_loci"], r16["mismatches"], r16["low_hit_instances"] = [7, 0, 0], [123, 0, 0], [2, 0, 0], [1, 2, 0]
+    r = bkx.expand_results16(r16, lens=np.array([100, 150, 75], dtype=np.uint16))
+    assert list(r["nar"]) == [1, 5, 3] and list(r["hit_rslt"]) == [1, 3, 0] and list(r["strand"]) == [ord("-"), ord("?"), 0]
+    assert list(r["match_len"]) == [100, 150, 0] and list(r["flags"]) == [1, 0, 0] and list(r["mismatches"]) == [2, 0, 0]
+    assert abi.RESULT16_DTYPE.itemsize == 16
