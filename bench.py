@@ -9,9 +9,12 @@ injected diverged repeats, 20 M simulated 150 bp SE reads carrying 0..4 substitu
 and reads are generated on the device with fixed seeds; there are no datasets to download.
 
 A "step" is one pass of the align hot path over the rank's 20 M reads.
-  value     reads/s with reads already resident in HBM (device-pointer C-ABI entry, CUDA events)
-  e2e       the same metric through bkx_align_reads() with pinned HOST buffers: H2D of the reads and
-            D2H of the 32-byte records are inside the timed region
+  value     reads/s with reads already resident in HBM, one byte per base plus the 2-bit copy the fast kernel takes
+            (device-pointer C-ABI entry bkx_align_reads_device_packed2, CUDA events); the one-byte-only entry
+            is timed beside it (value_byte_layout)
+  e2e       the same metric through the compact host call bkx_align_reads_packed2() with pinned HOST buffers: H2D
+            of the reads (2 bits per base) and D2H of the 16-byte records are inside the timed region; the 4-bit
+            and one-byte-per-base host calls are timed beside it
   roofline  algorithmic bytes of one launch / measured kernel time / measured HBM peak
   cpu_baseline  the CPU restatement (oracle/, "port") on a bounded sample with all host cores
 N > 1 (torchrun): rank 0 builds the index and broadcasts it over NCCL/NVLink; every rank aligns its
@@ -197,10 +200,20 @@ def run_bkx(args):
     d_pst = torch.zeros(C.sizeof(abi.PEStats) // 8, dtype=torch.int64, device=dev)
     d_ld = torch.zeros(100001, dtype=torch.int32, device=dev)
 
+    # the reads are resident in both layouts: one byte per base (the reference's in-memory layout; read by the general
+    # kernel, the orphan recovery and for reads holding an N) and 2 bits per base (what the fast kernel takes)
+    d_pk2, d_rflags = wl.pack2_device(d_bases, d_offs)
+    torch.cuda.synchronize()
+    byte_layout = [False]
+
     def step():
         d_stats.zero_()
-        idx.align_device(p, d_bases.data_ptr(), d_offs.data_ptr(), nreads, args.read_len, d_out.data_ptr(),
-                         d_stats.data_ptr(), stream)
+        if byte_layout[0]:
+            idx.align_device(p, d_bases.data_ptr(), d_offs.data_ptr(), nreads, args.read_len, d_out.data_ptr(),
+                             d_stats.data_ptr(), stream)
+        else:
+            idx.align_device_packed2(p, d_bases.data_ptr(), d_pk2.data_ptr(), d_rflags.data_ptr(), d_offs.data_ptr(), nreads,
+                                     args.read_len, d_out.data_ptr(), d_stats.data_ptr(), stream)
         if pe_mode:
             d_pst.zero_()
             idx.pair_device(p, pe, d_out.data_ptr(), nreads // 2, d_bases.data_ptr(), d_offs.data_ptr(), args.read_len,
@@ -247,8 +260,25 @@ def run_bkx(args):
     ms_per_step = total_ms / args.steps
     value = world * nreads / (ms_per_step / 1e3)
 
-    res = d_out.cpu().numpy().view(abi.RESULT_DTYPE)
+    res = d_out.cpu().numpy().view(abi.RESULT_DTYPE).copy()
     stats = d_stats.cpu().numpy()
+    # the one-byte-per-base entry point on the same reads (what round 1 reported as `value`)
+    byte_layout[0] = True
+    step()
+    barrier()
+    evb = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    nb_steps = max(1, min(args.steps, 3))
+    evb[0].record()
+    for _ in range(nb_steps):
+        step()
+    evb[1].record()
+    barrier()
+    tb = torch.tensor([evb[0].elapsed_time(evb[1]) / nb_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    value_bytes = world * nreads / (float(tb.item()) / 1e3)
+    same_layouts = bool(d_out.cpu().numpy().view(abi.RESULT_DTYPE).tobytes() == res.tobytes())
+    byte_layout[0] = False
     alg_bytes = wl.algorithmic_bytes(res, n, 4, args.read_len)
     kms = float(np.mean(kern_ms))
     peak, peak_src = measured_peak()
@@ -261,47 +291,58 @@ def run_bkx(args):
     h_bases = torch.empty(nreads * args.read_len, dtype=torch.uint8).pin_memory()
     h_bases.copy_(d_bases)
     h_packed = torch.from_numpy(bkx.pack_bases4(h_bases.numpy())).pin_memory()
+    pk2_np, exc_pos_np, exc_code_np = bkx.pack_bases2(h_bases.numpy())
+    h_pk2 = torch.from_numpy(pk2_np).pin_memory()
+    h_exc_pos = torch.from_numpy(exc_pos_np.view(np.int64) if len(exc_pos_np) else np.zeros(1, dtype=np.int64)).pin_memory()
+    h_exc_code = torch.from_numpy(exc_code_np if len(exc_code_np) else np.zeros(1, dtype=np.uint8)).pin_memory()
+    n_exc = int(len(exc_pos_np))
     h_offs = (torch.arange(nreads + 1, dtype=torch.int64) * args.read_len).pin_memory()
     h_out = torch.empty(nreads * 32, dtype=torch.uint8).pin_memory()
+    h_out16 = torch.empty(nreads * 16, dtype=torch.uint8).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
     hst = abi.AlignStats()
-    h_res_np = h_out.numpy().view(abi.RESULT_DTYPE)
-
     h_pst = abi.PEStats()
 
-    def e2e_call(packed):
-        if pe_mode:  # align + pair fused: every slice is paired (orphans recovered) while it is still on the GPU
-            idx.align_pairs_ptr(p, pe, (h_packed if packed else h_bases).data_ptr(), h_offs.data_ptr(), nreads // 2,
-                                h_out.data_ptr(), hst, h_pst, None, packed=packed)
-        elif packed:
+    def e2e_call(form):
+        if form == "packed2":   # the compact host interface: 2 bits per base in, 16-byte records out
+            idx.align_packed2_ptr(p, h_pk2.data_ptr(), None, args.read_len, h_exc_pos.data_ptr() if n_exc else None,
+                                  h_exc_code.data_ptr() if n_exc else None, n_exc, nreads, h_out16.data_ptr(), hst,
+                                  pe if pe_mode else None, h_pst if pe_mode else None, None)
+        elif pe_mode:  # align + pair fused: every slice is paired (orphans recovered) while it is still on the GPU
+            idx.align_pairs_ptr(p, pe, (h_packed if form == "packed4" else h_bases).data_ptr(), h_offs.data_ptr(), nreads // 2,
+                                h_out.data_ptr(), hst, h_pst, None, packed=form == "packed4")
+        elif form == "packed4":
             idx.align_packed4_ptr(p, h_packed.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
         else:
             idx.align_ptr(p, h_bases.data_ptr(), h_offs.data_ptr(), nreads, h_out.data_ptr(), hst)
 
-    def time_e2e(packed):
-        e2e_call(packed)  # warm-up
+    def time_e2e(form):
+        e2e_call(form)  # warm-up
         barrier()
         reps = []
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             t1 = time.perf_counter()
-            e2e_call(packed)
+            e2e_call(form)
             reps.append(round((time.perf_counter() - t1) * 1e3, 2))
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        log("[bench] e2e %s: per-call ms %s, kernel ms %.2f" % ("packed4" if packed else "bytes", reps, idx.last_kernel_ms()))
+        log("[bench] e2e %s: per-call ms %s, kernel ms %.2f" % (form, reps, idx.last_kernel_ms()))
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        ok = bool(np.array_equal(h_out.numpy().view(abi.RESULT_DTYPE)["match_loci"], res["match_loci"]))
+        if form == "packed2":
+            got = bkx.expand_results16(h_out16.numpy().view(abi.RESULT16_DTYPE), fixed_len=args.read_len)
+        else:
+            got = h_out.numpy().view(abi.RESULT_DTYPE)
+        ok = all(bool(np.array_equal(got[f], res[f])) for f in ("nar", "hit_rslt", "strand", "chrom_id", "match_loci", "match_len",
+                                                                "mismatches", "low_mm", "nxt_low_mm", "low_hit_instances", "flags"))
         return world * nreads / float(te.item()), ok
 
-    e2e_value, same = time_e2e(True)
-    e2e_bytes_value, same_b = time_e2e(False)
-    if os.environ.get("BKX_E2E_AGAIN"):
-        time_e2e(True)
-        time_e2e(False)
-    same = same and same_b
+    e2e_value, same = time_e2e("packed2")
+    e2e_p4_value, same_4 = time_e2e("packed4")
+    e2e_bytes_value, same_b = time_e2e("bytes")
+    same = same and same_4 and same_b
 
     line = {
         "metric": "aligned reads/sec (150bp, <=4 subs)", "value": value, "unit": "reads/s", "n_gpus": world,
@@ -318,14 +359,23 @@ def run_bkx(args):
                    "max_subs_per_100bp": args.max_subs, "prefix_k": int(idx.info.prefix_k),
                    "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (
                        idx.info.device_bytes / 1e9, nreads * args.read_len / 1e9),
+                   "resident_layout": "reads in HBM one byte per base + their 2-bit copy (bkx_align_reads_device_packed2)",
                    "parallelism": "reads sharded over %d GPU(s), index replicated" % world},
+        "value_byte_layout": {"value": value_bytes, "call": "bkx_align_reads_device (reads resident one byte per base only)",
+                              "same_records": same_layouts},
         "e2e": {"value": e2e_value, "unit": "reads/s",
-                "h2d_bytes_per_step": int((nreads * args.read_len + 1) // 2 + (nreads + 1) * 8),
-                "d2h_bytes_per_step": int(nreads * 32), "matches_device_run": same,
-                "call": ("bkx_align_pairs_packed4" if pe_mode else "bkx_align_reads_packed4") +
-                        " (pinned host buffers, reads 4-bit packed)",
+                "h2d_bytes_per_step": int((nreads * args.read_len + 3) // 4 + n_exc * 9),
+                "d2h_bytes_per_step": int(nreads * 16), "matches_device_run": same,
+                "call": ("bkx_align_pairs_packed2" if pe_mode else "bkx_align_reads_packed2") +
+                        " (pinned host buffers: reads 2 bits per base + list of the non-ACGT bases, fixed read length, "
+                        "16-byte records back)",
+                "bytes_per_read_over_pcie": ((nreads * args.read_len + 3) // 4 + n_exc * 9 + nreads * 16) / nreads,
+                "packed4_call": {"value": e2e_p4_value, "call": "bkx_align_pairs_packed4" if pe_mode else "bkx_align_reads_packed4",
+                                 "h2d_bytes_per_step": int((nreads * args.read_len + 1) // 2 + (nreads + 1) * 8),
+                                 "d2h_bytes_per_step": int(nreads * 32)},
                 "byte_per_base_call": {"value": e2e_bytes_value, "call": "bkx_align_pairs" if pe_mode else "bkx_align_reads",
-                                       "h2d_bytes_per_step": int(nreads * args.read_len + (nreads + 1) * 8)}},
+                                       "h2d_bytes_per_step": int(nreads * args.read_len + (nreads + 1) * 8),
+                                       "d2h_bytes_per_step": int(nreads * 32)}},
         "gpu_launches": int(args.steps * launches_per_step),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(args), "kernel": "align_fast_kernel + align_reads_kernel (deferred reads)",
@@ -436,23 +486,33 @@ def run_hexaploid(args):
     torch.cuda.synchronize()
     t1 = time.time()
     five = n >= 4_000_000_000
-    d_lo = torch.empty(n, dtype=torch.int32, device=dev)
-    d_hi = torch.empty(n, dtype=torch.uint8, device=dev) if five else None
-    torch.cuda.empty_cache()
-    bkx.build_suffix_array_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr() if five else None, 0, 0)
+    if five:   # 5-byte elements back to back, as in the .sfx file: the layout the search reads (one fetch per element)
+        d_sa = torch.zeros(n * 5 + 16, dtype=torch.uint8, device=dev)
+        torch.cuda.empty_cache()
+        bkx.build_suffix_array_packed5(d_seq.data_ptr(), n, d_sa.data_ptr(), 0, 0)
+    else:
+        d_sa = torch.empty(n, dtype=torch.int32, device=dev)
+        torch.cuda.empty_cache()
+        bkx.build_suffix_array_planes(d_seq.data_ptr(), n, d_sa.data_ptr(), None, 0, 0)
     torch.cuda.synchronize()
     t2 = time.time()
     log("[bench] hexaploid genome %.2f Gsym in %.1fs, suffix array (%d-byte elements) in %.1fs" % (
         n / 1e9, t1 - t0, 5 if five else 4, t2 - t1))
-    idx = bkx.Index.from_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr() if five else None, ents,
-                                name="hexaploid%dM" % args.genome_mbp, device=0, prefix_k=args.prefix_k)
-    torch.cuda.synchronize()
-    t3 = time.time()
-    log("[bench] index resident: %.1f GB HBM, prefix k=%d, %.1fs" % (idx.info.device_bytes / 1e9, idx.info.prefix_k, t3 - t2))
+    # the reads are drawn before the index takes the rest of the HBM (k = 17 table: 69 GB beside the 70 GB suffix array)
     nreads, L = args.reads, args.read_len
     d_bases, d_offs = wl.sim_reads(d_seq, ents, nreads, L, seed=args.seed + 100, subs=tuple(range(0, args.read_subs + 1)),
                                    device=dev)
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if five:
+        idx = bkx.Index.from_packed5(d_seq.data_ptr(), n, d_sa.data_ptr(), ents, name="hexaploid%dM" % args.genome_mbp, device=0,
+                                     prefix_k=args.prefix_k)
+    else:
+        idx = bkx.Index.from_planes(d_seq.data_ptr(), n, d_sa.data_ptr(), None, ents, name="hexaploid%dM" % args.genome_mbp,
+                                    device=0, prefix_k=args.prefix_k)
+    torch.cuda.synchronize()
+    t3 = time.time()
+    log("[bench] index resident: %.1f GB HBM, prefix k=%d, %.1fs" % (idx.info.device_bytes / 1e9, idx.info.prefix_k, t3 - t2))
     el = int(idx.info.sfx_el_size)
     p = idx.default_params(0, max_subs=args.max_subs)
     d_out = torch.empty(nreads * 32, dtype=torch.uint8, device=dev)
@@ -557,16 +617,9 @@ def run_hexaploid(args):
             tc = time.time()
             host_seq = d_seq.cpu().numpy()
             if el == 4:
-                host_sa = d_lo.cpu().numpy().view(np.uint32)
+                host_sa = d_sa.cpu().numpy().view(np.uint32)
             else:
-                host_sa = np.empty((n, 5), dtype=np.uint8)
-                CHK = 1 << 28
-                for s0 in range(0, n, CHK):
-                    m = min(CHK, n - s0)
-                    blk = torch.cat([d_lo[s0:s0 + m].view(torch.uint8).view(m, 4), d_hi[s0:s0 + m].view(m, 1)], dim=1)
-                    host_sa[s0:s0 + m] = blk.cpu().numpy()
-                    del blk
-                host_sa = host_sa.reshape(-1)
+                host_sa = d_sa[:n * 5].cpu().numpy()
             log("[bench] index copied to host in %.1fs" % (time.time() - tc))
             oidx = po.OracleIndex(seq=host_seq, sa=host_sa, el_size=el, entries=ents)
             m = min(args.cpu_sample, 300000, nreads)   # the 14 G-symbol search is several times slower per read

@@ -144,11 +144,14 @@ static int choose_k(uint64_t n, int requested, size_t free_bytes, bool wide) {
   if (requested > 0) return std::min(std::max(requested, 4), 17);
   // ceil(log4 n) + 1: on average 1/4 suffix per bucket, so most absent cores die at the table lookup
   // without touching the suffix array (measured: k=17 beats 16 by 8 % at 3.1 G symbols).  HBM is there
-  // to be used (180 GB): the table may take up to 55 % of what is free.
+  // to be used (180 GB): the table may take up to 55 % of what is free -- for indexes of >= 2^32 symbols (wheat scale:
+  // 70 GB of suffix array, where a table one size down leaves 3.3 suffixes per bucket and nearly every absent core then
+  // costs a suffix-array and a genome fetch) everything but 14 GB for reads, records and the kernels' hash sets.
   int k = 8;
   while (k < 17 && (1ull << (2 * (k - 1))) < n) ++k;
-  size_t el = wide ? 8 : 4;
-  while (k > 8 && (double)((1ull << (2 * k)) + 1) * el > 0.55 * (double)free_bytes) --k;
+  const double budget = wide ? std::max(0.55 * (double)free_bytes, (double)free_bytes - 14.0 * (double)(1ull << 30))
+                             : 0.55 * (double)free_bytes;
+  while (k > 8 && (double)((1ull << (2 * k)) + 1) * 4.0 > budget) --k;
   return k;
 }
 
@@ -157,9 +160,10 @@ static int choose_k(uint64_t n, int requested, size_t free_bytes, bool wide) {
 static thread_local bool g_selfcheck_failed = false;   // set by finish_index, read by bkx_open_index's retry loop
 
 struct SaSrc {
-  const void* raw = nullptr;
-  const uint32_t* lo = nullptr;
-  const uint8_t* hi = nullptr;
+  const void* raw = nullptr;      // elements as the .sfx stores them (4 or 5 bytes each): copied
+  const uint32_t* lo = nullptr;   // planes already on the device: used as they are (4-byte elements) or merged into 5-byte
+  const uint8_t* hi = nullptr;    //   elements (copied)
+  const uint8_t* packed5 = nullptr;   // 5-byte elements already on the device, 8-byte aligned with 16 bytes of slack: used as they are
 };
 
 // Build every derived structure from a device-resident 1-byte/base sequence and the suffix array.
@@ -199,27 +203,33 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
   x->d.g2 = g2; x->d.gx = gx; x->d.gxc = gxc; x->d.n = n;
   REG_ARR(x, g2, g2w * 8); REG_ARR(x, gx, gxw * 8); REG_ARR(x, gxc, gcw * 4);
 
-  if (sa.lo) {
-    if (el == 5 && !sa.hi) return fail(BKX_ERR_PARAM, "5-byte suffix elements need the high plane");
+  if (sa.packed5) {
+    if ((uintptr_t)sa.packed5 & 7) return fail(BKX_ERR_PARAM, "5-byte suffix elements must start on an 8-byte boundary");
+    x->d.sa5 = sa.packed5;
+    REG_ARR(x, sa5, n * 5 + 16);
+  } else if (sa.lo && el == 4) {
     x->d.sa_lo = sa.lo;
-    x->d.sa_hi = el == 5 ? sa.hi : nullptr;
     REG_ARR(x, sa_lo, n * 4);
-    if (el == 5) REG_ARR(x, sa_hi, n);
+  } else if (sa.lo) {   // borrowed planes, 5-byte elements: merged into the one-fetch layout (the planes stay the caller's)
+    if (!sa.hi) return fail(BKX_ERR_PARAM, "5-byte suffix elements need the high plane");
+    uint8_t* s5;
+    if ((rc = dev_alloc(x, &s5, n * 5 + 16, false)) < 0) return rc;
+    CU(launch_merge_sa5(sa.lo, sa.hi, n, s5, st));
+    x->launches += 1;
+    x->d.sa5 = s5;
+    REG_ARR(x, sa5, n * 5 + 16);
   } else if (el == 4) {
     uint32_t* lo;
     if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
     CU(cudaMemcpyAsync(lo, sa.raw, n * 4, cudaMemcpyDeviceToDevice, st));
     x->d.sa_lo = lo;
-    x->d.sa_hi = nullptr;
     REG_ARR(x, sa_lo, n * 4);
   } else {
-    uint32_t* lo; uint8_t* hi;
-    if ((rc = dev_alloc(x, &lo, n, false)) < 0) return rc;
-    if ((rc = dev_alloc(x, &hi, n, false)) < 0) return rc;
-    CU(launch_split_sa5((const uint8_t*)sa.raw, n, lo, hi, st));
-    x->launches += 1;
-    x->d.sa_lo = lo; x->d.sa_hi = hi;
-    REG_ARR(x, sa_lo, n * 4); REG_ARR(x, sa_hi, n);
+    uint8_t* s5;
+    if ((rc = dev_alloc(x, &s5, n * 5 + 16, false)) < 0) return rc;
+    CU(cudaMemcpyAsync(s5, sa.raw, n * 5, cudaMemcpyDeviceToDevice, st));
+    x->d.sa5 = s5;
+    REG_ARR(x, sa5, n * 5 + 16);
   }
   // chromosome table
   std::vector<uint64_t> es(n_ent), ee(n_ent);
@@ -267,16 +277,23 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
   // prefix table
   size_t free_b = 0, total_b = 0;
   CU(cudaMemGetInfo(&free_b, &total_b));
-  bool wide = n >= (1ull << 32) || getenv("BKX_FORCE_WIDE_PT") != nullptr;  // (env: test hook for the u64 table)
+  bool wide = n >= (1ull << 32) || getenv("BKX_FORCE_WIDE_PT") != nullptr;  // (env: test hook for the two-level table)
   int k = choose_k(n, prefix_k, free_b, wide);
   uint64_t pt_entries = (1ull << (2 * k)) + 1;
-  void* pt = nullptr;
-  if (wide) { uint64_t* t; if ((rc = dev_alloc(x, &t, pt_entries, false)) < 0) return rc; pt = t; x->d.pt64 = t; x->d.pt32 = nullptr; }
-  else { uint32_t* t; if ((rc = dev_alloc(x, &t, pt_entries, false)) < 0) return rc; pt = t; x->d.pt32 = t; x->d.pt64 = nullptr; }
+  uint32_t* pt = nullptr;
+  uint64_t* pt_hi = nullptr;
+  if ((rc = dev_alloc(x, &pt, pt_entries, false)) < 0) return rc;
+  x->d.pt32 = pt;
+  x->d.pt_hi = nullptr;   // set once the table is built: the histogram kernel reads the genome through x->d only
   x->d.k = k;
   x->info.prefix_k = (uint32_t)k;
-  if (wide) REG_ARR(x, pt64, pt_entries * 8); else REG_ARR(x, pt32, pt_entries * 4);
-  CU(build_prefix_table(x->d, k, pt, wide, st));
+  REG_ARR(x, pt32, pt_entries * 4);
+  const uint64_t pt_blocks = (pt_entries + (1u << kPtBlockShift) - 1) >> kPtBlockShift;
+  if (wide) {
+    if ((rc = dev_alloc(x, &pt_hi, pt_blocks, false)) < 0) return rc;
+  }
+  CU(build_prefix_table(x->d, k, pt, pt_hi, st));
+  if (wide) { x->d.pt_hi = pt_hi; REG_ARR(x, pt_hi, pt_blocks * 8); }
   x->launches += 2;
   CU(cudaStreamSynchronize(st));
   // self-check: every suffix-array element inside the table bucket of its suffix (0.3 s at 3.1 G symbols); a failure
@@ -400,6 +417,22 @@ extern "C" int bkx_open_index_planes(const uint8_t* d_seq, uint64_t concat_len, 
   return BKX_OK;
 }
 
+extern "C" int bkx_open_index_packed5(const uint8_t* d_seq, uint64_t concat_len, const uint8_t* d_sa5, const bkx_entry* entries,
+                                      uint32_t n_ent, const char* name, int device, int prefix_k, bkx_index** out) {
+  if (!d_seq || !d_sa5 || !entries || !out) return fail(BKX_ERR_PARAM, "null argument");
+  bkx_index* x = nullptr;
+  int rc = new_index(device, &x);
+  if (rc < 0) return rc;
+  x->info.version = 5;
+  CU(cudaDeviceSynchronize());  // the caller's buffers may come from any stream; the library's streams are non-blocking
+  SaSrc src;  // borrowed: not entered in x->owned, so bkx_close_index leaves the array alone
+  src.packed5 = d_sa5;
+  rc = finish_index(x, d_seq, concat_len, src, 5, entries, n_ent, name, prefix_k);
+  if (rc < 0) { bkx_close_index(x); return rc; }
+  *out = x;
+  return BKX_OK;
+}
+
 extern "C" int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t el,
                                   const bkx_entry* entries, uint32_t n_ent, const char* name, int device, int prefix_k,
                                   bkx_index** out) {
@@ -515,12 +548,10 @@ static int open_index_once(const char* path, int device, int prefix_k, bkx_index
   // array; 5-byte elements pass through a device staging buffer and are split into the two planes chunk by chunk, so
   // an 84 GB index never needs more than its final footprint.
   uint8_t* d_seq = nullptr;
-  uint32_t* d_lo = nullptr;
-  uint8_t* d_hi = nullptr;
+  uint8_t* d_sa = nullptr;   // the elements as the file holds them: u32, or 5 bytes each (+ 16 bytes of slack)
   const size_t chunk = (size_t)60 << 20;  // a multiple of 5 and of 4
   cudaError_t e = cudaMalloc((void**)&d_seq, n);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_lo, n * 4);
-  if (e == cudaSuccess && el == 5) e = cudaMalloc((void**)&d_hi, n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_sa, n * el + 16);
   bool io_ok = true;
   if (e == cudaSuccess) {
     const uint64_t seq_chunks = (n + chunk - 1) / chunk, sa_bytes = n * el, sa_chunks = (sa_bytes + chunk - 1) / chunk;
@@ -534,30 +565,18 @@ static int open_index_once(const char* path, int device, int prefix_k, bkx_index
       workers.emplace_back([&, w]() {
         cudaError_t ce = cudaSetDevice(device);
         uint8_t* pin = nullptr;
-        uint8_t* stage = nullptr;
         cudaStream_t st = nullptr;
         if (ce == cudaSuccess) ce = cudaMallocHost((void**)&pin, chunk);
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-        if (ce == cudaSuccess && el == 5) ce = cudaMalloc((void**)&stage, chunk);
         for (uint64_t c = (uint64_t)w; c < n_chunks && ce == cudaSuccess && wio[(size_t)w]; c += (uint64_t)n_workers) {
           const bool is_seq = c < seq_chunks;
           const uint64_t ofs = is_seq ? c * chunk : (c - seq_chunks) * chunk;
           const size_t len = (size_t)std::min<uint64_t>(chunk, (is_seq ? n : sa_bytes) - ofs);
           if (!pread_all(fd, pin, len, (off_t)(blk_ofs + 20 + (is_seq ? ofs : n + ofs)))) { wio[(size_t)w] = 0; break; }
-          if (is_seq) {
-            ce = cudaMemcpyAsync(d_seq + ofs, pin, len, cudaMemcpyHostToDevice, st);
-          } else if (el == 4) {
-            ce = cudaMemcpyAsync((uint8_t*)d_lo + ofs, pin, len, cudaMemcpyHostToDevice, st);
-          } else {
-            const uint64_t first = ofs / 5;  // chunks start on element boundaries (chunk % 5 == 0)
-            ce = cudaMemcpyAsync(stage, pin, len, cudaMemcpyHostToDevice, st);
-            if (ce == cudaSuccess) ce = launch_split_sa5(stage, len / 5, d_lo + first, d_hi + first, st);
-            ++wlaunch[(size_t)w];
-          }
+          ce = cudaMemcpyAsync((is_seq ? d_seq : d_sa) + ofs, pin, len, cudaMemcpyHostToDevice, st);
           if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // the pinned buffer is about to be refilled
         }
         if (pin) cudaFreeHost(pin);
-        if (stage) cudaFree(stage);
         if (st) cudaStreamDestroy(st);
         werr[(size_t)w] = ce;
       });
@@ -570,16 +589,14 @@ static int open_index_once(const char* path, int device, int prefix_k, bkx_index
   }
   close(fd);
   if (e != cudaSuccess || !io_ok) {
-    cudaFree(d_seq); cudaFree(d_lo); cudaFree(d_hi); bkx_close_index(x);
+    cudaFree(d_seq); cudaFree(d_sa); bkx_close_index(x);
     return e != cudaSuccess ? fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e))
                             : fail(BKX_ERR_FILE, "'%s': short read", path);
   }
-  x->owned.push_back(d_lo);
-  x->info.device_bytes += n * 4;
-  if (d_hi) { x->owned.push_back(d_hi); x->info.device_bytes += n; }
+  x->owned.push_back(d_sa);
+  x->info.device_bytes += n * el + 16;
   SaSrc src;
-  src.lo = d_lo;
-  src.hi = d_hi;
+  if (el == 4) src.lo = (const uint32_t*)d_sa; else src.packed5 = d_sa;
   rc = finish_index(x, d_seq, n, src, el, ents.data(), n_ent, dataset, prefix_k);
   cudaFree(d_seq);
   if (rc < 0) { bkx_close_index(x); return rc; }
@@ -994,6 +1011,7 @@ struct HostReads {
   const uint64_t* exc_pos = nullptr;  // PACKED2: bases that are not A C G T
   const uint8_t* exc_code = nullptr;
   uint64_t n_exc = 0;
+  uint64_t first_base = 0;            // PACKED2: stream position of read 0
 };
 
 static int align_host(bkx_index* x, const bkx_align_params* p, const HostReads& hr, uint32_t n_reads, void* out_any,
@@ -1044,7 +1062,7 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const HostReads& 
   uint32_t ramp = kMinSlice;
   float ms_total = 0.f;
   uint32_t start = 0;
-  uint64_t base_pos = 0;   // PACKED2: position of read `start` in the concatenation
+  uint64_t base_pos = hr.first_base;   // PACKED2: position of read `start` in the stream
   uint64_t exc_next = 0;   // PACKED2: first exception at or after base_pos
   int b = 0;
   bool inflight[kSlots] = {};
@@ -1288,11 +1306,12 @@ static HostReads reads_bytes(const uint8_t* bases, const uint64_t* offsets, bool
   h.offsets = offsets;
   return h;
 }
-static HostReads reads_packed2(const uint8_t* packed2, const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos,
-                               const uint8_t* exc_code, uint64_t n_exc) {
+static HostReads reads_packed2(const uint8_t* packed2, uint64_t first_base, const uint16_t* lens, uint32_t fixed_len,
+                               const uint64_t* exc_pos, const uint8_t* exc_code, uint64_t n_exc) {
   HostReads h;
   h.fmt = HostReads::PACKED2;
   h.data = packed2; h.lens = lens; h.fixed_len = fixed_len; h.exc_pos = exc_pos; h.exc_code = exc_code; h.n_exc = n_exc;
+  h.first_base = first_base;
   return h;
 }
 
@@ -1330,21 +1349,22 @@ extern "C" int bkx_align_reads_packed4(bkx_index* x, const bkx_align_params* p, 
   return align_host(x, p, reads_bytes(packed, offsets, true), n_reads, out, false, stats);
 }
 
-extern "C" int bkx_align_reads_packed2(bkx_index* x, const bkx_align_params* p, const uint8_t* packed2, const uint16_t* lens,
-                                       uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code, uint64_t n_exc,
-                                       uint32_t n_reads, bkx_read_result16* out, bkx_align_stats* stats) {
+extern "C" int bkx_align_reads_packed2(bkx_index* x, const bkx_align_params* p, const uint8_t* packed2, uint64_t first_base,
+                                       const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code,
+                                       uint64_t n_exc, uint32_t n_reads, bkx_read_result16* out, bkx_align_stats* stats) {
   if (p && p->ml_mode >= BKX_ML_UNIQ) return fail(BKX_ERR_UNSUPPORTED, "-r3..5 need bkx_align_reads_multi");
-  return align_host(x, p, reads_packed2(packed2, lens, fixed_len, exc_pos, exc_code, n_exc), n_reads, out, true, stats);
+  return align_host(x, p, reads_packed2(packed2, first_base, lens, fixed_len, exc_pos, exc_code, n_exc), n_reads, out, true, stats);
 }
 
 extern "C" int bkx_align_pairs_packed2(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, const uint8_t* packed2,
-                                       const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code,
-                                       uint64_t n_exc, uint32_t n_pairs, bkx_read_result16* out, bkx_align_stats* stats,
-                                       bkx_pe_stats* pe_stats, uint32_t* len_dist) {
+                                       uint64_t first_base, const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos,
+                                       const uint8_t* exc_code, uint64_t n_exc, uint32_t n_pairs, bkx_read_result16* out,
+                                       bkx_align_stats* stats, bkx_pe_stats* pe_stats, uint32_t* len_dist) {
   if (n_pairs > 0x7fffffffu) return fail(BKX_ERR_PARAM, "too many pairs");
   PeCall pc;
   pc.pe = pe; pc.stats = pe_stats; pc.len_dist = len_dist;
-  return align_host(x, p, reads_packed2(packed2, lens, fixed_len, exc_pos, exc_code, n_exc), 2 * n_pairs, out, true, stats, nullptr, &pc);
+  return align_host(x, p, reads_packed2(packed2, first_base, lens, fixed_len, exc_pos, exc_code, n_exc), 2 * n_pairs, out, true, stats,
+                    nullptr, &pc);
 }
 
 // One-byte codes -> 2-bit stream + exception list (the loop a loader fuses into its parser).  A code above T goes into the

@@ -5,10 +5,12 @@
 //        (A0 C1 G2 T3; N is stored as 0 and EOS as 3, both flagged in gx)          n/4 bytes
 //   gx   1 bit/base "not ACGT" (N or EOS)                                             n/8 bytes
 //   gxc  1 bit per 64-base block: block holds any flagged base (L2 resident)          n/512 bytes
-//   sa   the reference's suffix array as written by `biokanga index`: u32 per element; for 5-byte
-//        elements (n >= 4e9) split into a u32 low plane and a u8 high plane           4n (+n) bytes
+//   sa   the reference's suffix array as written by `biokanga index`: u32 per element (sa_lo); for 5-byte elements
+//        (n >= 4e9) the 5-byte elements back to back, exactly as in the file (sa5): one element = one 128-byte line
+//        fetch (a u32 plane + a u8 plane cost two)                                    4n / 5n bytes
 //   pt   k-mer prefix table: pt[x] = number of suffixes whose first-k symbols sort below the ACGT
-//        k-mer x (first base most significant); 4^k+1 entries of u32 (u64 when n >= 2^32)
+//        k-mer x (first base most significant); 4^k+1 entries of u32.  For n >= 2^32 the u32 entries are relative to
+//        their block of 4096 entries, whose absolute starts (u64, 4^k/4096 of them: L2 resident) sit in pt_hi
 //   ent  chromosome table sorted by start offset + a coarse block -> entry lookup table
 #pragma once
 #include <cstdint>
@@ -20,10 +22,11 @@ struct DevIndex {
   const uint64_t* g2;
   const uint64_t* gx;
   const uint32_t* gxc;
-  const uint32_t* sa_lo;
-  const uint8_t* sa_hi;  // nullptr for 4-byte elements
-  const uint32_t* pt32;  // one of pt32 / pt64 is set
-  const uint64_t* pt64;
+  const uint32_t* sa_lo;  // 4-byte elements, or the low plane of borrowed planes
+  const uint8_t* sa_hi;   // high plane of borrowed planes (bkx_open_index_planes below 2^32 symbols), else nullptr
+  const uint8_t* sa5;     // 5-byte elements back to back (8-byte aligned, 16 bytes of slack); set instead of sa_lo
+  const uint32_t* pt32;   // prefix table; relative to pt_hi[x >> kPtBlockShift] when pt_hi is set
+  const uint64_t* pt_hi;
   const uint64_t* ent_start;
   const uint64_t* ent_end;
   const uint32_t* ent_id;
@@ -36,14 +39,26 @@ struct DevIndex {
   int k;
 };
 
+constexpr int kPtBlockShift = 12;   // two-level prefix table: 4096 entries per block
+
 __device__ __forceinline__ uint64_t sa_get(const DevIndex& I, uint64_t i) {
+  if (I.sa5) {   // 40 bits at byte 5i: one aligned 64-bit word, two when the element runs over its end
+    const uint64_t a = i * 5;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(I.sa5) + (a >> 3);
+    const unsigned sh = (unsigned)(a & 7) * 8;
+    uint64_t v = __ldg(w) >> sh;
+    if (sh > 24) v |= __ldg(w + 1) << (64 - sh);
+    return v & 0xffffffffffull;
+  }
   uint64_t v = __ldg(I.sa_lo + i);
   if (I.sa_hi) v |= (uint64_t)__ldg(I.sa_hi + i) << 32;
   return v;
 }
 
 __device__ __forceinline__ uint64_t pt_get(const DevIndex& I, uint64_t x) {
-  return I.pt32 ? (uint64_t)__ldg(I.pt32 + x) : __ldg(I.pt64 + x);
+  uint64_t v = __ldg(I.pt32 + x);
+  if (I.pt_hi) v += __ldg(I.pt_hi + (x >> kPtBlockShift));
+  return v;
 }
 
 // 32 bases of the concatenation starting at base g (little-endian base order).

@@ -97,11 +97,65 @@ __device__ __forceinline__ uint64_t suffix_key(const DevIndex& I, uint64_t i, in
   return key;
 }
 
-template <typename CntT>
-__global__ void kmer_hist_kernel(DevIndex I, int k, CntT* __restrict__ cnt) {
+__global__ void kmer_hist_kernel(DevIndex I, int k, uint32_t* __restrict__ cnt) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < I.n; i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t key = suffix_key(I, i, k);
-    atomicAdd(cnt + key + 1, (CntT)1);
+    atomicAdd(cnt + key + 1, 1u);
+  }
+}
+
+// Two-level table (n >= 2^32): the counts of each block of 4096 entries are summed (pass 1), the block sums are scanned
+// into the absolute block starts pt_hi (CUB), and each block is scanned in place into entries relative to its start
+// (pass 2).  One thread block of 256 threads per table block, 16 entries per thread.
+__global__ void pt_block_sums_kernel(const uint32_t* __restrict__ cnt, uint64_t entries, uint64_t* __restrict__ sums) {
+  __shared__ unsigned long long warp_sum[8];
+  const uint64_t nblk = (entries + (1u << kPtBlockShift) - 1) >> kPtBlockShift;
+  for (uint64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const uint64_t base = b << kPtBlockShift;
+    unsigned long long v = 0;
+    for (int q = 0; q < 16; ++q) {
+      const uint64_t x = base + (uint64_t)q * 256 + threadIdx.x;
+      if (x < entries) v += cnt[x];
+    }
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      for (int w = 0; w < 8; ++w) t += warp_sum[w];
+      sums[b] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void pt_block_scan_kernel(uint32_t* __restrict__ cnt, uint64_t entries) {
+  __shared__ uint32_t part[256];
+  const uint64_t nblk = (entries + (1u << kPtBlockShift) - 1) >> kPtBlockShift;
+  for (uint64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const uint64_t base = (b << kPtBlockShift) + (uint64_t)threadIdx.x * 16;   // 16 consecutive entries per thread
+    uint32_t v[16];
+    uint32_t run = 0;
+    for (int q = 0; q < 16; ++q) {
+      const uint64_t x = base + q;
+      run += x < entries ? cnt[x] : 0u;
+      v[q] = run;   // inclusive within the thread's 16
+    }
+    part[threadIdx.x] = run;
+    __syncthreads();
+    // exclusive scan of the 256 per-thread totals (Hillis-Steele in shared memory)
+    for (int o = 1; o < 256; o <<= 1) {
+      const uint32_t add = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0u;
+      __syncthreads();
+      part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    const uint32_t before = part[threadIdx.x] - run;
+    for (int q = 0; q < 16; ++q) {
+      const uint64_t x = base + q;
+      if (x < entries) cnt[x] = before + v[q];
+    }
+    __syncthreads();
   }
 }
 
@@ -298,40 +352,58 @@ cudaError_t launch_split_sa5(const uint8_t* sa5, uint64_t n, uint32_t* lo, uint8
   return cudaGetLastError();
 }
 
-cudaError_t build_prefix_table(const DevIndex& I, int k, void* table, bool wide, cudaStream_t st) {
-  uint64_t entries = (1ull << (2 * k)) + 1;
-  cudaError_t e;
-  if (wide) {
-    e = cudaMemsetAsync(table, 0, entries * 8, st);
-    if (e != cudaSuccess) return e;
-    kmer_hist_kernel<unsigned long long><<<148 * 16, 256, 0, st>>>(I, k, (unsigned long long*)table);
-  } else {
-    e = cudaMemsetAsync(table, 0, entries * 4, st);
-    if (e != cudaSuccess) return e;
-    kmer_hist_kernel<uint32_t><<<148 * 16, 256, 0, st>>>(I, k, (uint32_t*)table);
-  }
+// pt[x] = number of suffixes whose key sorts below x: a histogram of the keys (at x + 1) and its inclusive prefix sum.
+// block_starts == nullptr: one u32 sum over the whole table (n < 2^32).  Otherwise the two-level form described at
+// pt_block_sums_kernel: table entries relative to their block, block_starts[b] = absolute value before block b.
+cudaError_t build_prefix_table(const DevIndex& I, int k, uint32_t* table, uint64_t* block_starts, cudaStream_t st) {
+  const uint64_t entries = (1ull << (2 * k)) + 1;
+  cudaError_t e = cudaMemsetAsync(table, 0, entries * 4, st);
+  if (e != cudaSuccess) return e;
+  kmer_hist_kernel<<<148 * 16, 256, 0, st>>>(I, k, table);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
-  if (wide) {
-    unsigned long long* t = (unsigned long long*)table;
-    e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, t, t, (long long)entries, st);
+  if (!block_starts) {
+    e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, table, table, (long long)entries, st);
     if (e != cudaSuccess) return e;
     e = cudaMalloc(&tmp, tmp_bytes);
     if (e != cudaSuccess) return e;
-    e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, t, t, (long long)entries, st);
+    e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, table, table, (long long)entries, st);
   } else {
-    uint32_t* t = (uint32_t*)table;
-    e = cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, t, t, (long long)entries, st);
+    const uint64_t nblk = (entries + (1u << kPtBlockShift) - 1) >> kPtBlockShift;
+    const int grid = (int)std::min<uint64_t>(nblk, 148 * 16);
+    pt_block_sums_kernel<<<grid, 256, 0, st>>>(table, entries, block_starts);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    unsigned long long* bs = (unsigned long long*)block_starts;
+    e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, bs, bs, (long long)nblk, st);
     if (e != cudaSuccess) return e;
     e = cudaMalloc(&tmp, tmp_bytes);
     if (e != cudaSuccess) return e;
-    e = cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, t, t, (long long)entries, st);
+    e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, bs, bs, (long long)nblk, st);
+    if (e == cudaSuccess) {
+      pt_block_scan_kernel<<<grid, 256, 0, st>>>(table, entries);
+      e = cudaGetLastError();
+    }
   }
   cudaError_t e2 = cudaStreamSynchronize(st);
   cudaFree(tmp);
   return e != cudaSuccess ? e : e2;
+}
+
+// borrowed planes -> 5-byte elements back to back
+__global__ void merge_sa5_kernel(const uint32_t* __restrict__ lo, const uint8_t* __restrict__ hi, uint64_t n, uint8_t* __restrict__ sa5) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = lo[i];
+    uint8_t* p = sa5 + i * 5;
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+    p[4] = hi ? hi[i] : (uint8_t)0;
+  }
+}
+cudaError_t launch_merge_sa5(const uint32_t* lo, const uint8_t* hi, uint64_t n, uint8_t* sa5, cudaStream_t st) {
+  merge_sa5_kernel<<<148 * 8, 256, 0, st>>>(lo, hi, n, sa5);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -920,7 +992,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
             const int c1 = ci1 <= K ? ci1 * delta : last_ofs;
             uint64_t key1 = rev2(fl_word(f, s1, c1)) >> (64 - 2 * k);
             if (CL < k) { const int sh1 = 2 * (k - CL); key1 = (key1 >> sh1) << sh1; }
-            const void* pa = I.pt32 ? (const void*)(I.pt32 + key1) : (const void*)(I.pt64 + key1);
+            const void* pa = (const void*)(I.pt32 + key1);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
           }
         }

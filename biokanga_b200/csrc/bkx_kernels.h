@@ -24,7 +24,8 @@ cudaError_t launch_fixed_offsets(uint64_t* offs, uint32_t n_reads, uint32_t len,
 cudaError_t launch_len_offsets(const uint16_t* lens, uint32_t n_reads, uint64_t* offs, void* tmp, size_t* tmp_bytes, cudaStream_t st);
 cudaError_t launch_compact_results(const bkx_read_result* in, uint32_t n, bkx_read_result16* out, cudaStream_t st);
 cudaError_t launch_split_sa5(const uint8_t* sa5, uint64_t n, uint32_t* lo, uint8_t* hi, cudaStream_t st);
-cudaError_t build_prefix_table(const DevIndex& I, int k, void* table, bool wide, cudaStream_t st);
+cudaError_t build_prefix_table(const DevIndex& I, int k, uint32_t* table, uint64_t* block_starts, cudaStream_t st);
+cudaError_t launch_merge_sa5(const uint32_t* lo, const uint8_t* hi, uint64_t n, uint8_t* sa5, cudaStream_t st);
 
 size_t align_smem_bytes(int W);
 int align_blocks_per_sm(int W);

@@ -115,7 +115,14 @@ __global__ void __launch_bounds__(kThreads) sl_gather(const uint8_t* __restrict_
   }
 }
 
+// lo == nullptr: `hi` is an array of 5-byte elements back to back (the layout of the .sfx file and of DevIndex::sa5)
 __device__ __forceinline__ void put_sa(uint32_t* __restrict__ lo, uint8_t* __restrict__ hi, uint64_t at, uint64_t pos) {
+  if (!lo) {
+    uint8_t* p = hi + at * 5;
+    p[0] = (uint8_t)pos; p[1] = (uint8_t)(pos >> 8); p[2] = (uint8_t)(pos >> 16); p[3] = (uint8_t)(pos >> 24);
+    p[4] = (uint8_t)(pos >> 32);
+    return;
+  }
   lo[at] = (uint32_t)pos;
   if (hi) hi[at] = (uint8_t)(pos >> 32);
 }
@@ -220,12 +227,23 @@ struct Carver {  // bump allocation inside the one arena
 
 }  // namespace
 
+static int build_large(const uint8_t* d_seq, uint64_t n, uint32_t* d_sa_lo, uint8_t* d_sa_hi, int device, uint64_t max_batch);
+
 extern "C" int bkx_build_suffix_array_planes(const uint8_t* d_seq, uint64_t n, uint32_t* d_sa_lo, uint8_t* d_sa_hi,
                                              int device, uint64_t max_batch) {
   if (!d_seq || !d_sa_lo) return bkx_fail(BKX_ERR_PARAM, "null argument");
+  if (n > 0xffffffffull && !d_sa_hi) return bkx_fail(BKX_ERR_PARAM, "more than 2^32 symbols need the high plane");
+  return build_large(d_seq, n, d_sa_lo, d_sa_hi, device, max_batch);
+}
+
+extern "C" int bkx_build_suffix_array_packed5(const uint8_t* d_seq, uint64_t n, uint8_t* d_sa5, int device, uint64_t max_batch) {
+  if (!d_seq || !d_sa5) return bkx_fail(BKX_ERR_PARAM, "null argument");
+  return build_large(d_seq, n, nullptr, d_sa5, device, max_batch);
+}
+
+static int build_large(const uint8_t* d_seq, uint64_t n, uint32_t* d_sa_lo, uint8_t* d_sa_hi, int device, uint64_t max_batch) {
   if (n < 2) return bkx_fail(BKX_ERR_PARAM, "sequence too short");
   if (n >= (1ull << 40)) return bkx_fail(BKX_ERR_PARAM, "sequence longer than 2^40 symbols");
-  if (n > 0xffffffffull && !d_sa_hi) return bkx_fail(BKX_ERR_PARAM, "more than 2^32 symbols need the high plane");
   int rc = BKX_OK;
   cudaStream_t st = nullptr;
   unsigned long long* d_hist = nullptr;

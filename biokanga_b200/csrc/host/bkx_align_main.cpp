@@ -34,7 +34,9 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <memory>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include <glob.h>
@@ -67,13 +69,32 @@ static void diag(const char* fmt, ...) {  // CDiagnostics::DiagOut format: "[Mon
   if (g_log) { fputs(line, g_log); fflush(g_log); }
 }
 
+// Buffers of several GB (file text, read arena) must not be value-initialised by one thread: resize() leaves new
+// elements untouched, the threads that fill them take the page faults.
+template <class T>
+struct NoInit : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInit<U>; };
+  template <class U, class... A>
+  void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T> using Buf = std::vector<T, NoInit<T>>;
+using ResVec = Buf<bkx_read_result>;
+
 // ---- read ingest ---------------------------------------------------------------------------------
 struct Reads {
-  std::vector<uint8_t> packed;    // the same bases 4-bit packed (what crosses PCIe): base i in nibble i & 1 of byte i / 2
-  std::vector<uint8_t> bases;     // 1 byte/base, etSeqBase code in the low 3 bits
-  std::vector<uint64_t> offs{0};
-  std::vector<char> names;        // NUL-terminated descriptors, back to back
-  std::vector<uint64_t> name_ofs;
+  // what crosses PCIe (the library's compact host interface): the bases 2 bits each (base i at bits [2(i%4), +2) of byte i/4,
+  // non-ACGT bases as 0 and listed in exc_*), read lengths (empty when all reads are equally long)
+  Buf<uint8_t> packed2;
+  std::vector<uint64_t> exc_pos;
+  std::vector<uint8_t> exc_code;
+  Buf<uint16_t> lens;
+  uint32_t fixed_len = 0;
+  Buf<uint8_t> bases;             // 1 byte/base, etSeqBase code in the low 3 bits
+  Buf<uint64_t> offs = Buf<uint64_t>(1, 0);
+  Buf<char> names;                // NUL-terminated descriptors, back to back
+  Buf<uint64_t> name_ofs;
   uint32_t n() const { return (uint32_t)(offs.size() - 1); }
   const char* name(uint32_t i) const { return names.data() + name_ofs[i]; }
   int len(uint32_t i) const { return (int)(offs[i + 1] - offs[i]); }
@@ -141,7 +162,8 @@ struct RawRec {        // one FASTA / FASTQ record as pointers into the file tex
   uint32_t name_n, len, qlen;
 };
 
-static bool slurp(const std::string& path, std::vector<char>& text, unsigned threads) {
+template <class Text>
+static bool slurp(const std::string& path, Text& text, unsigned threads) {
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) return false;
   unsigned char magic[2] = {0, 0};
@@ -260,7 +282,7 @@ static bool parse_records(const char* b, const char* e, const char* end, bool fa
   return true;
 }
 
-static bool parse_file(const std::string& path, unsigned threads, std::vector<char>& text, std::vector<RawRec>& recs) {
+static bool parse_file(const std::string& path, unsigned threads, Buf<char>& text, std::vector<RawRec>& recs) {
   if (!slurp(path, text, threads)) return false;
   const char* b = text.data();
   const char* end = b + text.size();
@@ -324,7 +346,7 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
   const unsigned T = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   diag("Loading reads from file...");
   for (size_t fi = 0; fi < o.in.size(); ++fi) {
-    std::vector<char> text[2];
+    Buf<char> text[2];
     std::vector<RawRec> recs[2];
     bool opened[2] = {true, true};
     {
@@ -412,20 +434,46 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
     if (under) diag("Load: total of %d under length sequences sloughed from file '%s'", under, o.in[fi].c_str());
     if (over) diag("Load: total of %d over length sequences sloughed from file '%s'", over, o.in[fi].c_str());
   }
-  {  // nibble-packed copy for the H2D stream; threads own disjoint byte ranges of the packed array
-    const size_t nb = R.bases.size(), np = (nb + 1) / 2;
-    R.packed.resize(np);
+  {  // the 2-bit stream + exception list + lengths for the H2D copies; threads own disjoint byte ranges of the stream
+    const size_t nb = R.bases.size(), np = (nb + 3) / 4;
+    R.packed2.resize(np + 16);
+    std::vector<std::vector<uint64_t>> epos(T);
+    std::vector<std::vector<uint8_t>> ecode(T);
+    const uint32_t nreads = R.n();
+    R.lens.resize(nreads);
+    std::vector<uint8_t> uniform(T, 1);
+    const uint32_t len0 = nreads ? (uint32_t)R.len(0) : 0;
     std::vector<std::thread> th;
     for (unsigned t = 0; t < T; ++t)
       th.emplace_back([&, t]() {
         size_t b = np * t / T, e = np * (t + 1) / T;
+        if (t + 1 == T) e = np + 16;   // the slack the device copies may read
         const uint8_t* src = R.bases.data();
         for (size_t i = b; i < e; ++i) {
-          uint8_t lo = src[2 * i] & 0x0f, hi = 2 * i + 1 < nb ? (uint8_t)(src[2 * i + 1] & 0x0f) : 0;
-          R.packed[i] = (uint8_t)(lo | (hi << 4));
+          unsigned v = 0;
+          for (unsigned j = 0; j < 4; ++j) {
+            const size_t q = 4 * i + j;
+            if (q >= nb) break;
+            const unsigned c = src[q] & 7u;
+            if (c > 3) { epos[t].push_back(q); ecode[t].push_back((uint8_t)c); } else v |= c << (2 * j);
+          }
+          R.packed2[i] = (uint8_t)v;
+        }
+        const uint32_t rb = (uint32_t)((uint64_t)nreads * t / T), re = (uint32_t)((uint64_t)nreads * (t + 1) / T);
+        for (uint32_t r = rb; r < re; ++r) {
+          const uint32_t l = (uint32_t)R.len(r);
+          R.lens[r] = (uint16_t)l;
+          if (l != len0) uniform[t] = 0;
         }
       });
     for (auto& x : th) x.join();
+    for (unsigned t = 0; t < T; ++t) {
+      R.exc_pos.insert(R.exc_pos.end(), epos[t].begin(), epos[t].end());
+      R.exc_code.insert(R.exc_code.end(), ecode[t].begin(), ecode[t].end());
+    }
+    bool all_same = nreads > 0;
+    for (unsigned t = 0; t < T; ++t) all_same = all_same && uniform[t];
+    R.fixed_len = all_same ? len0 : 0;
   }
   return 0;
 }
@@ -679,6 +727,17 @@ static void emit_rows(OutBuf& ob, uint32_t n, unsigned threads, F&& row) {
   const uint32_t chunk = 1u << 16;
   if (threads < 1) threads = 1;
   std::vector<std::string> bufs(threads);
+  // plain files: every worker writes its own rows at their final offset (pwrite), so that formatting AND writing run on
+  // all threads; gzip streams are sequential by nature
+  int fd = -1;
+  off_t file_ofs = 0;
+  if (ob.f && !ob.gz) {
+    ob.flush();
+    fflush(ob.f);
+    fd = fileno(ob.f);
+    file_ofs = ftello(ob.f);
+    if (file_ofs < 0) fd = -1;
+  }
   for (uint64_t base = 0; base < n; base += (uint64_t)chunk * threads) {
     std::vector<std::thread> th;
     unsigned used = 0;
@@ -694,8 +753,30 @@ static void emit_rows(OutBuf& ob, uint32_t n, unsigned threads, F&& row) {
       });
     }
     for (auto& x : th) x.join();
-    for (unsigned t = 0; t < used; ++t) ob.write(bufs[t]);
+    if (fd < 0) {
+      for (unsigned t = 0; t < used; ++t) ob.write(bufs[t]);
+      continue;
+    }
+    std::vector<off_t> at(used);
+    for (unsigned t = 0; t < used; ++t) { at[t] = file_ofs; file_ofs += (off_t)bufs[t].size(); }
+    std::vector<char> ok(used, 1);
+    th.clear();
+    for (unsigned t = 0; t < used; ++t)
+      th.emplace_back([&bufs, &at, &ok, fd, t]() {
+        const char* p = bufs[t].data();
+        size_t left = bufs[t].size();
+        off_t o = at[t];
+        while (left) {
+          ssize_t w = pwrite(fd, p, left, o);
+          if (w <= 0) { ok[t] = 0; return; }
+          p += w; left -= (size_t)w; o += w;
+        }
+      });
+    for (auto& x : th) x.join();
+    for (unsigned t = 0; t < used; ++t) if (!ok[t]) { fd = -2; break; }
+    if (fd == -2) { diag("Fatal: write to the result file failed"); exit(1); }
   }
+  if (fd >= 0) fseeko(ob.f, file_ofs, SEEK_SET);
 }
 
 // ---- BAM (BGZF) + BAI, as CSAMfile writes them (libbiokanga/SAMfile.cpp:1383-1660, 1839-2030, 2286-2556; bgzf.cpp) ----
@@ -980,7 +1061,7 @@ static int load_constraints(const std::string& path, const std::vector<bkx_entry
 struct Records {
   const Opts& o;
   Reads& R;                                          // -6 rewrites read bases
-  std::vector<bkx_read_result>& res;                 // one per record: per read, or per reported locus under -r5
+  ResVec& res;                 // one per record: per read, or per reported locus under -r5
   const std::vector<uint32_t>& src;                  // record -> read (empty: identity)
   const std::vector<bkx_entry>& ents;                // [1 .. num_entries]
   const std::vector<std::vector<uint8_t>>& genome;   // host copy of the chromosomes (1 byte/base), filled when a pass or writer needs it
@@ -1810,13 +1891,16 @@ int main(int argc, char** argv) {
   diag("Now aligning with minimum core size of %dbp...\n", P.min_core_len);
 
   // ---- align: contiguous, even-sized read ranges, one host thread per GPU (reads shard with no exchange)
-  std::vector<bkx_read_result> res(n);
-  // page-lock the read arena and the record array: H2D / D2H then stream asynchronously, double buffered
-  bool pinned = bkx_pin_host(R.packed.data(), R.packed.size()) >= 0 && bkx_pin_host(R.offs.data(), R.offs.size() * 8) >= 0 &&
-                bkx_pin_host(res.data(), res.size() * sizeof(bkx_read_result)) >= 0;
-  if (!pinned) diag("Note: unable to page-lock host buffers (%s); continuing with pageable copies", bkx_last_error());
   const bool all_loci = o.ml_mode == BKX_ML_ALL;   // -r5: every locus of a read becomes a record of its own
   const bool clustered = o.ml_mode == BKX_ML_UNIQ || o.ml_mode == BKX_ML_MULTI;   // -r3 / -r4: one locus by clustering
+  const bool compact = !(all_loci || clustered);   // the compact host interface: 2 bits per base in, 16-byte records out
+  ResVec res(n);            // filled below (expanded from the 16-byte records, or written by the multi-loci call)
+  Buf<bkx_read_result16> res16(compact ? n : 0);
+  // page-lock what crosses PCIe: H2D / D2H then stream asynchronously, double buffered
+  bool pinned = true;
+  if (compact) pinned = bkx_pin_host(R.packed2.data(), R.packed2.size()) >= 0 && bkx_pin_host(res16.data(), res16.size() * sizeof(bkx_read_result16)) >= 0;
+  else pinned = bkx_pin_host(R.bases.data(), R.bases.size()) >= 0 && bkx_pin_host(res.data(), res.size() * sizeof(bkx_read_result)) >= 0;
+  if (!pinned) diag("Note: unable to page-lock host buffers (%s); continuing with pageable copies", bkx_last_error());
   std::vector<bkx_multi_hit> multi;
   if (all_loci || clustered) multi.resize((size_t)n * (size_t)o.max_ml);
   // paired ends: aligned and paired in one pass over the data (each GPU pairs its own contiguous, even-sized range)
@@ -1844,16 +1928,23 @@ int main(int argc, char** argv) {
       memset(&st[(size_t)g], 0, sizeof(bkx_align_stats));
       th.emplace_back([&, g, b, e]() {
         if (e > b) {
+          // this GPU's share of the stream: its first base and its slice of the (ascending) exception list
+          const uint64_t o_b = R.offs[b], o_e = R.offs[e];
+          const size_t x0 = (size_t)(std::lower_bound(R.exc_pos.begin(), R.exc_pos.end(), o_b) - R.exc_pos.begin());
+          const size_t x1 = (size_t)(std::lower_bound(R.exc_pos.begin(), R.exc_pos.end(), o_e) - R.exc_pos.begin());
+          const uint16_t* lens = R.fixed_len ? nullptr : R.lens.data() + b;
           if (o.pe_mode)
-            rcs[(size_t)g] = bkx_align_pairs_packed4(idx[(size_t)g], &P, &PE, R.packed.data(), R.offs.data() + b, (e - b) / 2,
-                                                     res.data() + b, &st[(size_t)g], &pst[(size_t)g],
+            rcs[(size_t)g] = bkx_align_pairs_packed2(idx[(size_t)g], &P, &PE, R.packed2.data(), o_b, lens, R.fixed_len,
+                                                     R.exc_pos.data() + x0, R.exc_code.data() + x0, x1 - x0, (e - b) / 2,
+                                                     res16.data() + b, &st[(size_t)g], &pst[(size_t)g],
                                                      len_dist[(size_t)g].empty() ? nullptr : len_dist[(size_t)g].data());
-          else if (all_loci || clustered)
+          else if (!compact)
             rcs[(size_t)g] = bkx_align_reads_multi(idx[(size_t)g], &P, R.bases.data(), R.offs.data() + b, e - b, res.data() + b,
                                                    multi.data() + (size_t)b * (size_t)o.max_ml, &st[(size_t)g]);
           else
-            rcs[(size_t)g] = bkx_align_reads_packed4(idx[(size_t)g], &P, R.packed.data(), R.offs.data() + b, e - b, res.data() + b,
-                                                     &st[(size_t)g]);
+            rcs[(size_t)g] = bkx_align_reads_packed2(idx[(size_t)g], &P, R.packed2.data(), o_b, lens, R.fixed_len,
+                                                     R.exc_pos.data() + x0, R.exc_code.data() + x0, x1 - x0, e - b,
+                                                     res16.data() + b, &st[(size_t)g]);
           if (rcs[(size_t)g] < 0) errs[(size_t)g] = bkx_last_error();
         }
       });
@@ -1868,7 +1959,19 @@ int main(int argc, char** argv) {
     const uint64_t* s = (const uint64_t*)&st[(size_t)g];
     for (size_t k = 0; k < sizeof(S) / 8; ++k) d[k] += s[k];
   }
-  bkx_unpin_host(R.packed.data()); bkx_unpin_host(R.offs.data()); bkx_unpin_host(res.data());
+  if (compact) { bkx_unpin_host(R.packed2.data()); bkx_unpin_host(res16.data()); }
+  else { bkx_unpin_host(R.bases.data()); bkx_unpin_host(res.data()); }
+  if (compact) {   // 16-byte records -> the 32-byte form the passes and writers work on, by all host threads
+    const unsigned T = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+      th.emplace_back([&, t]() {
+        const uint32_t b = (uint32_t)((uint64_t)n * t / T), e = (uint32_t)((uint64_t)n * (t + 1) / T);
+        if (e > b) bkx_expand_results16(res16.data() + b, e - b, R.fixed_len ? nullptr : R.lens.data() + b, R.fixed_len, res.data() + b);
+      });
+    for (auto& x : th) x.join();
+    Buf<bkx_read_result16>().swap(res16);
+  }
   diag("Alignment of %u from %u loaded completed", n, n);
 
   // -O: m_MultiHitDist (Aligner.cpp:9364, 9521) -- reads whose search ended eHRhits, by their number of equally good loci;
@@ -1917,7 +2020,7 @@ int main(int argc, char** argv) {
   if (all_loci) {
     diag("Treating accepted %d multialigned reads as uniquely aligned %d source reads in subsequent processing",
          (int)S.tot_accepted_multi, (int)(S.tot_loci_aligned - S.tot_accepted_unique));
-    std::vector<bkx_read_result> rec;
+    ResVec rec;
     rec.reserve((size_t)S.tot_loci_aligned + 16);
     for (uint32_t i = 0; i < n; ++i) {
       const bkx_read_result& r = res[i];
@@ -2045,7 +2148,7 @@ int main(int argc, char** argv) {
   // ---- order (SortReadHits(eRSMHitMatch): on the alignment as reported, i.e. after trimming)
   std::vector<uint32_t> order(nrec);
   {
-    std::vector<bkx_read_result> keyed;
+    ResVec keyed;
     if (!trim_l.empty()) {
       keyed = res;
       for (uint32_t i = 0; i < nrec; ++i) { keyed[i].match_loci = rc.adj_start(i); keyed[i].match_len = (uint16_t)rc.adj_len(i); }

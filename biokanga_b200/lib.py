@@ -27,7 +27,7 @@ EXPORTS = [
     "bkx_pack_bases4", "bkx_align_reads_multi", "bkx_align_pairs", "bkx_align_pairs_packed4",
     "bkx_assign_multi_matches", "bkx_self_check", "bkx_debug_reset", "bkx_set_chrom_filter",
     "bkx_align_reads_packed2", "bkx_align_pairs_packed2", "bkx_pack_bases2", "bkx_expand_results16",
-    "bkx_align_reads_device_packed2",
+    "bkx_align_reads_device_packed2", "bkx_open_index_packed5", "bkx_build_suffix_array_packed5",
 ]
 
 
@@ -65,12 +65,15 @@ def lib():
     L.bkx_open_index_dev.argtypes = [vp, u64, vp, u32, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_open_index_planes.argtypes = [vp, u64, vp, vp, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_build_suffix_array_planes.argtypes = [vp, u64, vp, vp, i32, u64]
+    L.bkx_build_suffix_array_packed5.argtypes = [vp, u64, vp, i32, u64]
+    L.bkx_open_index_packed5.argtypes = [vp, u64, vp, vp, u32, C.c_char_p, i32, i32, C.POINTER(vp)]
     L.bkx_sort_hits.argtypes = [vp, u32, vp, i32]
     L.bkx_align_reads_packed4.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, C.POINTER(abi.AlignStats)]
     L.bkx_pack_bases4.argtypes = [vp, u64, vp]
-    L.bkx_align_reads_packed2.argtypes = [vp, C.POINTER(abi.AlignParams), vp, vp, u32, vp, vp, u64, u32, vp, C.POINTER(abi.AlignStats)]
-    L.bkx_align_pairs_packed2.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, vp, u32, vp, vp, u64, u32, vp,
-                                          C.POINTER(abi.AlignStats), C.POINTER(abi.PEStats), vp]
+    L.bkx_align_reads_packed2.argtypes = [vp, C.POINTER(abi.AlignParams), vp, u64, vp, u32, vp, vp, u64, u32, vp,
+                                          C.POINTER(abi.AlignStats)]
+    L.bkx_align_pairs_packed2.argtypes = [vp, C.POINTER(abi.AlignParams), C.POINTER(abi.PEParams), vp, u64, vp, u32, vp, vp, u64, u32,
+                                          vp, C.POINTER(abi.AlignStats), C.POINTER(abi.PEStats), vp]
     L.bkx_pack_bases2.argtypes = [vp, u64, vp, vp, vp, u64]
     L.bkx_pack_bases2.restype = C.c_int64
     L.bkx_expand_results16.argtypes = [vp, u32, vp, u32, vp]
@@ -127,6 +130,11 @@ def build_suffix_array_device(d_seq_ptr, concat_len, d_sa_ptr, device=0):
 def build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr=None, device=0, max_batch=0):
     """Bounded-memory builder for any size (the one for >= 4e9 symbols): u32 low plane + u8 high plane out."""
     check(lib().bkx_build_suffix_array_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, device, max_batch))
+
+
+def build_suffix_array_packed5(d_seq_ptr, concat_len, d_sa5_ptr, device=0, max_batch=0):
+    """Same builder, 5-byte elements back to back out (allocate concat_len * 5 + 16 bytes)."""
+    check(lib().bkx_build_suffix_array_packed5(d_seq_ptr, concat_len, d_sa5_ptr, device, max_batch))
 
 
 def pack_bases4(bases):
@@ -223,6 +231,15 @@ class Index:
         h = C.c_void_p()
         check(lib().bkx_open_index_planes(d_seq_ptr, concat_len, d_sa_lo_ptr, d_sa_hi_ptr, entries.ctypes.data,
                                           len(entries), name.encode(), device, prefix_k, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_packed5(cls, d_seq_ptr, concat_len, d_sa5_ptr, entries, name="bkx", device=0, prefix_k=0):
+        """Index over 5-byte suffix elements already on the device (borrowed; 8-byte aligned, 16 bytes of slack)."""
+        entries = np.ascontiguousarray(entries, dtype=abi.ENTRY_DTYPE)
+        h = C.c_void_p()
+        check(lib().bkx_open_index_packed5(d_seq_ptr, concat_len, d_sa5_ptr, entries.ctypes.data, len(entries), name.encode(),
+                                           device, prefix_k, C.byref(h)))
         return cls(h)
 
     def debug_reset(self, what):
@@ -330,34 +347,39 @@ class Index:
         return out, st
 
     def align_packed2_ptr(self, params, packed2_ptr, lens_ptr, fixed_len, exc_pos_ptr, exc_code_ptr, n_exc, n_reads, out16_ptr,
-                          stats=None, pe=None, pe_stats=None, len_dist_ptr=None):
+                          stats=None, pe=None, pe_stats=None, len_dist_ptr=None, first_base=0):
         """The compact host interface on raw host pointers: 2 bits per base in, 16-byte records out (n_reads = reads, also
         for paired ends)."""
         st = C.byref(stats) if stats is not None else None
         if pe is None:
-            check(lib().bkx_align_reads_packed2(self._h, C.byref(params), packed2_ptr, lens_ptr, fixed_len, exc_pos_ptr,
+            check(lib().bkx_align_reads_packed2(self._h, C.byref(params), packed2_ptr, first_base, lens_ptr, fixed_len, exc_pos_ptr,
                                                 exc_code_ptr, n_exc, n_reads, out16_ptr, st))
         else:
-            check(lib().bkx_align_pairs_packed2(self._h, C.byref(params), C.byref(pe), packed2_ptr, lens_ptr, fixed_len,
+            check(lib().bkx_align_pairs_packed2(self._h, C.byref(params), C.byref(pe), packed2_ptr, first_base, lens_ptr, fixed_len,
                                                 exc_pos_ptr, exc_code_ptr, n_exc, n_reads // 2, out16_ptr, st,
                                                 C.byref(pe_stats) if pe_stats is not None else None, len_dist_ptr))
 
-    def align_packed2(self, params, bases, offsets, pe=None, len_dist=None, fixed=None):
+    def align_packed2(self, params, bases, offsets, pe=None, len_dist=None, fixed=None, first_base=0):
         """Packs `bases` / `offsets` (one byte per base) into the compact layout, aligns, expands the records again:
-        (records, stats[, PE stats]).  fixed=None picks the fixed-length form when every read has the same length."""
+        (records, stats[, PE stats]).  fixed=None picks the fixed-length form when every read has the same length;
+        first_base > 0 puts that many filler bases in front of the stream (a shard of a longer stream)."""
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
         lens = np.diff(offsets).astype(np.uint16)
         o0 = int(offsets[0])
-        packed, pos, code = pack_bases2(bases[o0:int(offsets[-1])])
+        packed, pos, code = pack_bases2(np.concatenate([np.full(first_base, 4, dtype=np.uint8), bases[o0:int(offsets[-1])]]))
+        if first_base:   # the filler (Ns) belongs to some other shard: its exceptions are not this call's
+            keep = pos >= first_base
+            pos, code = pos[keep].copy(), code[keep].copy()
         if fixed is None:
             fixed = n > 0 and bool((lens == lens[0]).all())
         out16 = np.zeros(n, dtype=abi.RESULT16_DTYPE)
         st, ps = abi.AlignStats(), abi.PEStats()
         self.align_packed2_ptr(params, packed.ctypes.data, None if fixed else lens.ctypes.data, int(lens[0]) if fixed else 0,
                                pos.ctypes.data if len(pos) else None, code.ctypes.data if len(code) else None, len(pos), n,
-                               out16.ctypes.data, st, pe, ps, len_dist.ctypes.data if len_dist is not None else None)
+                               out16.ctypes.data, st, pe, ps, len_dist.ctypes.data if len_dist is not None else None,
+                               first_base=first_base)
         res = expand_results16(out16, None if fixed else lens, int(lens[0]) if fixed else 0)
         return (res, st) if pe is None else (res, st, ps)
 

@@ -212,12 +212,18 @@ int bkx_open_index_mem(const uint8_t* seq, uint64_t concat_len, const void* sa, 
 int bkx_open_index_dev(const uint8_t* d_seq, uint64_t concat_len, const void* d_sa, uint32_t sfx_el_size,
                        const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
                        int prefix_k, bkx_index** out);
-/* Same, from a suffix array already split into the two device planes DevIndex reads (u32 low words and, for
- * 5-byte elements, u8 high bytes; d_sa_hi may be NULL below 4e9 symbols).  The planes are BORROWED, not copied --
- * at 14 G symbols they are 70 GB -- and must outlive the index; bkx_close_index leaves them alone. */
+/* Same, from a suffix array split into two device planes (u32 low words and, for 5-byte elements, u8 high bytes; d_sa_hi
+ * may be NULL below 4e9 symbols).  Without a high plane the low plane is BORROWED, not copied, and must outlive the index
+ * (bkx_close_index leaves it alone); with one, the planes are merged into an array of 5-byte elements owned by the index
+ * -- at wheat scale use bkx_build_suffix_array_packed5 + bkx_open_index_packed5, which need no second copy. */
 int bkx_open_index_planes(const uint8_t* d_seq, uint64_t concat_len, const uint32_t* d_sa_lo, const uint8_t* d_sa_hi,
                           const bkx_entry* entries, uint32_t num_entries, const char* dataset_name, int device,
                           int prefix_k, bkx_index** out);
+/* Same, from 5-byte suffix elements back to back on the device (the element layout of the .sfx file; what
+ * bkx_build_suffix_array_packed5 writes): the layout the search reads for indexes of >= 4e9 symbols -- one memory fetch per
+ * element.  d_sa5 must start on an 8-byte boundary and be followed by 16 readable bytes; it is BORROWED like the planes. */
+int bkx_open_index_packed5(const uint8_t* d_seq, uint64_t concat_len, const uint8_t* d_sa5, const bkx_entry* entries,
+                           uint32_t num_entries, const char* dataset_name, int device, int prefix_k, bkx_index** out);
 /* Every bkx_open_index* ends with a device self-check: each suffix-array element must lie inside the prefix-table bucket
  * of the suffix it names (ties genome words, table and suffix array together; BKX_NO_VERIFY=1 skips it).  This re-runs
  * it on a live index and returns the number of elements that fail (0 = sound), < 0 on error. */
@@ -268,14 +274,17 @@ int bkx_pack_bases4(const uint8_t* bases, uint64_t n_bases, uint8_t* packed);
  *   packed2   base i of the concatenated reads at bits [2(i%4), +2) of byte i/4, codes A0 C1 G2 T3; reads back to back at
  *             base granularity.  Bases that are not A C G T are stored as 0 and listed in
  *   exc_pos / exc_code   (n_exc entries, exc_pos ascending): position in the concatenation and etSeqBase code (4 = N, ...).
+ *   first_base  position in the stream of the first base of read 0 (a caller that shards one stream over several GPUs
+ *             hands each its reads' lengths and the position they start at; exc_pos are stream positions too, the first
+ *             entry at or after first_base).
  *   lens      read lengths (n_reads u16; cMaxSeqLen is 2000), or NULL when every read has fixed_len bases.
  *   out       n_reads 16-byte records.
  * Same search, same results as bkx_align_reads (the device expands the reads to the layout the kernels take).
  * bkx_pack_bases2 packs n_bases one-byte codes (low 3 bits) that way: packed2 needs (n_bases + 3) / 4 bytes (+ 8 bytes of
  * slack so that device copies may run in words); returns the number of exceptions, or BKX_ERR_MEM if exc_cap is too small. */
-int bkx_align_reads_packed2(bkx_index* idx, const bkx_align_params* params, const uint8_t* packed2, const uint16_t* lens,
-                            uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code, uint64_t n_exc,
-                            uint32_t n_reads, bkx_read_result16* out, bkx_align_stats* stats);
+int bkx_align_reads_packed2(bkx_index* idx, const bkx_align_params* params, const uint8_t* packed2, uint64_t first_base,
+                            const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code,
+                            uint64_t n_exc, uint32_t n_reads, bkx_read_result16* out, bkx_align_stats* stats);
 int64_t bkx_pack_bases2(const uint8_t* bases, uint64_t n_bases, uint8_t* packed2, uint64_t* exc_pos, uint8_t* exc_code,
                         uint64_t exc_cap);
 /* 16-byte records -> 32-byte records (seeds / cands 0); lens / fixed_len as above. */
@@ -337,9 +346,9 @@ int bkx_align_pairs_packed4(bkx_index* idx, const bkx_align_params* params, cons
 
 /* Paired ends through the compact host interface (see bkx_align_reads_packed2): reads 2i / 2i+1 are PE1 / PE2 of pair i. */
 int bkx_align_pairs_packed2(bkx_index* idx, const bkx_align_params* params, const bkx_pe_params* pe, const uint8_t* packed2,
-                            const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code,
-                            uint64_t n_exc, uint32_t n_pairs, bkx_read_result16* out, bkx_align_stats* stats,
-                            bkx_pe_stats* pe_stats, uint32_t* len_dist);
+                            uint64_t first_base, const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos,
+                            const uint8_t* exc_code, uint64_t n_exc, uint32_t n_pairs, bkx_read_result16* out,
+                            bkx_align_stats* stats, bkx_pe_stats* pe_stats, uint32_t* len_dist);
 
 /* ---- -r3 / -r4: one locus for reads that hit several, by clustering with the loci of other reads.  Replaces
  * CAligner::AssignMultiMatches + ProcAssignMultiMatches (Aligner.cpp:5108-5270, 4961-5105).  Host code (no device
@@ -376,6 +385,8 @@ int bkx_build_suffix_array_device(const uint8_t* d_seq, uint64_t concat_len, uin
  * (d_sa_hi may be NULL when concat_len <= 2^32).  max_batch = 0 sizes the batches from free device memory. */
 int bkx_build_suffix_array_planes(const uint8_t* d_seq, uint64_t concat_len, uint32_t* d_sa_lo, uint8_t* d_sa_hi,
                                   int device, uint64_t max_batch);
+/* Same builder, output as 5-byte elements back to back (concat_len * 5 bytes; allocate 16 more for bkx_open_index_packed5). */
+int bkx_build_suffix_array_packed5(const uint8_t* d_seq, uint64_t concat_len, uint8_t* d_sa5, int device, uint64_t max_batch);
 /* Write host-resident sequence + suffix array as a version-5 .sfx the reference's `biokanga align` loads. */
 int bkx_write_sfx(const char* path, const uint8_t* seq, uint64_t concat_len, const void* sa, uint32_t sfx_el_size,
                   const bkx_entry* entries, uint32_t num_entries, const char* dataset_name);

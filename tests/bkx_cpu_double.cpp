@@ -81,6 +81,71 @@ int bkx_align_pairs_packed4(bkx_index* x, const bkx_align_params* p, const bkx_p
   return bko_pair_reads_filtered(x->o, p, pe, out, n_pairs, b.data(), offs, pst, len_dist,
                                  x->keep.empty() ? nullptr : x->keep.data());
 }
+// the compact host interface: 2 bits per base + exception list in, 16-byte records out
+static void unpack2(const uint8_t* packed2, uint64_t first_base, const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos,
+                    const uint8_t* exc_code, uint64_t n_exc, uint32_t n, std::vector<uint8_t>& b, std::vector<uint64_t>& offs) {
+  offs.assign((size_t)n + 1, 0);
+  for (uint32_t i = 0; i < n; ++i) offs[i + 1] = offs[i] + (lens ? lens[i] : fixed_len);
+  b.resize(offs[n]);
+  for (uint64_t i = 0; i < offs[n]; ++i) { const uint64_t q = first_base + i; b[i] = (packed2[q >> 2] >> ((q & 3) * 2)) & 3; }
+  for (uint64_t k = 0; k < n_exc; ++k)
+    if (exc_pos[k] >= first_base && exc_pos[k] - first_base < offs[n]) b[exc_pos[k] - first_base] = exc_code[k];
+}
+static void compact16(const std::vector<bkx_read_result>& r, bkx_read_result16* out) {
+  for (size_t i = 0; i < r.size(); ++i) {
+    bkx_read_result16 c;
+    c.nar_hr = (uint8_t)((r[i].nar & 0x1f) | (r[i].hit_rslt << 5));
+    const unsigned sc = r[i].strand == '+' ? 1u : r[i].strand == '-' ? 2u : r[i].strand == '?' ? 3u : 0u;
+    c.strand_flags = (uint8_t)(sc | ((r[i].flags & 3u) << 2));
+    c.num_hits = r[i].num_hits; c.mismatches = r[i].mismatches; c.low_mm = r[i].low_mm; c.nxt_low_mm = r[i].nxt_low_mm;
+    c.low_hit_instances = r[i].low_hit_instances; c.chrom_id = r[i].chrom_id; c.match_loci = r[i].match_loci;
+    out[i] = c;
+  }
+}
+int bkx_align_reads_packed2(bkx_index* x, const bkx_align_params* p, const uint8_t* packed2, uint64_t first_base, const uint16_t* lens,
+                            uint32_t fixed_len, const uint64_t* exc_pos, const uint8_t* exc_code, uint64_t n_exc, uint32_t n,
+                            bkx_read_result16* out, bkx_align_stats* st) {
+  std::vector<uint8_t> b;
+  std::vector<uint64_t> offs;
+  unpack2(packed2, first_base, lens, fixed_len, exc_pos, exc_code, n_exc, n, b, offs);
+  std::vector<bkx_read_result> r(n);
+  int rc = bko_align_batch(x->o, p, b.data(), offs.data(), n, r.data(), st, 4);
+  if (rc < 0) return rc;
+  compact16(r, out);
+  return BKX_OK;
+}
+int bkx_align_pairs_packed2(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, const uint8_t* packed2,
+                            uint64_t first_base, const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos,
+                            const uint8_t* exc_code, uint64_t n_exc, uint32_t n_pairs, bkx_read_result16* out, bkx_align_stats* st,
+                            bkx_pe_stats* pst, uint32_t* len_dist) {
+  std::vector<uint8_t> b;
+  std::vector<uint64_t> offs;
+  unpack2(packed2, first_base, lens, fixed_len, exc_pos, exc_code, n_exc, 2 * n_pairs, b, offs);
+  std::vector<bkx_read_result> r((size_t)2 * n_pairs);
+  int rc = bko_align_batch(x->o, p, b.data(), offs.data(), 2 * n_pairs, r.data(), st, 4);
+  if (rc < 0) return rc;
+  rc = bko_pair_reads_filtered(x->o, p, pe, r.data(), n_pairs, b.data(), offs.data(), pst, len_dist,
+                               x->keep.empty() ? nullptr : x->keep.data());
+  if (rc < 0) return rc;
+  compact16(r, out);
+  return BKX_OK;
+}
+int bkx_expand_results16(const bkx_read_result16* in, uint32_t n, const uint16_t* lens, uint32_t fixed_len, bkx_read_result* out) {
+  static const uint8_t kStrand[4] = {0, '+', '-', '?'};
+  for (uint32_t i = 0; i < n; ++i) {
+    const bkx_read_result16 c = in[i];
+    bkx_read_result r;
+    memset(&r, 0, sizeof(r));
+    r.nar = c.nar_hr & 0x1f; r.hit_rslt = c.nar_hr >> 5;
+    r.strand = kStrand[c.strand_flags & 3]; r.flags = (c.strand_flags >> 2) & 3;
+    r.num_hits = c.num_hits; r.mismatches = c.mismatches; r.low_mm = c.low_mm; r.nxt_low_mm = c.nxt_low_mm;
+    r.low_hit_instances = c.low_hit_instances; r.chrom_id = c.chrom_id; r.match_loci = c.match_loci;
+    r.match_len = r.strand ? (uint16_t)(lens ? lens[i] : fixed_len) : 0;
+    out[i] = r;
+  }
+  return BKX_OK;
+}
+
 int bkx_set_chrom_filter(bkx_index* x, const uint8_t* keep, uint32_t n_keep) {
   bkx_index_info info;
   bko_info(x->o, &info);

@@ -1,6 +1,6 @@
 """GPU: the homeolog-rich regime of BASELINE.json configs[3] at a size the oracle handles in seconds -- a 3 x 7
-chromosome hexaploid whose B and D sub-genomes are 2-5 % diverged copies of A, suffix array built in planes by the
-bounded-memory builder and served with 5-byte elements.  Every record against the oracle; multi-map classes must
+chromosome hexaploid whose B and D sub-genomes are 2-5 % diverged copies of A, suffix array built by the
+bounded-memory builder as 5-byte elements and served that way.  Every record against the oracle; multi-map classes must
 actually occur (LocateCoreMultiples' MMDelta / hit-instance rules, libbiokanga/SfxArrayV2.cpp:6157-6261)."""
 import numpy as np
 import pytest
@@ -18,18 +18,22 @@ torch = pytest.importorskip("torch")
 def hexa():
     d_seq, ents = wl.make_hexaploid(1_200_000, seed=4, device="cuda", block=20_000)
     n = int(d_seq.numel())
-    d_lo = torch.empty(n, dtype=torch.int32, device="cuda")
-    d_hi = torch.empty(n, dtype=torch.uint8, device="cuda")
-    bkx.build_suffix_array_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr(), 0, 5_000_000)
+    # 5-byte elements back to back (the .sfx element layout; one fetch per element), read through the two-level prefix
+    # table that indexes of >= 2^32 symbols get (forced here)
+    d_sa5 = torch.zeros(n * 5 + 16, dtype=torch.uint8, device="cuda")
+    bkx.build_suffix_array_packed5(d_seq.data_ptr(), n, d_sa5.data_ptr(), 0, 5_000_000)
     torch.cuda.synchronize()
-    gidx = bkx.Index.from_planes(d_seq.data_ptr(), n, d_lo.data_ptr(), d_hi.data_ptr(), ents, name="hexa")
-    sa5 = np.zeros((n, 5), dtype=np.uint8)
-    sa5[:, :4] = d_lo.cpu().numpy().view(np.uint8).reshape(-1, 4)
-    sa5[:, 4] = d_hi.cpu().numpy()
+    import os
+    os.environ["BKX_FORCE_WIDE_PT"] = "1"
+    try:
+        gidx = bkx.Index.from_packed5(d_seq.data_ptr(), n, d_sa5.data_ptr(), ents, name="hexa")
+    finally:
+        del os.environ["BKX_FORCE_WIDE_PT"]
+    sa5 = d_sa5[:n * 5].cpu().numpy()
     seq = d_seq.cpu().numpy()
-    oidx = po.OracleIndex(seq=seq, sa=sa5.reshape(-1), el_size=5, entries=ents)
+    oidx = po.OracleIndex(seq=seq, sa=sa5, el_size=5, entries=ents)
     d_bases, d_offs = wl.sim_reads(d_seq, ents, 60_000, 150, seed=9, subs=(0, 1, 2, 3, 4))
-    keep = (d_seq, d_lo, d_hi)
+    keep = (d_seq, d_sa5)
     return gidx, oidx, d_bases.cpu().numpy(), d_offs.cpu().numpy().astype(np.uint64), keep
 
 

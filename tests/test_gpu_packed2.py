@@ -44,6 +44,8 @@ def test_packed2_records_equal_byte_per_base_records(case, tag, tiny_slices, gol
             forms = [(got, gst)]
             got2, gst2 = idx.align_packed2(p, bases, offs, fixed=False)   # lengths given even when they are all equal
             forms.append((got2, gst2))
+            got3, gst3 = idx.align_packed2(p, bases, offs, first_base=1237)   # a shard that starts inside a longer stream
+            forms.append((got3, gst3))
         else:
             ld2 = np.zeros(100001, dtype=np.uint32)
             got, gst, gps = idx.align_packed2(p, bases, offs, pe=pe, len_dist=ld2)
