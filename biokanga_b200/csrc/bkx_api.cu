@@ -37,6 +37,19 @@ int bkx_fail(int code, const char* fmt, ...) {
 
 #define fail bkx_fail
 
+// BKX_TRACE=1: stage timings of the index load on stderr
+#include <chrono>
+struct StageTimer {
+  bool on = getenv("BKX_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bkx trace] %-34s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 #define CU(call)                                                                                      \
   do {                                                                                                \
     cudaError_t e__ = (call);                                                                         \
@@ -183,6 +196,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
   for (auto& e : x->entries) tot += e.seq_len;
   x->info.tot_seq_len = tot;
 
+  StageTimer tm;
   cudaStream_t st = x->slot[0].st;
   uint64_t* g2; uint64_t* gx; uint32_t* gxc;
   size_t g2w = ((n + 63) >> 6) * 2 + 4, gxw = ((n + 63) >> 6) + 2, gcw = (((n + 63) >> 6) + 31) / 32 + 2;
@@ -199,6 +213,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
   CU(cudaStreamSynchronize(st));
   cudaFree(d_bad);
   x->launches += 1;
+  tm.mark("finish_index: pack genome");
   if (bad) return fail(BKX_ERR_UNSUPPORTED, "%llu symbols other than A,C,G,T,N,EOS in the index sequence", bad);
   x->d.g2 = g2; x->d.gx = gx; x->d.gxc = gxc; x->d.n = n;
   REG_ARR(x, g2, g2w * 8); REG_ARR(x, gx, gxw * 8); REG_ARR(x, gxc, gcw * 4);
@@ -292,10 +307,12 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
   if (wide) {
     if ((rc = dev_alloc(x, &pt_hi, pt_blocks, false)) < 0) return rc;
   }
+  tm.mark("finish_index: small tables, allocs");
   CU(build_prefix_table(x->d, k, pt, pt_hi, st));
   if (wide) { x->d.pt_hi = pt_hi; REG_ARR(x, pt_hi, pt_blocks * 8); }
   x->launches += 2;
   CU(cudaStreamSynchronize(st));
+  tm.mark("finish_index: prefix table");
   // self-check: every suffix-array element inside the table bucket of its suffix (0.3 s at 3.1 G symbols); a failure
   // means the suffix array does not belong to this sequence or an array was damaged on its way to the device
   if (!getenv("BKX_NO_VERIFY")) {
@@ -317,6 +334,7 @@ static int finish_index(bkx_index* x, const uint8_t* d_seq, uint64_t n, const Sa
   }
   // the small tables above went up with cudaMemcpy on the legacy stream, which the work streams do not wait for
   CU(cudaDeviceSynchronize());
+  tm.mark("finish_index: self-check");
   return BKX_OK;
 }
 
@@ -538,9 +556,11 @@ static int open_index_once(const char* path, int device, int prefix_k, bkx_index
     close(fd);
     return fail(BKX_ERR_FORMAT, "'%s': bad suffix block", path);
   }
+  StageTimer tm;
   bkx_index* x = nullptr;
   int rc = new_index(device, &x);
   if (rc < 0) { close(fd); return rc; }
+  tm.mark("open: CUDA context, streams");
   x->info.version = version;
   x->info.attributes = attributes;
   // Stream the block to the GPU: a few reader threads, each with its own pinned staging buffer and CUDA stream, take
@@ -553,10 +573,12 @@ static int open_index_once(const char* path, int device, int prefix_k, bkx_index
   cudaError_t e = cudaMalloc((void**)&d_seq, n);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_sa, n * el + 16);
   bool io_ok = true;
+  tm.mark("open: device allocations");
   if (e == cudaSuccess) {
     const uint64_t seq_chunks = (n + chunk - 1) / chunk, sa_bytes = n * el, sa_chunks = (sa_bytes + chunk - 1) / chunk;
     const uint64_t n_chunks = seq_chunks + sa_chunks;
-    const int n_workers = (int)std::min<uint64_t>(6, n_chunks);
+    int n_workers = (int)std::min<uint64_t>(std::max(4u, std::min(12u, std::thread::hardware_concurrency() / 2)), n_chunks);
+    if (const char* ev = getenv("BKX_LOAD_THREADS")) n_workers = (int)std::min<uint64_t>((uint64_t)std::max(1, atoi(ev)), n_chunks);
     std::vector<cudaError_t> werr((size_t)n_workers, cudaSuccess);
     std::vector<char> wio((size_t)n_workers, 1);
     std::vector<uint64_t> wlaunch((size_t)n_workers, 0);
@@ -588,6 +610,7 @@ static int open_index_once(const char* path, int device, int prefix_k, bkx_index
     }
   }
   close(fd);
+  tm.mark("open: file -> device");
   if (e != cudaSuccess || !io_ok) {
     cudaFree(d_seq); cudaFree(d_sa); bkx_close_index(x);
     return e != cudaSuccess ? fail(BKX_ERR_CUDA, "index upload: %s", cudaGetErrorString(e))
@@ -823,6 +846,7 @@ static uint32_t pool_slots_needed(const KParams& k, uint64_t max_len) {
 
 // Size the persistent grid and the per-warp overflow hash sets for reads up to max_len bases.
 static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int* W_out) {
+  StageTimer tm;
   if (max_len > 2000) return fail(BKX_ERR_PARAM, "read length %u exceeds cMaxSeqLen 2000", max_len);
   int W = (int)((max_len + 31) / 32) + 1;
   if (W < 3) W = 3;
@@ -876,6 +900,7 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
     }
   }
   *W_out = x->grid_W;
+  tm.mark("prepare_launch");
   return BKX_OK;
 }
 
@@ -1557,6 +1582,15 @@ extern "C" int bkx_pair_reads_device(bkx_index* x, const bkx_align_params* p, co
 }
 
 // Page-lock / unlock caller memory so the library's H2D / D2H copies run asynchronously at full PCIe speed.
+// Page-locked host memory from the start (no registration pass later): for buffers the caller fills itself and then hands
+// to the host-buffer calls -- bkx-align's read stream and record array.
+extern "C" void* bkx_alloc_host(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); fail(BKX_ERR_MEM, "cudaHostAlloc(%zu bytes) failed", bytes); return nullptr; }
+  return p;
+}
+extern "C" void bkx_free_host(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
 extern "C" int bkx_pin_host(void* ptr, size_t bytes) {
   if (!ptr || !bytes) return BKX_OK;
   cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);

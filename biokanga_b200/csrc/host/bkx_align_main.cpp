@@ -41,6 +41,7 @@
 
 #include <glob.h>
 #include <regex.h>
+#include <sys/mman.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -80,17 +81,47 @@ struct NoInit : std::allocator<T> {
   }
 };
 template <class T> using Buf = std::vector<T, NoInit<T>>;
+
+// A buffer that crosses PCIe: page-locked by the library from the start (bkx_alloc_host), plain memory if that fails.
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  bool pinned = false;
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { release(); }
+  void release() {
+    if (p) { if (pinned) bkx_free_host(p); else free(p); }
+    p = nullptr; n = 0;
+  }
+  bool resize(size_t count) {   // contents are not kept
+    release();
+    p = (T*)bkx_alloc_host(count * sizeof(T));
+    pinned = p != nullptr;
+    if (!p) p = (T*)malloc(std::max<size_t>(count * sizeof(T), 1));
+    n = p ? count : 0;
+    return p != nullptr;
+  }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
 using ResVec = Buf<bkx_read_result>;
 
 // ---- read ingest ---------------------------------------------------------------------------------
 struct Reads {
   // what crosses PCIe (the library's compact host interface): the bases 2 bits each (base i at bits [2(i%4), +2) of byte i/4,
   // non-ACGT bases as 0 and listed in exc_*), read lengths (empty when all reads are equally long)
-  Buf<uint8_t> packed2;
+  PinnedBuf<uint8_t> packed2;
   std::vector<uint64_t> exc_pos;
   std::vector<uint8_t> exc_code;
   Buf<uint16_t> lens;
   uint32_t fixed_len = 0;
+  PinnedBuf<bkx_read_result16> res16;   // the records of the compact interface, allocated along with the stream
   Buf<uint8_t> bases;             // 1 byte/base, etSeqBase code in the low 3 bits
   Buf<uint64_t> offs = Buf<uint64_t>(1, 0);
   Buf<char> names;                // NUL-terminated descriptors, back to back
@@ -434,9 +465,10 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
     if (under) diag("Load: total of %d under length sequences sloughed from file '%s'", under, o.in[fi].c_str());
     if (over) diag("Load: total of %d over length sequences sloughed from file '%s'", over, o.in[fi].c_str());
   }
-  {  // the 2-bit stream + exception list + lengths for the H2D copies; threads own disjoint byte ranges of the stream
+  if (o.ml_mode < 3) {  // the 2-bit stream + exception list + lengths for the H2D copies (the multi-loci calls -r3..5 take the
+                        // one-byte-per-base arena); threads own disjoint byte ranges of the stream
     const size_t nb = R.bases.size(), np = (nb + 3) / 4;
-    R.packed2.resize(np + 16);
+    if (!R.packed2.resize(np + 16) || !R.res16.resize(R.n())) { diag("Fatal: out of memory"); return -1; }
     std::vector<std::vector<uint64_t>> epos(T);
     std::vector<std::vector<uint8_t>> ecode(T);
     const uint32_t nreads = R.n();
@@ -703,7 +735,8 @@ struct OutBuf {  // plain or gzip (when the output name ends in .gz, as the refe
   bool open(const std::string& path) {
     s.reserve(1 << 22);
     if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0) { gz = gzopen(path.c_str(), "wb"); return gz != nullptr; }
-    f = fopen(path.c_str(), "wb");
+    f = fopen(path.c_str(), "w+b");   // readable too: emit_rows maps the file to let all threads fill it
+    if (!f) f = fopen(path.c_str(), "wb");
     return f != nullptr;
   }
   void flush() {
@@ -758,14 +791,25 @@ static void emit_rows(OutBuf& ob, uint32_t n, unsigned threads, F&& row) {
       continue;
     }
     std::vector<off_t> at(used);
+    const off_t batch_ofs = file_ofs;
     for (unsigned t = 0; t < used; ++t) { at[t] = file_ofs; file_ofs += (off_t)bufs[t].size(); }
+    if (file_ofs == batch_ofs) continue;
+    // the file grows by the batch and the workers copy their rows into a shared mapping of that stretch: page faults and
+    // copies run on all threads (concurrent write() calls on one file serialise on its inode lock); pwrite if mmap fails
+    const off_t page = (off_t)sysconf(_SC_PAGESIZE), map_ofs = batch_ofs & ~(page - 1);
+    char* map = nullptr;
+    if (ftruncate(fd, file_ofs) == 0) {
+      void* m = mmap(nullptr, (size_t)(file_ofs - map_ofs), PROT_READ | PROT_WRITE, MAP_SHARED, fd, map_ofs);
+      if (m != MAP_FAILED) map = (char*)m;
+    }
     std::vector<char> ok(used, 1);
     th.clear();
     for (unsigned t = 0; t < used; ++t)
-      th.emplace_back([&bufs, &at, &ok, fd, t]() {
+      th.emplace_back([&bufs, &at, &ok, fd, t, map, map_ofs]() {
         const char* p = bufs[t].data();
         size_t left = bufs[t].size();
         off_t o = at[t];
+        if (map) { memcpy(map + (o - map_ofs), p, left); return; }
         while (left) {
           ssize_t w = pwrite(fd, p, left, o);
           if (w <= 0) { ok[t] = 0; return; }
@@ -773,6 +817,7 @@ static void emit_rows(OutBuf& ob, uint32_t n, unsigned threads, F&& row) {
         }
       });
     for (auto& x : th) x.join();
+    if (map) munmap(map, (size_t)(file_ofs - map_ofs));
     for (unsigned t = 0; t < used; ++t) if (!ok[t]) { fd = -2; break; }
     if (fd == -2) { diag("Fatal: write to the result file failed"); exit(1); }
   }
@@ -978,7 +1023,12 @@ static bool is_bam_name(const std::string& p) {  // kanga.cpp:849-857: longer th
   return e == ".bam";
 }
 
-static void append_uint(std::string& s, uint64_t v) { char b[24]; int n = snprintf(b, sizeof(b), "%llu", (unsigned long long)v); s.append(b, n); }
+static void append_uint(std::string& s, uint64_t v) {   // decimal digits without printf (hundreds of millions of calls per run)
+  char b[24];
+  int n = 24;
+  do { b[--n] = (char)('0' + v % 10); v /= 10; } while (v);
+  s.append(b + n, (size_t)(24 - n));
+}
 
 // ---- -5: loci base constraints, CAligner::LoadLociConstraints, Aligner.cpp:1245-1441.  CSV rows chrom,start,end,bases:
 //      reads aligned over [start, end] of chrom are only kept if their base there is one of `bases` (A C G T; R = the
@@ -1895,10 +1945,11 @@ int main(int argc, char** argv) {
   const bool clustered = o.ml_mode == BKX_ML_UNIQ || o.ml_mode == BKX_ML_MULTI;   // -r3 / -r4: one locus by clustering
   const bool compact = !(all_loci || clustered);   // the compact host interface: 2 bits per base in, 16-byte records out
   ResVec res(n);            // filled below (expanded from the 16-byte records, or written by the multi-loci call)
-  Buf<bkx_read_result16> res16(compact ? n : 0);
-  // page-lock what crosses PCIe: H2D / D2H then stream asynchronously, double buffered
+  // what crosses PCIe is page-locked: the 2-bit read stream and the 16-byte records from the moment they are allocated (by the
+  // reads thread, while the index streams in); the multi-loci calls register their one-byte-per-base arena here
+  PinnedBuf<bkx_read_result16>& res16 = R.res16;
   bool pinned = true;
-  if (compact) pinned = bkx_pin_host(R.packed2.data(), R.packed2.size()) >= 0 && bkx_pin_host(res16.data(), res16.size() * sizeof(bkx_read_result16)) >= 0;
+  if (compact) pinned = R.packed2.pinned && res16.pinned;
   else pinned = bkx_pin_host(R.bases.data(), R.bases.size()) >= 0 && bkx_pin_host(res.data(), res.size() * sizeof(bkx_read_result)) >= 0;
   if (!pinned) diag("Note: unable to page-lock host buffers (%s); continuing with pageable copies", bkx_last_error());
   std::vector<bkx_multi_hit> multi;
@@ -1959,8 +2010,7 @@ int main(int argc, char** argv) {
     const uint64_t* s = (const uint64_t*)&st[(size_t)g];
     for (size_t k = 0; k < sizeof(S) / 8; ++k) d[k] += s[k];
   }
-  if (compact) { bkx_unpin_host(R.packed2.data()); bkx_unpin_host(res16.data()); }
-  else { bkx_unpin_host(R.bases.data()); bkx_unpin_host(res.data()); }
+  if (!compact) { bkx_unpin_host(R.bases.data()); bkx_unpin_host(res.data()); }
   if (compact) {   // 16-byte records -> the 32-byte form the passes and writers work on, by all host threads
     const unsigned T = o.threads > 0 ? (unsigned)o.threads : std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     std::vector<std::thread> th;
@@ -1970,7 +2020,8 @@ int main(int argc, char** argv) {
         if (e > b) bkx_expand_results16(res16.data() + b, e - b, R.fixed_len ? nullptr : R.lens.data() + b, R.fixed_len, res.data() + b);
       });
     for (auto& x : th) x.join();
-    Buf<bkx_read_result16>().swap(res16);
+    res16.release();
+    R.packed2.release();
   }
   diag("Alignment of %u from %u loaded completed", n, n);
 

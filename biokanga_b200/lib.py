@@ -28,6 +28,7 @@ EXPORTS = [
     "bkx_assign_multi_matches", "bkx_self_check", "bkx_debug_reset", "bkx_set_chrom_filter",
     "bkx_align_reads_packed2", "bkx_align_pairs_packed2", "bkx_pack_bases2", "bkx_expand_results16",
     "bkx_align_reads_device_packed2", "bkx_open_index_packed5", "bkx_build_suffix_array_packed5",
+    "bkx_alloc_host", "bkx_free_host",
 ]
 
 
@@ -107,6 +108,10 @@ def lib():
                                         vp, vp]
     L.bkx_set_chrom_filter.argtypes = [vp, vp, u32]
     L.bkx_pin_host.argtypes = [vp, C.c_size_t]
+    L.bkx_alloc_host.argtypes = [C.c_size_t]
+    L.bkx_alloc_host.restype = vp
+    L.bkx_free_host.argtypes = [vp]
+    L.bkx_free_host.restype = None
     L.bkx_unpin_host.argtypes = [vp]
     L.bkx_last_kernel_ms.argtypes = [vp]
     L.bkx_last_kernel_ms.restype = C.c_float

@@ -395,6 +395,10 @@ int bkx_write_sfx(const char* path, const uint8_t* seq, uint64_t concat_len, con
  * Page-lock caller buffers (read arena, result array) so bkx_align_reads() copies asynchronously at PCIe speed;
  * the reference keeps its reads in one mmap'd arena (Aligner.cpp:10572-10677) -- pin that arena once. */
 int bkx_pin_host(void* ptr, size_t bytes);
+/* Page-locked host memory from the start (NULL on failure; bkx_last_error() says why): for buffers the caller fills itself
+ * and then hands to the host-buffer calls, instead of a registration pass over them afterwards. */
+void* bkx_alloc_host(size_t bytes);
+void bkx_free_host(void* ptr);
 int bkx_unpin_host(void* ptr);
 
 /* ---- instrumentation -------------------------------------------------------------------------- */

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -61,6 +62,8 @@ int64_t bkx_get_seq(const bkx_index* x, uint32_t id, uint64_t loci, uint64_t len
 }
 int bkx_default_params(const bkx_index* x, int pmode, bkx_align_params* out) { return bko_default_params(x->o, pmode, out); }
 int bkx_pin_host(void*, size_t) { return BKX_OK; }
+void* bkx_alloc_host(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void bkx_free_host(void* p) { free(p); }
 int bkx_unpin_host(void*) { return BKX_OK; }
 
 int bkx_align_reads_packed4(bkx_index* x, const bkx_align_params* p, const uint8_t* packed, const uint64_t* offs, uint32_t n,
