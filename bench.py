@@ -401,25 +401,32 @@ def run_bkx(args):
 
 
 def run_sweep(args):
-    """BASELINE.json configs[4]: substitutions 0..8 x read length 50..300 on the configs[1] genome.  One table row per
-    (L, -s): device-resident reads/s, class histogram, algorithmic-bytes roofline and a parity check of a sample of
-    the records against the CPU oracle.  Writes gpurun_out/sweep.json; prints one summary JSON line."""
+    """BASELINE.json configs[4]: substitutions 0..8 x read length 50..300 on the configs[1] genome, at 1/2/4/8 GPUs (under
+    torchrun the index is broadcast over NCCL, every rank aligns its own reads of every cell, a cell's time is the maximum
+    over the ranks).  One table row per (L, -s): device-resident reads/s (all ranks), class histogram, algorithmic-bytes
+    roofline and -- on rank 0 -- a parity check of a sample of the records against the CPU oracle, whose throughput on
+    that sample is the host-CPU figure of the row.  Writes gpurun_out/sweep[_Ngpu].json; prints one summary JSON line."""
     import torch
+    import torch.distributed as dist
     from biokanga_b200 import abi
     from biokanga_b200 import lib as bkx
     from biokanga_b200 import workload as wl
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
-    lens = wl.chrom_layout(int(args.genome_mbp * 1e6))
-    d_seq, ents = wl.make_genome(lens, seed=args.seed, device=dev)
-    n = int(d_seq.numel())
-    d_sa = torch.empty(n, dtype=torch.int32, device=dev)
-    bkx.build_suffix_array_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 0)
-    torch.cuda.synchronize()
-    idx = bkx.Index.from_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 4, ents, name="sweep", device=0, prefix_k=args.prefix_k)
-    oidx = po.OracleIndex(seq=d_seq.cpu().numpy(), sa=d_sa.cpu().numpy().view(np.uint32), el_size=4, entries=ents)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    args.reads = 1024   # the reads build_workload makes are not used: every cell draws its own
+    d_seq, d_sa, ents, n, _, _ = build_workload(args, rank, world, dev, torch, dist)
+    idx = bkx.Index.from_device(d_seq.data_ptr(), n, d_sa.data_ptr(), 4, ents, name="sweep", device=local, prefix_k=args.prefix_k)
+    oidx = None
+    if rank == 0:
+        oidx = po.OracleIndex(seq=d_seq.cpu().numpy(), sa=d_sa.cpu().numpy().view(np.uint32), el_size=4, entries=ents)
     del d_sa
     torch.cuda.empty_cache()
     peak, _ = measured_peak()
@@ -428,42 +435,62 @@ def run_sweep(args):
     torch.cuda.set_stream(tstream)
     rows = []
     all_ok = True
+    cores = os.cpu_count() or 1
     lens_ = [int(v) for v in args.sweep_lens.split(",")]
     subs_ = [int(v) for v in args.sweep_subs.split(",")]
     for L in lens_:
         for s_ in subs_:
             for mmd in ((1, 2) if s_ in (3, 8) else (1,)):
                 max_tot = 0 if s_ == 0 else max(1, (L * s_ + 50) // 100)
-                d_bases, d_offs = wl.sim_reads(d_seq, ents, nreads, L, seed=args.seed + 7 * L + s_, subs=tuple(range(0, max_tot + 2)),
-                                               device=dev)
+                d_bases, d_offs = wl.sim_reads(d_seq, ents, nreads, L, seed=args.seed + 7 * L + s_ + 1000 * rank,
+                                               subs=tuple(range(0, max_tot + 2)), device=dev)
+                d_pk2, d_rflags = wl.pack2_device(d_bases, d_offs)
                 p = idx.default_params(0, max_subs=s_, min_edit_dist=mmd)
                 d_out = torch.empty(nreads * 32, dtype=torch.uint8, device=dev)
                 ms = []
                 for rep in range(3):
-                    idx.align_device(p, d_bases.data_ptr(), d_offs.data_ptr(), nreads, L, d_out.data_ptr(), None, tstream.cuda_stream)
+                    if world > 1:
+                        dist.barrier()
                     torch.cuda.synchronize()
-                    ms.append(idx.last_kernel_ms())
+                    idx.align_device_packed2(p, d_bases.data_ptr(), d_pk2.data_ptr(), d_rflags.data_ptr(), d_offs.data_ptr(), nreads, L,
+                                             d_out.data_ptr(), None, tstream.cuda_stream)
+                    torch.cuda.synchronize()
+                    t = torch.tensor([idx.last_kernel_ms()], dtype=torch.float64, device=dev)
+                    if world > 1:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms.append(float(t.item()))
+                if rank != 0:
+                    del d_bases, d_offs, d_out, d_pk2, d_rflags
+                    continue
                 res = d_out.cpu().numpy().view(abi.RESULT_DTYPE)
                 m = min(args.sweep_check, nreads)
                 bases = d_bases[:m * L].cpu().numpy()
                 offs = np.arange(m + 1, dtype=np.uint64) * L
-                exp, _ = oidx.align(oidx.default_params(0, max_subs=s_, min_edit_dist=mmd), bases, offs, nthreads=os.cpu_count() or 1)
+                tq = time.perf_counter()
+                exp, _ = oidx.align(oidx.default_params(0, max_subs=s_, min_edit_dist=mmd), bases, offs, nthreads=cores)
+                cpu_s = time.perf_counter() - tq
                 ok = all(np.array_equal(res[f][:m], exp[f]) for f in abi.RESULT_DTYPE.names)
                 all_ok &= ok
                 nar = np.bincount(res["nar"], minlength=abi.NAR_COUNT)
                 best = min(ms[1:])
                 ab = wl.algorithmic_bytes(res, n, 4, L)
-                rows.append({"L": L, "s": s_, "e": mmd, "max_tot_mm": max_tot, "reads": nreads, "ms": best,
-                             "reads_per_s": nreads / (best / 1e3), "roofline_frac": ab / (best / 1e3) / 1e9 / peak,
+                rows.append({"L": L, "s": s_, "e": mmd, "max_tot_mm": max_tot, "reads_per_gpu": nreads, "n_gpus": world, "ms": best,
+                             "reads_per_s": world * nreads / (best / 1e3), "roofline_frac": ab / (best / 1e3) / 1e9 / peak,
                              "bytes_per_read": ab / nreads, "parity_sample": m, "parity_ok": bool(ok),
+                             "host_cpu_port_reads_per_s": m / cpu_s, "host_cores": cores,
                              "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]}})
-                log("[sweep] L=%d -s%d -e%d: %.1f M reads/s, frac %.2f, parity %s, %s" % (
-                    L, s_, mmd, rows[-1]["reads_per_s"] / 1e6, rows[-1]["roofline_frac"], ok, rows[-1]["classes"]))
-                del d_bases, d_offs, d_out
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)
-    print(json.dumps({"sweep_rows": len(rows), "all_parity_ok": bool(all_ok),
-                      "min_reads_per_s": min(r["reads_per_s"] for r in rows), "max_reads_per_s": max(r["reads_per_s"] for r in rows)}))
+                log("[sweep] L=%d -s%d -e%d: %.1f M reads/s on %d GPU(s), frac %.2f per GPU, parity %s, host CPU %.0f k reads/s, %s" % (
+                    L, s_, mmd, rows[-1]["reads_per_s"] / 1e6, world, rows[-1]["roofline_frac"], ok, m / cpu_s / 1e3, rows[-1]["classes"]))
+                del d_bases, d_offs, d_out, d_pk2, d_rflags
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        name = "sweep.json" if world == 1 else "sweep_%dgpu.json" % world
+        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
+        print(json.dumps({"sweep_rows": len(rows), "n_gpus": world, "all_parity_ok": bool(all_ok),
+                          "min_reads_per_s": min(r["reads_per_s"] for r in rows), "max_reads_per_s": max(r["reads_per_s"] for r in rows)}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_hexaploid(args):
