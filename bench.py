@@ -108,7 +108,7 @@ def ncu_traffic(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu
     capture -- only when this run is the workload that capture was taken on (else null)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_final_traffic.json")))
         w = t["workload"]
         same = (float(args.genome_mbp) == w["genome_mbp"] and args.reads == w["reads"] and args.read_len == w["read_len"] and
                 args.read_subs == w["read_subs"] and args.max_subs == w["max_subs"] and args.seed == w["seed"] and
@@ -381,7 +381,7 @@ def run_bkx(args):
                      "traffic": ncu_traffic(args), "kernel": "align_fast_kernel + align_reads_kernel (deferred reads)",
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": int(alg_bytes), "bytes_per_read": alg_bytes / nreads,
                      "peak_source": peak_src,
-                     "traffic_source": "profiles/r01_final_traffic.json (ncu --set full, one launch of align_fast_kernel)"},
+                     "traffic_source": "profiles/r02_final_traffic.json (ncu --set full, one launch of align_fast_kernel)"},
         "clocks": clocks,
         "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]},
         "stats_reads_all_ranks": int(stats[-1]),

@@ -39,7 +39,7 @@ class AlignParams(C.Structure):
                 ("max_ns", C.c_int32), ("align_strand", C.c_int32), ("max_ml_matches", C.c_int32),
                 ("min_core_len", C.c_int32), ("max_num_slides", C.c_int32), ("max_iter", C.c_int32),
                 ("max_ident_nodes", C.c_int32), ("ml_mode", C.c_int32), ("clamp_max_ml", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("best_matches", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class PEParams(C.Structure):

@@ -1189,22 +1189,38 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
   __syncthreads();
   enum { UNAL = 0, ACCP = 1, ACCSE = 2, PPAIRED = 3, PUNP = 4, FILT = 5, UNDER = 6, OVER = 7 };
   const int mode = pe.pe_proc;
+  unsigned int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // this thread's share of the counters: one shared-memory atomic each at the end
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
-    bkx_read_result f = res[2 * i], r = res[2 * i + 1];
+    // the two 32-byte records of a pair as four 16-byte loads (and stores below): the kernel streams 128 bytes per pair and
+    // was limited by the number of load / store instructions in flight (lg_throttle, profiles/r02_pe_kernels_ncu.md)
+    bkx_read_result f, r;
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(res + 2 * (size_t)i);
+      const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+      memcpy(&f, &a, 16); memcpy(reinterpret_cast<char*>(&f) + 16, &b, 16);
+      memcpy(&r, &c, 16); memcpy(reinterpret_cast<char*>(&r) + 16, &d, 16);
+    }
+    auto store_pair = [&]() {
+      uint4 a, b, c, d;
+      memcpy(&a, &f, 16); memcpy(&b, reinterpret_cast<const char*>(&f) + 16, 16);
+      memcpy(&c, &r, 16); memcpy(&d, reinterpret_cast<const char*>(&r) + 16, 16);
+      uint4* dst = reinterpret_cast<uint4*>(res + 2 * (size_t)i);
+      dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+    };
     f.flags &= (uint8_t)~(BKX_FLG_PE_ALIGNED | BKX_FLG_PE_RECOVERED);
     r.flags &= (uint8_t)~(BKX_FLG_PE_ALIGNED | BKX_FLG_PE_RECOVERED);
     bool f_un = f.nar == BKX_NAR_NS || f.nar == BKX_NAR_NOHIT || f.nar == BKX_NAR_UNALIGNED;
     bool r_un = r.nar == BKX_NAR_NS || r.nar == BKX_NAR_NOHIT || r.nar == BKX_NAR_UNALIGNED;
     bool done = false;
     if (!(f.nar == BKX_NAR_ACCEPTED || r.nar == BKX_NAR_ACCEPTED)) {
-      atomicAdd(&pb.v[UNAL], 1u);
+      ++cnt[UNAL];
       done = true;
     } else if (mode == BKX_PE_UNIQUE && (f_un || r_un)) {
       f.num_hits = r.num_hits = 0;
       f.low_hit_instances = r.low_hit_instances = 0;
       if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
       if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
-      atomicAdd(&pb.v[PUNP], 1u);
+      ++cnt[PUNP];
       done = true;
     } else if (f.nar == BKX_NAR_ACCEPTED && r.nar == BKX_NAR_ACCEPTED) {
       int frag;
@@ -1222,7 +1238,7 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
         f.flags |= BKX_FLG_PE_ALIGNED;
         r.flags |= BKX_FLG_PE_ALIGNED;
         if (len_dist) atomicAdd(len_dist + frag, 1u);
-        atomicAdd(&pb.v[ACCP], 1u);
+        ++cnt[ACCP];
         done = true;
       } else {
         switch (frag) {
@@ -1231,7 +1247,7 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
           case -6: f.nar = r.nar = BKX_NAR_PEINSERTMIN; break;
           case -7: f.nar = r.nar = BKX_NAR_PEINSERTMAX; break;
           case -3:  // Aligner.cpp:3170
-            atomicAdd(&pb.v[FILT], 1u);
+            ++cnt[FILT];
             f.num_hits = r.num_hits = 0;
             f.low_hit_instances = r.low_hit_instances = 0;
             f.nar = r.nar = BKX_NAR_CHROMFILT;
@@ -1246,24 +1262,23 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
           f.low_hit_instances = r.low_hit_instances = 0;
           if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PENOHIT;
           if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PENOHIT;
-          atomicAdd(&pb.v[PUNP], 1u);
+          ++cnt[PUNP];
           done = true;
         }
       }
     }
     if (!done) {
-      atomicAdd(&pb.v[PUNP], 1u);
+      ++cnt[PUNP];
       if ((mode == BKX_PE_ORPHAN || mode == BKX_PE_ORPHAN_SE) && orphan_list &&
           ((f.num_hits == 1 && !r_un) || (r.num_hits == 1 && !f_un))) {
         // orphan recovery is a separate (warp per orphan) kernel; it finishes this pair
         orphan_list[atomicAdd(n_orphans, 1u)] = i;
-        res[2 * i] = f;
-        res[2 * i + 1] = r;
+        store_pair();
         continue;
       }
-      if (f.nar == BKX_NAR_CHROMFILT || r.nar == BKX_NAR_CHROMFILT) atomicAdd(&pb.v[FILT], 1u);
-      if (f.nar == BKX_NAR_PEINSERTMIN || r.nar == BKX_NAR_PEINSERTMIN) atomicAdd(&pb.v[UNDER], 1u);
-      if (f.nar == BKX_NAR_PEINSERTMAX || r.nar == BKX_NAR_PEINSERTMAX) atomicAdd(&pb.v[OVER], 1u);
+      if (f.nar == BKX_NAR_CHROMFILT || r.nar == BKX_NAR_CHROMFILT) ++cnt[FILT];
+      if (f.nar == BKX_NAR_PEINSERTMIN || r.nar == BKX_NAR_PEINSERTMIN) ++cnt[UNDER];
+      if (f.nar == BKX_NAR_PEINSERTMAX || r.nar == BKX_NAR_PEINSERTMAX) ++cnt[OVER];
       if (!(mode == BKX_PE_ORPHAN_SE || mode == BKX_PE_UNIQUE_SE)) {
         f.num_hits = r.num_hits = 0;
         f.low_hit_instances = r.low_hit_instances = 0;
@@ -1274,16 +1289,18 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
         if (f.num_hits != 1 || (keep && !__ldg(keep + f.chrom_id))) {
           f.num_hits = 0; f.low_hit_instances = 0;
           if (f.nar == BKX_NAR_ACCEPTED) f.nar = BKX_NAR_PEUNALIGN;
-        } else { f.nar = BKX_NAR_ACCEPTED; atomicAdd(&pb.v[ACCSE], 1u); }
+        } else { f.nar = BKX_NAR_ACCEPTED; ++cnt[ACCSE]; }
         if (r.num_hits != 1 || (keep && !__ldg(keep + r.chrom_id))) {
           r.num_hits = 0; r.low_hit_instances = 0;
           if (r.nar == BKX_NAR_ACCEPTED) r.nar = BKX_NAR_PEUNALIGN;
-        } else { r.nar = BKX_NAR_ACCEPTED; atomicAdd(&pb.v[ACCSE], 1u); }
+        } else { r.nar = BKX_NAR_ACCEPTED; ++cnt[ACCSE]; }
       }
     }
-    res[2 * i] = f;
-    res[2 * i + 1] = r;
+    store_pair();
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (cnt[k]) atomicAdd(&pb.v[k], cnt[k]);
   __syncthreads();
   if (threadIdx.x == 0 && stats) {
     atomicAdd((unsigned long long*)&stats->unaligned_pairs, (unsigned long long)pb.v[UNAL]);

@@ -107,7 +107,10 @@ typedef struct bkx_align_params {
   int32_t max_ident_nodes;  /* cMaxNumIdentNodes = 1 024 000 (SfxArrayV2.h:15)   */
   int32_t ml_mode;          /* -r  BKX_ML_*: what to do with reads hitting several loci (default slough)  */
   int32_t clamp_max_ml;     /* -X  treat reads with more than max_ml_matches loci as if exactly that many */
-  int32_t reserved[4];
+  int32_t best_matches;     /* -N  with a multi-loci mode: the max_ml_matches loci with the fewest mismatches (<= the -s limit),
+                             *     found in ONE un-staged pass -- CSfxArrayV3::LocateBestMatches (SfxArrayV2.cpp:6654-7019)
+                             *     instead of AlignReads; implies clamp_max_ml (kanga.cpp:695-696) */
+  int32_t reserved[3];
 } bkx_align_params;
 
 /* Fixed 32-byte per-read record: the tsReadHit fields written by ProcCoredApprox

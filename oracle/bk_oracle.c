@@ -388,6 +388,105 @@ static int locate_core_multiples(const bko_index* x, work_ctx* w, int max_tot_mm
   return BKX_HR_HITS;
 }
 
+/* -N: LocateBestMatches, SfxArrayV2.cpp:6654-7019 -- ONE pass (no staged phases) over the cores of both strands that keeps
+ * the max_hits loci with the fewest mismatches (<= max_tot_mm), ordered by mismatches, equal ones in discovery order.
+ * Returns 0 (no locus), else the number kept, plus one if a locus was turned away from a full list; *p_inst = number kept. */
+static int locate_best_matches(const bko_index* x, work_ctx* w, int max_tot_mm, int core_len, int core_delta, int max_slides,
+                               int align_strand, uint8_t* probe, int probe_len, int max_hits, int* p_inst,
+                               bkx_read_result* hits, int cur_max_iter, int max_nodes) {
+  int64_t sfx_len = (int64_t)x->concat_len;
+  int inst = 0, sloughed = 0;
+  char strand;
+  *p_inst = 0;
+  if (align_strand == BKX_STRAND_CRICK) { revcpl(probe, probe_len); strand = '-'; } else strand = '+';
+  int strands_left = align_strand;
+  do {
+    int cur_delta = core_delta, slides = 0, nodes = 0;
+    seen_reset(&w->seen);
+    for (int ofs = 0; slides < max_slides && ofs <= probe_len - core_len && cur_delta > core_len / 3 && nodes < max_nodes;
+         slides++, ofs += cur_delta) {                                                 /* :6748-6756 */
+      if (ofs + core_len + cur_delta > probe_len) cur_delta = probe_len - (ofs + core_len);
+      w->seeds++;
+      int64_t ti = bko_locate_first_exact(x, probe + ofs, core_len, 0, sfx_len - 1);
+      if (ti != 0) {
+        ti -= 1;
+        int iter = 0;
+        uint32_t num_copies = 0;
+        int first = 1;
+        while (!cur_max_iter || iter < cur_max_iter) {
+          if (nodes >= max_nodes) break;
+          if (!first) {
+            if (ti + 1 >= sfx_len || (int64_t)sa_at(x, ti + 1) + core_len > sfx_len) break;
+            if (iter == 100 && !num_copies) {                                          /* :6781-6788 */
+              int64_t last = bko_locate_last_exact(x, probe + ofs, core_len, ti - 1, sfx_len - 1);
+              num_copies = last > 0 ? (uint32_t)(1 + last - ti) : 0;
+              if (cur_max_iter && num_copies > (uint32_t)cur_max_iter) break;
+            }
+            if (cmp_probe(x, probe + ofs, core_len, sa_at(x, ti + 1)) != 0) break;
+            ti += 1;
+          }
+          first = 0;
+          uint64_t loci = sa_at(x, ti);
+          if (loci < (uint32_t)ofs) continue;                                         /* :6832 */
+          uint64_t left = loci - (uint64_t)ofs;
+          if (!probe_len || left + (uint32_t)probe_len > x->concat_len) continue;     /* :6840 (no entry test here) */
+          uint32_t key = (uint32_t)(1 + loci - (uint32_t)ofs);
+          if (seen_test_and_set(&w->seen, key)) continue;
+          nodes++;
+          iter++;
+          w->cands++;
+          const uint8_t* t = x->seq + left;
+          int mm = 0, i;
+          for (i = 0; i < probe_len; i++) {                                           /* :6878-6934: EOS ends the match */
+            uint8_t tb = t[i] & 0x0f, pb = probe[i] & 0x0f;
+            if (tb == BKX_BASE_EOS) break;
+            if (pb == tb) continue;
+            if (++mm > max_tot_mm) break;
+          }
+          if (i != probe_len) continue;
+          int at = -1;                                                                /* :6938-6959 */
+          if (inst) {
+            if (inst == max_hits) sloughed = 1;
+            int b;
+            for (b = 0; b < inst; b++)
+              if (hits[b].mismatches > mm) {
+                at = b;
+                int move = inst - b;
+                if (b + move >= max_hits) move = max_hits - 1 - b;   /* the last one falls off a full list */
+                if (move > 0) memmove(&hits[b + 1], &hits[b], sizeof(*hits) * (size_t)move);
+                break;
+              }
+            if (b == inst && inst < max_hits) at = inst;
+          } else at = 0;
+          if (at >= 0) {
+            const bkx_entry* he = map_entry(x, left);
+            bkx_read_result* h = &hits[at];
+            memset(h, 0, sizeof(*h));
+            h->strand = (uint8_t)strand;
+            h->chrom_id = he ? he->entry_id : 0;
+            h->match_loci = he ? (uint32_t)(left - he->start_ofs) : 0;
+            h->match_len = (uint16_t)probe_len;
+            h->mismatches = (uint8_t)mm;
+            if (inst < max_hits) inst += 1;
+            else max_tot_mm = hits[inst - 1].mismatches;                              /* :6980-6984 */
+          }
+        }
+      }
+      if (inst == max_hits && max_tot_mm == 0 && !sloughed) { strands_left = -1; break; }   /* :6988-6992 */
+    }
+    if (strands_left == -1) break;
+    if (strand == '+' && strands_left == BKX_STRAND_BOTH) {
+      revcpl(probe, probe_len);
+      strand = '-';
+      strands_left = BKX_STRAND_CRICK;
+    } else strands_left = -1;
+  } while (!(inst == max_hits && max_tot_mm == 0 && !sloughed) && strands_left != -1);
+  if (strand == '-') revcpl(probe, probe_len);
+  *p_inst = inst;
+  if (inst == 0) return 0;
+  return sloughed ? inst + 1 : inst;
+}
+
 static int align_reads(const bko_index* x, work_ctx* w, const bkx_align_params* p, int max_tot_mm, int core_len,
                        int core_delta, int max_slides, uint8_t* probe, int probe_len, int* inst, int* low,
                        int* nxt, bkx_read_result* hits) { /* SfxArrayV2.cpp:7666-7760 */
@@ -466,9 +565,15 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
   if (core_delta < core_len) core_delta = core_len;
   int inst = 0, low = 0, nxt = 0;
   memset(hits, 0, sizeof(*hits));
-  int hr = align_reads(x, w, p, max_tot_mm, core_len, core_delta, slides, seqbuf, len, &inst, &low, &nxt, hits);
+  int hr;
+  if (p->best_matches && p->ml_mode != BKX_ML_DEFAULT) {                                 /* -N, Aligner.cpp:9197-9218 */
+    hr = locate_best_matches(x, w, max_tot_mm, core_len, core_delta, slides, p->align_strand, seqbuf, len, p->max_ml_matches,
+                             &inst, hits, p->max_iter, p->max_ident_nodes);
+    hr = hr >= 1 ? BKX_HR_HITS : BKX_HR_NONE;
+  } else
+    hr = align_reads(x, w, p, max_tot_mm, core_len, core_delta, slides, seqbuf, len, &inst, &low, &nxt, hits);
   if (inst > p->max_ml_matches) inst = p->max_ml_matches + 1;                           /* :9241 */
-  if (p->clamp_max_ml && hr == BKX_HR_HITINSTS) { inst = p->max_ml_matches; hr = BKX_HR_HITS; } /* :9243 */
+  if ((p->clamp_max_ml || p->best_matches) && hr == BKX_HR_HITINSTS) { inst = p->max_ml_matches; hr = BKX_HR_HITS; } /* :9243 */
   out->hit_rslt = (uint8_t)hr;
   out->seeds = w->seeds;
   out->cands = w->cands;

@@ -625,10 +625,37 @@ def case_grammar():
         strip_log(os.path.join(tmp, "g1.log"), os.path.join(d, "g1.log"))
 
 
+def case_bestmatches():
+    """-N (best matches, CSfxArrayV3::LocateBestMatches): the -R<n> loci with the fewest mismatches from one un-staged pass,
+    behind every multi-loci mode that can be repeated (-r1 stats only, -r3 / -r4 clustering, -r5 all loci), on the lowcopy
+    genome (2..9-copy repeat families).  -T1 so that the -r5 record numbering is the read order."""
+    d = os.path.join(GOLD, "bestmatches")
+    os.makedirs(d, exist_ok=True)
+    low = os.path.join(GOLD, "lowcopy")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("lowcopy.sfx", "r100.fa", "deep.fa"):
+            with gzip.open(os.path.join(low, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        meta = {}
+        for tag, reads, args, out in (("n5_r5", "r100.fa", ["-s3", "-M0", "-r5", "-R5", "-N"], "n5_r5.csv"),
+                                      ("n5_r5sam", "r100.fa", ["-s3", "-M6", "-r5", "-R5", "-N"], "n5_r5.sam"),
+                                      ("n3_r5s8", "r100.fa", ["-s8", "-e2", "-M0", "-r5", "-R3", "-N"], "n3_r5s8.csv"),
+                                      ("n8_r5Q1", "r100.fa", ["-s5", "-M0", "-r5", "-R8", "-N", "-Q1"], "n8_r5Q1.csv"),
+                                      ("n2_r5s0", "r100.fa", ["-s0", "-M0", "-r5", "-R2", "-N"], "n2_r5s0.csv"),
+                                      ("n4_r1", "r100.fa", ["-s5", "-M0", "-r1", "-R4", "-N"], "n4_r1.csv"),
+                                      ("n5_r3", "deep.fa", ["-s3", "-M0", "-r3", "-R5", "-N"], "n5_r3.csv"),
+                                      ("n6_r4", "deep.fa", ["-s5", "-M0", "-r4", "-R6", "-N"], "n6_r4.csv")):
+            run(["align", "-I", "lowcopy.sfx", "-i", reads, "-T1", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [reads + ".gz"], "index": "lowcopy"}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -655,4 +682,6 @@ if __name__ == "__main__":
         case_simreads()
     if "grammar" in which:
         case_grammar()
+    if "bestmatches" in which:
+        case_bestmatches()
     print("fixtures written under", GOLD)
