@@ -40,6 +40,7 @@ constexpr int kGroup = 8;            // lanes per read
 struct KParams {
   int max_subs, mmd, max_ns, strand_mode, max_hits, min_core_len, slides_per100, max_iter, max_nodes;
   int ml_mode, clamp_ml;
+  int best;               // -N: LocateBestMatches instead of the staged AlignReads (general kernel only)
   int prefetch;           // fast kernel: prefetch the next core's prefix-table entry into L2 (1) or not (0)
   int scan_iters;         // fast kernel: cores a lane may run down per step looking for a non-empty bucket (0: one core per step)
   bkx_multi_hit* multi;   // -r5: max_hits slots per read of this launch, or nullptr
@@ -69,7 +70,7 @@ static __device__ __noinline__ bkx_read_result make_result(const DevIndex& I, co
     case BKX_HR_HITS:
       if (inst == 1 || P.ml_mode == BKX_ML_DEFAULT || P.ml_mode == BKX_ML_ALL) {  // unique, or every locus is wanted
         res.nar = BKX_NAR_ACCEPTED;
-        res.num_hits = (P.ml_mode == BKX_ML_ALL) ? (uint8_t)inst : 1;
+        res.num_hits = (P.ml_mode == BKX_ML_ALL) ? (uint8_t)min(inst, 255) : 1;   // beyond 255 loci: low_hit_instances has the count
         res.strand = hit_strand ? '-' : '+';
         res.chrom_id = __ldg(I.ent_id + hit_ent);
         res.match_loci = (uint32_t)(hit_p - __ldg(I.ent_start + hit_ent));
@@ -136,6 +137,9 @@ struct Grp {
   uint64_t hit_p;
   bkx_multi_hit* multi;   // this read's -r5 slots or nullptr
   uint32_t seeds, cands;
+  // -N (LocateBestMatches): the mismatch limit as tightened by a full list, "a locus was turned away from a full list"
+  int bm_max;
+  bool bm_sloughed;
 
   __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & kLaneMask; }
   template <typename T>
@@ -392,7 +396,7 @@ __device__ __forceinline__ void seen_insert(Grp<G>& c, const HashPool& hp, bool 
 // valid/cofs/sidx are lane-private.  capped => all lanes belong to one core whose interval ends at
 // hi_idx and iter_cnt counts its new candidates so far (the 100th-candidate probe and MaxIter cap
 // of SfxArrayV2.cpp:5857-5875 apply).  Returns the lane at which processing stopped (or -1).
-template <int G>
+template <int G, bool BEST>
 __device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, const HashPool& hp, Grp<G>& c, int s,
                                          int max_mm, bool valid, int cofs, uint64_t sidx, bool capped, int& iter_cnt,
                                          uint64_t hi_idx, bool& stop_core, bool& stop_strand, bool& stop_all) {
@@ -401,7 +405,12 @@ __device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, co
   bool ok = valid && loci >= (uint64_t)cofs;
   uint64_t p = loci - (uint64_t)cofs;
   int ent = -1;
-  if (ok) {
+  if (ok && BEST) {
+    // LocateBestMatches only asks for the window to end inside the concatenation (SfxArrayV2.cpp:6839-6841); a window that
+    // runs over a chromosome end is counted as a candidate and dies in the Hamming loop at the terminator
+    ok = p + (uint64_t)c.L <= I.n;
+    if (ok) ent = find_entry(I, p);
+  } else if (ok) {
     ent = find_entry(I, p);
     ok = ent >= 0 && (p + (uint64_t)c.L - 1) <= __ldg(I.ent_end + ent);
   }
@@ -441,6 +450,66 @@ __device__ __forceinline__ int walk_step(const DevIndex& I, const KParams& P, co
   int mm = 255;
   if (isnew) mm = hamming(I, c, s, p, max_mm);
   bool acc = isnew && mm <= max_mm;
+  if constexpr (BEST) {
+    // ---- -N: keep the max_hits loci with the fewest mismatches, equal ones in discovery order (SfxArrayV2.cpp:6936-6986).
+    // The candidates of this step are taken in lane order; lane 0 owns the list (this read's slots in global memory).
+    const int nnew = __popc(newm);
+    seen_insert(c, hp, isnew, key);
+    c.nodes += nnew;
+    iter_cnt += nnew;
+    c.cands += (uint32_t)nnew;
+    unsigned accm = c.ballot(acc && ent >= 0);
+    bkx_multi_hit h;
+    h.chrom_id = 0; h.match_loci = 0; h.match_len = (uint16_t)c.L; h.strand = s ? '-' : '+'; h.mismatches = (uint8_t)mm;
+    if (acc && ent >= 0) {
+      h.chrom_id = __ldg(I.ent_id + ent);
+      h.match_loci = (uint32_t)(p - __ldg(I.ent_start + ent));
+    }
+    while (accm) {
+      const int l = __ffs(accm) - 1;
+      accm &= accm - 1;
+      const int lmm = c.bcast(mm, l);
+      const uint32_t l_chrom = c.bcast(h.chrom_id, l), l_loci = c.bcast(h.match_loci, l);
+      const uint64_t l_p = c.bcast(p, l);
+      const int l_ent = c.bcast(ent, l);
+      if (lmm > c.bm_max) continue;                    // the tightened limit: its Hamming loop would have given up
+      if (c.inst == P.max_hits) c.bm_sloughed = true;
+      // position: behind every kept locus with at most this many mismatches; none if the list is full of such
+      int pos = -1;
+      if (c.multi) {
+        int at = 0;
+        if (c.gl == 0) {
+          at = c.inst;
+          for (int b = 0; b < c.inst; ++b)
+            if ((int)c.multi[b].mismatches > lmm) { at = b; break; }
+          if (at < P.max_hits) {
+            int last = min(c.inst, P.max_hits - 1);          // the last one falls off a full list
+            for (int b = last; b > at; --b) c.multi[b] = c.multi[b - 1];
+            bkx_multi_hit nh;
+            nh.chrom_id = l_chrom; nh.match_loci = l_loci; nh.match_len = (uint16_t)c.L; nh.strand = s ? '-' : '+';
+            nh.mismatches = (uint8_t)lmm;
+            c.multi[at] = nh;
+          }
+        }
+        at = c.bcast(at, 0);
+        pos = at < P.max_hits ? at : -1;
+      } else {
+        // no list wanted (-r1): only the number kept and the first of the best matter
+        pos = (c.inst == 0 || lmm < c.hit_mm) ? 0 : (c.inst < P.max_hits ? c.inst : -1);
+      }
+      if (pos >= 0) {
+        if (pos == 0) { c.hit_p = l_p; c.hit_ent = l_ent; c.hit_mm = lmm; c.hit_strand = s; }
+        if (c.inst < P.max_hits) c.inst += 1;
+        else if (c.multi) {   // inserted into a full list: the limit drops to the worst one kept
+          int worst = 0;
+          if (c.gl == 0) worst = (int)c.multi[c.inst - 1].mismatches;
+          c.bm_max = c.bcast(worst, 0);
+        }
+      }
+    }
+    c.sync();
+    return stop_lane;
+  }
   // ordered early exit: the (MaxHits+1)-th exact match ends the whole search (SfxArrayV2.cpp:6206-6214)
   unsigned zm = c.ballot(acc && mm == 0);
   if (zm) {
@@ -517,14 +586,21 @@ struct CoreLayout {
 };
 
 // One phase = LocateCoreMultiples(max_mm, CL, delta).  Returns tHRslt.
-template <int G>
+template <int G, bool BEST>
 __device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, const HashPool& hp, Grp<G>& c,
                                          int max_mm, int CL, int delta, int max_slides) {
-  if (c.inst > P.max_hits && c.low == 0) return BKX_HR_HITINSTS;
-  if (c.inst >= 1 && c.low == 0 && (c.nxt - c.low) < P.mmd) return BKX_HR_MMDELTA;
-  if (c.inst <= 0 || c.low < 0 || c.nxt < 0) {
+  constexpr bool best = BEST;   // -N: this one call is the whole search (LocateBestMatches, SfxArrayV2.cpp:6654-7019)
+  if (!best) {
+    if (c.inst > P.max_hits && c.low == 0) return BKX_HR_HITINSTS;
+    if (c.inst >= 1 && c.low == 0 && (c.nxt - c.low) < P.mmd) return BKX_HR_MMDELTA;
+    if (c.inst <= 0 || c.low < 0 || c.nxt < 0) {
+      c.inst = 0;
+      c.low = c.nxt = max_mm + P.mmd + 1;
+    }
+  } else {
     c.inst = 0;
-    c.low = c.nxt = max_mm + P.mmd + 1;
+    c.bm_max = max_mm;
+    c.bm_sloughed = false;
   }
   const int inst0 = c.inst, low0 = c.low, nxt0 = c.nxt;
   const CoreLayout lay(c.L, CL, delta, max_slides);
@@ -565,7 +641,7 @@ __device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, co
       int cores_done = lanes;  // cores of this strand/chunk whose LocateFirstExact the reference issues
       if (cmax == 0) {
         // nothing to walk
-      } else if (cmax <= 100) {
+      } else if (cmax <= 100 && !best) {
         // flattened: every interval is short enough that no cap can trigger
         int incl = (int)mycnt;
 #pragma unroll
@@ -594,7 +670,7 @@ __device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, co
           const uint64_t sidx = cf + (uint64_t)(e - c.pre[ci]);
           int iter_dummy = 0;
           bool sc = false;
-          int sl = walk_step(I, P, hp, c, s, max_mm, valid, co, sidx, false, iter_dummy, 0, sc, stop_strand, stop_all);
+          int sl = walk_step<G, BEST>(I, P, hp, c, s, max_mm, valid, co, sidx, false, iter_dummy, 0, sc, stop_strand, stop_all);
           if (stop_all || stop_strand) {
             cores_done = c.bcast(ci, sl < 0 ? 0 : sl) - lane0 + 1;
             break;
@@ -613,8 +689,11 @@ __device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, co
           const uint64_t hi_idx = cf + cc - 1;
           for (uint64_t e0 = 0; e0 < cc && !stop_core; e0 += G) {
             uint64_t e = e0 + (uint64_t)c.gl;
-            walk_step(I, P, hp, c, s, max_mm, e < cc, co, cf + e, true, iter_cnt, hi_idx, stop_core, stop_strand, stop_all);
+            walk_step<G, BEST>(I, P, hp, c, s, best ? c.bm_max : max_mm, e < cc, co, cf + e, true, iter_cnt, hi_idx, stop_core,
+                               stop_strand, stop_all);
           }
+          // -N: a full list of exact matches that turned nothing away cannot improve (SfxArrayV2.cpp:6988-6992)
+          if (best && c.inst == P.max_hits && c.bm_max == 0 && !c.bm_sloughed) stop_all = true;
           if (stop_all || stop_strand) cores_done = ci - lane0 + 1;
         }
       }
@@ -623,6 +702,7 @@ __device__ __forceinline__ int run_phase(const DevIndex& I, const KParams& P, co
     }
   }
   hash_release(c, hp);
+  if (best) return c.inst >= 1 ? BKX_HR_HITS : BKX_HR_NONE;   // Aligner.cpp:9211-9217
   // return-code logic, SfxArrayV2.cpp:6237-6261
   if (c.low == low0 && c.inst == inst0) {
     if (nxt0 > c.nxt) return (c.nxt - c.low) < P.mmd ? BKX_HR_MMDELTA : BKX_HR_RMMDELTA;

@@ -813,8 +813,9 @@ static int check_params(const bkx_align_params* p, KParams* k) {
     if (p->max_ml_matches < 2 || p->max_ml_matches > 500)  // cMaxMultiHits, Aligner.h:62
       return fail(BKX_ERR_PARAM, "max_ml_matches %d out of range 2..500", p->max_ml_matches);
   } else if (p->ml_mode == BKX_ML_ALL || p->ml_mode == BKX_ML_UNIQ || p->ml_mode == BKX_ML_MULTI) {
-    if (p->max_ml_matches < 2 || p->max_ml_matches > 64)  // the reference allows 500 (100000 with -r5); the per-read slots here 64
-      return fail(BKX_ERR_UNSUPPORTED, "max_ml_matches %d with -r3..5: 2..64 loci per read are supported", p->max_ml_matches);
+    if (p->max_ml_matches < 2 || p->max_ml_matches > 500)  // cMaxMultiHits, Aligner.h:62 (-r5 alone goes on to cMaxAllHits = 100000
+      // in the reference, which writes loci out as it finds them; here every read owns max_ml_matches slots of 12 bytes)
+      return fail(BKX_ERR_UNSUPPORTED, "max_ml_matches %d with -r3..5: 2..500 loci per read are supported", p->max_ml_matches);
   } else {
     return fail(BKX_ERR_UNSUPPORTED, "ml_mode %d: -r2 picks a locus with libc rand() in the reference and is not reproducible", p->ml_mode);
   }
@@ -826,6 +827,8 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   k->max_hits = p->max_ml_matches; k->min_core_len = p->min_core_len; k->slides_per100 = p->max_num_slides;
   k->max_iter = p->max_iter; k->max_nodes = p->max_ident_nodes;
   k->ml_mode = p->ml_mode; k->clamp_ml = p->clamp_max_ml ? 1 : 0;
+  k->best = (p->best_matches && p->ml_mode != BKX_ML_DEFAULT) ? 1 : 0;   // kanga.cpp:666, 686: only with a multi-loci mode
+  if (k->best) k->clamp_ml = 1;                                           // kanga.cpp:695-696
   k->multi = nullptr;
   k->prefetch = 0;   // measured: 31.5 ms without, 33.9 ms with (configs[1])
   if (const char* ev = getenv("BKX_PREFETCH")) k->prefetch = atoi(ev) != 0;   // tuning hook
@@ -909,7 +912,7 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
                        int W, bkx_read_result* d_out, bkx_align_stats* d_stats, int si, uint32_t* d_hard,
                        cudaStream_t st, const Packed2Src& p2 = Packed2Src()) {
   unsigned int* cur = x->d_cursor[si];
-  if (getenv("BKX_NO_FAST")) {
+  if (getenv("BKX_NO_FAST") || k.best) {   // -N: a different search (LocateBestMatches), built in the general kernel only
     CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, nullptr, nullptr, x->grid, st));
     x->launches += 1;
     return BKX_OK;
@@ -1132,6 +1135,7 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const HostReads& 
     uint32_t cnt = std::min(ramp, std::max(kMinSlice, left / 2));
     if (cnt > left || left - cnt < kMinSlice / 2) cnt = left;
     ramp = std::min<uint64_t>(kMaxSlice, (uint64_t)ramp * 2);
+    if (multi) cnt = std::min<uint32_t>(cnt, std::max<uint32_t>(1024u, (1u << 27) / (uint32_t)k.max_hits));  // <= 1.6 GB of loci slots per slice
     uint64_t nb = 0, max_len = 0;
     // longest read of this slice (overlaps with the GPU work of the previous slices)
     bool mono = measure(start, cnt, nb, max_len);

@@ -432,7 +432,7 @@ static cudaError_t ensure_smem(K kernel, size_t smem, SmemOptIn& cfg) {
   }
   return cudaSuccess;
 }
-static SmemOptIn g_smem_general, g_smem_fast, g_smem_fast_mlx, g_smem_fast_scan, g_smem_fast_mlx_scan, g_smem_rescue;
+static SmemOptIn g_smem_general, g_smem_general_best, g_smem_fast, g_smem_fast_mlx, g_smem_fast_scan, g_smem_fast_mlx_scan, g_smem_rescue;
 
 __host__ __device__ inline size_t group_smem_bytes(int W) {
   size_t per = (size_t)W * 8 * 2 + (size_t)W * 4 * 2 + kSeenCap * 4 + (kGroup + 2) * 4;
@@ -492,6 +492,7 @@ __device__ __forceinline__ void stats_flush(const BlockStats& bs, bkx_align_stat
 
 // Per-read driver: ProcCoredApprox body (Aligner.cpp:9027-9504) + AlignReads phase loop
 // (SfxArrayV2.cpp:7666-7760).  One kGroup-lane group per read; reads are claimed from a global cursor.
+template <bool BEST>
 __global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
@@ -581,15 +582,20 @@ __global__ void __launch_bounds__(kBlockThreads, 3) align_reads_kernel(
       c.inst = 0; c.low = 0; c.nxt = 0;
       c.hit_strand = 0; c.hit_ent = -1; c.hit_mm = 0; c.hit_p = 0;
       int hr = 0, allow = 0;
-      if (max_tot_mm > 0) {
-        for (allow = 0; allow <= max_tot_mm; ++allow) {
-          int cl = L / (allow + P.mmd);
-          if (cl <= core_len) break;
-          hr = run_phase<G>(I, P, hp, c, allow, cl, cl, slides);
-          if (hr != 0) break;
+      if constexpr (BEST) {   // -N: one un-staged pass that keeps the best loci (Aligner.cpp:9197-9218); LowMMCnt / NxtLowMMCnt stay 0
+        hr = run_phase<G, true>(I, P, hp, c, max_tot_mm, core_len, core_delta, slides);
+        c.low = 0; c.nxt = 0;
+      } else {
+        if (max_tot_mm > 0) {
+          for (allow = 0; allow <= max_tot_mm; ++allow) {
+            int cl = L / (allow + P.mmd);
+            if (cl <= core_len) break;
+            hr = run_phase<G, false>(I, P, hp, c, allow, cl, cl, slides);
+            if (hr != 0) break;
+          }
         }
+        if (hr == 0 && allow <= max_tot_mm) hr = run_phase<G, false>(I, P, hp, c, max_tot_mm, core_len, core_delta, slides);
       }
-      if (hr == 0 && allow <= max_tot_mm) hr = run_phase<G>(I, P, hp, c, max_tot_mm, core_len, core_delta, slides);
       res = make_result(I, P, hr, c.inst, c.low, c.nxt, L, c.hit_strand, c.hit_ent, c.hit_p, c.hit_mm, c.seeds, c.cands);
     }
     if (c.gl == 0) {
@@ -606,21 +612,26 @@ cudaError_t launch_align(const DevIndex& I, const KParams& P, const uint8_t* bas
                          uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats, unsigned int* cursor,
                          const HashPool& hp, const uint32_t* ids, const unsigned int* n_ids, int grid, cudaStream_t st) {
   size_t smem = align_smem_bytes(W);
-  cudaError_t e = ensure_smem(align_reads_kernel, smem, g_smem_general);
+  cudaError_t e = P.best ? ensure_smem(align_reads_kernel<true>, smem, g_smem_general_best)
+                         : ensure_smem(align_reads_kernel<false>, smem, g_smem_general);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(cursor, 0, sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
-  align_reads_kernel<<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hp, ids,
-                                                        n_ids);
+  if (P.best)
+    align_reads_kernel<true><<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hp, ids, n_ids);
+  else
+    align_reads_kernel<false><<<grid, kBlockThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hp, ids, n_ids);
   return cudaGetLastError();
 }
 
 int align_blocks_per_sm(int W) {
   size_t smem = align_smem_bytes(W);
-  ensure_smem(align_reads_kernel, smem, g_smem_general);
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_reads_kernel, kBlockThreads, smem);
-  return nb;
+  ensure_smem(align_reads_kernel<false>, smem, g_smem_general);
+  ensure_smem(align_reads_kernel<true>, smem, g_smem_general_best);
+  int nb = 0, nb2 = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, align_reads_kernel<false>, kBlockThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, align_reads_kernel<true>, kBlockThreads, smem);
+  return nb < nb2 ? nb : nb2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -740,7 +751,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     res.hit_rslt = (uint8_t)hr;
     if (hr == BKX_HR_HITS && !multi) {
       res.nar = BKX_NAR_ACCEPTED;
-      res.num_hits = (uint8_t)nh;
+      res.num_hits = (uint8_t)min(nh, 255);   // -r5 beyond 255 loci: low_hit_instances holds the count
       res.strand = hit_strand ? '-' : '+';
       res.chrom_id = __ldg(I.ent_id + hit_ent);
       res.match_loci = (uint32_t)(hit_p - __ldg(I.ent_start + hit_ent));

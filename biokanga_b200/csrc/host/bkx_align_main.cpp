@@ -170,6 +170,7 @@ struct Opts {
       qmode = 3;
   int ml_mode = 0, max_ml = 0;   // -r / -R (kanga.cpp:482-486, 667-696); max_ml 0 = not given
   bool clamp_ml = false;         // -X
+  bool best_matches = false;     // -N: the -R loci with the fewest mismatches from one un-staged pass (only with -r; implies -X)
   bool pair_strand = false, pe_circ = false;
   int sample_nth = 1;            // -#: sample every Nth raw read or read pair
   int pcr_primer = 0;            // -6: align with -s + this many substitutions, then correct 5' primer artefacts back to -s
@@ -645,7 +646,7 @@ static int parse(int argc0, char** argv0, Opts& o) {
       case '6': o.pcr_primer = iv; break;
       case 'b': unsupported.push_back("-b bisulfite"); break;
       case 'C': unsupported.push_back("-C colorspace"); break;
-      case 'N': unsupported.push_back("-N best matches"); break;
+      case 'N': o.best_matches = true; break;
       case 'X': o.clamp_ml = true; break;
       case '5': o.constraints_file = v; break;
       case 'O': o.stats_file = v; break;
@@ -658,7 +659,7 @@ static int parse(int argc0, char** argv0, Opts& o) {
         printf("\nbiokanga align Version 4.4.2 (bkx B200 path)\n");
         return 1;
       case 'h':
-        printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -M0..6 -g -t -U -d -D -E "
+        printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -N -M0..6 -g -t -U -d -D -E "
                "-y -Y -l -L -# -5 -k -6 -x -Z -z -j -J -O -4 -T -i -u -I -o -F -q -w -W [--gpus N], the reference's long option names, "
                "and @file parameter files\n");
         return 1;
@@ -694,7 +695,8 @@ static int parse(int argc0, char** argv0, Opts& o) {
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
     if (o.max_ml == 0) o.max_ml = 5;  // cDfltMaxMultiHits
-    const int lim = o.ml_mode >= 3 ? 64 : 500;  // the reference takes 500 (100000 with -r5); the per-read slots here hold 64
+    const int lim = 500;  // cMaxMultiHits; -r5 alone goes on to 100000 in the reference (it writes loci out as it finds them),
+                          // here every read owns -R slots
     if (o.max_ml < 2 || o.max_ml > lim) { fprintf(stderr, "Error: multiple aligned reads '-R%d' specified outside of range 2..%d\n", o.max_ml, lim); return -1; }
     if (o.ml_mode == 5) { o.none_file.clear(); o.multi_file.clear(); }   // kanga.cpp:1045-1069: -j / -J are dropped under -r5
     if (o.ml_mode == 5 && o.fmt == 6 && (!o.excl.empty() || !o.incl.empty())) {
@@ -710,9 +712,11 @@ static int parse(int argc0, char** argv0, Opts& o) {
       fprintf(stderr, "Error: '-r5' is only reported as -M0, -M4, -M5 or -M6\n");
       return -1;
     }
+    if (o.best_matches) o.clamp_ml = true;   // kanga.cpp:695-696
   } else {
     o.max_ml = 1;
     o.clamp_ml = false;  // kanga.cpp:691-694: -X only counts together with -R
+    o.best_matches = false;   // kanga.cpp:666, 686: -N is only read together with a multi-loci mode
   }
   return 0;
 }
@@ -1905,6 +1909,7 @@ int main(int argc, char** argv) {
   const int align_subs = o.pcr_primer > 0 ? std::min(o.max_subs + o.pcr_primer, 15) : o.max_subs;   // m_InitalAlignSubs, Aligner.cpp:208-213
   P.max_subs = align_subs; P.min_edit_dist = o.edit_delta; P.max_ns = o.max_ns; P.align_strand = o.strand;
   P.ml_mode = o.ml_mode; P.max_ml_matches = o.max_ml; P.clamp_max_ml = o.clamp_ml ? 1 : 0;
+  P.best_matches = o.best_matches ? 1 : 0;
 
   std::vector<bkx_entry> ents(info.num_entries + 1);
   for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
@@ -2043,7 +2048,7 @@ int main(int argc, char** argv) {
     for (uint32_t i = 0; i < n; ++i) {
       if (res[i].nar != BKX_NAR_ACCEPTED) continue;
       int kept = 0;
-      for (int h = 0; h < res[i].num_hits; ++h) kept += r5_keep[multi[(size_t)i * (size_t)o.max_ml + (size_t)h].chrom_id];
+      for (int h = 0; h < res[i].low_hit_instances; ++h) kept += r5_keep[multi[(size_t)i * (size_t)o.max_ml + (size_t)h].chrom_id];
       if (!kept) continue;
       ++S.tot_accepted_aligned;
       S.tot_loci_aligned += (uint64_t)kept;
@@ -2073,6 +2078,7 @@ int main(int argc, char** argv) {
          (int)S.tot_accepted_multi, (int)(S.tot_loci_aligned - S.tot_accepted_unique));
     ResVec rec;
     rec.reserve((size_t)S.tot_loci_aligned + 16);
+    std::vector<int> kept((size_t)std::max(1, o.max_ml));
     for (uint32_t i = 0; i < n; ++i) {
       const bkx_read_result& r = res[i];
       if (r.nar == BKX_NAR_ACCEPTED) {
@@ -2081,8 +2087,8 @@ int main(int argc, char** argv) {
         // a kept FIRST locus leaves the cursor behind, the following kept loci overwrite it, and the tail of the reported
         // list (its length is the number of kept loci) is whatever the slots held before -- a repeated or even a filtered
         // locus, which FiltByChroms then removes as eNARChromFilt.  Reproduced by running the same compaction.
-        int kept[64], nk = 0;
-        const int nh = std::min<int>(r.num_hits, 64);
+        int nk = 0;
+        const int nh = std::min<int>(r.low_hit_instances, o.max_ml);
         for (int h = 0; h < nh; ++h) kept[h] = h;
         if (r5_keep.empty()) nk = nh;
         else

@@ -59,7 +59,7 @@ enum { BKX_PMODE_DEFAULT = 0, BKX_PMODE_MORESENS = 1, BKX_PMODE_ULTRASENS = 2, B
 
 /* ---- etMLMode: biokanga/Aligner.h:224-231.  Built: DEFAULT (max_ml_matches must be 1), DIST ("-r1", stats only:
  * reads with 2..max_ml_matches equally good loci are reported eNARMultiAlign with their exact LowHitInstances,
- * Aligner.cpp:9328-9400), ALL ("-r5": every one of up to max_ml_matches <= 64 equally good loci is returned, through
+ * Aligner.cpp:9328-9400), ALL ("-r5": every one of up to max_ml_matches <= 500 equally good loci is returned, through
  * bkx_align_reads_multi) and UNIQ / MULTI ("-r3" / "-r4": the same call returns the loci, records of multi-loci reads
  * stay eNARMultiAlign until bkx_assign_multi_matches picks a locus by clustering).  RAND uses libc rand() in the
  * reference and cannot be reproduced -- rejected with BKX_ERR_UNSUPPORTED. */
@@ -121,7 +121,7 @@ typedef struct bkx_read_result {
   uint8_t nar;                /* BKX_NAR_*                                   */
   uint8_t hit_rslt;           /* BKX_HR_* returned by AlignReads              */
   uint8_t strand;             /* '+', '-', '?' or 0                           */
-  uint8_t num_hits;           /* tsReadHit::NumHits                           */
+  uint8_t num_hits;           /* tsReadHit::NumHits (-r5: loci returned, saturating at 255 -- low_hit_instances has the count) */
   int8_t low_mm;              /* tsReadHit::LowMMCnt                          */
   int8_t nxt_low_mm;          /* tsReadHit::NxtLowMMCnt                       */
   int16_t low_hit_instances;  /* tsReadHit::LowHitInstances (clamped MaxML+1) */

@@ -588,7 +588,7 @@ static void proc_read(const bko_index* x, work_ctx* w, const bkx_align_params* p
       if (inst == 1) st->tot_accepted_unique++; else st->tot_accepted_multi++;
       if (inst == 1 || p->ml_mode == BKX_ML_DEFAULT || p->ml_mode == BKX_ML_ALL) {  /* unique, or every locus is wanted */
         out->nar = BKX_NAR_ACCEPTED;
-        out->num_hits = (p->ml_mode == BKX_ML_ALL) ? (uint8_t)inst : 1;  /* -r5: every hit is reported (:9336-9352) */
+        out->num_hits = (p->ml_mode == BKX_ML_ALL) ? (uint8_t)(inst > 255 ? 255 : inst) : 1;  /* -r5: every hit is reported (:9336-9352) */
         out->strand = hits[0].strand;
         out->chrom_id = hits[0].chrom_id;
         out->match_loci = hits[0].match_loci;
@@ -664,7 +664,7 @@ static void* thr_main(void* a_) {
       if (a->multi) {  /* -r5: the pMultiHits list WriteHitLoci walks */
         bkx_multi_hit* m = a->multi + (size_t)i * (size_t)a->p->max_ml_matches;
         memset(m, 0, (size_t)a->p->max_ml_matches * sizeof(*m));
-        int nh = a->out[i].nar == BKX_NAR_ACCEPTED ? a->out[i].num_hits
+        int nh = a->out[i].nar == BKX_NAR_ACCEPTED ? (a->p->ml_mode == BKX_ML_ALL ? a->out[i].low_hit_instances : a->out[i].num_hits)
                  : (a->out[i].nar == BKX_NAR_MULTIALIGN && a->out[i].hit_rslt == BKX_HR_HITS) ? a->out[i].low_hit_instances : 0;
         if (nh > 0)
           for (int h = 0; h < nh && h < a->p->max_ml_matches; h++) {

@@ -652,10 +652,37 @@ def case_bestmatches():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_manyloci():
+    """-R beyond a few loci (the reference takes up to 500 with -r1/-r3/-r4, more with -r5) on the `repeats` genome, whose
+    reads from the 400-copy and 3000-copy units carry hundreds of equally good loci: -r5 with and without -X, -r4, and -N."""
+    d = os.path.join(GOLD, "manyloci")
+    os.makedirs(d, exist_ok=True)
+    rep = os.path.join(GOLD, "repeats")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("repeats.sfx", "r100.fa", "r60.fa"):
+            with gzip.open(os.path.join(rep, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        recs = [">" + x for x in open(os.path.join(tmp, "r60.fa")).read().split(">")[1:]]
+        open(os.path.join(tmp, "r60a.fa"), "w").write("".join(recs[:400]))     # keeps the -r5 outputs small
+        gz(os.path.join(tmp, "r60a.fa"), os.path.join(d, "r60a.fa.gz"))
+        meta = {}
+        # 60 bp reads inside the 64-base unit have ~2850 exact loci, inside the 90-base unit dozens to hundreds within -s5
+        for tag, reads, args, out in (("r5_R300X", "r60a.fa", ["-s5", "-M0", "-r5", "-R300", "-X"], "r5_R300X.csv"),
+                                      ("r5_R500", "r60a.fa", ["-s5", "-M0", "-r5", "-R500"], "r5_R500.csv"),
+                                      ("r5_R100N", "r60a.fa", ["-s5", "-M0", "-r5", "-R100", "-N"], "r5_R100N.csv"),
+                                      ("r4_R200X", "r60a.fa", ["-s5", "-M0", "-r4", "-R200", "-X"], "r4_R200X.csv"),
+                                      ("r1_R500", "r60a.fa", ["-s5", "-M0", "-r1", "-R500"], "r1_R500.csv")):
+            run(["align", "-I", "repeats.sfx", "-i", reads, "-T1", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [reads + ".gz"], "index": "repeats", "reads_dir": "manyloci"}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches", "manyloci"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -684,4 +711,6 @@ if __name__ == "__main__":
         case_grammar()
     if "bestmatches" in which:
         case_bestmatches()
+    if "manyloci" in which:
+        case_manyloci()
     print("fixtures written under", GOLD)

@@ -294,6 +294,43 @@ def test_cli_parameter_file_long_options_and_wildcards_match_reference(golden_di
     assert r.returncode != 0 and "Unable to open options file" in r.stdout
 
 
+BEST_TAGS = ["n5_r5", "n5_r5sam", "n3_r5s8", "n8_r5Q1", "n2_r5s0", "n4_r1", "n5_r3", "n6_r4"]
+
+
+@pytest.mark.parametrize("tag", BEST_TAGS)
+def test_cli_best_matches_match_reference(tag, golden_dir, tmp_path):
+    """-N (CSfxArrayV3::LocateBestMatches, SfxArrayV2.cpp:6654-7019): the -R<n> loci with the fewest mismatches from one
+    un-staged pass, behind -r1 (distribution only), -r3 / -r4 (clustering) and -r5 (every locus a record, numbered in read
+    order: compared line for line); -s0, -e2, -Q1 among the runs."""
+    test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="bestmatches")
+    import json
+    run = json.load(open(os.path.join(gu.GOLD, "bestmatches", "runs.json")))[tag]
+    if "-r5" in run["args"] and run["out"].endswith(".csv"):
+        ours = {ln.split(",", 1)[0]: ln for ln in _lines(tmp_path / run["out"])}
+        ref = {ln.split(",", 1)[0]: ln for ln in _lines(os.path.join(gu.GOLD, "bestmatches", run["out"] + ".gz"))}
+        assert ours == ref
+
+
+MANY_TAGS = ["r5_R300X", "r5_R500", "r5_R100N", "r4_R200X", "r1_R500"]
+
+
+@pytest.mark.parametrize("tag", MANY_TAGS)
+def test_cli_hundreds_of_loci_per_read_match_reference(tag, golden_dir, tmp_path):
+    """-R up to the reference's 500 (cMaxMultiHits) behind -r1 / -r4 / -r5, with -X and -N: 60 bp reads inside the 64-base unit
+    of the `repeats` genome carry ~2850 equally good loci, the ones inside the 90-base unit dozens to hundreds."""
+    import json
+    fdir = os.path.join(gu.GOLD, "manyloci")
+    run = json.load(open(os.path.join(fdir, "runs.json")))[tag]
+    sfx = gu.sfx_path("repeats", golden_dir)
+    subprocess.run([CLI, "align", "-I", sfx, "-i", os.path.join(fdir, run["reads"][0])] + run["args"] + ["-o", run["out"], "-F", "o.log"],
+                   check=True, stdout=subprocess.DEVNULL, cwd=tmp_path)
+    ours, ref = _lines(tmp_path / run["out"]), _lines(os.path.join(fdir, run["out"] + ".gz"))
+    if "-r5" in run["args"]:   # numbered in read order: line for line
+        assert {ln.split(",", 1)[0]: ln for ln in ours} == {ln.split(",", 1)[0]: ln for ln in ref}
+    assert sorted(ours) == sorted(ref)
+    assert summary_block(tmp_path / "o.log") == open(os.path.join(fdir, tag + ".log")).read().splitlines()
+
+
 def _bgzf_blocks(raw):
     import struct
     o, out = 0, []

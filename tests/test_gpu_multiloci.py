@@ -94,3 +94,33 @@ def test_distribution_mode_matches_oracle(lowcopy, limit, clamp):
         assert np.array_equal(got[f], exp[f]), f
     assert gst.as_dict() == est.as_dict()
     assert gst.tot_accepted_multi > 100 and gst.tot_loci_aligned > gst.tot_accepted_aligned
+
+
+@pytest.mark.parametrize("mode,limit,max_subs,mmd,strand", [(5, 5, 3, 1, 0), (5, 3, 8, 2, 0), (5, 8, 5, 1, 1), (5, 2, 0, 1, 0), (5, 64, 10, 1, 0),
+                                                            (3, 5, 3, 1, 0), (4, 6, 5, 1, 2), (1, 4, 5, 1, 0), (1, 2, 0, 1, 0), (1, 300, 8, 1, 0)])
+def test_best_matches_match_oracle(lowcopy, mode, limit, max_subs, mmd, strand):
+    """-N (best_matches = 1, CSfxArrayV3::LocateBestMatches): one un-staged pass that keeps the `limit` loci with the fewest
+    mismatches, equal ones in discovery order -- records, hit lists (where the mode returns them), seeds / cands and stats
+    against the oracle, whose restatement is pinned on eight reference runs (tests/golden/bestmatches)."""
+    gidx, oidx, bases, offs = lowcopy
+    kw = dict(max_subs=max_subs, min_edit_dist=mmd, ml_mode=mode, max_ml_matches=limit, best_matches=1, align_strand=strand)
+    if mode == 1:
+        got, gst = gidx.align(gidx.default_params(0, **kw), bases, offs)
+        exp, est = oidx.align(oidx.default_params(0, **kw), bases, offs, nthreads=4)
+    else:
+        got, gm, gst = gidx.align_multi(gidx.default_params(0, **kw), bases, offs)
+        exp, em, est = oidx.align_multi(oidx.default_params(0, **kw), bases, offs, nthreads=4)
+    for f in abi.RESULT_DTYPE.names:
+        bad = np.nonzero(got[f] != exp[f])[0]
+        assert len(bad) == 0, (f, int(bad[0]), got[bad[0]], exp[bad[0]])
+    assert gst.as_dict() == est.as_dict()
+    if mode != 1:
+        hits = got["hit_rslt"] == 1
+        cnt = np.where(hits & (got["nar"] == abi.NAR_ACCEPTED), np.maximum(got["num_hits"], 1),
+                       np.where(hits & (got["nar"] == abi.NAR_MULTIALIGN), got["low_hit_instances"], 0))
+        valid = np.arange(limit)[None, :] < cnt[:, None]
+        assert gm[valid].tobytes() == em[valid].tobytes()
+        # the kept loci come sorted by mismatches
+        mmv = np.where(valid, gm["mismatches"].astype(np.int32), 255)
+        assert bool((np.diff(mmv, axis=1) >= 0).all())
+    assert int((got["hit_rslt"] == 1).sum()) > 1000

@@ -91,6 +91,16 @@ def test_host_parameter_file_long_options_and_wildcards_match_reference(cli, gol
     g.test_cli_parameter_file_long_options_and_wildcards_match_reference(golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", g.BEST_TAGS)
+def test_host_best_matches_match_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_best_matches_match_reference(tag, golden_dir, tmp_path)
+
+
+@pytest.mark.parametrize("tag", g.MANY_TAGS)
+def test_host_hundreds_of_loci_per_read_match_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_hundreds_of_loci_per_read_match_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag,args,out", g.BAM_RUNS)
 def test_host_bam_and_bai_match_reference(tag, args, out, cli, golden_dir, tmp_path):
     g.test_cli_bam_and_bai_match_reference(tag, args, out, golden_dir, tmp_path)
