@@ -460,9 +460,9 @@ __device__ __forceinline__ void stats_add(BlockStats& bs, const bkx_read_result&
   if (res.nar == BKX_NAR_MULTIALIGN && res.hit_rslt == BKX_HR_HITS) {
     atomicAdd(&bs.multi, 1u);
     atomicAdd(&bs.multi_loci, (unsigned int)res.low_hit_instances);
-  } else if (res.nar == BKX_NAR_ACCEPTED && res.num_hits > 1) {
+  } else if (res.nar == BKX_NAR_ACCEPTED && res.num_hits > 1) {   // -r5: the count is in low_hit_instances (num_hits stops at 255)
     atomicAdd(&bs.acc_multi, 1u);
-    atomicAdd(&bs.multi_loci, (unsigned int)res.num_hits);
+    atomicAdd(&bs.multi_loci, (unsigned int)res.low_hit_instances);
   }
 }
 
@@ -1191,12 +1191,18 @@ __device__ __forceinline__ int pe_insert_size(const bkx_pe_params& pe, uint8_t s
 
 struct PEBlock { unsigned int v[8]; };
 
+constexpr int kPairHistBins = 4096;
+
 __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict__ res, uint32_t n_pairs,
                                   bkx_pe_stats* __restrict__ stats, uint32_t* __restrict__ len_dist,
                                   uint32_t* __restrict__ orphan_list, unsigned int* __restrict__ n_orphans,
                                   const uint8_t* __restrict__ keep) {
   __shared__ PEBlock pb;
+  // insert lengths concentrate on a few hundred values: counted per block in shared memory and added to the global
+  // histogram once per block (one global atomic per accepted pair on those few addresses was what the kernel waited for)
+  __shared__ unsigned int sh_hist[kPairHistBins];
   if (threadIdx.x < 8) pb.v[threadIdx.x] = 0;
+  if (len_dist) for (int k = threadIdx.x; k < kPairHistBins; k += blockDim.x) sh_hist[k] = 0;
   __syncthreads();
   enum { UNAL = 0, ACCP = 1, ACCSE = 2, PPAIRED = 3, PUNP = 4, FILT = 5, UNDER = 6, OVER = 7 };
   const int mode = pe.pe_proc;
@@ -1248,7 +1254,7 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
       if (frag > 0) {
         f.flags |= BKX_FLG_PE_ALIGNED;
         r.flags |= BKX_FLG_PE_ALIGNED;
-        if (len_dist) atomicAdd(len_dist + frag, 1u);
+        if (len_dist) { if (frag < kPairHistBins) atomicAdd(&sh_hist[frag], 1u); else atomicAdd(len_dist + frag, 1u); }
         ++cnt[ACCP];
         done = true;
       } else {
@@ -1313,6 +1319,9 @@ __global__ void pair_reads_kernel(bkx_pe_params pe, bkx_read_result* __restrict_
   for (int k = 0; k < 8; ++k)
     if (cnt[k]) atomicAdd(&pb.v[k], cnt[k]);
   __syncthreads();
+  if (len_dist)
+    for (int k = threadIdx.x; k < kPairHistBins; k += blockDim.x)
+      if (sh_hist[k]) atomicAdd(len_dist + k, sh_hist[k]);
   if (threadIdx.x == 0 && stats) {
     atomicAdd((unsigned long long*)&stats->unaligned_pairs, (unsigned long long)pb.v[UNAL]);
     atomicAdd((unsigned long long*)&stats->accepted_num_paired, (unsigned long long)pb.v[ACCP]);

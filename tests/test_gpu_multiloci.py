@@ -77,7 +77,7 @@ def test_all_loci_mode_needs_its_own_call(lowcopy):
     with pytest.raises(bkx.BkxError):
         gidx.align(gidx.default_params(0, ml_mode=5, max_ml_matches=5), bases, offs)
     with pytest.raises(bkx.BkxError):
-        gidx.align_multi(gidx.default_params(0, ml_mode=5, max_ml_matches=100), bases, offs)
+        gidx.align_multi(gidx.default_params(0, ml_mode=5, max_ml_matches=501), bases, offs)
     with pytest.raises(bkx.BkxError):
         gidx.align(gidx.default_params(0, ml_mode=3, max_ml_matches=5), bases, offs)
     with pytest.raises(bkx.BkxError):
@@ -124,3 +124,31 @@ def test_best_matches_match_oracle(lowcopy, mode, limit, max_subs, mmd, strand):
         mmv = np.where(valid, gm["mismatches"].astype(np.int32), 255)
         assert bool((np.diff(mmv, axis=1) >= 0).all())
     assert int((got["hit_rslt"] == 1).sum()) > 1000
+
+
+@pytest.mark.parametrize("mode,limit,clamp,best,max_subs", [(5, 300, 1, 0, 5), (5, 500, 0, 0, 5), (5, 100, 0, 1, 5), (4, 200, 1, 0, 5),
+                                                            (1, 500, 0, 0, 5), (5, 64, 1, 0, 5)])
+def test_hundreds_of_loci_match_oracle(golden_dir, mode, limit, clamp, best, max_subs):
+    """-R up to 500 on the `repeats` genome: 60 bp reads with dozens to ~2850 equally good loci (tests/golden/manyloci)."""
+    import os
+    sfx = gu.sfx_path("repeats", golden_dir)
+    gidx, oidx = bkx.Index.open(sfx), po.OracleIndex(sfx)
+    names, bases, offs = po.read_fasta_reads(os.path.join(gu.GOLD, "manyloci", "r60a.fa.gz"))
+    kw = dict(max_subs=max_subs, ml_mode=mode, max_ml_matches=limit, clamp_max_ml=clamp, best_matches=best)
+    if mode == 1:
+        got, gst = gidx.align(gidx.default_params(0, **kw), bases, offs)
+        exp, est = oidx.align(oidx.default_params(0, **kw), bases, offs, nthreads=4)
+    else:
+        got, gm, gst = gidx.align_multi(gidx.default_params(0, **kw), bases, offs)
+        exp, em, est = oidx.align_multi(oidx.default_params(0, **kw), bases, offs, nthreads=4)
+    for f in abi.RESULT_DTYPE.names:
+        bad = np.nonzero(got[f] != exp[f])[0]
+        assert len(bad) == 0, (f, len(bad), int(bad[0]), names[int(bad[0])], got[bad[0]], exp[bad[0]])
+    assert gst.as_dict() == est.as_dict()
+    if mode != 1:
+        hits = got["hit_rslt"] == 1
+        cnt = np.where(hits, got["low_hit_instances"], 0)
+        valid = np.arange(limit)[None, :] < cnt[:, None]
+        assert gm[valid].tobytes() == em[valid].tobytes()
+        assert int(cnt.max()) > 64 or limit <= 64
+    gidx.close()
