@@ -41,6 +41,7 @@ struct KParams {
   int max_subs, mmd, max_ns, strand_mode, max_hits, min_core_len, slides_per100, max_iter, max_nodes;
   int ml_mode, clamp_ml;
   int best;               // -N: LocateBestMatches instead of the staged AlignReads (general kernel only)
+  int xdedup;             // fast kernel: "already processed" decided by comparing the earlier cores with the window (no key set)
   int prefetch;           // fast kernel: prefetch the next core's prefix-table entry into L2 (1) or not (0)
   int scan_iters;         // fast kernel: cores a lane may run down per step looking for a non-empty bucket (0: one core per step)
   bkx_multi_hit* multi;   // -r5: max_hits slots per read of this launch, or nullptr

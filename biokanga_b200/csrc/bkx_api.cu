@@ -830,6 +830,8 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   k->best = (p->best_matches && p->ml_mode != BKX_ML_DEFAULT) ? 1 : 0;   // kanga.cpp:666, 686: only with a multi-loci mode
   if (k->best) k->clamp_ml = 1;                                           // kanga.cpp:695-696
   k->multi = nullptr;
+  k->xdedup = 0;   // measured: faster in some sweep cells (L=100 -s6: +11 %), slower in others (L=150 -s8: -13 %) and at configs[1] (-7 %)
+  if (const char* ev = getenv("BKX_XDEDUP")) k->xdedup = atoi(ev) != 0;   // tuning hook
   k->prefetch = 0;   // measured: 31.5 ms without, 33.9 ms with (configs[1])
   if (const char* ev = getenv("BKX_PREFETCH")) k->prefetch = atoi(ev) != 0;   // tuning hook
   k->scan_iters = 0;
@@ -938,7 +940,9 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     cudaEventRecord(t0, st);
   }
   static const bool no_direct = getenv("BKX_NO_DIRECT2") != nullptr;   // tuning hook: ignore the 2-bit copy of the reads
-  CU(launch_align_fast(x->d, k, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash[si], epoch_base,
+  KParams kf = k;
+  if (x->d.n > (1ull << 32)) kf.xdedup = 0;   // 32-bit dedup keys collide beyond 2^32 symbols: keep the reference's key set there
+  CU(launch_align_fast(x->d, kf, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash[si], epoch_base,
                        x->fast_grid, st, no_direct ? Packed2Src() : p2));
   if (trace) cudaEventRecord(t1, st);
   CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, d_hard, cur + 2, x->grid, st));

@@ -1055,7 +1055,20 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
         int ent = find_entry(I, p);
         if (ent < 0 || (p + (uint64_t)L - 1) > __ldg(I.ent_end + ent)) continue;
         uint32_t kk = (uint32_t)(1u + (uint32_t)loci - (uint32_t)cofs);
-        if (seen_n <= kFastSeen) {  // beyond that the strand's keys live in the lane's hash set
+        if (P.xdedup) {
+          // "Already processed" without a set: this placement was reached before in this strand / phase exactly when an
+          // earlier core of the read also matches the genome there (its interval then held this locus, and the fast path
+          // walks every interval it keeps in full).  Tested on the packed words of a window the Hamming loop is about to
+          // read anyway -- no key list to scan, no hash set in HBM to probe.  (Indexes of more than 2^32 symbols keep the
+          // key set: the reference's 32-bit keys collide there, and that is reproduced.)
+          if (span_has_exc(I, p, (uint32_t)L)) { dfr = true; break; }
+          bool dup = false;
+          for (int j = 0; j < ci && !dup; ++j) {
+            const int oj = j <= K ? j * delta : last_ofs;
+            dup = fl_cmp(I, f, s, oj, CL, p + (uint64_t)oj) == 0;
+          }
+          if (dup) continue;
+        } else if (seen_n <= kFastSeen) {  // beyond that the strand's keys live in the lane's hash set
           bool dup = false;
           for (int i = 0; i < seen_n; ++i) dup |= (f.seen[i * 32] == kk);
           if (dup) continue;
@@ -1071,7 +1084,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
         }
         ++seen_n;
         ++cands;
-        if (span_has_exc(I, p, (uint32_t)L)) { dfr = true; break; }
+        if (!P.xdedup && span_has_exc(I, p, (uint32_t)L)) { dfr = true; break; }
         // Hamming over packed words; rejected once > MaxTotMM or >= NxtLowMMCnt (SfxArrayV2.cpp:6148-6151)
         uint64_t w = p >> 5;
         unsigned sh = (unsigned)(p & 31) * 2;
