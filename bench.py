@@ -352,9 +352,10 @@ def run_bkx(args):
                                 "0..%d subs, -s%d -U%d -d%d -D%d" % (args.genome_mbp / 1e3, nreads // 2, args.read_len,
                                                                         args.read_subs, args.max_subs, args.pe_mode, args.pe_min,
                                                                         args.pe_max)) if pe_mode else
-                               ("configs[1]: %.1f Gbp synthetic genome + injected repeats, %d x %d bp SE reads per GPU, "
-                                "0..%d subs, -s%d" % (args.genome_mbp / 1e3, nreads, args.read_len, args.read_subs,
-                                                       args.max_subs)),
+                               ("%s: %s synthetic genome + injected repeats, %d x %d bp SE reads per GPU, "
+                                "0..%d subs, -s%d" % ("configs[0]" if args.genome_mbp < 100 else "configs[1]",
+                                                       ("%.0f Mbp" % args.genome_mbp) if args.genome_mbp < 100 else ("%.1f Gbp" % (args.genome_mbp / 1e3)),
+                                                       nreads, args.read_len, args.read_subs, args.max_subs)),
                    "genome_symbols": int(n), "reads_per_gpu": nreads, "read_len": args.read_len,
                    "max_subs_per_100bp": args.max_subs, "prefix_k": int(idx.info.prefix_k),
                    "l2_policy": "inputs larger than L2 (index %.1f GB, reads %.1f GB per step)" % (
