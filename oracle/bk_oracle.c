@@ -15,8 +15,9 @@
  *
  * PARITY PIN: the reference ships no tests or golden vectors; this file is
  * pinned against outputs of the reference binary itself (oracle/_ref/biokanga, built by
- * oracle/build_ref.sh) on the fixtures under tests/golden/ (made by oracle/make_fixtures.py) and,
- * when oracle/_ref/biokanga is present, on freshly generated inputs (tests/test_oracle_vs_ref.py).
+ * oracle/build_ref.sh) on the fixtures under tests/golden/ (made by oracle/make_fixtures.py; checked by
+ * tests/test_oracle_golden.py) and, when oracle/_ref/biokanga is present, on freshly drawn option sets and
+ * inputs (tests/test_host_fuzz_cpu.py, tests/fuzz_host_cli.py) and on full-size files (bench.py --dropin).
  */
 #define _GNU_SOURCE
 #include "bk_oracle.h"
