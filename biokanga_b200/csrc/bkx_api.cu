@@ -18,6 +18,7 @@
 
 #include "bkx_align.cuh"
 #include "bkx_fast.cuh"
+#include "bkx_wave.cuh"
 #include "bkx_rescue.cuh"
 #include "bkx_kernels.h"
 
@@ -89,6 +90,8 @@ struct Slot {
   uint8_t* d_rflags = nullptr;   // per read of the slice: holds a non-ACGT base
   uint32_t* d_hard = nullptr;   // reads the fast kernel deferred to the general kernel
   size_t hard_cap = 0;
+  WaveBuf wave;                 // scratch of the wave path (bkx_wave.cuh), for wave_cap reads
+  size_t wave_cap = 0;
   size_t reads_cap = 0;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
   cudaEvent_t in_ready = nullptr;   // this slot's H2D copies are done (the compute stream waits on it)
@@ -380,6 +383,11 @@ extern "C" void bkx_close_index(bkx_index* x) {
     if (x->slot[s].d_scan_tmp) cudaFree(x->slot[s].d_scan_tmp);
     if (x->slot[s].d_rflags) cudaFree(x->slot[s].d_rflags);
     if (x->slot[s].d_hard) cudaFree(x->slot[s].d_hard);
+    {
+      WaveBuf& B = x->slot[s].wave;
+      void* wp[] = {B.act[0], B.act[1], B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
+      for (void* q : wp) if (q) cudaFree(q);
+    }
     if (x->slot[s].k0) cudaEventDestroy(x->slot[s].k0);
     if (x->slot[s].k1) cudaEventDestroy(x->slot[s].k1);
     if (x->slot[s].in_ready) cudaEventDestroy(x->slot[s].in_ready);
@@ -910,9 +918,44 @@ static int prepare_launch(bkx_index* x, const KParams& k, uint32_t max_len, int*
 }
 
 // fast kernel over all reads, then the general kernel over the reads it deferred (same stream)
+// Scratch of the wave path for n reads in slot si; false (and no error) when the device has no room for it
+static bool ensure_wave(bkx_index* x, int si, uint32_t n, cudaStream_t st) {
+  Slot& s = x->slot[si];
+  static const int row = [] { const char* e = getenv("BKX_WAVE_ROW"); int r = e ? atoi(e) : 8; return std::max(2, std::min(r, 32)); }();
+  if (n <= s.wave_cap && s.wave.cnt) return true;
+  cudaStreamSynchronize(st);
+  cudaStreamSynchronize(x->cst);
+  WaveBuf& B = s.wave;
+  void* ptrs[] = {B.act[0], B.act[1], B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  B = WaveBuf();
+  s.wave_cap = 0;
+  const size_t cap = (size_t)n * 5 / 4 + 1024;
+  const size_t item_cap = cap * 4 + 65536;
+  const size_t need = cap * (4 + 4 + 1 + 1 + 8 + 4 + (size_t)row * 8 + 4) + item_cap * 16 + kWaveCounters * 4;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < need + ((size_t)2 << 30)) return false;
+  bool ok = cudaMalloc((void**)&B.act[0], cap * 4) == cudaSuccess && cudaMalloc((void**)&B.act[1], cap * 4) == cudaSuccess &&
+            cudaMalloc((void**)&B.cnt, kWaveCounters * 4) == cudaSuccess && cudaMalloc((void**)&B.ph, cap) == cudaSuccess &&
+            cudaMalloc((void**)&B.fb, cap) == cudaSuccess && cudaMalloc((void**)&B.acc, cap * 8) == cudaSuccess &&
+            cudaMalloc((void**)&B.ncand, cap * 4) == cudaSuccess && cudaMalloc((void**)&B.cand, cap * (size_t)row * 8) == cudaSuccess &&
+            cudaMalloc((void**)&B.items, item_cap * 16) == cudaSuccess && cudaMalloc((void**)&B.fb_ids, cap * 4) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    void* got[] = {B.act[0], B.act[1], B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
+    for (void* q : got) if (q) cudaFree(q);
+    B = WaveBuf();
+    return false;
+  }
+  B.item_cap = item_cap;
+  B.row = row;
+  s.wave_cap = cap;
+  return true;
+}
+
 static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, const uint64_t* d_offs, uint32_t n,
                        int W, bkx_read_result* d_out, bkx_align_stats* d_stats, int si, uint32_t* d_hard,
-                       cudaStream_t st, const Packed2Src& p2 = Packed2Src()) {
+                       cudaStream_t st, const Packed2Src& p2 = Packed2Src(), uint32_t max_len = 0) {
   unsigned int* cur = x->d_cursor[si];
   if (getenv("BKX_NO_FAST") || k.best) {   // -N: a different search (LocateBestMatches), built in the general kernel only
     CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, nullptr, nullptr, x->grid, st));
@@ -942,8 +985,25 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
   static const bool no_direct = getenv("BKX_NO_DIRECT2") != nullptr;   // tuning hook: ignore the 2-bit copy of the reads
   KParams kf = k;
   if (x->d.n > (1ull << 32)) kf.xdedup = 0;   // 32-bit dedup keys collide beyond 2^32 symbols: keep the reference's key set there
+  // The default search goes down the wave path first (bkx_wave.cuh) when the reads came 2-bit packed; the lane-per-read
+  // kernel then only redoes what that path hands on.
+  const char* wave_env = getenv("BKX_WAVE");   // read per launch: the A/B harness (profiles/ab_kernel.py) switches it inside one process
+  const int wave_mode = wave_env ? atoi(wave_env) : 0;
+  const uint32_t* fast_ids = nullptr;
+  const unsigned int* fast_n = nullptr;
+  cudaEvent_t tw = nullptr;
+  if (wave_mode && p2.words && !no_direct && k.ml_mode == BKX_ML_DEFAULT && !k.clamp_ml && k.max_hits == 1 && max_len > 0 &&
+      x->d.n < (1ull << 40) && ensure_wave(x, si, n, st)) {
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, x->device));
+    CU(launch_wave(x->d, k, d_offs, n, max_len, p2, x->slot[si].wave, d_out, d_stats, sms, st));
+    fast_ids = x->slot[si].wave.fb_ids;
+    fast_n = x->slot[si].wave.cnt + kWaveCntFallback;
+    x->launches += (uint64_t)wave_launches(k, max_len);
+    if (trace) { cudaEventCreate(&tw); cudaEventRecord(tw, st); }
+  }
   CU(launch_align_fast(x->d, kf, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash[si], epoch_base,
-                       x->fast_grid, st, no_direct ? Packed2Src() : p2));
+                       x->fast_grid, st, no_direct ? Packed2Src() : p2, fast_ids, fast_n));
   if (trace) cudaEventRecord(t1, st);
   CU(launch_align(x->d, k, d_bases, d_offs, n, W, d_out, d_stats, cur + 1, x->hp, d_hard, cur + 2, x->grid, st));
   if (trace) {
@@ -954,6 +1014,15 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     float a = 0.f, b = 0.f;
     cudaEventElapsedTime(&a, t0, t1);
     cudaEventElapsedTime(&b, t1, t2);
+    if (tw) {
+      unsigned int nfb = 0;
+      float wv = 0.f;
+      cudaMemcpy(&nfb, fast_n, 4, cudaMemcpyDeviceToHost);
+      cudaEventElapsedTime(&wv, t0, tw);
+      cudaEventElapsedTime(&a, tw, t1);
+      fprintf(stderr, "[bkx trace] reads %u: wave %.3f ms, handed on %u (%.2f%%)\n", n, wv, nfb, 100.0 * nfb / n);
+      cudaEventDestroy(tw);
+    }
     fprintf(stderr, "[bkx trace] reads %u: fast %.3f ms, deferred %u (%.2f%%), general %.3f ms\n", n, a, nh, 100.0 * nh / n, b);
     cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
   }
@@ -1018,7 +1087,7 @@ extern "C" int bkx_align_reads_device_packed2(bkx_index* x, const bkx_align_para
   Packed2Src psrc;
   psrc.words = d_packed2; psrc.flags = d_read_flags; psrc.phase = 0;
   CU(cudaEventRecord(s.k0, st));
-  if ((rc = launch_both(x, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, 0, s.d_hard, st, psrc)) < 0) return rc;
+  if ((rc = launch_both(x, k, d_bases, d_offsets, n_reads, W, d_out, d_stats, 0, s.d_hard, st, psrc, max_read_len)) < 0) return rc;
   CU(cudaEventRecord(s.k1, st));
   s.timed = true;
   for (int si = 1; si < kSlots; ++si) x->slot[si].timed = false;
@@ -1254,7 +1323,7 @@ static int align_host(bkx_index* x, const bkx_align_params* p, const HostReads& 
     const uint8_t* kbases = p2 ? s.d_bases : s.d_bases - o0;
     Packed2Src psrc;   // PACKED2: the fast kernel takes its reads straight from the 2-bit stream that came over PCIe
     if (p2) { psrc.words = (const uint64_t*)s.d_packed; psrc.flags = s.d_rflags; psrc.phase = (uint32_t)(o0 & 3); }
-    if ((rc = launch_both(x, k, kbases, s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard, x->cst, psrc)) < 0) return rc;
+    if ((rc = launch_both(x, k, kbases, s.d_offs, cnt, W, s.d_out, x->d_stats, b, s.d_hard, x->cst, psrc, (uint32_t)max_len)) < 0) return rc;
     if (pec) {  // pair the slice's reads while they are still on the device (ProcessPairedEnds, Aligner.cpp:2876-3049)
       unsigned int* cur = x->d_cursor[b];
       if ((size_t)cnt / 2 > s.orphans_cap) {

@@ -1,6 +1,7 @@
 // CUDA kernels of the bkx library (sm_100a): index preparation, read alignment, paired-end pairing.
 #include "bkx_align.cuh"
 #include "bkx_fast.cuh"
+#include "bkx_wave.cuh"
 #include "bkx_rescue.cuh"
 #include "bkx_kernels.h"
 
@@ -8,6 +9,7 @@
 #include <cub/iterator/transform_input_iterator.cuh>
 
 #include <mutex>
+#include <vector>
 
 namespace bkx {
 
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
     DevIndex I, KParams P, const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, uint32_t n_reads,
     int W, bkx_read_result* __restrict__ out, bkx_align_stats* __restrict__ stats, unsigned int* __restrict__ cursor,
     uint32_t* __restrict__ hard_ids, unsigned int* __restrict__ n_hard, uint64_t* __restrict__ lane_hash,
-    uint32_t epoch_base, Packed2Src p2) {
+    uint32_t epoch_base, Packed2Src p2, const uint32_t* __restrict__ ids, const unsigned int* __restrict__ n_ids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ BlockStats bs;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -832,9 +834,10 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
       bool bad = false;
       if (want) {
         r = base_r + __popc(need & lt);
-        if (r >= n_reads) {
+        if (r >= (ids ? __ldg(n_ids) : n_reads)) {   // ids: only the reads the wave path handed on (bkx_wave.cuh)
           exhausted = true;
         } else {
+          if (ids) r = __ldg(ids + r);
           active = true;
           seeds = cands = 0;
           L = (int)(__ldg(offs + r + 1) - __ldg(offs + r));
@@ -1149,7 +1152,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) align_fast_kernel(
 cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                               uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
                               unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, uint64_t* lane_hash,
-                              uint32_t epoch_base, int grid, cudaStream_t st, const Packed2Src& p2) {
+                              uint32_t epoch_base, int grid, cudaStream_t st, const Packed2Src& p2, const uint32_t* ids,
+                              const unsigned int* n_ids) {
   size_t smem = fast_smem_bytes(W);
   const bool mlx = P.ml_mode != 0 || P.clamp_ml != 0;
   const bool scan = P.scan_iters > 0;
@@ -1164,7 +1168,7 @@ cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t
   if (e != cudaSuccess) return e;
 #define BKX_LAUNCH_FAST(M, S)                                                                                              \
   align_fast_kernel<M, S><<<grid, kFastThreads, smem, st>>>(I, P, bases, offs, n_reads, W, out, stats, cursor, hard_ids, \
-                                                            n_hard, lane_hash, epoch_base, p2)
+                                                            n_hard, lane_hash, epoch_base, p2, ids, n_ids)
   if (mlx) { if (scan) BKX_LAUNCH_FAST(true, true); else BKX_LAUNCH_FAST(true, false); }
   else { if (scan) BKX_LAUNCH_FAST(false, true); else BKX_LAUNCH_FAST(false, false); }
 #undef BKX_LAUNCH_FAST
@@ -1183,6 +1187,356 @@ int fast_blocks_per_sm(int W) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[2], align_fast_kernel<false, true>, kFastThreads, smem);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[3], align_fast_kernel<true, true>, kFastThreads, smem);
   return std::min(std::min(nb[0], nb[1]), std::min(nb[2], nb[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wave path: the default search laid out by kind of work instead of by read (see bkx_wave.cuh)
+// ------------------------------------------------------------------------------------------------
+constexpr int kWaveThreads = 256;
+
+__device__ __forceinline__ void wave_none_result(bkx_read_result& res, uint32_t seeds, uint32_t cands) {
+  res.nar = BKX_NAR_NOHIT; res.hit_rslt = BKX_HR_NONE; res.strand = 0; res.num_hits = 0; res.low_mm = 0; res.nxt_low_mm = 0;
+  res.low_hit_instances = 0; res.chrom_id = 0; res.match_loci = 0; res.match_len = 0; res.mismatches = 0;
+  res.flags = 0; res.seeds = seeds; res.cands = cands; res.reserved = 0;
+}
+
+// every read of the launch: onto the first wave, or onto the list align_fast_kernel redoes
+__global__ void __launch_bounds__(kWaveThreads) wave_init_kernel(KParams P, const uint64_t* __restrict__ offs, uint32_t n_reads,
+                                                                 Packed2Src p2, WaveBuf B, bkx_read_result* __restrict__ out,
+                                                                 bkx_align_stats* __restrict__ stats) {
+  __shared__ BlockStats bs;
+  for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_reads; t += stride) {
+    const uint32_t r = (uint32_t)t;
+    const uint64_t len = __ldg(offs + r + 1) - __ldg(offs + r);
+    if (len < 1 || len > (uint64_t)kFastMaxLen || (p2.flags && __ldg(p2.flags + r))) {
+      B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = r;
+      continue;
+    }
+    WaveRead w;
+    wave_read(P, (int)len, w);
+    const int state = wave_enter(P, w, 0, true);
+    B.fb[r] = 0;
+    B.ncand[r] = 0;
+    B.acc[r] = make_uint2(0u, 0u);
+    if (state < 0) {
+      bkx_read_result res;
+      wave_none_result(res, 0, 0);
+      out[r] = res;
+      stats_add_basic(bs, res);
+      continue;
+    }
+    B.ph[r] = (uint8_t)state;
+    B.act[0][wave_push(B.cnt + kWaveCntAct)] = r;
+  }
+  __syncthreads();
+  if (stats) stats_flush(bs, stats);
+}
+
+// one thread per (read of the wave, strand): the prefix-table lookups of all cores of the read's phase
+__global__ void __launch_bounds__(kWaveThreads) wave_lookup_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
+                                                                   Packed2Src p2, WaveBuf B, int round) {
+  const unsigned n_act = B.cnt[kWaveCntAct + round];
+  const uint32_t* __restrict__ act = B.act[round & 1];
+  const int s_first = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
+  const int s_last = (P.strand_mode == BKX_STRAND_WATSON) ? 0 : 1;
+  const bool both = s_last > s_first;
+  const uint64_t total = (uint64_t)n_act << (both ? 1 : 0);
+  const int k = I.k;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint32_t r = __ldg(act + (both ? (t >> 1) : t));
+    const int s = both ? (int)(t & 1) : s_first;
+    const uint64_t o0 = __ldg(offs + r);
+    ReadRef q;
+    q.words = p2.words; q.bo = o0 + p2.phase; q.L = (int)(__ldg(offs + r + 1) - o0);
+    WaveRead w;
+    wave_read(P, q.L, w);
+    WavePhase ph;
+    wave_phase(P, w, B.ph[r], ph);
+    for (int c0 = 0; c0 < ph.n_cores; c0 += 4) {
+      uint64_t lo[4], hi[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {   // four cores' lookups are issued before any of them is looked at
+        lo[j] = hi[j] = 0;
+        const int ci = c0 + j;
+        if (ci < ph.n_cores) {
+          const int cofs = ci <= ph.K ? ci * ph.delta : ph.last_ofs;
+          const uint64_t key = rev2(rr_word(q, s, cofs)) >> (64 - 2 * k);
+          if (ph.CL >= k) {
+            lo[j] = pt_get(I, key);
+            hi[j] = pt_get(I, key + 1);
+          } else {
+            const int sh = 2 * (k - ph.CL);
+            const uint64_t pfx = key >> sh;
+            lo[j] = pt_get(I, pfx << sh);
+            hi[j] = pt_get(I, (pfx + 1) << sh);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (lo[j] < hi[j]) {
+          const uint64_t size = hi[j] - lo[j];
+          const uint64_t at = size < 0xffffffffull ? (uint64_t)wave_push(B.cnt + kWaveCntItems + round) : ~0ull;
+          if (at >= B.item_cap) { B.fb[r] = 1; continue; }
+          B.items[at] = make_ulonglong2(lo[j] | ((uint64_t)s << 40) | ((uint64_t)(c0 + j) << 41), (uint64_t)r | (size << 32));
+        }
+      }
+    }
+  }
+}
+
+// one thread per item: the core's interval inside its bucket, the walk over it, Hamming of every placement
+// (the body of align_fast_kernel's step (2), with the read taken from the 2-bit stream)
+__global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
+                                                                  Packed2Src p2, WaveBuf B, int round) {
+  const uint64_t n_raw = B.cnt[kWaveCntItems + round];
+  const uint64_t n_items = n_raw < B.item_cap ? n_raw : B.item_cap;
+  const int k = I.k;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += stride) {
+    const ulonglong2 it = B.items[t];
+    const uint64_t blo = it.x & 0xffffffffffull, bhi = blo + (it.y >> 32);
+    const int s = (int)((it.x >> 40) & 1), ci = (int)(it.x >> 41);
+    const uint32_t r = (uint32_t)it.y;
+    const uint64_t o0 = __ldg(offs + r);
+    ReadRef q;
+    q.words = p2.words; q.bo = o0 + p2.phase; q.L = (int)(__ldg(offs + r + 1) - o0);
+    const int L = q.L;
+    WaveRead w;
+    wave_read(P, L, w);
+    WavePhase ph;
+    wave_phase(P, w, B.ph[r], ph);
+    const int CL = ph.CL;
+    const int cofs = ci <= ph.K ? ci * ph.delta : ph.last_ofs;
+    bool dfr = false;
+    uint64_t first = 0, cnt = 0;
+    bool located = false;
+    if (CL <= k) {
+      // core no longer than the table key: the bucket IS the interval, except for suffixes holding an N/EOS inside the
+      // core span, which sort at the bucket's end -- so if the last element matches, every element does
+      const uint64_t g = sa_get(I, bhi - 1);
+      if (!span_has_exc(I, g, (uint32_t)CL) && rr_cmp(I, q, s, cofs, CL, g) == 0) {
+        first = blo;
+        cnt = bhi - blo;
+        located = true;
+        if (cnt > (uint64_t)kFastMaxCnt) dfr = true;
+      }
+    }
+    if (!located) {
+      uint64_t l = blo, h = bhi;
+      bool h_equal = false;
+      while (l < h) {
+        const uint64_t m = l + ((h - l) >> 1);
+        const uint64_t g = sa_get(I, m);
+        if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
+        const int c = rr_cmp(I, q, s, cofs, CL, g);
+        if (c > 0) l = m + 1; else { h = m; h_equal = (c == 0); }
+      }
+      if (!dfr && l < bhi && h_equal) {
+        first = l;
+        uint64_t ul = l + 1;
+        while (ul < bhi) {
+          if (ul - first >= (uint64_t)kFastMaxCnt) { dfr = true; break; }
+          const uint64_t g = sa_get(I, ul);
+          if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
+          if (rr_cmp(I, q, s, cofs, CL, g) != 0) break;
+          ++ul;
+        }
+        cnt = ul - first;
+      }
+    }
+    for (uint64_t e = 0; e < cnt && !dfr; ++e) {
+      const uint64_t loci = sa_get(I, first + e);
+      if (loci < (uint64_t)cofs) continue;
+      const uint64_t p = loci - (uint64_t)cofs;
+      const int ent = find_entry(I, p);
+      if (ent < 0 || (p + (uint64_t)L - 1) > __ldg(I.ent_end + ent)) continue;
+      const unsigned slot = atomicAdd(B.ncand + r, 1u);
+      if (slot >= (unsigned)B.row || span_has_exc(I, p, (uint32_t)L)) { dfr = true; break; }
+      // Hamming over packed words, given up once beyond the phase's allowance
+      uint64_t gw_i = p >> 5;
+      const unsigned sh = (unsigned)(p & 31) * 2;
+      uint64_t prev = __ldg(I.g2 + gw_i);
+      int mm = 0;
+      for (int b = 0; b < L; b += 32) {
+        const uint64_t next = __ldg(I.g2 + (++gw_i));
+        const uint64_t gw = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
+        prev = next;
+        const uint64_t x = rr_word(q, s, b) ^ gw;   // rr_word is zero beyond the read: mask the genome side
+        uint64_t m = (x | (x >> 1)) & 0x5555555555555555ull;
+        const int rem = L - b;
+        if (rem < 32) m &= (1ull << (2 * rem)) - 1;
+        mm += __popcll(m);
+        if (mm > ph.mm_max) break;
+      }
+      const uint64_t mmc = mm > ph.mm_max ? (uint64_t)kWaveFailed : (uint64_t)mm;
+      B.cand[(size_t)r * B.row + slot] = p | ((uint64_t)s << 40) | (mmc << 41);
+    }
+    if (dfr) B.fb[r] = 1;
+  }
+}
+
+// one thread per read of the wave: what the phase found, then the read's result or its next phase
+__global__ void __launch_bounds__(kWaveThreads) wave_reduce_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
+                                                                   WaveBuf B, int round, bkx_read_result* __restrict__ out,
+                                                                   bkx_align_stats* __restrict__ stats) {
+  __shared__ BlockStats bs;
+  for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
+  __syncthreads();
+  const unsigned n_act = B.cnt[kWaveCntAct + round];
+  const uint32_t* __restrict__ act = B.act[round & 1];
+  uint32_t* __restrict__ act_next = B.act[(round + 1) & 1];
+  const int n_strands = (P.strand_mode == BKX_STRAND_BOTH) ? 2 : 1;
+  const bool wide = I.n > (1ull << 32);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_act; t += stride) {
+    const uint32_t r = __ldg(act + t);
+    if (B.fb[r]) {
+      B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = r;
+      continue;
+    }
+    const int L = (int)(__ldg(offs + r + 1) - __ldg(offs + r));
+    WaveRead w;
+    wave_read(P, L, w);
+    const unsigned state = B.ph[r];
+    WavePhase ph;
+    wave_phase(P, w, state, ph);
+    const unsigned nc = B.ncand[r];
+    int inst = 0, low = ph.mm_max + P.mmd + 1, nxt = low;
+    unsigned distinct = 0;
+    uint64_t hit = 0;
+    bool redo = false;
+    if (nc) {
+      const uint64_t* __restrict__ row = B.cand + (size_t)r * B.row;
+      const uint64_t kmask = (1ull << 41) - 1;   // placement + strand
+      for (unsigned i = 0; i < nc; ++i) {
+        const uint64_t c = row[i];
+        const uint64_t key = c & kmask;
+        bool dup = false;
+        for (unsigned j = 0; j < i; ++j) {
+          const uint64_t kj = row[j] & kmask;
+          if (kj == key) dup = true;
+          // the reference's "already processed" keys are 32 bits wide (SfxArrayV2.cpp:6093): beyond 2^32 symbols two
+          // placements of one strand can share a key, and which of them is dropped depends on the order they are met in
+          else if (wide && ((kj ^ key) >> 40) == 0 && (uint32_t)kj == (uint32_t)key) redo = true;
+        }
+        if (dup) continue;
+        ++distinct;
+        const int mm = (int)((c >> 41) & 127);
+        if (mm == (int)kWaveFailed) continue;
+        if (mm < low) { inst = 1; nxt = low; low = mm; hit = c; }
+        else if (mm == low) ++inst;
+        else if (mm < nxt) nxt = mm;
+      }
+      B.ncand[r] = 0;
+    }
+    // more exact placements than MaxHits: the reference stops the phase there (SfxArrayV2.cpp:6199) and what it has
+    // seen by then depends on the order
+    if (redo || (inst > P.max_hits && low == 0)) {
+      B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = r;
+      continue;
+    }
+    const uint2 acc = B.acc[r];
+    const uint32_t seeds = acc.x + (uint32_t)(n_strands * ph.n_cores), cands = acc.y + distinct;
+    bkx_read_result res;
+    if (inst == 0) {
+      const int next = wave_enter(P, w, (int)state, false);
+      if (next >= 0) {
+        B.ph[r] = (uint8_t)next;
+        B.acc[r] = make_uint2(seeds, cands);
+        act_next[wave_push(B.cnt + kWaveCntAct + round + 1)] = r;
+        continue;
+      }
+      wave_none_result(res, seeds, cands);
+    } else {
+      // ProcCoredApprox's mapping for the default multi-loci mode (finish() of align_fast_kernel)
+      wave_none_result(res, seeds, cands);
+      const int hr = (nxt - low) < P.mmd ? BKX_HR_MMDELTA : inst > P.max_hits ? BKX_HR_HITINSTS : BKX_HR_HITS;
+      res.hit_rslt = (uint8_t)hr;
+      res.low_mm = (int8_t)low;
+      res.nxt_low_mm = (int8_t)nxt;
+      res.match_len = (uint16_t)L;
+      if (hr == BKX_HR_HITS) {
+        const uint64_t p = hit & 0xffffffffffull;
+        const int ent = find_entry(I, p);
+        res.nar = BKX_NAR_ACCEPTED;
+        res.num_hits = 1;
+        res.strand = ((hit >> 40) & 1) ? '-' : '+';
+        res.chrom_id = __ldg(I.ent_id + ent);
+        res.match_loci = (uint32_t)(p - __ldg(I.ent_start + ent));
+        res.mismatches = (uint8_t)low;
+        res.low_hit_instances = 1;
+      } else {
+        res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
+        res.strand = '?';
+        res.low_hit_instances = (int16_t)(inst > P.max_hits ? P.max_hits + 1 : inst);
+      }
+    }
+    out[r] = res;
+    stats_add_basic(bs, res);
+  }
+  __syncthreads();
+  if (stats) stats_flush(bs, stats);
+}
+
+// reads still on a wave after the last round (none, unless the round count was short): redone like the others
+__global__ void __launch_bounds__(kWaveThreads) wave_drain_kernel(WaveBuf B, int round) {
+  const unsigned n_act = B.cnt[kWaveCntAct + round];
+  const uint32_t* __restrict__ act = B.act[round & 1];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_act; t += stride)
+    B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = __ldg(act + t);
+}
+
+// a read goes through at most one phase per allowance 0..MaxTotMM and the final one
+static int wave_rounds(const KParams& P, uint32_t max_len) {
+  const uint32_t len = max_len < (uint32_t)kFastMaxLen ? max_len : (uint32_t)kFastMaxLen;
+  int mt = P.max_subs == 0 ? 0 : std::max(1, (int)((len * (uint32_t)P.max_subs + 50) / 100));
+  if (mt > 63) mt = 63;
+  return std::min(mt + 2, kWaveMaxRounds - 1);
+}
+int wave_launches(const KParams& P, uint32_t max_len) { return 2 + 3 * wave_rounds(P, max_len); }
+
+cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* offs, uint32_t n_reads, uint32_t max_len,
+                        const Packed2Src& p2, const WaveBuf& B, bkx_read_result* out, bkx_align_stats* stats, int sms,
+                        cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(B.cnt, 0, kWaveCounters * sizeof(unsigned int), st);
+  if (e != cudaSuccess) return e;
+  const int grid = sms * (2048 / kWaveThreads);
+  wave_init_kernel<<<grid, kWaveThreads, 0, st>>>(P, offs, n_reads, p2, B, out, stats);
+  const int rounds = wave_rounds(P, max_len);
+  static const bool trace = getenv("BKX_TRACE") != nullptr;   // diagnostic: time of every kernel of every round, serialising
+  std::vector<cudaEvent_t> ev;
+  auto mark = [&]() { if (trace) { cudaEvent_t e2; cudaEventCreate(&e2); cudaEventRecord(e2, st); ev.push_back(e2); } };
+  mark();
+  for (int round = 0; round < rounds; ++round) {
+    wave_lookup_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, p2, B, round);
+    mark();
+    wave_probe_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, p2, B, round);
+    mark();
+    wave_reduce_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, B, round, out, stats);
+    mark();
+  }
+  if (trace) {
+    cudaStreamSynchronize(st);
+    std::vector<unsigned int> c(kWaveCounters);
+    cudaMemcpy(c.data(), B.cnt, kWaveCounters * 4, cudaMemcpyDeviceToHost);
+    for (int round = 0; round < rounds; ++round) {
+      float a = 0.f, b = 0.f, d = 0.f;
+      cudaEventElapsedTime(&a, ev[3 * round], ev[3 * round + 1]);
+      cudaEventElapsedTime(&b, ev[3 * round + 1], ev[3 * round + 2]);
+      cudaEventElapsedTime(&d, ev[3 * round + 2], ev[3 * round + 3]);
+      fprintf(stderr, "[bkx trace] wave %d: %u reads, %u items; lookup %.3f ms, probe %.3f ms, reduce %.3f ms\n", round,
+              c[kWaveCntAct + round], c[kWaveCntItems + round], a, b, d);
+    }
+    for (cudaEvent_t e2 : ev) cudaEventDestroy(e2);
+  }
+  wave_drain_kernel<<<grid, kWaveThreads, 0, st>>>(B, rounds);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

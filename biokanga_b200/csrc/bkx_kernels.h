@@ -36,7 +36,14 @@ int fast_blocks_per_sm(int W);
 cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t* bases, const uint64_t* offs,
                               uint32_t n_reads, int W, bkx_read_result* out, bkx_align_stats* stats,
                               unsigned int* cursor, uint32_t* hard_ids, unsigned int* n_hard, uint64_t* lane_hash,
-                              uint32_t epoch_base, int grid, cudaStream_t st, const Packed2Src& p2);
+                              uint32_t epoch_base, int grid, cudaStream_t st, const Packed2Src& p2,
+                              const uint32_t* ids = nullptr, const unsigned int* n_ids = nullptr);
+struct WaveBuf;
+int wave_launches(const KParams& P, uint32_t max_len);   // kernels one launch_wave starts
+// the wave path (bkx_wave.cuh): results for the reads it finishes, B.fb_ids / B.cnt[kWaveCntFallback] for the others
+cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* offs, uint32_t n_reads, uint32_t max_len,
+                        const Packed2Src& p2, const WaveBuf& B, bkx_read_result* out, bkx_align_stats* stats, int sms,
+                        cudaStream_t st);
 cudaError_t launch_flag_exception_reads(const uint64_t* pos, uint32_t n_exc, uint64_t first_base, const uint64_t* offs,
                                         uint32_t n_reads, uint8_t* flags, cudaStream_t st);
 cudaError_t launch_pair(const bkx_pe_params& pe, bkx_read_result* res, uint32_t n_pairs, bkx_pe_stats* stats,

@@ -84,6 +84,12 @@ def main():
         if first is None:
             first = res
         same = bool(res.tobytes() == first.tobytes())
+        if not same:   # which records differ, and how
+            bad = np.nonzero(res != first)[0]
+            print("  %d of %d records differ; by field: %s" % (
+                len(bad), nreads, {f: int((res[f] != first[f]).sum()) for f in res.dtype.names if (res[f] != first[f]).any()}), flush=True)
+            for i in bad[:12]:
+                print("  read %d\n    first: %s\n    this : %s" % (i, first[i], res[i]), flush=True)
         row = {"setting": setting, "ms_best": min(ms), "ms_median": float(np.median(ms)), "reads_per_s": nreads / (min(ms) / 1e3),
                "identical_to_first": same}
         rows.append(row)
