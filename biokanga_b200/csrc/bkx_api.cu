@@ -385,7 +385,7 @@ extern "C" void bkx_close_index(bkx_index* x) {
     if (x->slot[s].d_hard) cudaFree(x->slot[s].d_hard);
     {
       WaveBuf& B = x->slot[s].wave;
-      void* wp[] = {B.act[0], B.act[1], B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
+      void* wp[] = {B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
       for (void* q : wp) if (q) cudaFree(q);
     }
     if (x->slot[s].k0) cudaEventDestroy(x->slot[s].k0);
@@ -843,7 +843,6 @@ static int check_params(const bkx_align_params* p, KParams* k) {
   k->prefetch = 0;   // measured: 31.5 ms without, 33.9 ms with (configs[1])
   if (const char* ev = getenv("BKX_PREFETCH")) k->prefetch = atoi(ev) != 0;   // tuning hook
   k->scan_iters = 0;
-  if (const char* ev = getenv("BKX_SCAN_ITERS")) k->scan_iters = std::max(0, std::min(64, atoi(ev)));   // tuning hook; 0 = one core per step
   return BKX_OK;
 }
 
@@ -926,23 +925,22 @@ static bool ensure_wave(bkx_index* x, int si, uint32_t n, cudaStream_t st) {
   cudaStreamSynchronize(st);
   cudaStreamSynchronize(x->cst);
   WaveBuf& B = s.wave;
-  void* ptrs[] = {B.act[0], B.act[1], B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
+  void* ptrs[] = {B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
   for (void* q : ptrs) if (q) cudaFree(q);
   B = WaveBuf();
   s.wave_cap = 0;
   const size_t cap = (size_t)n * 5 / 4 + 1024;
-  const size_t item_cap = cap * 4 + 65536;
-  const size_t need = cap * (4 + 4 + 1 + 1 + 8 + 4 + (size_t)row * 8 + 4) + item_cap * 16 + kWaveCounters * 4;
+  const size_t item_cap = ((cap * 3 + (1u << 20)) / kWaveChunk) * kWaveChunk;
+  const size_t need = cap * (1 + 1 + 8 + 4 + (size_t)row * 8 + 4) + item_cap * 32 + kWaveCounters * 4;
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < need + ((size_t)2 << 30)) return false;
-  bool ok = cudaMalloc((void**)&B.act[0], cap * 4) == cudaSuccess && cudaMalloc((void**)&B.act[1], cap * 4) == cudaSuccess &&
-            cudaMalloc((void**)&B.cnt, kWaveCounters * 4) == cudaSuccess && cudaMalloc((void**)&B.ph, cap) == cudaSuccess &&
+  bool ok = cudaMalloc((void**)&B.cnt, kWaveCounters * 4) == cudaSuccess && cudaMalloc((void**)&B.ph, cap) == cudaSuccess &&
             cudaMalloc((void**)&B.fb, cap) == cudaSuccess && cudaMalloc((void**)&B.acc, cap * 8) == cudaSuccess &&
             cudaMalloc((void**)&B.ncand, cap * 4) == cudaSuccess && cudaMalloc((void**)&B.cand, cap * (size_t)row * 8) == cudaSuccess &&
-            cudaMalloc((void**)&B.items, item_cap * 16) == cudaSuccess && cudaMalloc((void**)&B.fb_ids, cap * 4) == cudaSuccess;
+            cudaMalloc((void**)&B.items, item_cap * 32) == cudaSuccess && cudaMalloc((void**)&B.fb_ids, cap * 4) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
-    void* got[] = {B.act[0], B.act[1], B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
+    void* got[] = {B.cnt, B.ph, B.fb, B.acc, B.ncand, B.cand, B.items, B.fb_ids};
     for (void* q : got) if (q) cudaFree(q);
     B = WaveBuf();
     return false;

@@ -1200,126 +1200,280 @@ __device__ __forceinline__ void wave_none_result(bkx_read_result& res, uint32_t 
   res.flags = 0; res.seeds = seeds; res.cands = cands; res.reserved = 0;
 }
 
-// every read of the launch: onto the first wave, or onto the list align_fast_kernel redoes
-__global__ void __launch_bounds__(kWaveThreads) wave_init_kernel(KParams P, const uint64_t* __restrict__ offs, uint32_t n_reads,
-                                                                 Packed2Src p2, WaveBuf B, bkx_read_result* __restrict__ out,
+// One thread per read, once per round: (a) what the read's phase of the previous round found -- then its result, or its
+// next phase (round 0: whether the read can go down this path at all, and its first phase); (b) the prefix-table lookups
+// of all cores of the phase it is in now, both strands, and an item per bucket that is not empty.  Items go to the queue
+// in chunks of kWaveChunk slots owned by one warp: one global atomic per chunk (a returning atomic per append bounds a
+// kernel at 2.9 ns each); the unused tail of a chunk is filled with empty items.
+// mode 0: first round; 1: a round in between; 2: after the last round -- (a) only, a read still on the path is handed on
+__global__ void __launch_bounds__(kWaveThreads) wave_step_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
+                                                                 uint32_t n_reads, Packed2Src p2, WaveBuf B, int round, int mode,
+                                                                 bkx_read_result* __restrict__ out,
                                                                  bkx_align_stats* __restrict__ stats) {
   __shared__ BlockStats bs;
   for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
   __syncthreads();
+  const int s_first = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
+  const int s_last = (P.strand_mode == BKX_STRAND_WATSON) ? 0 : 1;
+  const int n_strands = s_last - s_first + 1;
+  const bool wide = I.n > (1ull << 32);
+  const int k = I.k;
+  const int lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_reads; t += stride) {
-    const uint32_t r = (uint32_t)t;
-    const uint64_t len = __ldg(offs + r + 1) - __ldg(offs + r);
-    if (len < 1 || len > (uint64_t)kFastMaxLen || (p2.flags && __ldg(p2.flags + r))) {
-      B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = r;
-      continue;
-    }
+  unsigned int* q_count = B.cnt + kWaveCntItems + round;
+  uint64_t cur = 0, end = 0;   // this warp's chunk of the item queue (warp-uniform)
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n_reads; base += stride) {
+    const uint32_t r = (uint32_t)(base + lane);
+    const bool in_range = base + lane < n_reads;
+    unsigned state = kWaveOff;
+    ReadRef q;
+    q.words = p2.words; q.bo = 0; q.L = 0;
     WaveRead w;
-    wave_read(P, (int)len, w);
-    const int state = wave_enter(P, w, 0, true);
-    B.fb[r] = 0;
-    B.ncand[r] = 0;
-    B.acc[r] = make_uint2(0u, 0u);
-    if (state < 0) {
-      bkx_read_result res;
-      wave_none_result(res, 0, 0);
-      out[r] = res;
-      stats_add_basic(bs, res);
-      continue;
+    w.L = 0; w.max_tot_mm = 0; w.core_len = 0; w.slides = 0; w.core_delta = 0;
+    bool handed_on = false;
+    if (in_range) {
+      if (mode == 0) {
+        const uint64_t o0 = __ldg(offs + r);
+        const uint64_t len = __ldg(offs + r + 1) - o0;
+        if (len < 1 || len > (uint64_t)kFastMaxLen || (p2.flags && __ldg(p2.flags + r))) {
+          handed_on = true;
+        } else {
+          q.bo = o0 + p2.phase; q.L = (int)len;
+          wave_read(P, q.L, w);
+          const int first = wave_enter(P, w, 0, true);
+          B.fb[r] = 0;
+          B.ncand[r] = 0;
+          B.acc[r] = make_uint2(0u, 0u);
+          if (first < 0) {
+            bkx_read_result res;
+            wave_none_result(res, 0, 0);
+            out[r] = res;
+            stats_add_basic(bs, res);
+          } else {
+            state = (unsigned)first;
+          }
+        }
+        B.ph[r] = (uint8_t)state;
+      } else {
+        state = B.ph[r];
+        if (state != kWaveOff) {
+          // ---- (a) the phase the read was in
+          const unsigned old_state = state;
+          state = kWaveOff;
+          const uint64_t o0 = __ldg(offs + r);
+          q.bo = o0 + p2.phase; q.L = (int)(__ldg(offs + r + 1) - o0);
+          wave_read(P, q.L, w);
+          if (B.fb[r]) {
+            handed_on = true;
+          } else {
+            WavePhase ph;
+            wave_phase(P, w, old_state, ph);
+            const unsigned nc = B.ncand[r];
+            int inst = 0, low = ph.mm_max + P.mmd + 1, nxt = low;
+            unsigned distinct = 0;
+            uint64_t hit = 0;
+            bool redo = false;
+            if (nc) {
+              const uint64_t* __restrict__ row = B.cand + (size_t)r * B.row;
+              const uint64_t kmask = (1ull << 41) - 1;   // placement + strand
+              for (unsigned i = 0; i < nc; ++i) {
+                const uint64_t c = row[i];
+                const uint64_t key = c & kmask;
+                bool dup = false;
+                for (unsigned j = 0; j < i; ++j) {
+                  const uint64_t kj = row[j] & kmask;
+                  if (kj == key) dup = true;
+                  // the reference's "already processed" keys are 32 bits wide (SfxArrayV2.cpp:6093): beyond 2^32 symbols
+                  // two placements of one strand can share a key, and which of them is dropped depends on the order they
+                  // are met in
+                  else if (wide && ((kj ^ key) >> 40) == 0 && (uint32_t)kj == (uint32_t)key) redo = true;
+                }
+                if (dup) continue;
+                ++distinct;
+                const int mm = (int)((c >> 41) & 127);
+                if (mm == (int)kWaveFailed) continue;
+                if (mm < low) { inst = 1; nxt = low; low = mm; hit = c; }
+                else if (mm == low) ++inst;
+                else if (mm < nxt) nxt = mm;
+              }
+              B.ncand[r] = 0;
+            }
+            // more exact placements than MaxHits: the reference stops the phase there (SfxArrayV2.cpp:6199) and what it
+            // has seen by then depends on the order
+            if (redo || (inst > P.max_hits && low == 0)) {
+              handed_on = true;
+            } else {
+              const uint2 acc = B.acc[r];
+              const uint32_t seeds = acc.x + (uint32_t)(n_strands * ph.n_cores), cands = acc.y + distinct;
+              bkx_read_result res;
+              wave_none_result(res, seeds, cands);
+              bool done = true;
+              if (inst == 0) {
+                const int next = wave_enter(P, w, (int)old_state, false);
+                if (next >= 0) {
+                  if (mode == 2) handed_on = true;
+                  else { state = (unsigned)next; B.acc[r] = make_uint2(seeds, cands); }
+                  done = false;
+                }
+              } else {
+                // ProcCoredApprox's mapping for the default multi-loci mode (finish() of align_fast_kernel)
+                const int hr = (nxt - low) < P.mmd ? BKX_HR_MMDELTA : inst > P.max_hits ? BKX_HR_HITINSTS : BKX_HR_HITS;
+                res.hit_rslt = (uint8_t)hr;
+                res.low_mm = (int8_t)low;
+                res.nxt_low_mm = (int8_t)nxt;
+                res.match_len = (uint16_t)q.L;
+                if (hr == BKX_HR_HITS) {
+                  const uint64_t p = hit & 0xffffffffffull;
+                  const int ent = find_entry(I, p);
+                  res.nar = BKX_NAR_ACCEPTED;
+                  res.num_hits = 1;
+                  res.strand = ((hit >> 40) & 1) ? '-' : '+';
+                  res.chrom_id = __ldg(I.ent_id + ent);
+                  res.match_loci = (uint32_t)(p - __ldg(I.ent_start + ent));
+                  res.mismatches = (uint8_t)low;
+                  res.low_hit_instances = 1;
+                } else {
+                  res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
+                  res.strand = '?';
+                  res.low_hit_instances = (int16_t)(inst > P.max_hits ? P.max_hits + 1 : inst);
+                }
+              }
+              if (done) {
+                out[r] = res;
+                stats_add_basic(bs, res);
+              }
+            }
+          }
+          B.ph[r] = (uint8_t)state;
+        }
+      }
+      if (handed_on) B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = r;
     }
-    B.ph[r] = (uint8_t)state;
-    B.act[0][wave_push(B.cnt + kWaveCntAct)] = r;
+    if (mode == 2) continue;
+    // ---- (b) the lookups of the phase the read is in now
+    WavePhase ph;
+    ph.n_cores = 0; ph.CL = 0; ph.K = 0; ph.delta = 0; ph.last_ofs = 0; ph.mm_max = 0;
+    if (state != kWaveOff) wave_phase(P, w, state, ph);
+    const int maxc = __reduce_max_sync(0xffffffffu, ph.n_cores);
+    for (int s = s_first; s <= s_last; ++s) {
+      for (int c0 = 0; c0 < maxc; c0 += 4) {
+        uint64_t lo[4], hi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // four cores' lookups are issued before any of them is looked at
+          lo[j] = hi[j] = 0;
+          const int ci = c0 + j;
+          if (ci < ph.n_cores) {
+            const int cofs = ci <= ph.K ? ci * ph.delta : ph.last_ofs;
+            const uint64_t key = rev2(rr_word(q, s, cofs)) >> (64 - 2 * k);
+            if (ph.CL >= k) {
+              lo[j] = pt_get(I, key);
+              hi[j] = pt_get(I, key + 1);
+            } else {
+              const int sh = 2 * (k - ph.CL);
+              const uint64_t pfx = key >> sh;
+              lo[j] = pt_get(I, pfx << sh);
+              hi[j] = pt_get(I, (pfx + 1) << sh);
+            }
+          }
+        }
+        int mine = 0;
+        bool huge = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (hi[j] - lo[j] >= 0xffffffffull) { huge = true; hi[j] = lo[j]; }
+          mine += lo[j] < hi[j];
+        }
+        if (huge) B.fb[r] = 1;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int all = __shfl_sync(0xffffffffu, incl, 31);
+        if (all == 0) continue;
+        if (cur + (uint64_t)all > end) {   // the warp's chunk is used up: close it, take the next
+          for (uint64_t i = cur + lane; i < end; i += 32) B.items[i] = make_ulonglong4(0, kWaveNoItem, 0, 0);
+          unsigned int nb = 0;
+          if (lane == 0) nb = atomicAdd(q_count, (unsigned)kWaveChunk);
+          nb = __shfl_sync(0xffffffffu, nb, 0);
+          cur = nb;
+          end = cur + kWaveChunk;
+        }
+        if (end > B.item_cap) {   // queue full: these reads are redone by align_fast_kernel
+          if (mine) B.fb[r] = 1;
+          cur = end = 0;
+          continue;
+        }
+        uint64_t at = cur + (uint64_t)(incl - mine);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (lo[j] < hi[j]) {
+            B.items[at++] = make_ulonglong4(lo[j] | ((uint64_t)s << 40) | ((uint64_t)(c0 + j) << 41),
+                                            (uint64_t)r | ((hi[j] - lo[j]) << 32),
+                                            q.bo | ((uint64_t)q.L << 44) | ((uint64_t)state << 56), 0);
+          }
+        }
+        cur += (uint64_t)all;
+      }
+    }
   }
+  for (uint64_t i = cur + lane; i < end; i += 32) B.items[i] = make_ulonglong4(0, kWaveNoItem, 0, 0);
   __syncthreads();
   if (stats) stats_flush(bs, stats);
 }
 
-// one thread per (read of the wave, strand): the prefix-table lookups of all cores of the read's phase
-__global__ void __launch_bounds__(kWaveThreads) wave_lookup_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
-                                                                   Packed2Src p2, WaveBuf B, int round) {
-  const unsigned n_act = B.cnt[kWaveCntAct + round];
-  const uint32_t* __restrict__ act = B.act[round & 1];
-  const int s_first = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
-  const int s_last = (P.strand_mode == BKX_STRAND_WATSON) ? 0 : 1;
-  const bool both = s_last > s_first;
-  const uint64_t total = (uint64_t)n_act << (both ? 1 : 0);
+// one thread per item: the suffix-array element the search of its bucket looks at first -- the bucket's last one when
+// the bucket is the interval (core no longer than the table key), its middle one otherwise.  Nothing but that gather.
+__global__ void __launch_bounds__(kWaveThreads) wave_sa_kernel(DevIndex I, KParams P, WaveBuf B, int round) {
+  const uint64_t n_raw = B.cnt[kWaveCntItems + round];
+  const uint64_t n_items = n_raw < B.item_cap ? n_raw : (B.item_cap / kWaveChunk) * kWaveChunk;
   const int k = I.k;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const uint32_t r = __ldg(act + (both ? (t >> 1) : t));
-    const int s = both ? (int)(t & 1) : s_first;
-    const uint64_t o0 = __ldg(offs + r);
-    ReadRef q;
-    q.words = p2.words; q.bo = o0 + p2.phase; q.L = (int)(__ldg(offs + r + 1) - o0);
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += stride) {
+    const ulonglong4 it = B.items[t];
+    if (it.y == kWaveNoItem) continue;
+    const uint64_t blo = it.x & 0xffffffffffull, size = it.y >> 32;
     WaveRead w;
-    wave_read(P, q.L, w);
+    wave_read(P, (int)((it.z >> 44) & 0xfff), w);
     WavePhase ph;
-    wave_phase(P, w, B.ph[r], ph);
-    for (int c0 = 0; c0 < ph.n_cores; c0 += 4) {
-      uint64_t lo[4], hi[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {   // four cores' lookups are issued before any of them is looked at
-        lo[j] = hi[j] = 0;
-        const int ci = c0 + j;
-        if (ci < ph.n_cores) {
-          const int cofs = ci <= ph.K ? ci * ph.delta : ph.last_ofs;
-          const uint64_t key = rev2(rr_word(q, s, cofs)) >> (64 - 2 * k);
-          if (ph.CL >= k) {
-            lo[j] = pt_get(I, key);
-            hi[j] = pt_get(I, key + 1);
-          } else {
-            const int sh = 2 * (k - ph.CL);
-            const uint64_t pfx = key >> sh;
-            lo[j] = pt_get(I, pfx << sh);
-            hi[j] = pt_get(I, (pfx + 1) << sh);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (lo[j] < hi[j]) {
-          const uint64_t size = hi[j] - lo[j];
-          const uint64_t at = size < 0xffffffffull ? (uint64_t)wave_push(B.cnt + kWaveCntItems + round) : ~0ull;
-          if (at >= B.item_cap) { B.fb[r] = 1; continue; }
-          B.items[at] = make_ulonglong2(lo[j] | ((uint64_t)s << 40) | ((uint64_t)(c0 + j) << 41), (uint64_t)r | (size << 32));
-        }
-      }
-    }
+    wave_phase(P, w, (unsigned)(it.z >> 56), ph);
+    const uint64_t at = ph.CL <= k ? blo + size - 1 : blo + (size >> 1);
+    reinterpret_cast<uint64_t*>(B.items + t)[3] = sa_get(I, at);
   }
 }
 
 // one thread per item: the core's interval inside its bucket, the walk over it, Hamming of every placement
 // (the body of align_fast_kernel's step (2), with the read taken from the 2-bit stream)
-__global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
-                                                                  Packed2Src p2, WaveBuf B, int round) {
+__global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KParams P, Packed2Src p2, WaveBuf B, int round) {
   const uint64_t n_raw = B.cnt[kWaveCntItems + round];
-  const uint64_t n_items = n_raw < B.item_cap ? n_raw : B.item_cap;
+  const uint64_t n_items = n_raw < B.item_cap ? n_raw : (B.item_cap / kWaveChunk) * kWaveChunk;
   const int k = I.k;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += stride) {
-    const ulonglong2 it = B.items[t];
+    const ulonglong4 it = B.items[t];
+    if (it.y == kWaveNoItem) continue;
     const uint64_t blo = it.x & 0xffffffffffull, bhi = blo + (it.y >> 32);
     const int s = (int)((it.x >> 40) & 1), ci = (int)(it.x >> 41);
     const uint32_t r = (uint32_t)it.y;
-    const uint64_t o0 = __ldg(offs + r);
     ReadRef q;
-    q.words = p2.words; q.bo = o0 + p2.phase; q.L = (int)(__ldg(offs + r + 1) - o0);
+    q.words = p2.words; q.bo = it.z & ((1ull << 44) - 1); q.L = (int)((it.z >> 44) & 0xfff);
     const int L = q.L;
     WaveRead w;
     wave_read(P, L, w);
     WavePhase ph;
-    wave_phase(P, w, B.ph[r], ph);
+    wave_phase(P, w, (unsigned)(it.z >> 56), ph);
     const int CL = ph.CL;
     const int cofs = ci <= ph.K ? ci * ph.delta : ph.last_ofs;
     bool dfr = false;
     uint64_t first = 0, cnt = 0;
     bool located = false;
+    // the element wave_sa_kernel fetched: SA[at0] = g0
+    const uint64_t at0 = CL <= k ? bhi - 1 : blo + ((bhi - blo) >> 1), g0 = it.w;
     if (CL <= k) {
       // core no longer than the table key: the bucket IS the interval, except for suffixes holding an N/EOS inside the
       // core span, which sort at the bucket's end -- so if the last element matches, every element does
-      const uint64_t g = sa_get(I, bhi - 1);
-      if (!span_has_exc(I, g, (uint32_t)CL) && rr_cmp(I, q, s, cofs, CL, g) == 0) {
+      if (!span_has_exc(I, g0, (uint32_t)CL) && rr_cmp(I, q, s, cofs, CL, g0) == 0) {
         first = blo;
         cnt = bhi - blo;
         located = true;
@@ -1331,7 +1485,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
       bool h_equal = false;
       while (l < h) {
         const uint64_t m = l + ((h - l) >> 1);
-        const uint64_t g = sa_get(I, m);
+        const uint64_t g = m == at0 ? g0 : sa_get(I, m);
         if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
         const int c = rr_cmp(I, q, s, cofs, CL, g);
         if (c > 0) l = m + 1; else { h = m; h_equal = (c == 0); }
@@ -1350,7 +1504,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
       }
     }
     for (uint64_t e = 0; e < cnt && !dfr; ++e) {
-      const uint64_t loci = sa_get(I, first + e);
+      const uint64_t loci = first + e == at0 ? g0 : sa_get(I, first + e);
       if (loci < (uint64_t)cofs) continue;
       const uint64_t p = loci - (uint64_t)cofs;
       const int ent = find_entry(I, p);
@@ -1366,10 +1520,10 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
         const uint64_t next = __ldg(I.g2 + (++gw_i));
         const uint64_t gw = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
         prev = next;
-        const uint64_t x = rr_word(q, s, b) ^ gw;   // rr_word is zero beyond the read: mask the genome side
+        const uint64_t x = rr_word(q, s, b) ^ gw;
         uint64_t m = (x | (x >> 1)) & 0x5555555555555555ull;
         const int rem = L - b;
-        if (rem < 32) m &= (1ull << (2 * rem)) - 1;
+        if (rem < 32) m &= (1ull << (2 * rem)) - 1;   // rr_word is zero beyond the read: the genome side is masked here
         mm += __popcll(m);
         if (mm > ph.mm_max) break;
       }
@@ -1380,118 +1534,6 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
   }
 }
 
-// one thread per read of the wave: what the phase found, then the read's result or its next phase
-__global__ void __launch_bounds__(kWaveThreads) wave_reduce_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
-                                                                   WaveBuf B, int round, bkx_read_result* __restrict__ out,
-                                                                   bkx_align_stats* __restrict__ stats) {
-  __shared__ BlockStats bs;
-  for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
-  __syncthreads();
-  const unsigned n_act = B.cnt[kWaveCntAct + round];
-  const uint32_t* __restrict__ act = B.act[round & 1];
-  uint32_t* __restrict__ act_next = B.act[(round + 1) & 1];
-  const int n_strands = (P.strand_mode == BKX_STRAND_BOTH) ? 2 : 1;
-  const bool wide = I.n > (1ull << 32);
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_act; t += stride) {
-    const uint32_t r = __ldg(act + t);
-    if (B.fb[r]) {
-      B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = r;
-      continue;
-    }
-    const int L = (int)(__ldg(offs + r + 1) - __ldg(offs + r));
-    WaveRead w;
-    wave_read(P, L, w);
-    const unsigned state = B.ph[r];
-    WavePhase ph;
-    wave_phase(P, w, state, ph);
-    const unsigned nc = B.ncand[r];
-    int inst = 0, low = ph.mm_max + P.mmd + 1, nxt = low;
-    unsigned distinct = 0;
-    uint64_t hit = 0;
-    bool redo = false;
-    if (nc) {
-      const uint64_t* __restrict__ row = B.cand + (size_t)r * B.row;
-      const uint64_t kmask = (1ull << 41) - 1;   // placement + strand
-      for (unsigned i = 0; i < nc; ++i) {
-        const uint64_t c = row[i];
-        const uint64_t key = c & kmask;
-        bool dup = false;
-        for (unsigned j = 0; j < i; ++j) {
-          const uint64_t kj = row[j] & kmask;
-          if (kj == key) dup = true;
-          // the reference's "already processed" keys are 32 bits wide (SfxArrayV2.cpp:6093): beyond 2^32 symbols two
-          // placements of one strand can share a key, and which of them is dropped depends on the order they are met in
-          else if (wide && ((kj ^ key) >> 40) == 0 && (uint32_t)kj == (uint32_t)key) redo = true;
-        }
-        if (dup) continue;
-        ++distinct;
-        const int mm = (int)((c >> 41) & 127);
-        if (mm == (int)kWaveFailed) continue;
-        if (mm < low) { inst = 1; nxt = low; low = mm; hit = c; }
-        else if (mm == low) ++inst;
-        else if (mm < nxt) nxt = mm;
-      }
-      B.ncand[r] = 0;
-    }
-    // more exact placements than MaxHits: the reference stops the phase there (SfxArrayV2.cpp:6199) and what it has
-    // seen by then depends on the order
-    if (redo || (inst > P.max_hits && low == 0)) {
-      B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = r;
-      continue;
-    }
-    const uint2 acc = B.acc[r];
-    const uint32_t seeds = acc.x + (uint32_t)(n_strands * ph.n_cores), cands = acc.y + distinct;
-    bkx_read_result res;
-    if (inst == 0) {
-      const int next = wave_enter(P, w, (int)state, false);
-      if (next >= 0) {
-        B.ph[r] = (uint8_t)next;
-        B.acc[r] = make_uint2(seeds, cands);
-        act_next[wave_push(B.cnt + kWaveCntAct + round + 1)] = r;
-        continue;
-      }
-      wave_none_result(res, seeds, cands);
-    } else {
-      // ProcCoredApprox's mapping for the default multi-loci mode (finish() of align_fast_kernel)
-      wave_none_result(res, seeds, cands);
-      const int hr = (nxt - low) < P.mmd ? BKX_HR_MMDELTA : inst > P.max_hits ? BKX_HR_HITINSTS : BKX_HR_HITS;
-      res.hit_rslt = (uint8_t)hr;
-      res.low_mm = (int8_t)low;
-      res.nxt_low_mm = (int8_t)nxt;
-      res.match_len = (uint16_t)L;
-      if (hr == BKX_HR_HITS) {
-        const uint64_t p = hit & 0xffffffffffull;
-        const int ent = find_entry(I, p);
-        res.nar = BKX_NAR_ACCEPTED;
-        res.num_hits = 1;
-        res.strand = ((hit >> 40) & 1) ? '-' : '+';
-        res.chrom_id = __ldg(I.ent_id + ent);
-        res.match_loci = (uint32_t)(p - __ldg(I.ent_start + ent));
-        res.mismatches = (uint8_t)low;
-        res.low_hit_instances = 1;
-      } else {
-        res.nar = (hr == BKX_HR_MMDELTA) ? BKX_NAR_MMDELTA : BKX_NAR_MULTIALIGN;
-        res.strand = '?';
-        res.low_hit_instances = (int16_t)(inst > P.max_hits ? P.max_hits + 1 : inst);
-      }
-    }
-    out[r] = res;
-    stats_add_basic(bs, res);
-  }
-  __syncthreads();
-  if (stats) stats_flush(bs, stats);
-}
-
-// reads still on a wave after the last round (none, unless the round count was short): redone like the others
-__global__ void __launch_bounds__(kWaveThreads) wave_drain_kernel(WaveBuf B, int round) {
-  const unsigned n_act = B.cnt[kWaveCntAct + round];
-  const uint32_t* __restrict__ act = B.act[round & 1];
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_act; t += stride)
-    B.fb_ids[wave_push(B.cnt + kWaveCntFallback)] = __ldg(act + t);
-}
-
 // a read goes through at most one phase per allowance 0..MaxTotMM and the final one
 static int wave_rounds(const KParams& P, uint32_t max_len) {
   const uint32_t len = max_len < (uint32_t)kFastMaxLen ? max_len : (uint32_t)kFastMaxLen;
@@ -1499,7 +1541,7 @@ static int wave_rounds(const KParams& P, uint32_t max_len) {
   if (mt > 63) mt = 63;
   return std::min(mt + 2, kWaveMaxRounds - 1);
 }
-int wave_launches(const KParams& P, uint32_t max_len) { return 2 + 3 * wave_rounds(P, max_len); }
+int wave_launches(const KParams& P, uint32_t max_len) { return 1 + 3 * wave_rounds(P, max_len); }
 
 cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* offs, uint32_t n_reads, uint32_t max_len,
                         const Packed2Src& p2, const WaveBuf& B, bkx_read_result* out, bkx_align_stats* stats, int sms,
@@ -1507,20 +1549,20 @@ cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* off
   cudaError_t e = cudaMemsetAsync(B.cnt, 0, kWaveCounters * sizeof(unsigned int), st);
   if (e != cudaSuccess) return e;
   const int grid = sms * (2048 / kWaveThreads);
-  wave_init_kernel<<<grid, kWaveThreads, 0, st>>>(P, offs, n_reads, p2, B, out, stats);
   const int rounds = wave_rounds(P, max_len);
   static const bool trace = getenv("BKX_TRACE") != nullptr;   // diagnostic: time of every kernel of every round, serialising
   std::vector<cudaEvent_t> ev;
   auto mark = [&]() { if (trace) { cudaEvent_t e2; cudaEventCreate(&e2); cudaEventRecord(e2, st); ev.push_back(e2); } };
   mark();
   for (int round = 0; round < rounds; ++round) {
-    wave_lookup_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, p2, B, round);
+    wave_step_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, n_reads, p2, B, round, round == 0 ? 0 : 1, out, stats);
     mark();
-    wave_probe_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, p2, B, round);
+    wave_sa_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, B, round);
     mark();
-    wave_reduce_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, B, round, out, stats);
+    wave_probe_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, p2, B, round);
     mark();
   }
+  wave_step_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, n_reads, p2, B, rounds, 2, out, stats);
   if (trace) {
     cudaStreamSynchronize(st);
     std::vector<unsigned int> c(kWaveCounters);
@@ -1530,12 +1572,11 @@ cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* off
       cudaEventElapsedTime(&a, ev[3 * round], ev[3 * round + 1]);
       cudaEventElapsedTime(&b, ev[3 * round + 1], ev[3 * round + 2]);
       cudaEventElapsedTime(&d, ev[3 * round + 2], ev[3 * round + 3]);
-      fprintf(stderr, "[bkx trace] wave %d: %u reads, %u items; lookup %.3f ms, probe %.3f ms, reduce %.3f ms\n", round,
-              c[kWaveCntAct + round], c[kWaveCntItems + round], a, b, d);
+      fprintf(stderr, "[bkx trace] wave %d: %u item slots; step %.3f ms, sa %.3f ms, probe %.3f ms\n", round,
+              c[kWaveCntItems + round], a, b, d);
     }
     for (cudaEvent_t e2 : ev) cudaEventDestroy(e2);
   }
-  wave_drain_kernel<<<grid, kWaveThreads, 0, st>>>(B, rounds);
   return cudaGetLastError();
 }
 

@@ -29,21 +29,23 @@
 namespace bkx {
 
 constexpr int kWaveMaxRounds = 66;        // staged phases 0..63 + the final one (+1)
-constexpr int kWaveCntAct = 0;            // counters: reads in wave i at [i]
-constexpr int kWaveCntItems = 80;         //           items of wave i at [80 + i]
+constexpr int kWaveCntItems = 80;         // counters: item slots of wave i at [80 + i]
 constexpr int kWaveCntFallback = 160;     //           reads handed to align_fast_kernel
 constexpr int kWaveCounters = 176;
 constexpr unsigned kWaveFailed = 127;     // candidate record: more mismatches than the phase allows
+constexpr unsigned kWaveOff = 0xffu;      // state byte: the read is not (or no longer) on the wave path
+constexpr int kWaveChunk = 256;           // item slots a warp takes from the queue at a time (>= 4 x 32)
+constexpr unsigned long long kWaveNoItem = ~0ull;   // items[].y of an empty slot
 
 struct WaveBuf {
-  uint32_t* act[2] = {nullptr, nullptr};  // read ids of the current / the next wave
   unsigned int* cnt = nullptr;            // kWaveCounters counters
-  uint8_t* ph = nullptr;                  // per read: allow (bits 0..6) | final phase (bit 7)
+  uint8_t* ph = nullptr;                  // per read: allow (bits 0..6) | final phase (bit 7); kWaveOff: not on the wave path
   uint8_t* fb = nullptr;                  // per read: must be redone by align_fast_kernel
   uint2* acc = nullptr;                   // per read: seeds, candidates of its finished phases
   uint32_t* ncand = nullptr;              // per read: candidate records of the current phase
   uint64_t* cand = nullptr;               // per read: `row` records: placement (40 bits) | strand << 40 | mismatches << 41
-  ulonglong2* items = nullptr;            // x: bucket start (40 bits) | strand << 40 | core << 41;  y: read | bucket size << 32
+  ulonglong4* items = nullptr;            // x: bucket start (40 bits) | strand << 40 | core << 41;  y: read | bucket size << 32;
+                                          // z: the read's first base in the 2-bit stream (44 bits) | length << 44 | state << 56
   uint32_t* fb_ids = nullptr;
   uint64_t item_cap = 0;
   int row = 8;

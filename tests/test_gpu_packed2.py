@@ -60,6 +60,38 @@ def test_packed2_records_equal_byte_per_base_records(case, tag, tiny_slices, gol
     idx.close()
 
 
+@pytest.mark.parametrize("tiny_slices", [False, True])
+@pytest.mark.parametrize("case,tag", CASES)
+def test_wave_path_gives_the_same_records(case, tag, tiny_slices, golden_dir):
+    """BKX_WAVE=1: the default search laid out as streaming kernels per phase (bkx_wave.cuh), the lane-per-read kernel
+    redoing what that path hands on -- the records and the statistics (with the seed and candidate totals) equal those of
+    the default path.  (profiles/ab_kernel.py compares the 32-byte records of both paths byte for byte at full size.)"""
+    run = gu.runs(case)[tag]
+    idx = bkx.Index.open(gu.sfx_path(case, golden_dir))
+    names, bases, offs = gu.load_reads(case, run)
+    p, pe = gu.params_from_args(idx, run["args"])
+    ld, ld2 = np.zeros(100001, dtype=np.uint32), np.zeros(100001, dtype=np.uint32)
+    if pe is None:
+        exp, est = idx.align(p, bases, offs)
+    else:
+        exp, est, eps = idx.align_pairs(p, pe, bases, offs, len_dist=ld)
+    os.environ["BKX_WAVE"] = "1"
+    if tiny_slices:
+        os.environ["BKX_SLICE_MIN"], os.environ["BKX_SLICE_MAX"] = "1024", "1999"
+    try:
+        if pe is None:
+            got, gst = idx.align_packed2(p, bases, offs)
+        else:
+            got, gst, gps = idx.align_packed2(p, bases, offs, pe=pe, len_dist=ld2)
+            assert bytes(gps) == bytes(eps) and np.array_equal(ld, ld2)
+    finally:
+        for v in ("BKX_WAVE", "BKX_SLICE_MIN", "BKX_SLICE_MAX"):
+            os.environ.pop(v, None)
+    same_records(got, exp)                  # the 16-byte records carry no per-read seed / candidate counts ...
+    assert gst.as_dict() == est.as_dict()   # ... their sums are in the statistics
+    idx.close()
+
+
 def test_packed2_non_acgt_codes_and_odd_offsets(golden_dir):
     """Reads of every length 20..90 back to back (every slice start phase), Ns and InDel / undefined codes sprinkled in."""
     idx = bkx.Index.open(gu.sfx_path("tiny", golden_dir))
