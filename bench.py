@@ -104,11 +104,23 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(args):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu
-    capture -- only when this run is the workload that capture was taken on (else null)."""
+KERNELS_LANE = "align_fast_kernel + align_reads_kernel (deferred reads)"
+KERNELS_WAVE = ("one search launch = wave_step_kernel + wave_probe_kernel per search phase (bkx_wave.cuh), then align_fast_kernel "
+                "and align_reads_kernel on the reads handed on")
+
+
+def search_kernels(launches_per_step):
+    """Which kernels one device-resident search call launched (the wave path starts ~20 of them)."""
+    return KERNELS_WAVE if launches_per_step > 4 else KERNELS_LANE
+
+
+def ncu_traffic(args, launches_per_step=2):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one search launch, from the committed ncu capture -- only when this
+    run is the workload AND the kernels that capture was taken on (else null)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r02_final_traffic.json")))
+        if (launches_per_step > 4) != bool(t.get("wave_path", False)):
+            return None
         w = t["workload"]
         same = (float(args.genome_mbp) == w["genome_mbp"] and args.reads == w["reads"] and args.read_len == w["read_len"] and
                 args.read_subs == w["read_subs"] and args.max_subs == w["max_subs"] and args.seed == w["seed"] and
@@ -379,10 +391,11 @@ def run_bkx(args):
                                        "d2h_bytes_per_step": int(nreads * 32)}},
         "gpu_launches": int(args.steps * launches_per_step),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args), "kernel": "align_fast_kernel + align_reads_kernel (deferred reads)",
+                     "traffic": ncu_traffic(args, launches_per_step), "kernel": search_kernels(launches_per_step),
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": int(alg_bytes), "bytes_per_read": alg_bytes / nreads,
                      "peak_source": peak_src,
-                     "traffic_source": "profiles/r02_final_traffic.json (ncu --set full, one launch of align_fast_kernel)"},
+                     "traffic_source": "profiles/r02_final_traffic.json (ncu, one search launch of the same kernels; null when "
+                                       "this run used other kernels or another workload)"},
         "clocks": clocks,
         "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]},
         "stats_reads_all_ranks": int(stats[-1]),
@@ -641,7 +654,7 @@ def run_hexaploid(args):
         "gpu_launches": int(args.steps * launches_per_step),
         "roofline": {"bound": "hbm", "achieved": alg / (kms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (kms / 1e3) / 1e9 / peak, "traffic": None,
-                     "kernel": "align_fast_kernel + align_reads_kernel (deferred reads)", "kernel_ms": kms,
+                     "kernel": search_kernels(launches_per_step), "kernel_ms": kms,
                      "algorithmic_bytes_per_launch": int(alg), "bytes_per_read": alg / nreads, "peak_source": peak_src},
         "clocks": clocks,
         "classes": {abi.NAR_CODES[i]: int(nar[i]) for i in range(abi.NAR_COUNT) if nar[i]},

@@ -947,6 +947,7 @@ static bool ensure_wave(bkx_index* x, int si, uint32_t n, cudaStream_t st) {
   }
   B.item_cap = item_cap;
   B.row = row;
+  B.sa_split = getenv("BKX_WAVE_SA_SPLIT") ? 1 : 0;   // tuning hook
   s.wave_cap = cap;
   return true;
 }
@@ -983,10 +984,12 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
   static const bool no_direct = getenv("BKX_NO_DIRECT2") != nullptr;   // tuning hook: ignore the 2-bit copy of the reads
   KParams kf = k;
   if (x->d.n > (1ull << 32)) kf.xdedup = 0;   // 32-bit dedup keys collide beyond 2^32 symbols: keep the reference's key set there
-  // The default search goes down the wave path first (bkx_wave.cuh) when the reads came 2-bit packed; the lane-per-read
-  // kernel then only redoes what that path hands on.
-  const char* wave_env = getenv("BKX_WAVE");   // read per launch: the A/B harness (profiles/ab_kernel.py) switches it inside one process
-  const int wave_mode = wave_env ? atoi(wave_env) : 0;
+  // The default search goes down the wave path first (bkx_wave.cuh) when the reads came 2-bit packed and the launch is large:
+  // its ~20 kernels per launch take 27.5 ms per 20 M reads against 29.5-30.4 ms for the lane-per-read kernel (configs[1]),
+  // but 3.7 ms against 2.8 ms per 2 M reads.  The lane-per-read kernel then only redoes what that path hands on.
+  // BKX_WAVE=0 / 1: never / always (read per launch: profiles/ab_kernel.py switches it inside one process).
+  const char* wave_env = getenv("BKX_WAVE");
+  const int wave_mode = wave_env ? atoi(wave_env) : (n >= kWaveAutoReads ? 1 : 0);
   const uint32_t* fast_ids = nullptr;
   const unsigned int* fast_n = nullptr;
   cudaEvent_t tw = nullptr;

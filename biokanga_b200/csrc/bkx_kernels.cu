@@ -1200,6 +1200,37 @@ __device__ __forceinline__ void wave_none_result(bkx_read_result& res, uint32_t 
   res.flags = 0; res.seeds = seeds; res.cands = cands; res.reserved = 0;
 }
 
+// The read of this lane, both strands, into its column of the block's shared memory (word w of strand s at wr[s][w * 32],
+// as in align_fast_kernel): every later extract is a conflict-free shared-memory access instead of a scattered global
+// load -- 32 lanes x 2-4 loads per extract kept the load/store unit, not DRAM, busy.
+__device__ __forceinline__ void wave_stage(const ReadRef& q, uint64_t* wr0, uint64_t* wr1, bool fwd_only) {
+  const int L = q.L, words = (L + 31) >> 5;
+  const uint64_t* src = q.words + (q.bo >> 5);
+  const unsigned sh = (unsigned)(q.bo & 31) * 2;
+  uint64_t prev = __ldg(src);
+  for (int w = 0; w < words; ++w) {
+    const uint64_t next = __ldg(src + w + 1);
+    uint64_t v = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
+    prev = next;
+    const int len = L - 32 * w;
+    if (len < 32) v &= (1ull << (2 * len)) - 1;
+    wr0[w * 32] = v;
+  }
+  wr0[words * 32] = 0;
+  if (fwd_only) return;
+  FastLane f;
+  f.w2[0] = wr0; f.w2[1] = wr1; f.seen = nullptr; f.L = L;
+  for (int w = 0; w < words; ++w) {
+    const int t = L - 32 * (w + 1);   // forward position of the last base of this reverse-complement word
+    const uint64_t fw = t >= 0 ? fl_word(f, 0, t) : (wr0[0] << (2 * (-t)));
+    uint64_t rc = rev2(~fw);
+    const int len = min(32, L - 32 * w);
+    if (len < 32) rc &= (1ull << (2 * len)) - 1;
+    wr1[w * 32] = rc;
+  }
+  wr1[words * 32] = 0;
+}
+
 // One thread per read, once per round: (a) what the read's phase of the previous round found -- then its result, or its
 // next phase (round 0: whether the read can go down this path at all, and its first phase); (b) the prefix-table lookups
 // of all cores of the phase it is in now, both strands, and an item per bucket that is not empty.  Items go to the queue
@@ -1208,11 +1239,17 @@ __device__ __forceinline__ void wave_none_result(bkx_read_result& res, uint32_t 
 // mode 0: first round; 1: a round in between; 2: after the last round -- (a) only, a read still on the path is handed on
 __global__ void __launch_bounds__(kWaveThreads) wave_step_kernel(DevIndex I, KParams P, const uint64_t* __restrict__ offs,
                                                                  uint32_t n_reads, Packed2Src p2, WaveBuf B, int round, int mode,
-                                                                 bkx_read_result* __restrict__ out,
+                                                                 int W, bkx_read_result* __restrict__ out,
                                                                  bkx_align_stats* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char wave_smem[];
   __shared__ BlockStats bs;
   for (int i = threadIdx.x; i < (int)(sizeof(BlockStats) / 4); i += blockDim.x) ((unsigned int*)&bs)[i] = 0;
   __syncthreads();
+  FastLane f;   // this lane's column of the block's staging area: W words per strand
+  f.w2[0] = (uint64_t*)wave_smem + (size_t)(threadIdx.x >> 5) * ((size_t)2 * W * 32) + (threadIdx.x & 31);
+  f.w2[1] = f.w2[0] + (size_t)W * 32;
+  f.seen = nullptr;
+  f.L = 0;
   const int s_first = (P.strand_mode == BKX_STRAND_CRICK) ? 1 : 0;
   const int s_last = (P.strand_mode == BKX_STRAND_WATSON) ? 0 : 1;
   const int n_strands = s_last - s_first + 1;
@@ -1235,7 +1272,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_step_kernel(DevIndex I, KPa
       if (mode == 0) {
         const uint64_t o0 = __ldg(offs + r);
         const uint64_t len = __ldg(offs + r + 1) - o0;
-        if (len < 1 || len > (uint64_t)kFastMaxLen || (p2.flags && __ldg(p2.flags + r))) {
+        if (len < 1 || len > (uint64_t)kFastMaxLen || (int)((len + 31) >> 5) + 1 > W || (p2.flags && __ldg(p2.flags + r))) {
           handed_on = true;
         } else {
           q.bo = o0 + p2.phase; q.L = (int)len;
@@ -1353,7 +1390,11 @@ __global__ void __launch_bounds__(kWaveThreads) wave_step_kernel(DevIndex I, KPa
     // ---- (b) the lookups of the phase the read is in now
     WavePhase ph;
     ph.n_cores = 0; ph.CL = 0; ph.K = 0; ph.delta = 0; ph.last_ofs = 0; ph.mm_max = 0;
-    if (state != kWaveOff) wave_phase(P, w, state, ph);
+    if (state != kWaveOff) {
+      wave_phase(P, w, state, ph);
+      wave_stage(q, (uint64_t*)f.w2[0], (uint64_t*)f.w2[1], s_first == s_last && s_first == 0);
+      f.L = q.L;
+    }
     const int maxc = __reduce_max_sync(0xffffffffu, ph.n_cores);
     for (int s = s_first; s <= s_last; ++s) {
       for (int c0 = 0; c0 < maxc; c0 += 4) {
@@ -1364,7 +1405,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_step_kernel(DevIndex I, KPa
           const int ci = c0 + j;
           if (ci < ph.n_cores) {
             const int cofs = ci <= ph.K ? ci * ph.delta : ph.last_ofs;
-            const uint64_t key = rev2(rr_word(q, s, cofs)) >> (64 - 2 * k);
+            const uint64_t key = rev2(fl_word(f, s, cofs)) >> (64 - 2 * k);
             if (ph.CL >= k) {
               lo[j] = pt_get(I, key);
               hi[j] = pt_get(I, key + 1);
@@ -1445,7 +1486,13 @@ __global__ void __launch_bounds__(kWaveThreads) wave_sa_kernel(DevIndex I, KPara
 
 // one thread per item: the core's interval inside its bucket, the walk over it, Hamming of every placement
 // (the body of align_fast_kernel's step (2), with the read taken from the 2-bit stream)
-__global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KParams P, Packed2Src p2, WaveBuf B, int round) {
+__global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KParams P, Packed2Src p2, WaveBuf B, int round,
+                                                                  int W) {
+  extern __shared__ __align__(16) unsigned char wave_smem[];
+  FastLane f;
+  f.w2[0] = (uint64_t*)wave_smem + (size_t)(threadIdx.x >> 5) * ((size_t)2 * W * 32) + (threadIdx.x & 31);
+  f.w2[1] = f.w2[0] + (size_t)W * 32;
+  f.seen = nullptr;
   const uint64_t n_raw = B.cnt[kWaveCntItems + round];
   const uint64_t n_items = n_raw < B.item_cap ? n_raw : (B.item_cap / kWaveChunk) * kWaveChunk;
   const int k = I.k;
@@ -1459,6 +1506,8 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
     ReadRef q;
     q.words = p2.words; q.bo = it.z & ((1ull << 44) - 1); q.L = (int)((it.z >> 44) & 0xfff);
     const int L = q.L;
+    f.L = L;
+    wave_stage(q, (uint64_t*)f.w2[0], (uint64_t*)f.w2[1], s == 0);   // only strand s is looked at
     WaveRead w;
     wave_read(P, L, w);
     WavePhase ph;
@@ -1468,12 +1517,13 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
     bool dfr = false;
     uint64_t first = 0, cnt = 0;
     bool located = false;
-    // the element wave_sa_kernel fetched: SA[at0] = g0
-    const uint64_t at0 = CL <= k ? bhi - 1 : blo + ((bhi - blo) >> 1), g0 = it.w;
+    // the element the search of the bucket looks at first -- SA[at0] = g0 -- comes from wave_sa_kernel when that ran
+    const uint64_t at0 = CL <= k ? bhi - 1 : blo + ((bhi - blo) >> 1);
+    const uint64_t g0 = B.sa_split ? it.w : sa_get(I, at0);
     if (CL <= k) {
       // core no longer than the table key: the bucket IS the interval, except for suffixes holding an N/EOS inside the
       // core span, which sort at the bucket's end -- so if the last element matches, every element does
-      if (!span_has_exc(I, g0, (uint32_t)CL) && rr_cmp(I, q, s, cofs, CL, g0) == 0) {
+      if (!span_has_exc(I, g0, (uint32_t)CL) && fl_cmp(I, f, s, cofs, CL, g0) == 0) {
         first = blo;
         cnt = bhi - blo;
         located = true;
@@ -1487,7 +1537,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
         const uint64_t m = l + ((h - l) >> 1);
         const uint64_t g = m == at0 ? g0 : sa_get(I, m);
         if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
-        const int c = rr_cmp(I, q, s, cofs, CL, g);
+        const int c = fl_cmp(I, f, s, cofs, CL, g);
         if (c > 0) l = m + 1; else { h = m; h_equal = (c == 0); }
       }
       if (!dfr && l < bhi && h_equal) {
@@ -1497,7 +1547,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
           if (ul - first >= (uint64_t)kFastMaxCnt) { dfr = true; break; }
           const uint64_t g = sa_get(I, ul);
           if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
-          if (rr_cmp(I, q, s, cofs, CL, g) != 0) break;
+          if (fl_cmp(I, f, s, cofs, CL, g) != 0) break;
           ++ul;
         }
         cnt = ul - first;
@@ -1516,14 +1566,14 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
       const unsigned sh = (unsigned)(p & 31) * 2;
       uint64_t prev = __ldg(I.g2 + gw_i);
       int mm = 0;
-      for (int b = 0; b < L; b += 32) {
+      for (int b = 0, wi = 0; b < L; b += 32, ++wi) {
         const uint64_t next = __ldg(I.g2 + (++gw_i));
         const uint64_t gw = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
         prev = next;
-        const uint64_t x = rr_word(q, s, b) ^ gw;
+        const uint64_t x = f.w2[s][wi * 32] ^ gw;
         uint64_t m = (x | (x >> 1)) & 0x5555555555555555ull;
         const int rem = L - b;
-        if (rem < 32) m &= (1ull << (2 * rem)) - 1;   // rr_word is zero beyond the read: the genome side is masked here
+        if (rem < 32) m &= (1ull << (2 * rem)) - 1;   // the read's last word is zero beyond its end: mask the genome side
         mm += __popcll(m);
         if (mm > ph.mm_max) break;
       }
@@ -1550,19 +1600,22 @@ cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* off
   if (e != cudaSuccess) return e;
   const int grid = sms * (2048 / kWaveThreads);
   const int rounds = wave_rounds(P, max_len);
+  // staging area: two strands x W words per thread (reads of up to kFastMaxLen bases: 11 words, 45 KB per block)
+  const int W = (int)((std::min<uint32_t>(std::max<uint32_t>(max_len, 1), (uint32_t)kFastMaxLen) + 31) / 32) + 1;
+  const size_t smem = (size_t)2 * W * 8 * kWaveThreads;
   static const bool trace = getenv("BKX_TRACE") != nullptr;   // diagnostic: time of every kernel of every round, serialising
   std::vector<cudaEvent_t> ev;
   auto mark = [&]() { if (trace) { cudaEvent_t e2; cudaEventCreate(&e2); cudaEventRecord(e2, st); ev.push_back(e2); } };
   mark();
   for (int round = 0; round < rounds; ++round) {
-    wave_step_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, n_reads, p2, B, round, round == 0 ? 0 : 1, out, stats);
+    wave_step_kernel<<<grid, kWaveThreads, smem, st>>>(I, P, offs, n_reads, p2, B, round, round == 0 ? 0 : 1, W, out, stats);
     mark();
-    wave_sa_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, B, round);
+    if (B.sa_split) wave_sa_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, B, round);
     mark();
-    wave_probe_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, p2, B, round);
+    wave_probe_kernel<<<grid, kWaveThreads, smem, st>>>(I, P, p2, B, round, W);
     mark();
   }
-  wave_step_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, offs, n_reads, p2, B, rounds, 2, out, stats);
+  wave_step_kernel<<<grid, kWaveThreads, smem, st>>>(I, P, offs, n_reads, p2, B, rounds, 2, W, out, stats);
   if (trace) {
     cudaStreamSynchronize(st);
     std::vector<unsigned int> c(kWaveCounters);

@@ -3,17 +3,17 @@
 // The lane-per-read kernel carries one read through its phases, cores, interval walk and Hamming loop in ONE thread: every
 // DRAM line of a read is fetched behind the previous one, and a warp runs with a third of its lanes because its 32
 // reads stand at different places of that state machine (profiles/r02_final_align_fast_ncu.md).  Here the same work is
-// laid out by KIND instead of by read -- all reads that are in search phase `allow` go through three streaming kernels
-// together:
+// laid out by KIND instead of by read -- all reads that are in search phase `allow` go through two streaming kernels
+// together, once per phase ("round"):
 //
-//   wave_lookup  one thread per (read, strand): the prefix-table lookups of all its cores -- independent loads, issued
-//                four cores at a time -- and an ITEM (read, strand, core, bucket) for every bucket that is not empty;
-//   wave_probe   one thread per item: bound refinement in the bucket, interval walk, Hamming of every placement against
-//                the read; a CANDIDATE record (placement, strand, mismatches) per placement into the read's row;
-//   wave_reduce  one thread per read: "already processed" (the same placement reached through several cores), lowest /
-//                next-lowest mismatch count and instance count of the phase, and then either the read's result
-//                (ProcCoredApprox's mapping, Aligner.cpp:9239-9479) or its next phase (AlignReads' staged loop,
-//                SfxArrayV2.cpp:7666-7760) in the next wave.
+//   wave_step   one thread per read: (a) what the read's previous phase found -- "already processed" (one placement reached
+//               through several cores), lowest / next-lowest mismatch count and instance count -- and then either the
+//               read's result (ProcCoredApprox's mapping, Aligner.cpp:9239-9479) or its next phase (AlignReads' staged
+//               loop, SfxArrayV2.cpp:7666-7760); (b) the prefix-table lookups of all cores of the phase the read is in
+//               now -- independent loads, four cores at a time -- and an ITEM (read, strand, core, bucket) for every
+//               bucket that is not empty;
+//   wave_probe  one thread per item: bound refinement in the bucket, interval walk, Hamming of every placement against
+//               the read; a CANDIDATE record (placement, strand, mismatches) per placement into the read's row.
 //
 // What one phase of LocateCoreMultiples (SfxArrayV2.cpp:5693-6262) leaves behind -- LowHitInstances, LowMMCnt, NxtLowMMCnt
 // and the hit when it is unique -- does not depend on the order in which placements are met, with one exception: the early
@@ -21,6 +21,14 @@
 // kernel would hand on as well (an N or a chromosome end in a window, an interval of more than kFastMaxCnt suffixes, more
 // placements than its row holds, reads that did not arrive 2-bit packed), is put on a list and redone from scratch by
 // align_fast_kernel; so the result of a read still never depends on which kernel produced it.
+//
+// Measured (profiles/r02_experiments.md): 27.5 ms against 29.5-30.4 ms per 20 M reads at configs[1], 46.8 ms against 63 ms
+// at configs[3] (14 G symbols), but 3.7 ms against 2.8 ms per 2 M reads -- launches of kWaveAutoReads reads and more take
+// this path.  What it took: no list append through a returning atomic (one per warp bounded the first version at 2.9 ns
+// each -- items now go into chunks of the queue owned by a warp, and reads stay in place with a state byte instead of
+// being compacted), items that carry the read's position, length and phase (no dependent loads in front of the
+// suffix-array fetch), the read staged in shared memory.  Gathering the suffix-array element in a kernel of its own
+// (sa_split) and 1536 threads per SM for wave_probe both lost.
 //
 // Only the default search is laid out this way (no multi-loci option, no -N): those keep the lane-per-read kernel.
 #pragma once
@@ -34,6 +42,7 @@ constexpr int kWaveCntFallback = 160;     //           reads handed to align_fas
 constexpr int kWaveCounters = 176;
 constexpr unsigned kWaveFailed = 127;     // candidate record: more mismatches than the phase allows
 constexpr unsigned kWaveOff = 0xffu;      // state byte: the read is not (or no longer) on the wave path
+constexpr uint32_t kWaveAutoReads = 6000000;   // launches of at least this many reads take the wave path by default
 constexpr int kWaveChunk = 256;           // item slots a warp takes from the queue at a time (>= 4 x 32)
 constexpr unsigned long long kWaveNoItem = ~0ull;   // items[].y of an empty slot
 
@@ -49,6 +58,8 @@ struct WaveBuf {
   uint32_t* fb_ids = nullptr;
   uint64_t item_cap = 0;
   int row = 8;
+  int sa_split = 0;                       // 1: the first suffix-array element of every item is gathered by its own kernel
+                                          // (measured: 5.1 + 13.5 ms instead of 15.2 ms in one kernel -- off)
 };
 
 struct ReadRef { const uint64_t* words; uint64_t bo; int L; };

@@ -208,25 +208,38 @@ def algorithmic_bytes(results, concat_len, el_size, read_len):
     return seeds * S * (el_size + 8) + cands * (el_size + q) + len(results) * (q + 32)
 
 
-def pack2_device(d_bases, d_offs):
+def pack2_device(d_bases, d_offs, chunk_reads=1 << 21):
     """The 2-bit copy of device-resident reads that bkx_align_reads_device_packed2 takes beside the one-byte-per-base layout:
     (uint8 tensor of the packed stream with 16 bytes of slack -- base i at bits [2(i%4), +2) of byte i/4, non-ACGT bases as
-    0 --, uint8 per-read flags: the read holds a non-ACGT base)."""
+    0 --, uint8 per-read flags: the read holds a non-ACGT base).  Works through the reads a chunk at a time: beside a
+    144 GB index there is no room for whole-stream temporaries."""
     import torch
+    dev = d_bases.device
     nb = int(d_bases.numel())
-    codes = d_bases & 7
-    exc = codes > 3
-    c2 = torch.where(exc, torch.zeros_like(codes), codes)
-    pad = (-nb) % 4
-    if pad:
-        c2 = torch.cat([c2, torch.zeros(pad, dtype=c2.dtype, device=c2.device)])
-    q = c2.view(-1, 4)
-    pk = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).to(torch.uint8)
-    out = torch.zeros(((pk.numel() + 16 + 7) // 8) * 8, dtype=torch.uint8, device=d_bases.device)
-    out[:pk.numel()] = pk
-    # per-read flag: any exception inside [offs[r], offs[r + 1])
-    csum = torch.cumsum(exc.to(torch.int32), 0, dtype=torch.int64)
-    csum = torch.cat([torch.zeros(1, dtype=torch.int64, device=d_bases.device), csum])
-    o = d_offs.to(torch.int64)
-    flags = ((csum[o[1:]] - csum[o[:-1]]) > 0).to(torch.uint8)
+    n_reads = int(d_offs.numel()) - 1
+    out = torch.zeros((((nb + 3) // 4 + 16 + 7) // 8) * 8, dtype=torch.uint8, device=dev)
+    flags = torch.zeros(n_reads, dtype=torch.uint8, device=dev)
+    offs = d_offs.to(torch.int64)
+    r0 = 0
+    while r0 < n_reads:
+        r1 = min(n_reads, r0 + chunk_reads)
+        b0, b1 = int(offs[r0]), int(offs[r1])
+        a0 = b0 & ~3                          # start the chunk on a packed byte; the bases before b0 are packed again
+        codes = d_bases[a0:b1] & 7
+        exc = codes > 3
+        c2 = torch.where(exc, torch.zeros_like(codes), codes)
+        pad = (-int(c2.numel())) % 4
+        if pad:                               # only the last chunk can end inside a byte (the next one starts at b1 & ~3)
+            c2 = torch.cat([c2, torch.zeros(pad, dtype=c2.dtype, device=dev)])
+        q = c2.view(-1, 4)
+        pk = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).to(torch.uint8)
+        if r1 < n_reads and (b1 & 3):         # the byte shared with the next chunk is written by that chunk, in full
+            pk = pk[:-1]
+        out[a0 // 4:a0 // 4 + pk.numel()] = pk
+        csum = torch.cumsum(exc.to(torch.int32), 0, dtype=torch.int32)
+        csum = torch.cat([torch.zeros(1, dtype=torch.int32, device=dev), csum])
+        o = offs[r0:r1 + 1] - a0
+        flags[r0:r1] = ((csum[o[1:]] - csum[o[:-1]]) > 0).to(torch.uint8)
+        del codes, exc, c2, q, pk, csum, o
+        r0 = r1
     return out, flags
