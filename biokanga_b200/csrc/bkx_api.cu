@@ -948,6 +948,7 @@ static bool ensure_wave(bkx_index* x, int si, uint32_t n, cudaStream_t st) {
   B.item_cap = item_cap;
   B.row = row;
   B.sa_split = getenv("BKX_WAVE_SA_SPLIT") ? 1 : 0;   // tuning hook
+  B.half_loads = 1;
   s.wave_cap = cap;
   return true;
 }
@@ -997,6 +998,7 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
       x->d.n < (1ull << 40) && ensure_wave(x, si, n, st)) {
     int sms = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, x->device));
+    if (const char* hv = getenv("BKX_WAVE_HALF")) x->slot[si].wave.half_loads = atoi(hv) != 0;   // tuning hook, read per launch
     CU(launch_wave(x->d, k, d_offs, n, max_len, p2, x->slot[si].wave, d_out, d_stats, sms, st));
     fast_ids = x->slot[si].wave.fb_ids;
     fast_n = x->slot[si].wave.cnt + kWaveCntFallback;

@@ -41,6 +41,25 @@ struct DevIndex {
 
 constexpr int kPtBlockShift = 12;   // two-level prefix table: 4096 entries per block
 
+// Loads that ask L2 for 64 bytes of a missing line instead of all 128 (ld.global.nc.L2::64B; profiles/probes/gather_modes.cu:
+// 63.8 instead of 127.3 DRAM bytes per random gather, same gather rate).  For kernels that sit on the DRAM bandwidth with
+// single-element gathers -- the wave path's table and suffix-array lookups (5.0 TB/s before, profiles/r02_wave_ncu.md).
+__device__ __forceinline__ uint32_t ldg_half_u32(const uint32_t* p) {
+  uint32_t v;
+  asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint64_t ldg_half_u64(const uint64_t* p) {
+  uint64_t v;
+  asm("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_half_u8(const uint8_t* p) {
+  uint32_t v;
+  asm("ld.global.nc.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ uint64_t sa_get(const DevIndex& I, uint64_t i) {
   if (I.sa5) {   // 40 bits at byte 5i: one aligned 64-bit word, two when the element runs over its end
     const uint64_t a = i * 5;
@@ -57,6 +76,26 @@ __device__ __forceinline__ uint64_t sa_get(const DevIndex& I, uint64_t i) {
 
 __device__ __forceinline__ uint64_t pt_get(const DevIndex& I, uint64_t x) {
   uint64_t v = __ldg(I.pt32 + x);
+  if (I.pt_hi) v += __ldg(I.pt_hi + (x >> kPtBlockShift));
+  return v;
+}
+
+// sa_get / pt_get with the 64-byte loads above
+__device__ __forceinline__ uint64_t sa_get_half(const DevIndex& I, uint64_t i) {
+  if (I.sa5) {
+    const uint64_t a = i * 5;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(I.sa5) + (a >> 3);
+    const unsigned sh = (unsigned)(a & 7) * 8;
+    uint64_t v = ldg_half_u64(w) >> sh;
+    if (sh > 24) v |= ldg_half_u64(w + 1) << (64 - sh);
+    return v & 0xffffffffffull;
+  }
+  uint64_t v = ldg_half_u32(I.sa_lo + i);
+  if (I.sa_hi) v |= (uint64_t)ldg_half_u8(I.sa_hi + i) << 32;
+  return v;
+}
+__device__ __forceinline__ uint64_t pt_get_half(const DevIndex& I, uint64_t x) {
+  uint64_t v = ldg_half_u32(I.pt32 + x);
   if (I.pt_hi) v += __ldg(I.pt_hi + (x >> kPtBlockShift));
   return v;
 }

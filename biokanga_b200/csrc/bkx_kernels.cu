@@ -1258,6 +1258,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_step_kernel(DevIndex I, KPa
   const int lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   unsigned int* q_count = B.cnt + kWaveCntItems + round;
+  const bool half = B.half_loads != 0;
   uint64_t cur = 0, end = 0;   // this warp's chunk of the item queue (warp-uniform)
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n_reads; base += stride) {
     const uint32_t r = (uint32_t)(base + lane);
@@ -1407,8 +1408,8 @@ __global__ void __launch_bounds__(kWaveThreads) wave_step_kernel(DevIndex I, KPa
             const int cofs = ci <= ph.K ? ci * ph.delta : ph.last_ofs;
             const uint64_t key = rev2(fl_word(f, s, cofs)) >> (64 - 2 * k);
             if (ph.CL >= k) {
-              lo[j] = pt_get(I, key);
-              hi[j] = pt_get(I, key + 1);
+              lo[j] = half ? pt_get_half(I, key) : pt_get(I, key);
+              hi[j] = half ? pt_get_half(I, key + 1) : pt_get(I, key + 1);
             } else {
               const int sh = 2 * (k - ph.CL);
               const uint64_t pfx = key >> sh;
@@ -1486,6 +1487,7 @@ __global__ void __launch_bounds__(kWaveThreads) wave_sa_kernel(DevIndex I, KPara
 
 // one thread per item: the core's interval inside its bucket, the walk over it, Hamming of every placement
 // (the body of align_fast_kernel's step (2), with the read taken from the 2-bit stream)
+template <bool HALF>
 __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KParams P, Packed2Src p2, WaveBuf B, int round,
                                                                   int W) {
   extern __shared__ __align__(16) unsigned char wave_smem[];
@@ -1519,11 +1521,11 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
     bool located = false;
     // the element the search of the bucket looks at first -- SA[at0] = g0 -- comes from wave_sa_kernel when that ran
     const uint64_t at0 = CL <= k ? bhi - 1 : blo + ((bhi - blo) >> 1);
-    const uint64_t g0 = B.sa_split ? it.w : sa_get(I, at0);
+    const uint64_t g0 = B.sa_split ? it.w : wv_sa<HALF>(I, at0);
     if (CL <= k) {
       // core no longer than the table key: the bucket IS the interval, except for suffixes holding an N/EOS inside the
       // core span, which sort at the bucket's end -- so if the last element matches, every element does
-      if (!span_has_exc(I, g0, (uint32_t)CL) && fl_cmp(I, f, s, cofs, CL, g0) == 0) {
+      if (!span_has_exc(I, g0, (uint32_t)CL) && wv_cmp<HALF>(I, f, s, cofs, CL, g0) == 0) {
         first = blo;
         cnt = bhi - blo;
         located = true;
@@ -1535,9 +1537,9 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
       bool h_equal = false;
       while (l < h) {
         const uint64_t m = l + ((h - l) >> 1);
-        const uint64_t g = m == at0 ? g0 : sa_get(I, m);
+        const uint64_t g = m == at0 ? g0 : wv_sa<HALF>(I, m);
         if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
-        const int c = fl_cmp(I, f, s, cofs, CL, g);
+        const int c = wv_cmp<HALF>(I, f, s, cofs, CL, g);
         if (c > 0) l = m + 1; else { h = m; h_equal = (c == 0); }
       }
       if (!dfr && l < bhi && h_equal) {
@@ -1545,16 +1547,16 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
         uint64_t ul = l + 1;
         while (ul < bhi) {
           if (ul - first >= (uint64_t)kFastMaxCnt) { dfr = true; break; }
-          const uint64_t g = sa_get(I, ul);
+          const uint64_t g = wv_sa<HALF>(I, ul);
           if (span_has_exc(I, g, (uint32_t)CL)) { dfr = true; break; }
-          if (fl_cmp(I, f, s, cofs, CL, g) != 0) break;
+          if (wv_cmp<HALF>(I, f, s, cofs, CL, g) != 0) break;
           ++ul;
         }
         cnt = ul - first;
       }
     }
     for (uint64_t e = 0; e < cnt && !dfr; ++e) {
-      const uint64_t loci = first + e == at0 ? g0 : sa_get(I, first + e);
+      const uint64_t loci = first + e == at0 ? g0 : wv_sa<HALF>(I, first + e);
       if (loci < (uint64_t)cofs) continue;
       const uint64_t p = loci - (uint64_t)cofs;
       const int ent = find_entry(I, p);
@@ -1564,10 +1566,10 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
       // Hamming over packed words, given up once beyond the phase's allowance
       uint64_t gw_i = p >> 5;
       const unsigned sh = (unsigned)(p & 31) * 2;
-      uint64_t prev = __ldg(I.g2 + gw_i);
+      uint64_t prev = wv_g2<HALF>(I, gw_i);
       int mm = 0;
       for (int b = 0, wi = 0; b < L; b += 32, ++wi) {
-        const uint64_t next = __ldg(I.g2 + (++gw_i));
+        const uint64_t next = wv_g2<HALF>(I, ++gw_i);
         const uint64_t gw = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
         prev = next;
         const uint64_t x = f.w2[s][wi * 32] ^ gw;
@@ -1612,7 +1614,8 @@ cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* off
     mark();
     if (B.sa_split) wave_sa_kernel<<<grid, kWaveThreads, 0, st>>>(I, P, B, round);
     mark();
-    wave_probe_kernel<<<grid, kWaveThreads, smem, st>>>(I, P, p2, B, round, W);
+    if (B.half_loads) wave_probe_kernel<true><<<grid, kWaveThreads, smem, st>>>(I, P, p2, B, round, W);
+    else wave_probe_kernel<false><<<grid, kWaveThreads, smem, st>>>(I, P, p2, B, round, W);
     mark();
   }
   wave_step_kernel<<<grid, kWaveThreads, smem, st>>>(I, P, offs, n_reads, p2, B, rounds, 2, W, out, stats);

@@ -58,6 +58,7 @@ struct WaveBuf {
   uint32_t* fb_ids = nullptr;
   uint64_t item_cap = 0;
   int row = 8;
+  int half_loads = 1;                     // 64-byte L2 fetches for the table, suffix-array and genome gathers (BKX_WAVE_HALF=0: off)
   int sa_split = 0;                       // 1: the first suffix-array element of every item is gathered by its own kernel
                                           // (measured: 5.1 + 13.5 ms instead of 15.2 ms in one kernel -- off)
 };
@@ -97,6 +98,38 @@ __device__ __forceinline__ int rr_cmp(const DevIndex& I, const ReadRef& q, int s
     const uint64_t gw = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
     prev = next;
     const uint64_t rw = rr_word(q, s, ofs + b);
+    uint64_t x = rw ^ gw;
+    const int rem = len - b;
+    if (rem < 32) x &= (1ull << (2 * rem)) - 1;
+    if (x) {
+      const int pos = (__ffsll((long long)x) - 1) >> 1;
+      return ((rw >> (2 * pos)) & 3) > ((gw >> (2 * pos)) & 3) ? 1 : -1;
+    }
+  }
+  return 0;
+}
+
+// fl_cmp of bkx_fast.cuh with 64-byte genome loads (HALF), for the one-compare-per-item pattern of wave_probe
+template <bool HALF>
+__device__ __forceinline__ uint64_t wv_g2(const DevIndex& I, uint64_t w) {
+  if constexpr (HALF) return ldg_half_u64(I.g2 + w);
+  else return __ldg(I.g2 + w);
+}
+template <bool HALF>
+__device__ __forceinline__ uint64_t wv_sa(const DevIndex& I, uint64_t i) {
+  if constexpr (HALF) return sa_get_half(I, i);
+  else return sa_get(I, i);
+}
+template <bool HALF>
+__device__ __forceinline__ int wv_cmp(const DevIndex& I, const FastLane& f, int s, int ofs, int len, uint64_t g) {
+  uint64_t w = g >> 5;
+  const unsigned sh = (unsigned)(g & 31) * 2;
+  uint64_t prev = wv_g2<HALF>(I, w);
+  for (int b = 0; b < len; b += 32) {
+    const uint64_t next = wv_g2<HALF>(I, ++w);
+    const uint64_t gw = sh ? ((prev >> sh) | (next << (64 - sh))) : prev;
+    prev = next;
+    const uint64_t rw = fl_word(f, s, ofs + b);
     uint64_t x = rw ^ gw;
     const int rem = len - b;
     if (rem < 32) x &= (1ull << (2 * rem)) - 1;
