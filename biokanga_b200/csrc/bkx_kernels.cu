@@ -1586,12 +1586,14 @@ __global__ void __launch_bounds__(kWaveThreads) wave_probe_kernel(DevIndex I, KP
   }
 }
 
-// a read goes through at most one phase per allowance 0..MaxTotMM and the final one
+// rounds of a launch: a read goes through at most one phase per allowance and the final one
 static int wave_rounds(const KParams& P, uint32_t max_len) {
   const uint32_t len = max_len < (uint32_t)kFastMaxLen ? max_len : (uint32_t)kFastMaxLen;
   int mt = P.max_subs == 0 ? 0 : std::max(1, (int)((len * (uint32_t)P.max_subs + 50) / 100));
   if (mt > 63) mt = 63;
-  return std::min(mt + 2, kWaveMaxRounds - 1);
+  // staged phases exist for allowances below MaxTotMM only (at MaxTotMM the staged core is the final core), then the final
+  // one; whatever is still on the path after the last round is handed on by the closing step
+  return std::min(mt + 1, kWaveMaxRounds - 1);
 }
 int wave_launches(const KParams& P, uint32_t max_len) { return 1 + 3 * wave_rounds(P, max_len); }
 
