@@ -16,11 +16,12 @@
 //                     PCR5PrimerCorrect (-6)              Aligner.cpp:1996-2107
 //                     AutoTrimFlanks (-x)                 Aligner.cpp:1608-1812
 //                     FiltByChroms (-Z / -z)              Aligner.cpp:4019-4124, 4736-4798
+//                     priority regions (-B / -V)          Aligner.cpp:280-299, 9102-9186, 4126-4186
 //                     ReportNoneAligned / ReportMultiAlign (-j / -J)   Aligner.cpp:3826-4016
 //                     WriteSubDist / WriteBasicCountStats / ReportTargHitCnts (-O)   Aligner.cpp:6275-6331, 4191-4332, 5475-5537
 // Written from the behaviour of those functions; no reference code is reused.  Options of the
-// reference that select paths outside SURVEY section 8 (-r2 random locus, -N best matches, -c chimeric, -a/-A indel
-// and splice, -p SNP calling, -B priority regions, -H contaminants, -b/-C bisulfite/SOLiD) are recognised and
+// reference that select paths outside SURVEY section 8 (-r2 random locus, -c chimeric, -a/-A indel
+// and splice, -p SNP calling, -H contaminants, -b/-C bisulfite/SOLiD) are recognised and
 // rejected with a clear message.  Output formats: CSV -M0..3, BED -M4, SAM -M5/-M6 (gzip when the name ends in
 // .gz), BAM + BAI when the name ends in .bam (kanga.cpp:849-857).
 #include <algorithm>
@@ -178,6 +179,8 @@ struct Opts {
   int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
   std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
   std::string constraints_file;          // -5: loci base constraints CSV (chrom, start, end, bases)
+  std::string priority_file;             // -B: BED file of priority regions (reads with one locus in them are taken as unique)
+  bool priority_nofilt = false;          // -V: keep the accepted alignments outside the priority regions
   std::string stats_file;                // -O: substitution / quality / multi-hit / insert-length distributions (CSV)
   std::string none_file, multi_file;     // -j / -J: FASTA of the reads without a locus / with too many loci
   std::vector<std::string> in, pair;
@@ -653,17 +656,19 @@ static int parse(int argc0, char** argv0, Opts& o) {
       case 'q': o.sqlite_file = v; break;   // results-summary database: accepted, see below
       case 'w': o.exp_name = v; break;
       case 'W': o.exp_descr = v; break;
-      case 'B': case 'H': case 'S': case '7': case '8':
+      case 'B': o.priority_file = v; break;
+      case 'V': o.priority_nofilt = true; break;
+      case 'H': case 'S': case '7': case '8':
         unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'v':
         printf("\nbiokanga align Version 4.4.2 (bkx B200 path)\n");
         return 1;
       case 'h':
         printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -N -M0..6 -g -t -U -d -D -E "
-               "-y -Y -l -L -# -5 -k -6 -x -Z -z -j -J -O -4 -T -i -u -I -o -F -q -w -W [--gpus N], the reference's long option names, "
+               "-y -Y -l -L -# -5 -k -6 -x -Z -z -B -V -j -J -O -4 -T -i -u -I -o -F -q -w -W [--gpus N], the reference's long option names, "
                "and @file parameter files\n");
         return 1;
-      default: break;  // remaining reference options have no effect on this path (-K -G -P -1 -9 -V -0 -3)
+      default: break;  // remaining reference options have no effect on this path (-K -G -P -1 -9 -0 -3)
     }
    }
   }
@@ -692,6 +697,11 @@ static int parse(int argc0, char** argv0, Opts& o) {
   if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
   if (o.gpus < 1) o.gpus = 1;
+  if (!o.priority_file.empty() && (o.ml_mode != 0 || o.pe_mode != 0)) {
+    fprintf(stderr, "bkx-align: option -B (priority regions) is supported for single-end reads in the default multi-loci mode only\n");
+    return -1;
+  }
+  if (o.priority_file.empty()) o.priority_nofilt = false;   // kanga.cpp:1071-1082: -V is only read together with -B
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
     if (o.max_ml == 0) o.max_ml = 5;  // cDfltMaxMultiHits
@@ -1402,6 +1412,117 @@ static void filter_by_chroms(Records& rc, std::vector<regex_t>& rin, std::vector
   diag("Filtering aligned reads by chromosome completed");
 }
 
+// ---- -B: priority regions (CAligner::Align loads them as a CBEDfile, Aligner.cpp:280-299; BED lines "chrom start end
+//      [name [score [strand ...]]]" separated by white space -- or by commas when the first feature line does not parse
+//      otherwise --, '#' comments, header lines in front of the first feature; BEDfile.cpp:760-905).  A feature covers
+//      [start, end); chromosome names are compared without case, "chloroplast" / "ChrC" and "mitochondria" / "ChrM" are
+//      synonyms (LocateChromIDbyName, BEDfile.cpp:2588-2613).  Kept per chromosome of the index as sorted, merged intervals.
+struct PriorityRegions {
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> by_chrom;   // [chrom id]: inclusive [first, last], disjoint, ascending
+  // InAnyFeature: does [first, last] overlap a feature of this chromosome (BEDfile.cpp:3509-3526)
+  bool in_any(uint32_t chrom, uint32_t first, uint32_t last) const {
+    if (chrom >= by_chrom.size()) return false;
+    const auto& v = by_chrom[chrom];
+    auto it = std::lower_bound(v.begin(), v.end(), first, [](const std::pair<uint32_t, uint32_t>& a, uint32_t x) { return a.second < x; });
+    return it != v.end() && it->first <= last;
+  }
+};
+
+static int load_priority_regions(const std::string& path, const std::vector<bkx_entry>& ents, PriorityRegions& out) {
+  diag("Loading high priority regions BED file '%s'", path.c_str());
+  FILE* fp = fopen(path.c_str(), "r");
+  if (!fp) {
+    diag("Unable to open high priority regions BED file '%s'", path.c_str());
+    return -1;
+  }
+  struct Feat { std::string chrom; long start, end; };
+  std::vector<Feat> feats;
+  char line[16384];
+  int line_num = 0;
+  bool csv = false, bad = false;
+  while (fgets(line, sizeof(line) - 1, fp)) {
+    ++line_num;
+    if (feats.empty() && line_num >= 20) { bad = true; break; }   // no feature in the first 20 lines: not a BED file
+    char* t = line;
+    while (*t && isspace((unsigned char)*t)) ++t;
+    size_t len = strlen(t);
+    while (len && isspace((unsigned char)t[len - 1])) t[--len] = '\0';
+    if (*t == '\0' || *t == '#') continue;
+    char chrom[300];
+    int a = 0, b = 0, cnt = 0;
+    if (!csv) {
+      cnt = sscanf(t, " %140s %d %d", chrom, &a, &b);
+      if (feats.empty() && cnt < 3) csv = true;
+    }
+    if (csv) cnt = sscanf(t, " %140s , %d , %d", chrom, &a, &b);
+    if (cnt < 3) {
+      if (feats.empty()) { csv = false; continue; }   // could be a header line
+      bad = true;
+      break;
+    }
+    chrom[35] = '\0';   // cMaxDatasetSpeciesChrom - 1
+    feats.push_back({chrom, a, b});
+  }
+  fclose(fp);
+  if (bad || feats.empty()) {
+    diag("Unable to open high priority regions BED file '%s'", path.c_str());
+    return -1;
+  }
+  auto canon = [](const char* name) {   // one spelling per synonym class, lower case
+    std::string s(name);
+    for (auto& ch : s) ch = (char)tolower((unsigned char)ch);
+    if (s == "chloroplast") s = "chrc";
+    if (s == "mitochondria") s = "chrm";
+    return s;
+  };
+  out.by_chrom.assign(ents.size(), {});
+  for (size_t e = 1; e < ents.size(); ++e) {
+    // LocateChromIDbyName resolves the name of the INDEX chromosome against the BED names: the name itself first
+    const std::string want = canon(ents[e].name);
+    std::string exact(ents[e].name);
+    for (auto& ch : exact) ch = (char)tolower((unsigned char)ch);
+    bool have_exact = false;
+    for (const auto& f : feats) {
+      std::string fl(f.chrom);
+      for (auto& ch : fl) ch = (char)tolower((unsigned char)ch);
+      if (fl == exact) { have_exact = true; break; }
+    }
+    for (const auto& f : feats) {
+      std::string fl(f.chrom);
+      for (auto& ch : fl) ch = (char)tolower((unsigned char)ch);
+      const bool match = have_exact ? fl == exact : canon(f.chrom.c_str()) == want && fl != exact;
+      if (!match || f.end <= f.start || f.end <= 0) continue;
+      out.by_chrom[e].push_back({(uint32_t)std::max<long>(0, f.start), (uint32_t)(f.end - 1)});
+    }
+    auto& v = out.by_chrom[e];
+    std::sort(v.begin(), v.end());
+    size_t w = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+      if (w && v[i].first <= v[w - 1].second + 1) v[w - 1].second = std::max(v[w - 1].second, v[i].second);
+      else v[w++] = v[i];
+    }
+    v.resize(w);
+  }
+  diag("High priority regions BED file '%s' loaded", path.c_str());
+  return 0;
+}
+
+// FiltByPriorityRegions, Aligner.cpp:4126-4186: accepted alignments outside every priority region become eNARRegionFilt
+static void filter_by_priority_regions(Records& rc, const PriorityRegions& pr) {
+  diag("Now filtering matches by prioritorised regions");
+  uint32_t kept = 0, removed = 0;
+  for (uint32_t i = 0; i < rc.n(); ++i) {
+    bkx_read_result& r = rc.res[i];
+    if (r.nar != BKX_NAR_ACCEPTED) continue;
+    if (pr.in_any(r.chrom_id, r.match_loci, r.match_loci + r.match_len - 1)) { ++kept; continue; }
+    ++removed;
+    r.nar = BKX_NAR_REGIONFILT;
+    r.num_hits = 0;
+    r.chrom_id = 0;
+  }
+  diag("Filtering by prioritorised regions completed - retained %u, removed %u matches", kept, removed);
+}
+
 // ---- simulated-read truth check of ReportAlignStats, Aligner.cpp:3556-3657.  Reads written by `biokanga simreads` name
 //      their origin in the descriptor: <type>|usimreads|<n>|<chrom>|<start>|<end>|<len>|<strand>|<errs>..., where <chrom> may
 //      itself be three '|' separated parts (gnl|UG|Ta#S58887126).  Records are walked in load order; the first accepted one
@@ -1915,6 +2036,8 @@ int main(int argc, char** argv) {
   for (uint32_t e = 1; e <= info.num_entries; ++e) bkx_get_entry(idx[0], e, &ents[e]);
   std::vector<LociConstraint> constraints;
   if (!o.constraints_file.empty() && load_constraints(o.constraints_file, ents, constraints) < 0) return 1;
+  PriorityRegions priority;
+  if (!o.priority_file.empty() && load_priority_regions(o.priority_file, ents, priority) < 0) return 1;
 
   // -Z / -z as AcceptThisChromID evaluates them (Aligner.cpp:2651-2710: exclude expressions first, then -- if any -- the
   // include expressions).  Two callers in the reference: the pairing of paired-end runs (AcceptProvPE, the orphan-recovery
@@ -2027,6 +2150,59 @@ int main(int argc, char** argv) {
     for (auto& x : th) x.join();
     res16.release();
     R.packed2.release();
+  }
+  // ---- -B: ProcCoredApprox first searches every read with room for cPriorityExacts = 10 more loci (Aligner.cpp:9102-9145); when
+  //      that search ends eHRhits and, of its loci, no more than -R (here: one) lie inside a priority region, the read is
+  //      accepted at that locus as if it were unique (:9146-9186) -- otherwise the ordinary search decides.  The first
+  //      search is the library's all-loci call with 1 + 10 slots per read; the ordinary search above already ran for
+  //      every read, so its record is simply replaced, and the provisional totals move with it.
+  if (!o.priority_file.empty()) {
+    const int slots = o.max_ml + 10;   // m_MaxMLmatches + cPriorityExacts
+    bkx_align_params PP = P;
+    PP.ml_mode = BKX_ML_ALL; PP.max_ml_matches = slots; PP.clamp_max_ml = 0; PP.best_matches = 0;
+    ResVec pre(n);
+    std::vector<bkx_multi_hit> phits((size_t)n * (size_t)slots);
+    std::vector<bkx_align_stats> pst2((size_t)o.gpus);
+    std::vector<int> prc((size_t)o.gpus, 0);
+    std::vector<std::string> perr((size_t)o.gpus);
+    std::vector<std::thread> th;
+    const uint32_t per = ((n + o.gpus - 1) / o.gpus + 1) & ~1u;
+    for (int g = 0; g < o.gpus; ++g) {
+      const uint32_t b = std::min<uint64_t>(n, (uint64_t)per * g), e = std::min<uint64_t>(n, (uint64_t)per * (g + 1));
+      th.emplace_back([&, g, b, e]() {
+        if (e <= b) return;
+        prc[(size_t)g] = bkx_align_reads_multi(idx[(size_t)g], &PP, R.bases.data(), R.offs.data() + b, e - b, pre.data() + b,
+                                               phits.data() + (size_t)b * (size_t)slots, &pst2[(size_t)g]);
+        if (prc[(size_t)g] < 0) perr[(size_t)g] = bkx_last_error();
+      });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < o.gpus; ++g)
+      if (prc[(size_t)g] < 0) { diag("Fatal: %s", perr[(size_t)g].c_str()); return 1; }
+    std::vector<bkx_multi_hit> h((size_t)slots);
+    for (uint32_t i = 0; i < n; ++i) {
+      const bkx_read_result& q = pre[i];
+      if (q.hit_rslt != BKX_HR_HITS) continue;
+      const int nh = std::min<int>(q.low_hit_instances, slots);
+      for (int k = 0; k < nh; ++k) h[(size_t)k] = phits[(size_t)i * (size_t)slots + (size_t)k];
+      // the reference's in-place compaction: its cursor only advances when it copies, and it copies only once a locus
+      // outside the regions has been seen (Aligner.cpp:9152-9176)
+      int in_pri = 0, not_pri = 0, cursor = 0;
+      for (int k = 0; k < nh; ++k) {
+        const bkx_multi_hit m = h[(size_t)k];
+        if (!priority.in_any(m.chrom_id, m.match_loci, m.match_loci + m.match_len - 1)) { ++not_pri; continue; }
+        if (not_pri > 0) h[(size_t)cursor++] = m;
+        ++in_pri;
+      }
+      if (in_pri == 0 || !(o.clamp_ml || in_pri <= o.max_ml)) continue;
+      const bkx_multi_hit& m = h[0];
+      bkx_read_result r = q;
+      r.nar = BKX_NAR_ACCEPTED; r.hit_rslt = BKX_HR_HITS; r.num_hits = 1; r.low_hit_instances = 1;
+      r.chrom_id = m.chrom_id; r.match_loci = m.match_loci; r.match_len = m.match_len; r.strand = m.strand;
+      r.mismatches = m.mismatches; r.flags = 0;
+      if (res[i].nar != BKX_NAR_ACCEPTED) { ++S.tot_accepted_aligned; ++S.tot_accepted_unique; ++S.tot_loci_aligned; }
+      res[i] = r;
+    }
   }
   diag("Alignment of %u from %u loaded completed", n, n);
 
@@ -2193,6 +2369,7 @@ int main(int argc, char** argv) {
   }
   if (o.min_flank > 0) auto_trim_flanks(rc);
   if (!o.excl.empty() || !o.incl.empty()) filter_by_chroms(rc, rin, rex);
+  if (!o.priority_file.empty() && !o.priority_nofilt) filter_by_priority_regions(rc, priority);
   const auto& trim_l = rc.trim_l;
   const auto& trim_r = rc.trim_r;
   const uint32_t elim_plus = rc.elim_plus, elim_minus = rc.elim_minus;

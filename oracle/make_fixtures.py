@@ -679,10 +679,44 @@ def case_manyloci():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_priority():
+    """-B / -V (priority regions, Aligner.cpp:9102-9186, 4126-4186) on the lowcopy genome (2..9-copy repeat families): reads
+    with several equally good loci become unique when exactly one of them lies inside a region of the BED file; without -V
+    the accepted alignments outside every region are then filtered (PR).  One BED file with tabs, upper-case chromosome names,
+    comments, a header line and overlapping features; one with commas (which the reference's sscanf only takes with
+    white space around them)."""
+    d = os.path.join(GOLD, "priority")
+    os.makedirs(d, exist_ok=True)
+    low = os.path.join(GOLD, "lowcopy")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("lowcopy.sfx", "r100.fa", "deep.fa"):
+            with gzip.open(os.path.join(low, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        open(os.path.join(tmp, "pri.bed"), "w").write(
+            "# priority regions of the lowcopy genome\ntrack name=priority\nlc1\t0\t30000\tfirst\t0\t+\nlc2\t40000\t90861\n"
+            "LC3\t1000\t2000\tup\nlc3\t50000\t50100\nlc1 29500 31000 overlap 5 -\nlc9\t5\t500\n")
+        open(os.path.join(tmp, "pri_csv.bed"), "w").write("lc2 , 100 , 45000\nlc3 , 60000 , 90000\n")
+        for f in ("pri.bed", "pri_csv.bed"):
+            shutil.copy(os.path.join(tmp, f), os.path.join(d, f))
+        meta = {}
+        for tag, reads, args, out in (("b_s3", "r100.fa", ["-s3", "-M0", "-B", "pri.bed"], "b_s3.csv"),
+                                      ("bv_s3", "r100.fa", ["-s3", "-M0", "-B", "pri.bed", "-V"], "bv_s3.csv"),
+                                      ("bv_s5e2", "r100.fa", ["-s5", "-e2", "-M0", "-B", "pri.bed", "-V"], "bv_s5e2.csv"),
+                                      ("b_csv_sam", "r100.fa", ["-s3", "-M6", "-B", "pri_csv.bed"], "b_csv_sam.sam"),
+                                      ("bv_deep", "deep.fa", ["-s3", "-M0", "-B", "pri_csv.bed", "-V"], "bv_deep.csv"),
+                                      ("b_z", "r100.fa", ["-s3", "-M0", "-B", "pri.bed", "-Z", "lc2"], "b_z.csv"),
+                                      ("bv_x2k", "r100.fa", ["-s4", "-M0", "-B", "pri.bed", "-V", "-x2", "-k1"], "bv_x2k.csv")):
+            run(["align", "-I", "lowcopy.sfx", "-i", reads, "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [reads + ".gz"], "index": "lowcopy"}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches", "manyloci"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches", "manyloci", "priority"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -714,3 +748,5 @@ if __name__ == "__main__":
     if "manyloci" in which:
         case_manyloci()
     print("fixtures written under", GOLD)
+    if "priority" in which:
+        case_priority()

@@ -95,8 +95,18 @@ def draw(rng):
     if fmt != 6 and rng.random() < 0.3:
         a.append("-Ost.csv")
         side.append("st.csv")
+    if not pe and ml == 0 and rng.random() < 0.3:   # drawn last: the earlier draws of a seed stay what they were
+        a += ["-B", "pri.bed"] + (["-V"] if rng.random() < 0.5 else [])
     out = "out" + {0: ".csv", 1: ".csv", 2: ".csv", 3: ".csv", 4: ".bed", 5: ".sam", 6: ".sam"}[fmt]
     return reads, a, out, side, dedup, ml
+
+
+def write_side_files(work):
+    """The files some drawn options name: the loci constraints of the `constraints` case and a BED file of priority regions
+    over the tiny genome (upper-case and unknown chromosome names, a feature with all six columns, a comment)."""
+    shutil.copyfile(os.path.join(GOLD, "constraints", "cons.csv"), os.path.join(work, "cons.csv"))
+    open(os.path.join(work, "pri.bed"), "w").write("# priority regions\nchr1\t2000\t9000\nchr1 12000 12500\nCHR2\t0\t7000\n"
+                                                   "chr3\t2500\t2600\nchr4\t0\t300\tsmall\t0\t-\nchr7\t1\t2\n")
 
 
 def one(seed, cli, work):
@@ -109,7 +119,8 @@ def one(seed, cli, work):
         cmd = [exe, "align", "-I", os.path.join(work, "tiny.sfx"), "-i", os.path.join(work, reads[0])]
         if len(reads) > 1:
             cmd += ["-u", os.path.join(work, reads[1])]
-        cmd += [x if not x.startswith("-5") else "-5" + os.path.join(work, x[2:]) for x in args] + ["-o", out, "-F", "log.txt"]
+        cmd += [os.path.join(work, x) if i and args[i - 1] == "-B" else x if not x.startswith("-5") else "-5" + os.path.join(work, x[2:])
+                for i, x in enumerate(args)] + ["-o", out, "-F", "log.txt"]
         if who == "ref":
             cmd.append("-T1" if ml == 5 else "-T4")
         r = subprocess.run(cmd, cwd=d[who], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
@@ -163,7 +174,7 @@ def main():
     for f in ("tiny.sfx", "r100.fa", "r50.fa", "r150.fa", "mixed.fq", "pe1.fa", "pe2.fa"):
         with gzip.open(os.path.join(GOLD, "tiny", f + ".gz"), "rb") as a, open(os.path.join(work, f), "wb") as b:
             shutil.copyfileobj(a, b)
-    shutil.copyfile(os.path.join(GOLD, "constraints", "cons.csv"), os.path.join(work, "cons.csv"))
+    write_side_files(work)
     cli = o.cli
     if cli is None:
         cli = os.path.join(work, "bkx-align-cpu")

@@ -180,6 +180,7 @@ def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, ca
     sfx = gu.sfx_path(run.get("index", "tiny"), golden_dir)
     files = [os.path.join(gu.GOLD, run.get("index", "tiny"), f) for f in run["reads"]]
     args = [a if not a.startswith("-5") else "-5" + os.path.join(fdir, a[2:]) for a in run["args"]]
+    args = [os.path.join(fdir, a) if i and args[i - 1] == "-B" else a for i, a in enumerate(args)]   # -B <file of the case>
     subprocess.run([CLI, "align", "-I", sfx, "-i", files[0]] + (["-u", files[1]] if len(files) > 1 else []) + args +
                    ["-o", run["out"], "-F", "o.log"], check=True, stdout=subprocess.DEVNULL, cwd=tmp_path)
     ours, ref = _lines(tmp_path / run["out"]), _lines(os.path.join(fdir, run["out"] + ".gz"))
@@ -187,7 +188,7 @@ def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, ca
         def strip(ls):
             return sorted(x if x.startswith("@") else "\t".join([x.split("\t")[i] for i in (1, 2, 3, 5)] + x.split("\t")[11:]) for x in ls)
         assert strip(ours) == strip(ref)
-    elif tag in ("c5k", "i4"):   # -k behind it: survivors among identical keys are unspecified -> compare without read id / name
+    elif tag in ("c5k", "i4", "bv_x2k"):   # -k behind it: survivors among identical keys are unspecified -> compare without read id / name
         strip = lambda ls: sorted(",".join(x.split(",")[1:13]) for x in ls)
         assert strip(ours) == strip(ref)
     else:
@@ -309,6 +310,18 @@ def test_cli_best_matches_match_reference(tag, golden_dir, tmp_path):
         ours = {ln.split(",", 1)[0]: ln for ln in _lines(tmp_path / run["out"])}
         ref = {ln.split(",", 1)[0]: ln for ln in _lines(os.path.join(gu.GOLD, "bestmatches", run["out"] + ".gz"))}
         assert ours == ref
+
+
+PRIORITY_TAGS = ["b_s3", "bv_s3", "bv_s5e2", "b_csv_sam", "bv_deep", "b_z", "bv_x2k"]
+
+
+@pytest.mark.parametrize("tag", PRIORITY_TAGS)
+def test_cli_priority_regions_match_reference(tag, golden_dir, tmp_path):
+    """-B / -V (Aligner.cpp:9102-9186, 4126-4186): a read whose first search -- with room for 10 more loci -- ends with exactly
+    one locus inside a region of the BED file is accepted there as unique; without -V the accepted alignments outside every
+    region become PR.  BED with tabs / blanks / commas, comments, a header line, upper-case and unknown chromosome names,
+    overlapping features; behind it -Z, -x, -k; -e2; -M6."""
+    test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="priority")
 
 
 MANY_TAGS = ["r5_R300X", "r5_R500", "r5_R100N", "r4_R200X", "r1_R500"]

@@ -17,7 +17,7 @@ def test_front_end_matches_reference_on_drawn_option_sets(tmp_path):
     for f in ("tiny.sfx", "r100.fa", "r50.fa", "r150.fa", "mixed.fq", "pe1.fa", "pe2.fa"):
         with gzip.open(os.path.join(fz.GOLD, "tiny", f + ".gz"), "rb") as a, open(os.path.join(work, f), "wb") as b:
             shutil.copyfileobj(a, b)
-    shutil.copyfile(os.path.join(fz.GOLD, "constraints", "cons.csv"), os.path.join(work, "cons.csv"))
+    fz.write_side_files(work)
     cli = os.path.join(work, "bkx-align-cpu")
     fz.build_cpu_cli(cli)
     with ThreadPoolExecutor(8) as ex:
