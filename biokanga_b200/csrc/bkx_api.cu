@@ -990,7 +990,9 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
   // but 3.7 ms against 2.8 ms per 2 M reads.  The lane-per-read kernel then only redoes what that path hands on.
   // BKX_WAVE=0 / 1: never / always (read per launch: profiles/ab_kernel.py switches it inside one process).
   const char* wave_env = getenv("BKX_WAVE");
-  const int wave_mode = wave_env ? atoi(wave_env) : (n >= kWaveAutoReads ? 1 : 0);
+  uint32_t wave_min = kWaveAutoReads;
+  if (const char* ev = getenv("BKX_WAVE_MIN_READS")) wave_min = (uint32_t)std::max(1, atoi(ev));   // tuning hook
+  const int wave_mode = wave_env ? atoi(wave_env) : (n >= wave_min ? 1 : 0);
   const uint32_t* fast_ids = nullptr;
   const unsigned int* fast_n = nullptr;
   cudaEvent_t tw = nullptr;
