@@ -1,6 +1,7 @@
 """GPU: randomised differential test.  Random option combinations (-s, -e, -m, -Q, -n, multi-loci modes with -R / -X)
 and random read sets (lengths 16..400, fixed or ragged, substitutions, Ns, junk, chromosome-spanning reads) on the three
-golden genomes: every record of the fast + general kernel pair, and of the general kernel alone, against the oracle."""
+golden genomes: every record of the fast + general kernel pair, of the general kernel alone and (default multi-loci mode)
+of the wave path against the oracle."""
 import os
 
 import numpy as np
@@ -81,6 +82,21 @@ def test_random_options_and_reads(seed, golden_dir):
                            np.where(hits & (got["nar"] == abi.NAR_MULTIALIGN), got["low_hit_instances"], 0))
             valid = np.arange(gm.shape[1])[None, :] < cnt[:, None]
             assert gm[valid].tobytes() == em[valid].tobytes(), (case, pmode, kw, general_only)
+    if kw.get("ml_mode", 0) == 0:
+        # the default search once more through the wave path (bkx_wave.cuh; large launches take it on their own): the compact
+        # host call with the path forced on -- 16-byte records carry no per-read seed / candidate counts, the statistics
+        # carry their sums
+        os.environ["BKX_WAVE"] = "1"
+        try:
+            got, gst = gidx.align_packed2(gidx.default_params(pmode, **kw), bases, offs)
+        finally:
+            os.environ.pop("BKX_WAVE", None)
+        for f in abi.RESULT_DTYPE.names:
+            if f in ("seeds", "cands", "reserved"):
+                continue
+            bad = np.nonzero(got[f] != exp[f])[0]
+            assert len(bad) == 0, (case, pmode, kw, "wave", f, int(bad[0]), got[bad[0]], exp[bad[0]])
+        assert gst.as_dict() == est.as_dict(), (case, pmode, kw, "wave")
 
 
 @pytest.mark.parametrize("seed", range(int(os.environ.get("BKX_FUZZ_PE_SEEDS", "30"))))
