@@ -17,14 +17,16 @@
 //                     AutoTrimFlanks (-x)                 Aligner.cpp:1608-1812
 //                     FiltByChroms (-Z / -z)              Aligner.cpp:4019-4124, 4736-4798
 //                     priority regions (-B / -V)          Aligner.cpp:280-299, 9102-9186, 4126-4186
+//                     adaptor trimming at load (-H)       Aligner.cpp:250-268, 11036-11084; Contaminants.cpp:204-431, 1227-1310
 //                     ReportNoneAligned / ReportMultiAlign (-j / -J)   Aligner.cpp:3826-4016
 //                     WriteSubDist / WriteBasicCountStats / ReportTargHitCnts (-O)   Aligner.cpp:6275-6331, 4191-4332, 5475-5537
 // Written from the behaviour of those functions; no reference code is reused.  Options of the
 // reference that select paths outside SURVEY section 8 (-r2 random locus, -c chimeric, -a/-A indel
-// and splice, -p SNP calling, -H contaminants, -b/-C bisulfite/SOLiD) are recognised and
+// and splice, -p SNP calling, -b/-C bisulfite/SOLiD) are recognised and
 // rejected with a clear message.  Output formats: CSV -M0..3, BED -M4, SAM -M5/-M6 (gzip when the name ends in
 // .gz), BAM + BAI when the name ends in .bam (kanga.cpp:849-857).
 #include <algorithm>
+#include <unordered_map>
 #include <chrono>
 #include <cmath>
 #include <cerrno>
@@ -179,6 +181,7 @@ struct Opts {
   int min_flank = 0;             // -x: auto-trim flanks back to this many exactly matching bases (kanga.cpp:497, 804)
   std::vector<std::string> excl, incl;   // -Z / -z chromosome filters (POSIX extended, case insensitive)
   std::string constraints_file;          // -5: loci base constraints CSV (chrom, start, end, bases)
+  std::string contam_file;               // -H: adaptor (contaminant) sequences trimmed off the read ends at load
   std::string priority_file;             // -B: BED file of priority regions (reads with one locus in them are taken as unique)
   bool priority_nofilt = false;          // -V: keep the accepted alignments outside the priority regions
   std::string stats_file;                // -O: substitution / quality / multi-hit / insert-length distributions (CSV)
@@ -374,6 +377,218 @@ static int expand_input_specs(Opts& o) {
   return 0;
 }
 
+// ---- -H: adaptor sequences ("contaminants") overlapping the read ends are trimmed off at load (Aligner.cpp:250-268,
+//      11036-11084, 11283-11293; CContaminants::LoadContaminantsFile / MatchContaminants, Contaminants.cpp:204-431, 1227-1310).
+//      A multi-FASTA file; the name of a sequence may end in '@' + digits saying which read ends it is tried on: 1 / 2 the 5'
+//      end of SE-PE1 / PE2 reads, 3 / 4 their 3' end, 5..8 the same four with the sequence reverse complemented; no suffix
+//      means 1, 2, 5 and 6.  On a 5' end the read's first L bases are compared with the LAST L bases of a sequence, on a 3'
+//      end the read's last L bases with its FIRST L; the longest L (down from min(read, longest sequence) to the fixed
+//      trim + 1) at which some sequence fits with at most one substitution is trimmed -- one substitution is granted at
+//      every length, so a read loses at least one base at every end some sequence is tried on.  An N in the read never
+//      matches, an N in the sequence always does.  The reference walks a trie over the sequences (RecursiveMatch); the
+//      sequences are few and short, so here they are simply tried one by one.
+struct Contaminants {
+  std::vector<std::vector<uint8_t>> seqs[4];   // [0] 5' SE/PE1, [1] 5' PE2, [2] 3' SE/PE1, [3] 3' PE2
+  int max_len[4] = {0, 0, 0, 0};
+  // '&' entries: vector sequences a read may lie INSIDE, as it is (sense) or reverse complemented (antisense); a read that
+  // does is reported as overlapped over its whole length and so falls to the length filter (MatchVectContams /
+  // MatchVectContam, Contaminants.cpp:1038-1225).  Found through the 12-mers of the vector (the reference seeds with
+  // windows of read length / (allowed mismatches + 1) >= 13 bases through a suffix array of the vector).
+  struct Vector {
+    std::vector<uint8_t> seq;
+    bool pe1_sense = false, pe1_anti = false, pe2_sense = false, pe2_anti = false;
+    std::unordered_map<uint32_t, std::vector<uint32_t>> kmers;   // 12-mer without N -> positions
+  };
+  std::vector<Vector> vectors;
+  bool loaded = false;
+  static constexpr int kSeed = 12;
+  static bool seed_key(const uint8_t* p, uint32_t& key) {
+    key = 0;
+    for (int i = 0; i < kSeed; ++i) {
+      const uint8_t b = p[i] & 7;
+      if (b > 3) return false;
+      key = (key << 2) | b;
+    }
+    return true;
+  }
+  // does the vector hold the query with at most `allowed` substitutions (an N only equals an N)
+  static bool inside(const Vector& v, const uint8_t* q, int qlen, int allowed) {
+    const int n = (int)v.seq.size();
+    auto fits = [&](long p) {
+      if (p < 0 || p + qlen > n) return false;
+      int mm = 0;
+      for (int i = 0; i < qlen; ++i)
+        if ((q[i] & 7) != v.seq[(size_t)p + (size_t)i] && ++mm > allowed) return false;
+      return true;
+    };
+    const int win = qlen > 25 ? qlen / (allowed + 1) : qlen;
+    for (int ofs = 0; ofs < qlen; ofs += win) {
+      if (ofs + win > qlen) ofs = qlen - win;
+      // any 12-mer of an exactly matching window matches exactly as well: take the first one without an N
+      bool seeded = false;
+      for (int j = 0; j + kSeed <= win && !seeded; ++j) {
+        uint32_t key;
+        if (!seed_key(q + ofs + j, key)) continue;
+        seeded = true;
+        auto it = v.kmers.find(key);
+        if (it == v.kmers.end()) break;
+        for (uint32_t hit : it->second)
+          if (fits((long)hit - (long)(ofs + j))) return true;
+      }
+      if (!seeded)   // a window of Ns: every placement
+        for (long p = 0; p + qlen <= n; ++p) if (fits(p)) return true;
+      if (ofs + win >= qlen) break;
+    }
+    return false;
+  }
+  int match_vectors(bool pe2_flags, const uint8_t* q, int qlen) const {
+    if (vectors.empty() || qlen < 20 || qlen > 2000) return 0;
+    const int allowed = qlen > 25 ? qlen / 25 : 0;
+    std::vector<uint8_t> rc;
+    for (const auto& v : vectors) {
+      const bool sense = pe2_flags ? v.pe2_sense : v.pe1_sense, anti = pe2_flags ? v.pe2_anti : v.pe1_anti;
+      if (!(sense || anti) || (int)v.seq.size() < qlen) continue;
+      if (sense && inside(v, q, qlen, allowed)) return qlen;
+      if (anti) {
+        if (rc.empty()) {
+          rc.resize((size_t)qlen);
+          for (int i = 0; i < qlen; ++i) { const uint8_t b = q[qlen - 1 - i] & 7; rc[(size_t)i] = b < 4 ? (uint8_t)(3 - b) : b; }
+        }
+        if (inside(v, rc.data(), qlen, allowed)) return qlen;
+      }
+    }
+    return 0;
+  }
+  int match(int type, const uint8_t* q, int qlen, int min_overlap) const {
+    if (qlen < 20 || qlen > 2000) return 0;   // cMinContamQuerySeqLen .. cMaxContamQuerySeqLen
+    // vectors first; the reference picks the PE1 flags for the 5' end of SE / PE1 reads only -- its test for the 3' end
+    // names the 5' type twice (Contaminants.cpp:1257) -- and the PE2 flags for the other three
+    if (const int whole = match_vectors(type != 0, q, qlen)) return whole;
+    if (seqs[type].empty()) return 0;
+    if (min_overlap < 1) min_overlap = 1;
+    const int cur = std::min(qlen, max_len[type]);
+    const bool five = type < 2;
+    for (int L = cur; L >= min_overlap; --L)
+      for (const auto& c : seqs[type]) {
+        if ((int)c.size() < L) continue;
+        const uint8_t* qs = five ? q : q + qlen - L;
+        const uint8_t* cs = five ? c.data() + c.size() - (size_t)L : c.data();
+        int mm = 0;
+        for (int i = 0; i < L && mm <= 1; ++i) {
+          const uint8_t tb = qs[i] & 7, cb = cs[i];
+          if (tb == 4 || (cb != 4 && tb != cb)) ++mm;
+        }
+        if (mm <= 1) return L;
+      }
+    return 0;
+  }
+};
+static Contaminants g_contam;
+
+static int load_contaminants(const std::string& path, Contaminants& C) {
+  FILE* fp = fopen(path.c_str(), "r");
+  if (!fp) { diag("Unable to load contaminate sequences file '%s'", path.c_str()); return -1; }
+  diag("LoadContaminantsFile:- Processing %s..", path.c_str());
+  std::string text;
+  char buf[65536];
+  size_t got;
+  while ((got = fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, got);
+  fclose(fp);
+  bool flags[8] = {true, true, false, false, true, true, false, false};   // a file without any descriptor: 1, 2, 5, 6
+  bool vector_type = false;
+  std::string name = "ContamSeq.1";
+  std::vector<uint8_t> seq;
+  int n_seqs = 0;
+  bool ok = true;
+  auto flush = [&]() {
+    if (seq.empty()) return;
+    ++n_seqs;
+    if (vector_type) {
+      if (seq.size() < 100 || seq.size() > 0x0ffffff) {   // cMinVectorSeqLen .. cMaxVectorSeqLen
+        diag("LoadContamiantsFile: Vector sequence for '%s' outside of accepted length range %d..%d", name.c_str(), 100, 0x0ffffff);
+        ok = false;
+        return;
+      }
+      if (C.vectors.size() >= 10) {   // cMaxNumVectors
+        diag("AddVectContam: Too many vector contaminants (max allowed %d) current contaminant is '%s'", 10, name.c_str());
+        ok = false;
+        return;
+      }
+      Contaminants::Vector v;
+      v.seq = seq;
+      v.pe1_sense = flags[0] || flags[2]; v.pe1_anti = flags[4] || flags[6];
+      v.pe2_sense = flags[1] || flags[3]; v.pe2_anti = flags[5] || flags[7];
+      for (size_t i = 0; i + Contaminants::kSeed <= v.seq.size(); ++i) {
+        uint32_t key;
+        if (Contaminants::seed_key(v.seq.data() + i, key)) v.kmers[key].push_back((uint32_t)i);
+      }
+      C.vectors.push_back(std::move(v));
+      seq.clear();
+      return;
+    }
+    if (seq.size() < 4 || seq.size() > 200) {   // cMinContaminantLen .. cMaxContaminantLen
+      diag("LoadContamiantsFile: Sequence for '%s' outside of accepted length range %d..%d", name.c_str(), 4, 200);
+      ok = false;
+      return;
+    }
+    for (int t = 0; t < 4; ++t) if (flags[t]) { C.seqs[t].push_back(seq); C.max_len[t] = std::max(C.max_len[t], (int)seq.size()); }
+    if (flags[4] || flags[5] || flags[6] || flags[7]) {
+      std::vector<uint8_t> rc(seq.rbegin(), seq.rend());
+      for (auto& b : rc) if (b < 4) b = (uint8_t)(3 - b);
+      for (int t = 0; t < 4; ++t) if (flags[4 + t]) { C.seqs[t].push_back(rc); C.max_len[t] = std::max(C.max_len[t], (int)rc.size()); }
+    }
+    seq.clear();
+  };
+  size_t pos = 0;
+  while (pos < text.size() && ok) {
+    size_t eol = text.find('\n', pos);
+    if (eol == std::string::npos) eol = text.size();
+    std::string line = text.substr(pos, eol - pos);
+    pos = eol + 1;
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+    if (line.empty()) continue;
+    if (line[0] == '>') {
+      flush();
+      if (!ok) break;
+      for (bool& f : flags) f = false;
+      vector_type = false;
+      size_t a = 1;
+      while (a < line.size() && isspace((unsigned char)line[a])) ++a;
+      size_t b = a;
+      while (b < line.size() && !isspace((unsigned char)line[b])) ++b;
+      name = line.substr(a, b - a);
+      bool coded = false;
+      if (name.empty()) {
+        name = "ContamSeq." + std::to_string(n_seqs + 1);
+      } else {
+        // overlay codes: the digits 1..8 at the very end of the name, behind an '@' (adaptor) or '&' (vector)
+        size_t k = name.size() - 1;
+        for (size_t left = name.size(); left > 1; --left, --k)
+          if (name[k] == '@' || name[k] == '&' || !(name[k] >= '1' && name[k] <= '8')) break;
+        vector_type = name[k] == '&';
+        if ((name[k] == '@' || name[k] == '&') && k + 1 < name.size()) {
+          for (size_t i = k + 1; i < name.size(); ++i) flags[name[i] - '1'] = true;
+          name.resize(k);
+          coded = true;
+        }
+      }
+      if (!coded) flags[0] = flags[1] = flags[4] = flags[5] = true;
+      continue;
+    }
+    for (char ch : line) {
+      if (isspace((unsigned char)ch)) continue;
+      const uint8_t c = base_code(ch);
+      if (c > 4) { diag("LoadContaminantsFile: Illegal base in %s sequence, only bases A,C,G,T,N accepted", name.c_str()); ok = false; break; }
+      seq.push_back(c);
+    }
+  }
+  if (ok) flush();
+  if (!ok) { diag("Unable to load contaminate sequences file '%s'", path.c_str()); return -1; }
+  if (n_seqs == 0) diag("No contaminant sequences loaded from '%s'", path.c_str());
+  C.loaded = true;
+  return 0;
+}
+
 static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (default -g3: qualities ignored)
   bool pe = o.pe_mode != 0;
   uint8_t code_tab[256];
@@ -393,21 +608,52 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
     if (!opened[0]) { diag("Unable to open '%s'", o.in[fi].c_str()); return -1; }
     if (pe && !opened[1]) { diag("Unable to open '%s'", o.pair[fi].c_str()); return -1; }
     const size_t nrec = recs[0].size();
-    // length filter, pairwise for PE (Aligner.cpp:10895-10935)
+    // -H: bases an adaptor overlaps at the 5' / 3' end of every read that is going to be looked at, beyond the fixed trims
+    // (Aligner.cpp:11036-11084).  Computed on the raw read, by all threads, before the length filter that counts them in.
+    std::vector<uint16_t> c5[2], c3[2];
+    if (g_contam.loaded) {
+      for (int f = 0; f < (pe ? 2 : 1); ++f) { c5[f].assign(recs[f].size(), 0); c3[f].assign(recs[f].size(), 0); }
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+          std::vector<uint8_t> q;
+          for (int f = 0; f < (pe ? 2 : 1); ++f) {
+            const size_t nr = recs[f].size(), b = nr * t / T, e = nr * (t + 1) / T;
+            for (size_t i = b; i < e; ++i) {
+              if (o.sample_nth > 1 && i % (size_t)o.sample_nth) continue;
+              const RawRec& r = recs[f][i];
+              q.clear();
+              for (const char* c = r.sb; c < r.se; ++c) if (*c != '\n' && *c != '\r') q.push_back(code_tab[(unsigned char)*c]);
+              int a5 = g_contam.match(f, q.data(), (int)q.size(), o.trim5 + 1);
+              int a3 = g_contam.match(2 + f, q.data(), (int)q.size(), o.trim3 + 1);
+              a5 = a5 <= o.trim5 ? 0 : a5 - o.trim5;
+              a3 = a3 <= o.trim3 ? 0 : a3 - o.trim3;
+              c5[f][i] = (uint16_t)a5;
+              c3[f][i] = (uint16_t)a3;
+            }
+          }
+        });
+      for (auto& x : th) x.join();
+    }
+    auto contam5 = [&](int f, size_t i) -> int { return c5[f].empty() ? 0 : c5[f][i]; };
+    auto contam3 = [&](int f, size_t i) -> int { return c3[f].empty() ? 0 : c3[f][i]; };
+    // length filter, pairwise for PE (Aligner.cpp:10895-10935, 11086-11121)
     uint32_t accepted = 0, under = 0, over = 0;
+    uint32_t n_c5[2] = {0, 0}, n_c3[2] = {0, 0};
     std::vector<uint8_t> keep(nrec, 0);
-    auto bad_len = [&](uint32_t len, uint32_t& u, uint32_t& ov) {
-      if (o.trim5 + o.trim3 + o.min_len > (int)len) { ++u; return true; }
-      if (o.trim5 + o.trim3 + o.max_len < (int)len) { ++ov; return true; }
+    auto bad_len = [&](uint32_t len, int extra, uint32_t& u, uint32_t& ov) {
+      if (o.trim5 + o.trim3 + extra + o.min_len > (int)len) { ++u; return true; }
+      if (o.trim5 + o.trim3 + extra + o.max_len < (int)len) { ++ov; return true; }
       return false;
     };
     for (size_t i = 0; i < nrec; ++i) {
       if (pe && i >= recs[1].size()) { diag("Problem parsing sequence after %u reads parsed", accepted); return -1; }
       if (o.sample_nth > 1 && i % (size_t)o.sample_nth) continue;   // -#: every Nth raw read / pair of a file, from its first (Aligner.cpp:10943, 11027-11033)
-      if (bad_len(recs[0][i].len, under, over)) continue;
-      if (pe && bad_len(recs[1][i].len, under, over)) continue;
+      if (bad_len(recs[0][i].len, contam5(0, i) + contam3(0, i), under, over)) continue;
+      if (pe && bad_len(recs[1][i].len, contam5(1, i) + contam3(1, i), under, over)) continue;
       keep[i] = 1;
       ++accepted;
+      for (int f = 0; f < (pe ? 2 : 1); ++f) { n_c5[f] += contam5(f, i) > 0; n_c3[f] += contam3(f, i) > 0; }
     }
     // offsets of every accepted read in the arena, then a parallel fill
     const int per = pe ? 2 : 1;
@@ -425,7 +671,7 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
         R.offs[w] = bo;
         R.name_ofs[w] = no;
         src[w - first_read] = i;
-        bo += r.len - cut;
+        bo += r.len - cut - (size_t)contam5(f, i) - (size_t)contam3(f, i);
         no += r.name_n + 1;
         ++w;
       }
@@ -440,14 +686,16 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
           size_t b = add_reads * t / T, e = add_reads * (t + 1) / T;
           std::vector<uint8_t> tmp;
           for (size_t k = b; k < e; ++k) {
-            const RawRec& r = recs[pe ? (k & 1) : 0][src[k]];
+            const int fk = pe ? (int)(k & 1) : 0;
+            const RawRec& r = recs[fk][src[k]];
             uint8_t* dst = R.bases.data() + R.offs[first_read + k];
-            const size_t L = r.len - cut;
+            const size_t lead = (size_t)o.trim5 + (size_t)contam5(fk, src[k]);   // fixed 5' trim + what an adaptor overlaps (-H)
+            const size_t L = r.len - cut - (size_t)contam5(fk, src[k]) - (size_t)contam3(fk, src[k]);
             const bool useq = o.qmode != 3 && r.q && r.qlen == r.len;
             if ((size_t)(r.se - r.sb) == r.len) {  // one line
-              const char* sp = r.sb + o.trim5;
+              const char* sp = r.sb + lead;
               if (useq) {
-                const char* qp = r.q + o.trim5;
+                const char* qp = r.q + lead;
                 for (size_t i = 0; i < L; ++i)
                   dst[i] = (uint8_t)(code_tab[(unsigned char)sp[i]] | (qual4(o.qmode, (unsigned char)qp[i]) << 4));
               } else {
@@ -456,7 +704,7 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
             } else {  // multi-line FASTA: drop the line breaks first
               tmp.clear();
               for (const char* c = r.sb; c < r.se; ++c) if (*c != '\n' && *c != '\r') tmp.push_back(code_tab[(unsigned char)*c]);
-              memcpy(dst, tmp.data() + o.trim5, L);
+              memcpy(dst, tmp.data() + lead, L);
             }
             char* nm = R.names.data() + R.name_ofs[first_read + k];
             memcpy(nm, r.name, r.name_n);
@@ -468,6 +716,14 @@ static int load_reads(const Opts& o, Reads& R) {  // Aligner.cpp:10724-11427 (de
     diag("LoadReads: Total of %1.9d reads parsed and loaded from %s", accepted, o.in[fi].c_str());
     if (under) diag("Load: total of %d under length sequences sloughed from file '%s'", under, o.in[fi].c_str());
     if (over) diag("Load: total of %d over length sequences sloughed from file '%s'", over, o.in[fi].c_str());
+    if (g_contam.loaded) {   // Aligner.cpp:11403-11425 (the PE2 lines say "PE1" there too)
+      diag("Load: total of %d sequences PE1 sequences were 5' contaminate trimmed", (int)n_c5[0]);
+      diag("Load: total of %d sequences PE1 sequences were 3' contaminate trimmed", (int)n_c3[0]);
+      if (pe) {
+        diag("Load: total of %d sequences PE1 sequences were 5' contaminant trimmed", (int)n_c5[1]);
+        diag("Load: total of %d sequences PE1 sequences were 3' contaminant trimmed", (int)n_c3[1]);
+      }
+    }
   }
   if (o.ml_mode < 3) {  // the 2-bit stream + exception list + lengths for the H2D copies (the multi-loci calls -r3..5 take the
                         // one-byte-per-base arena); threads own disjoint byte ranges of the stream
@@ -658,14 +914,15 @@ static int parse(int argc0, char** argv0, Opts& o) {
       case 'W': o.exp_descr = v; break;
       case 'B': o.priority_file = v; break;
       case 'V': o.priority_nofilt = true; break;
-      case 'H': case 'S': case '7': case '8':
+      case 'H': o.contam_file = v; break;
+      case 'S': case '7': case '8':
         unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'v':
         printf("\nbiokanga align Version 4.4.2 (bkx B200 path)\n");
         return 1;
       case 'h':
         printf("bkx-align: B200 drop-in for `biokanga align` -- options -m -Q -s -e -n -r{1,3,4,5} -R -X -N -M0..6 -g -t -U -d -D -E "
-               "-y -Y -l -L -# -5 -k -6 -x -Z -z -B -V -j -J -O -4 -T -i -u -I -o -F -q -w -W [--gpus N], the reference's long option names, "
+               "-y -Y -l -L -# -H -5 -k -6 -x -Z -z -B -V -j -J -O -4 -T -i -u -I -o -F -q -w -W [--gpus N], the reference's long option names, "
                "and @file parameter files\n");
         return 1;
       default: break;  // remaining reference options have no effect on this path (-K -G -P -1 -9 -0 -3)
@@ -2009,6 +2266,8 @@ int main(int argc, char** argv) {
 
   FILE* stats_fp = nullptr;   // created up front like every result file (CreateOrTruncResultFiles, Aligner.cpp:4351)
   if (!o.stats_file.empty() && !(stats_fp = fopen(o.stats_file.c_str(), "wb"))) { diag("Fatal: unable to create '%s'", o.stats_file.c_str()); return 1; }
+
+  if (!o.contam_file.empty() && load_contaminants(o.contam_file, g_contam) < 0) return 1;
 
   // ---- reads load on their own thread while the index streams to the GPU (the reference also loads in the background)
   Reads R;

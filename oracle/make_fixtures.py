@@ -713,10 +713,106 @@ def case_priority():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_contam():
+    """-H (adaptor trimming at load, CContaminants): reads of the tiny case with adaptor tails written over their ends (the
+    last k bases of a 5' adaptor over the first k of the read, the first k of a 3' adaptor over its last k; one substitution
+    in a tenth of them), a contaminant file with every kind of overlay code -- @1, @3, @1234, reverse complements (@57),
+    no code (1, 2, 5, 6), an N inside, PE2 only, the minimum length of 4 --; single-end, with fixed trims and a length filter
+    on top, FASTQ with qualities, SAM, paired ends with orphan recovery and with sampling."""
+    d = os.path.join(GOLD, "contam")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    rng = np.random.default_rng(424242)
+    ad5 = ["ACACTCTTTCCCTACACGACGCTCTTCCGATCT", "CTGTCTCTTATACACATCT", "AATGATACGGCGACCACCGA", "TTNGACCATG"]
+    ad3 = ["AGATCGGAAGAGCACACGTCTGAACTCCAGTCA", "CTGTCTCTTATACACATCT", "TTNGACCATG", "ACACTCTTTCCCTACACGACGCTCTTCCGATC"]
+
+    def spoil(seq):
+        s = list(seq)
+        if rng.random() < 0.5:
+            a = ad5[int(rng.integers(0, len(ad5)))].replace("N", "A")
+            k = int(rng.integers(1, min(len(a), 30) + 1))
+            s[:k] = list(a[len(a) - k:])
+            if rng.random() < 0.1:
+                s[int(rng.integers(0, k))] = "ACGT"[int(rng.integers(0, 4))]
+        if rng.random() < 0.5:
+            a = ad3[int(rng.integers(0, len(ad3)))].replace("N", "C")
+            k = int(rng.integers(1, min(len(a), 30) + 1))
+            s[len(s) - k:] = list(a[:k])
+            if rng.random() < 0.1:
+                s[len(s) - 1 - int(rng.integers(0, k))] = "ACGT"[int(rng.integers(0, 4))]
+        return "".join(s)
+
+    with tempfile.TemporaryDirectory() as tmp:
+        with gzip.open(os.path.join(tiny, "tiny.sfx.gz"), "rb") as a, open(os.path.join(tmp, "tiny.sfx"), "wb") as b:
+            shutil.copyfileobj(a, b)
+        for src, dst, limit in (("r100.fa", "c100.fa", 1500), ("pe1.fa", "cpe1.fa", 800), ("pe2.fa", "cpe2.fa", 800)):
+            recs = gzip.open(os.path.join(tiny, src + ".gz"), "rt").read().split(">")[1:limit + 1]
+            with open(os.path.join(tmp, dst), "w") as o:
+                for r in recs:
+                    name, seq = r.split("\n", 1)
+                    o.write(">%s\n%s\n" % (name, spoil(seq.replace("\n", ""))))
+        lines = gzip.open(os.path.join(tiny, "mixed.fq.gz"), "rt").read().splitlines()
+        with open(os.path.join(tmp, "cmixed.fq"), "w") as o:
+            for i in range(0, min(len(lines), 4 * 1200), 4):
+                seq = spoil(lines[i + 1]) if len(lines[i + 1]) >= 40 else lines[i + 1]
+                o.write("%s\n%s\n+\n%s\n" % (lines[i], seq, lines[i + 3]))
+        open(os.path.join(tmp, "contam.fa"), "w").write(
+            ">ad5@1 five prime adaptor\nACACTCTTTCCCTACACGACGCTCTTCCGATCT\n>ad3@3\nAGATCGGAAGAGCACACGTC\nTGAACTCCAGTCA\n"
+            ">both@1234\nCTGTCTCTTATACACATCT\n>rc7@57\nGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT\n>nocode\nAATGATACGGCGACCACCGA\n"
+            ">withn@13\nTTNGACCATG\n>pe2only@24\nCAAGCAGAAGACGGCATACGAGAT\n>tiny4@3\nGGCC\n")
+        # vectors ('&' codes): reads cut out of a vector sequence -- as they are or reverse complemented, with 0..6
+        # substitutions (100 / 25 = 4 are tolerated) -- lie inside it and fall to the length filter; vec2 is marked for PE2
+        # reads only, yet the reference also tries it on the 3' end of SE / PE1 reads
+        comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+        vecs = ["".join("ACGT"[int(x)] for x in rng.integers(0, 4, n)) for n in (420, 260)]
+
+        def from_vector(v, length):
+            p = int(rng.integers(0, len(v) - length + 1))
+            s = list(v[p:p + length])
+            for _ in range(int(rng.integers(0, 7))):
+                i = int(rng.integers(0, length))
+                s[i] = "ACGT"[("ACGT".index(s[i]) + 1 + int(rng.integers(0, 3))) % 4]
+            s = "".join(s)
+            return s if rng.random() < 0.5 else "".join(comp[c] for c in reversed(s))
+
+        for src, dst in (("c100.fa", "cv100.fa"), ("cpe1.fa", "cvpe1.fa"), ("cpe2.fa", "cvpe2.fa")):
+            recs = open(os.path.join(tmp, src)).read().split(">")[1:601]
+            with open(os.path.join(tmp, dst), "w") as o:
+                for r in recs:
+                    name, seq = r.split("\n", 1)
+                    seq = seq.strip()
+                    if rng.random() < 0.25:
+                        seq = from_vector(vecs[int(rng.integers(0, 2))], len(seq))
+                    o.write(">%s\n%s\n" % (name, seq))
+        open(os.path.join(tmp, "contam_v.fa"), "w").write(
+            ">ad5@1\nACACTCTTTCCCTACACGACGCTCTTCCGATCT\n>vec1&15 cloning vector\n%s\n>ad3@34\nAGATCGGAAGAGCACACGTCTGAACTCCAGTCA\n>vec2&2\n%s\n"
+            % ("\n".join(vecs[0][i:i + 70] for i in range(0, len(vecs[0]), 70)), vecs[1]))
+        for fn in ("c100.fa", "cpe1.fa", "cpe2.fa", "cmixed.fq", "cv100.fa", "cvpe1.fa", "cvpe2.fa"):
+            gz(os.path.join(tmp, fn), os.path.join(d, fn + ".gz"))
+        shutil.copy(os.path.join(tmp, "contam.fa"), os.path.join(d, "contam.fa"))
+        shutil.copy(os.path.join(tmp, "contam_v.fa"), os.path.join(d, "contam_v.fa"))
+        meta = {}
+        for tag, reads, args, out in (("h_s3", ["c100.fa"], ["-s3", "-M0", "-H", "contam.fa"], "h_s3.csv"),
+                                      ("h_trim", ["c100.fa"], ["-s4", "-M0", "-H", "contam.fa", "-y3", "-Y2", "-l80"], "h_trim.csv"),
+                                      ("h_sam", ["c100.fa"], ["-s3", "-M6", "-H", "contam.fa"], "h_sam.sam"),
+                                      ("h_fq", ["cmixed.fq"], ["-s3", "-M6", "-g0", "-n2", "-H", "contam.fa"], "h_fq.sam"),
+                                      ("h_pe", ["cpe1.fa", "cpe2.fa"], ["-s3", "-M0", "-U1", "-D600", "-H", "contam.fa"], "h_pe.csv"),
+                                      ("h_pesam", ["cpe1.fa", "cpe2.fa"], ["-s5", "-M6", "-U3", "-D600", "-#2", "-H", "contam.fa", "-y1"], "h_pe.sam"),
+                                      ("h_x", ["c100.fa"], ["-s5", "-M0", "-H", "contam.fa", "-x3", "-Zchr2"], "h_x.csv"),
+                                      ("hv_s3", ["cv100.fa"], ["-s3", "-M0", "-H", "contam_v.fa"], "hv_s3.csv"),
+                                      ("hv_sam", ["cv100.fa"], ["-s5", "-M6", "-H", "contam_v.fa", "-l40"], "hv_sam.sam"),
+                                      ("hv_pe", ["cvpe1.fa", "cvpe2.fa"], ["-s3", "-M0", "-U1", "-D600", "-H", "contam_v.fa"], "hv_pe.csv")):
+            run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [r + ".gz" for r in reads], "index": "tiny"}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches", "manyloci", "priority"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches", "manyloci", "priority", "contam"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -750,3 +846,5 @@ if __name__ == "__main__":
     print("fixtures written under", GOLD)
     if "priority" in which:
         case_priority()
+    if "contam" in which:
+        case_contam()

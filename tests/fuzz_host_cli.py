@@ -97,14 +97,20 @@ def draw(rng):
         side.append("st.csv")
     if not pe and ml == 0 and rng.random() < 0.3:   # drawn last: the earlier draws of a seed stay what they were
         a += ["-B", "pri.bed"] + (["-V"] if rng.random() < 0.5 else [])
+    # adaptor trimming at load: every read loses at least a base at each end an adaptor is tried on -- not drawn for the
+    # 50-base reads, which the default minimum length of 50 would then slough to the last one
+    if rng.random() < 0.2 and reads[0] != "r50.fa":
+        a += ["-H", "contam.fa"]
     out = "out" + {0: ".csv", 1: ".csv", 2: ".csv", 3: ".csv", 4: ".bed", 5: ".sam", 6: ".sam"}[fmt]
     return reads, a, out, side, dedup, ml
 
 
 def write_side_files(work):
     """The files some drawn options name: the loci constraints of the `constraints` case and a BED file of priority regions
-    over the tiny genome (upper-case and unknown chromosome names, a feature with all six columns, a comment)."""
+    over the tiny genome (upper-case and unknown chromosome names, a feature with all six columns, a comment), the adaptor
+    file of the `contam` case."""
     shutil.copyfile(os.path.join(GOLD, "constraints", "cons.csv"), os.path.join(work, "cons.csv"))
+    shutil.copyfile(os.path.join(GOLD, "contam", "contam.fa"), os.path.join(work, "contam.fa"))
     open(os.path.join(work, "pri.bed"), "w").write("# priority regions\nchr1\t2000\t9000\nchr1 12000 12500\nCHR2\t0\t7000\n"
                                                    "chr3\t2500\t2600\nchr4\t0\t300\tsmall\t0\t-\nchr7\t1\t2\n")
 
@@ -119,7 +125,7 @@ def one(seed, cli, work):
         cmd = [exe, "align", "-I", os.path.join(work, "tiny.sfx"), "-i", os.path.join(work, reads[0])]
         if len(reads) > 1:
             cmd += ["-u", os.path.join(work, reads[1])]
-        cmd += [os.path.join(work, x) if i and args[i - 1] == "-B" else x if not x.startswith("-5") else "-5" + os.path.join(work, x[2:])
+        cmd += [os.path.join(work, x) if i and args[i - 1] in ("-B", "-H") else x if not x.startswith("-5") else "-5" + os.path.join(work, x[2:])
                 for i, x in enumerate(args)] + ["-o", out, "-F", "log.txt"]
         if who == "ref":
             cmd.append("-T1" if ml == 5 else "-T4")

@@ -324,6 +324,32 @@ def test_cli_priority_regions_match_reference(tag, golden_dir, tmp_path):
     test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="priority")
 
 
+CONTAM_TAGS = ["h_s3", "h_trim", "h_sam", "h_fq", "h_pe", "h_pesam", "h_x", "hv_s3", "hv_sam", "hv_pe"]
+
+
+@pytest.mark.parametrize("tag", CONTAM_TAGS)
+def test_cli_adaptor_trimming_matches_reference(tag, golden_dir, tmp_path):
+    """-H (CContaminants, Contaminants.cpp:204-431, 1227-1310; Aligner.cpp:11036-11084): adaptor tails at the read ends are
+    trimmed off at load -- every overlay code (@1, @3, @1234, reverse complements, none, PE2 only), an N in an adaptor, the
+    4-base minimum; reads carrying tails of 1..30 bases with and without a substitution; with fixed trims and a length filter,
+    FASTQ qualities, SAM, paired ends with orphan recovery, sampling, -x and -Z behind it; hv_*: vector sequences ('&'
+    codes) that reads cut out of them -- sense or antisense, 0..6 substitutions -- lie inside."""
+    import json
+    fdir = os.path.join(gu.GOLD, "contam")
+    run = json.load(open(os.path.join(fdir, "runs.json")))[tag]
+    sfx = gu.sfx_path("tiny", golden_dir)
+    files = [os.path.join(fdir, f) for f in run["reads"]]
+    args = [os.path.join(fdir, a) if i and run["args"][i - 1] == "-H" else a for i, a in enumerate(run["args"])]
+    subprocess.run([CLI, "align", "-I", sfx, "-i", files[0]] + (["-u", files[1]] if len(files) > 1 else []) + args +
+                   ["-o", run["out"], "-F", "o.log"], check=True, stdout=subprocess.DEVNULL, cwd=tmp_path)
+    ours, ref = _lines(tmp_path / run["out"]), _lines(os.path.join(fdir, run["out"] + ".gz"))
+    assert [x for x in ours if x.startswith("@")] == [x for x in ref if x.startswith("@")]
+    assert sorted(ours) == sorted(ref)
+    exp_log = [x for x in open(os.path.join(fdir, tag + ".log")).read().splitlines()
+               if not x.startswith(("Sorting alignments", "Header written", "Reported SAM", "Completed reporting SAM"))]
+    assert summary_block(tmp_path / "o.log") == exp_log
+
+
 MANY_TAGS = ["r5_R300X", "r5_R500", "r5_R100N", "r4_R200X", "r1_R500"]
 
 

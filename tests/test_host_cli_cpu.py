@@ -101,6 +101,11 @@ def test_host_priority_regions_match_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_priority_regions_match_reference(tag, golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", g.CONTAM_TAGS)
+def test_host_adaptor_trimming_matches_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_adaptor_trimming_matches_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag", g.MANY_TAGS)
 def test_host_hundreds_of_loci_per_read_match_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_hundreds_of_loci_per_read_match_reference(tag, golden_dir, tmp_path)
