@@ -954,10 +954,6 @@ static int parse(int argc0, char** argv0, Opts& o) {
   if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
   if (o.gpus < 1) o.gpus = 1;
-  if (!o.priority_file.empty() && (o.ml_mode != 0 || o.pe_mode != 0)) {
-    fprintf(stderr, "bkx-align: option -B (priority regions) is supported for single-end reads in the default multi-loci mode only\n");
-    return -1;
-  }
   if (o.priority_file.empty()) o.priority_nofilt = false;   // kanga.cpp:1071-1082: -V is only read together with -B
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
@@ -2371,7 +2367,7 @@ int main(int argc, char** argv) {
           const size_t x0 = (size_t)(std::lower_bound(R.exc_pos.begin(), R.exc_pos.end(), o_b) - R.exc_pos.begin());
           const size_t x1 = (size_t)(std::lower_bound(R.exc_pos.begin(), R.exc_pos.end(), o_e) - R.exc_pos.begin());
           const uint16_t* lens = R.fixed_len ? nullptr : R.lens.data() + b;
-          if (o.pe_mode)
+          if (o.pe_mode && o.priority_file.empty())
             rcs[(size_t)g] = bkx_align_pairs_packed2(idx[(size_t)g], &P, &PE, R.packed2.data(), o_b, lens, R.fixed_len,
                                                      R.exc_pos.data() + x0, R.exc_code.data() + x0, x1 - x0, (e - b) / 2,
                                                      res16.data() + b, &st[(size_t)g], &pst[(size_t)g],
@@ -2454,14 +2450,63 @@ int main(int argc, char** argv) {
         ++in_pri;
       }
       if (in_pri == 0 || !(o.clamp_ml || in_pri <= o.max_ml)) continue;
+      // eHRhits with LowHitInstances = the loci inside the regions (at most -R of them), the compacted list as the hit list:
+      // from here on the record is what ProcCoredApprox makes of any such search (Aligner.cpp:9328-9420)
+      const int k = std::min(in_pri, o.max_ml);
       const bkx_multi_hit& m = h[0];
       bkx_read_result r = q;
-      r.nar = BKX_NAR_ACCEPTED; r.hit_rslt = BKX_HR_HITS; r.num_hits = 1; r.low_hit_instances = 1;
-      r.chrom_id = m.chrom_id; r.match_loci = m.match_loci; r.match_len = m.match_len; r.strand = m.strand;
-      r.mismatches = m.mismatches; r.flags = 0;
-      if (res[i].nar != BKX_NAR_ACCEPTED) { ++S.tot_accepted_aligned; ++S.tot_accepted_unique; ++S.tot_loci_aligned; }
+      r.hit_rslt = BKX_HR_HITS; r.flags = 0;
+      if (k == 1 || o.ml_mode == BKX_ML_DEFAULT || o.ml_mode == BKX_ML_ALL) {
+        r.nar = BKX_NAR_ACCEPTED;
+        r.num_hits = o.ml_mode == BKX_ML_ALL ? (uint8_t)std::min(k, 255) : 1;
+        r.low_hit_instances = o.ml_mode == BKX_ML_ALL ? (int16_t)k : 1;
+        r.chrom_id = m.chrom_id; r.match_loci = m.match_loci; r.match_len = m.match_len; r.strand = m.strand;
+        r.mismatches = m.mismatches;
+      } else {   // -r1 / -r3 / -r4 with several loci: counted, not placed
+        r.nar = BKX_NAR_MULTIALIGN;
+        r.num_hits = 0; r.low_hit_instances = (int16_t)k;
+        r.chrom_id = 0; r.match_loci = 0; r.match_len = 0; r.strand = 0; r.mismatches = 0;
+      }
+      if (!multi.empty())   // -r3 / -r4 / -r5: the loci the clustering or the writers go on with
+        for (int j = 0; j < o.max_ml; ++j) {
+          bkx_multi_hit z;
+          memset(&z, 0, sizeof(z));
+          multi[(size_t)i * (size_t)o.max_ml + (size_t)j] = j < k ? h[(size_t)j] : z;
+        }
+      // the provisional totals move with the record (NumAcceptedAsAligned, NumLociAligned, unique / multi, and what counts
+      // as not aligned: no hit, or too many)
+      auto count = [&](const bkx_read_result& x, int sign) {
+        const bool placed = x.nar == BKX_NAR_ACCEPTED, counted = x.nar == BKX_NAR_MULTIALIGN && x.hit_rslt == BKX_HR_HITS;
+        if (placed || counted) {
+          const int loci = (placed && !(o.ml_mode == BKX_ML_ALL && x.low_hit_instances > 1)) ? 1 : x.low_hit_instances;
+          S.tot_accepted_aligned += (uint64_t)sign;
+          S.tot_loci_aligned += (uint64_t)(sign * loci);
+          if (loci == 1 && placed) S.tot_accepted_unique += (uint64_t)sign; else S.tot_accepted_multi += (uint64_t)sign;
+        }
+        if (x.nar == BKX_NAR_NOHIT || (x.nar == BKX_NAR_MULTIALIGN && x.hit_rslt != BKX_HR_HITS)) S.tot_non_aligned += (uint64_t)sign;
+      };
+      count(res[i], -1);
+      count(r, +1);
       res[i] = r;
     }
+  }
+  // paired ends behind -B: the reads were aligned one by one above (the priority regions decide between the two searches
+  // before ProcessPairedEnds sees a record), now they are paired -- the same kernels as the fused call, as a call of their own
+  if (o.pe_mode && !o.priority_file.empty()) {
+    std::vector<std::thread> th;
+    const uint32_t per = ((n + o.gpus - 1) / o.gpus + 1) & ~1u;
+    for (int g = 0; g < o.gpus; ++g) {
+      const uint32_t b = std::min<uint64_t>(n, (uint64_t)per * g), e = std::min<uint64_t>(n, (uint64_t)per * (g + 1));
+      th.emplace_back([&, g, b, e]() {
+        if (e <= b) return;
+        rcs[(size_t)g] = bkx_pair_reads(idx[(size_t)g], &P, &PE, res.data() + b, (e - b) / 2, R.bases.data(), R.offs.data() + b,
+                                        &pst[(size_t)g], len_dist[(size_t)g].empty() ? nullptr : len_dist[(size_t)g].data());
+        if (rcs[(size_t)g] < 0) errs[(size_t)g] = bkx_last_error();
+      });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < o.gpus; ++g)
+      if (rcs[(size_t)g] < 0) { diag("Fatal: %s", errs[(size_t)g].c_str()); return 1; }
   }
   diag("Alignment of %u from %u loaded completed", n, n);
 

@@ -698,15 +698,46 @@ def case_priority():
         open(os.path.join(tmp, "pri_csv.bed"), "w").write("lc2 , 100 , 45000\nlc3 , 60000 , 90000\n")
         for f in ("pri.bed", "pri_csv.bed"):
             shutil.copy(os.path.join(tmp, f), os.path.join(d, f))
+        # paired ends on the same genome (the pairing sees the records the priority regions decided)
+        chroms, name, seq = [], None, []
+        for ln in gzip.open(os.path.join(low, "genome.fa.gz"), "rt"):
+            if ln.startswith(">"):
+                if name:
+                    chroms.append((name, np.array(["ACGT".index(c) for c in "".join(seq).upper()], dtype=np.uint8)))
+                name, seq = ln[1:].split()[0], []
+            else:
+                seq.append(ln.strip())
+        chroms.append((name, np.array(["ACGT".index(c) for c in "".join(seq).upper()], dtype=np.uint8)))
+        n1, r1, n2, r2 = synth.sim_reads(chroms, 1200, 100, seed=77, subs=(0, 1, 2), pe=True, insert=(150, 450), junk_frac=0.03)
+        synth.write_reads_fasta(os.path.join(tmp, "lpe1.fa"), n1, r1)
+        synth.write_reads_fasta(os.path.join(tmp, "lpe2.fa"), n2, r2)
+        gz(os.path.join(tmp, "lpe1.fa"), os.path.join(d, "lpe1.fa.gz"))
+        gz(os.path.join(tmp, "lpe2.fa"), os.path.join(d, "lpe2.fa.gz"))
         meta = {}
+        for tag, args, out in (("b_pe", ["-s3", "-M0", "-U1", "-D600", "-B", "pri.bed"], "b_pe.csv"),
+                               ("bv_pe", ["-s3", "-M6", "-U2", "-D600", "-B", "pri.bed", "-V"], "bv_pe.sam"),
+                               ("b_pe3", ["-s5", "-M0", "-U3", "-d120", "-D500", "-B", "pri_csv.bed", "-Zlc1"], "b_pe3.csv"),
+                               ("bv_pe4", ["-s3", "-M0", "-U4", "-D600", "-B", "pri.bed", "-V", "-x3"], "bv_pe4.csv")):
+            run(["align", "-I", "lowcopy.sfx", "-i", "lpe1.fa", "-u", "lpe2.fa", "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": ["lpe1.fa.gz", "lpe2.fa.gz"], "index": "lowcopy", "reads_dir": "priority"}
         for tag, reads, args, out in (("b_s3", "r100.fa", ["-s3", "-M0", "-B", "pri.bed"], "b_s3.csv"),
                                       ("bv_s3", "r100.fa", ["-s3", "-M0", "-B", "pri.bed", "-V"], "bv_s3.csv"),
                                       ("bv_s5e2", "r100.fa", ["-s5", "-e2", "-M0", "-B", "pri.bed", "-V"], "bv_s5e2.csv"),
                                       ("b_csv_sam", "r100.fa", ["-s3", "-M6", "-B", "pri_csv.bed"], "b_csv_sam.sam"),
                                       ("bv_deep", "deep.fa", ["-s3", "-M0", "-B", "pri_csv.bed", "-V"], "bv_deep.csv"),
                                       ("b_z", "r100.fa", ["-s3", "-M0", "-B", "pri.bed", "-Z", "lc2"], "b_z.csv"),
-                                      ("bv_x2k", "r100.fa", ["-s4", "-M0", "-B", "pri.bed", "-V", "-x2", "-k1"], "bv_x2k.csv")):
-            run(["align", "-I", "lowcopy.sfx", "-i", reads, "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
+                                      ("bv_x2k", "r100.fa", ["-s4", "-M0", "-B", "pri.bed", "-V", "-x2", "-k1"], "bv_x2k.csv"),
+                                      # behind the multi-loci modes: up to -R loci inside the regions stand for the read
+                                      ("bv_r1", "r100.fa", ["-s3", "-M0", "-r1", "-R3", "-B", "pri.bed", "-V"], "bv_r1.csv"),
+                                      ("b_r1x", "r100.fa", ["-s5", "-M0", "-r1", "-R2", "-X", "-B", "pri.bed"], "b_r1x.csv"),
+                                      ("bv_r3", "deep.fa", ["-s3", "-M0", "-r3", "-R5", "-B", "pri.bed", "-V"], "bv_r3.csv"),
+                                      ("b_r4x", "deep.fa", ["-s3", "-M0", "-r4", "-R3", "-X", "-B", "pri_csv.bed"], "b_r4x.csv"),
+                                      ("bv_r5", "r100.fa", ["-s3", "-M0", "-r5", "-R4", "-B", "pri.bed", "-V"], "bv_r5.csv"),
+                                      ("b_r5x", "r100.fa", ["-s3", "-M0", "-r5", "-R2", "-X", "-B", "pri_csv.bed"], "b_r5x.csv"),
+                                      ("bv_r5n", "r100.fa", ["-s5", "-M0", "-r5", "-R3", "-N", "-B", "pri.bed", "-V"], "bv_r5n.csv")):
+            run(["align", "-I", "lowcopy.sfx", "-i", reads, "-T1" if "-r5" in args else "-T4", "-o", out, "-F", tag + ".log"] + args, tmp)
             gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
             strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
             meta[tag] = {"args": args, "out": out, "reads": [reads + ".gz"], "index": "lowcopy"}

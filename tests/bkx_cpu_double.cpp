@@ -84,6 +84,11 @@ int bkx_align_pairs_packed4(bkx_index* x, const bkx_align_params* p, const bkx_p
   return bko_pair_reads_filtered(x->o, p, pe, out, n_pairs, b.data(), offs, pst, len_dist,
                                  x->keep.empty() ? nullptr : x->keep.data());
 }
+int bkx_pair_reads(bkx_index* x, const bkx_align_params* p, const bkx_pe_params* pe, bkx_read_result* results, uint32_t n_pairs,
+                   const uint8_t* bases, const uint64_t* offs, bkx_pe_stats* pst, uint32_t* len_dist) {
+  return bko_pair_reads_filtered(x->o, p, pe, results, n_pairs, bases, offs, pst, len_dist,
+                                 x->keep.empty() ? nullptr : x->keep.data());
+}
 // the compact host interface: 2 bits per base + exception list in, 16-byte records out
 static void unpack2(const uint8_t* packed2, uint64_t first_base, const uint16_t* lens, uint32_t fixed_len, const uint64_t* exc_pos,
                     const uint8_t* exc_code, uint64_t n_exc, uint32_t n, std::vector<uint8_t>& b, std::vector<uint64_t>& offs) {

@@ -95,7 +95,7 @@ def draw(rng):
     if fmt != 6 and rng.random() < 0.3:
         a.append("-Ost.csv")
         side.append("st.csv")
-    if not pe and ml == 0 and rng.random() < 0.3:   # drawn last: the earlier draws of a seed stay what they were
+    if rng.random() < 0.3:   # drawn last: the earlier draws of a seed stay what they were
         a += ["-B", "pri.bed"] + (["-V"] if rng.random() < 0.5 else [])
     # adaptor trimming at load: every read loses at least a base at each end an adaptor is tried on -- not drawn for the
     # 50-base reads, which the default minimum length of 50 would then slough to the last one

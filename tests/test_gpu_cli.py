@@ -178,7 +178,7 @@ def test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, ca
     fdir = os.path.join(gu.GOLD, case)
     run = json.load(open(os.path.join(fdir, "runs.json")))[tag]
     sfx = gu.sfx_path(run.get("index", "tiny"), golden_dir)
-    files = [os.path.join(gu.GOLD, run.get("index", "tiny"), f) for f in run["reads"]]
+    files = [os.path.join(gu.GOLD, run.get("reads_dir", run.get("index", "tiny")), f) for f in run["reads"]]
     args = [a if not a.startswith("-5") else "-5" + os.path.join(fdir, a[2:]) for a in run["args"]]
     args = [os.path.join(fdir, a) if i and args[i - 1] == "-B" else a for i, a in enumerate(args)]   # -B <file of the case>
     subprocess.run([CLI, "align", "-I", sfx, "-i", files[0]] + (["-u", files[1]] if len(files) > 1 else []) + args +
@@ -312,7 +312,7 @@ def test_cli_best_matches_match_reference(tag, golden_dir, tmp_path):
         assert ours == ref
 
 
-PRIORITY_TAGS = ["b_s3", "bv_s3", "bv_s5e2", "b_csv_sam", "bv_deep", "b_z", "bv_x2k"]
+PRIORITY_TAGS = ["b_s3", "bv_s3", "bv_s5e2", "b_csv_sam", "bv_deep", "b_z", "bv_x2k", "bv_r1", "b_r1x", "bv_r3", "b_r4x", "bv_r5", "b_r5x", "bv_r5n", "b_pe", "bv_pe", "b_pe3", "bv_pe4"]
 
 
 @pytest.mark.parametrize("tag", PRIORITY_TAGS)
@@ -320,7 +320,8 @@ def test_cli_priority_regions_match_reference(tag, golden_dir, tmp_path):
     """-B / -V (Aligner.cpp:9102-9186, 4126-4186): a read whose first search -- with room for 10 more loci -- ends with exactly
     one locus inside a region of the BED file is accepted there as unique; without -V the accepted alignments outside every
     region become PR.  BED with tabs / blanks / commas, comments, a header line, upper-case and unknown chromosome names,
-    overlapping features; behind it -Z, -x, -k; -e2; -M6."""
+    overlapping features; behind it -Z, -x, -k; -e2; -M6; in front of every multi-loci mode (up to -R loci inside the regions
+    stand for the read), with -X and -N; in front of the pairing of paired-end runs (-U1..4, orphan recovery, -Z, -x)."""
     test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="priority")
 
 
