@@ -840,10 +840,33 @@ def case_contam():
         json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
 
 
+def case_empty():
+    """Runs in which no read survives the load filters (-l above every read length): the reference goes on and reports an empty
+    run -- average length 0 with a minimum of -1, one unprocessed record in the class summary, an empty record in -M6."""
+    d = os.path.join(GOLD, "empty")
+    os.makedirs(d, exist_ok=True)
+    tiny = os.path.join(GOLD, "tiny")
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("tiny.sfx", "r50.fa", "pe1.fa", "pe2.fa"):
+            with gzip.open(os.path.join(tiny, f + ".gz"), "rb") as a, open(os.path.join(tmp, f), "wb") as b:
+                shutil.copyfileobj(a, b)
+        meta = {}
+        for tag, reads, args, out in (("e_m0", ["r50.fa"], ["-s3", "-M0", "-l60"], "e_m0.csv"),
+                                      ("e_m6", ["r50.fa"], ["-s3", "-M6", "-l60"], "e_m6.sam"),
+                                      ("e_m4x", ["r50.fa"], ["-s0", "-M4", "-l60", "-x3", "-k0"], "e_m4x.bed"),
+                                      ("e_pe", ["pe1.fa", "pe2.fa"], ["-s3", "-M0", "-U1", "-l120"], "e_pe.csv"),
+                                      ("e_r5", ["r50.fa"], ["-s3", "-M0", "-l60", "-r5", "-R3"], "e_r5.csv")):
+            run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)
+            gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
+            strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))
+            meta[tag] = {"args": args, "out": out, "reads": [r + ".gz" for r in reads], "index": "tiny"}
+        json.dump(meta, open(os.path.join(d, "runs.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: oracle/build_ref.sh")
-    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches", "manyloci", "priority", "contam"]
+    which = sys.argv[1:] or ["tiny", "repeats", "formats", "lowcopy", "post", "dups", "constraints", "sample", "stats", "interplay", "pefilter", "simreads", "grammar", "bestmatches", "manyloci", "priority", "contam", "empty"]
     if "tiny" in which:
         case_tiny()
     if "repeats" in which:
@@ -879,3 +902,5 @@ if __name__ == "__main__":
         case_priority()
     if "contam" in which:
         case_contam()
+    if "empty" in which:
+        case_empty()

@@ -97,9 +97,9 @@ def draw(rng):
         side.append("st.csv")
     if rng.random() < 0.3:   # drawn last: the earlier draws of a seed stay what they were
         a += ["-B", "pri.bed"] + (["-V"] if rng.random() < 0.5 else [])
-    # adaptor trimming at load: every read loses at least a base at each end an adaptor is tried on -- not drawn for the
-    # 50-base reads, which the default minimum length of 50 would then slough to the last one
-    if rng.random() < 0.2 and reads[0] != "r50.fa":
+    # adaptor trimming at load: every read loses at least a base at each end an adaptor is tried on (the 50-base reads then
+    # all fall below the default minimum length of 50: a run without a read)
+    if rng.random() < 0.2:
         a += ["-H", "contam.fa"]
     out = "out" + {0: ".csv", 1: ".csv", 2: ".csv", 3: ".csv", 4: ".bed", 5: ".sam", 6: ".sam"}[fmt]
     return reads, a, out, side, dedup, ml

@@ -351,6 +351,13 @@ def test_cli_adaptor_trimming_matches_reference(tag, golden_dir, tmp_path):
     assert summary_block(tmp_path / "o.log") == exp_log
 
 
+@pytest.mark.parametrize("tag", ["e_m0", "e_m6", "e_m4x", "e_pe", "e_r5"])
+def test_cli_run_without_a_read_matches_reference(tag, golden_dir, tmp_path):
+    """No read survives the load filters: like the reference the front end goes on and reports an empty run (average length 0
+    with a minimum of -1, one unprocessed record in the class summary, an empty record in -M6)."""
+    test_cli_loci_base_constraints_match_reference(tag, golden_dir, tmp_path, case="empty")
+
+
 MANY_TAGS = ["r5_R300X", "r5_R500", "r5_R100N", "r4_R200X", "r1_R500"]
 
 

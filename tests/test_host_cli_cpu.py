@@ -106,6 +106,11 @@ def test_host_adaptor_trimming_matches_reference(tag, cli, golden_dir, tmp_path)
     g.test_cli_adaptor_trimming_matches_reference(tag, golden_dir, tmp_path)
 
 
+@pytest.mark.parametrize("tag", ["e_m0", "e_m6", "e_m4x", "e_pe", "e_r5"])
+def test_host_run_without_a_read_matches_reference(tag, cli, golden_dir, tmp_path):
+    g.test_cli_run_without_a_read_matches_reference(tag, golden_dir, tmp_path)
+
+
 @pytest.mark.parametrize("tag", g.MANY_TAGS)
 def test_host_hundreds_of_loci_per_read_match_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_hundreds_of_loci_per_read_match_reference(tag, golden_dir, tmp_path)
