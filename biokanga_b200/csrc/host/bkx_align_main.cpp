@@ -2611,7 +2611,8 @@ int main(int argc, char** argv) {
     diag("Sorting...");
     diag("Sorting completed, now clustering...");
     diag("Assigning...");
-    if (bkx_assign_multi_matches(res.data(), n, multi.data(), o.max_ml, o.ml_mode, longest, &cs) < 0) {
+    memset(&cs, 0, sizeof(cs));
+    if (n && bkx_assign_multi_matches(res.data(), n, multi.data(), o.max_ml, o.ml_mode, longest, &cs) < 0) {
       diag("Fatal: %s", bkx_last_error());
       return 1;
     }

@@ -855,7 +855,9 @@ def case_empty():
                                       ("e_m6", ["r50.fa"], ["-s3", "-M6", "-l60"], "e_m6.sam"),
                                       ("e_m4x", ["r50.fa"], ["-s0", "-M4", "-l60", "-x3", "-k0"], "e_m4x.bed"),
                                       ("e_pe", ["pe1.fa", "pe2.fa"], ["-s3", "-M0", "-U1", "-l120"], "e_pe.csv"),
-                                      ("e_r5", ["r50.fa"], ["-s3", "-M0", "-l60", "-r5", "-R3"], "e_r5.csv")):
+                                      ("e_r5", ["r50.fa"], ["-s3", "-M0", "-l60", "-r5", "-R3"], "e_r5.csv"),
+                                      ("e_r4", ["r50.fa"], ["-s5", "-M6", "-l60", "-r4", "-R8", "-x7"], "e_r4.sam"),
+                                      ("e_r1", ["r50.fa"], ["-s3", "-M0", "-l60", "-r1", "-R3", "-k0"], "e_r1.csv")):
             run(["align", "-I", "tiny.sfx", "-i", reads[0], "-T4", "-o", out, "-F", tag + ".log"] + (["-u", reads[1]] if len(reads) > 1 else []) + args, tmp)
             gz(os.path.join(tmp, out), os.path.join(d, out + ".gz"))
             strip_log(os.path.join(tmp, tag + ".log"), os.path.join(d, tag + ".log"))

@@ -351,7 +351,7 @@ def test_cli_adaptor_trimming_matches_reference(tag, golden_dir, tmp_path):
     assert summary_block(tmp_path / "o.log") == exp_log
 
 
-@pytest.mark.parametrize("tag", ["e_m0", "e_m6", "e_m4x", "e_pe", "e_r5"])
+@pytest.mark.parametrize("tag", ["e_m0", "e_m6", "e_m4x", "e_pe", "e_r5", "e_r4", "e_r1"])
 def test_cli_run_without_a_read_matches_reference(tag, golden_dir, tmp_path):
     """No read survives the load filters: like the reference the front end goes on and reports an empty run (average length 0
     with a minimum of -1, one unprocessed record in the class summary, an empty record in -M6)."""

@@ -106,7 +106,7 @@ def test_host_adaptor_trimming_matches_reference(tag, cli, golden_dir, tmp_path)
     g.test_cli_adaptor_trimming_matches_reference(tag, golden_dir, tmp_path)
 
 
-@pytest.mark.parametrize("tag", ["e_m0", "e_m6", "e_m4x", "e_pe", "e_r5"])
+@pytest.mark.parametrize("tag", ["e_m0", "e_m6", "e_m4x", "e_pe", "e_r5", "e_r4", "e_r1"])
 def test_host_run_without_a_read_matches_reference(tag, cli, golden_dir, tmp_path):
     g.test_cli_run_without_a_read_matches_reference(tag, golden_dir, tmp_path)
 
