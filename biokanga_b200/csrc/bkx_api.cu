@@ -1004,7 +1004,7 @@ static int launch_both(bkx_index* x, const KParams& k, const uint8_t* d_bases, c
     CU(launch_wave(x->d, k, d_offs, n, max_len, p2, x->slot[si].wave, d_out, d_stats, sms, st));
     fast_ids = x->slot[si].wave.fb_ids;
     fast_n = x->slot[si].wave.cnt + kWaveCntFallback;
-    x->launches += (uint64_t)wave_launches(k, max_len);
+    x->launches += (uint64_t)wave_launches(k, max_len, x->slot[si].wave.sa_split != 0);
     if (trace) { cudaEventCreate(&tw); cudaEventRecord(tw, st); }
   }
   CU(launch_align_fast(x->d, kf, d_bases, d_offs, n, x->fast_W, d_out, d_stats, cur, d_hard, cur + 2, x->fast_hash[si], epoch_base,

@@ -1595,7 +1595,9 @@ static int wave_rounds(const KParams& P, uint32_t max_len) {
   // one; whatever is still on the path after the last round is handed on by the closing step
   return std::min(mt + 1, kWaveMaxRounds - 1);
 }
-int wave_launches(const KParams& P, uint32_t max_len) { return 1 + 3 * wave_rounds(P, max_len); }
+// kernels one launch_wave starts: a step and a probe kernel per round (and the suffix-array gather when that is split off),
+// and the closing step
+int wave_launches(const KParams& P, uint32_t max_len, bool sa_split) { return 1 + (sa_split ? 3 : 2) * wave_rounds(P, max_len); }
 
 cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* offs, uint32_t n_reads, uint32_t max_len,
                         const Packed2Src& p2, const WaveBuf& B, bkx_read_result* out, bkx_align_stats* stats, int sms,

@@ -39,7 +39,7 @@ cudaError_t launch_align_fast(const DevIndex& I, const KParams& P, const uint8_t
                               uint32_t epoch_base, int grid, cudaStream_t st, const Packed2Src& p2,
                               const uint32_t* ids = nullptr, const unsigned int* n_ids = nullptr);
 struct WaveBuf;
-int wave_launches(const KParams& P, uint32_t max_len);   // kernels one launch_wave starts
+int wave_launches(const KParams& P, uint32_t max_len, bool sa_split);   // kernels one launch_wave starts
 // the wave path (bkx_wave.cuh): results for the reads it finishes, B.fb_ids / B.cnt[kWaveCntFallback] for the others
 cudaError_t launch_wave(const DevIndex& I, const KParams& P, const uint64_t* offs, uint32_t n_reads, uint32_t max_len,
                         const Packed2Src& p2, const WaveBuf& B, bkx_read_result* out, bkx_align_stats* stats, int sms,
