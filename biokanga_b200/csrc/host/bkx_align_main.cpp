@@ -829,6 +829,7 @@ static int parse(int argc0, char** argv0, Opts& o) {
   int i = 1;
   if (i < argc && (args[i] == "align" || args[i] == "kanga")) ++i;
   std::vector<std::string> unsupported;
+  bool pe_insert_dist = false;   // -3 (experimental in the reference): per-transcript insert lengths beside the -O file of a paired-end run
   for (; i < argc; ++i) {
     std::string a = args[i];
     if (a == "--gpus" && i + 1 < argc) { o.gpus = atoi(args[++i].c_str()); continue; }
@@ -915,6 +916,7 @@ static int parse(int argc0, char** argv0, Opts& o) {
       case 'B': o.priority_file = v; break;
       case 'V': o.priority_nofilt = true; break;
       case 'H': o.contam_file = v; break;
+      case '3': pe_insert_dist = true; break;
       case 'S': case '7': case '8':
         unsupported.push_back(std::string("-") + c + " (outside the accelerated path)"); break;
       case 'v':
@@ -925,7 +927,7 @@ static int parse(int argc0, char** argv0, Opts& o) {
                "-y -Y -l -L -# -H -5 -k -6 -x -Z -z -B -V -j -J -O -4 -T -i -u -I -o -F -q -w -W [--gpus N], the reference's long option names, "
                "and @file parameter files\n");
         return 1;
-      default: break;  // remaining reference options have no effect on this path (-K -G -P -1 -9 -0 -3)
+      default: break;  // remaining reference options have no effect on this path (-K -G -P -1 -9 -0: parameters of -p, -8 and -c, which are refused)
     }
    }
   }
@@ -954,6 +956,10 @@ static int parse(int argc0, char** argv0, Opts& o) {
   if (!o.stats_file.empty() && o.fmt == 6) { fprintf(stderr, "Error: Output induced substitution mode '-O<file>' not available in '-M6' output mode\n"); return -1; }  // kanga.cpp:1015-1021
   if (o.excl.size() > 20 || o.incl.size() > 20) { fprintf(stderr, "Error: at most 20 '-Z' and 20 '-z' chromosome expressions\n"); return -1; }
   if (o.gpus < 1) o.gpus = 1;
+  if (pe_insert_dist && o.pe_mode && !o.stats_file.empty()) {   // Aligner.cpp:175-185, 5340-5470: <stats file>.peinserts.csv
+    fprintf(stderr, "bkx-align: option -3 (paired-end insert lengths per target sequence, experimental in the reference) is not supported by the accelerated path\n");
+    return -1;
+  }
   if (o.priority_file.empty()) o.priority_nofilt = false;   // kanga.cpp:1071-1082: -V is only read together with -B
   if (o.ml_mode != 0) {  // kanga.cpp:535-537, 667-696
     if (o.pe_mode) { fprintf(stderr, "Error: Sorry, currently multiloci processing '-r%d' not supported in paired end '-U%d' processing\n", o.ml_mode, o.pe_mode); return -1; }
